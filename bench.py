@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Genome-on-Diet hot path on B200 (see BASELINE.json).
+
+Workload (config 2 of BASELINE.json, the one the metric is quoted on): batched ksw_extd2 over 1M
+synthetic 150x200 bp query/target pairs, band 150, sr scoring, Z-drop on (flag 0: exact max + Z-drop),
+CIGARs produced.  A "step" is one pass of the hot path (pack -> DP -> traceback) over the whole batch.
+
+  value      GCUPS with the inputs already resident in HBM (CUDA events on the library's stream)
+  e2e        GCUPS through the host-buffer C-ABI call gd_ksw_extd2_batch (pinned host buffers; H2D,
+             kernels, D2H of ksw_extz_t records and CIGARs inside the timed region)
+  roofline   integer-ALU roofline of the DP kernel (51 lane-ops per banded cell against the
+             IADD rate measured live by gd_ubench), plus the backtrack HBM traffic against MEASURED_PEAKS
+  cpu_baseline  the unmodified reference (oracle/_ref, ksw_extd2_avx512 when the host has AVX-512) on all
+             host threads over a bounded sample of the same pairs
+
+`--impl reference` times only that CPU reference arm.  With torchrun (N>1) every rank maps its own
+1M-pair shard (weak scaling, no data-path collective); time is the max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+QLEN, TLEN, BAND = 150, 200, 150
+OPS_PER_CELL = 51          # SSE4.1 lane-ops per cell with backtrack
+BYTES_PER_CELL = 1.0       # backtrack byte
+
+
+def band_prefix(qlen, tlen, w):
+    """cells executed after r rows, for r = 0..qlen+tlen-1 (SURVEY.md 8d definition of a banded cell)"""
+    pre = [0]
+    for r in range(qlen + tlen - 1):
+        st0 = max(0, r - qlen + 1, (r - w + 1) >> 1)
+        en0 = min(tlen - 1, r, (r + w) >> 1)
+        pre.append(pre[-1] + max(0, en0 - st0 + 1))
+    return np.array(pre, np.int64)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_pairs(n, seed):
+    import gdiet_b200  # noqa: F401
+    from gdiet_b200 import synth
+    return synth.ksw_pairs_fast(n, QLEN, TLEN, 0.05, seed=seed)
+
+
+def reference_arm(args, rank, world):
+    """CPU: the unmodified reference (oracle/_ref) on all host threads; bounded sample per step."""
+    if rank != 0:
+        return
+    from oraclelib import Ref, cpu_has_avx512
+    import gdiet_b200  # noqa: F401
+    from gdiet_b200 import synth
+    variant = "avx" if cpu_has_avx512() else "scalar"
+    R = Ref(variant)
+    cores = host_threads()
+    sc = synth.SCORING["sr"]
+    mat = synth.score_matrix(sc["a"], sc["b"])
+    pre = band_prefix(QLEN, TLEN, BAND)
+    # calibrate the sample so one step is ~3 s of wall time on this host
+    probe = make_pairs(4096, seed=3)
+    t0 = time.perf_counter()
+    R.ksw_extd2_batch(probe["qlen"], probe["qoff"], probe["qbuf"], probe["tlen"], probe["toff"], probe["tbuf"], mat, sc["q"], sc["e"],
+                      sc["q2"], sc["e2"], BAND, sc["zdrop"], sc["end_bonus"], args.flag, cores, cigar_stride=QLEN + TLEN)
+    dt = time.perf_counter() - t0
+    n = int(min(args.pairs, max(4096, 4096 * 3.0 / max(dt, 1e-3))))
+    P = make_pairs(n, seed=3)
+    times, cells = [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ez, _ = R.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], mat, sc["q"], sc["e"], sc["q2"],
+                                  sc["e2"], BAND, sc["zdrop"], sc["end_bonus"], args.flag, cores, cigar_stride=QLEN + TLEN)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    # rows executed: the reference does not report them; without Z-drop every pair runs all rows, with
+    # Z-drop we count full rows for pairs that did not drop and use the oracle-free bound for the rest
+    cells = int(n * pre[-1])
+    tot = sum(times)
+    value = cells * len(times) / tot / 1e9
+    line = {"impl": "reference", "metric": "ksw_extd2 GCUPS", "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": workload_config(args, n),
+            "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                             "sample": "%d of the %d pairs per step, ksw_extd2_%s, flag %#x, cells counted as full band" % (
+                                 n, args.pairs, "avx512" if variant == "avx" else "sse", args.flag)},
+            "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {"workload": "BASELINE config 2: batched ksw_extd2 microbench, %d synthetic %dx%d bp pairs per GPU, band %d, sr scoring "
+                        "(a2 b8 q12 e2 q2 24 e2 1 zdrop100 end_bonus10), flag %#x (%s), 5%% edits, N every 50th query, CIGAR on" % (
+                            n, QLEN, TLEN, BAND, args.flag, "exact max + Z-drop" if not (args.flag & 8) else "approx max"),
+            "pairs_per_gpu": n, "qlen": QLEN, "tlen": TLEN, "band": BAND, "flag": args.flag,
+            "cache": "inputs + backtrack arena per step >> 126 MB L2 (no flush needed)"}
+
+
+def run_ubench():
+    """integer pipe rates measured live on this GPU (gd_ubench); returns {op: lane_ops_per_clk_per_sm}"""
+    exe = os.path.join(ROOT, "genome-on-diet_b200", "lib", "gd_ubench")
+    out = {}
+    try:
+        txt = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+        for ln in txt.splitlines():
+            d = json.loads(ln)
+            if "op" in d:
+                out[d["op"]] = max(out.get(d["op"], 0.0), d["lane_ops_per_clk_per_sm"])
+    except Exception:
+        pass
+    return out
+
+
+def ours(args, rank, world, local_rank):
+    import torch
+    import gdiet_b200 as gd
+    from gdiet_b200 import synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = gd.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    n = args.pairs
+    sc = synth.SCORING["sr"]
+    prm = gd.KswParams(synth.score_matrix(sc["a"], sc["b"]), sc["q"], sc["e"], sc["q2"], sc["e2"], sc["zdrop"], sc["end_bonus"], args.flag)
+    P = make_pairs(n, seed=3 + rank)  # every rank maps its own shard
+    pre = band_prefix(QLEN, TLEN, BAND)
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    dev = torch.device("cuda", local_rank)
+    d = {k: torch.from_numpy(P[k]).to(dev) for k in ("qlen", "qoff", "qbuf", "tlen", "toff", "tbuf")}
+    stride = QLEN + TLEN
+    d_ez = torch.zeros(n * 16, dtype=torch.int32, device=dev)
+    d_cig = torch.zeros(n * stride, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        ctx.ksw_extd2_batch_device(n, d["qlen"], d["qoff"], d["qbuf"], d["tlen"], d["toff"], d["tbuf"], prm, QLEN, TLEN, BAND, d_ez,
+                                   d_cig, stride, w_all=BAND)
+
+    for _ in range(args.warmup):
+        step_device()
+    stream.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.stat("kernel_launches")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    e1.synchronize()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.stat("kernel_launches") - l0
+    ez = d_ez.cpu().numpy().view(gd.GD_EXTZ_DTYPE)
+    cells_step = int(pre[np.clip(ez["rows_done"], 0, len(pre) - 1)].sum())
+
+    # ---- per-kernel time of the DP kernel (for the roofline): time the DP kernel alone via score-only
+    # vs full? No: time the same step with CUDA events around each launch is not exposed by the ABI, so
+    # the DP kernel share is taken from the committed ncu launch list (profiles/) and the live figure is
+    # the whole step; the DP kernel is > 90 % of it (see profiles/).
+
+    # ---- end-to-end arm: host buffers through the C ABI ------------------------------------------
+    hp = {k: torch.from_numpy(P[k]).pin_memory() for k in ("qlen", "qoff", "qbuf", "tlen", "toff", "tbuf")}
+    out = {"ez": torch.zeros(n * 16, dtype=torch.int32).pin_memory().numpy().view(gd.GD_EXTZ_DTYPE),
+           "cigar_off": torch.zeros(n + 1, dtype=torch.int64).pin_memory().numpy(),
+           "cigar": torch.zeros(n * 24, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+
+    def step_e2e():
+        return ctx.ksw_extd2_batch(hp["qlen"].numpy(), hp["qoff"].numpy(), hp["qbuf"].numpy(), hp["tlen"].numpy(), hp["toff"].numpy(),
+                                   hp["tbuf"].numpy(), prm, w_all=BAND, out=out)
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ez_h, coff_h, _ = step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    h2d = int(sum(P[k].nbytes for k in ("qlen", "qoff", "qbuf", "tlen", "toff", "tbuf")))
+    d2h = int(n * 64 + (n + 1) * 8 + int(coff_h[n]) * 4)
+    assert np.array_equal(ez_h["score"], ez["score"]), "device-resident and host-buffer arms disagree"
+
+    # ---- max over ranks ------------------------------------------------------------------------
+    tot_cells = cells_step
+    if dist:
+        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        c = torch.tensor([cells_step, launches, h2d, d2h], dtype=torch.int64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        tot_cells, launches, h2d, d2h = (int(x) for x in c)
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    ms_per_step = dev_ms / args.steps
+    value = tot_cells / (ms_per_step * 1e-3) / 1e9
+    e2e_val = tot_cells / (e2e_ms / args.steps * 1e-3) / 1e9
+
+    # ---- roofline ---------------------------------------------------------------------------------
+    peaks = measured_peaks()
+    ub = run_ubench()
+    clk = sampler.summary()
+    sms = ctx.stat("device_sms")
+    iadd = ub.get("IADD")
+    f_hz = (clk["sm_mhz"] or (peaks or {}).get("sm_max_mhz") or 1965.0) * 1e6
+    per_gpu_cells_s = value * 1e9 / world
+    roof = {"bound": "int_alu", "unit": "Tlaneop/s", "achieved": per_gpu_cells_s * OPS_PER_CELL / 1e12,
+            "peak": (iadd * sms * f_hz / 1e12) if iadd else None,
+            "peak_source": "gd_ubench IADD lane-ops/clk/SM measured live x %d SMs x median SM clock under load" % sms if iadd else "unmeasured",
+            "ops_per_cell": OPS_PER_CELL, "traffic": None,
+            "hbm": {"achieved_gbs": per_gpu_cells_s * BYTES_PER_CELL / 1e9, "peak_gbs": (peaks or {}).get("hbm_gbs", 6650.0),
+                    "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s"},
+            "ubench": ub}
+    roof["frac"] = (roof["achieved"] / roof["peak"]) if roof["peak"] else None
+    roof["hbm"]["frac"] = roof["hbm"]["achieved_gbs"] / roof["hbm"]["peak_gbs"]
+
+    # ---- CPU baseline (bounded sample, rank 0, N=1 only) ------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_baseline_sample(args, P)
+        except Exception as e:  # the checker being absent must not hide the GPU number
+            cpu = {"value": None, "unit": "GCUPS", "cores": host_threads(), "kind": "unavailable", "sample": str(e)}
+
+    line = {"metric": "ksw_extd2 GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+            "data": "synthetic", "config": workload_config(args, n),
+            "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "extra": {"ksw_group_lanes": ctx.stat("ksw_group"), "ksw_ring_columns": ctx.stat("ksw_ring"), "chunks_per_step": ctx.stat("ksw_chunks"),
+                      "zdropped_frac": float((ez["zdropped"] != 0).mean()), "cells_per_step": tot_cells}}
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample(args, P):
+    from oraclelib import Ref, cpu_has_avx512
+    import gdiet_b200  # noqa: F401
+    from gdiet_b200 import synth
+    variant = "avx" if cpu_has_avx512() else "scalar"
+    R = Ref(variant)
+    cores = host_threads()
+    sc = synth.SCORING["sr"]
+    mat = synth.score_matrix(sc["a"], sc["b"])
+    pre = band_prefix(QLEN, TLEN, BAND)
+
+    def run(n):
+        t0 = time.perf_counter()
+        R.ksw_extd2_batch(P["qlen"][:n], P["qoff"][:n], P["qbuf"], P["tlen"][:n], P["toff"][:n], P["tbuf"], mat, sc["q"], sc["e"], sc["q2"],
+                          sc["e2"], BAND, sc["zdrop"], sc["end_bonus"], args.flag, cores, cigar_stride=QLEN + TLEN)
+        return time.perf_counter() - t0
+
+    dt = run(4096)
+    n = int(min(len(P["qlen"]), max(4096, 4096 * 12.0 / max(dt, 1e-3))))
+    dt = run(n)
+    return {"value": n * int(pre[-1]) / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
+            "sample": "first %d pairs of the step, ksw_extd2_%s via oracle/_ref on %d threads, %.1f s" % (
+                n, "avx512" if variant == "avx" else "sse", cores, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1_000_000)
+    ap.add_argument("--flag", type=lambda s: int(s, 0), default=0x00)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,355 @@
+"""genome-on-diet_b200 -- host-side Python mirror of the C ABI in include/gdiet_cuda.h.
+
+The product is libgdiet_cuda.so (hand-written sm_100a CUDA behind a C ABI that keeps the reference's
+``ksw_extd2_sse()/ksw_extz_t`` and ``mm_sketch*()/mm128_v`` signatures). This module only binds it with
+ctypes so that tests and bench.py can call exactly what a C host program would call. There is no
+CPU fallback anywhere: if the shared library is missing or no sm_100 GPU is usable, every entry
+point raises.
+
+Import it as ``import gdiet_b200`` (repo-root shim; the directory name contains a hyphen).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libgdiet_cuda.so")
+CSRC_DIR = os.path.join(PKG_DIR, "csrc")
+
+# KSW_EZ_* (GDiet-ShortReads/ksw2.h:9-18)
+KSW_EZ_SCORE_ONLY = 0x01
+KSW_EZ_RIGHT = 0x02
+KSW_EZ_GENERIC_SC = 0x04
+KSW_EZ_APPROX_MAX = 0x08
+KSW_EZ_APPROX_DROP = 0x10
+KSW_EZ_EXTZ_ONLY = 0x40
+KSW_EZ_REV_CIGAR = 0x80
+KSW_NEG_INF = -0x40000000
+
+GD_OK, GD_ERR_NO_DEVICE, GD_ERR_CUDA, GD_ERR_ARG, GD_ERR_CAPACITY = 0, 1, 2, 3, 4
+
+EXTZ_FIELDS = ["max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end"]
+GD_EXTZ_DTYPE = np.dtype([(f, np.int32) for f in EXTZ_FIELDS + ["tb_i", "tb_j", "rows_done", "r0", "r1"]])
+MM128_DTYPE = np.dtype([("x", np.uint64), ("y", np.uint64)])
+
+
+class GdietError(RuntimeError):
+    pass
+
+
+class ksw_extz_t(C.Structure):
+    """GDiet-ShortReads/ksw2.h:31-40"""
+    _fields_ = [("max_zdropped", C.c_uint32), ("max_q", C.c_int), ("max_t", C.c_int), ("mqe", C.c_int),
+                ("mqe_t", C.c_int), ("mte", C.c_int), ("mte_q", C.c_int), ("score", C.c_int), ("m_cigar", C.c_int),
+                ("n_cigar", C.c_int), ("reach_end", C.c_int), ("cigar", C.POINTER(C.c_uint32))]
+
+
+class mm128_v(C.Structure):
+    """GDiet-ShortReads/minimap.h:72-76"""
+    _fields_ = [("n", C.c_size_t), ("m", C.c_size_t), ("a", C.c_void_p)]
+
+
+class mm_pattern_t(C.Structure):
+    """GDiet-ShortReads/minimap.h:99-102"""
+    _fields_ = [("n", C.c_uint32), ("shift_seeds_number", C.POINTER(C.c_uint32))]
+
+
+class gd_ksw_params_t(C.Structure):
+    _fields_ = [("m", C.c_int32), ("mat", C.c_void_p), ("q", C.c_int32), ("e", C.c_int32), ("q2", C.c_int32),
+                ("e2", C.c_int32), ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("flag", C.c_int32)]
+
+
+def build(verbose=False):
+    """Compile libgdiet_cuda.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC_DIR, "-j4"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise GdietError("building libgdiet_cuda.so failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+# every symbol include/gdiet_cuda.h declares
+EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat", "gd_stream", "ksw_extd2_sse",
+           "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
+           "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
+           "gd_sketch_reads_batch"]
+
+
+def load():
+    """dlopen the product library (RTLD_LOCAL). Raises if it was not built: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GdietError("libgdiet_cuda.so not found at %s -- run __graft_entry__.build() / make -C %s" % (LIB_PATH, CSRC_DIR))
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.gd_init.restype = i32
+    L.gd_init.argtypes = [i32, C.POINTER(vp)]
+    L.gd_destroy.restype = None
+    L.gd_destroy.argtypes = [vp]
+    L.gd_strerror.restype = C.c_char_p
+    L.gd_strerror.argtypes = [vp]
+    L.gd_set_option.restype = i32
+    L.gd_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.gd_get_stat.restype = C.c_long
+    L.gd_get_stat.argtypes = [vp, C.c_char_p]
+    L.gd_stream.restype = vp
+    L.gd_stream.argtypes = [vp]
+    ksw_args = [vp, i32, vp, i32, vp, C.c_int8, vp, C.c_int8, C.c_int8, C.c_int8, C.c_int8, i32, i32, i32, i32,
+                C.POINTER(ksw_extz_t)]
+    for name in ("ksw_extd2_sse", "ksw_extd2_avx512"):
+        getattr(L, name).restype = None
+        getattr(L, name).argtypes = ksw_args
+    L.gd_ksw_extd2_batch.restype = i32
+    L.gd_ksw_extd2_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, C.POINTER(gd_ksw_params_t), vp, vp, vp, i64]
+    L.gd_ksw_extd2_batch_device.restype = i32
+    L.gd_ksw_extd2_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32,
+                                            C.POINTER(gd_ksw_params_t), vp, vp, i32]
+    L.gd_exact_match_batch_device.restype = i32
+    L.gd_exact_match_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    L.mm_sketch.restype = None
+    L.mm_sketch.argtypes = [vp, C.c_char_p, i32, i32, i32, C.c_uint32, i32, C.POINTER(mm128_v), C.c_char_p, i32]
+    L.mm_sketch2.restype = mm_pattern_t
+    L.mm_sketch2.argtypes = [vp, C.c_char_p, i32, i32, i32, C.c_uint32, i32, C.POINTER(mm128_v), C.c_char_p, i32, C.c_float]
+    L.mm_sketch3.restype = C.c_uint
+    L.mm_sketch3.argtypes = [vp, C.c_char_p, C.c_uint, i32, i32, C.c_uint32, i32, C.POINTER(mm128_v), C.c_char_p, i32, i32,
+                             C.c_uint32]
+    L.gd_sketch_ref_batch.restype = i32
+    L.gd_sketch_ref_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, C.c_char_p, i32, vp, vp, i64]
+    L.gd_sketch_ref_batch_device.restype = i32
+    L.gd_sketch_ref_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, i64, i32, i32, C.c_char_p, i32, vp, vp, i64]
+    L.gd_sketch_reads_batch.restype = i32
+    L.gd_sketch_reads_batch.argtypes = [vp, i32, vp, vp, vp, i32, i32, C.c_char_p, i32, C.c_float, C.c_uint32, vp, vp, vp,
+                                        i64, vp, vp, vp, i64]
+    _lib = L
+    return L
+
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):  # torch tensor (device or host)
+        return C.c_void_p(a.data_ptr())
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def score_matrix(a, b):
+    """5x5 matrix as the live call site builds it (GDiet-ShortReads/map.c:861-865)."""
+    bb = -abs(int(b))
+    m = np.full((5, 5), bb, np.int8)
+    np.fill_diagonal(m, a)
+    m[4, :] = 0
+    m[:, 4] = 0
+    return np.ascontiguousarray(m.reshape(-1))
+
+
+class KswParams:
+    """Batch-uniform arguments of ksw_extd2_sse (GDiet-ShortReads/ksw2.h:42-59)."""
+
+    def __init__(self, mat, q, e, q2, e2, zdrop, end_bonus, flag, m=None):
+        self.mat = np.ascontiguousarray(mat, np.int8)
+        self.m = int(m if m is not None else round(len(self.mat) ** 0.5))
+        self.c = gd_ksw_params_t(self.m, self.mat.ctypes.data, int(q), int(e), int(q2), int(e2), int(zdrop),
+                                 int(end_bonus), int(flag))
+        self.flag = int(flag)
+
+
+class Context:
+    """gd_ctx: one CUDA stream + staging memory. Raises GdietError when no sm_100 GPU is usable."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.gd_init(device, C.byref(h))
+        if rc != GD_OK:
+            raise GdietError("gd_init failed (%d): %s" % (rc, self.lib.gd_strerror(None).decode()))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != GD_OK:
+            raise GdietError("%s failed (%d): %s" % (what, rc, self.lib.gd_strerror(self.h).decode()))
+
+    def set_option(self, key, value):
+        self._check(self.lib.gd_set_option(self.h, key.encode(), int(value)), "gd_set_option")
+
+    def stat(self, key):
+        return int(self.lib.gd_get_stat(self.h, key.encode()))
+
+    @property
+    def stream(self):
+        return int(self.lib.gd_stream(self.h) or 0)
+
+    # ---- DP ----
+    def ksw_extd2_batch(self, qlen, qoff, qbuf, tlen, toff, tbuf, params, w=None, w_all=-1, want_cigar=True,
+                        out=None):
+        """gd_ksw_extd2_batch over host arrays (numpy, or pinned torch tensors). Returns (ez, cigar_off, cigar)."""
+        n = len(qlen)
+        ez = np.zeros(n, GD_EXTZ_DTYPE) if out is None else out["ez"]
+        coff = np.zeros(n + 1, np.int64) if out is None else out["cigar_off"]
+        if want_cigar:
+            if out is None:
+                cap = int(n) * 64 + 1024
+                cig = np.zeros(cap, np.uint32)
+            else:
+                cig = out["cigar"]
+                cap = len(cig)
+        else:
+            cig, cap = None, 0
+        while True:
+            rc = self.lib.gd_ksw_extd2_batch(self.h, n, _ptr(qlen), _ptr(qoff), _ptr(qbuf), _ptr(tlen), _ptr(toff),
+                                             _ptr(tbuf), _ptr(w), int(w_all), C.byref(params.c), _ptr(ez),
+                                             _ptr(coff), _ptr(cig), cap)
+            if rc == GD_ERR_CAPACITY and want_cigar and out is None and int(coff[n]) > cap:
+                cap = int(coff[n]) + 16
+                cig = np.zeros(cap, np.uint32)
+                continue
+            self._check(rc, "gd_ksw_extd2_batch")
+            break
+        return ez, coff, (cig[: int(coff[n])] if cig is not None and out is None else cig)
+
+    def ksw_extd2_batch_device(self, n, d_qlen, d_qoff, d_qbuf, d_tlen, d_toff, d_tbuf, params, max_qlen, max_tlen,
+                               max_w, d_ez, d_cigar=None, cigar_stride=0, d_w=None, w_all=-1):
+        """gd_ksw_extd2_batch_device: all arrays are device pointers / torch CUDA tensors; enqueues only."""
+        rc = self.lib.gd_ksw_extd2_batch_device(self.h, n, _ptr(d_qlen), _ptr(d_qoff), _ptr(d_qbuf), _ptr(d_tlen),
+                                                _ptr(d_toff), _ptr(d_tbuf), _ptr(d_w), int(w_all), int(max_qlen),
+                                                int(max_tlen), int(max_w), C.byref(params.c), _ptr(d_ez),
+                                                _ptr(d_cigar), int(cigar_stride))
+        self._check(rc, "gd_ksw_extd2_batch_device")
+
+    def exact_match_batch_device(self, n, d_qlen, d_qoff, d_qbuf, d_toff, d_tbuf, d_equal):
+        self._check(self.lib.gd_exact_match_batch_device(self.h, n, _ptr(d_qlen), _ptr(d_qoff), _ptr(d_qbuf),
+                                                         _ptr(d_toff), _ptr(d_tbuf), _ptr(d_equal)),
+                    "gd_exact_match_batch_device")
+
+    # ---- sketching ----
+    def sketch_ref_batch(self, off, lens, buf, w, k, Z, rid=None, out_cap=None):
+        """gd_sketch_ref_batch: mm_sketch of n sequences. Returns (out_off[n+1], mm128 array)."""
+        n = len(lens)
+        Zb = Z.encode() if isinstance(Z, str) else Z
+        out_off = np.zeros(n + 1, np.int64)
+        if out_cap is None:
+            out_cap = int(np.sum(lens)) // max(1, len(Zb)) * Zb.count(b"1") // max(1, w // 2) + 4096
+        while True:
+            out = np.zeros(out_cap, MM128_DTYPE)
+            rc = self.lib.gd_sketch_ref_batch(self.h, n, _ptr(off), _ptr(lens), _ptr(rid), _ptr(buf), w, k, Zb, len(Zb),
+                                              _ptr(out_off), _ptr(out), out_cap)
+            if rc == GD_ERR_CAPACITY and int(out_off[n]) > out_cap:
+                out_cap = int(out_off[n]) + 16
+                continue
+            self._check(rc, "gd_sketch_ref_batch")
+            return out_off, out[: int(out_off[n])]
+
+    def sketch_ref_batch_device(self, n, d_off, d_len, d_rid, d_buf, total_len, w, k, Z, d_out_off, d_out, out_cap):
+        Zb = Z.encode() if isinstance(Z, str) else Z
+        self._check(self.lib.gd_sketch_ref_batch_device(self.h, n, _ptr(d_off), _ptr(d_len), _ptr(d_rid), _ptr(d_buf),
+                                                        int(total_len), w, k, Zb, len(Zb), _ptr(d_out_off), _ptr(d_out),
+                                                        int(out_cap)), "gd_sketch_ref_batch_device")
+
+    def sketch_reads_batch(self, off, lens, buf, w, k, Z, max_seeds, max_nb_seeds):
+        """gd_sketch_reads_batch. Returns dict(s2_counts[n,W], s2_off[n+1], s2, s3_off[n*W+1], s3_ret[n,W], s3)."""
+        n = len(lens)
+        Zb = Z.encode() if isinstance(Z, str) else Z
+        W = len(Zb)
+        s2_counts = np.zeros((n, W), np.uint32)
+        s3_ret = np.zeros((n, W), np.uint32)
+        s2_off = np.zeros(n + 1, np.int64)
+        s3_off = np.zeros(n * W + 1, np.int64)
+        cap = int(np.sum(lens)) // max(1, w // 2) * W + 4096 * W
+        while True:
+            s2 = np.zeros(cap, MM128_DTYPE)
+            s3 = np.zeros(cap, MM128_DTYPE)
+            rc = self.lib.gd_sketch_reads_batch(self.h, n, _ptr(off), _ptr(lens), _ptr(buf), w, k, Zb, W,
+                                                float(max_seeds), int(max_nb_seeds), _ptr(s2_counts), _ptr(s2_off),
+                                                _ptr(s2), cap, _ptr(s3_off), _ptr(s3_ret), _ptr(s3), cap)
+            if rc == GD_ERR_CAPACITY:
+                cap *= 4
+                continue
+            self._check(rc, "gd_sketch_reads_batch")
+            return dict(s2_counts=s2_counts, s2_off=s2_off, s2=s2[: int(s2_off[n])], s3_off=s3_off, s3_ret=s3_ret,
+                        s3=s3[: int(s3_off[n * W])])
+
+
+# ---------------------------------------------------------------------------------------------
+# drop-in single-call mirrors: these call the symbols that carry the REFERENCE's names
+# ---------------------------------------------------------------------------------------------
+def ksw_extd2(query, target, mat, q, e, q2, e2, w, zdrop, end_bonus, flag, entry="ksw_extd2_avx512", m=None):
+    """Calls the drop-in ``ksw_extd2_avx512`` / ``ksw_extd2_sse`` symbol of libgdiet_cuda.so exactly like
+    GDiet-ShortReads/map.c:923-929 does. Returns (dict of ksw_extz_t fields, cigar array)."""
+    L = load()
+    query = np.ascontiguousarray(query, np.uint8)
+    target = np.ascontiguousarray(target, np.uint8)
+    mat = np.ascontiguousarray(mat, np.int8)
+    if m is None:
+        m = int(round(len(mat) ** 0.5))
+    ez = ksw_extz_t()  # memset 0 like map.c:866
+    getattr(L, entry)(None, len(query), _ptr(query), len(target), _ptr(target), m, _ptr(mat), q, e, q2, e2, w, zdrop,
+                      end_bonus, flag, C.byref(ez))
+    d = dict(max=ez.max_zdropped & 0x7fffffff, zdropped=ez.max_zdropped >> 31, max_q=ez.max_q, max_t=ez.max_t,
+             mqe=ez.mqe, mqe_t=ez.mqe_t, mte=ez.mte, mte_q=ez.mte_q, score=ez.score, n_cigar=ez.n_cigar,
+             reach_end=ez.reach_end)
+    cig = np.array([ez.cigar[i] for i in range(ez.n_cigar)], np.uint32)
+    if ez.cigar:
+        _libc.free(C.cast(ez.cigar, C.c_void_p))  # kfree(km=NULL, ...) == free (kalloc.c)
+    return d, cig
+
+
+def _take_v(v):
+    out = np.zeros(v.n, MM128_DTYPE)
+    if v.n:
+        C.memmove(out.ctypes.data, v.a, v.n * 16)
+    if v.a:
+        _libc.free(v.a)
+    return np.stack([out["x"], out["y"]], 1) if v.n else np.zeros((0, 2), np.uint64)
+
+
+def mm_sketch(seq, w, k, rid, Z):
+    """drop-in mm_sketch (GDiet-ShortReads/mmpriv.h:63)"""
+    L = load()
+    Zb = Z.encode() if isinstance(Z, str) else Z
+    v = mm128_v(0, 0, None)
+    L.mm_sketch(None, bytes(seq), len(seq), w, k, rid, 0, C.byref(v), Zb, len(Zb))
+    return _take_v(v)
+
+
+def mm_sketch3(seq, w, k, rid, Z, shift, max_nb_seeds):
+    """drop-in mm_sketch3 (GDiet-ShortReads/mmpriv.h:67). Returns (entries, return value)."""
+    L = load()
+    Zb = Z.encode() if isinstance(Z, str) else Z
+    v = mm128_v(0, 0, None)
+    ret = L.mm_sketch3(None, bytes(seq), len(seq), w, k, rid, 0, C.byref(v), Zb, len(Zb), shift, max_nb_seeds)
+    return _take_v(v), int(ret)
+
+
+def mm_sketch2(seq, w, k, rid, Z, max_seeds):
+    """drop-in mm_sketch2 (GDiet-ShortReads/mmpriv.h:65). Returns (entries, shift_seeds_number)."""
+    L = load()
+    Zb = Z.encode() if isinstance(Z, str) else Z
+    v = mm128_v(0, 0, None)
+    pat = L.mm_sketch2(None, bytes(seq), len(seq), w, k, rid, 0, C.byref(v), Zb, len(Zb), float(max_seeds))
+    counts = np.array([pat.shift_seeds_number[i] for i in range(pat.n)], np.uint32)
+    _libc.free(C.cast(pat.shift_seeds_number, C.c_void_p))
+    return _take_v(v), counts

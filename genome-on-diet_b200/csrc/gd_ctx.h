@@ -1,0 +1,82 @@
+// gd_ctx.h -- the context object behind the C ABI (include/gdiet_cuda.h): one CUDA stream plus
+// grow-only device / pinned-host staging buffers.  One context per host thread.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/gdiet_cuda.h"
+
+struct GdBuf { // grow-only device buffer
+	void *p = nullptr;
+	size_t cap = 0;
+};
+struct GdPinned { // grow-only pinned host buffer
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+struct gd_ctx {
+	int device = 0;
+	int sms = 0;
+	size_t smem_optin = 0;
+	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	std::string err;
+	// options
+	long opt_ksw_group = 0;
+	long opt_p_budget_mb = 0; // 0 = auto
+	long opt_ksw_blocks_per_sm = 0;
+	long opt_sketch_chunk = 0;
+	// stats
+	long stat_launches = 0;
+	long stat_ksw_ring = 0, stat_ksw_group = 0, stat_ksw_chunks = 0;
+	// DP scratch
+	GdBuf tpk, qpk, parena, ticket, cig_tmp, cig_off, cig_compact, res;
+	GdBuf d_qlen, d_tlen, d_w, d_qoff, d_toff, d_qbuf, d_tbuf;
+	GdPinned h_stage, h_res, h_cig, h_misc;
+	// sketch scratch
+	GdBuf sk_seq, sk_off, sk_len, sk_rid, sk_out, sk_out_off, sk_state, sk_misc, sk_jobs, sk_out2;
+	GdPinned h_sk_stage, h_sk_out, h_sk_misc;
+};
+
+#define GD_CUDA_OK(ctx, call)                                                                          \
+	do {                                                                                           \
+		cudaError_t e__ = (call);                                                              \
+		if (e__ != cudaSuccess) {                                                              \
+			char b__[512];                                                                 \
+			snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+			(ctx)->err = b__;                                                              \
+			return GD_ERR_CUDA;                                                            \
+		}                                                                                      \
+	} while (0)
+
+static inline int gd_reserve(gd_ctx *ctx, GdBuf &b, size_t bytes)
+{
+	if (bytes <= b.cap) return GD_OK;
+	if (b.p) GD_CUDA_OK(ctx, cudaFree(b.p));
+	b.p = nullptr, b.cap = 0;
+	size_t want = bytes + bytes / 8 + 256;
+	GD_CUDA_OK(ctx, cudaMalloc(&b.p, want));
+	b.cap = want;
+	return GD_OK;
+}
+static inline int gd_reserve_pinned(gd_ctx *ctx, GdPinned &b, size_t bytes)
+{
+	if (bytes <= b.cap) return GD_OK;
+	if (b.p) GD_CUDA_OK(ctx, cudaFreeHost(b.p));
+	b.p = nullptr, b.cap = 0;
+	size_t want = bytes + bytes / 8 + 256;
+	GD_CUDA_OK(ctx, cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+	b.cap = want;
+	return GD_OK;
+}
+
+// implemented in gd_ksw.cu
+int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *d_qoff, const uint8_t *d_qbuf,
+                      const int32_t *d_tlen, const int64_t *d_toff, const uint8_t *d_tbuf, const int32_t *d_w,
+                      int w_all, int max_qlen, int max_tlen, int max_w, const gd_ksw_params_t *prm, gd_extz_t *d_ez,
+                      uint32_t *d_cigar, int cigar_stride);
+int gd_ksw_compact_cigars(gd_ctx *ctx, int n, const gd_extz_t *d_ez, const uint32_t *d_cigar, int cigar_stride,
+                          int64_t *d_off /*n+1*/, uint32_t *d_compact, int64_t compact_cap);

@@ -1,0 +1,262 @@
+// gd_ksw.cu -- kernels and launcher of the batched ksw_extd2 DP (see gd_ksw.cuh for the design).
+#include "gd_ctx.h"
+#include "gd_ksw_host.h"
+#include <algorithm>
+
+using namespace gd;
+
+static_assert(sizeof(KswResult) == sizeof(gd_extz_t), "result layouts must match");
+
+// --------------------------------------------------------------------------------------------
+// kernels
+// --------------------------------------------------------------------------------------------
+template <int G, bool RIGHT, bool EXACT, bool WITH_P>
+__global__ void __launch_bounds__(128) gd_ksw_dp_kernel(const KswConsts C, const KswBatch B)
+{
+	extern __shared__ __align__(16) uint8_t gd_smem[];
+	const int tid = threadIdx.x, lane = tid & 31, li = lane & (G - 1);
+	const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1));
+	ksw_group_body<G, RIGHT, EXACT, WITH_P>(C, B, gd_smem + (size_t)(tid / G) * B.group_smem, li, gmask);
+}
+
+// one warp per pair: raw byte codes -> padded arenas
+__global__ void __launch_bounds__(128)
+    gd_ksw_pack_kernel(int n, int base, const int32_t *__restrict__ qlen, const int64_t *__restrict__ qoff,
+                       const uint8_t *__restrict__ qbuf, const int32_t *__restrict__ tlen,
+                       const int64_t *__restrict__ toff, const uint8_t *__restrict__ tbuf, uint8_t *tpk, int t_stride,
+                       uint8_t *qpk, int q_stride)
+{
+	const int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
+	for (int lp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; lp < n; lp += warps) {
+		const int pair = base + lp;
+		int ql = qlen[pair], tl = tlen[pair];
+		if (ql < 0) ql = 0;
+		if (tl < 0) tl = 0;
+		ksw_pack_pair(qbuf + qoff[pair], ql, tbuf + toff[pair], tl, tpk + (size_t)lp * t_stride, t_stride,
+		              qpk + (size_t)lp * q_stride, q_stride, lane, 32);
+	}
+}
+
+__global__ void __launch_bounds__(128) gd_ksw_traceback_kernel(const KswBatch B, int flag, uint32_t *cigar, int stride)
+{
+	const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+	if (lp < B.n) ksw_traceback_one(B, flag, lp, cigar, stride);
+}
+
+__global__ void gd_ksw_nocigar_kernel(int n, KswResult *res)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) res[i].n_cigar = 0;
+}
+
+// exclusive scan of max(n_cigar,0) over n pairs (single block; n_cigar arrays are small)
+__global__ void __launch_bounds__(1024) gd_ksw_cigar_scan_kernel(int n, const KswResult *res, int64_t *off)
+{
+	__shared__ int64_t warp_sum[32];
+	__shared__ int64_t carry;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < n; base += 1024) {
+		const int i = base + tid;
+		int64_t v = 0;
+		if (i < n) {
+			int c = res[i].n_cigar;
+			v = c > 0 ? c : 0;
+		}
+		int64_t inc = v;
+		for (int d = 1; d < 32; d <<= 1) {
+			int64_t o = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += o;
+		}
+		if (lane == 31) warp_sum[wid] = inc;
+		__syncthreads();
+		if (wid == 0) {
+			int64_t ws = warp_sum[lane], wi = ws;
+			for (int d = 1; d < 32; d <<= 1) {
+				int64_t o = __shfl_up_sync(0xffffffffu, wi, d);
+				if (lane >= d) wi += o;
+			}
+			warp_sum[lane] = wi - ws; // exclusive
+		}
+		__syncthreads();
+		const int64_t excl = carry + warp_sum[wid] + inc - v;
+		if (i < n) off[i] = excl;
+		__syncthreads();
+		if (tid == 1023) carry = excl + v;
+		__syncthreads();
+	}
+	if (tid == 0) off[n] = carry;
+}
+
+__global__ void __launch_bounds__(256)
+    gd_ksw_cigar_gather_kernel(int n, const KswResult *res, const uint32_t *cigar, int stride, const int64_t *off,
+                               uint32_t *out, int64_t cap)
+{
+	const int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+		const int c = res[i].n_cigar;
+		const int64_t o = off[i];
+		if (c <= 0 || o + c > cap) continue;
+		for (int k = lane; k < c; k += 32) out[o + k] = cigar[(size_t)i * stride + k];
+	}
+}
+
+__global__ void gd_exact_match_kernel(int n, const int32_t *qlen, const int64_t *qoff, const uint8_t *qbuf,
+                                      const int64_t *toff, const uint8_t *tbuf, uint8_t *equal)
+{ // exact_match_sse.c:27-88 == memcmp over qlen bytes; one warp per pair
+	const int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+		const int ql = qlen[i];
+		const uint8_t *q = qbuf + qoff[i], *t = tbuf + toff[i];
+		int diff = 0;
+		for (int k = lane; k < ql; k += 32) diff |= q[k] != t[k];
+		diff = __any_sync(0xffffffffu, diff);
+		if (lane == 0) equal[i] = (ql > 0 && !diff) ? 1 : 0;
+	}
+}
+
+// --------------------------------------------------------------------------------------------
+// launcher
+// --------------------------------------------------------------------------------------------
+typedef void (*dp_kernel_t)(const KswConsts, const KswBatch);
+
+template <int G> static dp_kernel_t pick_mode(bool right, bool exact, bool with_p)
+{
+	if (right) {
+		if (exact) return with_p ? gd_ksw_dp_kernel<G, true, true, true> : gd_ksw_dp_kernel<G, true, true, false>;
+		return with_p ? gd_ksw_dp_kernel<G, true, false, true> : gd_ksw_dp_kernel<G, true, false, false>;
+	}
+	if (exact) return with_p ? gd_ksw_dp_kernel<G, false, true, true> : gd_ksw_dp_kernel<G, false, true, false>;
+	return with_p ? gd_ksw_dp_kernel<G, false, false, true> : gd_ksw_dp_kernel<G, false, false, false>;
+}
+static dp_kernel_t pick_kernel(int G, bool right, bool exact, bool with_p)
+{
+	switch (G) {
+	case 4: return pick_mode<4>(right, exact, with_p);
+	case 8: return pick_mode<8>(right, exact, with_p);
+	case 16: return pick_mode<16>(right, exact, with_p);
+	default: return pick_mode<32>(right, exact, with_p);
+	}
+}
+
+int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *d_qoff, const uint8_t *d_qbuf,
+                      const int32_t *d_tlen, const int64_t *d_toff, const uint8_t *d_tbuf, const int32_t *d_w,
+                      int w_all, int max_qlen, int max_tlen, int max_w, const gd_ksw_params_t *prm, gd_extz_t *d_ez,
+                      uint32_t *d_cigar, int cigar_stride)
+{
+	if (n <= 0) return GD_OK;
+	if (!prm || !d_ez) {
+		ctx->err = "gd_ksw: null params / result pointer";
+		return GD_ERR_ARG;
+	}
+	if (prm->flag & KSW_F_GENERIC_SC) {
+		ctx->err = "gd_ksw: KSW_EZ_GENERIC_SC is not supported (never used by the Genome-on-Diet call sites)";
+		return GD_ERR_ARG;
+	}
+	const int flag = prm->flag;
+	const bool exact = !(flag & KSW_F_APPROX_MAX), right = (flag & KSW_F_RIGHT) != 0;
+	const bool with_p = !(flag & KSW_F_SCORE_ONLY) && d_cigar != nullptr && cigar_stride > 0;
+	KswConsts C = ksw_make_consts(prm->m, prm->mat, prm->q, prm->e, prm->q2, prm->e2, prm->zdrop, prm->end_bonus, flag);
+	if (max_w < 0) max_w = std::max(max_qlen, max_tlen);
+	KswGeom geo = ksw_geometry(max_qlen, max_tlen, max_w, exact, with_p);
+
+	// lanes per pair
+	int G = (int)ctx->opt_ksw_group;
+	if (G != 4 && G != 8 && G != 16 && G != 32) {
+		const int nb = h_ncol16(max_qlen, max_tlen, max_w) / 16 - 1; // 16-cell blocks in the widest row
+		G = nb <= 3 ? 4 : nb <= 16 ? 8 : nb <= 32 ? 16 : 32;
+	}
+	const int threads = 128, groups_per_block = threads / G;
+	const size_t smem = (size_t)groups_per_block * geo.group_smem;
+	if (smem > ctx->smem_optin) {
+		ctx->err = "gd_ksw: band too wide for the shared-memory ring of one block";
+		return GD_ERR_ARG;
+	}
+	dp_kernel_t kern = pick_kernel(G, right, exact, with_p);
+	GD_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int occ = 0;
+	GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+	if (occ < 1) occ = 1;
+	if (ctx->opt_ksw_blocks_per_sm > 0) occ = std::min<long>(occ, ctx->opt_ksw_blocks_per_sm);
+
+	// chunking: the backtrack arena is the only large scratch
+	size_t budget;
+	if (ctx->opt_p_budget_mb > 0) budget = (size_t)ctx->opt_p_budget_mb << 20;
+	else {
+		size_t fr = 0, tot = 0;
+		GD_CUDA_OK(ctx, cudaMemGetInfo(&fr, &tot));
+		budget = std::max<size_t>(ctx->parena.cap, (size_t)(fr * 0.6));
+		budget = std::min<size_t>(budget, (size_t)96 << 30);
+	}
+	int chunk = n;
+	if (with_p) {
+		size_t fit = std::max<size_t>(1, budget / (size_t)std::max<int64_t>(geo.p_stride, 1));
+		chunk = (int)std::min<size_t>(fit, (size_t)n);
+	}
+	chunk = std::min(chunk, 1 << 22);
+	int rc;
+	if ((rc = gd_reserve(ctx, ctx->tpk, (size_t)chunk * geo.t_stride + 64))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->qpk, (size_t)chunk * geo.q_stride + 64))) return rc;
+	if (with_p && (rc = gd_reserve(ctx, ctx->parena, (size_t)chunk * geo.p_stride + 64))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->ticket, 256))) return rc;
+
+	ctx->stat_ksw_ring = geo.ring, ctx->stat_ksw_group = G, ctx->stat_ksw_chunks = 0;
+	cudaStream_t s = ctx->stream;
+	for (int base = 0; base < n; base += chunk) {
+		const int cn = std::min(chunk, n - base);
+		KswBatch B;
+		B.n = cn, B.base = base, B.qlen = d_qlen, B.tlen = d_tlen, B.w = d_w, B.w_all = w_all;
+		B.tpk = (const uint8_t *)ctx->tpk.p, B.qpk = (const uint8_t *)ctx->qpk.p;
+		B.t_stride = geo.t_stride, B.q_stride = geo.q_stride;
+		B.p = (uint8_t *)ctx->parena.p, B.p_stride = geo.p_stride;
+		B.res = (KswResult *)d_ez, B.ticket = (int32_t *)ctx->ticket.p;
+		B.ring = geo.ring, B.group_smem = geo.group_smem;
+
+		GD_CUDA_OK(ctx, cudaMemsetAsync(ctx->ticket.p, 0, 4, s));
+		{
+			int blocks = std::min((cn + 3) / 4, ctx->sms * 16);
+			gd_ksw_pack_kernel<<<blocks, 128, 0, s>>>(cn, base, d_qlen, d_qoff, d_qbuf, d_tlen, d_toff, d_tbuf,
+			                                          (uint8_t *)ctx->tpk.p, geo.t_stride, (uint8_t *)ctx->qpk.p,
+			                                          geo.q_stride);
+		}
+		{
+			int blocks = std::min((cn + groups_per_block - 1) / groups_per_block, ctx->sms * occ);
+			kern<<<blocks, threads, smem, s>>>(C, B);
+		}
+		if (with_p) gd_ksw_traceback_kernel<<<(cn + 127) / 128, 128, 0, s>>>(B, flag, d_cigar, cigar_stride);
+		ctx->stat_launches += with_p ? 3 : 2;
+		ctx->stat_ksw_chunks++;
+	}
+	GD_CUDA_OK(ctx, cudaGetLastError());
+	return GD_OK;
+}
+
+int gd_ksw_compact_cigars(gd_ctx *ctx, int n, const gd_extz_t *d_ez, const uint32_t *d_cigar, int cigar_stride,
+                          int64_t *d_off, uint32_t *d_compact, int64_t compact_cap)
+{
+	cudaStream_t s = ctx->stream;
+	gd_ksw_cigar_scan_kernel<<<1, 1024, 0, s>>>(n, (const KswResult *)d_ez, d_off);
+	ctx->stat_launches++;
+	if (d_compact && d_cigar) {
+		int blocks = std::min((n + 7) / 8, ctx->sms * 8);
+		gd_ksw_cigar_gather_kernel<<<blocks, 256, 0, s>>>(n, (const KswResult *)d_ez, d_cigar, cigar_stride, d_off,
+		                                                  d_compact, compact_cap);
+		ctx->stat_launches++;
+	}
+	GD_CUDA_OK(ctx, cudaGetLastError());
+	return GD_OK;
+}
+
+extern "C" int gd_exact_match_batch_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *d_qoff,
+                                           const uint8_t *d_qbuf, const int64_t *d_toff, const uint8_t *d_tbuf,
+                                           uint8_t *d_equal)
+{
+	if (!ctx) return GD_ERR_ARG;
+	if (n <= 0) return GD_OK;
+	int blocks = std::min((n + 3) / 4, ctx->sms * 16);
+	gd_exact_match_kernel<<<blocks, 128, 0, ctx->stream>>>(n, d_qlen, d_qoff, d_qbuf, d_toff, d_tbuf, d_equal);
+	ctx->stat_launches++;
+	GD_CUDA_OK(ctx, cudaGetLastError());
+	return GD_OK;
+}

@@ -1,0 +1,88 @@
+// gd_ksw_host.h -- host-side preparation shared by the CUDA launcher (gd_ksw.cu) and the
+// logic tests (tests/emu): scoring constants, ring sizing, arena strides.
+#pragma once
+#include "gd_ksw.cuh"
+
+namespace gd {
+
+static inline uint32_t h_pack16(int v) { return ((uint32_t)(v & 0xff) << 8) | ((uint32_t)(v & 0xff) << 24); }
+static inline uint32_t h_rep4(int v) { return (uint32_t)(v & 0xff) * 0x01010101u; }
+
+// Mirrors the prologue of ksw_extd2_sse (GDiet-ShortReads/ksw2_extd2_sse.c:68-105).
+static inline KswConsts ksw_make_consts(int m, const int8_t *mat, int q_, int e_, int q2_, int e2_, int zdrop,
+                                        int end_bonus, int flag)
+{
+	KswConsts C;
+	int8_t q = (int8_t)q_, e = (int8_t)e_, q2 = (int8_t)q2_, e2 = (int8_t)e2_;
+	C.qe_seed = (int)q + (int)e; // evaluated before the swap in the reference
+	C.degenerate = 0;
+	if (m <= 1) {
+		C.degenerate = 1;
+		m = 2;
+	}
+	if ((int)q2 + e2 < (int)q + e) {
+		int8_t tq = q, te = e;
+		q = q2, e = e2, q2 = tq, e2 = te;
+	}
+	int min_sc = mat ? mat[1] : 0;
+	if (mat)
+		for (int t = 1; t < m * m; ++t) min_sc = min_sc < mat[t] ? min_sc : mat[t];
+	if (!mat || -min_sc > 2 * ((int)q + e)) C.degenerate = 1;
+	const int mch = mat ? mat[0] : 0, mis = mat ? mat[1] : 0;
+	const int scn = mat ? (mat[m * m - 1] == 0 ? (int8_t)(-e2) : mat[m * m - 1]) : 0;
+	const bool right = (flag & KSW_F_RIGHT) != 0;
+	// tags: larger tag wins a tie inside the packed max. Left-aligned gaps: first of (H,E,F,E~,F~)
+	// wins -> tags 7,6,5,4,3 (xor 7 gives 0..4); right-aligned: last wins -> tags 0..4.
+	const uint32_t ts = right ? 0 : 7, ta = right ? 1 : 6, tb = right ? 2 : 5, ta2 = right ? 3 : 4, tb2 = right ? 4 : 3;
+	C.TS4 = ts * 0x01010101u;
+	C.TA = ta * 0x00010001u, C.TB = tb * 0x00010001u, C.TA2 = ta2 * 0x00010001u, C.TB2 = tb2 * 0x00010001u;
+	C.TAGX = right ? 0u : 0x07070707u;
+	C.MCH16 = h_pack16(mch);
+	C.Q1 = h_pack16(q) + 0x00010001u;
+	C.Q21 = h_pack16(q2) + 0x00010001u;
+	C.NEGQE = h_pack16(-(int)(int8_t)(q + e));
+	C.NEGQE2 = h_pack16(-(int)(int8_t)(q2 + e2));
+	C.MCH4 = h_rep4(mch), C.MIS4 = h_rep4(mis), C.SCN4 = h_rep4(scn);
+	C.INIT_U = h_pack16(-q - e);
+	C.INIT_X = C.INIT_U | C.TA, C.INIT_Y = C.INIT_U | C.TB;
+	C.INIT_X2 = h_pack16(-q2 - e2) | C.TA2, C.INIT_Y2 = h_pack16(-q2 - e2) | C.TB2;
+	C.q = q, C.e = e, C.q2 = q2, C.e2 = e2;
+	int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+	if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
+	C.long_thres = long_thres;
+	C.long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+	C.zdrop = zdrop, C.end_bonus = end_bonus, C.flag = flag;
+	return C;
+}
+
+static inline int h_ncol16(int qlen, int tlen, int w)
+{
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	int n = qlen < tlen ? qlen : tlen;
+	n = n < w + 1 ? n : w + 1;
+	return ((n + 15) / 16 + 1) * 16;
+}
+
+// Geometry of one launch, derived from upper bounds on the chunk's pairs.
+struct KswGeom {
+	int ring;        // columns per ring
+	int group_smem;  // bytes per group
+	int t_stride, q_stride;
+	int64_t p_stride;
+};
+static inline KswGeom ksw_geometry(int max_qlen, int max_tlen, int max_w, bool exact, bool with_p)
+{
+	KswGeom g;
+	if (max_qlen < 1) max_qlen = 1;
+	if (max_tlen < 1) max_tlen = 1;
+	const int T16 = (max_tlen + 15) / 16 * 16;
+	const int ncol16 = h_ncol16(max_qlen, max_tlen, max_w);
+	g.ring = ncol16 + 32 < T16 ? ncol16 + 32 : T16;
+	g.group_smem = ksw_group_smem_bytes(g.ring, exact);
+	g.t_stride = T16 + 16;
+	g.q_stride = (max_qlen + 15) / 16 * 16 + 64;
+	g.p_stride = with_p ? (int64_t)(max_qlen + max_tlen - 1) * ncol16 : 0;
+	return g;
+}
+
+} // namespace gd

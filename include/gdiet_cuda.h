@@ -1,0 +1,185 @@
+/* gdiet_cuda.h -- C ABI of libgdiet_cuda.so: the B200 (sm_100a) replacement for the two kernels on
+ * Genome-on-Diet's per-read mapping hot path.
+ *
+ *   (1) ksw2 dual-affine banded extension DP      reference: GDiet-ShortReads/ksw2.h:68-69,
+ *       ksw_extd2_sse / ksw_extd2_avx512          GDiet-ShortReads/ksw2_extd2_avx.h:38,
+ *                                                 dispatch GDiet-ShortReads/ksw2_dispatch.c:79-92
+ *   (2) sparsified minimizer sketching            reference: GDiet-ShortReads/mmpriv.h:63-68
+ *       mm_sketch / mm_sketch2 / mm_sketch3       (GDiet-ShortReads/sketch.c:156,618,1078,2143)
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types.  Two layers:
+ *   - drop-in entry points with EXACTLY the reference's names and signatures (batch of one);
+ *   - batched entry points (gd_*) taking either host buffers or device-resident buffers.
+ * There is no CPU fallback: every entry point fails loudly (error code + gd_strerror, or abort()
+ * for the void drop-in functions) when no CUDA device is usable.
+ */
+#ifndef GDIET_CUDA_H
+#define GDIET_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* types                                                                                       */
+/* ------------------------------------------------------------------------------------------ */
+
+/* ksw_extz_t exactly as GDiet-ShortReads/ksw2.h:31-40 (the drop-in functions fill this one).
+ * Guarded so that a host program that already includes the reference's ksw2.h can include us. */
+#ifndef KSW2_H_
+typedef struct {
+	uint32_t max : 31, zdropped : 1;
+	int max_q, max_t;
+	int mqe, mqe_t;
+	int mte, mte_q;
+	int score;
+	int m_cigar, n_cigar;
+	int reach_end;
+	uint32_t *cigar;
+} ksw_extz_t;
+#endif
+
+/* mm128_t / mm128_v / mm_pattern_t exactly as GDiet-ShortReads/minimap.h:69-76,99-102 */
+#ifndef MINIMAP2_H
+typedef struct {
+	uint64_t x, y;
+} mm128_t;
+typedef struct {
+	size_t n, m;
+	mm128_t *a;
+} mm128_v;
+typedef struct {
+	uint32_t n;
+	uint32_t *shift_seeds_number;
+} mm_pattern_t;
+#endif
+
+/* Flat per-pair result of the batched DP (64 bytes). The first 11 fields are the fields of
+ * ksw_extz_t; n_cigar < 0 means the CIGAR needed -n_cigar entries and did not fit. */
+typedef struct {
+	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end;
+	int32_t tb_i, tb_j; /* traceback start cell (target, query), -1 = none */
+	int32_t rows_done;  /* anti-diagonals executed */
+	int32_t reserved[2];
+} gd_extz_t;
+
+/* Scoring / control arguments of ksw_extd2_sse(), batch-uniform (GDiet-ShortReads/ksw2.h:42-59). */
+typedef struct {
+	int32_t m;         /* alphabet size (5 at every call site) */
+	const int8_t *mat; /* m*m scores */
+	int32_t q, e, q2, e2;
+	int32_t zdrop, end_bonus, flag; /* KSW_EZ_* */
+} gd_ksw_params_t;
+
+typedef struct gd_ctx gd_ctx; /* one per host thread / stream; owns device and pinned staging memory */
+
+enum {
+	GD_OK = 0,
+	GD_ERR_NO_DEVICE = 1,   /* no usable sm_100 device / CUDA failure at init */
+	GD_ERR_CUDA = 2,        /* a CUDA call failed, see gd_strerror */
+	GD_ERR_ARG = 3,         /* invalid argument (also: unsupported flag KSW_EZ_GENERIC_SC) */
+	GD_ERR_CAPACITY = 4     /* caller-provided output buffer too small; required size reported */
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* context                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+int gd_init(int device, gd_ctx **ctx);
+void gd_destroy(gd_ctx *ctx);
+const char *gd_strerror(const gd_ctx *ctx); /* ctx may be NULL: last init error */
+/* options: "ksw_group" (lanes per pair: 0=auto,4,8,16,32), "p_budget_mb" (backtrack arena),
+ * "ksw_blocks_per_sm" (0=auto).  stats: "kernel_launches", "ksw_cells", "ksw_ring",
+ * "ksw_group", "device_sms" */
+int gd_set_option(gd_ctx *ctx, const char *key, long value);
+long gd_get_stat(const gd_ctx *ctx, const char *key);
+void *gd_stream(gd_ctx *ctx); /* the cudaStream_t all work of this context is issued on */
+
+/* ------------------------------------------------------------------------------------------ */
+/* (1) DP                                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Drop-in replacements: same names, arguments, result fields and CIGAR ownership as
+ * GDiet-ShortReads/ksw2.h:68-69 and GDiet-ShortReads/ksw2_extd2_avx.h:38.  ez->cigar is (re)allocated
+ * with krealloc(km, ...) when the host program provides kalloc, else realloc (km must then be NULL);
+ * the caller frees it with kfree(km, ez->cigar) exactly as at GDiet-ShortReads/map.c:952.
+ * Both names run the same kernel; scoring of codes > 4 follows ksw_extd2_avx512 (the GDiet_avx build). */
+void ksw_extd2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m,
+                   const int8_t *mat, int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus,
+                   int flag, ksw_extz_t *ez);
+void ksw_extd2_avx512(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m,
+                      const int8_t *mat, int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus,
+                      int flag, ksw_extz_t *ez);
+
+/* Batched DP over host buffers: pair i is query qbuf[qoff[i] .. +qlen[i]) against target
+ * tbuf[toff[i] .. +tlen[i]) (byte codes as at GDiet-ShortReads/map.c:737-757,840), band w[i] (or w_all if
+ * w == NULL).  Stages through pinned memory, runs pack + DP + traceback on the context's stream and
+ * returns after the results are on the host:
+ *   ez[i]                       per-pair result
+ *   cigar_off[0..n]             prefix offsets (entries) into cigar[]
+ *   cigar[cigar_off[i] .. cigar_off[i+1])   BAM-encoded CIGAR of pair i (len<<4|op)
+ * cigar may be NULL (then only ez and cigar_off are produced).  Returns GD_ERR_CAPACITY and sets
+ * cigar_off[n] to the required number of entries if cigar_cap is too small. */
+int gd_ksw_extd2_batch(gd_ctx *ctx, int n, const int32_t *qlen, const int64_t *qoff, const uint8_t *qbuf,
+                       const int32_t *tlen, const int64_t *toff, const uint8_t *tbuf, const int32_t *w, int w_all,
+                       const gd_ksw_params_t *prm, gd_extz_t *ez, int64_t *cigar_off, uint32_t *cigar,
+                       int64_t cigar_cap);
+
+/* Same, but every array argument is a DEVICE pointer and nothing is copied or synchronised: the
+ * work is enqueued on gd_stream(ctx).  max_qlen/max_tlen/max_w are upper bounds over the batch
+ * (they size the staging arenas).  d_cigar receives n * cigar_stride entries (pair i at
+ * i*cigar_stride, d_ez[i].n_cigar of them valid); pass NULL / KSW_EZ_SCORE_ONLY for scores only. */
+int gd_ksw_extd2_batch_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *d_qoff, const uint8_t *d_qbuf,
+                              const int32_t *d_tlen, const int64_t *d_toff, const uint8_t *d_tbuf,
+                              const int32_t *d_w, int w_all, int max_qlen, int max_tlen, int max_w,
+                              const gd_ksw_params_t *prm, gd_extz_t *d_ez, uint32_t *d_cigar, int cigar_stride);
+
+/* exact_match_sse (GDiet-ShortReads/exact_match_sse.c:27-88) for a batch, device-resident:
+ * d_equal[i] = (memcmp(query_i, target_i, qlen[i]) == 0). */
+int gd_exact_match_batch_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *d_qoff,
+                                const uint8_t *d_qbuf, const int64_t *d_toff, const uint8_t *d_tbuf,
+                                uint8_t *d_equal);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (2) sketching                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Drop-in replacements (GDiet-ShortReads/mmpriv.h:63-68): same append / allocation behaviour
+ * (kv_push semantics on *p with krealloc(km), kmalloc'd shift_seeds_number). */
+void mm_sketch(void *km, const char *str, int len, int w, int k, uint32_t rid, int is_hpc, mm128_v *p, const char *Z,
+               int W);
+mm_pattern_t mm_sketch2(void *km, const char *str, int len, int w, int k, uint32_t rid, int is_hpc, mm128_v *p,
+                        const char *Z, int W, const float max_seeds);
+unsigned mm_sketch3(void *km, const char *str, const unsigned len, int w, int k, uint32_t rid, int is_hpc, mm128_v *p,
+                    const char *Z, int W, int shift2, uint32_t MAX_NB_SEEDS);
+
+/* Index-build sketching of n reference sequences (mm_sketch semantics, rid[i] stamped into y):
+ * seqs are ASCII in buf at off[i], len[i].  Output minimizers are concatenated in input order:
+ * out[out_off[i] .. out_off[i+1]).  Host buffers; returns GD_ERR_CAPACITY with out_off[n] set when
+ * out_cap (entries) is too small. */
+int gd_sketch_ref_batch(gd_ctx *ctx, int n, const int64_t *off, const int32_t *len, const uint32_t *rid,
+                        const char *buf, int w, int k, const char *Z, int W, int64_t *out_off, mm128_t *out,
+                        int64_t out_cap);
+
+/* Device-resident variant: everything is a device pointer, nothing is synchronised.
+ * d_out_count[0] receives the total; d_out_off[0..n] the per-sequence offsets. */
+int gd_sketch_ref_batch_device(gd_ctx *ctx, int n, const int64_t *d_off, const int32_t *d_len, const uint32_t *d_rid,
+                               const char *d_buf, int64_t total_len, int w, int k, const char *Z, int W,
+                               int64_t *d_out_off, mm128_t *d_out, int64_t out_cap);
+
+/* Read sketching for the mapping pipeline: for every read the two calls the reference makes per
+ * read (GDiet-ShortReads/map.c:74-99), in one launch:
+ *   mm_sketch2(max_seeds)       -> s2_counts[i*W + shift], entries s2[s2_off[i] .. s2_off[i+1])
+ *   mm_sketch3(shift, cap) for EVERY shift 0..W-1
+ *                               -> s3[s3_off[i*W+shift] .. s3_off[i*W+shift+1]), s3_ret[i*W+shift]
+ * so the host can pick the shift (mm_get_shift) without a second device round trip. */
+int gd_sketch_reads_batch(gd_ctx *ctx, int n, const int64_t *off, const int32_t *len, const char *buf, int w, int k,
+                          const char *Z, int W, float max_seeds, uint32_t max_nb_seeds, uint32_t *s2_counts,
+                          int64_t *s2_off, mm128_t *s2, int64_t s2_cap, int64_t *s3_off, uint32_t *s3_ret,
+                          mm128_t *s3, int64_t s3_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

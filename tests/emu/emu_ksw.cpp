@@ -1,0 +1,72 @@
+// tests/emu/emu_ksw.cpp -- TEST INFRASTRUCTURE ONLY.
+// Runs the *device code* of genome-on-diet_b200/csrc/gd_ksw.cuh under the fiber SIMT emulator so
+// its logic can be compared with the oracle on a machine without a GPU.
+#define GD_HOST_EMU 1
+#include "simt_emu.h"
+#include "gd_ksw_host.h"
+#include <vector>
+
+using namespace gd;
+
+template <int G, bool RIGHT, bool EXACT, bool WITH_P>
+static void run_dp(const KswConsts &C, const KswBatch &B, int threads)
+{
+	int groups = threads / G;
+	emu::launch(1, threads, (size_t)groups * B.group_smem, [&]() {
+		int tid = emu::thread_idx(), lane = tid & 31, li = lane & (G - 1);
+		uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1));
+		uint8_t *sm = (uint8_t *)emu::smem() + (size_t)(tid / G) * B.group_smem;
+		ksw_group_body<G, RIGHT, EXACT, WITH_P>(C, B, sm, li, gmask);
+	});
+}
+
+template <int G>
+static void dispatch(const KswConsts &C, const KswBatch &B, int threads, bool right, bool exact, bool with_p)
+{
+#define GO(R_, E_, P_) run_dp<G, R_, E_, P_>(C, B, threads)
+	if (right) {
+		if (exact) { if (with_p) GO(true, true, true); else GO(true, true, false); }
+		else { if (with_p) GO(true, false, true); else GO(true, false, false); }
+	} else {
+		if (exact) { if (with_p) GO(false, true, true); else GO(false, true, false); }
+		else { if (with_p) GO(false, false, true); else GO(false, false, false); }
+	}
+#undef GO
+}
+
+extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, const uint8_t *qbuf, const int32_t *tlen,
+                             const int64_t *toff, const uint8_t *tbuf, const int32_t *w, int m, const int8_t *mat,
+                             int q, int e, int q2, int e2, int zdrop, int end_bonus, int flag, int G, int threads,
+                             KswResult *res, uint32_t *cigar, int cigar_stride)
+{
+	KswConsts C = ksw_make_consts(m, mat, q, e, q2, e2, zdrop, end_bonus, flag);
+	int max_q = 1, max_t = 1, max_w = 0;
+	for (int i = 0; i < n; ++i) {
+		int ww = w[i] < 0 ? (tlen[i] > qlen[i] ? tlen[i] : qlen[i]) : w[i];
+		if (qlen[i] > max_q) max_q = qlen[i];
+		if (tlen[i] > max_t) max_t = tlen[i];
+		if (ww > max_w) max_w = ww;
+	}
+	const bool exact = !(flag & KSW_F_APPROX_MAX), with_p = !(flag & KSW_F_SCORE_ONLY), right = (flag & KSW_F_RIGHT) != 0;
+	KswGeom g = ksw_geometry(max_q, max_t, max_w, exact, with_p);
+	std::vector<uint8_t> tpk((size_t)n * g.t_stride), qpk((size_t)n * g.q_stride), p((size_t)n * g.p_stride + 16);
+	memset(p.data(), 0xAA, p.size()); // poison: any read of an unwritten backtrack byte shows up
+	for (int i = 0; i < n; ++i)
+		ksw_pack_pair(qbuf + qoff[i], qlen[i], tbuf + toff[i], tlen[i], tpk.data() + (size_t)i * g.t_stride, g.t_stride,
+		              qpk.data() + (size_t)i * g.q_stride, g.q_stride, 0, 1);
+	int ticket = 0;
+	KswBatch B;
+	B.n = n, B.base = 0, B.qlen = qlen, B.tlen = tlen, B.w = w, B.w_all = 0;
+	B.tpk = tpk.data(), B.qpk = qpk.data(), B.t_stride = g.t_stride, B.q_stride = g.q_stride;
+	B.p = p.data(), B.p_stride = g.p_stride, B.res = res, B.ticket = &ticket, B.ring = g.ring, B.group_smem = g.group_smem;
+	switch (G) {
+	case 4: dispatch<4>(C, B, threads, right, exact, with_p); break;
+	case 8: dispatch<8>(C, B, threads, right, exact, with_p); break;
+	case 16: dispatch<16>(C, B, threads, right, exact, with_p); break;
+	case 32: dispatch<32>(C, B, threads, right, exact, with_p); break;
+	default: return -1;
+	}
+	if (with_p)
+		for (int i = 0; i < n; ++i) ksw_traceback_one(B, flag, i, cigar, cigar_stride);
+	return 0;
+}

@@ -1,0 +1,53 @@
+// tests/emu/emu_sketch.cpp -- TEST INFRASTRUCTURE ONLY: runs the device code of gd_sketch.cuh under
+// the fiber SIMT emulator (see simt_emu.h).
+#define GD_HOST_EMU 1
+#include "simt_emu.h"
+#include "gd_sketch.cuh"
+#include <vector>
+
+using namespace gd;
+
+template <int THREADS, int P>
+static void run_tiles(const SketchParams &S, SketchBatch &B, int grid)
+{
+	emu::launch(grid, THREADS, sizeof(SketchSmem<THREADS, P>),
+	            [&]() { sketch_tile_body<THREADS, P>(S, B, (SketchSmem<THREADS, P> *)emu::smem()); });
+}
+
+// jobs: n x {seq_off, len, shift, rid}; small != 0 forces the one-tile-per-job configuration
+extern "C" long emu_sketch_jobs(int njobs, const int64_t *seq_off, const int32_t *len, const int32_t *shift,
+                                const uint32_t *rid, const char *buf, int w, int k, const char *Z, int W, int small,
+                                int grid, int64_t *out_off, uint64_t *out, int64_t out_cap)
+{
+	SketchParams S;
+	memset(&S, 0, sizeof(S));
+	S.w = w, S.k = k, S.W = W, S.mask = (1ull << 2 * k) - 1;
+	for (int g = 0; g < W; ++g)
+		if (Z[g] == '1') S.ones_loc[S.ones++] = (uint8_t)g;
+	std::vector<SketchJob> jobs(njobs);
+	for (int i = 0; i < njobs; ++i) jobs[i] = SketchJob{seq_off[i], len[i], shift[i], rid[i], 0};
+	S.TP = (small ? 256 : 2048) - 2 * (w - 1);
+	S.one_tile_per_job = small;
+	std::vector<int64_t> tb(njobs + 1, 0);
+	for (int i = 0; i < njobs; ++i) {
+		// host copy of sk_diet_len
+		int64_t dl = 0;
+		if (len[i] >= shift[i]) {
+			uint32_t rem = (uint32_t)(len[i] - shift[i]) % (uint32_t)W;
+			dl = (int64_t)((uint32_t)(len[i] - shift[i]) / (uint32_t)W) * S.ones;
+			for (int o = 0; o < S.ones; ++o)
+				if (S.ones_loc[o] < rem) ++dl;
+		}
+		int64_t t = small ? 1 : (dl + S.TP - 1) / S.TP;
+		tb[i + 1] = tb[i] + (t < 1 ? 1 : t);
+	}
+	std::vector<unsigned long long> status(tb[njobs] + 1, 0);
+	int ticket = 0;
+	SketchBatch B;
+	memset(&B, 0, sizeof(B));
+	B.njobs = njobs, B.ntiles = tb[njobs], B.jobs = jobs.data(), B.tile_base = small ? nullptr : tb.data();
+	B.buf = buf, B.status = status.data(), B.ticket = &ticket, B.out_off = out_off, B.out = out, B.out_cap = out_cap;
+	if (small) run_tiles<64, 4>(S, B, grid);
+	else run_tiles<256, 8>(S, B, grid);
+	return (long)out_off[njobs];
+}

@@ -1,0 +1,60 @@
+"""Loader for tests/emu/libgd_emu.so: the DEVICE CODE of csrc/gd_ksw.cuh / gd_sketch.cuh compiled for
+the host against the fiber SIMT emulator (tests/emu/simt_emu.h). Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oraclelib import EXTZ_FIELDS, u8p, i8p, i32p, i64p, u32p, u64p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EMU_DIR = os.path.join(HERE, "emu")
+CSRC = os.path.join(ROOT, "genome-on-diet_b200", "csrc")
+RES = np.dtype([(f, np.int32) for f in EXTZ_FIELDS + ["tb_i", "tb_j", "rows_done", "pad0", "pad1"]])
+
+
+def build():
+    so = os.path.join(EMU_DIR, "libgd_emu.so")
+    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_ksw.cpp", "emu_sketch.cpp")]
+    deps = srcs + [os.path.join(EMU_DIR, "simt_emu.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                                                              if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-fPIC", "-shared", "-std=c++17", "-I", EMU_DIR, "-I", CSRC, "-o", so] + srcs)
+    return so
+
+
+class Emu:
+    def __init__(self):
+        L = self.lib = C.CDLL(build())
+        L.emu_ksw_batch.restype = C.c_int
+        L.emu_ksw_batch.argtypes = [C.c_int, i32p, i64p, u8p, i32p, i64p, u8p, i32p, C.c_int, i8p] + [C.c_int] * 9 + [
+            C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_sketch_jobs.restype = C.c_long
+        L.emu_sketch_jobs.argtypes = [C.c_int, i64p, i32p, i32p, u32p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                      C.c_int, C.c_int, i64p, u64p, C.c_int64]
+
+    def ksw_batch(self, P, w, mat, sc, flag, G, threads=64):
+        n = P["n"]
+        res = np.zeros(n, RES)
+        stride = int((P["qlen"] + P["tlen"]).max()) + 8
+        cig = np.zeros(n * stride, np.uint32)
+        rc = self.lib.emu_ksw_batch(n, P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"],
+                                    np.ascontiguousarray(w, np.int32), 5, mat, sc["q"], sc["e"], sc["q2"], sc["e2"],
+                                    sc["zdrop"], sc["end_bonus"], flag, G, threads, res.ctypes.data_as(C.c_void_p),
+                                    cig.ctypes.data_as(C.c_void_p), stride)
+        assert rc == 0
+        return res, cig.reshape(n, stride)
+
+    def sketch_jobs(self, seqs, shifts, rids, w, k, Z, small, grid=3):
+        buf = b"".join(seqs)
+        lens = np.array([len(s) for s in seqs], np.int32)
+        off = np.zeros(len(seqs), np.int64)
+        off[1:] = np.cumsum(lens[:-1])
+        cap = len(buf) + 16
+        out = np.zeros(2 * cap, np.uint64)
+        oo = np.zeros(len(seqs) + 1, np.int64)
+        self.lib.emu_sketch_jobs(len(seqs), off, lens, np.array(shifts, np.int32), np.array(rids, np.uint32), buf, w, k,
+                                 Z.encode(), len(Z), small, grid, oo, out, cap)
+        return [out[2 * oo[i]:2 * oo[i + 1]].reshape(-1, 2) for i in range(len(seqs))]

@@ -1,0 +1,82 @@
+"""CPU: the device code of the CUDA kernels, compiled for the host against a fiber SIMT emulator, must
+reproduce the oracle.  This checks lane ownership, the shared-memory ring, carries between steps, the
+tag-carrying packed arithmetic, the exact-max reduction and the look-back compaction without a GPU.
+(The GPU parity tests in test_gpu_*.py remain the authority for the real hardware path.)"""
+import numpy as np
+import pytest
+
+import gdiet_b200  # noqa: F401
+from gdiet_b200 import synth
+from oraclelib import EXTZ_FIELDS
+from helpers import pair
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from emulib import Emu
+    return Emu()
+
+
+def _check(emu, oracle, P, w, scn, flag, G):
+    sc = synth.SCORING[scn]
+    mat = synth.score_matrix(sc["a"], sc["b"])
+    res, cig = emu.ksw_batch(P, w, mat, sc, flag, G)
+    for i in range(P["n"]):
+        q, t = pair(P, i)
+        ez, oc = oracle.ksw_extd2(q, t, mat, sc["q"], sc["e"], sc["q2"], sc["e2"], int(w[i]), sc["zdrop"], sc["end_bonus"], flag)
+        mine = {f: int(res[i][f]) for f in EXTZ_FIELDS}
+        assert mine == ez, "pair %d flag %#x G %d" % (i, flag, G)
+        assert np.array_equal(cig[i][:ez["n_cigar"]], oc), "pair %d flag %#x G %d" % (i, flag, G)
+
+
+@pytest.mark.parametrize("flag", [0x08, 0x00, 0x18, 0x0a, 0x40, 0x42, 0x09, 0x80])
+def test_emu_ksw_ragged(emu, oracle, flag):
+    P = synth.ragged_pairs(10, seed=5 + flag, max_len=200)
+    rng = np.random.default_rng(flag)
+    for G, scn in ((4, "sr"), (8, "map-hifi"), (16, "map-ont"), (32, "sr")):
+        w = rng.choice([-1, 5, 10, 20, 33, 37, 100, 150, 400], P["n"]).astype(np.int32)
+        _check(emu, oracle, P, w, scn, flag, G)
+
+
+@pytest.mark.parametrize("G,wv", [(4, 10), (8, 37), (32, 64), (32, 5)])
+def test_emu_ksw_ring_wrap(emu, oracle, G, wv):
+    """narrow uniform band on longer pairs: the column ring wraps many times"""
+    P = synth.ragged_pairs(8, seed=9, max_len=700)
+    w = np.full(P["n"], wv, np.int32)
+    for flag in (0x08, 0x00):
+        _check(emu, oracle, P, w, "map-ont", flag, G)
+
+
+def test_emu_ksw_microbench_shape(emu, oracle):
+    P = synth.ksw_pairs(6, 150, 200, 0.05, seed=3, n_every=2)
+    w = np.full(P["n"], 150, np.int32)
+    for flag in (0x08, 0x00, 0x40):
+        _check(emu, oracle, P, w, "sr", flag, 8)
+
+
+def test_emu_sketch(emu, oracle):
+    rng = np.random.default_rng(3)
+    cfgs = [(21, 11), (19, 19), (15, 10), (28, 8), (17, 30), (11, 9), (12, 5)]
+    pats = ["10", "110", "1110", "100", "11", "101001", "1"]
+    for it in range(14):
+        k, w = cfgs[it % 7]
+        Z = pats[it % 6]
+        small = it % 2
+        if small:
+            lens = [int(rng.integers(len(Z), (256 - 2 * (w - 1)) * len(Z) // Z.count("1"))) for _ in range(10)]
+        else:
+            lens = [int(x) for x in rng.choice([40, 150, 1000, 5000, 9000], 5)]
+        seqs = []
+        for n in lens:
+            c = rng.integers(0, 4, n)
+            if it % 3 == 1:
+                c[rng.random(n) < 0.01] = 4
+            if it % 3 == 2:
+                a = int(rng.integers(0, n))
+                c[a:a + int(rng.integers(1, 40))] = 4
+            seqs.append(bytes(synth.ACGTN[c]))
+        shifts = [int(rng.integers(0, len(Z))) for _ in seqs]
+        got = emu.sketch_jobs(seqs, shifts, list(range(len(seqs))), w, k, Z, small)
+        for i, (s, sh) in enumerate(zip(seqs, shifts)):
+            exp, _ = oracle.mm_sketch3(s, w, k, i, Z, sh, 0)
+            assert np.array_equal(exp, got[i]), (it, i)

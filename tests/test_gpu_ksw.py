@@ -1,0 +1,171 @@
+"""GPU: bit-exact parity of the CUDA DP (called through the C ABI) with the oracle, the committed golden
+vectors of the reference, and size-independent properties at the BASELINE sizes."""
+import os
+
+import numpy as np
+import pytest
+
+import gdiet_b200 as gd
+from gdiet_b200 import synth
+from oraclelib import EXTZ_FIELDS
+from helpers import pair, oracle_batch, assert_batch_equal, params, cigar_spans
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SCORINGS = ["sr", "map-hifi", "map-ont"]
+
+
+def test_golden_vectors_through_batch_abi(ctx):
+    """every golden case (flags x scorings x bands, N, code 7, degenerate lengths), grouped by (flag, scoring)"""
+    g = np.load(os.path.join(GOLD, "ksw_golden.npz"))
+    meta = g["meta"]
+    keys = sorted(set((int(m[0]), int(m[1])) for m in meta))
+    for flag, sci in keys:
+        idx = np.nonzero((meta[:, 0] == flag) & (meta[:, 1] == sci))[0]
+        qs = [g["qbuf"][g["qoff"][i]:g["qoff"][i] + g["qlen"][i]] for i in idx]
+        ts = [g["tbuf"][g["toff"][i]:g["toff"][i] + g["tlen"][i]] for i in idx]
+        P = synth.pack_pairs(qs, ts)
+        w = np.ascontiguousarray(meta[idx, 2], np.int32)
+        for G in (0, 4, 32):
+            ctx.set_option("ksw_group", G)
+            ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"],
+                                                params(synth.SCORING[SCORINGS[sci]], flag), w=w)
+            for k, i in enumerate(idx):
+                mine = [int(ez[k][f]) for f in EXTZ_FIELDS]
+                assert mine == [int(x) for x in g["ez"][i]], "golden case %d flag %#x G %d" % (i, flag, G)
+                exp = g["cigar"][g["cigar_off"][i]:g["cigar_off"][i + 1]]
+                assert np.array_equal(cig[coff[k]:coff[k + 1]], exp), "golden case %d flag %#x G %d" % (i, flag, G)
+    ctx.set_option("ksw_group", 0)
+
+
+@pytest.mark.parametrize("flag", [0x08, 0x00, 0x18, 0x40, 0x48, 0xc2, 0x01, 0x0a, 0x42, 0x80])
+def test_ragged_pairs_vs_oracle(ctx, oracle, flag):
+    P = synth.ragged_pairs(300, seed=100 + flag, max_len=260)
+    rng = np.random.default_rng(flag)
+    w = rng.choice([-1, 5, 10, 20, 33, 37, 100, 150, 400], P["n"]).astype(np.int32)
+    for scn in ("sr", "map-ont"):
+        sc = synth.SCORING[scn]
+        exp = oracle_batch(oracle, P, w, sc, flag)
+        for G in (4, 8, 16, 32):
+            ctx.set_option("ksw_group", G)
+            ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"],
+                                                params(sc, flag), w=w)
+            assert_batch_equal(ez, coff, cig if not (flag & 1) else None, exp, what="flag %#x G %d %s" % (flag, G, scn))
+    ctx.set_option("ksw_group", 0)
+
+
+def test_swapped_gap_pieces_and_qe_seed(ctx, oracle):
+    """q2+e2 < q+e: the kernel must order the pieces but seed H with the caller's q+e (reference quirk)"""
+    P = synth.ragged_pairs(120, seed=31, max_len=200)
+    sc = dict(synth.SCORING["sr"])
+    sc["q"], sc["e"], sc["q2"], sc["e2"] = sc["q2"], sc["e2"], sc["q"], sc["e"]
+    w = np.full(P["n"], 100, np.int32)
+    for flag in (0x08, 0x00):
+        exp = oracle_batch(oracle, P, w, sc, flag)
+        ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"],
+                                            params(sc, flag), w=w)
+        assert_batch_equal(ez, coff, cig, exp)
+
+
+def test_long_banded_pairs_ring_wrap(ctx, oracle):
+    """HiFi/ONT-like shapes at a size the oracle finishes in seconds; the column ring wraps hundreds of times"""
+    for n, qlen, edit, wv, scn in ((6, 3000, 0.08, 200, "map-ont"), (4, 4000, 0.01, 500, "map-hifi")):
+        P = synth.long_pairs(n, qlen, edit, seed=qlen, tlen_extra=0.02)
+        w = np.full(P["n"], wv, np.int32)
+        sc = synth.SCORING[scn]
+        for flag in (0x08, 0x00):
+            exp = oracle_batch(oracle, P, w, sc, flag)
+            for G in (0, 16):
+                ctx.set_option("ksw_group", G)
+                ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"],
+                                                    params(sc, flag), w=w)
+                assert_batch_equal(ez, coff, cig, exp, what="long %d flag %#x" % (qlen, flag))
+    ctx.set_option("ksw_group", 0)
+
+
+def test_chunked_backtrack_arena(ctx, oracle):
+    """a tiny backtrack budget forces many chunks; results must not depend on chunking"""
+    P = synth.ksw_pairs(500, 150, 200, 0.05, seed=3)
+    w = np.full(P["n"], 150, np.int32)
+    sc = synth.SCORING["sr"]
+    ctx.set_option("p_budget_mb", 2)
+    ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], params(sc, 0x08), w=w)
+    assert ctx.stat("ksw_chunks") > 5
+    ctx.set_option("p_budget_mb", 0)
+    ez2, coff2, cig2 = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], params(sc, 0x08), w=w)
+    assert np.array_equal(ez, ez2) and np.array_equal(coff, coff2) and np.array_equal(cig, cig2)
+    idx = list(range(0, 500, 25))
+    assert_batch_equal(ez, coff, cig, oracle_batch(oracle, P, w, sc, 0x08, idx), idx)
+
+
+def test_dropin_symbols_match_oracle(oracle):
+    """ksw_extd2_avx512 / ksw_extd2_sse with the reference's own signature and ksw_extz_t"""
+    P = synth.ragged_pairs(40, seed=77, max_len=220)
+    sc = synth.SCORING["sr"]
+    mat = synth.score_matrix(sc["a"], sc["b"])
+    for i in range(P["n"]):
+        q, t = pair(P, i)
+        flag = [0x08, 0x00, 0x40, 0x01][i % 4]
+        w = [-1, 20, 150][i % 3]
+        exp = oracle.ksw_extd2(q, t, mat, sc["q"], sc["e"], sc["q2"], sc["e2"], w, sc["zdrop"], sc["end_bonus"], flag)
+        for entry in ("ksw_extd2_avx512", "ksw_extd2_sse"):
+            ez, cig = gd.ksw_extd2(q, t, mat, sc["q"], sc["e"], sc["q2"], sc["e2"], w, sc["zdrop"], sc["end_bonus"], flag,
+                                   entry=entry)
+            assert ez == exp[0] and np.array_equal(cig, exp[1]), (i, entry)
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    sc = synth.SCORING["sr"]
+    z = np.zeros(0, np.int32)
+    ez, coff, cig = ctx.ksw_extd2_batch(z, np.zeros(0, np.int64), np.zeros(1, np.uint8), z, np.zeros(0, np.int64),
+                                        np.zeros(1, np.uint8), params(sc, 0x08))
+    assert len(ez) == 0 and coff[0] == 0
+    # qlen == 0 / tlen == 0 pairs return the reset ksw_extz_t (ksw2_extd2_sse.c:75-76)
+    P = synth.pack_pairs([np.zeros(0, np.uint8), np.array([1, 2], np.uint8)], [np.array([1], np.uint8), np.zeros(0, np.uint8)])
+    ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], np.append(P["qbuf"], 0).astype(np.uint8), P["tlen"], P["toff"],
+                                        np.append(P["tbuf"], 0).astype(np.uint8), params(sc, 0x08), w_all=10)
+    for i in range(2):
+        assert ez[i]["score"] == gd.KSW_NEG_INF and ez[i]["n_cigar"] == 0 and ez[i]["max"] == 0 and ez[i]["zdropped"] == 0
+    # mismatch penalty beyond 2(q+e): the reference returns before the DP (ksw2_extd2_sse.c:100)
+    P = synth.ksw_pairs(4, 50, 60, 0.05, seed=1)
+    prm = gd.KswParams(synth.score_matrix(2, 60), 12, 2, 24, 1, 100, 10, 0x08)
+    ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], prm, w_all=50)
+    assert all(int(e["score"]) == gd.KSW_NEG_INF and int(e["n_cigar"]) == 0 for e in ez)
+    with pytest.raises(gd.GdietError):  # unsupported flag is an error, not a silent different answer
+        ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], params(sc, 0x04), w_all=50)
+
+
+def test_baseline_size_properties(ctx, oracle):
+    """Config 2 shape at 200k pairs: (1) every CIGAR spans exactly the aligned query/target ranges
+    (the assert of mm_update_extra, GDiet-ShortReads/align.c:314); (2) identical pairs -> score = a*len,
+    one M op; (3) results independent of batch order (shuffle -> same per-pair records);
+    (4) a strided sample equals the oracle."""
+    n = 200_000
+    P = synth.ksw_pairs_fast(n, 150, 200, 0.05, seed=3)
+    sc = synth.SCORING["sr"]
+    w = np.full(n, 150, np.int32)
+    for flag in (0x08, 0x00):
+        ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], params(sc, flag), w=w)
+        ok = ez["zdropped"] == 0
+        assert ok.mean() > 0.5
+        ops = cig & 0xf
+        lens = (cig >> 4).astype(np.int64)
+        pid = np.repeat(np.arange(n), np.diff(coff))
+        qspan = np.bincount(pid, weights=np.where((ops == 0) | (ops == 1), lens, 0), minlength=n).astype(np.int64)
+        tspan = np.bincount(pid, weights=np.where((ops == 0) | (ops == 2), lens, 0), minlength=n).astype(np.int64)
+        assert np.all(ez["n_cigar"] == np.diff(coff))
+        assert np.all(qspan[ok] == 150) and np.all(tspan[ok] == 200)
+        idx = list(range(0, n, n // 64))
+        assert_batch_equal(ez, coff, cig, oracle_batch(oracle, P, w, sc, flag, idx), idx, what="sample flag %#x" % flag)
+        # order independence
+        perm = np.random.default_rng(1).permutation(n)[:20000]
+        ez2, coff2, cig2 = ctx.ksw_extd2_batch(P["qlen"][perm], P["qoff"][perm], P["qbuf"], P["tlen"][perm], P["toff"][perm],
+                                               P["tbuf"], params(sc, flag), w=w[perm])
+        assert np.array_equal(ez2, ez[perm])
+        for k in range(0, 20000, 997):
+            assert np.array_equal(cig2[coff2[k]:coff2[k + 1]], cig[coff[perm[k]]:coff[perm[k] + 1]])
+    # identical sequences
+    t = synth.random_codes(np.random.default_rng(5), 150 * 1000).reshape(1000, 150)
+    Pi = synth.pack_pairs(list(t), list(t))
+    ez, coff, cig = ctx.ksw_extd2_batch(Pi["qlen"], Pi["qoff"], Pi["qbuf"], Pi["tlen"], Pi["toff"], Pi["tbuf"], params(sc, 0x08), w_all=150)
+    assert np.all(ez["score"] == 300) and np.all(ez["n_cigar"] == 1) and np.all(cig == (150 << 4))

@@ -1,0 +1,75 @@
+"""CPU: the oracle restatement against the committed golden vectors (generated from the unmodified
+reference's GDiet_avx objects by tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oraclelib import EXTZ_FIELDS
+
+import gdiet_b200  # noqa: F401
+from gdiet_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SCORINGS = ["sr", "map-hifi", "map-ont"]
+
+
+def load_ksw_golden():
+    return np.load(os.path.join(GOLD, "ksw_golden.npz"))
+
+
+def load_sketch_golden():
+    return np.load(os.path.join(GOLD, "sketch_golden.npz"))
+
+
+def test_ksw_oracle_matches_golden(oracle):
+    g = load_ksw_golden()
+    n = len(g["qlen"])
+    assert n >= 250
+    for i in range(n):
+        q = g["qbuf"][g["qoff"][i]:g["qoff"][i] + g["qlen"][i]]
+        t = g["tbuf"][g["toff"][i]:g["toff"][i] + g["tlen"][i]]
+        flag, sci, w = (int(x) for x in g["meta"][i])
+        sc = synth.SCORING[SCORINGS[sci]]
+        ez, cig = oracle.ksw_extd2(q, t, synth.score_matrix(sc["a"], sc["b"]), sc["q"], sc["e"], sc["q2"], sc["e2"], w,
+                                   sc["zdrop"], sc["end_bonus"], flag)
+        assert [ez[f] for f in EXTZ_FIELDS] == [int(x) for x in g["ez"][i]], "case %d" % i
+        assert np.array_equal(cig, g["cigar"][g["cigar_off"][i]:g["cigar_off"][i + 1]]), "case %d" % i
+
+
+def test_sketch_oracle_matches_golden(oracle):
+    g = load_sketch_golden()
+    pats = [str(p) for p in g["patterns"]]
+    n = len(g["meta"])
+    assert n >= 200
+    seq_all = g["seq"].tobytes()
+    for i in range(n):
+        kind, k, w, zi, fn, a0, a1 = (int(x) for x in g["meta"][i])
+        seq = seq_all[g["seq_off"][i]:g["seq_off"][i + 1]]
+        exp = g["entries"][g["entries_off"][i]:g["entries_off"][i + 1]]
+        extra = g["extra"][g["extra_off"][i]:g["extra_off"][i + 1]]
+        Z = pats[zi]
+        if fn == 0:
+            got = oracle.mm_sketch(seq, w, k, a0, Z)
+        elif fn == 1:
+            got, ret = oracle.mm_sketch3(seq, w, k, 0, Z, a0, a1)
+            assert ret == int(extra[0]), "case %d ret" % i
+        else:
+            got, counts = oracle.mm_sketch2(seq, w, k, 0, Z, a0 / 1000.0)
+            assert np.array_equal(counts, extra), "case %d counts" % i
+        assert np.array_equal(got, exp), "case %d (fn %d kind %d k %d w %d Z %s)" % (i, fn, kind, k, w, Z)
+
+
+def test_band_cells_closed_forms(oracle):
+    # full band = qlen*tlen; 150x200, w=150 = 28,775
+    assert oracle.band_cells(150, 150, 150) == 22500
+    assert oracle.band_cells(150, 200, 150) == 28775
+    assert oracle.band_cells(10, 10, -1) == 100
+
+
+def test_exact_match(oracle):
+    a = np.array([0, 1, 2, 3, 4, 0, 1], np.uint8)
+    assert oracle.exact_match(a, a.copy()) == 1
+    b = a.copy()
+    b[6] = 2
+    assert oracle.exact_match(a, b) == 0

@@ -28,7 +28,13 @@ GD_DEV uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 GD_DEV uint32_t vmax2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
 GD_DEV uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 GD_DEV uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
-GD_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+GD_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
+{ // raw PRMT: unlike __byte_perm (which masks the selector with 0x7777) this keeps bit 3 of every
+  // selector nibble = "replicate the sign bit of the selected byte"
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+	return r;
+}
 GD_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 GD_DEV uint32_t shfl_idx(uint32_t mask, uint32_t v, int src, int width) { return __shfl_sync(mask, v, src, width); }
 GD_DEV uint32_t shfl_xor(uint32_t mask, uint32_t v, int lm, int width) { return __shfl_xor_sync(mask, v, lm, width); }

@@ -167,12 +167,25 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 		const int nb = h_ncol16(max_qlen, max_tlen, max_w) / 16 - 1; // 16-cell blocks in the widest row
 		G = nb <= 3 ? 4 : nb <= 16 ? 8 : nb <= 32 ? 16 : 32;
 	}
-	const int threads = 128, groups_per_block = threads / G;
-	const size_t smem = (size_t)groups_per_block * geo.group_smem;
-	if (smem > ctx->smem_optin) {
-		ctx->err = "gd_ksw: band too wide for the shared-memory ring of one block";
-		return GD_ERR_ARG;
+	// block shape: as many groups per block as the shared-memory rings allow (128, 64 or 32 threads);
+	// when even one warp's worth of groups does not fit, widen the group (fewer pairs per warp)
+	int threads = 128;
+	for (;;) {
+		const size_t per_warp = (size_t)(32 / G) * geo.group_smem;
+		if (per_warp * 4 <= ctx->smem_optin) threads = 128;
+		else if (per_warp * 2 <= ctx->smem_optin) threads = 64;
+		else if (per_warp <= ctx->smem_optin) threads = 32;
+		else if (G < 32) {
+			G <<= 1;
+			continue;
+		} else {
+			ctx->err = "gd_ksw: band too wide for the shared-memory column ring (needs > 227 KB per pair)";
+			return GD_ERR_ARG;
+		}
+		break;
 	}
+	const int groups_per_block = threads / G;
+	const size_t smem = (size_t)groups_per_block * geo.group_smem;
 	dp_kernel_t kern = pick_kernel(G, right, exact, with_p);
 	GD_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int occ = 0;

@@ -28,6 +28,9 @@ GD_DEV uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 GD_DEV uint32_t vmax2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
 GD_DEV uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 GD_DEV uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+GD_DEV uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); } // max(a+b, c) per half
+GD_DEV int iaddmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }                          // max(a+b, c)
+GD_DEV int imax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 GD_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 { // raw PRMT: unlike __byte_perm (which masks the selector with 0x7777) this keeps bit 3 of every
   // selector nibble = "replicate the sign bit of the selected byte"
@@ -70,6 +73,17 @@ GD_DEV uint32_t vmin2(uint32_t a, uint32_t b)
 	return (uint16_t)(al < bl ? al : bl) | ((uint32_t)(uint16_t)(ah < bh ? ah : bh) << 16);
 }
 GD_DEV uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return vmax2(vmax2(a, b), c); }
+GD_DEV uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c) { return vmax2(vadd2(a, b), c); }
+GD_DEV int iaddmax(int a, int b, int c)
+{
+	int s = (int)((uint32_t)a + (uint32_t)b);
+	return s > c ? s : c;
+}
+GD_DEV int imax3(int a, int b, int c)
+{
+	int m = a > b ? a : b;
+	return m > c ? m : c;
+}
 GD_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 {
 	uint64_t v = ((uint64_t)b << 32) | a;

@@ -13,10 +13,12 @@ static_assert(sizeof(KswResult) == sizeof(gd_extz_t), "result layouts must match
 template <int G, bool RIGHT, bool EXACT, bool WITH_P>
 __global__ void __launch_bounds__(128) gd_ksw_dp_kernel(const KswConsts C, const KswBatch B)
 {
-	extern __shared__ __align__(16) uint8_t gd_smem[];
-	const int tid = threadIdx.x, lane = tid & 31, li = lane & (G - 1);
-	const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1));
-	ksw_group_body<G, RIGHT, EXACT, WITH_P>(C, B, gd_smem + (size_t)(tid / G) * B.group_smem, li, gmask);
+	extern __shared__ __align__(128) uint8_t gd_smem[];
+	const int tid = threadIdx.x;
+	ksw_build_lut(gd_smem, tid, blockDim.x);
+	__syncthreads();
+	uint8_t *warp_smem = gd_smem + GD_KSW_LUT_BYTES + (size_t)(tid >> 5) * (32 / G) * B.group_smem;
+	ksw_warp_body<G, RIGHT, EXACT, WITH_P>(C, B, warp_smem, gd_smem, tid & 31);
 }
 
 // one warp per pair: raw byte codes -> padded arenas
@@ -161,20 +163,25 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 	if (max_w < 0) max_w = std::max(max_qlen, max_tlen);
 	KswGeom geo = ksw_geometry(max_qlen, max_tlen, max_w, exact, with_p);
 
-	// lanes per pair
+	// lanes per pair: one 8-column chunk per lane and step; short rows keep 8 pairs per warp
 	int G = (int)ctx->opt_ksw_group;
 	if (G != 4 && G != 8 && G != 16 && G != 32) {
-		const int nb = h_ncol16(max_qlen, max_tlen, max_w) / 16 - 1; // 16-cell blocks in the widest row
-		G = nb <= 3 ? 4 : nb <= 16 ? 8 : nb <= 32 ? 16 : 32;
+		const int nch = h_ncol16(max_qlen, max_tlen, max_w) / 8; // chunks in the widest row
+		G = nch <= 24 ? 4 : nch <= 64 ? 8 : nch <= 160 ? 16 : 32;
+	}
+	if (geo.ring > GD_KSW_POS_MAX - 32 && exact) {
+		ctx->err = "gd_ksw: band too wide for the exact-max keys (ring > 8158 columns)";
+		return GD_ERR_ARG;
 	}
 	// block shape: as many groups per block as the shared-memory rings allow (128, 64 or 32 threads);
 	// when even one warp's worth of groups does not fit, widen the group (fewer pairs per warp)
 	int threads = 128;
+	const size_t avail = ctx->smem_optin - GD_KSW_LUT_BYTES;
 	for (;;) {
 		const size_t per_warp = (size_t)(32 / G) * geo.group_smem;
-		if (per_warp * 4 <= ctx->smem_optin) threads = 128;
-		else if (per_warp * 2 <= ctx->smem_optin) threads = 64;
-		else if (per_warp <= ctx->smem_optin) threads = 32;
+		if (per_warp * 4 <= avail) threads = 128;
+		else if (per_warp * 2 <= avail) threads = 64;
+		else if (per_warp <= avail) threads = 32;
 		else if (G < 32) {
 			G <<= 1;
 			continue;
@@ -185,7 +192,7 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 		break;
 	}
 	const int groups_per_block = threads / G;
-	const size_t smem = (size_t)groups_per_block * geo.group_smem;
+	const size_t smem = GD_KSW_LUT_BYTES + (size_t)groups_per_block * geo.group_smem;
 	dp_kernel_t kern = pick_kernel(G, right, exact, with_p);
 	GD_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int occ = 0;

@@ -1,26 +1,40 @@
-// gd_ksw.cuh -- batched ksw2 dual-affine banded extension DP for sm_100a.
+// gd_ksw.cuh -- batched ksw2 dual-affine banded extension DP for sm_100a (kernel design v2).
 //
 // Replaces ksw_extd2_sse / ksw_extd2_avx512 (GDiet-ShortReads/ksw2_extd2_sse.c:27-401,
 // GDiet-ShortReads/ksw2_extd2_avx.c:72-915) for whole batches of (query,target) pairs.
 //
-// Mapping.  A *group* of G lanes (G = 4..32, a power of two) owns one pair at a time and walks
-// its anti-diagonals r = 0..qlen+tlen-2.  One *step* of a group updates G/4 consecutive
-// 16-cell blocks of the row; each lane owns 4 consecutive target columns of its block.  The
-// reference's persistent per-column int8 state (u,v,x,y,x2,y2) and its score row s live in
-// shared memory in a ring of R columns; the 16-cell range rounding, the stale score cells and
-// the boundary injections of the reference are reproduced exactly because
-// cells outside the true band leak into later rows.
+// Mapping.  A *group* of G lanes (G = 4..32) owns one pair at a time and walks its anti-diagonals
+// r = 0..qlen+tlen-2.  A row is cut into 8-column *chunks* (aligned to multiples of 8 target
+// columns); one *step* of a group updates G consecutive chunks, one chunk per lane, and the steps
+// of a row run from the highest chunk down to the lowest.  The reference's persistent per-column
+// int8 state (u,v,x,y,x2,y2), its score row s and (exact mode) H live in shared memory in a ring
+// of R columns.  Because chunks are visited in descending order, the previous-row values of the
+// left neighbour column (x[t-1], v[t-1], x2[t-1]) are still in the ring when a lane needs them: no
+// shuffles and no carries between steps; the boundary injection of the reference
+// (ksw2_extd2_sse.c:149-159) is one store into the ring slot of column st-1.  The 16-cell range
+// rounding, the stale score cells and the boundary injections are reproduced exactly (SURVEY.md
+// 8 A2) because cells outside the true band leak into later rows.
 //
 // Arithmetic.  int8 with wrap-around is carried in the HIGH byte of each half of a 32-bit
-// register (two cells per register), so VIADD.16x2 / VIMNMX.S16x2 / VIMNMX3.S16x2 give exact
-// int8 modular add and signed compare on two cells per instruction.  The LOW byte of each half
-// carries a small tag (which of H,E,F,E~,F~ a value belongs to); the 5-way max therefore
-// returns the arg-max in its low byte for free, with exactly the reference's tie order
-// (strict '>' for left-aligned gaps, '>=' with KSW_EZ_RIGHT).
+// register (two cells per register), so VIADD.16x2 / VIMNMX.S16x2 / VIMNMX3.S16x2 / VIADDMNMX.S16x2
+// give exact int8 modular add and signed compare on two cells per instruction.  The LOW byte of
+// each half carries a tag (which of H,E,F,E~,F~ a value belongs to); the 5-way max therefore
+// returns the arg-max in its low byte for free, with exactly the reference's tie order (strict
+// '>' for left-aligned gaps, '>=' with KSW_EZ_RIGHT).  Inside a chunk the 8 columns c0..c7 sit in
+// four registers as (c0,c4) (c1,c5) (c2,c6) (c3,c7), so "shift by one column" is ONE byte permute
+// per state array; every per-chunk array in shared memory and the backtrack bytes use the same
+// order (position of column j: ((j&3)<<1)|(j>>2)).
+//
+// Exact mode (no KSW_EZ_APPROX_MAX).  H[t] (int32) is updated for the whole chunk; the row maximum
+// with the reference's 4-lane tie order is one 32-bit key per cell: (score relative to the
+// previous row's maximum, clamped) << 16 | priority of the column, reduced with VIMNMX3.  The
+// column en0 and the <= 3 columns of the scalar tail of the reference's scan get their update from
+// four dedicated lanes after the chunk sweep; sentinels keep them (and the dead columns left and
+// right of [st0,en0]) out of the bulk maximum.  Rows the clamped keys cannot represent fall back
+// to a literal restatement of the scan.
 //
 // Backtrack.  One byte per cell, same bit layout as ksw2.h:127-130, written straight to HBM as
-// one 32-bit store per lane-step (a group step writes 4*G contiguous bytes); the CIGAR is
-// produced by gd_ksw_traceback_kernel, one thread per pair.
+// one 8-byte store per lane-step; the CIGAR is produced by gd_ksw_traceback_kernel.
 #pragma once
 #include "gd_common.cuh"
 
@@ -36,6 +50,10 @@ enum {
 	KSW_F_REV_CIGAR = 0x80
 };
 #define GD_KSW_NEG_INF (-0x40000000)
+#define GD_KSW_REL_FLOOR (-30000) // exact-max keys: scores are compared relative to the previous row's maximum
+#define GD_KSW_POS_MAX 8190       // exact-max keys: 13-bit column position inside the live window
+#define GD_KSW_LUT_BYTES 1280     // per-block lookup tables at the start of shared memory
+#define GD_KSW_QFRONT 16          // zero bytes in front of the reversed query
 
 // Per-pair result record (device + host). First 11 ints mirror ksw_extz_t (ksw2.h:31-40).
 struct KswResult {
@@ -58,6 +76,7 @@ struct KswConsts {
 	int32_t long_thres, long_diff;
 	int32_t zdrop, end_bonus, flag;
 	int32_t degenerate;          // m<=1 or -min(mat) > 2(q+e): every call returns the reset ez
+	int32_t force_slow_max;      // test hook: always take the literal row-max scan (exact mode)
 };
 
 // One launch works on pairs [base, base+n) of the caller's batch ("chunk"); the packed sequence
@@ -66,9 +85,9 @@ struct KswBatch {
 	int32_t n, base;
 	const int32_t *qlen, *tlen, *w; // per pair (global index); w may be NULL -> w_all
 	int32_t w_all;
-	const uint8_t *tpk;  // target codes, zero padded; pair i at tpk + i*t_stride (16-byte aligned)
-	const uint8_t *qpk;  // reversed query, N(4)->8; pair i: qpk + i*q_stride + 16 is element 0,
-	                     // 16 zero bytes in front and >= 32 behind
+	const uint8_t *tpk;  // target codes, zero padded, 8-column chunks in strided order; pair i at tpk + i*t_stride
+	const uint8_t *qpk;  // reversed query, N(4)->8; pair i: qpk + i*q_stride + GD_KSW_QFRONT is element 0,
+	                     // GD_KSW_QFRONT zero bytes in front and >= 48 behind
 	int32_t t_stride, q_stride;
 	uint8_t *p;          // backtrack arena, pair i at p + i*p_stride
 	int64_t p_stride;
@@ -80,6 +99,7 @@ struct KswBatch {
 
 GD_DEV uint32_t pack16(int v) { return ((uint32_t)(v & 0xff) << 8) | ((uint32_t)(v & 0xff) << 24); }
 GD_DEV int hi8(uint32_t h16) { return (int)(int8_t)(h16 >> 8); } // value of a 16-bit cell image
+GD_DEV int chunk_pos(int j) { return ((j & 3) << 1) | ((j >> 2) & 1); } // place of column j inside its chunk
 
 GD_DEV int gap_delta(int r, const KswConsts &C)
 { // first-row / first-column difference (ksw2_extd2_sse.c:158,162); int8 wrap applied by the caller
@@ -88,8 +108,8 @@ GD_DEV int gap_delta(int r, const KswConsts &C)
 
 // Two cells of the recurrence (ksw2_extd2_sse.c:38-66,228-274). All operands are 16x2 images.
 // In: s (tag TS), xt1/x2t1 (left neighbours, tags TA/TA2), vt1, ut (no tag), y/y2 (tags TB/TB2).
-// Out: new u,v,x,y,x2,y2 and the word zt whose low bytes hold the arg-max tag, plus the four
-// "positive" words whose bit 15/31 is the continuation flag.
+// Out: new u,v,x,y,x2,y2, the word zt whose low bytes hold the arg-max tag, and four words whose
+// bit 15/31 is the continuation flag of E,F,E~,F~.
 template <bool RIGHT>
 GD_DEV void cell2(const KswConsts &C, uint32_t s, uint32_t xt1, uint32_t vt1, uint32_t x2t1, uint32_t ut, uint32_t &y,
                   uint32_t &y2, uint32_t &u_new, uint32_t &v_new, uint32_t &x_new, uint32_t &x2_new, uint32_t &zt,
@@ -97,34 +117,34 @@ GD_DEV void cell2(const KswConsts &C, uint32_t s, uint32_t xt1, uint32_t vt1, ui
 {
 	uint32_t a = vadd2(xt1, vt1), b = vadd2(y, ut), a2 = vadd2(x2t1, vt1), b2 = vadd2(y2, ut);
 	zt = vmax3(vmax3(s, a, b), a2, b2);
-	uint32_t z = vmin2(zt & 0xff00ff00u, C.MCH16);
-	uint32_t z1 = vadd2(z, 0x00010001u);
+	const uint32_t z = vmin2(zt & 0xff00ff00u, C.MCH16);
+	const uint32_t z1 = vadd2(z, 0x00010001u);
 	u_new = vadd2(z1, ~vt1); // z - v[t-1]
 	v_new = vadd2(z1, ~ut);  // z - u[t]
-	uint32_t nz = ~z;
-	uint32_t nzq = vadd2(nz, C.Q1), nzq2 = vadd2(nz, C.Q21); // q - z, q2 - z
-	a = vadd2(a, nzq), b = vadd2(b, nzq), a2 = vadd2(a2, nzq2), b2 = vadd2(b2, nzq2);
-	uint32_t ma = vmax2(a, C.TA), mb = vmax2(b, C.TB), ma2 = vmax2(a2, C.TA2), mb2 = vmax2(b2, C.TB2);
+	const uint32_t nz = ~z;
+	const uint32_t nzq = vadd2(nz, C.Q1), nzq2 = vadd2(nz, C.Q21); // q - z, q2 - z
+	uint32_t ma, mb, ma2, mb2;
 	if (!RIGHT) { // continuation iff value > 0  <=> high byte of max(value,0) >= 1
+		ma = vaddmax2(a, nzq, C.TA), mb = vaddmax2(b, nzq, C.TB), ma2 = vaddmax2(a2, nzq2, C.TA2), mb2 = vaddmax2(b2, nzq2, C.TB2);
 		fa = ma + 0x7f007f00u, fb = mb + 0x7f007f00u, fa2 = ma2 + 0x7f007f00u, fb2 = mb2 + 0x7f007f00u;
 	} else { // continuation iff value >= 0 <=> sign bit clear
+		a = vadd2(a, nzq), b = vadd2(b, nzq), a2 = vadd2(a2, nzq2), b2 = vadd2(b2, nzq2);
+		ma = vmax2(a, C.TA), mb = vmax2(b, C.TB), ma2 = vmax2(a2, C.TA2), mb2 = vmax2(b2, C.TB2);
 		fa = ~a, fb = ~b, fa2 = ~a2, fb2 = ~b2;
 	}
 	x_new = vadd2(ma, C.NEGQE), y = vadd2(mb, C.NEGQE), x2_new = vadd2(ma2, C.NEGQE2), y2 = vadd2(mb2, C.NEGQE2);
 }
 
-// 4 ksw2 backtrack bytes from the per-register words of a lane (A = cells 0,1; B = cells 2,3).
+// 4 ksw2 backtrack bytes from two registers' worth of cells (A = (ca,ca+4), B = (cb,cb+4)); the
+// byte order is (ca, ca+4, cb, cb+4), i.e. the strided chunk order.
 GD_DEV uint32_t make_dir4(const KswConsts &C, uint32_t ztA, uint32_t ztB, uint32_t faA, uint32_t faB, uint32_t fbA,
                           uint32_t fbB, uint32_t fa2A, uint32_t fa2B, uint32_t fb2A, uint32_t fb2B)
-{
-	uint32_t FA = prmt(faA, faB, 0x7531), FB = prmt(fbA, fbB, 0x7531);
-	uint32_t FA2 = prmt(fa2A, fa2B, 0x7531), FB2 = prmt(fb2A, fb2B, 0x7531);
-	uint32_t TG = prmt(ztA, ztB, 0x6420);
-	uint32_t d = (TG & 0x07070707u) ^ C.TAGX;
-	d |= (FA >> 4) & 0x08080808u;
-	d |= (FB >> 3) & 0x10101010u;
-	d |= (FA2 >> 2) & 0x20202020u;
-	d |= (FB2 >> 1) & 0x40404040u;
+{ // selector 0xfdb9: sign-replicated bytes 1,3 of A then 1,3 of B -> 0xff where the flag bit is set
+	uint32_t d = (prmt(ztA, ztB, 0x6420) & 0x07070707u) ^ C.TAGX;
+	d |= prmt(faA, faB, 0xfdb9) & 0x08080808u;
+	d |= prmt(fbA, fbB, 0xfdb9) & 0x10101010u;
+	d |= prmt(fa2A, fa2B, 0xfdb9) & 0x20202020u;
+	d |= prmt(fb2A, fb2B, 0xfdb9) & 0x40404040u;
 	return d;
 }
 
@@ -160,318 +180,453 @@ GD_DEV int ksw_ncol16(int qlen, int tlen, int w)
 	return ((n + 15) / 16 + 1) * 16;
 }
 
-// Shared-memory view of one group's column ring.
-struct Ring {
-	uint16_t *u, *v, *x, *y, *x2, *y2; // 16-bit cell images, R entries each
-	uint8_t *s;                        // score row bytes
-	int32_t *H;                        // exact-max scores (EXACT mode only)
-	int R;
-};
-GD_DEV Ring ring_view(uint8_t *base, int R, bool exact)
+// Shared memory of one group: a ring of NR = R/8 chunk records followed by the staged sequences.
+// One record holds everything the sweep needs for 8 columns, so a lane-step addresses it with
+// immediate offsets: 16-bit cell images of u,v,x,y,x2,y2 (6 x 16 B, chunk-strided order), the score
+// bytes (8 B, chunk-strided), 8 B padding, and in exact mode H (8 x int32, natural column order).
+// Record sizes 112 / 144 B make the four lanes of a group, and the two groups that share a 128-bit
+// access phase, hit disjoint banks.
+enum { REC_U = 0, REC_V = 16, REC_X = 32, REC_Y = 48, REC_X2 = 64, REC_Y2 = 80, REC_S = 96, REC_H = 112 };
+template <bool EXACT> struct RecSize { enum { value = EXACT ? 144 : 112 }; };
+static inline int ksw_group_smem_bytes(int R, bool exact, int seq_bytes)
 {
-	Ring g;
-	g.R = R;
-	g.u = (uint16_t *)base, g.v = g.u + R, g.x = g.v + R, g.y = g.x + R, g.x2 = g.y + R, g.y2 = g.x2 + R;
-	g.s = (uint8_t *)(g.y2 + R);
-	g.H = exact ? (int32_t *)(g.s + R) : 0;
-	return g;
-}
-static inline int ksw_group_smem_bytes(int R, bool exact)
-{
-	int b = R * 13 + (exact ? R * 4 : 0);
-	b = (b + 127) / 128 * 128 + 64; // == 64 (mod 128): two groups of a half-warp hit disjoint banks
+	int b = (R / 8) * (exact ? 144 : 112) + seq_bytes;
+	b = (b + 127) / 128 * 128 + 64; // == 64 (mod 128): two groups sharing a 128-bit access phase hit disjoint banks
 	return b;
 }
 
-GD_DEV int wrap(int slot, int R) { return slot >= R ? slot - R : slot; }
-
-GD_DEV uint2 lds2(const uint16_t *p) { return *(const uint2 *)p; }
-GD_DEV void sts2(uint16_t *p, uint32_t a, uint32_t b)
+// Per-block lookup tables (first GD_KSW_LUT_BYTES of shared memory):
+//   [0,1152)    uint2 fresh[16][9]: byte masks (chunk-strided order) of the columns j of a chunk with lo <= j < hi
+//   [1152,1216) uint32 pk[4][4]:    exact-max priority constants of register k for c0 = (-st0)&3
+GD_DEV void ksw_build_lut(uint8_t *lut, int tid, int nthreads)
 {
-	uint2 v;
-	v.x = a, v.y = b;
-	*(uint2 *)p = v;
+	for (int i = tid; i < 144; i += nthreads) {
+		const int lo = i / 9, hi = i % 9;
+		uint32_t w0 = 0, w1 = 0;
+		for (int j = 0; j < 8; ++j)
+			if (j >= lo && j < hi) {
+				const int p = chunk_pos(j);
+				if (p < 4) w0 |= 0xffu << (8 * p);
+				else w1 |= 0xffu << (8 * (p - 4));
+			}
+		uint2 m;
+		m.x = w0, m.y = w1;
+		((uint2 *)lut)[i] = m;
+	}
+	for (int i = tid; i < 16; i += nthreads) {
+		const int c0 = i >> 2, k = i & 3;
+		const uint32_t a = (0x8000u | (uint32_t)(3 - ((k + c0) & 3)) << 13) + (uint32_t)(GD_KSW_POS_MAX - k);
+		((uint32_t *)(lut + 1152))[i] = a | ((a - 4) << 16);
+	}
 }
 
-// 64-bit key used by the exact-max row scan: larger score wins; ties resolved exactly like the
-// 4-lane SSE scan of ksw2_extd2_sse.c:327-357: en0 first, then SIMD lane (t-st0)%4, then t, then the scalar tail.
-GD_DEV long long hkey(int H, uint32_t prio) { return (long long)(((unsigned long long)(uint32_t)H << 32) | prio); }
+GD_DEV int wrap(int k, int n) { return k >= n ? k - n : k; }
 
-template <int G, bool RIGHT, bool EXACT, bool WITH_P>
-GD_DEV void ksw_group_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_group, int li, uint32_t gmask)
+// Record of the column at distance d = t - st from the first column of the row's 16-aligned range
+// (d may be -1: the left-boundary column).  st_rec is the ring position of the record that holds column st.
+GD_DEV uint8_t *col_rec(uint8_t *ring, int rec_bytes, int NR, int st_rec, int d)
 {
-	const int BPS = G / 4; // 16-cell blocks per step
-	const int sub = li >> 2, c4 = (li & 3) * 4;
-	Ring g = ring_view(smem_group, B.ring, EXACT);
-	const int R = g.R;
+	int k = st_rec + (d >> 3);
+	if (k >= NR) k -= NR;
+	if (k < 0) k += NR;
+	return ring + k * rec_bytes;
+}
+GD_DEV uint16_t *col_hw(uint8_t *ring, int rec_bytes, int NR, int st_rec, int d, int arr)
+{ // 16-bit cell image of one column in state array `arr` (REC_U .. REC_Y2)
+	return (uint16_t *)(col_rec(ring, rec_bytes, NR, st_rec, d) + arr + 2 * chunk_pos(d & 7));
+}
+GD_DEV int32_t *col_H(uint8_t *ring, int rec_bytes, int NR, int st_rec, int d)
+{
+	return (int32_t *)(col_rec(ring, rec_bytes, NR, st_rec, d) + REC_H + 4 * (d & 7));
+}
+
+// Literal restatement of the row-maximum scan (ksw2_extd2_sse.c:327-357) over the updated H row:
+// only used when the relative 16-bit keys of the fast path cannot represent a row (never on real data).
+GD_DEV void row_max_literal(uint8_t *ring, int rec_bytes, int NR, int st_rec, int st, int st0, int en0, int &max_H,
+                            int &max_t)
+{
+	const int en1 = st0 + ((en0 - st0) & ~3);
+	max_H = *col_H(ring, rec_bytes, NR, st_rec, en0 - st), max_t = en0;
+	int HH[4], tt[4];
+	for (int i = 0; i < 4; ++i) HH[i] = max_H, tt[i] = max_t;
+	for (int t = st0; t < en1; t += 4)
+		for (int i = 0; i < 4; ++i) {
+			const int h = *col_H(ring, rec_bytes, NR, st_rec, t + i - st);
+			if (h > HH[i]) HH[i] = h, tt[i] = t;
+		}
+	for (int i = 0; i < 4; ++i)
+		if (max_H < HH[i]) max_H = HH[i], max_t = tt[i] + i;
+	for (int t = en1; t < en0; ++t) {
+		const int h = *col_H(ring, rec_bytes, NR, st_rec, t - st);
+		if (h > max_H) max_H = h, max_t = t;
+	}
+}
+
+GD_DEV uint4 rep4(uint32_t v)
+{
+	uint4 q;
+	q.x = q.y = q.z = q.w = v;
+	return q;
+}
+
+// One warp, 32/G pairs at a time.  All control flow is warp-uniform (every loop runs for the
+// maximum trip count over the groups of the warp, per-lane work is predicated), so every barrier
+// and vote uses the full mask.  A group that finishes its pair fetches the next one at once.
+template <int G, bool RIGHT, bool EXACT, bool WITH_P>
+GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_warp, const uint8_t *lut, int lane)
+{
+	const uint32_t FULL = 0xffffffffu;
+	const int REC = RecSize<EXACT>::value;
+	const int li = lane & (G - 1), leader = lane & ~(G - 1);
+	uint8_t *const ring = smem_warp + (size_t)(lane / G) * B.group_smem;
+	const int NR = B.ring >> 3;
+	uint8_t *const tsm = ring + NR * REC, *const qsm = tsm + B.t_stride;
+	const uint2 *lut_fresh = (const uint2 *)lut;
+	const uint32_t *lut_pk = (const uint32_t *)(lut + 1152);
+
+	// ---- per-group state (identical in all lanes of a group) ----
+	bool have = false, done = false;
+	int pair = 0, qlen = 0, tlen = 0, w = 0, T16 = 0, nblk_t = 0, ncol16 = 0, nrows = 0;
+	uint8_t *prow = 0; // backtrack row pointer of the current row
+	int r = 0, rows_exec = 0, last_st = -1, last_en = -1, st_rec = 0, st_cur = 0, init_hi = 0;
+	int H0 = 0, H0_t = 0;                   // approx mode
+	int Mprev = 0, Hleft = 0, st0_prev = 0; // exact mode
+	KswResult res;
+	res.max = 0, res.zdropped = 0, res.max_q = res.max_t = res.mqe_t = res.mte_q = -1;
+	res.score = res.mqe = res.mte = GD_KSW_NEG_INF, res.n_cigar = 0, res.reach_end = 0;
+	res.tb_i = res.tb_j = -1, res.rows_done = 0, res.pad0 = res.pad1 = 0;
 
 	for (;;) {
-		int lp = 0; // chunk-local pair number
-		if (li == 0) lp = atomic_add(B.ticket, 1);
-		lp = (int)shfl_idx(gmask, (uint32_t)lp, 0, G);
-		if (lp >= B.n) break;
-		const int pair = B.base + lp;
-
-		const int qlen = B.qlen[pair], tlen = B.tlen[pair];
-		int w = B.w ? B.w[pair] : B.w_all;
-		KswResult res;
-		res.max = 0, res.zdropped = 0, res.max_q = res.max_t = res.mqe_t = res.mte_q = -1;
-		res.score = res.mqe = res.mte = GD_KSW_NEG_INF, res.n_cigar = 0, res.reach_end = 0;
-		res.tb_i = res.tb_j = -1, res.rows_done = 0, res.pad0 = res.pad1 = 0;
-		if (C.degenerate || qlen <= 0 || tlen <= 0) {
-			if (li == 0) B.res[pair] = res;
-			continue;
+		// ================= fetch: groups without a pair take the next ticket =================
+		const bool need = !have && !done;
+		if (ballot(FULL, need)) {
+			int lp = 0;
+			if (need && li == 0) lp = atomic_add(B.ticket, 1);
+			lp = (int)shfl_idx(FULL, (uint32_t)lp, leader, 32);
+			bool fresh = false;
+			const uint8_t *tpk = 0, *qpk = 0;
+			if (need) {
+				if (lp >= B.n) done = true;
+				else {
+					pair = B.base + lp;
+					qlen = B.qlen[pair], tlen = B.tlen[pair];
+					w = B.w ? B.w[pair] : B.w_all;
+					res.max = 0, res.zdropped = 0, res.max_q = res.max_t = res.mqe_t = res.mte_q = -1;
+					res.score = res.mqe = res.mte = GD_KSW_NEG_INF, res.n_cigar = 0, res.reach_end = 0;
+					res.tb_i = res.tb_j = -1, res.rows_done = 0;
+					if (C.degenerate || qlen <= 0 || tlen <= 0) {
+						if (li == 0) B.res[pair] = res; // reset record, ksw2_extd2_sse.c:75-76,100
+					} else {
+						if (w < 0) w = imax(tlen, qlen);
+						T16 = (tlen + 15) & ~15, nblk_t = T16 >> 4;
+						ncol16 = ksw_ncol16(qlen, tlen, w);
+						nrows = qlen + tlen - 1;
+						tpk = B.tpk + (size_t)lp * B.t_stride;
+						qpk = B.qpk + (size_t)lp * B.q_stride;
+						prow = WITH_P ? B.p + (size_t)lp * B.p_stride : 0;
+						r = 0, rows_exec = 0, last_st = last_en = -1, st_rec = 0, st_cur = 0, init_hi = 0;
+						H0 = 0, H0_t = 0;
+						Mprev = -C.qe_seed, Hleft = GD_KSW_NEG_INF, st0_prev = 0;
+						have = true, fresh = true;
+					}
+				}
+			}
+			// stage the padded sequences of fresh pairs (strides are launch-uniform); the previous
+			// pair's readers are past their last row (every lane of the warp is here)
+			{
+				const int nt = B.t_stride >> 2, nq = B.q_stride >> 2;
+				for (int i = li; i < nt + nq; i += G)
+					if (fresh) {
+						if (i < nt) ((uint32_t *)tsm)[i] = ((const uint32_t *)tpk)[i];
+						else ((uint32_t *)qsm)[i - nt] = ((const uint32_t *)qpk)[i - nt];
+					}
+			}
+			sync_warp(FULL);
+			if (!ballot(FULL, have)) break; // nothing left anywhere in this warp
 		}
-		if (w < 0) w = imax(tlen, qlen);
-		const int T16 = (tlen + 15) & ~15, nblk_t = T16 >> 4;
-		const int ncol16 = ksw_ncol16(qlen, tlen, w);
-		const uint8_t *tpk = B.tpk + (size_t)lp * B.t_stride;
-		const uint8_t *qpk = B.qpk + (size_t)lp * B.q_stride + 16; // qpk[j] = mapped query[qlen-1-j]
-		uint8_t *prow = WITH_P ? B.p + (size_t)lp * B.p_stride : 0;
-		const int nrows = qlen + tlen - 1;
-
-		int last_st = -1, last_en = -1;
-		int st_slot = 0;   // ring slot of column `st_cur`
-		int st_cur = 0;
-		int init_hi = 0;   // blocks [0, init_hi) have been initialised in the ring
-		int H0 = 0, H0_t = 0;
-		int r, rows_exec = 0;
-		sync_warp(gmask); // previous pair's readers are done with the ring
-
-		for (r = 0; r < nrows; ++r) {
-			Bounds bd;
-			if (!row_bounds(r, qlen, tlen, w, bd)) {
-				res.zdropped = 1;
-				break;
+		// ================= one anti-diagonal for every group that has a pair =================
+		bool active = have, finish = false;
+		Bounds bd;
+		bd.st0 = bd.en0 = bd.st = 0, bd.en = 15;
+		if (active && !row_bounds(r, qlen, tlen, w, bd)) {
+			res.zdropped = 1; // band closed, ksw2_extd2_sse.c:142-145
+			active = false, finish = true;
+			bd.st0 = bd.en0 = bd.st = 0, bd.en = 15;
+		}
+		const int st = bd.st, en = bd.en, st0 = bd.st0, en0 = bd.en0;
+		int fe = 16; // score row is rewritten on [st0, fe)
+		const int en1 = st0 + ((en0 - st0) & ~3); // exact mode: end of the 4-lane part of the row scan
+		// exact mode: cells handled outside the bulk update (lanes 0..2: scan tail, lane 3: column en0)
+		int sp_t = -1, sp_h = 0;
+		// ---- phase A: ring bookkeeping, boundary injections ----
+		if (active) {
+			if (st != st_cur) st_rec = wrap(st_rec + ((st - st_cur) >> 3), NR), st_cur = st;
+			fe = imin(st0 + (((en0 - st0) >> 4) + 1) * 16, T16);
+			// The block that enters the window gets the reference's initial values (its memset / kcalloc).
+			// en0 grows by at most one per row, so at most one block enters, and none of this row's
+			// single-column patches below can fall into it (they touch columns <= en0|15) except on row 0.
+			const int bneed = imin((en0 + 15) >> 4, nblk_t - 1);
+			if (init_hi <= bneed) {
+				if (li < 2) {
+					uint8_t *rc = col_rec(ring, REC, NR, st_rec, init_hi * 16 + li * 8 - st);
+					*(uint4 *)(rc + REC_U) = rep4(C.INIT_U), *(uint4 *)(rc + REC_V) = rep4(C.INIT_U);
+					*(uint4 *)(rc + REC_X) = rep4(C.INIT_X), *(uint4 *)(rc + REC_Y) = rep4(C.INIT_Y);
+					*(uint4 *)(rc + REC_X2) = rep4(C.INIT_X2), *(uint4 *)(rc + REC_Y2) = rep4(C.INIT_Y2);
+					uint2 z2;
+					z2.x = z2.y = 0;
+					*(uint2 *)(rc + REC_S) = z2;
+					if (EXACT)
+						*(uint4 *)(rc + REC_H) = rep4((uint32_t)GD_KSW_NEG_INF), *(uint4 *)(rc + REC_H + 16) = rep4((uint32_t)GD_KSW_NEG_INF);
+				}
+				++init_hi;
 			}
-			const int st = bd.st, en = bd.en, st0 = bd.st0, en0 = bd.en0;
-			if (st != st_cur) { // st only ever advances, by exactly 16
-				st_slot = wrap(st_slot + (st - st_cur), R);
-				st_cur = st;
+		}
+		if (ballot(FULL, active && r == 0)) sync_warp(FULL); // row 0 patches column 0 of the block initialised just above
+		if (active) {
+			if (en >= r && li == G - 1) { // ksw2_extd2_sse.c:160-163
+				*col_hw(ring, REC, NR, st_rec, r - st, REC_Y) = (uint16_t)(C.INIT_Y & 0xffff);
+				*col_hw(ring, REC, NR, st_rec, r - st, REC_Y2) = (uint16_t)(C.INIT_Y2 & 0xffff);
+				*col_hw(ring, REC, NR, st_rec, r - st, REC_U) = (uint16_t)((gap_delta(r, C) & 0xff) << 8);
 			}
-			// ---- phase A: ring initialisation of blocks that enter, boundary stores, score row ----
-			{
-				int bneed = imin((en0 + 15) >> 4, nblk_t - 1);
-				const bool grow = init_hi <= bneed;
-				while (init_hi <= bneed) { // lanes 0..3 of the group write one 16-cell block
-					if (li < 4) {
-						int slot = wrap(st_slot + (init_hi * 16 - st) + li * 4, R);
-						sts2(g.u + slot, C.INIT_U, C.INIT_U);
-						sts2(g.v + slot, C.INIT_U, C.INIT_U);
-						sts2(g.x + slot, C.INIT_X, C.INIT_X);
-						sts2(g.y + slot, C.INIT_Y, C.INIT_Y);
-						sts2(g.x2 + slot, C.INIT_X2, C.INIT_X2);
-						sts2(g.y2 + slot, C.INIT_Y2, C.INIT_Y2);
-						*(uint32_t *)(g.s + slot) = 0;
-						if (EXACT) {
-							g.H[slot] = GD_KSW_NEG_INF, g.H[slot + 1] = GD_KSW_NEG_INF;
-							g.H[slot + 2] = GD_KSW_NEG_INF, g.H[slot + 3] = GD_KSW_NEG_INF;
-						}
-					}
-					++init_hi;
-				}
-				if (grow) sync_warp(gmask);
-				if (en >= r && li == G - 1) { // ksw2_extd2_sse.c:160-163
-					int slot = wrap(st_slot + (r - st), R);
-					g.y[slot] = (uint16_t)(C.INIT_Y & 0xffff);
-					g.y2[slot] = (uint16_t)(C.INIT_Y2 & 0xffff);
-					g.u[slot] = (uint16_t)((gap_delta(r, C) & 0xff) << 8);
-				}
-				// score row over [st0, fe): ksw2_extd2_sse.c:166-180 extent, AVX-512 scoring rule
-				const int fe = imin(st0 + (((en0 - st0) >> 4) + 1) * 16, T16);
-				const int qshift = qlen - 1 - r; // qpk index of column t is qshift + t
-				for (int t4 = (st0 & ~3) + li * 4; t4 < fe; t4 += G * 4) {
-					uint32_t tc = *(const uint32_t *)(tpk + t4);
-					int qi = qshift + t4 + 16; // >= 13; the arena has 16 zero bytes in front of qpk[0]
-					const uint32_t *qw = (const uint32_t *)(qpk - 16 + (qi & ~3));
-					uint32_t qc = funnel_r(qw[0], qw[1], (uint32_t)(qi & 3) * 8);
-					uint32_t sc = score4(C, tc, qc);
-					int slot = wrap(st_slot + (t4 - st), R);
-					uint32_t *sp = (uint32_t *)(g.s + slot);
-					int lo = st0 - t4, hi = fe - t4; // valid bytes: lo <= b < hi
-					if (lo > 0 || hi < 4) {
-						uint32_t m = 0xffffffffu;
-						if (lo > 0) m &= 0xffffffffu << (8 * lo);
-						if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
-						sc = (sc & m) | (*sp & ~m);
-					}
-					*sp = sc;
-				}
+			if (li == 0 && !(st > 0 && st - 1 >= last_st && st - 1 <= last_en)) {
+				// left boundary (ksw2_extd2_sse.c:149-159): lives in the ring slot of column st-1,
+				// which holds the previous row's values when that column was in its range
+				*col_hw(ring, REC, NR, st_rec, -1, REC_X) = (uint16_t)(C.INIT_X & 0xffff);
+				*col_hw(ring, REC, NR, st_rec, -1, REC_X2) = (uint16_t)(C.INIT_X2 & 0xffff);
+				*col_hw(ring, REC, NR, st_rec, -1, REC_V) =
+				    st > 0 ? (uint16_t)(C.INIT_U & 0xffff) : (uint16_t)((gap_delta(r, C) & 0xff) << 8);
 			}
-			sync_warp(gmask);
-			// ---- phase B: core update over blocks st/16 .. en/16 ----
-			{
-				// left boundary (ksw2_extd2_sse.c:149-159): becomes "previous send" of lane G-1
-				uint32_t prev_xv, prev_x2;
-				if (st > 0) {
-					if (st - 1 >= last_st && st - 1 <= last_en) {
-						int slot = st_slot == 0 ? R - 1 : st_slot - 1;
-						prev_xv = (uint32_t)g.x[slot] | ((uint32_t)g.v[slot] << 16);
-						prev_x2 = (uint32_t)g.x2[slot] << 16;
-					} else {
-						prev_xv = (C.INIT_X & 0xffffu) | (C.INIT_U << 16);
-						prev_x2 = C.INIT_X2 << 16;
-					}
-				} else {
-					prev_xv = (C.INIT_X & 0xffffu) | ((uint32_t)(gap_delta(r, C) & 0xff) << 24);
-					prev_x2 = C.INIT_X2 << 16;
-				}
-				const int nblk = ((en - st) >> 4) + 1;
-				uint8_t *pr = WITH_P ? prow + (size_t)r * ncol16 : 0;
-				for (int b0 = 0; b0 < nblk; b0 += BPS) {
-					const int blk = b0 + sub;
-					const bool active = blk < nblk;
-					const int slot = wrap(st_slot + blk * 16 + c4, R);
-					uint2 U, V, X, Y, X2, Y2;
-					uint32_t sw = 0;
-					if (active) {
-						U = lds2(g.u + slot), V = lds2(g.v + slot), X = lds2(g.x + slot), Y = lds2(g.y + slot);
-						X2 = lds2(g.x2 + slot), Y2 = lds2(g.y2 + slot);
-						sw = *(const uint32_t *)(g.s + slot);
-					} else {
-						U.x = U.y = V.x = V.y = X.x = X.y = Y.x = Y.y = X2.x = X2.y = Y2.x = Y2.y = 0;
-					}
-					// neighbour exchange: lane li needs x,v,x2 of column t-1 (old values)
-					uint32_t send_xv = prmt(X.y, V.y, 0x7632), send_x2 = X2.y;
-					uint32_t dep_xv = (li == G - 1) ? prev_xv : send_xv, dep_x2 = (li == G - 1) ? prev_x2 : send_x2;
-					uint32_t rxv = shfl_idx(gmask, dep_xv, (li + G - 1) & (G - 1), G);
-					uint32_t rx2 = shfl_idx(gmask, dep_x2, (li + G - 1) & (G - 1), G);
-					prev_xv = send_xv, prev_x2 = send_x2;
-					uint32_t xt1A = prmt(rxv, X.x, 0x5410), xt1B = prmt(X.x, X.y, 0x5432);
-					uint32_t vt1A = prmt(rxv, V.x, 0x5432), vt1B = prmt(V.x, V.y, 0x5432);
-					uint32_t x2t1A = prmt(rx2, X2.x, 0x5432), x2t1B = prmt(X2.x, X2.y, 0x5432);
-					uint32_t sA = prmt(sw, C.TS4, 0x1404), sB = prmt(sw, C.TS4, 0x3424);
-					uint32_t uA, vA, xA, x2A, ztA, faA, fbA, fa2A, fb2A;
-					uint32_t uB, vB, xB, x2B, ztB, faB, fbB, fa2B, fb2B;
-					cell2<RIGHT>(C, sA, xt1A, vt1A, x2t1A, U.x, Y.x, Y2.x, uA, vA, xA, x2A, ztA, faA, fbA, fa2A, fb2A);
-					cell2<RIGHT>(C, sB, xt1B, vt1B, x2t1B, U.y, Y.y, Y2.y, uB, vB, xB, x2B, ztB, faB, fbB, fa2B, fb2B);
-					if (active) {
-						sts2(g.u + slot, uA, uB), sts2(g.v + slot, vA, vB), sts2(g.x + slot, xA, xB);
-						sts2(g.y + slot, Y.x, Y.y), sts2(g.x2 + slot, x2A, x2B), sts2(g.y2 + slot, Y2.x, Y2.y);
-						if (WITH_P)
-							*(uint32_t *)(pr + blk * 16 + c4) =
-							    make_dir4(C, ztA, ztB, faA, faB, fbA, fbB, fa2A, fa2B, fb2A, fb2B);
+			if (EXACT) {
+				// the column that left [st0,en0] keeps its last score for "H[en0-1]" of one-cell rows
+				if (r > 0 && st0 > st0_prev) Hleft = *col_H(ring, REC, NR, st_rec, st0 - 1 - st);
+				if (li < 3) {
+					if (en1 + li < en0) sp_t = en1 + li, sp_h = *col_H(ring, REC, NR, st_rec, sp_t - st);
+				} else if (li == 3) {
+					if (en0 > 0) {
+						sp_t = en0;
+						sp_h = en0 - 1 >= st0 ? *col_H(ring, REC, NR, st_rec, en0 - 1 - st) : Hleft;
 					}
 				}
 			}
-			sync_warp(gmask);
-			++rows_exec;
-			// ---- phase C: score tracking ----
-			if (!EXACT) { // ksw2_extd2_sse.c:367-383; lane 0 only unless a Z-drop decision must be shared
-				if (li == 0) {
-					if (r > 0) {
-						bool in0 = H0_t >= st0 && H0_t <= en0, in1 = H0_t + 1 >= st0 && H0_t + 1 <= en0;
-						int s0 = wrap(st_slot + (H0_t - st), R); // only dereferenced when in range
-						if (in0 && in1) {
-							int d0 = hi8(g.v[s0]), d1 = hi8(g.u[wrap(s0 + 1, R)]);
-							if (d0 > d1) H0 += d0;
-							else H0 += d1, ++H0_t;
-						} else if (in0) {
-							H0 += hi8(g.v[s0]);
-						} else {
-							++H0_t;
-							H0 += hi8(g.u[wrap(st_slot + (H0_t - st), R)]);
-						}
-					} else H0 = hi8(g.v[st_slot]) - C.qe_seed, H0_t = 0;
+		}
+		if (EXACT) {
+			sync_warp(FULL); // all of the loads above precede the sentinel stores below
+			if (active) {
+				if (li == 3 && r > 0 && st0 > st0_prev) *col_H(ring, REC, NR, st_rec, st0 - 1 - st) = GD_KSW_NEG_INF;
+				if (li == 3 && r == 0) *col_H(ring, REC, NR, st_rec, 0) = -C.qe_seed; // the bulk update adds v[0]: H[0] = v[0] - qe
+				if (sp_t >= 0) *col_H(ring, REC, NR, st_rec, sp_t - st) = GD_KSW_NEG_INF; // keeps the bulk scan off these cells
+			}
+		}
+		sync_warp(FULL);
+		// ---- phase B: score row + core update, chunk by chunk from the right end of the row ----
+		int run = (int)0x80000000; // exact mode: best (relative score << 16 | priority) key of this lane
+		{
+			const int cbeg = st >> 3;
+			int ctop = active ? (imax(en, fe - 1) >> 3) : -1; // chunk of lane G-1 in the current step
+			const int qshift = active ? qlen - 1 - r + GD_KSW_QFRONT : GD_KSW_QFRONT; // qsm offset of the query base under column 0
+			const int nMprev = -Mprev;
+			uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;
+			if (EXACT) {
+				const uint4 pk = *(const uint4 *)(lut_pk + (((0 - st0) & 3) << 2));
+				pk0 = pk.x, pk1 = pk.y, pk2 = pk.z, pk3 = pk.w;
+			}
+			while (ballot(FULL, active && ctop >= cbeg)) {
+				// Lanes without a chunk in this step run the same instructions on chunk cbeg of their own ring
+				// (all addresses stay in range) and only their stores are predicated off: no divergence.
+				const int c0 = ctop - (G - 1 - li);
+				const bool valid = active && c0 >= cbeg;
+				const int c = valid ? c0 : cbeg;
+				const int tb = c << 3, d = tb - st;
+				const bool core = valid && tb <= en;
+				int k = st_rec + (d >> 3);
+				if (k >= NR) k -= NR;
+				uint8_t *const rc = ring + k * REC;
+				uint8_t *const rp = ring + (k == 0 ? NR - 1 : k - 1) * REC; // record of the left neighbour chunk
+				// score bytes of the 8 columns (xor-table rule), merged with the stale row outside [st0,fe)
+				uint32_t sw0, sw1;
+				{
+					const uint2 tw = *(const uint2 *)(tsm + tb);
+					const int qi = qshift + tb;
+					const uint32_t *qw = (const uint32_t *)(qsm + (qi & ~3));
+					const uint32_t q0 = qw[0], q1 = qw[1], q2 = qw[2], sh = (uint32_t)(qi & 3) * 8;
+					const uint32_t qa = funnel_r(q0, q1, sh), qb = funnel_r(q1, q2, sh);
+					const uint32_t f0 = score4(C, tw.x, prmt(qa, qb, 0x5140)), f1 = score4(C, tw.y, prmt(qa, qb, 0x7362));
+					const int lo = imax(st0 - tb, 0), hi = imax(imin(fe - tb, 8), 0);
+					const uint2 m = lut_fresh[lo * 9 + hi];
+					const uint2 old = *(const uint2 *)(rc + REC_S);
+					sw0 = (f0 & m.x) | (old.x & ~m.x), sw1 = (f1 & m.y) | (old.y & ~m.y);
 				}
-				if (C.flag & KSW_F_APPROX_DROP) {
-					int stop = 0;
-					if (li == 0) { // ksw_apply_zdrop, ksw2.h:172-188
-						if (H0 > res.max) res.max = H0, res.max_t = H0_t, res.max_q = r - H0_t;
-						else if (H0_t >= res.max_t && r - H0_t >= res.max_q) {
-							int tl = H0_t - res.max_t, ql = (r - H0_t) - res.max_q, l = tl > ql ? tl - ql : ql - tl;
-							if (C.zdrop >= 0 && res.max - H0 > C.zdrop + l * C.e2) res.zdropped = 1, stop = 1;
-						}
+				const uint4 U = *(const uint4 *)(rc + REC_U), V = *(const uint4 *)(rc + REC_V), X = *(const uint4 *)(rc + REC_X);
+				uint4 Y = *(const uint4 *)(rc + REC_Y), Y2 = *(const uint4 *)(rc + REC_Y2);
+				const uint4 X2 = *(const uint4 *)(rc + REC_X2);
+				const uint32_t xm1 = *(const uint16_t *)(rp + REC_X + 14), vm1 = *(const uint16_t *)(rp + REC_V + 14);
+				const uint32_t x2m1 = *(const uint16_t *)(rp + REC_X2 + 14);
+				uint4 ha, hb;
+				if (EXACT) ha = *(const uint4 *)(rc + REC_H), hb = *(const uint4 *)(rc + REC_H + 16);
+				sync_warp(FULL); // every lane has read its left neighbour's old column before anybody stores
+				uint32_t u0, v0, x0, x20, zt0, fa0, fb0, fa20, fb20;
+				uint32_t u1, v1, x1, x21, zt1, fa1, fb1, fa21, fb21;
+				uint32_t u2, v2, x2, x22, zt2, fa2, fb2, fa22, fb22;
+				uint32_t u3, v3, x3, x23, zt3, fa3, fb3, fa23, fb23;
+				cell2<RIGHT>(C, prmt(sw0, C.TS4, 0x1404), prmt(xm1, X.w, 0x5410), prmt(vm1, V.w, 0x5410),
+				             prmt(x2m1, X2.w, 0x5410), U.x, Y.x, Y2.x, u0, v0, x0, x20, zt0, fa0, fb0, fa20, fb20);
+				cell2<RIGHT>(C, prmt(sw0, C.TS4, 0x3424), X.x, V.x, X2.x, U.y, Y.y, Y2.y, u1, v1, x1, x21, zt1, fa1, fb1, fa21,
+				             fb21);
+				cell2<RIGHT>(C, prmt(sw1, C.TS4, 0x1404), X.y, V.y, X2.y, U.z, Y.z, Y2.z, u2, v2, x2, x22, zt2, fa2, fb2, fa22,
+				             fb22);
+				cell2<RIGHT>(C, prmt(sw1, C.TS4, 0x3424), X.z, V.z, X2.z, U.w, Y.w, Y2.w, u3, v3, x3, x23, zt3, fa3, fb3, fa23,
+				             fb23);
+				if (valid) {
+					uint2 sv;
+					sv.x = sw0, sv.y = sw1;
+					*(uint2 *)(rc + REC_S) = sv;
+				}
+				if (core) {
+					uint4 o;
+					o.x = u0, o.y = u1, o.z = u2, o.w = u3, *(uint4 *)(rc + REC_U) = o;
+					o.x = v0, o.y = v1, o.z = v2, o.w = v3, *(uint4 *)(rc + REC_V) = o;
+					o.x = x0, o.y = x1, o.z = x2, o.w = x3, *(uint4 *)(rc + REC_X) = o;
+					o.x = x20, o.y = x21, o.z = x22, o.w = x23, *(uint4 *)(rc + REC_X2) = o;
+					*(uint4 *)(rc + REC_Y) = Y, *(uint4 *)(rc + REC_Y2) = Y2;
+					if (WITH_P) {
+						uint2 dv;
+						dv.x = make_dir4(C, zt0, zt1, fa0, fa1, fb0, fb1, fa20, fa21, fb20, fb21);
+						dv.y = make_dir4(C, zt2, zt3, fa2, fa3, fb2, fb3, fa22, fa23, fb22, fb23);
+						*(uint2 *)(prow + d) = dv;
 					}
-					stop = (int)shfl_idx(gmask, (uint32_t)stop, 0, G);
-					if (stop) break;
 				}
-				if (li == 0 && r == nrows - 1 && en0 == tlen - 1) res.score = H0;
-			} else { // ksw2_extd2_sse.c:323-366
-				int max_H, max_t;
+				if (EXACT) { // H[t] += v[t] on the whole chunk; columns outside [st0,en1) hold sentinels
+					ha.x += prmt(v0, 0, 0x9991), hb.x += prmt(v0, 0, 0xbbb3);
+					ha.y += prmt(v1, 0, 0x9991), hb.y += prmt(v1, 0, 0xbbb3);
+					ha.z += prmt(v2, 0, 0x9991), hb.z += prmt(v2, 0, 0xbbb3);
+					ha.w += prmt(v3, 0, 0x9991), hb.w += prmt(v3, 0, 0xbbb3);
+					// keys: (score relative to the previous row's maximum) << 16 | priority of the column
+					const uint32_t nb2 = (uint32_t)((0 - d) & 0xffff) * 0x10001u;
+					const uint32_t p0 = vadd2(pk0, nb2), p1 = vadd2(pk1, nb2), p2 = vadd2(pk2, nb2), p3 = vadd2(pk3, nb2);
+					const int k0 = (int)prmt(p0, (uint32_t)iaddmax((int)ha.x, nMprev, GD_KSW_REL_FLOOR), 0x5410);
+					const int k4 = (int)prmt(p0, (uint32_t)iaddmax((int)hb.x, nMprev, GD_KSW_REL_FLOOR), 0x5432);
+					const int k1 = (int)prmt(p1, (uint32_t)iaddmax((int)ha.y, nMprev, GD_KSW_REL_FLOOR), 0x5410);
+					const int k5 = (int)prmt(p1, (uint32_t)iaddmax((int)hb.y, nMprev, GD_KSW_REL_FLOOR), 0x5432);
+					const int k2 = (int)prmt(p2, (uint32_t)iaddmax((int)ha.z, nMprev, GD_KSW_REL_FLOOR), 0x5410);
+					const int k6 = (int)prmt(p2, (uint32_t)iaddmax((int)hb.z, nMprev, GD_KSW_REL_FLOOR), 0x5432);
+					const int k3 = (int)prmt(p3, (uint32_t)iaddmax((int)ha.w, nMprev, GD_KSW_REL_FLOOR), 0x5410);
+					const int k7 = (int)prmt(p3, (uint32_t)iaddmax((int)hb.w, nMprev, GD_KSW_REL_FLOOR), 0x5432);
+					if (core) {
+						*(uint4 *)(rc + REC_H) = ha, *(uint4 *)(rc + REC_H + 16) = hb;
+						run = imax3(run, k0, k4), run = imax3(run, k1, k5), run = imax3(run, k2, k6), run = imax3(run, k3, k7);
+					}
+				}
+				ctop -= G;
+			}
+		}
+		sync_warp(FULL);
+		// ---- phase C: score tracking ----
+		int stop = 0;
+		if (!EXACT) { // ksw2_extd2_sse.c:367-383 (every lane of the group tracks the same H0)
+			if (active) {
 				if (r > 0) {
-					const int en1 = st0 + ((en0 - st0) & ~3);
-					// H[en0] first, from the not yet updated H[en0-1]
-					const int se = wrap(st_slot + (en0 - st), R);
-					int Hen;
-					if (en0 > 0) Hen = g.H[se == 0 ? R - 1 : se - 1] + hi8(g.u[se]);
-					else Hen = g.H[se] + hi8(g.v[se]);
-					sync_warp(gmask);
-					long long best = hkey(Hen, 0xffffffffu);
-					for (int t4 = (st0 & ~3) + li * 4; t4 < en0; t4 += G * 4) {
-						int slot = wrap(st_slot + (t4 - st), R);
-						for (int j = 0; j < 4; ++j) {
-							int t = t4 + j;
-							if (t < st0 || t >= en0) continue;
-							int h = g.H[slot + j] + hi8(g.v[slot + j]);
-							g.H[slot + j] = h;
-							uint32_t prio = t < en1 ? (0x40000000u | (uint32_t)(3 - ((t - st0) & 3)) << 28 | (0x0fffffffu - (uint32_t)t))
-							                        : (0x0fffffffu - (uint32_t)t);
-							long long k = hkey(h, prio);
-							if (k > best) best = k;
-						}
+					const bool in0 = H0_t >= st0 && H0_t <= en0, in1 = H0_t + 1 >= st0 && H0_t + 1 <= en0;
+					if (in0 && in1) {
+						const int d0 = hi8(*col_hw(ring, REC, NR, st_rec, H0_t - st, REC_V));
+						const int d1 = hi8(*col_hw(ring, REC, NR, st_rec, H0_t + 1 - st, REC_U));
+						if (d0 > d1) H0 += d0;
+						else H0 += d1, ++H0_t;
+					} else if (in0) {
+						H0 += hi8(*col_hw(ring, REC, NR, st_rec, H0_t - st, REC_V));
+					} else {
+						++H0_t;
+						H0 += hi8(*col_hw(ring, REC, NR, st_rec, imax(H0_t - st, 0), REC_U));
 					}
-					if (li == 0) g.H[se] = Hen;
-					for (int d = 1; d < G; d <<= 1) {
-						uint32_t lo = shfl_xor(gmask, (uint32_t)best, d, G);
-						uint32_t hi = shfl_xor(gmask, (uint32_t)((unsigned long long)best >> 32), d, G);
-						long long o = (long long)(((unsigned long long)hi << 32) | lo);
-						if (o > best) best = o;
+				} else H0 = hi8(*col_hw(ring, REC, NR, st_rec, 0, REC_V)) - C.qe_seed, H0_t = 0;
+				if (C.flag & KSW_F_APPROX_DROP) { // ksw_apply_zdrop, ksw2.h:172-188
+					if (H0 > res.max) res.max = H0, res.max_t = H0_t, res.max_q = r - H0_t;
+					else if (H0_t >= res.max_t && r - H0_t >= res.max_q) {
+						const int tl = H0_t - res.max_t, ql = (r - H0_t) - res.max_q, l = tl > ql ? tl - ql : ql - tl;
+						if (C.zdrop >= 0 && res.max - H0 > C.zdrop + l * C.e2) res.zdropped = 1, stop = 1;
 					}
-					max_H = (int)(best >> 32);
-					uint32_t pr = (uint32_t)best;
-					max_t = pr == 0xffffffffu ? en0 : (int)(0x0fffffffu - (pr & 0x0fffffffu));
-					sync_warp(gmask);
-				} else {
-					if (li == 0) g.H[st_slot] = hi8(g.v[st_slot]) - C.qe_seed;
-					sync_warp(gmask);
-					max_H = g.H[st_slot], max_t = 0;
 				}
-				{ // end-of-target / end-of-query bests (all lanes read the same words)
-					int He = g.H[wrap(st_slot + (en0 - st), R)], Hs = g.H[wrap(st_slot + (st0 - st), R)];
-					if (en0 == tlen - 1 && He > res.mte) res.mte = He, res.mte_q = r - en;
-					if (r - st0 == qlen - 1 && Hs > res.mqe) res.mqe = Hs, res.mqe_t = st0;
-					int stop = 0;
-					if (max_H > res.max) res.max = max_H, res.max_t = max_t, res.max_q = r - max_t;
-					else if (max_t >= res.max_t && r - max_t >= res.max_q) {
-						int tl = max_t - res.max_t, ql = (r - max_t) - res.max_q, l = tl > ql ? tl - ql : ql - tl;
-						if (C.zdrop >= 0 && res.max - max_H > C.zdrop + l * C.e2) res.zdropped = 1, stop = 1;
-					}
-					if (stop) break;
-					if (r == nrows - 1 && en0 == tlen - 1) res.score = g.H[wrap(st_slot + (tlen - 1 - st), R)];
-				}
+				if (r == nrows - 1 && en0 == tlen - 1) res.score = H0;
 			}
-			last_st = st, last_en = en;
+		} else { // ksw2_extd2_sse.c:323-366
+			// the cells kept out of the bulk update: scan tail (H += v) and column en0 (H[en0-1] + u[en0])
+			if (active && sp_t >= 0) {
+				const int cc = sp_t - st;
+				const int hn = sp_h + hi8(*col_hw(ring, REC, NR, st_rec, cc, li == 3 ? REC_U : REC_V));
+				*col_H(ring, REC, NR, st_rec, cc) = hn;
+				const int relc = imin(imax(hn - Mprev, GD_KSW_REL_FLOOR), 32767);
+				const uint32_t pr = li == 3 ? 0xffffu : (uint32_t)(3 - li) << 13 | (uint32_t)(GD_KSW_POS_MAX - cc);
+				run = imax(run, (int)((uint32_t)relc << 16 | pr));
+			}
+			for (int dd = 1; dd < G; dd <<= 1) run = imax(run, (int)shfl_xor(FULL, (uint32_t)run, dd, 32));
+			sync_warp(FULL);
+			if (active) {
+				const int rel = run >> 16;
+				const uint32_t pr = (uint32_t)run & 0xffffu;
+				int max_H = Mprev + rel, max_t = pr == 0xffffu ? en0 : st + (GD_KSW_POS_MAX - (int)(pr & 0x1fffu));
+				if (rel <= GD_KSW_REL_FLOOR || rel >= 32767 || C.force_slow_max)
+					row_max_literal(ring, REC, NR, st_rec, st, st0, en0, max_H, max_t);
+#ifdef GD_HOST_EMU
+				{ // logic tests only: the key-based maximum must agree with the literal scan on every row
+					int lit_H, lit_t;
+					row_max_literal(ring, REC, NR, st_rec, st, st0, en0, lit_H, lit_t);
+					if (lit_H != max_H || lit_t != max_t) ++emu::rowmax_mismatches();
+				}
+#endif
+				Mprev = max_H, st0_prev = st0;
+				const int He = *col_H(ring, REC, NR, st_rec, en0 - st), Hs = *col_H(ring, REC, NR, st_rec, st0 - st);
+				if (en0 == tlen - 1 && He > res.mte) res.mte = He, res.mte_q = r - en;
+				if (r - st0 == qlen - 1 && Hs > res.mqe) res.mqe = Hs, res.mqe_t = st0;
+				if (max_H > res.max) res.max = max_H, res.max_t = max_t, res.max_q = r - max_t;
+				else if (max_t >= res.max_t && r - max_t >= res.max_q) {
+					const int tl = max_t - res.max_t, ql = (r - max_t) - res.max_q, l = tl > ql ? tl - ql : ql - tl;
+					if (C.zdrop >= 0 && res.max - max_H > C.zdrop + l * C.e2) res.zdropped = 1, stop = 1;
+				}
+				if (!stop && r == nrows - 1 && en0 == tlen - 1) res.score = *col_H(ring, REC, NR, st_rec, tlen - 1 - st);
+			}
 		}
-		if (li == 0) {
-			res.rows_done = rows_exec;
-			if (WITH_P) { // choice of the traceback start, ksw2_extd2_sse.c:389-400
-				if (!res.zdropped && !(C.flag & KSW_F_EXTZ_ONLY)) res.tb_i = tlen - 1, res.tb_j = qlen - 1;
-				else if (!res.zdropped && (C.flag & KSW_F_EXTZ_ONLY) && res.mqe + C.end_bonus > res.max)
-					res.reach_end = 1, res.tb_i = res.mqe_t, res.tb_j = qlen - 1;
-				else if (res.max_t >= 0 && res.max_q >= 0) res.tb_i = res.max_t, res.tb_j = res.max_q;
+		if (active) {
+			++rows_exec;
+			last_st = st, last_en = en;
+			if (WITH_P) prow += ncol16;
+			++r;
+			if (stop || r == nrows) finish = true;
+		}
+		// ================= pair finished: publish the record =================
+		if (finish) {
+			if (li == 0) {
+				res.rows_done = rows_exec;
+				if (WITH_P) { // choice of the traceback start, ksw2_extd2_sse.c:389-400
+					if (!res.zdropped && !(C.flag & KSW_F_EXTZ_ONLY)) res.tb_i = tlen - 1, res.tb_j = qlen - 1;
+					else if (!res.zdropped && (C.flag & KSW_F_EXTZ_ONLY) && res.mqe + C.end_bonus > res.max)
+						res.reach_end = 1, res.tb_i = res.mqe_t, res.tb_j = qlen - 1;
+					else if (res.max_t >= 0 && res.max_q >= 0) res.tb_i = res.max_t, res.tb_j = res.max_q;
+				}
+				B.res[pair] = res;
 			}
-			B.res[pair] = res;
+			have = false;
 		}
 	}
 }
 
-// Stage one pair into the padded arenas the DP kernel reads (see KswBatch): target zero padded,
-// query reversed (qr[] of ksw2_extd2_sse.c:128) with N(4) -> 8 (ksw2_extd2_avx.c:187-190).
+// Stage one pair into the padded arenas the DP kernel reads (see KswBatch): target zero padded with
+// every 8-column chunk in strided order, query reversed (qr[] of ksw2_extd2_sse.c:128) with
+// N(4) -> 8 (ksw2_extd2_avx.c:187-190).
 GD_DEV void ksw_pack_pair(const uint8_t *GD_RESTRICT q, int qlen, const uint8_t *GD_RESTRICT t, int tlen,
                           uint8_t *GD_RESTRICT tpk, int t_stride, uint8_t *GD_RESTRICT qpk, int q_stride, int lane,
                           int nlanes)
 {
 	for (int i = lane * 4; i < t_stride; i += nlanes * 4) {
 		uint32_t wv = 0;
-		for (int k = 0; k < 4; ++k)
-			if (i + k < tlen) wv |= (uint32_t)t[i + k] << (8 * k);
+		for (int k = 0; k < 4; ++k) { // byte i+k of the arena holds column (chunk base) + j with chunk_pos(j) == (i+k)&7
+			const int p = (i + k) & 7, j = (p >> 1) | ((p & 1) << 2), col = ((i + k) & ~7) + j;
+			if (col < tlen) wv |= (uint32_t)t[col] << (8 * k);
+		}
 		*(uint32_t *)(tpk + i) = wv;
 	}
 	for (int i = lane * 4; i < q_stride; i += nlanes * 4) {
 		uint32_t wv = 0;
 		for (int k = 0; k < 4; ++k) {
-			int j = i + k - 16;
+			int j = i + k - GD_KSW_QFRONT;
 			if (j >= 0 && j < qlen) {
 				uint32_t c = q[qlen - 1 - j];
 				wv |= (c == 4 ? 8u : c) << (8 * k);
@@ -505,7 +660,8 @@ GD_DEV void ksw_traceback_one(const KswBatch &B, int flag, int lp, uint32_t *cig
 		row_bounds(r, qlen, tlen, w, bd);
 		if (i < bd.st) force = 2;
 		if (i > bd.en) force = 1;
-		uint32_t cell = force < 0 ? p[(size_t)r * ncol16 + (i - bd.st)] : 0;
+		const int cc = i - bd.st;
+		uint32_t cell = force < 0 ? p[(size_t)r * ncol16 + (cc & ~7) + chunk_pos(cc & 7)] : 0;
 		if (state == 0) state = cell & 7;
 		else if (!((cell >> (state + 2)) & 1)) state = 0;
 		if (state == 0) state = cell & 7;

@@ -52,6 +52,7 @@ static inline KswConsts ksw_make_consts(int m, const int8_t *mat, int q_, int e_
 	C.long_thres = long_thres;
 	C.long_diff = long_thres * (e - e2) - (q2 - q) - e2;
 	C.zdrop = zdrop, C.end_bonus = end_bonus, C.flag = flag;
+	C.force_slow_max = 0;
 	return C;
 }
 
@@ -65,8 +66,8 @@ static inline int h_ncol16(int qlen, int tlen, int w)
 
 // Geometry of one launch, derived from upper bounds on the chunk's pairs.
 struct KswGeom {
-	int ring;        // columns per ring
-	int group_smem;  // bytes per group
+	int ring;        // columns per ring (multiple of 16)
+	int group_smem;  // bytes per group: ring + staged sequences
 	int t_stride, q_stride;
 	int64_t p_stride;
 };
@@ -77,10 +78,11 @@ static inline KswGeom ksw_geometry(int max_qlen, int max_tlen, int max_w, bool e
 	if (max_tlen < 1) max_tlen = 1;
 	const int T16 = (max_tlen + 15) / 16 * 16;
 	const int ncol16 = h_ncol16(max_qlen, max_tlen, max_w);
-	g.ring = ncol16 + 32 < T16 ? ncol16 + 32 : T16;
-	g.group_smem = ksw_group_smem_bytes(g.ring, exact);
-	g.t_stride = T16 + 16;
+	// live columns of a row: [st-1, en+16] (left boundary slot .. the block the score row may run into)
+	g.ring = ncol16 + 32 < T16 + 16 ? ncol16 + 32 : T16 + 16;
+	g.t_stride = T16;
 	g.q_stride = (max_qlen + 15) / 16 * 16 + 64;
+	g.group_smem = ksw_group_smem_bytes(g.ring, exact, g.t_stride + g.q_stride);
 	g.p_stride = with_p ? (int64_t)(max_qlen + max_tlen - 1) * ncol16 : 0;
 	return g;
 }

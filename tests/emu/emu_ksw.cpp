@@ -12,11 +12,13 @@ template <int G, bool RIGHT, bool EXACT, bool WITH_P>
 static void run_dp(const KswConsts &C, const KswBatch &B, int threads)
 {
 	int groups = threads / G;
-	emu::launch(1, threads, (size_t)groups * B.group_smem, [&]() {
-		int tid = emu::thread_idx(), lane = tid & 31, li = lane & (G - 1);
-		uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1));
-		uint8_t *sm = (uint8_t *)emu::smem() + (size_t)(tid / G) * B.group_smem;
-		ksw_group_body<G, RIGHT, EXACT, WITH_P>(C, B, sm, li, gmask);
+	emu::launch(1, threads, GD_KSW_LUT_BYTES + (size_t)groups * B.group_smem, [&]() {
+		int tid = emu::thread_idx();
+		uint8_t *sm = (uint8_t *)emu::smem();
+		ksw_build_lut(sm, tid, threads);
+		emu::sync_block();
+		ksw_warp_body<G, RIGHT, EXACT, WITH_P>(C, B, sm + GD_KSW_LUT_BYTES + (size_t)(tid >> 5) * (32 / G) * B.group_smem, sm,
+		                                       tid & 31);
 	});
 }
 
@@ -39,7 +41,9 @@ extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, co
                              int q, int e, int q2, int e2, int zdrop, int end_bonus, int flag, int G, int threads,
                              KswResult *res, uint32_t *cigar, int cigar_stride)
 {
-	KswConsts C = ksw_make_consts(m, mat, q, e, q2, e2, zdrop, end_bonus, flag);
+	KswConsts C = ksw_make_consts(m, mat, q, e, q2, e2, zdrop, end_bonus, flag & 0xff);
+	C.force_slow_max = (flag >> 8) & 1; // test hook: bit 8 of the emulator's flag argument
+	flag &= 0xff;
 	int max_q = 1, max_t = 1, max_w = 0;
 	for (int i = 0; i < n; ++i) {
 		int ww = w[i] < 0 ? (tlen[i] > qlen[i] ? tlen[i] : qlen[i]) : w[i];
@@ -59,6 +63,7 @@ extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, co
 	B.n = n, B.base = 0, B.qlen = qlen, B.tlen = tlen, B.w = w, B.w_all = 0;
 	B.tpk = tpk.data(), B.qpk = qpk.data(), B.t_stride = g.t_stride, B.q_stride = g.q_stride;
 	B.p = p.data(), B.p_stride = g.p_stride, B.res = res, B.ticket = &ticket, B.ring = g.ring, B.group_smem = g.group_smem;
+	emu::rowmax_mismatches() = 0;
 	switch (G) {
 	case 4: dispatch<4>(C, B, threads, right, exact, with_p); break;
 	case 8: dispatch<8>(C, B, threads, right, exact, with_p); break;
@@ -68,5 +73,6 @@ extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, co
 	}
 	if (with_p)
 		for (int i = 0; i < n; ++i) ksw_traceback_one(B, flag, i, cigar, cigar_stride);
+	if (emu::rowmax_mismatches()) return -2; // fast row maximum disagreed with the literal scan
 	return 0;
 }

@@ -43,6 +43,12 @@ inline BlockState *&cur_block()
 	return b;
 }
 
+inline long &rowmax_mismatches()
+{ // self-check counter of the DP kernel's exact-max fast path (see gd_ksw.cuh)
+	static long n = 0;
+	return n;
+}
+
 inline void yield()
 {
 	BlockState *b = cur_block();
@@ -99,9 +105,14 @@ inline uint32_t shfl_up(uint32_t mask, uint32_t v, int d, int width)
 }
 inline uint32_t ballot(uint32_t mask, int pred)
 {
+	BlockState *b = cur_block();
+	int tid = b->cur, base = tid & ~31;
+	b->th[tid].xchg = pred ? 1u : 0u;
+	sync_warp(mask);
 	uint32_t r = 0;
 	for (int l = 0; l < 32; ++l)
-		if (mask >> l & 1) r |= (xchg(mask, pred ? 1u : 0u, l) & 1u) << l;
+		if ((mask >> l & 1) && base + l < b->nthreads && (b->th[base + l].xchg & 1u)) r |= 1u << l;
+	sync_warp(mask);
 	return r;
 }
 
@@ -134,7 +145,11 @@ inline void launch(int grid, int block, size_t smem_bytes, std::function<void()>
 	for (int bid = 0; bid < grid; ++bid) {
 		BlockState b;
 		b.bid = bid, b.nthreads = block, b.grid = grid, b.body = body;
-		b.smem = (char *)calloc(smem_bytes ? smem_bytes : 1, 1);
+		{ // shared memory is uninitialised on the device: poison it so that stale reads show up
+			size_t nb = (smem_bytes + 255) / 128 * 128;
+			b.smem = (char *)aligned_alloc(128, nb);
+			memset(b.smem, 0xCD, nb);
+		}
 		b.th.resize(block);
 		cur_block() = &b;
 		for (int t = 0; t < block; ++t) {

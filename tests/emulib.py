@@ -21,7 +21,7 @@ def build():
     deps = srcs + [os.path.join(EMU_DIR, "simt_emu.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)
                                                               if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-fPIC", "-shared", "-std=c++17", "-I", EMU_DIR, "-I", CSRC, "-o", so] + srcs)
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-I", EMU_DIR, "-I", CSRC, "-o", so] + srcs)
     return so
 
 

@@ -17,10 +17,10 @@ def emu():
     return Emu()
 
 
-def _check(emu, oracle, P, w, scn, flag, G):
+def _check(emu, oracle, P, w, scn, flag, G, force_literal_max=False):
     sc = synth.SCORING[scn]
     mat = synth.score_matrix(sc["a"], sc["b"])
-    res, cig = emu.ksw_batch(P, w, mat, sc, flag, G)
+    res, cig = emu.ksw_batch(P, w, mat, sc, flag | (0x100 if force_literal_max else 0), G)
     for i in range(P["n"]):
         q, t = pair(P, i)
         ez, oc = oracle.ksw_extd2(q, t, mat, sc["q"], sc["e"], sc["q2"], sc["e2"], int(w[i]), sc["zdrop"], sc["end_bonus"], flag)
@@ -45,6 +45,43 @@ def test_emu_ksw_ring_wrap(emu, oracle, G, wv):
     w = np.full(P["n"], wv, np.int32)
     for flag in (0x08, 0x00):
         _check(emu, oracle, P, w, "map-ont", flag, G)
+
+
+def _tie_pairs(n, seed):
+    """low-complexity pairs (short tandem repeats, homopolymers): many equal scores along an anti-diagonal,
+    which is what the reference's 4-lane row-maximum tie order is sensitive to"""
+    rng = np.random.default_rng(seed)
+    qs, ts = [], []
+    for i in range(n):
+        unit = rng.integers(0, 4, int(rng.integers(1, 4)), dtype=np.uint8)
+        tl, ql = int(rng.integers(8, 150)), int(rng.integers(8, 150))
+        t = np.resize(unit, tl).copy()
+        q = np.resize(unit, ql).copy()
+        for a in (t, q):
+            k = int(rng.integers(0, 4))
+            a[rng.integers(0, len(a), k)] = rng.integers(0, 4, k, dtype=np.uint8)
+        qs.append(q)
+        ts.append(t)
+    return synth.pack_pairs(qs, ts)
+
+
+@pytest.mark.parametrize("flag", [0x00, 0x40, 0x02])
+def test_emu_ksw_exact_max_ties(emu, oracle, flag):
+    P = _tie_pairs(16, seed=21 + flag)
+    rng = np.random.default_rng(flag)
+    for G, scn in ((4, "sr"), (8, "map-ont")):
+        w = rng.choice([-1, 7, 20, 64, 200], P["n"]).astype(np.int32)
+        _check(emu, oracle, P, w, scn, flag, G)
+
+
+def test_emu_ksw_literal_row_max(emu, oracle):
+    """the fallback scan taken when a row does not fit the relative 16-bit keys (forced here)"""
+    P = synth.ragged_pairs(8, seed=31, max_len=120)
+    T = _tie_pairs(8, seed=32)
+    rng = np.random.default_rng(5)
+    for Q in (P, T):
+        w = rng.choice([-1, 9, 33, 100], Q["n"]).astype(np.int32)
+        _check(emu, oracle, Q, w, "sr", 0x00, 4, force_literal_max=True)
 
 
 def test_emu_ksw_microbench_shape(emu, oracle):

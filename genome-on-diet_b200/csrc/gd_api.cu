@@ -60,6 +60,7 @@ extern "C" int gd_init(int device, gd_ctx **out)
 	ctx->device = device;
 	ctx->sms = prop.multiProcessorCount;
 	ctx->smem_optin = prop.sharedMemPerBlockOptin;
+	ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
 		g_init_err = "cudaStreamCreate failed";

@@ -43,6 +43,7 @@ GD_DEV uint32_t shfl_idx(uint32_t mask, uint32_t v, int src, int width) { return
 GD_DEV uint32_t shfl_xor(uint32_t mask, uint32_t v, int lm, int width) { return __shfl_xor_sync(mask, v, lm, width); }
 GD_DEV uint32_t shfl_up(uint32_t mask, uint32_t v, int d, int width) { return __shfl_up_sync(mask, v, d, width); }
 GD_DEV uint32_t ballot(uint32_t mask, int pred) { return __ballot_sync(mask, pred); }
+GD_DEV int reduce_max(uint32_t mask, int v) { return __reduce_max_sync(mask, v); } // REDUX.MAX
 GD_DEV void sync_warp(uint32_t mask) { __syncwarp(mask); }
 GD_DEV void sync_block() { __syncthreads(); }
 GD_DEV int thread_idx() { return (int)threadIdx.x; }
@@ -104,6 +105,14 @@ GD_DEV uint32_t shfl_idx(uint32_t mask, uint32_t v, int src, int width) { return
 GD_DEV uint32_t shfl_xor(uint32_t mask, uint32_t v, int lm, int width) { return emu::shfl_xor(mask, v, lm, width); }
 GD_DEV uint32_t shfl_up(uint32_t mask, uint32_t v, int d, int width) { return emu::shfl_up(mask, v, d, width); }
 GD_DEV uint32_t ballot(uint32_t mask, int pred) { return emu::ballot(mask, pred); }
+GD_DEV int reduce_max(uint32_t mask, int v)
+{
+	for (int d = 16; d >= 1; d >>= 1) {
+		int o = (int)emu::shfl_xor(mask, (uint32_t)v, d, 32);
+		v = o > v ? o : v;
+	}
+	return v;
+}
 GD_DEV void sync_warp(uint32_t mask) { emu::sync_warp(mask); }
 GD_DEV void sync_block() { emu::sync_block(); }
 GD_DEV int thread_idx() { return emu::thread_idx(); }

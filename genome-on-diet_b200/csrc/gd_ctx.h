@@ -19,7 +19,8 @@ struct GdPinned { // grow-only pinned host buffer
 struct gd_ctx {
 	int device = 0;
 	int sms = 0;
-	size_t smem_optin = 0;
+	size_t smem_optin = 0;  // max dynamic shared memory per block
+	size_t smem_per_sm = 0; // shared memory per SM
 	cudaStream_t stream = nullptr;
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

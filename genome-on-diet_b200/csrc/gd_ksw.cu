@@ -10,7 +10,7 @@ static_assert(sizeof(KswResult) == sizeof(gd_extz_t), "result layouts must match
 // --------------------------------------------------------------------------------------------
 // kernels
 // --------------------------------------------------------------------------------------------
-template <int G, bool RIGHT, bool EXACT, bool WITH_P>
+template <int G, bool RIGHT, int MODE, bool WITH_P>
 __global__ void __launch_bounds__(128) gd_ksw_dp_kernel(const KswConsts C, const KswBatch B)
 {
 	extern __shared__ __align__(128) uint8_t gd_smem[];
@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(128) gd_ksw_dp_kernel(const KswConsts C, const
 	ksw_build_lut(gd_smem, tid, blockDim.x);
 	__syncthreads();
 	uint8_t *warp_smem = gd_smem + GD_KSW_LUT_BYTES + (size_t)(tid >> 5) * (32 / G) * B.group_smem;
-	ksw_warp_body<G, RIGHT, EXACT, WITH_P>(C, B, warp_smem, gd_smem, tid & 31);
+	ksw_warp_body<G, RIGHT, MODE, WITH_P>(C, B, warp_smem, gd_smem, tid & 31);
 }
 
 // one warp per pair: raw byte codes -> padded arenas
@@ -26,8 +26,9 @@ __global__ void __launch_bounds__(128)
     gd_ksw_pack_kernel(int n, int base, const int32_t *__restrict__ qlen, const int64_t *__restrict__ qoff,
                        const uint8_t *__restrict__ qbuf, const int32_t *__restrict__ tlen,
                        const int64_t *__restrict__ toff, const uint8_t *__restrict__ tbuf, uint8_t *tpk, int t_stride,
-                       uint8_t *qpk, int q_stride)
+                       uint8_t *qpk, int q_stride, const KswConsts C, KswHot *hot)
 {
+	if (blockIdx.x == 0 && threadIdx.x == 0) *hot = ksw_hot_from_consts(C);
 	const int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
 	for (int lp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; lp < n; lp += warps) {
 		const int pair = base + lp;
@@ -123,22 +124,25 @@ __global__ void gd_exact_match_kernel(int n, const int32_t *qlen, const int64_t 
 // --------------------------------------------------------------------------------------------
 typedef void (*dp_kernel_t)(const KswConsts, const KswBatch);
 
-template <int G> static dp_kernel_t pick_mode(bool right, bool exact, bool with_p)
+template <int G, bool RIGHT> static dp_kernel_t pick_mode2(int mode, bool with_p)
 {
-	if (right) {
-		if (exact) return with_p ? gd_ksw_dp_kernel<G, true, true, true> : gd_ksw_dp_kernel<G, true, true, false>;
-		return with_p ? gd_ksw_dp_kernel<G, true, false, true> : gd_ksw_dp_kernel<G, true, false, false>;
+	switch (mode) {
+	case 0: return with_p ? gd_ksw_dp_kernel<G, RIGHT, 0, true> : gd_ksw_dp_kernel<G, RIGHT, 0, false>;
+	case 1: return with_p ? gd_ksw_dp_kernel<G, RIGHT, 1, true> : gd_ksw_dp_kernel<G, RIGHT, 1, false>;
+	default: return with_p ? gd_ksw_dp_kernel<G, RIGHT, 2, true> : gd_ksw_dp_kernel<G, RIGHT, 2, false>;
 	}
-	if (exact) return with_p ? gd_ksw_dp_kernel<G, false, true, true> : gd_ksw_dp_kernel<G, false, true, false>;
-	return with_p ? gd_ksw_dp_kernel<G, false, false, true> : gd_ksw_dp_kernel<G, false, false, false>;
 }
-static dp_kernel_t pick_kernel(int G, bool right, bool exact, bool with_p)
+template <int G> static dp_kernel_t pick_mode(bool right, int mode, bool with_p)
+{
+	return right ? pick_mode2<G, true>(mode, with_p) : pick_mode2<G, false>(mode, with_p);
+}
+static dp_kernel_t pick_kernel(int G, bool right, int mode, bool with_p)
 {
 	switch (G) {
-	case 4: return pick_mode<4>(right, exact, with_p);
-	case 8: return pick_mode<8>(right, exact, with_p);
-	case 16: return pick_mode<16>(right, exact, with_p);
-	default: return pick_mode<32>(right, exact, with_p);
+	case 4: return pick_mode<4>(right, mode, with_p);
+	case 8: return pick_mode<8>(right, mode, with_p);
+	case 16: return pick_mode<16>(right, mode, with_p);
+	default: return pick_mode<32>(right, mode, with_p);
 	}
 }
 
@@ -173,27 +177,31 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 		ctx->err = "gd_ksw: band too wide for the exact-max keys (ring > 8158 columns)";
 		return GD_ERR_ARG;
 	}
-	// block shape: as many groups per block as the shared-memory rings allow (128, 64 or 32 threads);
-	// when even one warp's worth of groups does not fit, widen the group (fewer pairs per warp)
-	int threads = 128;
-	const size_t avail = ctx->smem_optin - GD_KSW_LUT_BYTES;
+	// block shape: 1..4 warps per block, whichever packs the most resident warps into the SM's shared
+	// memory (each block also pays for the lookup tables and the driver's 1 KB); when even one warp's
+	// worth of groups does not fit, widen the group (fewer pairs per warp)
+	int threads = 0;
 	for (;;) {
 		const size_t per_warp = (size_t)(32 / G) * geo.group_smem;
-		if (per_warp * 4 <= avail) threads = 128;
-		else if (per_warp * 2 <= avail) threads = 64;
-		else if (per_warp <= avail) threads = 32;
-		else if (G < 32) {
+		int best_warps = 0;
+		for (int wpb = 1; wpb <= 4; ++wpb) {
+			const size_t blk = GD_KSW_LUT_BYTES + wpb * per_warp;
+			if (blk > ctx->smem_optin) break;
+			const int resident = (int)std::min<size_t>(32, ctx->smem_per_sm / (blk + 1024)) * wpb;
+			if (resident >= best_warps) best_warps = resident, threads = wpb * 32;
+		}
+		if (threads) break;
+		if (G < 32) {
 			G <<= 1;
 			continue;
-		} else {
-			ctx->err = "gd_ksw: band too wide for the shared-memory column ring (needs > 227 KB per pair)";
-			return GD_ERR_ARG;
 		}
-		break;
+		ctx->err = "gd_ksw: band too wide for the shared-memory column ring (needs > 227 KB per pair)";
+		return GD_ERR_ARG;
 	}
 	const int groups_per_block = threads / G;
 	const size_t smem = GD_KSW_LUT_BYTES + (size_t)groups_per_block * geo.group_smem;
-	dp_kernel_t kern = pick_kernel(G, right, exact, with_p);
+	const int mode = exact ? 2 : (flag & KSW_F_APPROX_DROP) ? 1 : 0;
+	dp_kernel_t kern = pick_kernel(G, right, mode, with_p);
 	GD_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int occ = 0;
 	GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -231,6 +239,7 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 		B.t_stride = geo.t_stride, B.q_stride = geo.q_stride;
 		B.p = (uint8_t *)ctx->parena.p, B.p_stride = geo.p_stride;
 		B.res = (KswResult *)d_ez, B.ticket = (int32_t *)ctx->ticket.p;
+		B.hot = (const KswHot *)((uint8_t *)ctx->ticket.p + 64);
 		B.ring = geo.ring, B.group_smem = geo.group_smem;
 
 		GD_CUDA_OK(ctx, cudaMemsetAsync(ctx->ticket.p, 0, 4, s));
@@ -238,7 +247,7 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 			int blocks = std::min((cn + 3) / 4, ctx->sms * 16);
 			gd_ksw_pack_kernel<<<blocks, 128, 0, s>>>(cn, base, d_qlen, d_qoff, d_qbuf, d_tlen, d_toff, d_tbuf,
 			                                          (uint8_t *)ctx->tpk.p, geo.t_stride, (uint8_t *)ctx->qpk.p,
-			                                          geo.q_stride);
+			                                          geo.q_stride, C, (KswHot *)((uint8_t *)ctx->ticket.p + 64));
 		}
 		{
 			int blocks = std::min((cn + groups_per_block - 1) / groups_per_block, ctx->sms * occ);

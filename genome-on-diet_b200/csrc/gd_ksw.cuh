@@ -38,6 +38,13 @@
 #pragma once
 #include "gd_common.cuh"
 
+#ifndef GD_KSW_PREFETCH
+#define GD_KSW_PREFETCH 0 // 1: load the next step's chunk before computing the current one
+#endif
+#ifndef GD_KSW_HOTMEM
+#define GD_KSW_HOTMEM 0 // 1: sweep constants come from device memory (stay in registers) instead of the constant bank
+#endif
+
 namespace gd {
 
 enum {
@@ -70,7 +77,7 @@ struct KswConsts {
 	uint32_t TA, TB, TA2, TB2;   // 16x2 tags (low byte of each half)
 	uint32_t TAGX;               // xor applied to the extracted tags -> 0..4 as in ksw2.h
 	uint32_t MCH4, MIS4, SCN4;   // byte-replicated match / mismatch / ambiguous scores
-	uint32_t INIT_U, INIT_X, INIT_Y, INIT_X2, INIT_Y2; // 16x2 initial column state
+	uint32_t INIT_A, INIT_B, INIT_C; // initial column state, two columns per word, packed as in the ring (see REC_*)
 	int32_t q, e, q2, e2;        // after ordering the two pieces (ksw2_extd2_sse.c:78)
 	int32_t qe_seed;             // q+e BEFORE ordering: seeds H (ksw2_extd2_sse.c:68,358,382)
 	int32_t long_thres, long_diff;
@@ -78,6 +85,8 @@ struct KswConsts {
 	int32_t degenerate;          // m<=1 or -min(mat) > 2(q+e): every call returns the reset ez
 	int32_t force_slow_max;      // test hook: always take the literal row-max scan (exact mode)
 };
+
+struct KswHot;
 
 // One launch works on pairs [base, base+n) of the caller's batch ("chunk"); the packed sequence
 // arenas and the backtrack arena are indexed by the chunk-local pair number with uniform strides.
@@ -93,7 +102,8 @@ struct KswBatch {
 	int64_t p_stride;
 	KswResult *res;      // global index
 	int32_t *ticket;     // dynamic pair dispenser (chunk-local)
-	int32_t ring;        // R: columns per ring (multiple of 16)
+	const KswHot *hot;   // sweep constants in device memory (see KswHot)
+	int32_t ring;        // R: columns per ring (multiple of 8)
 	int32_t group_smem;  // bytes of shared memory per group
 };
 
@@ -110,8 +120,8 @@ GD_DEV int gap_delta(int r, const KswConsts &C)
 // In: s (tag TS), xt1/x2t1 (left neighbours, tags TA/TA2), vt1, ut (no tag), y/y2 (tags TB/TB2).
 // Out: new u,v,x,y,x2,y2, the word zt whose low bytes hold the arg-max tag, and four words whose
 // bit 15/31 is the continuation flag of E,F,E~,F~.
-template <bool RIGHT>
-GD_DEV void cell2(const KswConsts &C, uint32_t s, uint32_t xt1, uint32_t vt1, uint32_t x2t1, uint32_t ut, uint32_t &y,
+template <bool RIGHT, class CT>
+GD_DEV void cell2(const CT &C, uint32_t s, uint32_t xt1, uint32_t vt1, uint32_t x2t1, uint32_t ut, uint32_t &y,
                   uint32_t &y2, uint32_t &u_new, uint32_t &v_new, uint32_t &x_new, uint32_t &x2_new, uint32_t &zt,
                   uint32_t &fa, uint32_t &fb, uint32_t &fa2, uint32_t &fb2)
 {
@@ -137,7 +147,8 @@ GD_DEV void cell2(const KswConsts &C, uint32_t s, uint32_t xt1, uint32_t vt1, ui
 
 // 4 ksw2 backtrack bytes from two registers' worth of cells (A = (ca,ca+4), B = (cb,cb+4)); the
 // byte order is (ca, ca+4, cb, cb+4), i.e. the strided chunk order.
-GD_DEV uint32_t make_dir4(const KswConsts &C, uint32_t ztA, uint32_t ztB, uint32_t faA, uint32_t faB, uint32_t fbA,
+template <class CT>
+GD_DEV uint32_t make_dir4(const CT &C, uint32_t ztA, uint32_t ztB, uint32_t faA, uint32_t faB, uint32_t fbA,
                           uint32_t fbB, uint32_t fa2A, uint32_t fa2B, uint32_t fb2A, uint32_t fb2B)
 { // selector 0xfdb9: sign-replicated bytes 1,3 of A then 1,3 of B -> 0xff where the flag bit is set
 	uint32_t d = (prmt(ztA, ztB, 0x6420) & 0x07070707u) ^ C.TAGX;
@@ -150,7 +161,8 @@ GD_DEV uint32_t make_dir4(const KswConsts &C, uint32_t ztA, uint32_t ztB, uint32
 
 // Score bytes for 4 cells with the AVX-512 xor-table rule (ksw2_extd2_avx.c:187-208,312-313):
 // pmat[(t ^ q') & 15] with pmat = {mch, mis x3, scN x9, 0 x3}; a byte with bit 7 set gives 0.
-GD_DEV uint32_t score4(const KswConsts &C, uint32_t tc, uint32_t qc)
+template <class CT>
+GD_DEV uint32_t score4(const CT &C, uint32_t tc, uint32_t qc)
 {
 	uint32_t x = tc ^ qc, idx = x & 0x0f0f0f0fu;
 	uint32_t nz = (idx + 0x7f7f7f7fu) | idx;  // bit7 of each byte: idx != 0
@@ -182,16 +194,17 @@ GD_DEV int ksw_ncol16(int qlen, int tlen, int w)
 
 // Shared memory of one group: a ring of NR = R/8 chunk records followed by the staged sequences.
 // One record holds everything the sweep needs for 8 columns, so a lane-step addresses it with
-// immediate offsets: 16-bit cell images of u,v,x,y,x2,y2 (6 x 16 B, chunk-strided order), the score
-// bytes (8 B, chunk-strided), 8 B padding, and in exact mode H (8 x int32, natural column order).
-// Record sizes 112 / 144 B make the four lanes of a group, and the two groups that share a 128-bit
-// access phase, hit disjoint banks.
-enum { REC_U = 0, REC_V = 16, REC_X = 32, REC_Y = 48, REC_X2 = 64, REC_Y2 = 80, REC_S = 96, REC_H = 112 };
-template <bool EXACT> struct RecSize { enum { value = EXACT ? 144 : 112 }; };
+// immediate offsets.  The six int8 state arrays are stored two to a 16-bit slot (8 slots per array
+// pair, chunk-strided order): A = (x << 8 | v), B = (x2 << 8 | u), C = (y << 8 | y2); then the score
+// bytes (8 B, chunk-strided) and, in exact mode, H (8 x int32, natural column order).  Record sizes
+// 80 / 96 B keep the four lanes of a group and the two groups that share a 128-bit access phase
+// (group pitch == 64 resp. 16 mod 128) on disjoint banks.
+enum { REC_A = 0, REC_B = 16, REC_C = 32, REC_S = 48, REC_H = 64 };
+template <bool EXACT> struct RecSize { enum { value = EXACT ? 96 : 80 }; };
 static inline int ksw_group_smem_bytes(int R, bool exact, int seq_bytes)
 {
-	int b = (R / 8) * (exact ? 144 : 112) + seq_bytes;
-	b = (b + 127) / 128 * 128 + 64; // == 64 (mod 128): two groups sharing a 128-bit access phase hit disjoint banks
+	int b = (R / 8) * (exact ? 96 : 80) + seq_bytes;
+	b = (b + 127) / 128 * 128 + (exact ? 16 : 64);
 	return b;
 }
 
@@ -231,9 +244,13 @@ GD_DEV uint8_t *col_rec(uint8_t *ring, int rec_bytes, int NR, int st_rec, int d)
 	if (k < 0) k += NR;
 	return ring + k * rec_bytes;
 }
-GD_DEV uint16_t *col_hw(uint8_t *ring, int rec_bytes, int NR, int st_rec, int d, int arr)
-{ // 16-bit cell image of one column in state array `arr` (REC_U .. REC_Y2)
+GD_DEV uint16_t *col_slot(uint8_t *ring, int rec_bytes, int NR, int st_rec, int d, int arr)
+{ // 16-bit slot of one column in array pair `arr` (REC_A/REC_B/REC_C): high byte / low byte as listed at REC_*
 	return (uint16_t *)(col_rec(ring, rec_bytes, NR, st_rec, d) + arr + 2 * chunk_pos(d & 7));
+}
+GD_DEV int col_lo8(uint8_t *ring, int rec_bytes, int NR, int st_rec, int d, int arr)
+{ // v (REC_A) or u (REC_B) of one column as a signed value
+	return (int)(int8_t)(*col_slot(ring, rec_bytes, NR, st_rec, d, arr) & 0xff);
 }
 GD_DEV int32_t *col_H(uint8_t *ring, int rec_bytes, int NR, int st_rec, int d)
 {
@@ -262,6 +279,36 @@ GD_DEV void row_max_literal(uint8_t *ring, int rec_bytes, int NR, int st_rec, in
 	}
 }
 
+// The constants the chunk sweep touches every step.  They are read from device memory (written by the
+// pack kernel) rather than from the kernel parameters: values that come from the constant bank are
+// re-loaded by ptxas inside the loop (10 LDC per step), values loaded from global memory stay in registers.
+struct KswHot {
+	uint32_t MCH16, Q1, Q21, NEGQE, NEGQE2, TS4, TA, TB, TA2, TB2, TAGX, MCH4, MIS4, SCN4, pad0, pad1;
+};
+GD_DEV KswHot ksw_hot_from_consts(const KswConsts &C)
+{
+	KswHot h;
+	h.MCH16 = C.MCH16, h.Q1 = C.Q1, h.Q21 = C.Q21, h.NEGQE = C.NEGQE, h.NEGQE2 = C.NEGQE2, h.TS4 = C.TS4, h.TA = C.TA;
+	h.TB = C.TB, h.TA2 = C.TA2, h.TB2 = C.TB2, h.TAGX = C.TAGX, h.MCH4 = C.MCH4, h.MIS4 = C.MIS4, h.SCN4 = C.SCN4;
+	h.pad0 = h.pad1 = 0;
+	return h;
+}
+GD_DEV KswHot ksw_hot_load(const KswHot *p)
+{
+	KswHot h;
+	const uint32_t *w = (const uint32_t *)p;
+	uint32_t *o = (uint32_t *)&h;
+	for (int i = 0; i < 16; ++i) o[i] = ld_volatile(w + i);
+	return h;
+}
+
+// Everything one lane reads from shared memory for one chunk (loaded one step ahead of its use).
+struct StepIn {
+	uint4 SA, SB, SC, ha, hb;
+	uint2 old, tw;
+	uint32_t am1, bm1, q0, q1, q2;
+};
+
 GD_DEV uint4 rep4(uint32_t v)
 {
 	uint4 q;
@@ -272,9 +319,11 @@ GD_DEV uint4 rep4(uint32_t v)
 // One warp, 32/G pairs at a time.  All control flow is warp-uniform (every loop runs for the
 // maximum trip count over the groups of the warp, per-lane work is predicated), so every barrier
 // and vote uses the full mask.  A group that finishes its pair fetches the next one at once.
-template <int G, bool RIGHT, bool EXACT, bool WITH_P>
+// MODE: 0 = KSW_EZ_APPROX_MAX, 1 = APPROX_MAX | APPROX_DROP, 2 = exact maximum (+ Z-drop, mqe, mte).
+template <int G, bool RIGHT, int MODE, bool WITH_P>
 GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_warp, const uint8_t *lut, int lane)
 {
+	const bool EXACT = MODE == 2;
 	const uint32_t FULL = 0xffffffffu;
 	const int REC = RecSize<EXACT>::value;
 	const int li = lane & (G - 1), leader = lane & ~(G - 1);
@@ -283,12 +332,17 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 	uint8_t *const tsm = ring + NR * REC, *const qsm = tsm + B.t_stride;
 	const uint2 *lut_fresh = (const uint2 *)lut;
 	const uint32_t *lut_pk = (const uint32_t *)(lut + 1152);
+#if GD_KSW_HOTMEM
+	const KswHot K = ksw_hot_load(B.hot);
+#else
+	const KswHot K = ksw_hot_from_consts(C);
+#endif
 
 	// ---- per-group state (identical in all lanes of a group) ----
 	bool have = false, done = false;
-	int pair = 0, qlen = 0, tlen = 0, w = 0, T16 = 0, nblk_t = 0, ncol16 = 0, nrows = 0;
+	int pair = 0, qlen = 1, tlen = 1, w = 0, T16 = 16, nblk_t = 1, ncol16 = 32, nrows = 1;
 	uint8_t *prow = 0; // backtrack row pointer of the current row
-	int r = 0, rows_exec = 0, last_st = -1, last_en = -1, st_rec = 0, st_cur = 0, init_hi = 0;
+	int r = 0, rows_exec = 0, last_st = -1, last_en = -1, st_rec = 0, st_cur = 0, init_hi = 1;
 	int H0 = 0, H0_t = 0;                   // approx mode
 	int Mprev = 0, Hleft = 0, st0_prev = 0; // exact mode
 	KswResult res;
@@ -316,6 +370,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 					res.tb_i = res.tb_j = -1, res.rows_done = 0;
 					if (C.degenerate || qlen <= 0 || tlen <= 0) {
 						if (li == 0) B.res[pair] = res; // reset record, ksw2_extd2_sse.c:75-76,100
+						qlen = tlen = 1;
 					} else {
 						if (w < 0) w = imax(tlen, qlen);
 						T16 = (tlen + 15) & ~15, nblk_t = T16 >> 4;
@@ -324,15 +379,15 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 						tpk = B.tpk + (size_t)lp * B.t_stride;
 						qpk = B.qpk + (size_t)lp * B.q_stride;
 						prow = WITH_P ? B.p + (size_t)lp * B.p_stride : 0;
-						r = 0, rows_exec = 0, last_st = last_en = -1, st_rec = 0, st_cur = 0, init_hi = 0;
-						H0 = 0, H0_t = 0;
+						r = 0, rows_exec = 0, last_st = last_en = -1, st_rec = 0, st_cur = 0, init_hi = 1;
+						H0 = -C.qe_seed, H0_t = 0; // row 0 adds v[0]: H0 = v[0] - qe (ksw2_extd2_sse.c:382)
 						Mprev = -C.qe_seed, Hleft = GD_KSW_NEG_INF, st0_prev = 0;
 						have = true, fresh = true;
 					}
 				}
 			}
-			// stage the padded sequences of fresh pairs (strides are launch-uniform); the previous
-			// pair's readers are past their last row (every lane of the warp is here)
+			// stage the padded sequences of fresh pairs (strides are launch-uniform) and give block 0 of the
+			// ring the reference's initial values; the previous pair's readers are past their last row
 			{
 				const int nt = B.t_stride >> 2, nq = B.q_stride >> 2;
 				for (int i = li; i < nt + nq; i += G)
@@ -340,63 +395,78 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 						if (i < nt) ((uint32_t *)tsm)[i] = ((const uint32_t *)tpk)[i];
 						else ((uint32_t *)qsm)[i - nt] = ((const uint32_t *)qpk)[i - nt];
 					}
+				if (fresh && li < 2) {
+					uint8_t *rc = ring + li * REC;
+					*(uint4 *)(rc + REC_A) = rep4(C.INIT_A), *(uint4 *)(rc + REC_B) = rep4(C.INIT_B);
+					*(uint4 *)(rc + REC_C) = rep4(C.INIT_C);
+					uint2 z2;
+					z2.x = z2.y = 0;
+					*(uint2 *)(rc + REC_S) = z2;
+					if (EXACT) {
+						uint4 h0 = rep4((uint32_t)GD_KSW_NEG_INF);
+						*(uint4 *)(rc + REC_H + 16) = h0;
+						if (li == 0) h0.x = (uint32_t)(-C.qe_seed); // the bulk update of row 0 adds v[0]: H[0] = v[0] - qe
+						*(uint4 *)(rc + REC_H) = h0;
+					}
+				}
 			}
 			sync_warp(FULL);
 			if (!ballot(FULL, have)) break; // nothing left anywhere in this warp
 		}
 		// ================= one anti-diagonal for every group that has a pair =================
-		bool active = have, finish = false;
-		Bounds bd;
-		bd.st0 = bd.en0 = bd.st = 0, bd.en = 15;
-		if (active && !row_bounds(r, qlen, tlen, w, bd)) {
-			res.zdropped = 1; // band closed, ksw2_extd2_sse.c:142-145
-			active = false, finish = true;
-			bd.st0 = bd.en0 = bd.st = 0, bd.en = 15;
-		}
-		const int st = bd.st, en = bd.en, st0 = bd.st0, en0 = bd.en0;
-		int fe = 16; // score row is rewritten on [st0, fe)
-		const int en1 = st0 + ((en0 - st0) & ~3); // exact mode: end of the 4-lane part of the row scan
-		// exact mode: cells handled outside the bulk update (lanes 0..2: scan tail, lane 3: column en0)
-		int sp_t = -1, sp_h = 0;
+		// (groups without a pair run the same instructions on a one-cell dummy row; their stores are off)
+		int st0 = imax(imax(0, r - qlen + 1), (r - w + 1) >> 1); // ksw2_extd2_sse.c:133-147
+		int en0 = imin(imin(tlen - 1, r), (r + w) >> 1);
+		bool finish = false;
+		bool active = have;
+		if (have && st0 > en0) res.zdropped = 1, finish = true, active = false; // band closed, ksw2_extd2_sse.c:142-145
+		if (!active) st0 = 0, en0 = 0;
+		const int st = st0 & ~15, en = en0 | 15;
 		// ---- phase A: ring bookkeeping, boundary injections ----
-		if (active) {
-			if (st != st_cur) st_rec = wrap(st_rec + ((st - st_cur) >> 3), NR), st_cur = st;
-			fe = imin(st0 + (((en0 - st0) >> 4) + 1) * 16, T16);
+		if (active && st != st_cur) st_rec = wrap(st_rec + 2, NR), st_cur = st; // st moves by exactly one 16-column block
+		const int fe = active ? imin(st0 + (((en0 - st0) >> 4) + 1) * 16, T16) : 16; // score row is rewritten on [st0, fe)
+		const int en1 = st0 + ((en0 - st0) & ~3); // exact mode: end of the 4-lane part of the row scan
+		{
 			// The block that enters the window gets the reference's initial values (its memset / kcalloc).
 			// en0 grows by at most one per row, so at most one block enters, and none of this row's
-			// single-column patches below can fall into it (they touch columns <= en0|15) except on row 0.
-			const int bneed = imin((en0 + 15) >> 4, nblk_t - 1);
-			if (init_hi <= bneed) {
-				if (li < 2) {
+			// single-column patches below can fall into it (they touch columns <= en0|15; block 0 is
+			// initialised when the pair is fetched).
+			const bool need_init = active && init_hi <= imin((en0 + 15) >> 4, nblk_t - 1);
+			if (ballot(FULL, need_init)) {
+				if (need_init && li < 2) {
 					uint8_t *rc = col_rec(ring, REC, NR, st_rec, init_hi * 16 + li * 8 - st);
-					*(uint4 *)(rc + REC_U) = rep4(C.INIT_U), *(uint4 *)(rc + REC_V) = rep4(C.INIT_U);
-					*(uint4 *)(rc + REC_X) = rep4(C.INIT_X), *(uint4 *)(rc + REC_Y) = rep4(C.INIT_Y);
-					*(uint4 *)(rc + REC_X2) = rep4(C.INIT_X2), *(uint4 *)(rc + REC_Y2) = rep4(C.INIT_Y2);
+					*(uint4 *)(rc + REC_A) = rep4(C.INIT_A), *(uint4 *)(rc + REC_B) = rep4(C.INIT_B);
+					*(uint4 *)(rc + REC_C) = rep4(C.INIT_C);
 					uint2 z2;
 					z2.x = z2.y = 0;
 					*(uint2 *)(rc + REC_S) = z2;
 					if (EXACT)
 						*(uint4 *)(rc + REC_H) = rep4((uint32_t)GD_KSW_NEG_INF), *(uint4 *)(rc + REC_H + 16) = rep4((uint32_t)GD_KSW_NEG_INF);
 				}
-				++init_hi;
+				if (need_init) ++init_hi;
 			}
 		}
-		if (ballot(FULL, active && r == 0)) sync_warp(FULL); // row 0 patches column 0 of the block initialised just above
-		if (active) {
-			if (en >= r && li == G - 1) { // ksw2_extd2_sse.c:160-163
-				*col_hw(ring, REC, NR, st_rec, r - st, REC_Y) = (uint16_t)(C.INIT_Y & 0xffff);
-				*col_hw(ring, REC, NR, st_rec, r - st, REC_Y2) = (uint16_t)(C.INIT_Y2 & 0xffff);
-				*col_hw(ring, REC, NR, st_rec, r - st, REC_U) = (uint16_t)((gap_delta(r, C) & 0xff) << 8);
+		{
+			const int gd = gap_delta(r, C);
+			// ksw2_extd2_sse.c:160-163: y[r], y2[r], u[r]
+			uint8_t *pc = col_rec(ring, REC, NR, st_rec, active ? imin(r - st, en - st) : 0) + 2 * chunk_pos(r & 7);
+			if (active && en >= r && li == G - 1) {
+				*(uint16_t *)(pc + REC_C) = (uint16_t)(C.INIT_C & 0xffff); // y, y2
+				*(pc + REC_B) = (uint8_t)gd;                               // u (low byte of B)
 			}
-			if (li == 0 && !(st > 0 && st - 1 >= last_st && st - 1 <= last_en)) {
-				// left boundary (ksw2_extd2_sse.c:149-159): lives in the ring slot of column st-1,
-				// which holds the previous row's values when that column was in its range
-				*col_hw(ring, REC, NR, st_rec, -1, REC_X) = (uint16_t)(C.INIT_X & 0xffff);
-				*col_hw(ring, REC, NR, st_rec, -1, REC_X2) = (uint16_t)(C.INIT_X2 & 0xffff);
-				*col_hw(ring, REC, NR, st_rec, -1, REC_V) =
-				    st > 0 ? (uint16_t)(C.INIT_U & 0xffff) : (uint16_t)((gap_delta(r, C) & 0xff) << 8);
+			// left boundary (ksw2_extd2_sse.c:149-159): lives in the ring slot of column st-1, which holds the
+			// previous row's values when that column was in its range
+			uint8_t *pl = ring + (st_rec == 0 ? NR - 1 : st_rec - 1) * REC + 14;
+			if (active && li == 0 && !(st > 0 && st - 1 >= last_st && st - 1 <= last_en)) {
+				const uint32_t v1 = st > 0 ? (C.INIT_A & 0xffu) : (uint32_t)(gd & 0xff);
+				*(uint16_t *)(pl + REC_A) = (uint16_t)((C.INIT_A & 0xff00u) | v1); // x, v
+				*(pl + REC_B + 1) = (uint8_t)(C.INIT_B >> 8);                      // x2 (high byte of B)
 			}
-			if (EXACT) {
+		}
+		// exact mode: cells handled outside the bulk update (lanes 0..2: scan tail, lane 3: column en0)
+		int sp_t = -1, sp_h = 0;
+		if (EXACT) {
+			if (active) {
 				// the column that left [st0,en0] keeps its last score for "H[en0-1]" of one-cell rows
 				if (r > 0 && st0 > st0_prev) Hleft = *col_H(ring, REC, NR, st_rec, st0 - 1 - st);
 				if (li < 3) {
@@ -408,12 +478,9 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 					}
 				}
 			}
-		}
-		if (EXACT) {
 			sync_warp(FULL); // all of the loads above precede the sentinel stores below
 			if (active) {
 				if (li == 3 && r > 0 && st0 > st0_prev) *col_H(ring, REC, NR, st_rec, st0 - 1 - st) = GD_KSW_NEG_INF;
-				if (li == 3 && r == 0) *col_H(ring, REC, NR, st_rec, 0) = -C.qe_seed; // the bulk update adds v[0]: H[0] = v[0] - qe
 				if (sp_t >= 0) *col_H(ring, REC, NR, st_rec, sp_t - st) = GD_KSW_NEG_INF; // keeps the bulk scan off these cells
 			}
 		}
@@ -422,80 +489,107 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 		int run = (int)0x80000000; // exact mode: best (relative score << 16 | priority) key of this lane
 		{
 			const int cbeg = st >> 3;
-			int ctop = active ? (imax(en, fe - 1) >> 3) : -1; // chunk of lane G-1 in the current step
+			const int ctop = imax(en, fe - 1) >> 3; // chunk of lane G-1 in the first step
+			const int nsteps = reduce_max(FULL, active ? (ctop - cbeg + G) / G : 0);
 			const int qshift = active ? qlen - 1 - r + GD_KSW_QFRONT : GD_KSW_QFRONT; // qsm offset of the query base under column 0
+			const uint32_t qsh = (uint32_t)(qshift & 3) * 8; // chunks start at multiples of 8: same byte phase in every step
 			const int nMprev = -Mprev;
 			uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;
 			if (EXACT) {
 				const uint4 pk = *(const uint4 *)(lut_pk + (((0 - st0) & 3) << 2));
 				pk0 = pk.x, pk1 = pk.y, pk2 = pk.z, pk3 = pk.w;
 			}
-			while (ballot(FULL, active && ctop >= cbeg)) {
-				// Lanes without a chunk in this step run the same instructions on chunk cbeg of their own ring
-				// (all addresses stay in range) and only their stores are predicated off: no divergence.
-				const int c0 = ctop - (G - 1 - li);
-				const bool valid = active && c0 >= cbeg;
-				const int c = valid ? c0 : cbeg;
+			// Lanes without a chunk in a step run the same instructions on chunk cbeg of their own ring (all
+			// addresses stay in range) and only their stores are predicated off: no divergence.
+			int c0 = ctop - (G - 1 - li);      // this lane's chunk in the current step (may be below cbeg)
+			bool valid = active && c0 >= cbeg;
+			int c = valid ? c0 : cbeg;
+			int k = st_rec + (c - cbeg);       // ring position of the chunk's record
+			if (k >= NR) k -= NR;
+			auto load_step = [&](int cc, int kk, StepIn &in) {
+				uint8_t *const rc = ring + kk * REC;
+				uint8_t *const rp = ring + (kk == 0 ? NR - 1 : kk - 1) * REC; // record of the left neighbour chunk
+				const int tb = cc << 3;
+				in.tw = *(const uint2 *)(tsm + tb);
+				const uint32_t *qw = (const uint32_t *)(qsm + ((qshift + tb) & ~3));
+				in.q0 = qw[0], in.q1 = qw[1], in.q2 = qw[2];
+				in.old = *(const uint2 *)(rc + REC_S);
+				in.SA = *(const uint4 *)(rc + REC_A), in.SB = *(const uint4 *)(rc + REC_B), in.SC = *(const uint4 *)(rc + REC_C);
+				in.am1 = *(const uint16_t *)(rp + REC_A + 14), in.bm1 = *(const uint16_t *)(rp + REC_B + 14);
+				if (EXACT) in.ha = *(const uint4 *)(rc + REC_H), in.hb = *(const uint4 *)(rc + REC_H + 16);
+			};
+#if GD_KSW_PREFETCH
+			StepIn nx;
+			load_step(c, k, nx);
+#endif
+			for (int step = 0; step < nsteps; ++step) {
+#if GD_KSW_PREFETCH
+				const StepIn in = nx;
+#else
+				StepIn in;
+				load_step(c, k, in);
+#endif
+				const bool cvalid = valid;
 				const int tb = c << 3, d = tb - st;
-				const bool core = valid && tb <= en;
-				int k = st_rec + (d >> 3);
-				if (k >= NR) k -= NR;
+				const bool core = cvalid && tb <= en;
 				uint8_t *const rc = ring + k * REC;
-				uint8_t *const rp = ring + (k == 0 ? NR - 1 : k - 1) * REC; // record of the left neighbour chunk
+				// the next step's chunk: G records further down; its loads do not touch anything this step stores
+				c0 -= G;
+				valid = active && c0 >= cbeg;
+				c = valid ? c0 : cbeg;
+				k = valid ? k - G : st_rec;
+				if (k < 0) k += NR;
+#if GD_KSW_PREFETCH
+				if (step + 1 < nsteps) load_step(c, k, nx);
+#endif
 				// score bytes of the 8 columns (xor-table rule), merged with the stale row outside [st0,fe)
 				uint32_t sw0, sw1;
 				{
-					const uint2 tw = *(const uint2 *)(tsm + tb);
-					const int qi = qshift + tb;
-					const uint32_t *qw = (const uint32_t *)(qsm + (qi & ~3));
-					const uint32_t q0 = qw[0], q1 = qw[1], q2 = qw[2], sh = (uint32_t)(qi & 3) * 8;
-					const uint32_t qa = funnel_r(q0, q1, sh), qb = funnel_r(q1, q2, sh);
-					const uint32_t f0 = score4(C, tw.x, prmt(qa, qb, 0x5140)), f1 = score4(C, tw.y, prmt(qa, qb, 0x7362));
+					const uint32_t qa = funnel_r(in.q0, in.q1, qsh), qb = funnel_r(in.q1, in.q2, qsh);
+					const uint32_t f0 = score4(K, in.tw.x, prmt(qa, qb, 0x5140)), f1 = score4(K, in.tw.y, prmt(qa, qb, 0x7362));
 					const int lo = imax(st0 - tb, 0), hi = imax(imin(fe - tb, 8), 0);
 					const uint2 m = lut_fresh[lo * 9 + hi];
-					const uint2 old = *(const uint2 *)(rc + REC_S);
-					sw0 = (f0 & m.x) | (old.x & ~m.x), sw1 = (f1 & m.y) | (old.y & ~m.y);
+					sw0 = (f0 & m.x) | (in.old.x & ~m.x), sw1 = (f1 & m.y) | (in.old.y & ~m.y);
 				}
-				const uint4 U = *(const uint4 *)(rc + REC_U), V = *(const uint4 *)(rc + REC_V), X = *(const uint4 *)(rc + REC_X);
-				uint4 Y = *(const uint4 *)(rc + REC_Y), Y2 = *(const uint4 *)(rc + REC_Y2);
-				const uint4 X2 = *(const uint4 *)(rc + REC_X2);
-				const uint32_t xm1 = *(const uint16_t *)(rp + REC_X + 14), vm1 = *(const uint16_t *)(rp + REC_V + 14);
-				const uint32_t x2m1 = *(const uint16_t *)(rp + REC_X2 + 14);
-				uint4 ha, hb;
-				if (EXACT) ha = *(const uint4 *)(rc + REC_H), hb = *(const uint4 *)(rc + REC_H + 16);
+				// unpack the slots into tagged 16x2 images; x,v,x2 come from the column to the left
+				const uint4 SA = in.SA, SB = in.SB, SC = in.SC;
+				const uint32_t SAs = prmt(in.am1, SA.w, 0x5410), SBs = prmt(in.bm1, SB.w, 0x5410); // (c-1, c3)
+				const uint32_t HI = 0xff00ff00u;
+				uint32_t u0, v0, x0, x20, zt0, fa0, fb0, fa20, fb20, y0 = (SC.x & HI) | K.TB, y20 = prmt(SC.x, K.TB2, 0x2404);
+				uint32_t u1, v1, x1, x21, zt1, fa1, fb1, fa21, fb21, y1 = (SC.y & HI) | K.TB, y21 = prmt(SC.y, K.TB2, 0x2404);
+				uint32_t u2, v2, x2, x22, zt2, fa2, fb2, fa22, fb22, y2 = (SC.z & HI) | K.TB, y22 = prmt(SC.z, K.TB2, 0x2404);
+				uint32_t u3, v3, x3, x23, zt3, fa3, fb3, fa23, fb23, y3 = (SC.w & HI) | K.TB, y23 = prmt(SC.w, K.TB2, 0x2404);
+				cell2<RIGHT>(K, prmt(sw0, K.TS4, 0x1404), (SAs & HI) | K.TA, prmt(SAs, 0, 0x2404), (SBs & HI) | K.TA2,
+				             prmt(SB.x, 0, 0x2404), y0, y20, u0, v0, x0, x20, zt0, fa0, fb0, fa20, fb20);
+				cell2<RIGHT>(K, prmt(sw0, K.TS4, 0x3424), (SA.x & HI) | K.TA, prmt(SA.x, 0, 0x2404), (SB.x & HI) | K.TA2,
+				             prmt(SB.y, 0, 0x2404), y1, y21, u1, v1, x1, x21, zt1, fa1, fb1, fa21, fb21);
+				cell2<RIGHT>(K, prmt(sw1, K.TS4, 0x1404), (SA.y & HI) | K.TA, prmt(SA.y, 0, 0x2404), (SB.y & HI) | K.TA2,
+				             prmt(SB.z, 0, 0x2404), y2, y22, u2, v2, x2, x22, zt2, fa2, fb2, fa22, fb22);
+				cell2<RIGHT>(K, prmt(sw1, K.TS4, 0x3424), (SA.z & HI) | K.TA, prmt(SA.z, 0, 0x2404), (SB.z & HI) | K.TA2,
+				             prmt(SB.w, 0, 0x2404), y3, y23, u3, v3, x3, x23, zt3, fa3, fb3, fa23, fb23);
 				sync_warp(FULL); // every lane has read its left neighbour's old column before anybody stores
-				uint32_t u0, v0, x0, x20, zt0, fa0, fb0, fa20, fb20;
-				uint32_t u1, v1, x1, x21, zt1, fa1, fb1, fa21, fb21;
-				uint32_t u2, v2, x2, x22, zt2, fa2, fb2, fa22, fb22;
-				uint32_t u3, v3, x3, x23, zt3, fa3, fb3, fa23, fb23;
-				cell2<RIGHT>(C, prmt(sw0, C.TS4, 0x1404), prmt(xm1, X.w, 0x5410), prmt(vm1, V.w, 0x5410),
-				             prmt(x2m1, X2.w, 0x5410), U.x, Y.x, Y2.x, u0, v0, x0, x20, zt0, fa0, fb0, fa20, fb20);
-				cell2<RIGHT>(C, prmt(sw0, C.TS4, 0x3424), X.x, V.x, X2.x, U.y, Y.y, Y2.y, u1, v1, x1, x21, zt1, fa1, fb1, fa21,
-				             fb21);
-				cell2<RIGHT>(C, prmt(sw1, C.TS4, 0x1404), X.y, V.y, X2.y, U.z, Y.z, Y2.z, u2, v2, x2, x22, zt2, fa2, fb2, fa22,
-				             fb22);
-				cell2<RIGHT>(C, prmt(sw1, C.TS4, 0x3424), X.z, V.z, X2.z, U.w, Y.w, Y2.w, u3, v3, x3, x23, zt3, fa3, fb3, fa23,
-				             fb23);
-				if (valid) {
+				if (cvalid) {
 					uint2 sv;
 					sv.x = sw0, sv.y = sw1;
 					*(uint2 *)(rc + REC_S) = sv;
 				}
 				if (core) {
-					uint4 o;
-					o.x = u0, o.y = u1, o.z = u2, o.w = u3, *(uint4 *)(rc + REC_U) = o;
-					o.x = v0, o.y = v1, o.z = v2, o.w = v3, *(uint4 *)(rc + REC_V) = o;
-					o.x = x0, o.y = x1, o.z = x2, o.w = x3, *(uint4 *)(rc + REC_X) = o;
-					o.x = x20, o.y = x21, o.z = x22, o.w = x23, *(uint4 *)(rc + REC_X2) = o;
-					*(uint4 *)(rc + REC_Y) = Y, *(uint4 *)(rc + REC_Y2) = Y2;
+					uint4 o; // repack: selector 0x3715 = (hi.b3, lo.b3, hi.b1, lo.b1)
+					o.x = prmt(x0, v0, 0x3715), o.y = prmt(x1, v1, 0x3715), o.z = prmt(x2, v2, 0x3715), o.w = prmt(x3, v3, 0x3715);
+					*(uint4 *)(rc + REC_A) = o;
+					o.x = prmt(x20, u0, 0x3715), o.y = prmt(x21, u1, 0x3715), o.z = prmt(x22, u2, 0x3715), o.w = prmt(x23, u3, 0x3715);
+					*(uint4 *)(rc + REC_B) = o;
+					o.x = prmt(y0, y20, 0x3715), o.y = prmt(y1, y21, 0x3715), o.z = prmt(y2, y22, 0x3715), o.w = prmt(y3, y23, 0x3715);
+					*(uint4 *)(rc + REC_C) = o;
 					if (WITH_P) {
 						uint2 dv;
-						dv.x = make_dir4(C, zt0, zt1, fa0, fa1, fb0, fb1, fa20, fa21, fb20, fb21);
-						dv.y = make_dir4(C, zt2, zt3, fa2, fa3, fb2, fb3, fa22, fa23, fb22, fb23);
+						dv.x = make_dir4(K, zt0, zt1, fa0, fa1, fb0, fb1, fa20, fa21, fb20, fb21);
+						dv.y = make_dir4(K, zt2, zt3, fa2, fa3, fb2, fb3, fa22, fa23, fb22, fb23);
 						*(uint2 *)(prow + d) = dv;
 					}
 				}
 				if (EXACT) { // H[t] += v[t] on the whole chunk; columns outside [st0,en1) hold sentinels
+					uint4 ha = in.ha, hb = in.hb;
 					ha.x += prmt(v0, 0, 0x9991), hb.x += prmt(v0, 0, 0xbbb3);
 					ha.y += prmt(v1, 0, 0x9991), hb.y += prmt(v1, 0, 0xbbb3);
 					ha.z += prmt(v2, 0, 0x9991), hb.z += prmt(v2, 0, 0xbbb3);
@@ -516,29 +610,22 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 						run = imax3(run, k0, k4), run = imax3(run, k1, k5), run = imax3(run, k2, k6), run = imax3(run, k3, k7);
 					}
 				}
-				ctop -= G;
 			}
 		}
 		sync_warp(FULL);
 		// ---- phase C: score tracking ----
 		int stop = 0;
 		if (!EXACT) { // ksw2_extd2_sse.c:367-383 (every lane of the group tracks the same H0)
+			// v[T] and u[T+1] of the updated row, T = last_H0_t (T >= st0-1 always holds; row 0 starts from H0 = -qe)
+			const int T = active ? H0_t : 0;
+			const int d0 = col_lo8(ring, REC, NR, st_rec, imax(T - st, 0), REC_A);
+			const int d1 = col_lo8(ring, REC, NR, st_rec, imin(T + 1 - st, en - st), REC_B);
+			const bool in0 = T >= st0 && T <= en0, in1 = T + 1 >= st0 && T + 1 <= en0;
+			const bool take_v = in0 && (!in1 || d0 > d1);
 			if (active) {
-				if (r > 0) {
-					const bool in0 = H0_t >= st0 && H0_t <= en0, in1 = H0_t + 1 >= st0 && H0_t + 1 <= en0;
-					if (in0 && in1) {
-						const int d0 = hi8(*col_hw(ring, REC, NR, st_rec, H0_t - st, REC_V));
-						const int d1 = hi8(*col_hw(ring, REC, NR, st_rec, H0_t + 1 - st, REC_U));
-						if (d0 > d1) H0 += d0;
-						else H0 += d1, ++H0_t;
-					} else if (in0) {
-						H0 += hi8(*col_hw(ring, REC, NR, st_rec, H0_t - st, REC_V));
-					} else {
-						++H0_t;
-						H0 += hi8(*col_hw(ring, REC, NR, st_rec, imax(H0_t - st, 0), REC_U));
-					}
-				} else H0 = hi8(*col_hw(ring, REC, NR, st_rec, 0, REC_V)) - C.qe_seed, H0_t = 0;
-				if (C.flag & KSW_F_APPROX_DROP) { // ksw_apply_zdrop, ksw2.h:172-188
+				H0 += take_v ? d0 : d1;
+				if (!take_v) ++H0_t;
+				if (MODE == 1) { // KSW_EZ_APPROX_DROP: ksw_apply_zdrop, ksw2.h:172-188
 					if (H0 > res.max) res.max = H0, res.max_t = H0_t, res.max_q = r - H0_t;
 					else if (H0_t >= res.max_t && r - H0_t >= res.max_q) {
 						const int tl = H0_t - res.max_t, ql = (r - H0_t) - res.max_q, l = tl > ql ? tl - ql : ql - tl;
@@ -551,7 +638,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			// the cells kept out of the bulk update: scan tail (H += v) and column en0 (H[en0-1] + u[en0])
 			if (active && sp_t >= 0) {
 				const int cc = sp_t - st;
-				const int hn = sp_h + hi8(*col_hw(ring, REC, NR, st_rec, cc, li == 3 ? REC_U : REC_V));
+				const int hn = sp_h + col_lo8(ring, REC, NR, st_rec, cc, li == 3 ? REC_B : REC_A);
 				*col_H(ring, REC, NR, st_rec, cc) = hn;
 				const int relc = imin(imax(hn - Mprev, GD_KSW_REL_FLOOR), 32767);
 				const uint32_t pr = li == 3 ? 0xffffu : (uint32_t)(3 - li) << 13 | (uint32_t)(GD_KSW_POS_MAX - cc);
@@ -604,6 +691,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 				B.res[pair] = res;
 			}
 			have = false;
+			qlen = tlen = 1, w = 0, r = 0; // idle geometry: one dummy cell per row until the next pair arrives
 		}
 	}
 }

@@ -43,9 +43,13 @@ static inline KswConsts ksw_make_consts(int m, const int8_t *mat, int q_, int e_
 	C.NEGQE = h_pack16(-(int)(int8_t)(q + e));
 	C.NEGQE2 = h_pack16(-(int)(int8_t)(q2 + e2));
 	C.MCH4 = h_rep4(mch), C.MIS4 = h_rep4(mis), C.SCN4 = h_rep4(scn);
-	C.INIT_U = h_pack16(-q - e);
-	C.INIT_X = C.INIT_U | C.TA, C.INIT_Y = C.INIT_U | C.TB;
-	C.INIT_X2 = h_pack16(-q2 - e2) | C.TA2, C.INIT_Y2 = h_pack16(-q2 - e2) | C.TB2;
+	{ // ring slots: A = (x << 8 | v), B = (x2 << 8 | u), C = (y << 8 | y2); the reference memsets
+	  // u,v,x,y to -q-e and x2,y2 to -q2-e2 (ksw2_extd2_sse.c:111-116)
+		const uint32_t i1 = (uint32_t)((-q - e) & 0xff), i2 = (uint32_t)((-q2 - e2) & 0xff);
+		C.INIT_A = (i1 << 8 | i1) * 0x10001u;
+		C.INIT_B = (i2 << 8 | i1) * 0x10001u;
+		C.INIT_C = (i1 << 8 | i2) * 0x10001u;
+	}
 	C.q = q, C.e = e, C.q2 = q2, C.e2 = e2;
 	int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
 	if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
@@ -66,7 +70,7 @@ static inline int h_ncol16(int qlen, int tlen, int w)
 
 // Geometry of one launch, derived from upper bounds on the chunk's pairs.
 struct KswGeom {
-	int ring;        // columns per ring (multiple of 16)
+	int ring;        // columns per ring (multiple of 8)
 	int group_smem;  // bytes per group: ring + staged sequences
 	int t_stride, q_stride;
 	int64_t p_stride;
@@ -79,7 +83,7 @@ static inline KswGeom ksw_geometry(int max_qlen, int max_tlen, int max_w, bool e
 	const int T16 = (max_tlen + 15) / 16 * 16;
 	const int ncol16 = h_ncol16(max_qlen, max_tlen, max_w);
 	// live columns of a row: [st-1, en+16] (left boundary slot .. the block the score row may run into)
-	g.ring = ncol16 + 32 < T16 + 16 ? ncol16 + 32 : T16 + 16;
+	g.ring = ncol16 + 24 < T16 + 8 ? ncol16 + 24 : T16 + 8;
 	g.t_stride = T16;
 	g.q_stride = (max_qlen + 15) / 16 * 16 + 64;
 	g.group_smem = ksw_group_smem_bytes(g.ring, exact, g.t_stride + g.q_stride);

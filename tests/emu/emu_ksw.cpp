@@ -8,7 +8,7 @@
 
 using namespace gd;
 
-template <int G, bool RIGHT, bool EXACT, bool WITH_P>
+template <int G, bool RIGHT, int MODE, bool WITH_P>
 static void run_dp(const KswConsts &C, const KswBatch &B, int threads)
 {
 	int groups = threads / G;
@@ -17,23 +17,24 @@ static void run_dp(const KswConsts &C, const KswBatch &B, int threads)
 		uint8_t *sm = (uint8_t *)emu::smem();
 		ksw_build_lut(sm, tid, threads);
 		emu::sync_block();
-		ksw_warp_body<G, RIGHT, EXACT, WITH_P>(C, B, sm + GD_KSW_LUT_BYTES + (size_t)(tid >> 5) * (32 / G) * B.group_smem, sm,
-		                                       tid & 31);
+		ksw_warp_body<G, RIGHT, MODE, WITH_P>(C, B, sm + GD_KSW_LUT_BYTES + (size_t)(tid >> 5) * (32 / G) * B.group_smem, sm,
+		                                      tid & 31);
 	});
 }
 
+template <int G, bool RIGHT>
+static void dispatch2(const KswConsts &C, const KswBatch &B, int threads, int mode, bool with_p)
+{
+	if (mode == 0) with_p ? run_dp<G, RIGHT, 0, true>(C, B, threads) : run_dp<G, RIGHT, 0, false>(C, B, threads);
+	else if (mode == 1) with_p ? run_dp<G, RIGHT, 1, true>(C, B, threads) : run_dp<G, RIGHT, 1, false>(C, B, threads);
+	else with_p ? run_dp<G, RIGHT, 2, true>(C, B, threads) : run_dp<G, RIGHT, 2, false>(C, B, threads);
+}
 template <int G>
 static void dispatch(const KswConsts &C, const KswBatch &B, int threads, bool right, bool exact, bool with_p)
 {
-#define GO(R_, E_, P_) run_dp<G, R_, E_, P_>(C, B, threads)
-	if (right) {
-		if (exact) { if (with_p) GO(true, true, true); else GO(true, true, false); }
-		else { if (with_p) GO(true, false, true); else GO(true, false, false); }
-	} else {
-		if (exact) { if (with_p) GO(false, true, true); else GO(false, true, false); }
-		else { if (with_p) GO(false, false, true); else GO(false, false, false); }
-	}
-#undef GO
+	const int mode = exact ? 2 : (C.flag & KSW_F_APPROX_DROP) ? 1 : 0;
+	if (right) dispatch2<G, true>(C, B, threads, mode, with_p);
+	else dispatch2<G, false>(C, B, threads, mode, with_p);
 }
 
 extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, const uint8_t *qbuf, const int32_t *tlen,
@@ -59,7 +60,9 @@ extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, co
 		ksw_pack_pair(qbuf + qoff[i], qlen[i], tbuf + toff[i], tlen[i], tpk.data() + (size_t)i * g.t_stride, g.t_stride,
 		              qpk.data() + (size_t)i * g.q_stride, g.q_stride, 0, 1);
 	int ticket = 0;
+	KswHot hot = ksw_hot_from_consts(C);
 	KswBatch B;
+	B.hot = &hot;
 	B.n = n, B.base = 0, B.qlen = qlen, B.tlen = tlen, B.w = w, B.w_all = 0;
 	B.tpk = tpk.data(), B.qpk = qpk.data(), B.t_stride = g.t_stride, B.q_stride = g.q_stride;
 	B.p = p.data(), B.p_stride = g.p_stride, B.res = res, B.ticket = &ticket, B.ring = g.ring, B.group_smem = g.group_smem;

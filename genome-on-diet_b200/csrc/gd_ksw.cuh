@@ -42,7 +42,7 @@
 #define GD_KSW_PREFETCH 0 // 1: load the next step's chunk before computing the current one
 #endif
 #ifndef GD_KSW_HOTMEM
-#define GD_KSW_HOTMEM 0 // 1: sweep constants come from device memory (stay in registers) instead of the constant bank
+#define GD_KSW_HOTMEM 1 // 1: sweep constants come from device memory (stay in registers) instead of the constant bank
 #endif
 
 namespace gd {
@@ -344,7 +344,8 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 	uint8_t *prow = 0; // backtrack row pointer of the current row
 	int r = 0, rows_exec = 0, last_st = -1, last_en = -1, st_rec = 0, st_cur = 0, init_hi = 1;
 	int H0 = 0, H0_t = 0;                   // approx mode
-	int Mprev = 0, Hleft = 0, st0_prev = 0; // exact mode
+	int Mprev = 0, Hleft = 0, st0_prev = 0, Hs_prev = 0; // exact mode
+	int32_t *Hs_ptr = (int32_t *)(ring + REC_H);          // exact mode: H[st0] of the previous row
 	KswResult res;
 	res.max = 0, res.zdropped = 0, res.max_q = res.max_t = res.mqe_t = res.mte_q = -1;
 	res.score = res.mqe = res.mte = GD_KSW_NEG_INF, res.n_cigar = 0, res.reach_end = 0;
@@ -381,7 +382,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 						prow = WITH_P ? B.p + (size_t)lp * B.p_stride : 0;
 						r = 0, rows_exec = 0, last_st = last_en = -1, st_rec = 0, st_cur = 0, init_hi = 1;
 						H0 = -C.qe_seed, H0_t = 0; // row 0 adds v[0]: H0 = v[0] - qe (ksw2_extd2_sse.c:382)
-						Mprev = -C.qe_seed, Hleft = GD_KSW_NEG_INF, st0_prev = 0;
+						Mprev = -C.qe_seed, Hleft = GD_KSW_NEG_INF, st0_prev = 0, Hs_prev = GD_KSW_NEG_INF;
 						have = true, fresh = true;
 					}
 				}
@@ -447,42 +448,46 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			}
 		}
 		{
+			// Two single-column patches, one lane each (the address arithmetic is shared):
+			//  lane G-1: y[r], y2[r], u[r] when column r is in the row's range (ksw2_extd2_sse.c:160-163);
+			//  lane 0:   the left boundary x1, x21, v1 (ksw2_extd2_sse.c:149-159); it lives in the ring slot of
+			//            column st-1, which already holds the previous row's values when that column was in its range.
 			const int gd = gap_delta(r, C);
-			// ksw2_extd2_sse.c:160-163: y[r], y2[r], u[r]
-			uint8_t *pc = col_rec(ring, REC, NR, st_rec, active ? imin(r - st, en - st) : 0) + 2 * chunk_pos(r & 7);
-			if (active && en >= r && li == G - 1) {
+			const int dp = li == G - 1 ? imin(r - st, en - st) : -1;
+			uint8_t *pc = col_rec(ring, REC, NR, st_rec, active ? dp : 0) + 2 * chunk_pos(dp & 7);
+			if (active && li == G - 1 && en >= r) {
 				*(uint16_t *)(pc + REC_C) = (uint16_t)(C.INIT_C & 0xffff); // y, y2
 				*(pc + REC_B) = (uint8_t)gd;                               // u (low byte of B)
 			}
-			// left boundary (ksw2_extd2_sse.c:149-159): lives in the ring slot of column st-1, which holds the
-			// previous row's values when that column was in its range
-			uint8_t *pl = ring + (st_rec == 0 ? NR - 1 : st_rec - 1) * REC + 14;
 			if (active && li == 0 && !(st > 0 && st - 1 >= last_st && st - 1 <= last_en)) {
 				const uint32_t v1 = st > 0 ? (C.INIT_A & 0xffu) : (uint32_t)(gd & 0xff);
-				*(uint16_t *)(pl + REC_A) = (uint16_t)((C.INIT_A & 0xff00u) | v1); // x, v
-				*(pl + REC_B + 1) = (uint8_t)(C.INIT_B >> 8);                      // x2 (high byte of B)
+				*(uint16_t *)(pc + REC_A) = (uint16_t)((C.INIT_A & 0xff00u) | v1); // x, v
+				*(pc + REC_B + 1) = (uint8_t)(C.INIT_B >> 8);                      // x2 (high byte of B)
 			}
 		}
-		// exact mode: cells handled outside the bulk update (lanes 0..2: scan tail, lane 3: column en0)
-		int sp_t = -1, sp_h = 0;
+		// Exact mode: column en0 (H[en0-1] + u[en0]) and the <= 3 columns of the scalar tail of the reference's
+		// row scan are kept out of the bulk update.  Lane li < 4 of the group owns column en0-3+li.
+		bool sp = false, sp_en0 = false;
+		int sp_h = 0, sp_cc = 0;
+		int32_t *sp_hp = 0;
+		uint8_t *sp_bp = 0;
 		if (EXACT) {
-			if (active) {
-				// the column that left [st0,en0] keeps its last score for "H[en0-1]" of one-cell rows
-				if (r > 0 && st0 > st0_prev) Hleft = *col_H(ring, REC, NR, st_rec, st0 - 1 - st);
-				if (li < 3) {
-					if (en1 + li < en0) sp_t = en1 + li, sp_h = *col_H(ring, REC, NR, st_rec, sp_t - st);
-				} else if (li == 3) {
-					if (en0 > 0) {
-						sp_t = en0;
-						sp_h = en0 - 1 >= st0 ? *col_H(ring, REC, NR, st_rec, en0 - 1 - st) : Hleft;
-					}
-				}
-			}
+			const int tcol = en0 - 3 + li;
+			sp_en0 = li == 3 && en0 > 0;
+			sp = active && li < 4 && (sp_en0 || (li < 3 && tcol >= en1));
+			sp_cc = active && li < 4 && tcol >= st0 ? tcol - st : 0;
+			uint8_t *rsp = col_rec(ring, REC, NR, st_rec, sp_cc);
+			sp_hp = (int32_t *)(rsp + REC_H) + (sp_cc & 7);
+			sp_bp = rsp + 2 * chunk_pos(sp_cc & 7);
+			sp_h = *sp_hp; // H[tcol] of the previous row
+			// column en0 starts from H[en0-1] (lane 2's column) or, on one-cell rows, from the last score of the
+			// column that left the band on the left (= the previous row's H[st0])
+			const int hleft = (int)shfl_idx(FULL, (uint32_t)sp_h, leader + 2, 32);
+			if (active && r > 0 && st0 > st0_prev) Hleft = Hs_prev;
+			if (sp_en0) sp_h = en0 - 1 >= st0 ? hleft : Hleft;
 			sync_warp(FULL); // all of the loads above precede the sentinel stores below
-			if (active) {
-				if (li == 3 && r > 0 && st0 > st0_prev) *col_H(ring, REC, NR, st_rec, st0 - 1 - st) = GD_KSW_NEG_INF;
-				if (sp_t >= 0) *col_H(ring, REC, NR, st_rec, sp_t - st) = GD_KSW_NEG_INF; // keeps the bulk scan off these cells
-			}
+			if (sp) *sp_hp = GD_KSW_NEG_INF; // keeps the bulk scan off these cells
+			if (active && li == 0 && r > 0 && st0 > st0_prev) *Hs_ptr = GD_KSW_NEG_INF; // ... and off the column that left
 		}
 		sync_warp(FULL);
 		// ---- phase B: score row + core update, chunk by chunk from the right end of the row ----
@@ -636,16 +641,19 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			}
 		} else { // ksw2_extd2_sse.c:323-366
 			// the cells kept out of the bulk update: scan tail (H += v) and column en0 (H[en0-1] + u[en0])
-			if (active && sp_t >= 0) {
-				const int cc = sp_t - st;
-				const int hn = sp_h + col_lo8(ring, REC, NR, st_rec, cc, li == 3 ? REC_B : REC_A);
-				*col_H(ring, REC, NR, st_rec, cc) = hn;
+			int hn = 0;
+			if (sp) {
+				hn = sp_h + (int)(int8_t) * (sp_bp + (sp_en0 ? REC_B : REC_A));
+				*sp_hp = hn;
 				const int relc = imin(imax(hn - Mprev, GD_KSW_REL_FLOOR), 32767);
-				const uint32_t pr = li == 3 ? 0xffffu : (uint32_t)(3 - li) << 13 | (uint32_t)(GD_KSW_POS_MAX - cc);
+				const uint32_t pr = sp_en0 ? 0xffffu : (uint32_t)(3 - li) << 13 | (uint32_t)(GD_KSW_POS_MAX - sp_cc);
 				run = imax(run, (int)((uint32_t)relc << 16 | pr));
-			}
+			} else if (li == 3) hn = *sp_hp; // en0 == 0: column 0 was updated by the bulk pass
 			for (int dd = 1; dd < G; dd <<= 1) run = imax(run, (int)shfl_xor(FULL, (uint32_t)run, dd, 32));
+			const int He = (int)shfl_idx(FULL, (uint32_t)hn, leader + 3, 32); // H[en0] of this row
 			sync_warp(FULL);
+			int32_t *const hs_ptr = col_H(ring, REC, NR, st_rec, st0 - st);
+			const int Hs = *hs_ptr; // H[st0] of this row
 			if (active) {
 				const int rel = run >> 16;
 				const uint32_t pr = (uint32_t)run & 0xffffu;
@@ -659,8 +667,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 					if (lit_H != max_H || lit_t != max_t) ++emu::rowmax_mismatches();
 				}
 #endif
-				Mprev = max_H, st0_prev = st0;
-				const int He = *col_H(ring, REC, NR, st_rec, en0 - st), Hs = *col_H(ring, REC, NR, st_rec, st0 - st);
+				Mprev = max_H, st0_prev = st0, Hs_prev = Hs, Hs_ptr = hs_ptr;
 				if (en0 == tlen - 1 && He > res.mte) res.mte = He, res.mte_q = r - en;
 				if (r - st0 == qlen - 1 && Hs > res.mqe) res.mqe = Hs, res.mqe_t = st0;
 				if (max_H > res.max) res.max = max_H, res.max_t = max_t, res.max_q = r - max_t;
@@ -668,7 +675,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 					const int tl = max_t - res.max_t, ql = (r - max_t) - res.max_q, l = tl > ql ? tl - ql : ql - tl;
 					if (C.zdrop >= 0 && res.max - max_H > C.zdrop + l * C.e2) res.zdropped = 1, stop = 1;
 				}
-				if (!stop && r == nrows - 1 && en0 == tlen - 1) res.score = *col_H(ring, REC, NR, st_rec, tlen - 1 - st);
+				if (!stop && r == nrows - 1 && en0 == tlen - 1) res.score = He;
 			}
 		}
 		if (active) {

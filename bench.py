@@ -8,8 +8,9 @@ CIGARs produced.  A "step" is one pass of the hot path (pack -> DP -> traceback)
   value      GCUPS with the inputs already resident in HBM (CUDA events on the library's stream)
   e2e        GCUPS through the host-buffer C-ABI call gd_ksw_extd2_batch (pinned host buffers; H2D,
              kernels, D2H of ksw_extz_t records and CIGARs inside the timed region)
-  roofline   integer-ALU roofline of the DP kernel (51 lane-ops per banded cell against the
-             IADD rate measured live by gd_ubench), plus the backtrack HBM traffic against MEASURED_PEAKS
+  roofline   integer-ALU roofline of the DP kernel from its own launch durations (CUDA events around every
+             launch, on the library's stream): SURVEY.md 8d's 51 lane-ops per banded cell against the packed
+             16x2 add rate measured live by gd_ubench; plus the backtrack bytes against MEASURED_PEAKS
   cpu_baseline  the unmodified reference (oracle/_ref, ksw_extd2_avx512 when the host has AVX-512) on all
              host threads over a bounded sample of the same pairs
 
@@ -177,6 +178,7 @@ def ours(args, rank, world, local_rank):
     ctx = gd.Context(local_rank)
     ctx.set_option("ksw_group", args.group)
     ctx.set_option("ksw_blocks_per_sm", args.blocks_per_sm)
+    ctx.set_option("time_kernels", 1)  # CUDA events around every DP kernel launch, on the library's own stream
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     n = args.pairs
     sc = synth.SCORING["sr"]
@@ -211,6 +213,7 @@ def ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = ctx.stat("kernel_launches")
+    ctx.stat("ksw_dp_reset")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -220,13 +223,10 @@ def ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     dev_ms = e0.elapsed_time(e1)
     launches = ctx.stat("kernel_launches") - l0
+    dp_us, dp_n = ctx.stat("ksw_dp_us"), ctx.stat("ksw_dp_launches")  # device time of the DP kernel alone
+    ctx.set_option("time_kernels", 0)
     ez = d_ez.cpu().numpy().view(gd.GD_EXTZ_DTYPE)
     cells_step = int(pre[np.clip(ez["rows_done"], 0, len(pre) - 1)].sum())
-
-    # ---- per-kernel time of the DP kernel (for the roofline): time the DP kernel alone via score-only
-    # vs full? No: time the same step with CUDA events around each launch is not exposed by the ABI, so
-    # the DP kernel share is taken from the committed ncu launch list (profiles/) and the live figure is
-    # the whole step; the DP kernel is > 90 % of it (see profiles/).
 
     # ---- end-to-end arm: host buffers through the C ABI ------------------------------------------
     hp = {k: torch.from_numpy(P[k]).pin_memory() for k in ("qlen", "qoff", "qbuf", "tlen", "toff", "tbuf")}
@@ -271,19 +271,37 @@ def ours(args, rank, world, local_rank):
     value = tot_cells / (ms_per_step * 1e-3) / 1e9
     e2e_val = tot_cells / (e2e_ms / args.steps * 1e-3) / 1e9
 
-    # ---- roofline ---------------------------------------------------------------------------------
+    # ---- roofline of the dominant kernel (the DP kernel), from its own launch durations ----------
+    # achieved = algorithmic lane-ops per launch (51 per banded cell x cells of the launch)
+    #            / average launch duration (CUDA events on the library's stream, rank 0's launches);
+    # peak     = issue rate of the packed 16x2 integer add the kernel is built from, measured live by
+    #            gd_ubench on this GPU (MEASURED_PEAKS.json has no integer entry) x SMs x SM clock under load.
     peaks = measured_peaks()
     ub = run_ubench()
     clk = sampler.summary()
     sms = ctx.stat("device_sms")
-    iadd = ub.get("IADD")
+    lane_rate = ub.get("VIADD.16x2")
     f_hz = (clk["sm_mhz"] or (peaks or {}).get("sm_max_mhz") or 1965.0) * 1e6
-    per_gpu_cells_s = value * 1e9 / world
-    roof = {"bound": "int_alu", "unit": "Tlaneop/s", "achieved": per_gpu_cells_s * OPS_PER_CELL / 1e12,
-            "peak": (iadd * sms * f_hz / 1e12) if iadd else None,
-            "peak_source": "gd_ubench IADD lane-ops/clk/SM measured live x %d SMs x median SM clock under load" % sms if iadd else "unmeasured",
-            "ops_per_cell": OPS_PER_CELL, "traffic": None,
-            "hbm": {"achieved_gbs": per_gpu_cells_s * BYTES_PER_CELL / 1e9, "peak_gbs": (peaks or {}).get("hbm_gbs", 6650.0),
+    dp_ms = dp_us / 1e3 / max(dp_n, 1)
+    cells_launch = cells_step * args.steps / max(dp_n, 1)  # this rank's cells per DP kernel launch
+    dp_cells_s = cells_launch / (dp_ms * 1e-3) if dp_ms > 0 else 0.0
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "dp_traffic.json")))
+        traffic = {"bytes_per_launch": tj["dram_bytes_per_pair"][str(args.flag)] * n / max(1, ctx.stat("ksw_chunks")),
+                   "source": tj["source"]}
+    except Exception:
+        pass
+    roof = {"bound": "int_alu", "kernel": "gd_ksw_dp_kernel", "unit": "Tlaneop/s",
+            "achieved": dp_cells_s * OPS_PER_CELL / 1e12,
+            "peak": (lane_rate * sms * f_hz / 1e12) if lane_rate else None,
+            "peak_source": ("gd_ubench VIADD.16x2 lane-ops/clk/SM measured live (%.1f) x %d SMs x median SM clock under load "
+                            "(%.0f MHz); nominal issue limit is 128" % (lane_rate, sms, f_hz / 1e6)) if lane_rate else "unmeasured",
+            "ops_per_cell": OPS_PER_CELL, "kernel_ms_per_launch": dp_ms, "kernel_launches": int(dp_n),
+            "kernel_share_of_step": (dp_us / 1e3) / dev_ms if dev_ms > 0 else None,
+            "kernel_gcups": dp_cells_s / 1e9,
+            "traffic": traffic,
+            "hbm": {"achieved_gbs": dp_cells_s * BYTES_PER_CELL / 1e9, "peak_gbs": (peaks or {}).get("hbm_gbs", 6650.0),
                     "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s"},
             "ubench": ub}
     roof["frac"] = (roof["achieved"] / roof["peak"]) if roof["peak"] else None
@@ -327,11 +345,15 @@ def cpu_baseline_sample(args, P):
         return time.perf_counter() - t0
 
     dt = run(4096)
-    n = int(min(len(P["qlen"]), max(4096, 4096 * 12.0 / max(dt, 1e-3))))
-    dt = run(n)
-    return {"value": n * int(pre[-1]) / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
-            "sample": "first %d pairs of the step, ksw_extd2_%s via oracle/_ref on %d threads, %.1f s" % (
-                n, "avx512" if variant == "avx" else "sse", cores, dt)}
+    n = int(min(len(P["qlen"]), max(4096, 4096 * 4.0 / max(dt, 1e-3))))
+    # ~12 s of CPU work: repeat passes over the first n pairs of the step
+    passes, tot = 0, 0.0
+    while tot < 12.0 and passes < 64:
+        tot += run(n)
+        passes += 1
+    return {"value": passes * n * int(pre[-1]) / tot / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
+            "sample": "%d passes over the first %d pairs of the step, ksw_extd2_%s via oracle/_ref on %d threads, %.1f s" % (
+                passes, n, "avx512" if variant == "avx" else "sse", cores, tot)}
 
 
 def main():

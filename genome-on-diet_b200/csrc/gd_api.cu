@@ -88,6 +88,9 @@ extern "C" void gd_destroy(gd_ctx *ctx)
 		if (b->p) cudaFreeHost(b->p);
 	for (int i = 0; i < 4; ++i)
 		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	gd_timer_collect(ctx, ctx->tm_dp, ctx->tm_dp_us, ctx->tm_dp_n);
+	gd_timer_collect(ctx, ctx->tm_sketch, ctx->tm_sketch_us, ctx->tm_sketch_n);
+	for (cudaEvent_t e : ctx->tm_pool) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->copy_stream);
 	delete ctx;
@@ -102,6 +105,7 @@ extern "C" int gd_set_option(gd_ctx *ctx, const char *key, long value)
 	else if (!strcmp(key, "p_budget_mb")) ctx->opt_p_budget_mb = value;
 	else if (!strcmp(key, "ksw_blocks_per_sm")) ctx->opt_ksw_blocks_per_sm = value;
 	else if (!strcmp(key, "sketch_chunk")) ctx->opt_sketch_chunk = value;
+	else if (!strcmp(key, "time_kernels")) ctx->opt_time_kernels = value;
 	else {
 		ctx->err = std::string("unknown option ") + key;
 		return GD_ERR_ARG;
@@ -109,9 +113,22 @@ extern "C" int gd_set_option(gd_ctx *ctx, const char *key, long value)
 	return GD_OK;
 }
 
-extern "C" long gd_get_stat(const gd_ctx *ctx, const char *key)
+extern "C" long gd_get_stat(const gd_ctx *cctx, const char *key)
 {
-	if (!ctx || !key) return -1;
+	if (!cctx || !key) return -1;
+	gd_ctx *ctx = const_cast<gd_ctx *>(cctx);
+	if (!strncmp(key, "ksw_dp_", 7) || !strncmp(key, "sketch_", 7)) { // device time of the hot kernels (option "time_kernels")
+		gd_timer_collect(ctx, ctx->tm_dp, ctx->tm_dp_us, ctx->tm_dp_n);
+		gd_timer_collect(ctx, ctx->tm_sketch, ctx->tm_sketch_us, ctx->tm_sketch_n);
+		if (!strcmp(key, "ksw_dp_us")) return (long)(ctx->tm_dp_us + 0.5);
+		if (!strcmp(key, "ksw_dp_launches")) return ctx->tm_dp_n;
+		if (!strcmp(key, "sketch_us")) return (long)(ctx->tm_sketch_us + 0.5);
+		if (!strcmp(key, "sketch_launches")) return ctx->tm_sketch_n;
+		if (!strcmp(key, "ksw_dp_reset") || !strcmp(key, "sketch_reset")) {
+			ctx->tm_dp_us = ctx->tm_sketch_us = 0, ctx->tm_dp_n = ctx->tm_sketch_n = 0;
+			return 0;
+		}
+	}
 	if (!strcmp(key, "kernel_launches")) return ctx->stat_launches;
 	if (!strcmp(key, "ksw_ring")) return ctx->stat_ksw_ring;
 	if (!strcmp(key, "ksw_group")) return ctx->stat_ksw_group;

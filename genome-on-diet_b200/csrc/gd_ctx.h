@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
+#include <vector>
 #include "../../include/gdiet_cuda.h"
 
 struct GdBuf { // grow-only device buffer
@@ -30,9 +32,15 @@ struct gd_ctx {
 	long opt_p_budget_mb = 0; // 0 = auto
 	long opt_ksw_blocks_per_sm = 0;
 	long opt_sketch_chunk = 0;
+	long opt_time_kernels = 0; // 1: bracket every DP / sketch kernel launch with CUDA events (bench.py roofline)
 	// stats
 	long stat_launches = 0;
 	long stat_ksw_ring = 0, stat_ksw_group = 0, stat_ksw_chunks = 0;
+	// per-kernel device time (opt_time_kernels): event pairs recorded on `stream`, summed when a stat is read
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tm_dp, tm_sketch;
+	std::vector<cudaEvent_t> tm_pool;
+	double tm_dp_us = 0, tm_sketch_us = 0;
+	long tm_dp_n = 0, tm_sketch_n = 0;
 	// DP scratch
 	GdBuf tpk, qpk, parena, ticket, cig_tmp, cig_off, cig_compact, res;
 	GdBuf d_qlen, d_tlen, d_w, d_qoff, d_toff, d_qbuf, d_tbuf;
@@ -52,6 +60,42 @@ struct gd_ctx {
 			return GD_ERR_CUDA;                                                            \
 		}                                                                                      \
 	} while (0)
+
+// Device-time bracket around one kernel launch: a no-op unless the "time_kernels" option is set.
+struct GdKernelTimer {
+	gd_ctx *ctx;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *list;
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	static cudaEvent_t get(gd_ctx *c)
+	{
+		cudaEvent_t e = nullptr;
+		if (!c->tm_pool.empty()) e = c->tm_pool.back(), c->tm_pool.pop_back();
+		else cudaEventCreate(&e);
+		return e;
+	}
+	GdKernelTimer(gd_ctx *c, std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *l) : ctx(c), list(l)
+	{
+		if (!ctx->opt_time_kernels) return;
+		e0 = get(ctx), e1 = get(ctx);
+		cudaEventRecord(e0, ctx->stream);
+	}
+	~GdKernelTimer()
+	{
+		if (!e0) return;
+		cudaEventRecord(e1, ctx->stream);
+		list->push_back(std::make_pair(e0, e1));
+	}
+};
+static inline void gd_timer_collect(gd_ctx *ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &l, double &us, long &n)
+{
+	for (auto &pr : l) {
+		float ms = 0;
+		cudaEventSynchronize(pr.second);
+		if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) us += 1e3 * ms, ++n;
+		ctx->tm_pool.push_back(pr.first), ctx->tm_pool.push_back(pr.second);
+	}
+	l.clear();
+}
 
 static inline int gd_reserve(gd_ctx *ctx, GdBuf &b, size_t bytes)
 {

@@ -251,6 +251,7 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 		}
 		{
 			int blocks = std::min((cn + groups_per_block - 1) / groups_per_block, ctx->sms * occ);
+			GdKernelTimer tm(ctx, &ctx->tm_dp);
 			kern<<<blocks, threads, smem, s>>>(C, B);
 		}
 		if (with_p) gd_ksw_traceback_kernel<<<(cn + 127) / 128, 128, 0, s>>>(B, flag, d_cigar, cigar_stride);

@@ -234,6 +234,11 @@ GD_DEV void ksw_build_lut(uint8_t *lut, int tid, int nthreads)
 }
 
 GD_DEV int wrap(int k, int n) { return k >= n ? k - n : k; }
+// The record of column t sits at ring position (t >> 3) mod NR; the kernel follows the few columns it
+// patches or reads one at a time (r, st-1, H0_t, en0, st0) with byte offsets that step through the ring.
+GD_DEV int ring_fwd(int off, int rec_bytes, int ring_bytes) { return off + rec_bytes >= ring_bytes ? 0 : off + rec_bytes; }
+GD_DEV int ring_bwd(int off, int rec_bytes, int ring_bytes) { return off == 0 ? ring_bytes - rec_bytes : off - rec_bytes; }
+GD_DEV int pos2(int j) { return ((j & 3) << 2) | ((j >> 1) & 2); } // 2 * chunk_pos(j): byte offset of column j's 16-bit slot
 
 // Record of the column at distance d = t - st from the first column of the row's 16-aligned range
 // (d may be -1: the left-boundary column).  st_rec is the ring position of the record that holds column st.
@@ -342,7 +347,11 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 	bool have = false, done = false;
 	int pair = 0, qlen = 1, tlen = 1, w = 0, T16 = 16, nblk_t = 1, ncol16 = 32, nrows = 1;
 	uint8_t *prow = 0; // backtrack row pointer of the current row
-	int r = 0, rows_exec = 0, last_st = -1, last_en = -1, st_rec = 0, st_cur = 0, init_hi = 1;
+	const int RB = NR * REC; // ring bytes
+	int r = 0, rows_exec = 0, st_rec = 0, st_cur = 0, init_hi = 1;
+	int r_off = 0;                          // ring offset of the record of column r
+	int T_off = 0;                          // approx mode: ... of column H0_t
+	int en0_cur = 0, en0_off = 0, st0_cur = 0, st0_off = 0; // exact mode: ... of columns en0 and st0
 	int H0 = 0, H0_t = 0;                   // approx mode
 	int Mprev = 0, Hleft = 0, st0_prev = 0, Hs_prev = 0; // exact mode
 	int32_t *Hs_ptr = (int32_t *)(ring + REC_H);          // exact mode: H[st0] of the previous row
@@ -380,7 +389,8 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 						tpk = B.tpk + (size_t)lp * B.t_stride;
 						qpk = B.qpk + (size_t)lp * B.q_stride;
 						prow = WITH_P ? B.p + (size_t)lp * B.p_stride : 0;
-						r = 0, rows_exec = 0, last_st = last_en = -1, st_rec = 0, st_cur = 0, init_hi = 1;
+						r = 0, rows_exec = 0, st_rec = 0, st_cur = 0, init_hi = 1;
+						r_off = T_off = 0, en0_cur = en0_off = st0_cur = st0_off = 0;
 						H0 = -C.qe_seed, H0_t = 0; // row 0 adds v[0]: H0 = v[0] - qe (ksw2_extd2_sse.c:382)
 						Mprev = -C.qe_seed, Hleft = GD_KSW_NEG_INF, st0_prev = 0, Hs_prev = GD_KSW_NEG_INF;
 						have = true, fresh = true;
@@ -424,7 +434,18 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 		if (!active) st0 = 0, en0 = 0;
 		const int st = st0 & ~15, en = en0 | 15;
 		// ---- phase A: ring bookkeeping, boundary injections ----
-		if (active && st != st_cur) st_rec = wrap(st_rec + 2, NR), st_cur = st; // st moves by exactly one 16-column block
+		const bool adv = active && st != st_cur; // st moves by exactly one 16-column block
+		if (adv) st_rec = wrap(st_rec + 2, NR), st_cur = st;
+		if (EXACT && active) { // en0 and st0 grow by at most one per row
+			if (en0 != en0_cur) {
+				en0_cur = en0;
+				if ((en0 & 7) == 0) en0_off = ring_fwd(en0_off, REC, RB);
+			}
+			if (st0 != st0_cur) {
+				st0_cur = st0;
+				if ((st0 & 7) == 0) st0_off = ring_fwd(st0_off, REC, RB);
+			}
+		}
 		const int fe = active ? imin(st0 + (((en0 - st0) >> 4) + 1) * 16, T16) : 16; // score row is rewritten on [st0, fe)
 		const int en1 = st0 + ((en0 - st0) & ~3); // exact mode: end of the 4-lane part of the row scan
 		{
@@ -453,13 +474,12 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			//  lane 0:   the left boundary x1, x21, v1 (ksw2_extd2_sse.c:149-159); it lives in the ring slot of
 			//            column st-1, which already holds the previous row's values when that column was in its range.
 			const int gd = gap_delta(r, C);
-			const int dp = li == G - 1 ? imin(r - st, en - st) : -1;
-			uint8_t *pc = col_rec(ring, REC, NR, st_rec, active ? dp : 0) + 2 * chunk_pos(dp & 7);
+			uint8_t *pc = ring + (li == G - 1 ? r_off + pos2(r & 7) : ring_bwd(st_rec * REC, REC, RB) + 14);
 			if (active && li == G - 1 && en >= r) {
 				*(uint16_t *)(pc + REC_C) = (uint16_t)(C.INIT_C & 0xffff); // y, y2
 				*(pc + REC_B) = (uint8_t)gd;                               // u (low byte of B)
 			}
-			if (active && li == 0 && !(st > 0 && st - 1 >= last_st && st - 1 <= last_en)) {
+			if (active && li == 0 && !adv) { // st-1 was not in the previous row's range (or st == 0)
 				const uint32_t v1 = st > 0 ? (C.INIT_A & 0xffu) : (uint32_t)(gd & 0xff);
 				*(uint16_t *)(pc + REC_A) = (uint16_t)((C.INIT_A & 0xff00u) | v1); // x, v
 				*(pc + REC_B + 1) = (uint8_t)(C.INIT_B >> 8);                      // x2 (high byte of B)
@@ -475,10 +495,12 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			const int tcol = en0 - 3 + li;
 			sp_en0 = li == 3 && en0 > 0;
 			sp = active && li < 4 && (sp_en0 || (li < 3 && tcol >= en1));
-			sp_cc = active && li < 4 && tcol >= st0 ? tcol - st : 0;
-			uint8_t *rsp = col_rec(ring, REC, NR, st_rec, sp_cc);
-			sp_hp = (int32_t *)(rsp + REC_H) + (sp_cc & 7);
-			sp_bp = rsp + 2 * chunk_pos(sp_cc & 7);
+			const bool mine = active && li < 4 && tcol >= st0; // this lane reads and may own column tcol
+			sp_cc = mine ? tcol - st : 0;
+			const int jsp = mine ? tcol & 7 : en0 & 7;
+			uint8_t *rsp = ring + (mine && (en0 & 7) < 3 - li ? ring_bwd(en0_off, REC, RB) : en0_off);
+			sp_hp = (int32_t *)(rsp + REC_H) + jsp;
+			sp_bp = rsp + pos2(jsp);
 			sp_h = *sp_hp; // H[tcol] of the previous row
 			// column en0 starts from H[en0-1] (lane 2's column) or, on one-cell rows, from the last score of the
 			// column that left the band on the left (= the previous row's H[st0])
@@ -622,14 +644,15 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 		int stop = 0;
 		if (!EXACT) { // ksw2_extd2_sse.c:367-383 (every lane of the group tracks the same H0)
 			// v[T] and u[T+1] of the updated row, T = last_H0_t (T >= st0-1 always holds; row 0 starts from H0 = -qe)
-			const int T = active ? H0_t : 0;
-			const int d0 = col_lo8(ring, REC, NR, st_rec, imax(T - st, 0), REC_A);
-			const int d1 = col_lo8(ring, REC, NR, st_rec, imin(T + 1 - st, en - st), REC_B);
+			const int T = H0_t;
+			const int T1_off = ((T + 1) & 7) == 0 ? ring_fwd(T_off, REC, RB) : T_off;
+			const int d0 = (int)*(const int8_t *)(ring + T_off + pos2(T & 7) + REC_A);        // v[T]
+			const int d1 = (int)*(const int8_t *)(ring + T1_off + pos2((T + 1) & 7) + REC_B); // u[T+1]
 			const bool in0 = T >= st0 && T <= en0, in1 = T + 1 >= st0 && T + 1 <= en0;
 			const bool take_v = in0 && (!in1 || d0 > d1);
 			if (active) {
 				H0 += take_v ? d0 : d1;
-				if (!take_v) ++H0_t;
+				if (!take_v) ++H0_t, T_off = T1_off;
 				if (MODE == 1) { // KSW_EZ_APPROX_DROP: ksw_apply_zdrop, ksw2.h:172-188
 					if (H0 > res.max) res.max = H0, res.max_t = H0_t, res.max_q = r - H0_t;
 					else if (H0_t >= res.max_t && r - H0_t >= res.max_q) {
@@ -652,7 +675,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			for (int dd = 1; dd < G; dd <<= 1) run = imax(run, (int)shfl_xor(FULL, (uint32_t)run, dd, 32));
 			const int He = (int)shfl_idx(FULL, (uint32_t)hn, leader + 3, 32); // H[en0] of this row
 			sync_warp(FULL);
-			int32_t *const hs_ptr = col_H(ring, REC, NR, st_rec, st0 - st);
+			int32_t *const hs_ptr = (int32_t *)(ring + st0_off + REC_H) + (st0 & 7);
 			const int Hs = *hs_ptr; // H[st0] of this row
 			if (active) {
 				const int rel = run >> 16;
@@ -680,9 +703,9 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 		}
 		if (active) {
 			++rows_exec;
-			last_st = st, last_en = en;
 			if (WITH_P) prow += ncol16;
 			++r;
+			if ((r & 7) == 0) r_off = ring_fwd(r_off, REC, RB);
 			if (stop || r == nrows) finish = true;
 		}
 		// ================= pair finished: publish the record =================
@@ -699,6 +722,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			}
 			have = false;
 			qlen = tlen = 1, w = 0, r = 0; // idle geometry: one dummy cell per row until the next pair arrives
+			H0_t = 0, T_off = 0, r_off = 0;
 		}
 	}
 }

@@ -220,6 +220,7 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 		int occ = 0;
 		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 64, sizeof(SM)));
 		int blocks = (int)std::min<int64_t>(ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));
+		GdKernelTimer tm(ctx, &ctx->tm_sketch);
 		kern<<<std::max(blocks, 1), 64, sizeof(SM), s>>>(S, B);
 	} else {
 		typedef SketchSmem<256, 8> SM;
@@ -227,6 +228,7 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 		int occ = 0;
 		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, sizeof(SM)));
 		int blocks = (int)std::min<int64_t>(ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));
+		GdKernelTimer tm(ctx, &ctx->tm_sketch);
 		kern<<<std::max(blocks, 1), 256, sizeof(SM), s>>>(S, B);
 	}
 	ctx->stat_launches++;

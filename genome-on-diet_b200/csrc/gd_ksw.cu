@@ -165,14 +165,9 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 	const bool with_p = !(flag & KSW_F_SCORE_ONLY) && d_cigar != nullptr && cigar_stride > 0;
 	KswConsts C = ksw_make_consts(prm->m, prm->mat, prm->q, prm->e, prm->q2, prm->e2, prm->zdrop, prm->end_bonus, flag);
 	if (max_w < 0) max_w = std::max(max_qlen, max_tlen);
-	KswGeom geo = ksw_geometry(max_qlen, max_tlen, max_w, exact, with_p);
-
-	// lanes per pair: one 8-column chunk per lane and step; short rows keep 8 pairs per warp
 	int G = (int)ctx->opt_ksw_group;
-	if (G != 4 && G != 8 && G != 16 && G != 32) {
-		const int nch = h_ncol16(max_qlen, max_tlen, max_w) / 8; // chunks in the widest row
-		G = nch <= 24 ? 4 : nch <= 64 ? 8 : nch <= 160 ? 16 : 32;
-	}
+	if (G != 4 && G != 8 && G != 16 && G != 32) G = ksw_pick_group(max_qlen, max_tlen, max_w);
+	KswGeom geo = ksw_geometry(max_qlen, max_tlen, max_w, exact, with_p, G);
 	if (geo.ring > GD_KSW_POS_MAX - 32 && exact) {
 		ctx->err = "gd_ksw: band too wide for the exact-max keys (ring > 8158 columns)";
 		return GD_ERR_ARG;
@@ -193,6 +188,7 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 		if (threads) break;
 		if (G < 32) {
 			G <<= 1;
+			geo = ksw_geometry(max_qlen, max_tlen, max_w, exact, with_p, G);
 			continue;
 		}
 		ctx->err = "gd_ksw: band too wide for the shared-memory column ring (needs > 227 KB per pair)";

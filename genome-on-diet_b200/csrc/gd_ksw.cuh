@@ -201,7 +201,7 @@ GD_DEV int ksw_ncol16(int qlen, int tlen, int w)
 // (group pitch == 64 resp. 16 mod 128) on disjoint banks.
 enum { REC_A = 0, REC_B = 16, REC_C = 32, REC_S = 48, REC_H = 64 };
 template <bool EXACT> struct RecSize { enum { value = EXACT ? 96 : 80 }; };
-static inline int ksw_group_smem_bytes(int R, bool exact, int seq_bytes)
+static inline int ksw_group_smem_bytes(int R, bool exact, int seq_bytes /* 0 when the sequences stay in global memory */)
 {
 	int b = (R / 8) * (exact ? 96 : 80) + seq_bytes;
 	b = (b + 127) / 128 * 128 + (exact ? 16 : 64);
@@ -334,7 +334,10 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 	const int li = lane & (G - 1), leader = lane & ~(G - 1);
 	uint8_t *const ring = smem_warp + (size_t)(lane / G) * B.group_smem;
 	const int NR = B.ring >> 3;
-	uint8_t *const tsm = ring + NR * REC, *const qsm = tsm + B.t_stride;
+	// Short pairs (G <= 8) stage both sequences next to the ring; long ones read the packed arenas in
+	// global memory (coalesced: the lanes of a step read consecutive chunks).
+	const bool SEQ_SMEM = G <= 8;
+	const uint8_t *tsm = SEQ_SMEM ? ring + NR * REC : B.tpk, *qsm = SEQ_SMEM ? tsm + B.t_stride : B.qpk;
 	const uint2 *lut_fresh = (const uint2 *)lut;
 	const uint32_t *lut_pk = (const uint32_t *)(lut + 1152);
 #if GD_KSW_HOTMEM
@@ -400,12 +403,15 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			// stage the padded sequences of fresh pairs (strides are launch-uniform) and give block 0 of the
 			// ring the reference's initial values; the previous pair's readers are past their last row
 			{
-				const int nt = B.t_stride >> 2, nq = B.q_stride >> 2;
-				for (int i = li; i < nt + nq; i += G)
-					if (fresh) {
-						if (i < nt) ((uint32_t *)tsm)[i] = ((const uint32_t *)tpk)[i];
-						else ((uint32_t *)qsm)[i - nt] = ((const uint32_t *)qpk)[i - nt];
-					}
+				if (SEQ_SMEM) {
+					const int nt = B.t_stride >> 2, nq = B.q_stride >> 2;
+					uint32_t *const tdst = (uint32_t *)(ring + NR * REC), *const qdst = tdst + nt;
+					for (int i = li; i < nt + nq; i += G)
+						if (fresh) {
+							if (i < nt) tdst[i] = ((const uint32_t *)tpk)[i];
+							else qdst[i - nt] = ((const uint32_t *)qpk)[i - nt];
+						}
+				} else if (fresh) tsm = tpk, qsm = qpk;
 				if (fresh && li < 2) {
 					uint8_t *rc = ring + li * REC;
 					*(uint4 *)(rc + REC_A) = rep4(C.INIT_A), *(uint4 *)(rc + REC_B) = rep4(C.INIT_B);
@@ -722,6 +728,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			}
 			have = false;
 			qlen = tlen = 1, w = 0, r = 0; // idle geometry: one dummy cell per row until the next pair arrives
+			if (!SEQ_SMEM) tsm = B.tpk, qsm = B.qpk; // any valid arena
 			H0_t = 0, T_off = 0, r_off = 0;
 		}
 	}

@@ -75,7 +75,16 @@ struct KswGeom {
 	int t_stride, q_stride;
 	int64_t p_stride;
 };
-static inline KswGeom ksw_geometry(int max_qlen, int max_tlen, int max_w, bool exact, bool with_p)
+// Lanes per pair: one 8-column chunk per lane and step.  Short rows keep 8 pairs per warp; pairs whose
+// sequences would not fit next to the ring (staged only for G <= 8) use wide groups.
+static inline int ksw_pick_group(int max_qlen, int max_tlen, int max_w)
+{
+	const int nch = h_ncol16(max_qlen, max_tlen, max_w) / 8; // chunks in the widest row
+	int G = nch <= 24 ? 4 : nch <= 64 ? 8 : nch <= 160 ? 16 : 32;
+	if (G <= 8 && max_qlen + max_tlen > 2048) G = 16;
+	return G;
+}
+static inline KswGeom ksw_geometry(int max_qlen, int max_tlen, int max_w, bool exact, bool with_p, int G)
 {
 	KswGeom g;
 	if (max_qlen < 1) max_qlen = 1;
@@ -86,7 +95,7 @@ static inline KswGeom ksw_geometry(int max_qlen, int max_tlen, int max_w, bool e
 	g.ring = ncol16 + 24 < T16 + 8 ? ncol16 + 24 : T16 + 8;
 	g.t_stride = T16;
 	g.q_stride = (max_qlen + 15) / 16 * 16 + 64;
-	g.group_smem = ksw_group_smem_bytes(g.ring, exact, g.t_stride + g.q_stride);
+	g.group_smem = ksw_group_smem_bytes(g.ring, exact, G <= 8 ? g.t_stride + g.q_stride : 0);
 	g.p_stride = with_p ? (int64_t)(max_qlen + max_tlen - 1) * ncol16 : 0;
 	return g;
 }

@@ -53,7 +53,7 @@ extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, co
 		if (ww > max_w) max_w = ww;
 	}
 	const bool exact = !(flag & KSW_F_APPROX_MAX), with_p = !(flag & KSW_F_SCORE_ONLY), right = (flag & KSW_F_RIGHT) != 0;
-	KswGeom g = ksw_geometry(max_q, max_t, max_w, exact, with_p);
+	KswGeom g = ksw_geometry(max_q, max_t, max_w, exact, with_p, G);
 	std::vector<uint8_t> tpk((size_t)n * g.t_stride), qpk((size_t)n * g.q_stride), p((size_t)n * g.p_stride + 16);
 	memset(p.data(), 0xAA, p.size()); // poison: any read of an unwritten backtrack byte shows up
 	for (int i = 0; i < n; ++i)

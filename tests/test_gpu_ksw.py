@@ -83,6 +83,20 @@ def test_long_banded_pairs_ring_wrap(ctx, oracle):
     ctx.set_option("ksw_group", 0)
 
 
+def test_baseline_long_read_shapes(ctx, oracle):
+    """BASELINE configs 3 and 4 at full size: 15 kbp HiFi-like pairs with -r 1000 and 50 kbp ONT-like pairs with
+    -r 1300 (live flag; HiFi also with the exact maximum), sequences read from global memory, ring of > 1000 columns"""
+    for n, qlen, edit, wv, scn, flags in ((2, 15000, 0.01, 1000, "map-hifi", (0x08, 0x00)), (2, 50000, 0.08, 1300, "map-ont", (0x08,))):
+        P = synth.long_pairs(n, qlen, edit, seed=qlen + 1, tlen_extra=0.01)
+        w = np.full(P["n"], wv, np.int32)
+        sc = synth.SCORING[scn]
+        for flag in flags:
+            exp = oracle_batch(oracle, P, w, sc, flag)
+            ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"],
+                                                params(sc, flag), w=w)
+            assert_batch_equal(ez, coff, cig, exp, what="baseline long %d flag %#x" % (qlen, flag))
+
+
 def test_chunked_backtrack_arena(ctx, oracle):
     """a tiny backtrack budget forces many chunks; results must not depend on chunking"""
     P = synth.ksw_pairs(500, 150, 200, 0.05, seed=3)

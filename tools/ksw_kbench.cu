@@ -80,10 +80,11 @@ int main(int argc, char **argv)
 	for (int flag : {0x08, 0x00}) {
 		const bool exact = !(flag & 8);
 		KswConsts C = ksw_make_consts(5, mat, 12, 2, 24, 1, 100, 10, flag);
-		KswGeom geo = ksw_geometry(qlen, tlen, w, exact, true);
+		KswGeom geo = ksw_geometry(qlen, tlen, w, exact, true, 4);
 		CK(cudaMalloc(&tpk, (size_t)n * geo.t_stride + 64)); CK(cudaMalloc(&qpk, (size_t)n * geo.q_stride + 64));
 		CK(cudaMalloc(&p, (size_t)n * geo.p_stride + 64));
 		for (int G : {4, 8}) {
+			geo = ksw_geometry(qlen, tlen, w, exact, true, G);
 			kern_t kern = G == 4 ? pick<4>(exact ? 2 : 0) : pick<8>(exact ? 2 : 0);
 			const size_t per_warp = (size_t)(32 / G) * geo.group_smem;
 			int threads = 0, best = 0;

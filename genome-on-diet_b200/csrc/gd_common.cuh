@@ -105,14 +105,7 @@ GD_DEV uint32_t shfl_idx(uint32_t mask, uint32_t v, int src, int width) { return
 GD_DEV uint32_t shfl_xor(uint32_t mask, uint32_t v, int lm, int width) { return emu::shfl_xor(mask, v, lm, width); }
 GD_DEV uint32_t shfl_up(uint32_t mask, uint32_t v, int d, int width) { return emu::shfl_up(mask, v, d, width); }
 GD_DEV uint32_t ballot(uint32_t mask, int pred) { return emu::ballot(mask, pred); }
-GD_DEV int reduce_max(uint32_t mask, int v)
-{
-	for (int d = 16; d >= 1; d >>= 1) {
-		int o = (int)emu::shfl_xor(mask, (uint32_t)v, d, 32);
-		v = o > v ? o : v;
-	}
-	return v;
-}
+GD_DEV int reduce_max(uint32_t mask, int v) { return emu::reduce_max(mask, v); }
 GD_DEV void sync_warp(uint32_t mask) { emu::sync_warp(mask); }
 GD_DEV void sync_block() { emu::sync_block(); }
 GD_DEV int thread_idx() { return emu::thread_idx(); }

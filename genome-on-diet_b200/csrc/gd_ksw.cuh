@@ -196,16 +196,17 @@ GD_DEV int ksw_ncol16(int qlen, int tlen, int w)
 // One record holds everything the sweep needs for 8 columns, so a lane-step addresses it with
 // immediate offsets.  The six int8 state arrays are stored two to a 16-bit slot (8 slots per array
 // pair, chunk-strided order): A = (x << 8 | v), B = (x2 << 8 | u), C = (y << 8 | y2); then the score
-// bytes (8 B, chunk-strided) and, in exact mode, H (8 x int32, natural column order).  Record sizes
+// bytes S and the target codes T of the 8 columns (8 B each, chunk-strided; T is filled from the packed
+// target arena when the block enters the window) and, in exact mode, H (8 x int32, natural column order).  Record sizes
 // 80 / 96 B keep the four lanes of a group and the two groups that share a 128-bit access phase
 // (group pitch == 64 resp. 16 mod 128) on disjoint banks.
-enum { REC_A = 0, REC_B = 16, REC_C = 32, REC_S = 48, REC_H = 64 };
+enum { REC_A = 0, REC_B = 16, REC_C = 32, REC_S = 48, REC_T = 56, REC_H = 64 };
 template <bool EXACT> struct RecSize { enum { value = EXACT ? 96 : 80 }; };
 static inline int ksw_group_smem_bytes(int R, bool exact, int seq_bytes /* 0 when the sequences stay in global memory */)
 {
 	int b = (R / 8) * (exact ? 96 : 80) + seq_bytes;
-	b = (b + 127) / 128 * 128 + (exact ? 16 : 64);
-	return b;
+	const int phase = exact ? 16 : 64; // smallest size >= b that is == phase (mod 128)
+	return (b - phase + 127) / 128 * 128 + phase;
 }
 
 // Per-block lookup tables (first GD_KSW_LUT_BYTES of shared memory):
@@ -334,10 +335,12 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 	const int li = lane & (G - 1), leader = lane & ~(G - 1);
 	uint8_t *const ring = smem_warp + (size_t)(lane / G) * B.group_smem;
 	const int NR = B.ring >> 3;
-	// Short pairs (G <= 8) stage both sequences next to the ring; long ones read the packed arenas in
-	// global memory (coalesced: the lanes of a step read consecutive chunks).
+	// The target codes travel in the ring records.  Short pairs (G <= 8) stage the reversed query next to
+	// the ring; long ones read the packed query arena in global memory (coalesced: the lanes of a step
+	// read consecutive chunks).
 	const bool SEQ_SMEM = G <= 8;
-	const uint8_t *tsm = SEQ_SMEM ? ring + NR * REC : B.tpk, *qsm = SEQ_SMEM ? tsm + B.t_stride : B.qpk;
+	const uint8_t *qsm = SEQ_SMEM ? ring + NR * REC : B.qpk;
+	const uint8_t *tpk_g = B.tpk; // packed target of the current pair (feeds the records of entering blocks)
 	const uint2 *lut_fresh = (const uint2 *)lut;
 	const uint32_t *lut_pk = (const uint32_t *)(lut + 1152);
 #if GD_KSW_HOTMEM
@@ -404,14 +407,12 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			// ring the reference's initial values; the previous pair's readers are past their last row
 			{
 				if (SEQ_SMEM) {
-					const int nt = B.t_stride >> 2, nq = B.q_stride >> 2;
-					uint32_t *const tdst = (uint32_t *)(ring + NR * REC), *const qdst = tdst + nt;
-					for (int i = li; i < nt + nq; i += G)
-						if (fresh) {
-							if (i < nt) tdst[i] = ((const uint32_t *)tpk)[i];
-							else qdst[i - nt] = ((const uint32_t *)qpk)[i - nt];
-						}
-				} else if (fresh) tsm = tpk, qsm = qpk;
+					const int nq = B.q_stride >> 2;
+					uint32_t *const qdst = (uint32_t *)(ring + NR * REC);
+					for (int i = li; i < nq; i += G)
+						if (fresh) qdst[i] = ((const uint32_t *)qpk)[i];
+				} else if (fresh) qsm = qpk;
+				if (fresh) tpk_g = tpk;
 				if (fresh && li < 2) {
 					uint8_t *rc = ring + li * REC;
 					*(uint4 *)(rc + REC_A) = rep4(C.INIT_A), *(uint4 *)(rc + REC_B) = rep4(C.INIT_B);
@@ -419,6 +420,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 					uint2 z2;
 					z2.x = z2.y = 0;
 					*(uint2 *)(rc + REC_S) = z2;
+					*(uint2 *)(rc + REC_T) = *(const uint2 *)(tpk + li * 8);
 					if (EXACT) {
 						uint4 h0 = rep4((uint32_t)GD_KSW_NEG_INF);
 						*(uint4 *)(rc + REC_H + 16) = h0;
@@ -468,6 +470,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 					uint2 z2;
 					z2.x = z2.y = 0;
 					*(uint2 *)(rc + REC_S) = z2;
+					*(uint2 *)(rc + REC_T) = *(const uint2 *)(tpk_g + init_hi * 16 + li * 8);
 					if (EXACT)
 						*(uint4 *)(rc + REC_H) = rep4((uint32_t)GD_KSW_NEG_INF), *(uint4 *)(rc + REC_H + 16) = rep4((uint32_t)GD_KSW_NEG_INF);
 				}
@@ -501,18 +504,22 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			const int tcol = en0 - 3 + li;
 			sp_en0 = li == 3 && en0 > 0;
 			sp = active && li < 4 && (sp_en0 || (li < 3 && tcol >= en1));
-			const bool mine = active && li < 4 && tcol >= st0; // this lane reads and may own column tcol
-			sp_cc = mine ? tcol - st : 0;
-			const int jsp = mine ? tcol & 7 : en0 & 7;
-			uint8_t *rsp = ring + (mine && (en0 & 7) < 3 - li ? ring_bwd(en0_off, REC, RB) : en0_off);
+			// what the lane reads: H[tcol] of the previous row; lane 3 reads H[en0-1] instead (column en0 starts
+			// from it, or, on one-cell rows, from the last score of the column that left the band on the left
+			// = the previous row's H[st0])
+			const int lcol = li == 3 ? en0 - 1 : tcol;
+			const bool lok = active && li < 4 && lcol >= st0;
+			const int lj = lok ? lcol & 7 : en0 & 7;
+			uint8_t *lrec = ring + (lok && (en0 & 7) < en0 - lcol ? ring_bwd(en0_off, REC, RB) : en0_off);
+			sp_h = *((const int32_t *)(lrec + REC_H) + lj);
+			if (active && r > 0 && st0 > st0_prev) Hleft = Hs_prev;
+			if (li == 3 && !lok) sp_h = Hleft;
+			// what the lane owns: column tcol
+			uint8_t *rsp = li == 3 ? ring + en0_off : lrec;
+			const int jsp = li == 3 ? en0 & 7 : lj;
+			sp_cc = tcol - st;
 			sp_hp = (int32_t *)(rsp + REC_H) + jsp;
 			sp_bp = rsp + pos2(jsp);
-			sp_h = *sp_hp; // H[tcol] of the previous row
-			// column en0 starts from H[en0-1] (lane 2's column) or, on one-cell rows, from the last score of the
-			// column that left the band on the left (= the previous row's H[st0])
-			const int hleft = (int)shfl_idx(FULL, (uint32_t)sp_h, leader + 2, 32);
-			if (active && r > 0 && st0 > st0_prev) Hleft = Hs_prev;
-			if (sp_en0) sp_h = en0 - 1 >= st0 ? hleft : Hleft;
 			sync_warp(FULL); // all of the loads above precede the sentinel stores below
 			if (sp) *sp_hp = GD_KSW_NEG_INF; // keeps the bulk scan off these cells
 			if (active && li == 0 && r > 0 && st0 > st0_prev) *Hs_ptr = GD_KSW_NEG_INF; // ... and off the column that left
@@ -543,7 +550,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 				uint8_t *const rc = ring + kk * REC;
 				uint8_t *const rp = ring + (kk == 0 ? NR - 1 : kk - 1) * REC; // record of the left neighbour chunk
 				const int tb = cc << 3;
-				in.tw = *(const uint2 *)(tsm + tb);
+				in.tw = *(const uint2 *)(rc + REC_T);
 				const uint32_t *qw = (const uint32_t *)(qsm + ((qshift + tb) & ~3));
 				in.q0 = qw[0], in.q1 = qw[1], in.q2 = qw[2];
 				in.old = *(const uint2 *)(rc + REC_S);
@@ -678,8 +685,8 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 				const uint32_t pr = sp_en0 ? 0xffffu : (uint32_t)(3 - li) << 13 | (uint32_t)(GD_KSW_POS_MAX - sp_cc);
 				run = imax(run, (int)((uint32_t)relc << 16 | pr));
 			} else if (li == 3) hn = *sp_hp; // en0 == 0: column 0 was updated by the bulk pass
+			const int He = hn; // lane 3 only: H[en0] of this row (mte and the final score are tracked by lane 3)
 			for (int dd = 1; dd < G; dd <<= 1) run = imax(run, (int)shfl_xor(FULL, (uint32_t)run, dd, 32));
-			const int He = (int)shfl_idx(FULL, (uint32_t)hn, leader + 3, 32); // H[en0] of this row
 			sync_warp(FULL);
 			int32_t *const hs_ptr = (int32_t *)(ring + st0_off + REC_H) + (st0 & 7);
 			const int Hs = *hs_ptr; // H[st0] of this row
@@ -716,7 +723,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 		}
 		// ================= pair finished: publish the record =================
 		if (finish) {
-			if (li == 0) {
+			if (li == 3) { // every lane holds the same record; in exact mode lane 3 alone tracks mte and the final score
 				res.rows_done = rows_exec;
 				if (WITH_P) { // choice of the traceback start, ksw2_extd2_sse.c:389-400
 					if (!res.zdropped && !(C.flag & KSW_F_EXTZ_ONLY)) res.tb_i = tlen - 1, res.tb_j = qlen - 1;
@@ -728,7 +735,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			}
 			have = false;
 			qlen = tlen = 1, w = 0, r = 0; // idle geometry: one dummy cell per row until the next pair arrives
-			if (!SEQ_SMEM) tsm = B.tpk, qsm = B.qpk; // any valid arena
+			if (!SEQ_SMEM) qsm = B.qpk; // any valid arena
 			H0_t = 0, T_off = 0, r_off = 0;
 		}
 	}

@@ -95,7 +95,7 @@ static inline KswGeom ksw_geometry(int max_qlen, int max_tlen, int max_w, bool e
 	g.ring = ncol16 + 24 < T16 + 8 ? ncol16 + 24 : T16 + 8;
 	g.t_stride = T16;
 	g.q_stride = (max_qlen + 15) / 16 * 16 + 64;
-	g.group_smem = ksw_group_smem_bytes(g.ring, exact, G <= 8 ? g.t_stride + g.q_stride : 0);
+	g.group_smem = ksw_group_smem_bytes(g.ring, exact, G <= 8 ? g.q_stride : 0); // the target travels in the ring records
 	g.p_stride = with_p ? (int64_t)(max_qlen + max_tlen - 1) * ncol16 : 0;
 	return g;
 }

@@ -116,6 +116,19 @@ inline uint32_t ballot(uint32_t mask, int pred)
 	return r;
 }
 
+inline int reduce_max(uint32_t mask, int v)
+{ // __reduce_max_sync: maximum over the lanes named in this thread's mask
+	BlockState *b = cur_block();
+	int tid = b->cur, base = tid & ~31;
+	b->th[tid].xchg = (uint32_t)v;
+	sync_warp(mask);
+	int r = v;
+	for (int l = 0; l < 32; ++l)
+		if ((mask >> l & 1) && base + l < b->nthreads && (int)b->th[base + l].xchg > r) r = (int)b->th[base + l].xchg;
+	sync_warp(mask);
+	return r;
+}
+
 inline void sync_block()
 {
 	BlockState *b = cur_block();

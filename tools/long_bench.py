@@ -19,8 +19,8 @@ def main():
     ctx = gd.Context(0)
     dev = torch.device("cuda", 0)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    for name, n, qlen, edit, w, scn, flag in (("hifi", 256, 15000, 0.01, 1000, "map-hifi", 0x08), ("ont", 96, 50000, 0.08, 1300, "map-ont", 0x08),
-                                              ("hifi-exact", 256, 15000, 0.01, 1000, "map-hifi", 0x00)):
+    for name, n, qlen, edit, w, scn, flag in (("hifi", 2048, 15000, 0.01, 1000, "map-hifi", 0x08), ("ont", 512, 50000, 0.08, 1300, "map-ont", 0x08),
+                                              ("hifi-exact", 2048, 15000, 0.01, 1000, "map-hifi", 0x00)):
         P = synth.long_pairs(8, qlen, edit, seed=7, tlen_extra=0.01)
         # replicate the 8 generated pairs to n (timing only)
         rep = n // 8

@@ -1,0 +1,11 @@
+# usage: bash tools/gpu_profile_round.sh TAG  -- the per-round evidence set (bench line, ncu launch list, ncu full capture of the DP kernel)
+mkdir -p gpurun_out
+T=$1
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
+$CMD > gpurun_out/${T}_bench_plain.json 2> gpurun_out/${T}_bench_plain.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_ncu_launches.log 2>&1
+$CMD > /dev/null 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:gd_ksw_dp -s 4 -c 1 -o gpurun_out/${T}_dp_full $CMD > gpurun_out/${T}_ncu_full.log 2>&1
+python bench.py > gpurun_out/${T}_bench_default.json 2> gpurun_out/${T}_bench_default.err
+python bench.py --flag 0x8 --no-cpu > gpurun_out/${T}_bench_flag8.json 2>> gpurun_out/${T}_bench_default.err
+ls -la gpurun_out | tail -12

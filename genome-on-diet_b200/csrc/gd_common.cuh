@@ -11,11 +11,13 @@
 #ifdef GD_HOST_EMU
 #include "simt_emu.h" // tests/emu/simt_emu.h (test infrastructure)
 #define GD_DEV static inline
+#define GD_HD static inline
 #define GD_GLOBAL static
 #define GD_RESTRICT
 #else
 #include <cuda_runtime.h>
 #define GD_DEV __device__ __forceinline__
+#define GD_HD __host__ __device__ __forceinline__
 #define GD_GLOBAL __global__
 #define GD_RESTRICT __restrict__
 #endif
@@ -53,6 +55,7 @@ GD_DEV int grid_dim() { return (int)gridDim.x; }
 GD_DEV int atomic_add(int *p, int v) { return atomicAdd(p, v); }
 GD_DEV unsigned long long atomic_add64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 GD_DEV int popc(uint32_t x) { return __popc(x); }
+GD_DEV int clz32(uint32_t x) { return __clz((int)x); }
 GD_DEV uint64_t brev64(uint64_t x) { return __brevll(x); }
 GD_DEV void fence() { __threadfence(); }
 template <class T> GD_DEV T ld_volatile(const T *p) { return *(const volatile T *)p; }
@@ -125,6 +128,7 @@ GD_DEV unsigned long long atomic_add64(unsigned long long *p, unsigned long long
 	return o;
 }
 GD_DEV int popc(uint32_t x) { return __builtin_popcount(x); }
+GD_DEV int clz32(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 GD_DEV uint64_t brev64(uint64_t x)
 {
 	uint64_t r = 0;

@@ -14,12 +14,12 @@ gd_ctx *gd_thread_ctx();
 // --------------------------------------------------------------------------------------------
 // kernels
 // --------------------------------------------------------------------------------------------
-template <int THREADS, int P>
-__global__ void __launch_bounds__(THREADS) gd_sketch_tile_kernel(const SketchParams S, SketchBatch B)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 16) gd_sketch_tile_kernel(const SketchParams S, SketchBatch B)
 {
 	extern __shared__ __align__(16) uint8_t gd_sk_smem[];
 	if (B.tile_base) B.ntiles = B.tile_base[B.njobs];
-	sketch_tile_body<THREADS, P>(S, B, (SketchSmem<THREADS, P> *)gd_sk_smem);
+	sketch_tile_body<THREADS>(S, B, (SketchSmem<THREADS> *)gd_sk_smem);
 }
 
 // jobs for index-build sketching: one per sequence, shift 0
@@ -194,14 +194,16 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 	SketchBatch B;
 	memset(&B, 0, sizeof(B));
 	B.njobs = njobs, B.jobs = d_jobs, B.buf = d_buf, B.out_off = d_out_off, B.out = d_out, B.out_cap = out_cap;
-	const bool small = max_dl <= 256 - 2 * (S.w - 1);
+	// short reads: one warp-sized tile (256 positions) per job; otherwise 2048-position tiles
+	const int tp_small = sk_tile_emit(256, S.w, S.k);
+	const bool small = tp_small > 0 && max_dl <= tp_small;
 	int64_t ntiles_bound;
 	if (small) {
-		S.TP = 256 - 2 * (S.w - 1), S.one_tile_per_job = 1;
+		S.TP = tp_small, S.one_tile_per_job = 1;
 		ntiles_bound = njobs;
 		B.ntiles = njobs, B.tile_base = nullptr;
 	} else {
-		S.TP = 2048 - 2 * (S.w - 1), S.one_tile_per_job = 0;
+		S.TP = sk_tile_emit(2048, S.w, S.k), S.one_tile_per_job = 0;
 		ntiles_bound = pos_total / S.TP + 2 * (int64_t)njobs + 2;
 		if ((rc = gd_reserve(ctx, ctx->sk_misc, (size_t)(njobs + 1) * 8))) return rc;
 		int64_t *tb = (int64_t *)ctx->sk_misc.p;
@@ -215,16 +217,16 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 	B.status = (unsigned long long *)ctx->sk_state.p;
 	B.ticket = (int32_t *)((char *)ctx->sk_state.p + (size_t)ntiles_bound * 8);
 	if (small) {
-		typedef SketchSmem<64, 4> SM;
-		auto kern = gd_sketch_tile_kernel<64, 4>;
+		typedef SketchSmem<32> SM;
+		auto kern = gd_sketch_tile_kernel<32>;
 		int occ = 0;
-		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 64, sizeof(SM)));
+		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, sizeof(SM)));
 		int blocks = (int)std::min<int64_t>(ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));
 		GdKernelTimer tm(ctx, &ctx->tm_sketch);
-		kern<<<std::max(blocks, 1), 64, sizeof(SM), s>>>(S, B);
+		kern<<<std::max(blocks, 1), 32, sizeof(SM), s>>>(S, B);
 	} else {
-		typedef SketchSmem<256, 8> SM;
-		auto kern = gd_sketch_tile_kernel<256, 8>;
+		typedef SketchSmem<256> SM;
+		auto kern = gd_sketch_tile_kernel<256>;
 		int occ = 0;
 		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, sizeof(SM)));
 		int blocks = (int)std::min<int64_t>(ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));

@@ -86,23 +86,54 @@ GD_DEV uint32_t sk_real(uint32_t i, uint32_t shift, const SketchParams &S)
 
 #define GD_SK_MAXU64 0xffffffffffffffffull
 
-// Shared memory of one block: X[NP], M[NP] (uint64), aux[NP] (uint16: run | strand<<15), scan scratch.
-template <int THREADS, int P> struct SketchSmem {
-	enum { NP = THREADS * P };
-	uint64_t X[NP];
-	uint64_t M[NP];
-	uint16_t aux[NP];
+// ---- tile geometry ----
+// A tile loads NP = THREADS*8 consecutive sparsified positions [B0, B0+NP), 8 per thread, and emits for the
+// TP positions that follow a left halo of HL = 2w+k-3 positions (w-1 for the windows that contain an emit
+// position + w+k-2 for the N-free run that decides whether such a window is full) and precede a right
+// halo of w-1 positions.
+GD_HD int sk_halo_left(int w, int k) { return 2 * w + k - 3; }
+GD_HD int sk_tile_emit(int np, int w, int k) { return np - sk_halo_left(w, k) - (w - 1); }
+
+#define GD_SK_PADW 2 // zero words in front of the forward-packed codes (>= k bases)
+#define GD_SK_RAW 6144 // bytes of original sequence a tile can stage (2048 positions of "10", "110", "100", "101001" ...)
+
+// Shared memory of one block.  SUF / PREM are indexed [p][t] (position 8t+p at p*THREADS+t) so that
+// the threads of a warp touch consecutive 8-byte words.
+template <int THREADS> struct SketchSmem {
+	enum { NP = THREADS * 8 };
+	uint64_t SUF[NP];  // w >= 9: minimum of X over [s, end of s's 8-position chunk]; w <= 8: X itself
+	uint64_t PREM[NP]; // w >= 9: maximum of M over [start of chunk, s];               w <= 8: M itself
+	uint32_t F2[NP / 16 + GD_SK_PADW + 2]; // 2-bit codes, position s at bit 2s (after GD_SK_PADW zero words)
+	uint32_t R2[NP / 16 + 4];              // 2-bit codes, position s at bit 2(NP-1-s); zero words behind
+	int32_t warp_val[32];
 	int32_t warp_cnt[32];
 	long long excl;
 	int32_t tile;
+	uint8_t ones_loc[64];      // copy of SketchParams::ones_loc (indexed per lane)
+	uint32_t raw[GD_SK_RAW / 4 + 2]; // the tile's slice of the ASCII sequence, staged with coalesced word loads
 };
 
-template <int THREADS, int P>
-GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, SketchSmem<THREADS, P> *sm)
+GD_DEV uint64_t sk_bits64(const uint32_t *wds, int bit)
+{ // 64 bits of a little-endian bit stream starting at bit offset `bit` (3 words are read)
+	const int wi = bit >> 5, sh = bit & 31;
+	const uint64_t lo = (uint64_t)wds[wi] | (uint64_t)wds[wi + 1] << 32;
+	return sh ? (lo >> sh) | ((uint64_t)wds[wi + 2] << (64 - sh)) : lo;
+}
+GD_DEV uint64_t sk_min64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+GD_DEV uint64_t sk_max64(uint64_t a, uint64_t b) { return a > b ? a : b; }
+
+template <int THREADS>
+GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, SketchSmem<THREADS> *sm)
 {
-	const int NP = THREADS * P;
+	const int NP = THREADS * 8;
 	const int tid = thread_idx(), lane = tid & 31, wid = tid >> 5;
 	const int w = S.w, k = S.k, full_run = w + k - 1;
+	const int HL = sk_halo_left(w, k);
+	uint16_t *const F2h = (uint16_t *)(sm->F2 + GD_SK_PADW), *const R2h = (uint16_t *)sm->R2;
+	if (tid < GD_SK_PADW) sm->F2[tid] = 0;
+	if (tid < 2) sm->F2[NP / 16 + GD_SK_PADW + tid] = 0;
+	if (tid < 4) sm->R2[NP / 16 + tid] = 0;
+	for (int i = tid; i < 64; i += THREADS) sm->ones_loc[i] = S.ones_loc[i];
 	for (;;) {
 		if (tid == 0) sm->tile = atomic_add(B.ticket, 1);
 		sync_block();
@@ -125,80 +156,164 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 		const char *seq = B.buf + J.seq_off;
 		const uint32_t shift = (uint32_t)J.shift;
 		const long long dl = (long long)sk_diet_len((uint32_t)J.len, shift, S);
-		const long long i0 = chunk * S.TP;          // first emit position of the tile
-		const long long jbase = i0 - (w - 1);       // position held in slot 0
-		// ---- per-thread rolling pass over P positions ----
+		const long long i0 = chunk * S.TP; // first emit position of the tile
+		const long long B0 = i0 - HL;      // sparsified position held in slot 0
+		const int s0 = tid * 8;
+		// ---- phase 0: stage the original bytes the tile touches, [real(first position), real(last position)] ----
+		const long long jlo = B0 > 0 ? B0 : 0, jhi = (B0 + NP < dl ? B0 + NP : dl) - 1; // loaded positions inside the sequence
+		long long raw_lo = 0; // offset (relative to seq, may be -1..-3) of the first staged byte
+		bool staged = false;
+		if (jhi >= jlo) {
+			const uint32_t rlo = sk_real((uint32_t)jlo, shift, S), rhi = sk_real((uint32_t)jhi, shift, S);
+			// word-aligned window of the global buffer; the last, possibly partial word is fetched bytewise
+			const unsigned long long a0 = (unsigned long long)(seq + rlo);
+			const uint32_t lead = (uint32_t)(a0 & 3);
+			const uint32_t nbytes = rhi - rlo + 1 + lead;
+			if (nbytes <= GD_SK_RAW) {
+				staged = true, raw_lo = (long long)rlo - lead;
+				const uint32_t *gsrc = (const uint32_t *)(seq + raw_lo);
+				const uint32_t nfull = nbytes >> 2;
+				for (uint32_t i = tid; i < nfull; i += THREADS) sm->raw[i] = gsrc[i];
+				if (tid < (int)(nbytes & 3)) ((uint8_t *)sm->raw)[nfull * 4 + tid] = (uint8_t)seq[raw_lo + nfull * 4 + tid];
+			}
+		}
+		sync_block();
+		// ---- phase 1: encode 8 positions per thread; positions outside [0,dl) count as N ----
+		uint32_t code = 0, nmask = 0;
 		{
-			const long long j0 = jbase + (long long)tid * P;
-			uint64_t fw = 0, rv = 0;
-			int run = 0;
-			// warm-up: the N-free run that ends just before j0 (only its last w+k-2 bases matter)
-			if (j0 > 0 && j0 <= dl) {
-				long long back = j0 - 1, stop = j0 - (full_run - 1);
-				if (stop < 0) stop = 0;
-				while (back >= stop && sk_nt4((unsigned char)seq[sk_real((uint32_t)back, shift, S)]) < 4) --back;
-				run = (int)(j0 - 1 - back);
-				int take = run < k - 1 ? run : k - 1;
-				for (long long j = j0 - take; j < j0; ++j) {
-					uint64_t c = (uint64_t)sk_nt4((unsigned char)seq[sk_real((uint32_t)j, shift, S)]);
-					fw = (fw << 2 | c) & S.mask;
-					rv = (rv >> 2) | (3ull ^ c) << (2 * (k - 1));
-				}
-			}
-			for (int p = 0; p < P; ++p) {
+			const uint8_t *src = staged ? (const uint8_t *)sm->raw - raw_lo : (const uint8_t *)seq;
+			const long long j0 = B0 + s0;
+			// real(j) = (j/ones)*W + ones_loc[j%ones] + shift (get_real_location, sketch.c:20-23), stepped incrementally
+			uint32_t qd = 0, rm = 0;
+			if (j0 > 0) qd = (uint32_t)j0 / (uint32_t)S.ones, rm = (uint32_t)j0 - qd * (uint32_t)S.ones;
+			uint32_t base = qd * (uint32_t)S.W + shift;
+#pragma unroll
+			for (int p = 0; p < 8; ++p) {
 				const long long j = j0 + p;
-				uint64_t X = GD_SK_MAXU64;
-				uint32_t a = 0;
-				if (j >= 0 && j < dl) {
-					int c = sk_nt4((unsigned char)seq[sk_real((uint32_t)j, shift, S)]);
-					if (c < 4) {
-						fw = (fw << 2 | (uint64_t)c) & S.mask;
-						rv = (rv >> 2) | (uint64_t)(3 ^ c) << (2 * (k - 1));
-						if (run < 0x7fff) ++run;
-						if (run >= k && fw != rv) {
-							const int z = fw < rv ? 0 : 1;
-							X = sk_hash64(z ? rv : fw, S.mask) << 8 | (uint64_t)k;
-							a = (uint32_t)z << 15;
-						}
-					} else run = 0;
-					a |= (uint32_t)run;
+				int c = 4;
+				if (j >= 0 && j < dl) c = sk_nt4(src[base + sm->ones_loc[rm]]);
+				if (c < 4) code |= (uint32_t)c << (2 * p);
+				else nmask |= 1u << p;
+				if (j >= 0 && ++rm == (uint32_t)S.ones) rm = 0, base += (uint32_t)S.W;
+			}
+			F2h[tid] = (uint16_t)code;
+			uint32_t rc = 0; // the same 8 codes in reverse position order
+#pragma unroll
+			for (int p = 0; p < 8; ++p) rc |= ((code >> (2 * p)) & 3u) << (2 * (7 - p));
+			R2h[THREADS - 1 - tid] = (uint16_t)rc;
+		}
+		// ---- last N position before this thread's chunk: block-wide inclusive max-scan, made exclusive ----
+		int lastn;
+		{
+			int v = nmask ? s0 + 31 - clz32(nmask) : -1; // position 'before the tile' counts as N
+			int inc = v;
+			for (int d = 1; d < 32; d <<= 1) {
+				int o = (int)shfl_up(0xffffffffu, (uint32_t)inc, d, 32);
+				if (lane >= d && o > inc) inc = o;
+			}
+			if (lane == 31) sm->warp_val[wid] = inc;
+			sync_block(); // also publishes F2 / R2
+			int prev = (int)shfl_up(0xffffffffu, (uint32_t)inc, 1, 32);
+			lastn = lane == 0 ? -1 : prev;
+			for (int i = 0; i < wid; ++i) lastn = sm->warp_val[i] > lastn ? sm->warp_val[i] : lastn;
+		}
+		// ---- phase 2: the k-mers ending just before the chunk come out of the packed arrays; roll over the 8
+		// positions, hash (sketch.c:1660-1683) ----
+		uint64_t X[8];
+		uint32_t zbits = 0, fullbits = 0;
+		{
+			uint64_t rv = (~sk_bits64(sm->F2, 32 * GD_SK_PADW + 2 * (s0 - k))) & S.mask; // bases s0-k .. s0-1, complemented
+			uint64_t fw = sk_bits64(sm->R2, 2 * (NP - s0)) & S.mask;                       // bases s0-1 .. s0-k
+			// (bases before slot 0 read as zero bits; such k-mers are never valid because slot -1 counts as N)
+#pragma unroll
+			for (int p = 0; p < 8; ++p) {
+				const int sp = s0 + p;
+				const uint64_t c = (code >> (2 * p)) & 3u;
+				fw = (fw << 2 | c) & S.mask;
+				rv = (rv >> 2) | (3ull ^ c) << (2 * (k - 1));
+				if (nmask >> p & 1) lastn = sp;
+				const int run = sp - lastn;
+				uint64_t x = GD_SK_MAXU64;
+				if (run >= k && fw != rv) {
+					const int z = fw < rv ? 0 : 1;
+					x = sk_hash64(z ? rv : fw, S.mask) << 8 | (uint64_t)k;
+					zbits |= (uint32_t)z << p;
 				}
-				sm->X[tid * P + p] = X;
-				sm->aux[tid * P + p] = (uint16_t)a;
+				if (run >= full_run) fullbits |= 1u << p;
+				X[p] = x;
 			}
 		}
-		sync_block();
-		// ---- minimum of every full window ending at e ----
-		for (int p = 0; p < P; ++p) {
-			const int s = tid * P + p;
-			const long long e = jbase + s;
-			uint64_t m = 0; // 0 = "no full window ends here" (X >= 1 always)
-			if (e >= 0 && e < dl && s >= w - 1 && (sm->aux[s] & 0x7fff) >= full_run) {
-				m = GD_SK_MAXU64;
-				for (int d = 0; d < w; ++d) {
-					uint64_t x = sm->X[s - d];
-					m = x < m ? x : m;
-				}
-				if (m == GD_SK_MAXU64) m = 0;
-			}
-			sm->M[s] = m;
-		}
-		sync_block();
-		// ---- emission: X(i) equals the largest full-window minimum among windows containing i ----
 		uint32_t emit = 0;
 		int cnt = 0;
-		for (int p = 0; p < P; ++p) {
-			const int s = tid * P + p;
-			const long long i = jbase + s;
-			if (s >= w - 1 && s < w - 1 + S.TP && i < dl) {
-				const uint64_t x = sm->X[s];
-				if (x != GD_SK_MAXU64) {
+		if (w >= 9) {
+			// ---- phase 3: minimum of every full window ending at e = s0+p.  The window starts in an earlier
+			// chunk (w-1 >= 8): own prefix minimum, whole chunks in between, suffix minimum of the first chunk ----
+			uint64_t pre[8], M[8];
+			{
+				uint64_t suf = GD_SK_MAXU64, pr = GD_SK_MAXU64;
+#pragma unroll
+				for (int p = 7; p >= 0; --p) suf = sk_min64(suf, X[p]), sm->SUF[p * THREADS + tid] = suf;
+#pragma unroll
+				for (int p = 0; p < 8; ++p) pr = sk_min64(pr, X[p]), pre[p] = pr;
+			}
+			sync_block();
+#pragma unroll
+			for (int p = 0; p < 8; ++p) {
+				const int a = s0 + p - (w - 1); // first position of the window
+				uint64_t m = 0;                 // 0 = "no full window ends here" (X >= 1 always)
+				if ((fullbits >> p & 1) && a >= 0) {
+					const int ta = a >> 3;
+					m = sk_min64(pre[p], sm->SUF[(a & 7) * THREADS + ta]);
+					for (int c = ta + 1; c < tid; ++c) m = sk_min64(m, sm->SUF[c]); // SUF[0][c] = minimum of chunk c
+					if (m == GD_SK_MAXU64) m = 0;
+				}
+				M[p] = m;
+			}
+			// ---- phase 4: X(i) is emitted iff it equals the largest full-window minimum among the windows that
+			// contain i, i.e. the maximum of M over [i, i+w-1]: own suffix maximum, whole chunks, prefix maximum ----
+			uint64_t sufm[8];
+			{
+				uint64_t pm = 0, sx = 0;
+#pragma unroll
+				for (int p = 0; p < 8; ++p) pm = sk_max64(pm, M[p]), sm->PREM[p * THREADS + tid] = pm;
+#pragma unroll
+				for (int p = 7; p >= 0; --p) sx = sk_max64(sx, M[p]), sufm[p] = sx;
+			}
+			sync_block();
+#pragma unroll
+			for (int p = 0; p < 8; ++p) {
+				const int sp = s0 + p;
+				if (sp >= HL && sp < HL + S.TP && B0 + sp < dl && X[p] != GD_SK_MAXU64) {
+					const int b = sp + w - 1, tb = b >> 3; // last position of the last window; b < NP in the emit range
+					uint64_t mx = sk_max64(sufm[p], sm->PREM[(b & 7) * THREADS + tb]);
+					for (int c = tid + 1; c < tb; ++c) mx = sk_max64(mx, sm->PREM[7 * THREADS + c]); // PREM[7][c] = maximum of chunk c
+					if (mx == X[p]) emit |= 1u << p, ++cnt;
+				}
+			}
+		} else {
+			// ---- small windows (w <= 8): direct scans over X and M in shared memory ----
+#pragma unroll
+			for (int p = 0; p < 8; ++p) sm->SUF[p * THREADS + tid] = X[p];
+			sync_block();
+#pragma unroll
+			for (int p = 0; p < 8; ++p) {
+				const int sp = s0 + p;
+				uint64_t m = 0;
+				if ((fullbits >> p & 1) && sp >= w - 1) {
+					m = GD_SK_MAXU64;
+					for (int d = 0; d < w; ++d) m = sk_min64(m, sm->SUF[((sp - d) & 7) * THREADS + ((sp - d) >> 3)]);
+					if (m == GD_SK_MAXU64) m = 0;
+				}
+				sm->PREM[p * THREADS + tid] = m;
+			}
+			sync_block();
+#pragma unroll
+			for (int p = 0; p < 8; ++p) {
+				const int sp = s0 + p;
+				if (sp >= HL && sp < HL + S.TP && B0 + sp < dl && X[p] != GD_SK_MAXU64) {
 					uint64_t mx = 0;
-					for (int d = 0; d < w && s + d < NP; ++d) {
-						uint64_t m = sm->M[s + d];
-						mx = m > mx ? m : mx;
-					}
-					if (mx == x) emit |= 1u << p, ++cnt;
+					for (int d = 0; d < w; ++d) mx = sk_max64(mx, sm->PREM[((sp + d) & 7) * THREADS + ((sp + d) >> 3)]);
+					if (mx == X[p]) emit |= 1u << p, ++cnt;
 				}
 			}
 		}
@@ -243,14 +358,13 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 		sync_block();
 		const long long obase = sm->excl + local;
 		int o = 0;
-		for (int p = 0; p < P; ++p)
+#pragma unroll
+		for (int p = 0; p < 8; ++p)
 			if (emit >> p & 1) {
-				const int s = tid * P + p;
-				const long long i = jbase + s, dst = obase + o;
+				const long long i = B0 + s0 + p, dst = obase + o;
 				if (dst < B.out_cap) {
-					const uint64_t y = (uint64_t)J.rid << 32 | (uint64_t)sk_real((uint32_t)i, shift, S) << 1 |
-					                   (uint64_t)(sm->aux[s] >> 15);
-					B.out[2 * dst] = sm->X[s];
+					const uint64_t y = (uint64_t)J.rid << 32 | (uint64_t)sk_real((uint32_t)i, shift, S) << 1 | (uint64_t)(zbits >> p & 1);
+					B.out[2 * dst] = X[p];
 					B.out[2 * dst + 1] = y;
 				}
 				++o;

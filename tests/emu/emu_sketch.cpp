@@ -7,11 +7,11 @@
 
 using namespace gd;
 
-template <int THREADS, int P>
+template <int THREADS>
 static void run_tiles(const SketchParams &S, SketchBatch &B, int grid)
 {
-	emu::launch(grid, THREADS, sizeof(SketchSmem<THREADS, P>),
-	            [&]() { sketch_tile_body<THREADS, P>(S, B, (SketchSmem<THREADS, P> *)emu::smem()); });
+	emu::launch(grid, THREADS, sizeof(SketchSmem<THREADS>),
+	            [&]() { sketch_tile_body<THREADS>(S, B, (SketchSmem<THREADS> *)emu::smem()); });
 }
 
 // jobs: n x {seq_off, len, shift, rid}; small != 0 forces the one-tile-per-job configuration
@@ -26,7 +26,7 @@ extern "C" long emu_sketch_jobs(int njobs, const int64_t *seq_off, const int32_t
 		if (Z[g] == '1') S.ones_loc[S.ones++] = (uint8_t)g;
 	std::vector<SketchJob> jobs(njobs);
 	for (int i = 0; i < njobs; ++i) jobs[i] = SketchJob{seq_off[i], len[i], shift[i], rid[i], 0};
-	S.TP = (small ? 256 : 2048) - 2 * (w - 1);
+	S.TP = sk_tile_emit(small ? 256 : 2048, w, k);
 	S.one_tile_per_job = small;
 	std::vector<int64_t> tb(njobs + 1, 0);
 	for (int i = 0; i < njobs; ++i) {
@@ -47,7 +47,7 @@ extern "C" long emu_sketch_jobs(int njobs, const int64_t *seq_off, const int32_t
 	memset(&B, 0, sizeof(B));
 	B.njobs = njobs, B.ntiles = tb[njobs], B.jobs = jobs.data(), B.tile_base = small ? nullptr : tb.data();
 	B.buf = buf, B.status = status.data(), B.ticket = &ticket, B.out_off = out_off, B.out = out, B.out_cap = out_cap;
-	if (small) run_tiles<64, 4>(S, B, grid);
-	else run_tiles<256, 8>(S, B, grid);
+	if (small) run_tiles<32>(S, B, grid);
+	else run_tiles<256>(S, B, grid);
 	return (long)out_off[njobs];
 }

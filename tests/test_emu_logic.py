@@ -100,7 +100,8 @@ def test_emu_sketch(emu, oracle):
         Z = pats[it % 6]
         small = it % 2
         if small:
-            lens = [int(rng.integers(len(Z), (256 - 2 * (w - 1)) * len(Z) // Z.count("1"))) for _ in range(10)]
+            tp = 256 - (2 * w + k - 3) - (w - 1)  # emit positions of the one-warp tile (gd_sketch.cuh: sk_tile_emit)
+            lens = [int(rng.integers(len(Z), tp * len(Z) // Z.count("1"))) for _ in range(10)]
         else:
             lens = [int(x) for x in rng.choice([40, 150, 1000, 5000, 9000], 5)]
         seqs = []

@@ -6,7 +6,7 @@ python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; echo "pyt
 tail -3 gpurun_out/${T}_pytest.log
 fi
 for G in 4 8; do for F in 0x8 0x0; do
-python bench.py --steps 5 --warmup 3 --pairs 262144 --flag $F --group $G --no-cpu >> gpurun_out/${T}_bench_tune.jsonl 2>> gpurun_out/${T}_bench_err.log
+python bench.py --steps 5 --warmup 3 --pairs 262144 --flag $F --group $G --no-cpu --no-sketch >> gpurun_out/${T}_bench_tune.jsonl 2>> gpurun_out/${T}_bench_err.log
 done; done
 python - <<PY
 import json

@@ -1,7 +1,7 @@
 # usage: bash tools/gpu_profile_round.sh TAG  -- the per-round evidence set (bench line, ncu launch list, ncu full capture of the DP kernel)
 mkdir -p gpurun_out
 T=$1
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-sketch"
 $CMD > gpurun_out/${T}_bench_plain.json 2> gpurun_out/${T}_bench_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_ncu_launches.log 2>&1
 $CMD > /dev/null 2>&1 &&

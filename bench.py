@@ -255,14 +255,10 @@ def ours(args, rank, world, local_rank):
     assert np.array_equal(ez_h["score"], ez["score"]), "device-resident and host-buffer arms disagree"
 
     # ---- max over ranks ------------------------------------------------------------------------
-    tot_cells = cells_step
-    if dist:
-        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
-        c = torch.tensor([cells_step, launches, h2d, d2h], dtype=torch.int64, device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        tot_cells, launches, h2d, d2h = (int(x) for x in c)
+    # time = MAX over ranks, work = SUM over ranks (genome-on-diet_b200/shard.py; no data-path collective)
+    from gdiet_b200 import shard
+    (dev_ms, e2e_ms), (tot_cells, launches, h2d, d2h) = shard.reduce_timing([dev_ms, e2e_ms], [cells_step, launches, h2d, d2h],
+                                                                              device=dev if dist else "cpu")
     if rank != 0:
         if dist:
             dist.destroy_process_group()

@@ -33,6 +33,12 @@ GD_DEV uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x
 GD_DEV uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); } // max(a+b, c) per half
 GD_DEV int iaddmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }                          // max(a+b, c)
 GD_DEV int imax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+GD_DEV uint32_t fma_add(uint32_t a, uint32_t one, uint32_t c)
+{ // a * one + c with `one` == 1 at run time: an IMAD (FMA pipe) where a plain add would be an ALU-pipe VIADD
+	uint32_t r;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(c));
+	return r;
+}
 GD_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 { // raw PRMT: unlike __byte_perm (which masks the selector with 0x7777) this keeps bit 3 of every
   // selector nibble = "replicate the sign bit of the selected byte"
@@ -88,6 +94,7 @@ GD_DEV int imax3(int a, int b, int c)
 	int m = a > b ? a : b;
 	return m > c ? m : c;
 }
+GD_DEV uint32_t fma_add(uint32_t a, uint32_t one, uint32_t c) { return a * one + c; }
 GD_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 {
 	uint64_t v = ((uint64_t)b << 32) | a;

@@ -128,7 +128,7 @@ GD_DEV void cell2(const CT &C, uint32_t s, uint32_t xt1, uint32_t vt1, uint32_t 
 	uint32_t a = vadd2(xt1, vt1), b = vadd2(y, ut), a2 = vadd2(x2t1, vt1), b2 = vadd2(y2, ut);
 	zt = vmax3(vmax3(s, a, b), a2, b2);
 	const uint32_t z = vmin2(zt & 0xff00ff00u, C.MCH16);
-	const uint32_t z1 = vadd2(z, 0x00010001u);
+	const uint32_t z1 = fma_add(z, C.ONE, 0x00010001u); // low bytes of z are 0: no carry between the halves
 	u_new = vadd2(z1, ~vt1); // z - v[t-1]
 	v_new = vadd2(z1, ~ut);  // z - u[t]
 	const uint32_t nz = ~z;
@@ -136,7 +136,8 @@ GD_DEV void cell2(const CT &C, uint32_t s, uint32_t xt1, uint32_t vt1, uint32_t 
 	uint32_t ma, mb, ma2, mb2;
 	if (!RIGHT) { // continuation iff value > 0  <=> high byte of max(value,0) >= 1
 		ma = vaddmax2(a, nzq, C.TA), mb = vaddmax2(b, nzq, C.TB), ma2 = vaddmax2(a2, nzq2, C.TA2), mb2 = vaddmax2(b2, nzq2, C.TB2);
-		fa = ma + 0x7f007f00u, fb = mb + 0x7f007f00u, fa2 = ma2 + 0x7f007f00u, fb2 = mb2 + 0x7f007f00u;
+		fa = fma_add(ma, C.ONE, 0x7f007f00u), fb = fma_add(mb, C.ONE, 0x7f007f00u);
+		fa2 = fma_add(ma2, C.ONE, 0x7f007f00u), fb2 = fma_add(mb2, C.ONE, 0x7f007f00u);
 	} else { // continuation iff value >= 0 <=> sign bit clear
 		a = vadd2(a, nzq), b = vadd2(b, nzq), a2 = vadd2(a2, nzq2), b2 = vadd2(b2, nzq2);
 		ma = vmax2(a, C.TA), mb = vmax2(b, C.TB), ma2 = vmax2(a2, C.TA2), mb2 = vmax2(b2, C.TB2);
@@ -289,14 +290,16 @@ GD_DEV void row_max_literal(uint8_t *ring, int rec_bytes, int NR, int st_rec, in
 // pack kernel) rather than from the kernel parameters: values that come from the constant bank are
 // re-loaded by ptxas inside the loop (10 LDC per step), values loaded from global memory stay in registers.
 struct KswHot {
-	uint32_t MCH16, Q1, Q21, NEGQE, NEGQE2, TS4, TA, TB, TA2, TB2, TAGX, MCH4, MIS4, SCN4, pad0, pad1;
+	uint32_t MCH16, Q1, Q21, NEGQE, NEGQE2, TS4, TA, TB, TA2, TB2, TAGX, MCH4, MIS4, SCN4;
+	uint32_t ONE;  // the constant 1, opaque to the compiler: fma_add(a, ONE, c) = a + c issues on the FMA pipe (IMAD)
+	uint32_t pad1; // instead of the integer-ALU pipe that bounds the kernel
 };
 GD_DEV KswHot ksw_hot_from_consts(const KswConsts &C)
 {
 	KswHot h;
 	h.MCH16 = C.MCH16, h.Q1 = C.Q1, h.Q21 = C.Q21, h.NEGQE = C.NEGQE, h.NEGQE2 = C.NEGQE2, h.TS4 = C.TS4, h.TA = C.TA;
 	h.TB = C.TB, h.TA2 = C.TA2, h.TB2 = C.TB2, h.TAGX = C.TAGX, h.MCH4 = C.MCH4, h.MIS4 = C.MIS4, h.SCN4 = C.SCN4;
-	h.pad0 = h.pad1 = 0;
+	h.ONE = 1, h.pad1 = 0;
 	return h;
 }
 GD_DEV KswHot ksw_hot_load(const KswHot *p)

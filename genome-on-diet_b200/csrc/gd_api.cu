@@ -3,6 +3,8 @@
 #include "gd_ctx.h"
 #include <algorithm>
 #include <mutex>
+#include <thread>
+#include <vector>
 #include <stdlib.h>
 #include <string.h>
 
@@ -93,6 +95,7 @@ extern "C" void gd_destroy(gd_ctx *ctx)
 	for (cudaEvent_t e : ctx->tm_pool) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->copy_stream);
+	if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
 	delete ctx;
 }
 
@@ -106,6 +109,7 @@ extern "C" int gd_set_option(gd_ctx *ctx, const char *key, long value)
 	else if (!strcmp(key, "ksw_blocks_per_sm")) ctx->opt_ksw_blocks_per_sm = value;
 	else if (!strcmp(key, "sketch_chunk")) ctx->opt_sketch_chunk = value;
 	else if (!strcmp(key, "time_kernels")) ctx->opt_time_kernels = value;
+	else if (!strcmp(key, "ksw_slice")) ctx->opt_ksw_slice = value;
 	else {
 		ctx->err = std::string("unknown option ") + key;
 		return GD_ERR_ARG;
@@ -151,6 +155,10 @@ extern "C" int gd_ksw_extd2_batch_device(gd_ctx *ctx, int n, const int32_t *d_ql
 	                         max_w, prm, d_ez, d_cigar, cigar_stride);
 }
 
+// Host-buffer entry point.  The batch is cut into slices that flow through three streams: inputs go up on
+// copy_stream, pack + DP + traceback + CIGAR compaction run on stream, results come down on d2h_stream, so
+// the transfers of one slice overlap the kernels of its neighbours.  The dense CIGAR pool is filled in pair
+// order by chaining the per-slice offset scans through a device-side running base.
 extern "C" int gd_ksw_extd2_batch(gd_ctx *ctx, int n, const int32_t *qlen, const int64_t *qoff, const uint8_t *qbuf,
                                   const int32_t *tlen, const int64_t *toff, const uint8_t *tbuf, const int32_t *w,
                                   int w_all, const gd_ksw_params_t *prm, gd_extz_t *ez, int64_t *cigar_off,
@@ -164,20 +172,50 @@ extern "C" int gd_ksw_extd2_batch(gd_ctx *ctx, int n, const int32_t *qlen, const
 	if (cigar_off) cigar_off[0] = 0;
 	if (n == 0) return GD_OK;
 	cudaSetDevice(ctx->device);
-	// extents and bounds
+	if (!ctx->d2h_stream) GD_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+	// slices
+	int slice = (int)ctx->opt_ksw_slice;
+	if (slice <= 0) slice = n < 65536 ? n : std::max(32768, (n + 7) / 8);
+	const int nsl = (n + slice - 1) / slice;
+	// extents and bounds (whole batch and per slice)
+	struct Sl {
+		int b, n, max_q, max_t, max_w;
+		int64_t q0, q1, t0, t1;
+	};
+	std::vector<Sl> sl(nsl);
 	int64_t qbytes = 0, tbytes = 0;
-	int max_q = 1, max_t = 1, max_w = 0;
-	for (int i = 0; i < n; ++i) {
-		const int ql = std::max(qlen[i], 0), tl = std::max(tlen[i], 0);
-		qbytes = std::max<int64_t>(qbytes, qoff[i] + ql);
-		tbytes = std::max<int64_t>(tbytes, toff[i] + tl);
-		max_q = std::max(max_q, ql), max_t = std::max(max_t, tl);
-		int ww = w ? w[i] : w_all;
-		if (ww < 0) ww = std::max(ql, tl);
-		max_w = std::max(max_w, ww);
+	int max_q = 1, max_t = 1;
+	auto scan_slice = [&](int k) {
+		Sl &S = sl[k];
+		S.b = k * slice, S.n = std::min(slice, n - S.b), S.max_q = S.max_t = 1, S.max_w = 0;
+		S.q0 = S.t0 = INT64_MAX, S.q1 = S.t1 = 0;
+		for (int i = S.b; i < S.b + S.n; ++i) {
+			const int ql = std::max(qlen[i], 0), tl = std::max(tlen[i], 0);
+			S.q0 = std::min<int64_t>(S.q0, qoff[i]), S.q1 = std::max<int64_t>(S.q1, qoff[i] + ql);
+			S.t0 = std::min<int64_t>(S.t0, toff[i]), S.t1 = std::max<int64_t>(S.t1, toff[i] + tl);
+			S.max_q = std::max(S.max_q, ql), S.max_t = std::max(S.max_t, tl);
+			int ww = w ? w[i] : w_all;
+			if (ww < 0) ww = std::max(ql, tl);
+			S.max_w = std::max(S.max_w, ww);
+		}
+	};
+	if (nsl > 1) { // one host thread per slice: the scan of a million descriptors is otherwise ~3 ms of the call
+		std::vector<std::thread> th;
+		for (int k = 0; k < nsl; ++k) th.emplace_back(scan_slice, k);
+		for (auto &t : th) t.join();
+	} else scan_slice(0);
+	for (int k = 0; k < nsl; ++k) {
+		const Sl &S = sl[k];
+		if (S.q0 < 0 || S.t0 < 0) {
+			ctx->err = "gd_ksw_extd2_batch: negative sequence offset";
+			return GD_ERR_ARG;
+		}
+		qbytes = std::max(qbytes, S.q1), tbytes = std::max(tbytes, S.t1);
+		max_q = std::max(max_q, S.max_q), max_t = std::max(max_t, S.max_t);
 	}
 	const bool want_cigar = !(prm->flag & 0x01) && cigar_off != nullptr;
 	const int stride = want_cigar ? max_q + max_t : 0;
+	const bool want_pool = want_cigar && cigar && cigar_cap > 0;
 	int rc;
 	if ((rc = gd_reserve(ctx, ctx->d_qlen, (size_t)n * 4))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->d_tlen, (size_t)n * 4))) return rc;
@@ -187,48 +225,91 @@ extern "C" int gd_ksw_extd2_batch(gd_ctx *ctx, int n, const int32_t *qlen, const
 	if ((rc = gd_reserve(ctx, ctx->d_qbuf, (size_t)qbytes + 16))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->d_tbuf, (size_t)tbytes + 16))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->res, (size_t)n * sizeof(gd_extz_t)))) return rc;
-	if ((rc = gd_reserve(ctx, ctx->cig_off, (size_t)(n + 1) * 8))) return rc;
-	if (want_cigar && (rc = gd_reserve(ctx, ctx->cig_tmp, (size_t)n * stride * 4))) return rc;
-	cudaStream_t s = ctx->stream;
-	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_qlen.p, qlen, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tlen.p, tlen, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_qoff.p, qoff, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_toff.p, toff, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-	if (w) GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_w.p, w, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_qbuf.p, qbuf, (size_t)qbytes, cudaMemcpyHostToDevice, s));
-	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tbuf.p, tbuf, (size_t)tbytes, cudaMemcpyHostToDevice, s));
-	rc = gd_ksw_run_device(ctx, n, (const int32_t *)ctx->d_qlen.p, (const int64_t *)ctx->d_qoff.p,
-	                       (const uint8_t *)ctx->d_qbuf.p, (const int32_t *)ctx->d_tlen.p, (const int64_t *)ctx->d_toff.p,
-	                       (const uint8_t *)ctx->d_tbuf.p, w ? (const int32_t *)ctx->d_w.p : nullptr, w_all, max_q, max_t,
-	                       max_w, prm, (gd_extz_t *)ctx->res.p, want_cigar ? (uint32_t *)ctx->cig_tmp.p : nullptr, stride);
-	if (rc) return rc;
-	GD_CUDA_OK(ctx, cudaMemcpyAsync(ez, ctx->res.p, (size_t)n * sizeof(gd_extz_t), cudaMemcpyDeviceToHost, s));
-	if (cigar_off) {
-		// offsets first (tiny), then a compact gather sized from the total
-		rc = gd_ksw_compact_cigars(ctx, n, (const gd_extz_t *)ctx->res.p, nullptr, stride, (int64_t *)ctx->cig_off.p,
-		                           nullptr, 0);
-		if (rc) return rc;
-		GD_CUDA_OK(ctx, cudaMemcpyAsync(cigar_off, ctx->cig_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
-		GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
-		const int64_t total = cigar_off[n];
-		if (cigar && total > 0) {
-			if (total > cigar_cap) {
-				ctx->err = "gd_ksw_extd2_batch: cigar buffer too small";
-				return GD_ERR_CAPACITY;
+	if ((rc = gd_reserve(ctx, ctx->cig_off, (size_t)(n + 2) * 8))) return rc;
+	if (want_cigar && (rc = gd_reserve(ctx, ctx->cig_tmp, (size_t)std::min(slice, n) * stride * 4 * (nsl > 1 ? 2 : 1)))) return rc;
+	if (want_pool && (rc = gd_reserve(ctx, ctx->cig_compact, (size_t)cigar_cap * 4))) return rc;
+	if ((rc = gd_reserve_pinned(ctx, ctx->h_misc, (size_t)(nsl + 1) * 8))) return rc;
+	int64_t *h_end = (int64_t *)ctx->h_misc.p;       // pool position after each slice (written by the device)
+	int64_t *d_run = (int64_t *)ctx->cig_off.p + n + 1; // device-side running base
+	cudaStream_t s = ctx->stream, up = ctx->copy_stream, down = ctx->d2h_stream;
+	std::vector<cudaEvent_t> ev_up(nsl), ev_done(nsl);
+	for (int k = 0; k < nsl; ++k) ev_up[k] = GdKernelTimer::get(ctx), ev_done[k] = GdKernelTimer::get(ctx);
+	auto release = [&]() {
+		for (int k = 0; k < nsl; ++k) ctx->tm_pool.push_back(ev_up[k]), ctx->tm_pool.push_back(ev_done[k]);
+	};
+	GD_CUDA_OK(ctx, cudaMemsetAsync(d_run, 0, 8, s));
+	// the previous call's kernels may still read the staging buffers: uploads start after them
+	GD_CUDA_OK(ctx, cudaEventRecord(ev_done[0], s));
+	GD_CUDA_OK(ctx, cudaStreamWaitEvent(up, ev_done[0], 0));
+	for (int k = 0; k < nsl; ++k) { // ---- enqueue everything
+		const Sl &S = sl[k];
+		GD_CUDA_OK(ctx, cudaMemcpyAsync((int32_t *)ctx->d_qlen.p + S.b, qlen + S.b, (size_t)S.n * 4, cudaMemcpyHostToDevice, up));
+		GD_CUDA_OK(ctx, cudaMemcpyAsync((int32_t *)ctx->d_tlen.p + S.b, tlen + S.b, (size_t)S.n * 4, cudaMemcpyHostToDevice, up));
+		GD_CUDA_OK(ctx, cudaMemcpyAsync((int64_t *)ctx->d_qoff.p + S.b, qoff + S.b, (size_t)S.n * 8, cudaMemcpyHostToDevice, up));
+		GD_CUDA_OK(ctx, cudaMemcpyAsync((int64_t *)ctx->d_toff.p + S.b, toff + S.b, (size_t)S.n * 8, cudaMemcpyHostToDevice, up));
+		if (w) GD_CUDA_OK(ctx, cudaMemcpyAsync((int32_t *)ctx->d_w.p + S.b, w + S.b, (size_t)S.n * 4, cudaMemcpyHostToDevice, up));
+		if (S.q1 > S.q0)
+			GD_CUDA_OK(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_qbuf.p + S.q0, qbuf + S.q0, (size_t)(S.q1 - S.q0), cudaMemcpyHostToDevice, up));
+		if (S.t1 > S.t0)
+			GD_CUDA_OK(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_tbuf.p + S.t0, tbuf + S.t0, (size_t)(S.t1 - S.t0), cudaMemcpyHostToDevice, up));
+		GD_CUDA_OK(ctx, cudaEventRecord(ev_up[k], up));
+		GD_CUDA_OK(ctx, cudaStreamWaitEvent(s, ev_up[k], 0));
+		uint32_t *tmp = want_cigar ? (uint32_t *)ctx->cig_tmp.p + (size_t)(k & 1) * slice * stride : nullptr;
+		gd_extz_t *d_res = (gd_extz_t *)ctx->res.p + S.b;
+		rc = gd_ksw_run_device(ctx, S.n, (const int32_t *)ctx->d_qlen.p + S.b, (const int64_t *)ctx->d_qoff.p + S.b,
+		                       (const uint8_t *)ctx->d_qbuf.p, (const int32_t *)ctx->d_tlen.p + S.b,
+		                       (const int64_t *)ctx->d_toff.p + S.b, (const uint8_t *)ctx->d_tbuf.p,
+		                       w ? (const int32_t *)ctx->d_w.p + S.b : nullptr, w_all, S.max_q, S.max_t, S.max_w, prm, d_res, tmp,
+		                       stride);
+		if (rc) {
+			release();
+			return rc;
+		}
+		if (cigar_off) {
+			rc = gd_ksw_compact_cigars(ctx, S.n, d_res, want_pool ? tmp : nullptr, stride, (int64_t *)ctx->cig_off.p + S.b,
+			                           want_pool ? (uint32_t *)ctx->cig_compact.p : nullptr, cigar_cap, d_run, h_end + k + 1);
+			if (rc) {
+				release();
+				return rc;
 			}
-			if ((rc = gd_reserve(ctx, ctx->cig_compact, (size_t)total * 4))) return rc;
-			rc = gd_ksw_compact_cigars(ctx, n, (const gd_extz_t *)ctx->res.p, (const uint32_t *)ctx->cig_tmp.p, stride,
-			                           (int64_t *)ctx->cig_off.p, (uint32_t *)ctx->cig_compact.p, total);
-			if (rc) return rc;
-			GD_CUDA_OK(ctx, cudaMemcpyAsync(cigar, ctx->cig_compact.p, (size_t)total * 4, cudaMemcpyDeviceToHost, s));
+		}
+		GD_CUDA_OK(ctx, cudaEventRecord(ev_done[k], s));
+	}
+	h_end[0] = 0;
+	int status = GD_OK;
+	for (int k = 0; k < nsl; ++k) { // ---- results come down slice by slice while later slices compute
+		const Sl &S = sl[k];
+		GD_CUDA_OK(ctx, cudaStreamWaitEvent(down, ev_done[k], 0));
+		GD_CUDA_OK(ctx, cudaMemcpyAsync(ez + S.b, (gd_extz_t *)ctx->res.p + S.b, (size_t)S.n * sizeof(gd_extz_t), cudaMemcpyDeviceToHost, down));
+		if (cigar_off) {
+			GD_CUDA_OK(ctx, cudaMemcpyAsync(cigar_off + S.b, (int64_t *)ctx->cig_off.p + S.b, (size_t)(S.n + 1) * 8, cudaMemcpyDeviceToHost, down));
+			GD_CUDA_OK(ctx, cudaEventSynchronize(ev_done[k])); // h_end[k+1] is valid now
+			if (h_end[k + 1] < 0) status = GD_ERR_ARG, h_end[k + 1] = -1 - h_end[k + 1]; // stride overflow inside the slice
+			const int64_t lo = h_end[k], hi = h_end[k + 1];
+			if (want_pool && hi > lo) {
+				if (hi > cigar_cap) status = status == GD_OK ? GD_ERR_CAPACITY : status;
+				else GD_CUDA_OK(ctx, cudaMemcpyAsync(cigar + lo, (uint32_t *)ctx->cig_compact.p + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, down));
+			}
 		}
 	}
+	GD_CUDA_OK(ctx, cudaStreamSynchronize(down));
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
-	for (int i = 0; i < n; ++i)
-		if (ez[i].n_cigar < 0) {
-			ctx->err = "gd_ksw_extd2_batch: internal cigar stride overflow";
-			return GD_ERR_CAPACITY;
-		}
+	release();
+	if (status == GD_ERR_CAPACITY) {
+		ctx->err = "gd_ksw_extd2_batch: cigar buffer too small";
+		return status;
+	}
+	if (cigar && cigar_off && !want_pool && cigar_off[n] > 0) {
+		ctx->err = "gd_ksw_extd2_batch: cigar buffer too small";
+		return GD_ERR_CAPACITY;
+	}
+	if (status == GD_ERR_ARG || !cigar_off) { // (without CIGAR offsets nobody scanned n_cigar on the device)
+		for (int i = 0; i < n; ++i)
+			if (ez[i].n_cigar < 0) {
+				ctx->err = "gd_ksw_extd2_batch: internal cigar stride overflow";
+				return GD_ERR_CAPACITY;
+			}
+	}
 	return GD_OK;
 }
 

@@ -24,7 +24,8 @@ struct gd_ctx {
 	size_t smem_optin = 0;  // max dynamic shared memory per block
 	size_t smem_per_sm = 0; // shared memory per SM
 	cudaStream_t stream = nullptr;
-	cudaStream_t copy_stream = nullptr;
+	cudaStream_t copy_stream = nullptr; // host -> device
+	cudaStream_t d2h_stream = nullptr;  // device -> host (PCIe is full duplex)
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	std::string err;
 	// options
@@ -32,6 +33,7 @@ struct gd_ctx {
 	long opt_p_budget_mb = 0; // 0 = auto
 	long opt_ksw_blocks_per_sm = 0;
 	long opt_sketch_chunk = 0;
+	long opt_ksw_slice = 0;    // pairs per pipeline slice of the host-buffer DP call (0 = auto)
 	long opt_time_kernels = 0; // 1: bracket every DP / sketch kernel launch with CUDA events (bench.py roofline)
 	// stats
 	long stat_launches = 0;
@@ -123,5 +125,8 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
                       const int32_t *d_tlen, const int64_t *d_toff, const uint8_t *d_tbuf, const int32_t *d_w,
                       int w_all, int max_qlen, int max_tlen, int max_w, const gd_ksw_params_t *prm, gd_extz_t *d_ez,
                       uint32_t *d_cigar, int cigar_stride);
+// offsets (+ optional gather into a dense pool); d_run_base: device word with the pool position to start from
+// (updated to the end), h_end: pinned host word that receives the end -- both may be NULL
 int gd_ksw_compact_cigars(gd_ctx *ctx, int n, const gd_extz_t *d_ez, const uint32_t *d_cigar, int cigar_stride,
-                          int64_t *d_off /*n+1*/, uint32_t *d_compact, int64_t compact_cap);
+                          int64_t *d_off /*n+1*/, uint32_t *d_compact, int64_t compact_cap, int64_t *d_run_base = nullptr,
+                          int64_t *h_end = nullptr);

@@ -53,12 +53,15 @@ __global__ void gd_ksw_nocigar_kernel(int n, KswResult *res)
 }
 
 // exclusive scan of max(n_cigar,0) over n pairs (single block; n_cigar arrays are small)
-__global__ void __launch_bounds__(1024) gd_ksw_cigar_scan_kernel(int n, const KswResult *res, int64_t *off)
-{
+// off[i] = *run_base + (sum of earlier counts); off[n] and *run_base receive the end, *h_end too (pinned host word)
+__global__ void __launch_bounds__(1024)
+    gd_ksw_cigar_scan_kernel(int n, const KswResult *res, int64_t *off, int64_t *run_base, int64_t *h_end)
+{ // h_end[0] receives the end position; h_end[-1]... is not touched; a negative n_cigar (stride overflow) makes the end negative
 	__shared__ int64_t warp_sum[32];
 	__shared__ int64_t carry;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	if (tid == 0) carry = 0;
+	int bad = 0;
+	if (tid == 0) carry = run_base ? *run_base : 0;
 	__syncthreads();
 	for (int base = 0; base < n; base += 1024) {
 		const int i = base + tid;
@@ -66,6 +69,7 @@ __global__ void __launch_bounds__(1024) gd_ksw_cigar_scan_kernel(int n, const Ks
 		if (i < n) {
 			int c = res[i].n_cigar;
 			v = c > 0 ? c : 0;
+			if (c < 0) bad = 1;
 		}
 		int64_t inc = v;
 		for (int d = 1; d < 32; d <<= 1) {
@@ -89,7 +93,12 @@ __global__ void __launch_bounds__(1024) gd_ksw_cigar_scan_kernel(int n, const Ks
 		if (tid == 1023) carry = excl + v;
 		__syncthreads();
 	}
-	if (tid == 0) off[n] = carry;
+	bad = __syncthreads_or(bad);
+	if (tid == 0) {
+		off[n] = carry;
+		if (run_base) *run_base = carry;
+		if (h_end) *h_end = bad ? -1 - carry : carry; // negative: some pair overflowed its CIGAR stride
+	}
 }
 
 __global__ void __launch_bounds__(256)
@@ -259,10 +268,10 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 }
 
 int gd_ksw_compact_cigars(gd_ctx *ctx, int n, const gd_extz_t *d_ez, const uint32_t *d_cigar, int cigar_stride,
-                          int64_t *d_off, uint32_t *d_compact, int64_t compact_cap)
+                          int64_t *d_off, uint32_t *d_compact, int64_t compact_cap, int64_t *d_run_base, int64_t *h_end)
 {
 	cudaStream_t s = ctx->stream;
-	gd_ksw_cigar_scan_kernel<<<1, 1024, 0, s>>>(n, (const KswResult *)d_ez, d_off);
+	gd_ksw_cigar_scan_kernel<<<1, 1024, 0, s>>>(n, (const KswResult *)d_ez, d_off, d_run_base, h_end);
 	ctx->stat_launches++;
 	if (d_compact && d_cigar) {
 		int blocks = std::min((n + 7) / 8, ctx->sms * 8);

@@ -315,6 +315,11 @@ def ours(args, rank, world, local_rank):
     if not args.no_sketch:
         try:
             sk = sketch_extra(ctx, stream, dev, peaks)
+            if world == 1 and not args.no_cpu:
+                try:
+                    sk["cpu_baseline"] = sketch_cpu_baseline()
+                except Exception as e:
+                    sk["cpu_baseline"] = {"kind": "unavailable", "sample": str(e)}
         except Exception as e:
             sk = {"error": str(e)}
     line = {"metric": "ksw_extd2 GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -327,6 +332,30 @@ def ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
+
+
+def sketch_cpu_baseline():
+    """reference mm_sketch (AVX-512 build of oracle/_ref when the host has it) on all host threads: contigs of 2 Mbp,
+    repeated for ~5 s"""
+    from oraclelib import Ref, cpu_has_avx512
+    import gdiet_b200  # noqa: F401
+    from gdiet_b200 import synth
+    variant = "avx" if cpu_has_avx512() else "scalar"
+    R = Ref(variant)
+    cores = host_threads()
+    L, nc = 250_000, cores * 32  # the glue hands out 16 sequences per grab: 2 grabs per thread
+    g = synth.random_genome(L * nc, seed=11).tobytes()
+    off = np.arange(nc, dtype=np.int64) * L
+    lens = np.full(nc, L, np.int32)
+    R.mm_sketch_batch(off, lens, g, 11, 21, "10", cores)
+    tot, passes = 0.0, 0
+    while tot < 5.0 and passes < 64:
+        t0 = time.perf_counter()
+        R.mm_sketch_batch(off, lens, g, 11, 21, "10", cores)
+        tot += time.perf_counter() - t0
+        passes += 1
+    return {"value": passes * L * nc / tot / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "reference",
+            "sample": "%d passes of mm_sketch (%s build) over %d contigs of %d bp on %d threads, %.1f s" % (passes, variant, nc, L, cores, tot)}
 
 
 def sketch_extra(ctx, stream, dev, peaks):

@@ -63,10 +63,12 @@ GD_DEV uint64_t sk_hash64(uint64_t key, uint64_t mask)
 }
 
 GD_DEV int sk_nt4(unsigned c)
-{ // seq_nt4_table, GDiet-ShortReads/sketch.c:11-18
-	unsigned u = c & 0xdfu; // fold case
-	if (c < 4) return (int)c;
-	return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : (u == 'T' || u == 'U') ? 3 : 4;
+{ // seq_nt4_table, GDiet-ShortReads/sketch.c:11-18, branch-free: A/a C/c G/g T/t U/u -> 0 1 2 3 3, bytes 0..3 map to
+  // themselves, everything else -> 4.  For the letters ((c>>1)^(c>>2))&3 is the code; they are the bytes 0x40..0x7f
+  // whose low five bits are 1, 3, 7, 20 or 21.
+	const unsigned letter = ((c & 0xc0u) == 0x40u) & ((0x0030008au >> (c & 31u)) & 1u);
+	const unsigned code = ((c >> 1) ^ (c >> 2)) & 3u;
+	return c < 4 ? (int)c : letter ? (int)code : 4;
 }
 
 GD_DEV uint32_t sk_diet_len(uint32_t len, uint32_t shift, const SketchParams &S)
@@ -179,9 +181,10 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 		}
 		sync_block();
 		// ---- phase 1: encode 8 positions per thread; positions outside [0,dl) count as N ----
-		uint32_t code = 0, nmask = 0;
+		uint32_t code = 0, nmask = 0, real[8];
 		{
-			const uint8_t *src = staged ? (const uint8_t *)sm->raw - raw_lo : (const uint8_t *)seq;
+			const uint32_t raw_lo0 = jhi >= jlo ? sk_real((uint32_t)jlo, shift, S) : 0; // some byte of the sequence that is staged / exists
+			const uint8_t *src = staged ? (const uint8_t *)sm->raw - raw_lo : jhi >= jlo ? (const uint8_t *)seq : (const uint8_t *)sm->raw;
 			const long long j0 = B0 + s0;
 			// real(j) = (j/ones)*W + ones_loc[j%ones] + shift (get_real_location, sketch.c:20-23), stepped incrementally
 			uint32_t qd = 0, rm = 0;
@@ -190,9 +193,11 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 #pragma unroll
 			for (int p = 0; p < 8; ++p) {
 				const long long j = j0 + p;
-				int c = 4;
-				if (j >= 0 && j < dl) c = sk_nt4(src[base + sm->ones_loc[rm]]);
-				if (c < 4) code |= (uint32_t)c << (2 * p);
+				const bool in = j >= 0 && j < dl;
+				const uint32_t rp = base + sm->ones_loc[rm];
+				const int c = sk_nt4(src[in ? rp : (uint32_t)raw_lo0]); // out-of-range positions read a valid byte, count as N
+				real[p] = rp;
+				if (in && c < 4) code |= (uint32_t)c << (2 * p);
 				else nmask |= 1u << p;
 				if (j >= 0 && ++rm == (uint32_t)S.ones) rm = 0, base += (uint32_t)S.W;
 			}
@@ -264,6 +269,7 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 				if ((fullbits >> p & 1) && a >= 0) {
 					const int ta = a >> 3;
 					m = sk_min64(pre[p], sm->SUF[(a & 7) * THREADS + ta]);
+#pragma unroll 1
 					for (int c = ta + 1; c < tid; ++c) m = sk_min64(m, sm->SUF[c]); // SUF[0][c] = minimum of chunk c
 					if (m == GD_SK_MAXU64) m = 0;
 				}
@@ -286,6 +292,7 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 				if (sp >= HL && sp < HL + S.TP && B0 + sp < dl && X[p] != GD_SK_MAXU64) {
 					const int b = sp + w - 1, tb = b >> 3; // last position of the last window; b < NP in the emit range
 					uint64_t mx = sk_max64(sufm[p], sm->PREM[(b & 7) * THREADS + tb]);
+#pragma unroll 1
 					for (int c = tid + 1; c < tb; ++c) mx = sk_max64(mx, sm->PREM[7 * THREADS + c]); // PREM[7][c] = maximum of chunk c
 					if (mx == X[p]) emit |= 1u << p, ++cnt;
 				}
@@ -301,6 +308,7 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 				uint64_t m = 0;
 				if ((fullbits >> p & 1) && sp >= w - 1) {
 					m = GD_SK_MAXU64;
+#pragma unroll 1
 					for (int d = 0; d < w; ++d) m = sk_min64(m, sm->SUF[((sp - d) & 7) * THREADS + ((sp - d) >> 3)]);
 					if (m == GD_SK_MAXU64) m = 0;
 				}
@@ -312,6 +320,7 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 				const int sp = s0 + p;
 				if (sp >= HL && sp < HL + S.TP && B0 + sp < dl && X[p] != GD_SK_MAXU64) {
 					uint64_t mx = 0;
+#pragma unroll 1
 					for (int d = 0; d < w; ++d) mx = sk_max64(mx, sm->PREM[((sp + d) & 7) * THREADS + ((sp + d) >> 3)]);
 					if (mx == X[p]) emit |= 1u << p, ++cnt;
 				}
@@ -361,9 +370,9 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 #pragma unroll
 		for (int p = 0; p < 8; ++p)
 			if (emit >> p & 1) {
-				const long long i = B0 + s0 + p, dst = obase + o;
+				const long long dst = obase + o;
 				if (dst < B.out_cap) {
-					const uint64_t y = (uint64_t)J.rid << 32 | (uint64_t)sk_real((uint32_t)i, shift, S) << 1 | (uint64_t)(zbits >> p & 1);
+					const uint64_t y = (uint64_t)J.rid << 32 | (uint64_t)real[p] << 1 | (uint64_t)(zbits >> p & 1);
 					B.out[2 * dst] = X[p];
 					B.out[2 * dst + 1] = y;
 				}

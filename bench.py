@@ -133,7 +133,7 @@ def reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": "ksw_extd2 GCUPS", "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-            "config": workload_config(args, n),
+            "config": workload_config(args, args.pairs),  # same workload as our arm; each step times a bounded sample of it
             "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": cores, "kind": "reference",
                              "sample": "%d of the %d pairs per step, ksw_extd2_%s, flag %#x, cells counted as full band" % (
                                  n, args.pairs, "avx512" if variant == "avx" else "sse", args.flag)},

@@ -46,6 +46,15 @@ __global__ void __launch_bounds__(128) gd_ksw_traceback_kernel(const KswBatch B,
 	if (lp < B.n) ksw_traceback_one(B, flag, lp, cigar, stride);
 }
 
+// long pairs: one warp per pair, backtrack bytes staged through shared memory tiles
+__global__ void __launch_bounds__(128) gd_ksw_traceback_warp_kernel(const KswBatch B, int flag, uint32_t *cigar, int stride)
+{
+	__shared__ uint2 tiles[4][GD_KSW_TB_ROWS * GD_KSW_TB_CHUNKS];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int lp = blockIdx.x * 4 + wid;
+	if (lp < B.n) ksw_traceback_warp(B, flag, lp, cigar, stride, tiles[wid], lane);
+}
+
 __global__ void gd_ksw_nocigar_kernel(int n, KswResult *res)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,7 +268,10 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 			GdKernelTimer tm(ctx, &ctx->tm_dp);
 			kern<<<blocks, threads, smem, s>>>(C, B);
 		}
-		if (with_p) gd_ksw_traceback_kernel<<<(cn + 127) / 128, 128, 0, s>>>(B, flag, d_cigar, cigar_stride);
+		if (with_p) {
+			if (max_qlen + max_tlen >= 2048) gd_ksw_traceback_warp_kernel<<<(cn + 3) / 4, 128, 0, s>>>(B, flag, d_cigar, cigar_stride);
+			else gd_ksw_traceback_kernel<<<(cn + 127) / 128, 128, 0, s>>>(B, flag, d_cigar, cigar_stride);
+		}
 		ctx->stat_launches += with_p ? 3 : 2;
 		ctx->stat_ksw_chunks++;
 	}

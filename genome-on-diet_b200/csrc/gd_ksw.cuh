@@ -851,4 +851,116 @@ GD_DEV void ksw_traceback_one(const KswBatch &B, int flag, int lp, uint32_t *cig
 	res->n_cigar = overflow ? -n : n;
 }
 
+// Same walk for long pairs, one WARP per pair: the backtrack bytes the path can touch next (32 rows x 80
+// columns ending at the current cell -- a step moves up one or two rows and at most one column to the
+// left) are fetched into shared memory with one coalesced 8-byte load per lane and chunk, then every lane
+// walks the tile redundantly (identical state, broadcast reads) and lane 0 writes the CIGAR.  This turns
+// ~10^5 dependent global loads per ONT-sized pair into ~10^5 / 24 tile fills.
+#define GD_KSW_TB_ROWS 32
+#define GD_KSW_TB_CHUNKS 10
+GD_DEV void ksw_traceback_warp(const KswBatch &B, int flag, int lp, uint32_t *cig_out, int stride, uint2 *tile, int lane)
+{
+	const int pair = B.base + lp;
+	KswResult *res = &B.res[pair];
+	int i = res->tb_i, j = res->tb_j, n = 0, state = 0, overflow = 0;
+	if (i < 0 || j < 0) {
+		if (lane == 0) res->n_cigar = 0;
+		return;
+	}
+	const int qlen = B.qlen[pair], tlen = B.tlen[pair];
+	int w = B.w ? B.w[pair] : B.w_all;
+	if (w < 0) w = imax(tlen, qlen);
+	const int ncol16 = ksw_ncol16(qlen, tlen, w);
+	const uint8_t *p = B.p + (size_t)lp * B.p_stride;
+	uint32_t *cig = cig_out + (size_t)pair * stride;
+	uint32_t cur = 0; // pending op: len<<4|op, 0 = none
+	while (i >= 0 && j >= 0) {
+		// ---- fill the tile: rows r_top .. r_top-31, columns [wlo, wlo+80) ----
+		const int r_top = i + j, r_bot = imax(r_top - (GD_KSW_TB_ROWS - 1), 0);
+		const int wlo = ((i >> 3) - (GD_KSW_TB_CHUNKS - 1)) * 8; // may be negative: those chunks are outside every row
+		sync_warp(0xffffffffu);                                   // the previous tile's readers are done
+		{
+			const int rr = r_top - lane;
+			Bounds rb;
+			rb.st = 0, rb.en = -1;
+			if (rr >= 0) row_bounds(rr, qlen, tlen, w, rb);
+			for (int c = 0; c < GD_KSW_TB_CHUNKS; ++c) {
+				const int cb = wlo + 8 * c;
+				uint2 v;
+				v.x = v.y = 0;
+				if (rr >= 0 && cb >= rb.st && cb <= rb.en) v = *(const uint2 *)(p + (size_t)rr * ncol16 + (cb - rb.st));
+				tile[lane * GD_KSW_TB_CHUNKS + c] = v;
+			}
+		}
+		sync_warp(0xffffffffu);
+		// ---- walk while the path stays inside the tile's rows ----
+		while (i >= 0 && j >= 0 && i + j >= r_bot) {
+			const int r = i + j;
+			int force = -1;
+			Bounds bd;
+			row_bounds(r, qlen, tlen, w, bd);
+			if (i < bd.st) force = 2;
+			if (i > bd.en) force = 1;
+			const int cc = i - wlo; // 0..79
+			const uint8_t *row = (const uint8_t *)(tile + (r_top - r) * GD_KSW_TB_CHUNKS);
+			uint32_t cell = force < 0 ? row[(cc & ~7) + chunk_pos(cc & 7)] : 0;
+			if (state == 0) state = cell & 7;
+			else if (!((cell >> (state + 2)) & 1)) state = 0;
+			if (state == 0) state = cell & 7;
+			if (force >= 0) state = force;
+			uint32_t op;
+			if (state == 0) op = 0, --i, --j;
+			else if (state == 1 || state == 3) op = 2, --i;
+			else op = 1, --j;
+			if (cur && (cur & 0xf) == op) cur += 16;
+			else {
+				if (cur) {
+					if (n < stride) {
+						if (lane == 0) cig[n] = cur;
+					} else overflow = 1;
+					++n;
+				}
+				cur = 16 | op;
+			}
+		}
+	}
+	if (i >= 0) { // leading deletion
+		if (cur && (cur & 0xf) == 2) cur += (uint32_t)(i + 1) << 4;
+		else {
+			if (cur) {
+				if (n < stride) {
+					if (lane == 0) cig[n] = cur;
+				} else overflow = 1;
+				++n;
+			}
+			cur = (uint32_t)(i + 1) << 4 | 2;
+		}
+	}
+	if (j >= 0) { // leading insertion
+		if (cur && (cur & 0xf) == 1) cur += (uint32_t)(j + 1) << 4;
+		else {
+			if (cur) {
+				if (n < stride) {
+					if (lane == 0) cig[n] = cur;
+				} else overflow = 1;
+				++n;
+			}
+			cur = (uint32_t)(j + 1) << 4 | 1;
+		}
+	}
+	if (cur) {
+		if (n < stride) {
+			if (lane == 0) cig[n] = cur;
+		} else overflow = 1;
+		++n;
+	}
+	sync_warp(0xffffffffu);
+	if (!overflow && !(flag & KSW_F_REV_CIGAR)) // ksw2.h:158-160: forward order unless REV_CIGAR (all lanes swap disjoint entries)
+		for (int k = lane; k < n >> 1; k += 32) {
+			uint32_t t = cig[k];
+			cig[k] = cig[n - 1 - k], cig[n - 1 - k] = t;
+		}
+	if (lane == 0) res->n_cigar = overflow ? -n : n;
+}
+
 } // namespace gd

@@ -11,12 +11,14 @@
 #ifdef GD_HOST_EMU
 #include "simt_emu.h" // tests/emu/simt_emu.h (test infrastructure)
 #define GD_DEV static inline
+#define GD_MEM inline /* static member functions */
 #define GD_HD static inline
 #define GD_GLOBAL static
 #define GD_RESTRICT
 #else
 #include <cuda_runtime.h>
 #define GD_DEV __device__ __forceinline__
+#define GD_MEM __device__ __forceinline__
 #define GD_HD __host__ __device__ __forceinline__
 #define GD_GLOBAL __global__
 #define GD_RESTRICT __restrict__

@@ -10,6 +10,7 @@ static_assert(sizeof(KswResult) == sizeof(gd_extz_t), "result layouts must match
 // --------------------------------------------------------------------------------------------
 // kernels
 // --------------------------------------------------------------------------------------------
+// G <= 32: every warp of the block carries 32/G pairs; G = 64 / 128: block-per-pair (blockDim.x == G)
 template <int G, bool RIGHT, int MODE, bool WITH_P>
 __global__ void __launch_bounds__(128) gd_ksw_dp_kernel(const KswConsts C, const KswBatch B)
 {
@@ -17,8 +18,10 @@ __global__ void __launch_bounds__(128) gd_ksw_dp_kernel(const KswConsts C, const
 	const int tid = threadIdx.x;
 	ksw_build_lut(gd_smem, tid, blockDim.x);
 	__syncthreads();
-	uint8_t *warp_smem = gd_smem + GD_KSW_LUT_BYTES + (size_t)(tid >> 5) * (32 / G) * B.group_smem;
-	ksw_warp_body<G, RIGHT, MODE, WITH_P>(C, B, warp_smem, gd_smem, tid & 31);
+	if (G <= 32) {
+		uint8_t *warp_smem = gd_smem + GD_KSW_LUT_BYTES + (size_t)(tid >> 5) * (32 / (G <= 32 ? G : 32)) * B.group_smem;
+		ksw_warp_body<G, RIGHT, MODE, WITH_P>(C, B, warp_smem, gd_smem, tid & 31);
+	} else ksw_warp_body<G, RIGHT, MODE, WITH_P>(C, B, gd_smem + GD_KSW_LUT_BYTES, gd_smem, tid);
 }
 
 // one warp per pair: raw byte codes -> padded arenas
@@ -160,7 +163,9 @@ static dp_kernel_t pick_kernel(int G, bool right, int mode, bool with_p)
 	case 4: return pick_mode<4>(right, mode, with_p);
 	case 8: return pick_mode<8>(right, mode, with_p);
 	case 16: return pick_mode<16>(right, mode, with_p);
-	default: return pick_mode<32>(right, mode, with_p);
+	case 32: return pick_mode<32>(right, mode, with_p);
+	case 64: return pick_mode<64>(right, mode, with_p);
+	default: return pick_mode<128>(right, mode, with_p);
 	}
 }
 
@@ -184,7 +189,7 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 	KswConsts C = ksw_make_consts(prm->m, prm->mat, prm->q, prm->e, prm->q2, prm->e2, prm->zdrop, prm->end_bonus, flag);
 	if (max_w < 0) max_w = std::max(max_qlen, max_tlen);
 	int G = (int)ctx->opt_ksw_group;
-	if (G != 4 && G != 8 && G != 16 && G != 32) G = ksw_pick_group(max_qlen, max_tlen, max_w);
+	if (G != 4 && G != 8 && G != 16 && G != 32 && G != 64 && G != 128) G = ksw_pick_group(max_qlen, max_tlen, max_w, exact, n, ctx->sms);
 	KswGeom geo = ksw_geometry(max_qlen, max_tlen, max_w, exact, with_p, G);
 	if (geo.ring > GD_KSW_POS_MAX - 32 && exact) {
 		ctx->err = "gd_ksw: band too wide for the exact-max keys (ring > 8158 columns)";
@@ -195,16 +200,20 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 	// worth of groups does not fit, widen the group (fewer pairs per warp)
 	int threads = 0;
 	for (;;) {
-		const size_t per_warp = (size_t)(32 / G) * geo.group_smem;
-		int best_warps = 0;
-		for (int wpb = 1; wpb <= 4; ++wpb) {
-			const size_t blk = GD_KSW_LUT_BYTES + wpb * per_warp;
-			if (blk > ctx->smem_optin) break;
-			const int resident = (int)std::min<size_t>(32, ctx->smem_per_sm / (blk + 1024)) * wpb;
-			if (resident >= best_warps) best_warps = resident, threads = wpb * 32;
+		if (G > 32) { // block-per-pair
+			if (GD_KSW_LUT_BYTES + (size_t)geo.group_smem <= ctx->smem_optin) threads = G;
+		} else {
+			const size_t per_warp = (size_t)(32 / G) * geo.group_smem;
+			int best_warps = 0;
+			for (int wpb = 1; wpb <= 4; ++wpb) {
+				const size_t blk = GD_KSW_LUT_BYTES + wpb * per_warp;
+				if (blk > ctx->smem_optin) break;
+				const int resident = (int)std::min<size_t>(32, ctx->smem_per_sm / (blk + 1024)) * wpb;
+				if (resident >= best_warps) best_warps = resident, threads = wpb * 32;
+			}
 		}
 		if (threads) break;
-		if (G < 32) {
+		if (G < 128) {
 			G <<= 1;
 			geo = ksw_geometry(max_qlen, max_tlen, max_w, exact, with_p, G);
 			continue;
@@ -212,7 +221,7 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 		ctx->err = "gd_ksw: band too wide for the shared-memory column ring (needs > 227 KB per pair)";
 		return GD_ERR_ARG;
 	}
-	const int groups_per_block = threads / G;
+	const int groups_per_block = G > 32 ? 1 : threads / G;
 	const size_t smem = GD_KSW_LUT_BYTES + (size_t)groups_per_block * geo.group_smem;
 	const int mode = exact ? 2 : (flag & KSW_F_APPROX_DROP) ? 1 : 0;
 	dp_kernel_t kern = pick_kernel(G, right, mode, with_p);

@@ -325,6 +325,36 @@ GD_DEV uint4 rep4(uint32_t v)
 	return q;
 }
 
+// Collectives of one "gang": the lanes that execute the row loop together.  G <= 32: a warp that carries
+// 32/G pairs (groups) at once; G > 32 (block-per-pair, for the widest bands): one pair per thread block
+// of G threads, where every value the row loop votes on is already uniform.
+template <int G> struct Gang {
+	static GD_MEM void sync() { if (G <= 32) sync_warp(0xffffffffu); else sync_block(); }
+	static GD_MEM bool any(bool p) { return G <= 32 ? ballot(0xffffffffu, p) != 0 : p; }
+	static GD_MEM int max_steps(int v) { return G <= 32 ? reduce_max(0xffffffffu, v) : v; }
+	// value held by lane 0 of every group -> all lanes of that group (scratch: >= 1 int of shared memory per block)
+	static GD_MEM int from_leader(int v, int lane, int *scratch)
+	{
+		if (G <= 32) return (int)shfl_idx(0xffffffffu, (uint32_t)v, lane & ~(G - 1), 32);
+		if (lane == 0) scratch[0] = v;
+		sync_block();
+		const int r = scratch[0];
+		sync_block();
+		return r;
+	}
+	// maximum over the lanes of a group (scratch: >= G/32 ints)
+	static GD_MEM int group_max(int v, int lane, int *scratch)
+	{
+		for (int dd = 1; dd < (G <= 32 ? G : 32); dd <<= 1) v = imax(v, (int)shfl_xor(0xffffffffu, (uint32_t)v, dd, 32));
+		if (G <= 32) return v;
+		if ((lane & 31) == 0) scratch[1 + (lane >> 5)] = v;
+		sync_block();
+		for (int i = 0; i < G / 32; ++i) v = imax(v, scratch[1 + i]);
+		sync_block();
+		return v;
+	}
+};
+
 // One warp, 32/G pairs at a time.  All control flow is warp-uniform (every loop runs for the
 // maximum trip count over the groups of the warp, per-lane work is predicated), so every barrier
 // and vote uses the full mask.  A group that finishes its pair fetches the next one at once.
@@ -335,7 +365,8 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 	const bool EXACT = MODE == 2;
 	const uint32_t FULL = 0xffffffffu;
 	const int REC = RecSize<EXACT>::value;
-	const int li = lane & (G - 1), leader = lane & ~(G - 1);
+	const int li = lane & (G - 1);
+	int *const scratch = (int *)(lut + 1216); // spare words of the lookup-table block (block-per-pair collectives)
 	uint8_t *const ring = smem_warp + (size_t)(lane / G) * B.group_smem;
 	const int NR = B.ring >> 3;
 	// The target codes travel in the ring records.  Short pairs (G <= 8) stage the reversed query next to
@@ -372,10 +403,10 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 	for (;;) {
 		// ================= fetch: groups without a pair take the next ticket =================
 		const bool need = !have && !done;
-		if (ballot(FULL, need)) {
+		if (Gang<G>::any(need)) {
 			int lp = 0;
 			if (need && li == 0) lp = atomic_add(B.ticket, 1);
-			lp = (int)shfl_idx(FULL, (uint32_t)lp, leader, 32);
+			lp = Gang<G>::from_leader(lp, lane, scratch);
 			bool fresh = false;
 			const uint8_t *tpk = 0, *qpk = 0;
 			if (need) {
@@ -432,8 +463,8 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 					}
 				}
 			}
-			sync_warp(FULL);
-			if (!ballot(FULL, have)) break; // nothing left anywhere in this warp
+			Gang<G>::sync();
+			if (!Gang<G>::any(have)) break; // nothing left anywhere in this warp / block
 		}
 		// ================= one anti-diagonal for every group that has a pair =================
 		// (groups without a pair run the same instructions on a one-cell dummy row; their stores are off)
@@ -465,7 +496,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			// single-column patches below can fall into it (they touch columns <= en0|15; block 0 is
 			// initialised when the pair is fetched).
 			const bool need_init = active && init_hi <= imin((en0 + 15) >> 4, nblk_t - 1);
-			if (ballot(FULL, need_init)) {
+			if (Gang<G>::any(need_init)) {
 				if (need_init && li < 2) {
 					uint8_t *rc = col_rec(ring, REC, NR, st_rec, init_hi * 16 + li * 8 - st);
 					*(uint4 *)(rc + REC_A) = rep4(C.INIT_A), *(uint4 *)(rc + REC_B) = rep4(C.INIT_B);
@@ -523,17 +554,17 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 			sp_cc = tcol - st;
 			sp_hp = (int32_t *)(rsp + REC_H) + jsp;
 			sp_bp = rsp + pos2(jsp);
-			sync_warp(FULL); // all of the loads above precede the sentinel stores below
+			Gang<G>::sync(); // all of the loads above precede the sentinel stores below
 			if (sp) *sp_hp = GD_KSW_NEG_INF; // keeps the bulk scan off these cells
 			if (active && li == 0 && r > 0 && st0 > st0_prev) *Hs_ptr = GD_KSW_NEG_INF; // ... and off the column that left
 		}
-		sync_warp(FULL);
+		Gang<G>::sync();
 		// ---- phase B: score row + core update, chunk by chunk from the right end of the row ----
 		int run = (int)0x80000000; // exact mode: best (relative score << 16 | priority) key of this lane
 		{
 			const int cbeg = st >> 3;
 			const int ctop = imax(en, fe - 1) >> 3; // chunk of lane G-1 in the first step
-			const int nsteps = reduce_max(FULL, active ? (ctop - cbeg + G) / G : 0);
+			const int nsteps = Gang<G>::max_steps(active ? (ctop - cbeg + G) / G : 0);
 			const int qshift = active ? qlen - 1 - r + GD_KSW_QFRONT : GD_KSW_QFRONT; // qsm offset of the query base under column 0
 			const uint32_t qsh = (uint32_t)(qshift & 3) * 8; // chunks start at multiples of 8: same byte phase in every step
 			const int nMprev = -Mprev;
@@ -610,7 +641,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 				             prmt(SB.z, 0, 0x2404), y2, y22, u2, v2, x2, x22, zt2, fa2, fb2, fa22, fb22);
 				cell2<RIGHT>(K, prmt(sw1, K.TS4, 0x3424), (SA.z & HI) | K.TA, prmt(SA.z, 0, 0x2404), (SB.z & HI) | K.TA2,
 				             prmt(SB.w, 0, 0x2404), y3, y23, u3, v3, x3, x23, zt3, fa3, fb3, fa23, fb23);
-				sync_warp(FULL); // every lane has read its left neighbour's old column before anybody stores
+				Gang<G>::sync(); // every lane has read its left neighbour's old column before anybody stores
 				if (cvalid) {
 					uint2 sv;
 					sv.x = sw0, sv.y = sw1;
@@ -655,7 +686,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 				}
 			}
 		}
-		sync_warp(FULL);
+		Gang<G>::sync();
 		// ---- phase C: score tracking ----
 		int stop = 0;
 		if (!EXACT) { // ksw2_extd2_sse.c:367-383 (every lane of the group tracks the same H0)
@@ -689,8 +720,8 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 				run = imax(run, (int)((uint32_t)relc << 16 | pr));
 			} else if (li == 3) hn = *sp_hp; // en0 == 0: column 0 was updated by the bulk pass
 			const int He = hn; // lane 3 only: H[en0] of this row (mte and the final score are tracked by lane 3)
-			for (int dd = 1; dd < G; dd <<= 1) run = imax(run, (int)shfl_xor(FULL, (uint32_t)run, dd, 32));
-			sync_warp(FULL);
+			run = Gang<G>::group_max(run, lane, scratch);
+			Gang<G>::sync();
 			int32_t *const hs_ptr = (int32_t *)(ring + st0_off + REC_H) + (st0 & 7);
 			const int Hs = *hs_ptr; // H[st0] of this row
 			if (active) {

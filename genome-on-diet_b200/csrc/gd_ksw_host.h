@@ -77,11 +77,17 @@ struct KswGeom {
 };
 // Lanes per pair: one 8-column chunk per lane and step.  Short rows keep 8 pairs per warp; pairs whose
 // sequences would not fit next to the ring (staged only for G <= 8) use wide groups.
-static inline int ksw_pick_group(int max_qlen, int max_tlen, int max_w)
+static inline int ksw_pick_group(int max_qlen, int max_tlen, int max_w, bool exact = false, int npairs = 1 << 30, int sms = 148)
 {
 	const int nch = h_ncol16(max_qlen, max_tlen, max_w) / 8; // chunks in the widest row
 	int G = nch <= 24 ? 4 : nch <= 64 ? 8 : nch <= 160 ? 16 : 32;
 	if (G <= 8 && max_qlen + max_tlen > 2048) G = 16;
+	// Long pairs: the backtrack arena limits how many pairs one launch can hold (31 MB per 15 kbp HiFi pair, 141 MB
+	// per 50 kbp ONT pair), so narrow gangs leave the SMs short of warps -- widen the gang, up to a block of two
+	// warps per pair, until the launch has ~24 warps per SM.  (Measured: HiFi 2048 pairs 497 -> 600 GCUPS, ONT 512
+	// pairs 324 -> 434 GCUPS; four warps per pair and exact mode do not gain.)
+	if (!exact)
+		while (G >= 16 && G < 64 && (int64_t)npairs * G / 32 < (int64_t)sms * 24) G <<= 1;
 	return G;
 }
 static inline KswGeom ksw_geometry(int max_qlen, int max_tlen, int max_w, bool exact, bool with_p, int G)

@@ -11,14 +11,17 @@ using namespace gd;
 template <int G, bool RIGHT, int MODE, bool WITH_P>
 static void run_dp(const KswConsts &C, const KswBatch &B, int threads)
 {
-	int groups = threads / G;
-	emu::launch(1, threads, GD_KSW_LUT_BYTES + (size_t)groups * B.group_smem, [&]() {
+	if (G > 32) threads = G; // block-per-pair: one block of G threads, two blocks so that the ticket is shared
+	int groups = G > 32 ? 1 : threads / G;
+	emu::launch(G > 32 ? 2 : 1, threads, GD_KSW_LUT_BYTES + (size_t)groups * B.group_smem, [&]() {
 		int tid = emu::thread_idx();
 		uint8_t *sm = (uint8_t *)emu::smem();
 		ksw_build_lut(sm, tid, threads);
 		emu::sync_block();
-		ksw_warp_body<G, RIGHT, MODE, WITH_P>(C, B, sm + GD_KSW_LUT_BYTES + (size_t)(tid >> 5) * (32 / G) * B.group_smem, sm,
-		                                      tid & 31);
+		if (G <= 32)
+			ksw_warp_body<G, RIGHT, MODE, WITH_P>(C, B, sm + GD_KSW_LUT_BYTES + (size_t)(tid >> 5) * (32 / (G <= 32 ? G : 32)) * B.group_smem,
+			                                      sm, tid & 31);
+		else ksw_warp_body<G, RIGHT, MODE, WITH_P>(C, B, sm + GD_KSW_LUT_BYTES, sm, tid);
 	});
 }
 
@@ -72,6 +75,8 @@ extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, co
 	case 8: dispatch<8>(C, B, threads, right, exact, with_p); break;
 	case 16: dispatch<16>(C, B, threads, right, exact, with_p); break;
 	case 32: dispatch<32>(C, B, threads, right, exact, with_p); break;
+	case 64: dispatch<64>(C, B, threads, right, exact, with_p); break;
+	case 128: dispatch<128>(C, B, threads, right, exact, with_p); break;
 	default: return -1;
 	}
 	if (with_p)

@@ -84,6 +84,16 @@ def test_emu_ksw_literal_row_max(emu, oracle):
         _check(emu, oracle, Q, w, "sr", 0x00, 4, force_literal_max=True)
 
 
+@pytest.mark.parametrize("G", [64, 128])
+def test_emu_ksw_block_per_pair(emu, oracle, G):
+    """G > 32: one pair per thread block (the widest bands); block-level barriers and reductions replace the warp ones"""
+    P = synth.ragged_pairs(6, seed=41 + G, max_len=900)
+    rng = np.random.default_rng(G)
+    w = rng.choice([-1, 64, 300, 700], P["n"]).astype(np.int32)
+    for flag, scn in ((0x08, "map-ont"), (0x00, "map-hifi"), (0x18, "sr")):
+        _check(emu, oracle, P, w, scn, flag, G)
+
+
 def test_emu_ksw_microbench_shape(emu, oracle):
     P = synth.ksw_pairs(6, 150, 200, 0.05, seed=3, n_every=2)
     w = np.full(P["n"], 150, np.int32)

@@ -15,6 +15,9 @@ def cells(qlen, tlen, w):
     en0 = np.minimum(np.minimum(tlen - 1, r), (r + w) >> 1)
     return int(np.maximum(en0 - st0 + 1, 0).sum())
 
+GROUP = int(os.environ.get("GD_GROUP", "0"))
+
+
 def main():
     ctx = gd.Context(0)
     dev = torch.device("cuda", 0)
@@ -35,6 +38,7 @@ def main():
         d_ez = torch.zeros(n * 16, dtype=torch.int32, device=dev)
         d_cig = torch.zeros(n * 4096, dtype=torch.int32, device=dev)
         ctx.set_option("time_kernels", 1)
+        ctx.set_option("ksw_group", GROUP)
         tot = sum(cells(int(a), int(b), w) for a, b in zip(ql, tl))
         for it in range(3):
             ctx.stat("ksw_dp_reset")

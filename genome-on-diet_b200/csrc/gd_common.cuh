@@ -64,6 +64,7 @@ GD_DEV int atomic_add(int *p, int v) { return atomicAdd(p, v); }
 GD_DEV unsigned long long atomic_add64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 GD_DEV int popc(uint32_t x) { return __popc(x); }
 GD_DEV int clz32(uint32_t x) { return __clz((int)x); }
+GD_DEV int ffs32(uint32_t x) { return __ffs((int)x); } // 1-based position of the lowest set bit, 0 if none
 GD_DEV uint64_t brev64(uint64_t x) { return __brevll(x); }
 GD_DEV void fence() { __threadfence(); }
 template <class T> GD_DEV T ld_volatile(const T *p) { return *(const volatile T *)p; }
@@ -138,6 +139,7 @@ GD_DEV unsigned long long atomic_add64(unsigned long long *p, unsigned long long
 }
 GD_DEV int popc(uint32_t x) { return __builtin_popcount(x); }
 GD_DEV int clz32(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+GD_DEV int ffs32(uint32_t x) { return __builtin_ffs((int)x); }
 GD_DEV uint64_t brev64(uint64_t x)
 {
 	uint64_t r = 0;

@@ -341,28 +341,40 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 			total += c;
 		}
 		const int local = wbase + inc - cnt;
-		// ---- decoupled look-back over tiles ----
-		if (tid == 0) {
+		// ---- decoupled look-back over tiles, 32 predecessors per probe (warp 0) ----
+		if (wid == 0) {
 			long long excl = 0;
 			if (tile == 0) {
-				st_volatile(&B.status[0], (2ull << 62) | (unsigned long long)total);
+				if (lane == 0) st_volatile(&B.status[0], (2ull << 62) | (unsigned long long)total);
 			} else {
-				st_volatile(&B.status[tile], (1ull << 62) | (unsigned long long)total);
-				fence();
+				if (lane == 0) {
+					st_volatile(&B.status[tile], (1ull << 62) | (unsigned long long)total);
+					fence();
+				}
 				long long pt = tile - 1;
 				for (;;) {
-					unsigned long long sv = ld_volatile(&B.status[pt]);
-					unsigned long long state = sv >> 62;
-					if (state == 0) continue;
-					excl += (long long)(sv & 0x3fffffffffffffffull);
-					if (state == 2) break;
-					--pt;
+					const long long idx = pt - lane;
+					unsigned long long sv = 2ull << 62; // "before the first tile": an inclusive prefix of 0
+					if (idx >= 0) do sv = ld_volatile(&B.status[idx]);
+						while ((sv >> 62) == 0);
+					const uint32_t incl = ballot(0xffffffffu, (sv >> 62) == 2); // lanes that hold an inclusive prefix
+					const int first = incl ? ffs32(incl) - 1 : 32;                // the nearest one ends the walk
+					unsigned long long c = lane <= first ? (sv & 0x3fffffffffffffffull) : 0ull;
+					for (int d = 16; d >= 1; d >>= 1) {
+						const uint32_t lo = shfl_xor(0xffffffffu, (uint32_t)c, d, 32), hi = shfl_xor(0xffffffffu, (uint32_t)(c >> 32), d, 32);
+						c += (unsigned long long)hi << 32 | lo;
+					}
+					excl += (long long)c;
+					if (incl) break;
+					pt -= 32;
 				}
-				st_volatile(&B.status[tile], (2ull << 62) | (unsigned long long)(excl + total));
+				if (lane == 0) st_volatile(&B.status[tile], (2ull << 62) | (unsigned long long)(excl + total));
 			}
-			sm->excl = excl;
-			if (chunk == 0) B.out_off[job] = excl;
-			if (tile == B.ntiles - 1) B.out_off[B.njobs] = excl + total;
+			if (lane == 0) {
+				sm->excl = excl;
+				if (chunk == 0) B.out_off[job] = excl;
+				if (tile == B.ntiles - 1) B.out_off[B.njobs] = excl + total;
+			}
 		}
 		sync_block();
 		const long long obase = sm->excl + local;

@@ -61,6 +61,36 @@ class gd_ksw_params_t(C.Structure):
                 ("e2", C.c_int32), ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("flag", C.c_int32)]
 
 
+class gd_sr_opt_t(C.Structure):
+    """include/gdiet_cuda.h: the mm_mapopt_t fields the short-read path reads (GDiet-ShortReads/minimap.h:142-205)."""
+    _fields_ = [("W", C.c_int32), ("Z", C.c_char * 64), ("max_seeds", C.c_float), ("frag_mode", C.c_int32),
+                ("max_frag_len", C.c_int32), ("bw", C.c_uint32), ("min_cnt", C.c_float), ("rec_threshold_frac", C.c_float),
+                ("af_max_loc", C.c_int32), ("mid_occ", C.c_int32), ("max_max_occ", C.c_int32), ("occ_dist", C.c_int32),
+                ("q_occ_frac", C.c_float), ("for_only", C.c_int32), ("rev_only", C.c_int32),
+                ("a", C.c_int32), ("b", C.c_int32), ("q", C.c_int32), ("e", C.c_int32), ("q2", C.c_int32), ("e2", C.c_int32),
+                ("zdrop", C.c_int32), ("end_bonus", C.c_int32)]
+
+
+SR_CAND_FIELDS = ["rid", "rs", "re", "qs", "qe", "rev", "votes", "first_q", "last_q", "exact", "score", "n_cigar", "cigar_off"]
+SR_CAND_DTYPE = np.dtype([(f, np.int32) for f in SR_CAND_FIELDS] + [("reserved", np.int32, 3)])
+
+
+def sr_options(Z="10", qlen=150, bw_frac=0.05, bw_min=150, bw_max=200, min_cnt=2.0, rec_frac=0.0, af_max_loc=20, **kw):
+    """What `-ax sr -Z .. -W .. -r bw_frac,bw_min,bw_max -n min_cnt,rec_frac` leaves in mm_mapopt_t
+    (GDiet-ShortReads/options.c:130-150, main.c:166-182), with the band clamped as at map.c:624-631."""
+    bw = int(np.float32(qlen * np.float32(bw_frac)))
+    if bw_min > bw:
+        bw = bw_min
+    elif bw_max < bw:
+        bw = bw_max
+    o = gd_sr_opt_t(W=len(Z), Z=Z.encode(), max_seeds=0.1, frag_mode=1, max_frag_len=800, bw=bw, min_cnt=min_cnt,
+                    rec_threshold_frac=rec_frac, af_max_loc=af_max_loc, mid_occ=1000, max_max_occ=4095, occ_dist=500,
+                    q_occ_frac=0.01, for_only=0, rev_only=0, a=2, b=8, q=12, e=2, q2=24, e2=1, zdrop=100, end_bonus=10)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
 def build(verbose=False):
     """Compile libgdiet_cuda.so for sm_100a (nvcc cross-compiles without a GPU)."""
     out = subprocess.run(["make", "-C", CSRC_DIR, "-j4"], capture_output=True, text=True)
@@ -77,7 +107,8 @@ _lib = None
 EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat", "gd_stream", "ksw_extd2_sse",
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
-           "gd_sketch_reads_batch"]
+           "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
+           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch"]
 
 
 def load():
@@ -127,6 +158,20 @@ def load():
     L.gd_sketch_reads_batch.restype = i32
     L.gd_sketch_reads_batch.argtypes = [vp, i32, vp, vp, vp, i32, i32, C.c_char_p, i32, C.c_float, C.c_uint32, vp, vp, vp,
                                         i64, vp, vp, vp, i64]
+    L.gd_index_build.restype = i32
+    L.gd_index_build.argtypes = [vp, i32, vp, vp, vp, i32, i32, C.c_char_p, i32, C.POINTER(vp)]
+    L.gd_index_destroy.restype = None
+    L.gd_index_destroy.argtypes = [vp]
+    L.gd_index_stat.restype = i64
+    L.gd_index_stat.argtypes = [vp, C.c_char_p]
+    L.gd_index_get_batch.restype = i32
+    L.gd_index_get_batch.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.gd_index_export.restype = i32
+    L.gd_index_export.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.gd_index_cal_max_occ.restype = i32
+    L.gd_index_cal_max_occ.argtypes = [vp, vp, C.c_float, C.POINTER(C.c_int32)]
+    L.gd_sr_map_batch.restype = i32
+    L.gd_sr_map_batch.argtypes = [vp, vp, i32, vp, vp, vp, C.POINTER(gd_sr_opt_t), vp, vp, i64, vp, i64, C.POINTER(i64)]
     _lib = L
     return L
 
@@ -291,6 +336,84 @@ class Context:
             self._check(rc, "gd_sketch_reads_batch")
             return dict(s2_counts=s2_counts, s2_off=s2_off, s2=s2[: int(s2_off[n])], s3_off=s3_off, s3_ret=s3_ret,
                         s3=s3[: int(s3_off[n * W])])
+
+
+    # ---- index + short-read mapping ----
+    def index_build(self, contigs, w, k, Z):
+        """gd_index_build over a list of ASCII contigs (uint8 arrays / bytes). Returns an Index."""
+        bufs = [np.frombuffer(c, np.uint8) if isinstance(c, (bytes, bytearray)) else np.ascontiguousarray(c, np.uint8) for c in contigs]
+        lens = np.array([len(b) for b in bufs], np.int32)
+        off = np.zeros(len(bufs), np.int64)
+        off[1:] = np.cumsum(lens[:-1].astype(np.int64))
+        buf = np.concatenate(bufs) if len(bufs) > 1 else bufs[0]
+        Zb = Z.encode() if isinstance(Z, str) else Z
+        h = C.c_void_p()
+        self._check(self.lib.gd_index_build(self.h, len(bufs), _ptr(off), _ptr(lens), _ptr(buf), w, k, Zb, len(Zb), C.byref(h)),
+                    "gd_index_build")
+        return Index(self, h)
+
+    def sr_map_batch(self, index, off, lens, buf, opt, cand_cap=None, cigar_cap=None):
+        """gd_sr_map_batch. Returns (cand_off[n+1], candidates (SR_CAND_DTYPE), cigar pool)."""
+        n = len(lens)
+        cand_off = np.zeros(n + 1, np.int64)
+        cand_cap = cand_cap or 2 * n + 64
+        cigar_cap = cigar_cap or 16 * n + 1024
+        ncig = C.c_int64(0)
+        while True:
+            cand = np.zeros(cand_cap, SR_CAND_DTYPE)
+            cig = np.zeros(cigar_cap, np.uint32)
+            rc = self.lib.gd_sr_map_batch(self.h, index.h, n, _ptr(off), _ptr(lens), _ptr(buf), C.byref(opt), _ptr(cand_off),
+                                          _ptr(cand), cand_cap, _ptr(cig), cigar_cap, C.byref(ncig))
+            if rc == GD_ERR_CAPACITY:
+                cand_cap = max(cand_cap, int(cand_off[n]) + 16)
+                cigar_cap = max(cigar_cap, int(ncig.value) + 16)
+                continue
+            self._check(rc, "gd_sr_map_batch")
+            return cand_off, cand[: int(cand_off[n])], cig[: int(ncig.value)]
+
+
+class Index:
+    """gd_index: the device-resident minimizer index (mm_idx_t of GDiet-ShortReads/minimap.h:86-96)."""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def stat(self, key):
+        return int(self.ctx.lib.gd_index_stat(self.h, key.encode()))
+
+    def get(self, minier):
+        """mm_idx_get for an array of minimizer values (x >> 8): (count, first position offset or -1)."""
+        m = np.ascontiguousarray(minier, np.uint64)
+        cnt = np.zeros(len(m), np.uint32)
+        first = np.zeros(len(m), np.int64)
+        self.ctx._check(self.ctx.lib.gd_index_get_batch(self.ctx.h, self.h, len(m), _ptr(m), _ptr(cnt), _ptr(first)),
+                        "gd_index_get_batch")
+        return cnt, first
+
+    def export(self):
+        keys = np.zeros(self.stat("n_keys"), np.uint64)
+        counts = np.zeros(self.stat("n_keys"), np.uint32)
+        pos = np.zeros(self.stat("n_minimizers"), np.uint64)
+        S = np.zeros(self.stat("s_words"), np.uint32)
+        self.ctx._check(self.ctx.lib.gd_index_export(self.ctx.h, self.h, _ptr(keys), _ptr(counts), _ptr(pos), _ptr(S)),
+                        "gd_index_export")
+        return keys, counts, pos, S
+
+    def cal_max_occ(self, frac):
+        v = C.c_int32(0)
+        self.ctx._check(self.ctx.lib.gd_index_cal_max_occ(self.ctx.h, self.h, float(frac), C.byref(v)), "gd_index_cal_max_occ")
+        return int(v.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gd_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------------------------

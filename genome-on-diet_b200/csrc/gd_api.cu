@@ -82,10 +82,13 @@ extern "C" void gd_destroy(gd_ctx *ctx)
 	GdBuf *bufs[] = {&ctx->tpk, &ctx->qpk, &ctx->parena, &ctx->ticket, &ctx->cig_tmp, &ctx->cig_off, &ctx->cig_compact,
 	                 &ctx->res, &ctx->d_qlen, &ctx->d_tlen, &ctx->d_w, &ctx->d_qoff, &ctx->d_toff, &ctx->d_qbuf,
 	                 &ctx->d_tbuf, &ctx->sk_seq, &ctx->sk_off, &ctx->sk_len, &ctx->sk_rid, &ctx->sk_out,
-	                 &ctx->sk_out_off, &ctx->sk_state, &ctx->sk_misc, &ctx->sk_jobs, &ctx->sk_out2};
+	                 &ctx->sk_out_off, &ctx->sk_state, &ctx->sk_misc, &ctx->sk_jobs, &ctx->sk_out2,
+	                 &ctx->mp_seq, &ctx->mp_off, &ctx->mp_len, &ctx->mp_seed_n, &ctx->mp_seed_first, &ctx->mp_state, &ctx->mp_hoff,
+	                 &ctx->mp_ht, &ctx->mp_hq, &ctx->mp_cand_tmp, &ctx->mp_ncand, &ctx->mp_coff, &ctx->mp_cand, &ctx->mp_qbuf,
+	                 &ctx->mp_tbuf, &ctx->mp_pair, &ctx->mp_ez, &ctx->mp_cig, &ctx->mp_cnt, &ctx->mp_cpool, &ctx->mp_tmp};
 	for (GdBuf *b : bufs)
 		if (b->p) cudaFree(b->p);
-	GdPinned *pins[] = {&ctx->h_stage, &ctx->h_res, &ctx->h_cig, &ctx->h_misc, &ctx->h_sk_stage, &ctx->h_sk_out, &ctx->h_sk_misc};
+	GdPinned *pins[] = {&ctx->h_stage, &ctx->h_res, &ctx->h_cig, &ctx->h_misc, &ctx->h_sk_stage, &ctx->h_sk_out, &ctx->h_sk_misc, &ctx->h_mp};
 	for (GdPinned *b : pins)
 		if (b->p) cudaFreeHost(b->p);
 	for (int i = 0; i < 4; ++i)

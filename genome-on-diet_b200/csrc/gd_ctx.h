@@ -50,6 +50,10 @@ struct gd_ctx {
 	// sketch scratch
 	GdBuf sk_seq, sk_off, sk_len, sk_rid, sk_out, sk_out_off, sk_state, sk_misc, sk_jobs, sk_out2;
 	GdPinned h_sk_stage, h_sk_out, h_sk_misc;
+	// short-read mapping scratch (gd_map.cu)
+	GdBuf mp_seq, mp_off, mp_len, mp_seed_n, mp_seed_first, mp_state, mp_hoff, mp_ht, mp_hq, mp_cand_tmp, mp_ncand, mp_coff, mp_cand,
+	    mp_qbuf, mp_tbuf, mp_pair, mp_ez, mp_cig, mp_cnt, mp_cpool, mp_tmp;
+	GdPinned h_mp;
 };
 
 #define GD_CUDA_OK(ctx, call)                                                                          \
@@ -119,6 +123,19 @@ static inline int gd_reserve_pinned(gd_ctx *ctx, GdPinned &b, size_t bytes)
 	b.cap = want;
 	return GD_OK;
 }
+
+// implemented in gd_sketch.cu: device-resident read sketching for the mapper
+struct GdReadSketch {
+	const int64_t *job_off; // [n*JW+1]
+	const uint64_t *raw;    // x,y pairs of every job
+	const int64_t *c3, *c2; // [n*W] capped list lengths of mm_sketch3 / mm_sketch2
+	const uint32_t *ret3;   // [n*W] return value of mm_sketch3
+	int JW, crop;
+	int64_t raw_cap;
+};
+int gd_sketch_reads_device_raw(gd_ctx *ctx, int n, const int64_t *d_off, const int32_t *d_len, const char *d_buf,
+                               int64_t max_len, int64_t sum_len, int w, int k, const char *Z, int W, float max_seeds,
+                               uint32_t max_nb_seeds, GdReadSketch *out);
 
 // implemented in gd_ksw.cu
 int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *d_qoff, const uint8_t *d_qbuf,

@@ -1,0 +1,719 @@
+// gd_map.cu -- short-read mapping between the two hot kernels, on the device (SURVEY.md 8 F1 + F2):
+// what GDiet-ShortReads/map.c:mm_map_frag does from mm_sketch2 up to the ksw_extz_t of every candidate.
+//
+//   reads (ASCII, HBM) --sketch kernel--> per (read, shift) minimizer lists
+//   K1 gd_sr_seed_kernel   warp per read: mm_get_shift (seed.c:166-194), mm_seed_mz_flt (seed.c:5-29),
+//                          index lookups + mm_seed_select (seed.c:36-113,143-164) -> seed table, hit count
+//   scan of the hit counts -> one flat hit array for the batch
+//   K2 gd_sr_vote_kernel   warp per read: collect_seed_hits (map.c:261-356; the k-way merge is a sort by
+//                          target, done as a bitonic network over the warp), vote x2 (map.c:447-584, the
+//                          sequential cluster scan runs on lane 0 over 32-hit chunks staged in shared memory),
+//                          window arithmetic (map.c:764-839) -> candidates
+//   K3 gd_sr_window_kernel warp per candidate: query codes (map.c:737-757), target codes from the 4-bit
+//                          reference (index.c:157-166), exact_match_sse (map.c:873-915)
+//   DP kernel on the candidates that are not exact (gd_ksw_run_device), flag KSW_EZ_APPROX_MAX
+//   K4 scores + CIGARs into the dense, input-ordered output
+//
+// Only three words per batch cross back to the host before the results do (the totals that size the next
+// stage's arrays).
+#include "gd_ctx.h"
+#include "gd_index.cuh"
+#include "gd_sketch.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <string.h>
+#include <vector>
+
+using namespace gd;
+
+#define SR_FLT 0x80000000u // seed filtered (mm_seed_mz_flt / mm_seed_select / max_occ)
+#define SR_WARPS 4         // warps per block of the per-read kernels
+#define SR_MAX_LOC 32
+
+struct SrParams {
+	int32_t W, JW, crop, k, frag_mode;
+	uint32_t max_nb_seeds, bw;
+	float min_cnt, rec_frac, q_occ_frac;
+	int32_t af_max_loc, mid_occ, max_max_occ, occ_dist, for_only, rev_only, a;
+	int32_t stride; // bytes per candidate in the query / target code buffers
+};
+
+struct SrRead { // per-read state between K1 and K2
+	uint32_t shift, n0, n_mv, ext;
+};
+
+struct SrVt { // vt_t, map.c:433-440
+	uint32_t chrom_id;
+	int32_t target_loc;
+	uint32_t fq, lq, str, score;
+};
+
+// --------------------------------------------------------------------------------------------
+// K1: shift, seed filters, lookups
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+{
+	for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+	return v;
+}
+
+// mm_seed_select (seed.c:67-113) over the present seeds of one read, in raw-list index space; lane 0 only.
+__device__ void sr_seed_select(const uint64_t *mv, uint32_t *sn, int n0, int qlen, int max_occ, int max_max_occ, int dist)
+{
+	int present = 0, m = 0;
+	for (int e = 0; e < n0; ++e) {
+		const uint32_t v = sn[e];
+		if (v == 0 || (v & SR_FLT)) continue;
+		++present;
+		if ((int)v > max_occ) ++m;
+	}
+	if (present <= 1 || m == 0) return;
+	unsigned long long b[128];
+	int last0 = -1, st = -1, cnt = 0; // last low-occurrence seed, first seed of the streak, streak length
+	for (int e = 0; e <= n0; ++e) {
+		if (e < n0) {
+			const uint32_t v = sn[e];
+			if (v == 0 || (v & SR_FLT)) continue;
+			if ((int)v > max_occ) {
+				if (cnt++ == 0) st = e;
+				continue;
+			}
+		}
+		if (cnt > 0) {
+			const int ps = last0 < 0 ? 0 : (int)((uint32_t)mv[2 * last0 + 1] >> 1);
+			const int pe = e == n0 ? qlen : (int)((uint32_t)mv[2 * e + 1] >> 1);
+			int max_high_occ = (int)((double)(pe - ps) / dist + .499);
+			if (max_high_occ > 0) {
+				if (max_high_occ > 128) max_high_occ = 128;
+				int k = 0, j = st;
+				for (; j < e && k < max_high_occ; ++j) {
+					const uint32_t v = sn[j];
+					if (v == 0 || (v & SR_FLT)) continue;
+					b[k++] = (unsigned long long)v << 32 | (uint32_t)j;
+				}
+				for (; j < e; ++j) { // the heap top of seed.c:94-99 is the maximum of b[]
+					const uint32_t v = sn[j];
+					if (v == 0 || (v & SR_FLT)) continue;
+					int top = 0;
+					for (int t = 1; t < k; ++t)
+						if (b[t] > b[top]) top = t;
+					if ((int)v < (int)(b[top] >> 32)) b[top] = (unsigned long long)v << 32 | (uint32_t)j;
+				}
+				for (int t = 0; t < k; ++t) sn[(uint32_t)b[t]] |= 0x40000000u; // chosen (flt = 1 before the xor)
+			}
+			for (int j = st; j < e; ++j) { // flt ^= 1, then the max_max_occ rule
+				uint32_t v = sn[j];
+				if (v == 0 || (v & SR_FLT)) continue;
+				const bool chosen = (v & 0x40000000u) != 0;
+				v &= 0x3fffffffu;
+				if (!chosen || (int)v > max_max_occ) v |= SR_FLT;
+				sn[j] = v;
+			}
+		}
+		last0 = e, cnt = 0;
+	}
+}
+
+__global__ void __launch_bounds__(SR_WARPS * 32) gd_sr_seed_kernel(IndexDev I, SrParams P, int n, const int32_t *len,
+                                                                  const int64_t *job_off, const uint64_t *raw, const int64_t *c3,
+                                                                  const int64_t *c2, const uint32_t *ret3, uint32_t *seed_n,
+                                                                  uint32_t *seed_first, SrRead *rd, uint32_t *n_hits)
+{
+	const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+		const int64_t *jo = job_off + (size_t)i * P.JW;
+		// ---- mm_get_shift: the shift whose mm_sketch2 list has the most index hits (first strict maximum)
+		uint32_t best = 0, shift = 0;
+		for (int s = 0; s < P.W; ++s) {
+			const int64_t base = (P.crop && s == 0) ? jo[P.W] : jo[s];
+			const int64_t cnt = c2[(size_t)i * P.W + s];
+			uint32_t sum = 0, f;
+			for (int64_t e = lane; e < cnt; e += 32) sum += idx_get(I, raw[2 * (base + e)] >> 8, f);
+			sum = warp_sum(sum);
+			if (sum > best) best = sum, shift = (uint32_t)s;
+		}
+		// ---- the seeds: mm_sketch3(shift)
+		const int64_t base = jo[shift];
+		const int n0 = (int)c3[(size_t)i * P.W + shift];
+		const uint64_t *mv = raw + 2 * base;
+		uint32_t *sn = seed_n + base, *sf = seed_first + base;
+		uint32_t removed = 0;
+		for (int e = lane; e < n0; e += 32) sn[e] = 0;
+		__syncwarp();
+		if (P.q_occ_frac > 0.f && P.mid_occ > 0 && n0 > P.mid_occ) { // mm_seed_mz_flt (rare: reads with > mid_occ seeds)
+			for (int e0 = 0; e0 < n0; ++e0) {
+				const uint64_t x = mv[2 * e0];
+				uint32_t c = 0;
+				for (int e = lane; e < n0; e += 32) c += mv[2 * e] == x;
+				c = warp_sum(c);
+				if ((int)c > P.mid_occ && (float)(int)c > (float)n0 * P.q_occ_frac) {
+					if (lane == 0) sn[e0] = SR_FLT;
+					++removed;
+				}
+			}
+			__syncwarp();
+		}
+		int high = 0;
+		for (int e = lane; e < n0; e += 32) {
+			if (sn[e] & SR_FLT) continue;
+			uint32_t f;
+			const uint32_t c = idx_get(I, mv[2 * e] >> 8, f);
+			sn[e] = c, sf[e] = f;
+			high |= (int)c > P.mid_occ;
+		}
+		high = __any_sync(0xffffffffu, high);
+		__syncwarp();
+		if (high) { // mm_collect_matches2, seed.c:149-155
+			if (P.occ_dist > 0 && P.max_max_occ > P.mid_occ) {
+				if (lane == 0) sr_seed_select(mv, sn, n0, len[i], P.mid_occ, P.max_max_occ, P.occ_dist);
+			} else {
+				for (int e = lane; e < n0; e += 32)
+					if (!(sn[e] & SR_FLT) && (int)sn[e] > P.mid_occ) sn[e] |= SR_FLT;
+			}
+			__syncwarp();
+		}
+		uint32_t na = 0;
+		for (int e = lane; e < n0; e += 32)
+			if (!(sn[e] & SR_FLT)) na += sn[e];
+		na = warp_sum(na);
+		if (lane == 0) {
+			SrRead r;
+			r.shift = shift, r.n0 = (uint32_t)n0, r.n_mv = (uint32_t)n0 - removed, r.ext = ret3[(size_t)i * P.W + shift];
+			rd[i] = r;
+			n_hits[i] = na;
+		}
+	}
+}
+
+// --------------------------------------------------------------------------------------------
+// K2: hits, sort, vote, windows
+// --------------------------------------------------------------------------------------------
+// ascending sort of (target, query) by target with one warp; ties in target may end in any order (the vote
+// does not depend on it: tied hits join the same cluster and only min / max of their query positions are kept)
+__device__ void sr_sort_hits(uint64_t *t, uint32_t *q, int n, int lane)
+{
+	if (n <= 1) return;
+	if (n <= 32) {
+		uint64_t key = lane < n ? t[lane] : ~0ull;
+		uint32_t val = lane < n ? q[lane] : 0;
+		for (int k = 2; k <= 32; k <<= 1)
+			for (int j = k >> 1; j > 0; j >>= 1) {
+				const uint64_t ok = __shfl_xor_sync(0xffffffffu, key, j);
+				const uint32_t ov = __shfl_xor_sync(0xffffffffu, val, j);
+				const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+				if (take_min ? ok < key : ok > key) key = ok, val = ov;
+			}
+		if (lane < n) t[lane] = key, q[lane] = val;
+		__syncwarp();
+		return;
+	}
+	int P2 = 64;
+	while (P2 < n) P2 <<= 1;
+	// all comparators ascending (flip network): virtual elements >= n are +inf and never move
+	for (int k = 2; k <= P2; k <<= 1) {
+		for (int p = lane; p < P2 / 2; p += 32) {
+			const int blk = p / (k >> 1), o = p % (k >> 1);
+			const int l = blk * k + o, h = blk * k + k - 1 - o;
+			if (h < n) {
+				const uint64_t a = t[l], b = t[h];
+				if (b < a) {
+					const uint32_t qa = q[l], qb = q[h];
+					t[l] = b, t[h] = a, q[l] = qb, q[h] = qa;
+				}
+			}
+		}
+		__syncwarp();
+		for (int j = k >> 2; j > 0; j >>= 1) {
+			for (int p = lane; p < P2 / 2; p += 32) {
+				const int l = (p / j) * 2 * j + (p % j), h = l + j;
+				if (h < n) {
+					const uint64_t a = t[l], b = t[h];
+					if (b < a) {
+						const uint32_t qa = q[l], qb = q[h];
+						t[l] = b, t[h] = a, q[l] = qb, q[h] = qa;
+					}
+				}
+			}
+			__syncwarp();
+		}
+	}
+}
+
+struct SrVoteState {
+	unsigned out_len;
+	SrVt recovery;
+};
+
+// the common tail of both branches of vote() (map.c:475-520 and :527-565); lane 0 only
+__device__ __forceinline__ void sr_vt_emit(SrVt *pot, SrVoteState &S, uint64_t target_loc, uint32_t fq, uint32_t lq,
+                                           unsigned counter, int str, int32_t tmp_ext, unsigned thr, unsigned max_loc,
+                                           unsigned rec_thr)
+{
+	SrVt v;
+	v.chrom_id = (uint32_t)(target_loc >> 32);
+	v.target_loc = (int32_t)(uint32_t)target_loc + (str ? 0 : -tmp_ext);
+	v.fq = fq, v.lq = lq, v.str = (uint32_t)str, v.score = counter;
+	if (counter > thr) {
+		if (S.out_len == max_loc) {
+			if (pot[S.out_len - 1].score >= counter) return;
+		} else ++S.out_len;
+		pot[S.out_len - 1] = v;
+		for (unsigned k = S.out_len - 1; k > 0; k--) {
+			if (pot[k].score > pot[k - 1].score) {
+				const SrVt t = pot[k];
+				pot[k] = pot[k - 1], pot[k - 1] = t;
+			} else break;
+		}
+	} else if (S.out_len == 0 && counter > rec_thr && counter > S.recovery.score) S.recovery = v;
+}
+
+__device__ void sr_vote(const uint64_t *ht, const uint32_t *hq, unsigned len, int str, SrVt *pot, SrVoteState &S, uint64_t *s_t,
+                        uint32_t *s_q, unsigned dist, int32_t tmp_ext, unsigned thr, unsigned max_loc, unsigned rec_thr, int lane)
+{
+	if (len == 0) return;
+	unsigned counter = 0;
+	uint64_t target_loc = 0;
+	uint32_t fq = 0, lq = 0;
+	for (unsigned c0 = 0; c0 < len; c0 += 32) {
+		if (c0 + lane < len) s_t[lane] = ht[c0 + lane], s_q[lane] = hq[c0 + lane];
+		__syncwarp();
+		if (lane == 0) {
+			const unsigned m = len - c0 < 32 ? len - c0 : 32;
+			for (unsigned j = 0; j < m; ++j) {
+				const uint64_t ct = s_t[j];
+				const uint32_t cq = s_q[j];
+				if (counter == 0) {
+					target_loc = ct, fq = lq = cq, counter = 1;
+				} else if (ct - target_loc <= dist) {
+					counter++;
+					if (cq < fq) target_loc = ct, fq = cq;
+					if (cq > lq) lq = cq;
+				} else {
+					sr_vt_emit(pot, S, target_loc, fq, lq, counter, str, tmp_ext, thr, max_loc, rec_thr);
+					target_loc = ct, fq = lq = cq, counter = 1;
+				}
+			}
+		}
+		__syncwarp();
+	}
+	if (lane == 0) sr_vt_emit(pot, S, target_loc, fq, lq, counter, str, tmp_ext, thr, max_loc, rec_thr);
+}
+
+__global__ void __launch_bounds__(SR_WARPS * 32) gd_sr_vote_kernel(IndexDev I, SrParams P, int n, const int32_t *len,
+                                                                  const int64_t *job_off, const uint64_t *raw,
+                                                                  const uint32_t *seed_n, const uint32_t *seed_first,
+                                                                  const SrRead *rd, const int64_t *hits_off, uint64_t *ht,
+                                                                  uint32_t *hq, gd_sr_cand_t *cand_tmp, uint32_t *n_cand)
+{
+	__shared__ uint64_t s_t[SR_WARPS][32];
+	__shared__ uint32_t s_q[SR_WARPS][32];
+	__shared__ SrVt s_pot[SR_WARPS][SR_MAX_LOC];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = (gridDim.x * blockDim.x) >> 5;
+	const uint32_t lt = (1u << lane) - 1;
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+		const SrRead R = rd[i];
+		const int64_t base = job_off[(size_t)i * P.JW + R.shift];
+		const uint64_t *mv = raw + 2 * base;
+		const uint32_t *sn = seed_n + base, *sf = seed_first + base;
+		const int64_t hoff = hits_off[i];
+		const uint32_t na = (uint32_t)(hits_off[i + 1] - hoff);
+		const int n0 = (int)R.n0;
+		uint64_t *t = ht + hoff;
+		uint32_t *q = hq + hoff;
+		uint32_t nf = 0, nr = 0;
+		// ---- collect_seed_hits, map.c:284-311: forward hits grow from the front, reverse hits from the back
+		auto put = [&](bool valid, uint64_t r, uint32_t qp) {
+			const uint32_t qpos = qp >> 1, loc = (uint32_t)r >> 1;
+			const uint32_t str = (uint32_t)(r & 1) ^ (qp & 1);
+			const bool keep = valid && !(str ? P.for_only : P.rev_only); // skip_seed, map.c:121-127
+			const uint32_t fm = __ballot_sync(0xffffffffu, keep && !str), rm = __ballot_sync(0xffffffffu, keep && str);
+			if (keep) {
+				if (str) {
+					const uint32_t slot = na - 1 - (nr + __popc(rm & lt));
+					t[slot] = (r >> 32) << 32 | (uint32_t)(loc + qpos), q[slot] = qpos;
+				} else {
+					const uint32_t slot = nf + __popc(fm & lt);
+					t[slot] = (r >> 32) << 32 | (uint32_t)(loc + R.ext - qpos), q[slot] = qpos;
+				}
+			}
+			nf += __popc(fm), nr += __popc(rm);
+		};
+		for (int e0 = 0; e0 < n0; e0 += 32) {
+			const int e = e0 + lane;
+			uint32_t c = e < n0 ? sn[e] : 0;
+			if (c & SR_FLT) c = 0;
+			const uint32_t qp = e < n0 ? (uint32_t)mv[2 * e + 1] : 0, first = e < n0 ? sf[e] : 0;
+			put(c == 1, c == 1 ? I.pos[first] : 0, qp);
+			uint32_t mm = __ballot_sync(0xffffffffu, c > 1);
+			while (mm) {
+				const int src = __ffs(mm) - 1;
+				mm &= mm - 1;
+				const uint32_t bc = __shfl_sync(0xffffffffu, c, src), bf = __shfl_sync(0xffffffffu, first, src);
+				const uint32_t bq = __shfl_sync(0xffffffffu, qp, src);
+				for (uint32_t j0 = 0; j0 < bc; j0 += 32) {
+					const uint32_t j = j0 + lane;
+					put(j < bc, j < bc ? I.pos[bf + j] : 0, bq);
+				}
+			}
+		}
+		__syncwarp();
+		uint64_t *tr = t + (na - nr);
+		uint32_t *qr = q + (na - nr);
+		sr_sort_hits(t, q, (int)nf, lane);
+		sr_sort_hits(tr, qr, (int)nr, lane);
+		// ---- voting, map.c:665-699
+		const uint32_t qlen_sum = (uint32_t)len[i];
+		const bool frag = P.frag_mode && R.ext < qlen_sum;
+		unsigned thr = frag ? (unsigned)((float)P.max_nb_seeds * P.min_cnt) : (unsigned)((float)R.n_mv * P.min_cnt);
+		const unsigned rec_thr = frag ? (unsigned)((float)P.max_nb_seeds * P.rec_frac) : (unsigned)((float)R.n_mv * P.rec_frac);
+		if (thr == 0) thr = 1;
+		SrVoteState S;
+		S.out_len = 0;
+		S.recovery.score = 0, S.recovery.chrom_id = 0, S.recovery.target_loc = 0, S.recovery.fq = S.recovery.lq = S.recovery.str = 0;
+		SrVt *pot = s_pot[wib];
+		sr_vote(t, q, nf, 0, pot, S, s_t[wib], s_q[wib], P.bw, (int32_t)R.ext, thr, (unsigned)P.af_max_loc, rec_thr, lane);
+		sr_vote(tr, qr, nr, 1, pot, S, s_t[wib], s_q[wib], P.bw, (int32_t)R.ext, thr, (unsigned)P.af_max_loc, rec_thr, lane);
+		if (lane == 0 && S.out_len == 0 && S.recovery.score != 0) pot[0] = S.recovery, S.out_len = 1; // map.c:692-699
+		const unsigned nb = __shfl_sync(0xffffffffu, S.out_len, 0);
+		__syncwarp();
+		// ---- candidate windows, map.c:764-839 (one lane per candidate)
+		gd_sr_cand_t c;
+		bool keep = false;
+		if (lane < (int)nb) {
+			const SrVt v = pot[lane];
+			const int str = (int)v.str, k = P.k;
+			const int32_t tlen = (int32_t)I.seq_len[v.chrom_id];
+			int32_t loc = v.target_loc;
+			if (str) loc -= (k - 1);
+			int32_t target_start = loc, target_end = loc;
+			uint32_t start_offset, end_offset;
+			keep = true;
+			if (qlen_sum > 300) {
+				if (v.fq == v.lq) keep = false;
+				start_offset = v.fq - (uint32_t)(k - 1);
+				end_offset = v.lq;
+				if (str) {
+					target_end -= (int32_t)start_offset, target_start -= (int32_t)end_offset;
+					if (target_start < 0) end_offset += (uint32_t)target_start, target_start = 0;
+				} else {
+					target_start += (int32_t)start_offset, target_end += (int32_t)end_offset;
+					if (target_end + 1 > tlen) end_offset = (uint32_t)(tlen - 1 - target_start) + start_offset, target_end = tlen - 1;
+				}
+			} else if (str) {
+				if (target_end > tlen - 1) start_offset = (uint32_t)(target_end - (tlen - 1)), target_end = tlen - 1;
+				else start_offset = 0;
+				if ((uint32_t)target_end < qlen_sum - start_offset - 1) end_offset = start_offset + (uint32_t)target_end, target_start = 0;
+				else end_offset = qlen_sum - 1, target_start = target_end - (int32_t)(end_offset - start_offset);
+			} else {
+				if (target_start < 0) start_offset = (uint32_t)(-target_start), target_start = 0;
+				else start_offset = 0;
+				if ((uint32_t)(tlen - target_start) < qlen_sum - start_offset)
+					end_offset = (uint32_t)(tlen - 1 - target_start) + start_offset, target_end = tlen - 1;
+				else end_offset = qlen_sum - 1, target_end = target_start + (int32_t)(end_offset - start_offset);
+			}
+			c.rid = (int32_t)v.chrom_id, c.rs = target_start, c.re = target_end + 1, c.qs = (int32_t)start_offset;
+			c.qe = (int32_t)end_offset + 1, c.rev = str, c.votes = (int32_t)v.score, c.first_q = (int32_t)v.fq, c.last_q = (int32_t)v.lq;
+			c.exact = 0, c.score = 0, c.n_cigar = 0, c.cigar_off = 0;
+			c.reserved[0] = i, c.reserved[1] = 0, c.reserved[2] = 0;
+		}
+		const uint32_t km = __ballot_sync(0xffffffffu, keep);
+		if (keep) cand_tmp[(size_t)i * P.af_max_loc + __popc(km & lt)] = c;
+		if (lane == 0) n_cand[i] = (uint32_t)__popc(km);
+		__syncwarp();
+	}
+}
+
+// candidates of all reads, dense and in input order
+__global__ void gd_sr_compact_kernel(int n, int af, const gd_sr_cand_t *cand_tmp, const int64_t *cand_off, gd_sr_cand_t *cand)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int64_t o = cand_off[i];
+	const int m = (int)(cand_off[i + 1] - o);
+	const uint4 *src = (const uint4 *)(cand_tmp + (size_t)i * af);
+	uint4 *dst = (uint4 *)(cand + o);
+	for (int j = 0; j < m * 4; ++j) dst[j] = src[j];
+}
+
+// --------------------------------------------------------------------------------------------
+// K3: query / target codes of every candidate + exact match; one warp per candidate
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gd_sr_window_kernel(IndexDev I, SrParams P, int64_t nc, const int64_t *off, const int32_t *len,
+                                                          const char *buf, gd_sr_cand_t *cand, uint8_t *qbuf, uint8_t *tbuf,
+                                                          uint32_t *need_dp)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	for (int64_t ci = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < nc; ci += warps) {
+		gd_sr_cand_t *c = cand + ci;
+		const int i = c->reserved[0], qs = c->qs, qe = c->qe, rev = c->rev, n = qe - qs;
+		const char *rdp = buf + off[i];
+		const uint64_t tb = I.seq_off[c->rid] + (uint64_t)c->rs;
+		const int tl = c->re - c->rs; // == n for every window the arithmetic above produces
+		uint8_t *qo = qbuf + ci * P.stride, *to = tbuf + ci * P.stride;
+		int diff = 0;
+		for (int j = lane; j < n; j += 32) {
+			// map.c:737-757: forward = nt4, reverse strand = reversed and ^3 (N becomes 7)
+			const int qc = rev ? (sk_nt4((unsigned char)rdp[qe - 1 - j]) ^ 3) : sk_nt4((unsigned char)rdp[qs + j]);
+			const int tc = j < tl ? (int)idx_base(I, tb + j) : 0;
+			qo[j] = (uint8_t)qc, to[j] = (uint8_t)tc;
+			diff |= qc != tc;
+		}
+		diff = __any_sync(0xffffffffu, diff);
+		if (lane == 0) {
+			const int exact = (len[i] < 300 && n > 0 && !diff) ? 1 : 0; // map.c:873
+			c->exact = exact;
+			need_dp[ci] = exact ? 0u : 1u;
+		}
+	}
+}
+
+// DP work list: the candidates that were not exact matches
+__global__ void gd_sr_pairs_kernel(int64_t nc, int stride, const gd_sr_cand_t *cand, const int64_t *pair_off, int32_t *plen,
+                                   int64_t *poff, int32_t *pcand)
+{
+	const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (ci >= nc) return;
+	if (pair_off[ci + 1] == pair_off[ci]) return;
+	const int64_t p = pair_off[ci];
+	plen[p] = cand[ci].qe - cand[ci].qs, poff[p] = ci * stride, pcand[p] = (int32_t)ci;
+}
+
+// K4a: scores and CIGAR lengths of every candidate
+__global__ void gd_sr_scores_kernel(int64_t nc, SrParams P, const int32_t *len, gd_sr_cand_t *cand, const int64_t *pair_off,
+                                    const gd_extz_t *ez, uint32_t *ncig)
+{
+	const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (ci >= nc) return;
+	gd_sr_cand_t *c = cand + ci;
+	if (c->exact) c->score = len[c->reserved[0]] * P.a, c->n_cigar = 1; // map.c:901-903
+	else {
+		const gd_extz_t e = ez[pair_off[ci]];
+		c->score = e.score, c->n_cigar = e.n_cigar;
+	}
+	ncig[ci] = c->n_cigar > 0 ? (uint32_t)c->n_cigar : 0u;
+}
+
+// K4b: CIGARs into the dense pool; one warp per candidate
+__global__ void __launch_bounds__(128) gd_sr_cigars_kernel(int64_t nc, gd_sr_cand_t *cand, const int64_t *pair_off, const int64_t *cig_off,
+                                                          const uint32_t *dp_cigar, int cigar_stride, uint32_t *pool, int64_t pool_cap)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	for (int64_t ci = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < nc; ci += warps) {
+		gd_sr_cand_t *c = cand + ci;
+		const int64_t o = cig_off[ci];
+		const int m = (int)(cig_off[ci + 1] - o);
+		if (lane == 0) c->cigar_off = (int32_t)o, c->reserved[0] = 0;
+		if (o + m > pool_cap) continue;
+		if (c->exact) {
+			if (lane == 0) pool[o] = (uint32_t)(c->qe - c->qs) << 4; // <len>M
+		} else {
+			const uint32_t *src = dp_cigar + pair_off[ci] * cigar_stride;
+			for (int j = lane; j < m; j += 32) pool[o + j] = src[j];
+		}
+	}
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+template <class T> static int scan_u32(gd_ctx *ctx, const uint32_t *d_in, T *d_out, int64_t n)
+{ // exclusive prefix sums with the total in d_out[n]; the input has n+1 readable entries (the last one is ignored)
+	size_t tmp = 0;
+	GD_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_in, d_out, n + 1, ctx->stream));
+	int rc = gd_reserve(ctx, ctx->mp_tmp, tmp + 16);
+	if (rc) return rc;
+	GD_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->mp_tmp.p, tmp, d_in, d_out, n + 1, ctx->stream));
+	ctx->stat_launches += 2;
+	return GD_OK;
+}
+
+static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
+                        const gd_sr_opt_t *o, int64_t cand_base, int64_t cig_base, int64_t *cand_off, gd_sr_cand_t *cand,
+                        int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cand_out, int64_t *n_cig_out)
+{
+	cudaStream_t s = ctx->stream;
+	int rc;
+	int64_t lo = INT64_MAX, hi = 0, sum_len = 0;
+	int max_len = 0;
+	for (int i = 0; i < n; ++i) {
+		if (len[i] < o->W || off[i] < 0) {
+			ctx->err = "gd_sr_map_batch: read shorter than the pattern";
+			return GD_ERR_ARG;
+		}
+		lo = std::min<int64_t>(lo, off[i]), hi = std::max<int64_t>(hi, off[i] + len[i]);
+		max_len = std::max(max_len, len[i]), sum_len += len[i];
+	}
+	SrParams P;
+	memset(&P, 0, sizeof(P));
+	P.W = o->W, P.k = idx->d.k, P.frag_mode = o->frag_mode;
+	P.max_nb_seeds = o->frag_mode ? (o->max_frag_len == 0 ? 800u : (uint32_t)o->max_frag_len) : 0xffffffffu; // map.c:621-622
+	P.bw = o->bw, P.min_cnt = o->min_cnt, P.rec_frac = o->rec_threshold_frac, P.q_occ_frac = o->q_occ_frac;
+	P.af_max_loc = o->af_max_loc, P.mid_occ = o->mid_occ, P.max_max_occ = o->max_max_occ, P.occ_dist = o->occ_dist;
+	P.for_only = o->for_only, P.rev_only = o->rev_only, P.a = o->a;
+	P.stride = (max_len + 15) / 16 * 16;
+	// ---- reads up
+	if ((rc = gd_reserve(ctx, ctx->mp_seq, (size_t)(hi - lo) + 16))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_off, (size_t)n * 8))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_len, (size_t)n * 4))) return rc;
+	if ((rc = gd_reserve_pinned(ctx, ctx->h_mp, (size_t)n * 8 + 64))) return rc;
+	int64_t *h_off = (int64_t *)ctx->h_mp.p;
+	for (int i = 0; i < n; ++i) h_off[i] = off[i] - lo;
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_seq.p, buf + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s));
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_off.p, h_off, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_len.p, len, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+	const int64_t *d_off = (const int64_t *)ctx->mp_off.p;
+	const int32_t *d_len = (const int32_t *)ctx->mp_len.p;
+	const char *d_buf = (const char *)ctx->mp_seq.p;
+	// ---- sketches of every shift (mm_sketch2 + mm_sketch3)
+	GdReadSketch K;
+	if ((rc = gd_sketch_reads_device_raw(ctx, n, d_off, d_len, d_buf, max_len, sum_len, idx->d.w, idx->d.k, o->Z, o->W, o->max_seeds,
+	                                     P.max_nb_seeds == 0xffffffffu ? 0u : P.max_nb_seeds, &K)))
+		return rc;
+	P.JW = K.JW, P.crop = K.crop;
+	// ---- K1
+	if ((rc = gd_reserve(ctx, ctx->mp_seed_n, (size_t)K.raw_cap * 4))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_seed_first, (size_t)K.raw_cap * 4))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_state, (size_t)n * sizeof(SrRead)))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_cnt, (size_t)(n + 1) * 4))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_hoff, (size_t)(n + 2) * 8))) return rc;
+	const int blocks = std::max(1, std::min((n + SR_WARPS - 1) / SR_WARPS, ctx->sms * 16));
+	gd_sr_seed_kernel<<<blocks, SR_WARPS * 32, 0, s>>>(idx->d, P, n, d_len, K.job_off, K.raw, K.c3, K.c2, K.ret3,
+	                                                 (uint32_t *)ctx->mp_seed_n.p, (uint32_t *)ctx->mp_seed_first.p,
+	                                                 (SrRead *)ctx->mp_state.p, (uint32_t *)ctx->mp_cnt.p);
+	ctx->stat_launches++;
+	GD_CUDA_OK(ctx, cudaGetLastError());
+	if ((rc = scan_u32(ctx, (const uint32_t *)ctx->mp_cnt.p, (int64_t *)ctx->mp_hoff.p, n))) return rc;
+	int64_t *h_word = (int64_t *)ctx->h_mp.p; // (h_off has been consumed by the copy above once the stream reaches here)
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, (int64_t *)ctx->mp_hoff.p + n, 8, cudaMemcpyDeviceToHost, s));
+	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
+	const int64_t n_hits = h_word[0];
+	// ---- K2
+	if ((rc = gd_reserve(ctx, ctx->mp_ht, (size_t)(n_hits + 1) * 8))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_hq, (size_t)(n_hits + 1) * 4))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_cand_tmp, (size_t)n * o->af_max_loc * sizeof(gd_sr_cand_t)))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_ncand, (size_t)(n + 1) * 4))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_coff, (size_t)(n + 2) * 8))) return rc;
+	gd_sr_vote_kernel<<<blocks, SR_WARPS * 32, 0, s>>>(idx->d, P, n, d_len, K.job_off, K.raw, (const uint32_t *)ctx->mp_seed_n.p,
+	                                                 (const uint32_t *)ctx->mp_seed_first.p, (const SrRead *)ctx->mp_state.p,
+	                                                 (const int64_t *)ctx->mp_hoff.p, (uint64_t *)ctx->mp_ht.p, (uint32_t *)ctx->mp_hq.p,
+	                                                 (gd_sr_cand_t *)ctx->mp_cand_tmp.p, (uint32_t *)ctx->mp_ncand.p);
+	ctx->stat_launches++;
+	GD_CUDA_OK(ctx, cudaGetLastError());
+	if ((rc = scan_u32(ctx, (const uint32_t *)ctx->mp_ncand.p, (int64_t *)ctx->mp_coff.p, n))) return rc;
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, (int64_t *)ctx->mp_coff.p + n, 8, cudaMemcpyDeviceToHost, s));
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(cand_off, ctx->mp_coff.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
+	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
+	const int64_t nc = h_word[0];
+	*n_cand_out = nc, *n_cig_out = 0;
+	for (int i = 0; i <= n; ++i) cand_off[i] += cand_base;
+	if (nc == 0) return GD_OK;
+	// ---- K3
+	if ((rc = gd_reserve(ctx, ctx->mp_cand, (size_t)nc * sizeof(gd_sr_cand_t)))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_qbuf, (size_t)nc * P.stride + 64))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_tbuf, (size_t)nc * P.stride + 64))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_cnt, (size_t)(std::max<int64_t>(nc, n) + 1) * 4))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_hoff, (size_t)(std::max<int64_t>(nc, n) + 2) * 8))) return rc;
+	gd_sr_cand_t *d_cand = (gd_sr_cand_t *)ctx->mp_cand.p;
+	gd_sr_compact_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, o->af_max_loc, (const gd_sr_cand_t *)ctx->mp_cand_tmp.p,
+	                                                   (const int64_t *)ctx->mp_coff.p, d_cand);
+	const int wblocks = (int)std::max<int64_t>(1, std::min<int64_t>((nc + 3) / 4, (int64_t)ctx->sms * 16));
+	gd_sr_window_kernel<<<wblocks, 128, 0, s>>>(idx->d, P, nc, d_off, d_len, d_buf, d_cand, (uint8_t *)ctx->mp_qbuf.p,
+	                                          (uint8_t *)ctx->mp_tbuf.p, (uint32_t *)ctx->mp_cnt.p);
+	ctx->stat_launches += 2;
+	GD_CUDA_OK(ctx, cudaGetLastError());
+	int64_t *d_pair_off = (int64_t *)ctx->mp_hoff.p;
+	if ((rc = scan_u32(ctx, (const uint32_t *)ctx->mp_cnt.p, d_pair_off, nc))) return rc;
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, d_pair_off + nc, 8, cudaMemcpyDeviceToHost, s));
+	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
+	const int64_t np = h_word[0];
+	// ---- DP on the candidates that are not exact matches (flag KSW_EZ_APPROX_MAX, map.c:867)
+	const int cig_stride = 2 * P.stride;
+	if (np > 0) {
+		if (np > 0x7fffffff) {
+			ctx->err = "gd_sr_map_batch: too many DP pairs in one slice";
+			return GD_ERR_ARG;
+		}
+		if ((rc = gd_reserve(ctx, ctx->mp_pair, (size_t)np * 16 + 64))) return rc;
+		if ((rc = gd_reserve(ctx, ctx->mp_ez, (size_t)np * sizeof(gd_extz_t)))) return rc;
+		if ((rc = gd_reserve(ctx, ctx->mp_cig, (size_t)np * cig_stride * 4))) return rc;
+		int64_t *d_poff = (int64_t *)ctx->mp_pair.p;
+		int32_t *d_plen = (int32_t *)(d_poff + np), *d_pcand = d_plen + np;
+		gd_sr_pairs_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(nc, P.stride, d_cand, d_pair_off, d_plen, d_poff, d_pcand);
+		ctx->stat_launches++;
+		int8_t mat[25]; // map.c:861-865
+		const int g = o->a, bb = o->b < 0 ? o->b : -o->b;
+		for (int x = 0; x < 5; ++x)
+			for (int y = 0; y < 5; ++y) mat[x * 5 + y] = (x == 4 || y == 4) ? 0 : (x == y ? g : bb);
+		gd_ksw_params_t prm = {5, mat, o->q, o->e, o->q2, o->e2, o->zdrop, o->end_bonus, 0x08};
+		if ((rc = gd_ksw_run_device(ctx, (int)np, d_plen, d_poff, (const uint8_t *)ctx->mp_qbuf.p, d_plen, d_poff,
+		                            (const uint8_t *)ctx->mp_tbuf.p, nullptr, (int)o->bw, max_len, max_len, (int)o->bw, &prm,
+		                            (gd_extz_t *)ctx->mp_ez.p, (uint32_t *)ctx->mp_cig.p, cig_stride)))
+			return rc;
+	}
+	// ---- K4
+	if ((rc = gd_reserve(ctx, ctx->mp_ncand, (size_t)(nc + 1) * 4))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_coff, (size_t)(std::max<int64_t>(nc, n) + 2) * 8))) return rc;
+	gd_sr_scores_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(nc, P, d_len, d_cand, d_pair_off, (const gd_extz_t *)ctx->mp_ez.p,
+	                                                               (uint32_t *)ctx->mp_ncand.p);
+	ctx->stat_launches++;
+	int64_t *d_cig_off = (int64_t *)ctx->mp_coff.p;
+	if ((rc = scan_u32(ctx, (const uint32_t *)ctx->mp_ncand.p, d_cig_off, nc))) return rc;
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, d_cig_off + nc, 8, cudaMemcpyDeviceToHost, s));
+	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
+	const int64_t ncig = h_word[0];
+	*n_cig_out = ncig;
+	const bool fits = cand_base + nc <= cand_cap && cig_base + ncig <= cigar_cap && cand && cigar;
+	if ((rc = gd_reserve(ctx, ctx->mp_cpool, (size_t)(ncig + 1) * 4))) return rc;
+	gd_sr_cigars_kernel<<<wblocks, 128, 0, s>>>(nc, d_cand, d_pair_off, d_cig_off, (const uint32_t *)ctx->mp_cig.p, cig_stride,
+	                                          (uint32_t *)ctx->mp_cpool.p, ncig);
+	ctx->stat_launches++;
+	GD_CUDA_OK(ctx, cudaGetLastError());
+	if (fits) {
+		GD_CUDA_OK(ctx, cudaMemcpyAsync(cand + cand_base, d_cand, (size_t)nc * sizeof(gd_sr_cand_t), cudaMemcpyDeviceToHost, s));
+		if (ncig) GD_CUDA_OK(ctx, cudaMemcpyAsync(cigar + cig_base, ctx->mp_cpool.p, (size_t)ncig * 4, cudaMemcpyDeviceToHost, s));
+	}
+	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
+	if (fits && cig_base)
+		for (int64_t c = 0; c < nc; ++c) cand[cand_base + c].cigar_off += (int32_t)cig_base;
+	return GD_OK;
+}
+
+extern "C" int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
+                               const gd_sr_opt_t *o, int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar,
+                               int64_t cigar_cap, int64_t *n_cigar)
+{
+	if (!ctx) return GD_ERR_ARG;
+	if (!idx || !o || n < 0 || !cand_off || (n > 0 && (!off || !len || !buf))) {
+		ctx->err = "gd_sr_map_batch: bad argument";
+		return GD_ERR_ARG;
+	}
+	if (o->af_max_loc < 1 || o->af_max_loc > SR_MAX_LOC || o->W < 1 || o->W > 63 || idx->device != ctx->device) {
+		ctx->err = "gd_sr_map_batch: need 1 <= af_max_loc <= 32, 1 <= W <= 63 and an index built on this device";
+		return GD_ERR_ARG;
+	}
+	cand_off[0] = 0;
+	if (n_cigar) *n_cigar = 0;
+	if (n == 0) return GD_OK;
+	cudaSetDevice(ctx->device);
+	const int slice = 1 << 18;
+	int64_t cand_base = 0, cig_base = 0;
+	for (int b = 0; b < n; b += slice) {
+		const int m = std::min(slice, n - b);
+		int64_t nc = 0, ng = 0;
+		int rc = sr_map_slice(ctx, idx, m, off + b, len + b, buf, o, cand_base, cig_base, cand_off + b, cand, cand_cap, cigar, cigar_cap, &nc, &ng);
+		if (rc) return rc;
+		cand_base += nc, cig_base += ng;
+	}
+	if (n_cigar) *n_cigar = cig_base;
+	if (cig_base > 0x7fffffff) {
+		ctx->err = "gd_sr_map_batch: CIGAR pool of one call exceeds 2^31 entries; map fewer reads per call";
+		return GD_ERR_ARG;
+	}
+	if (cand_base > cand_cap || cig_base > cigar_cap || (cand_base && !cand) || (cig_base && !cigar)) {
+		ctx->err = "gd_sr_map_batch: output buffer too small";
+		return GD_ERR_CAPACITY;
+	}
+	return GD_OK;
+}

@@ -480,6 +480,52 @@ extern "C" int gd_sketch_reads_batch(gd_ctx *ctx, int n, const int64_t *off, con
 }
 
 // --------------------------------------------------------------------------------------------
+// device-resident read sketching for the mapper (gd_map.cu): every (read, shift) job plus the cropped job of
+// mm_sketch2, cap rules applied, nothing copied or synchronised; the lists stay in the context's sketch scratch
+// (list of (read i, shift s): raw[job_off[i*JW+s] ..], first c3 / c2 entries; mm_sketch2's shift-0 list is job W).
+// --------------------------------------------------------------------------------------------
+int gd_sketch_reads_device_raw(gd_ctx *ctx, int n, const int64_t *d_off, const int32_t *d_len, const char *d_buf,
+                               int64_t max_len, int64_t sum_len, int w, int k, const char *Z, int W, float max_seeds,
+                               uint32_t max_nb_seeds, GdReadSketch *out)
+{
+	SketchParams S;
+	int rc = make_params(ctx, w, k, Z, W, S);
+	if (rc) return rc;
+	const int crop = max_seeds < 1.0f ? 1 : 0;
+	const int JW = W + crop;
+	const uint32_t cap2_const = crop ? 0u : (uint32_t)max_seeds;
+	const int64_t njobs64 = (int64_t)n * JW;
+	if (njobs64 > 0x7fffffff) {
+		ctx->err = "read sketching: too many (read,shift) jobs in one call";
+		return GD_ERR_ARG;
+	}
+	const int njobs = (int)njobs64;
+	cudaStream_t s = ctx->stream;
+	const int64_t per_job = max_len / S.W * S.ones + S.ones;
+	const int64_t worst = (sum_len / S.W * S.ones + (int64_t)n * S.ones) * JW + 16;
+	if ((rc = gd_reserve(ctx, ctx->sk_jobs, (size_t)njobs * sizeof(SketchJob)))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->sk_out_off, (size_t)(njobs + 1) * 8))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->sk_out, (size_t)worst * 16))) return rc;
+	gd_sketch_read_jobs_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, d_off, d_len, W, crop, max_seeds, (SketchJob *)ctx->sk_jobs.p);
+	ctx->stat_launches++;
+	rc = gd_sketch_run_jobs(ctx, S, njobs, (const SketchJob *)ctx->sk_jobs.p, per_job, worst, d_buf, (int64_t *)ctx->sk_out_off.p,
+	                        (uint64_t *)ctx->sk_out.p, worst);
+	if (rc) return rc;
+	const size_t nq = (size_t)n * W;
+	const size_t need = (nq + 1) * 8 * 2 + nq * 4 * 2 + 64;
+	if ((rc = gd_reserve(ctx, ctx->sk_rid, need))) return rc;
+	int64_t *c3 = (int64_t *)ctx->sk_rid.p, *c2 = c3 + nq + 1;
+	uint32_t *d_ret = (uint32_t *)(c2 + nq + 1), *d_cnt2 = d_ret + nq;
+	gd_sketch_read_counts_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, W, crop, cap2_const, max_nb_seeds, d_len, (const int64_t *)ctx->sk_out_off.p,
+	                                                         (const uint64_t *)ctx->sk_out.p, c3, c2, d_ret, d_cnt2);
+	ctx->stat_launches++;
+	GD_CUDA_OK(ctx, cudaGetLastError());
+	out->job_off = (const int64_t *)ctx->sk_out_off.p, out->raw = (const uint64_t *)ctx->sk_out.p;
+	out->c3 = c3, out->c2 = c2, out->ret3 = d_ret, out->JW = JW, out->crop = crop, out->raw_cap = worst;
+	return GD_OK;
+}
+
+// --------------------------------------------------------------------------------------------
 // drop-in single-sequence entry points (GDiet-ShortReads/mmpriv.h:63-68)
 // --------------------------------------------------------------------------------------------
 static void fatal(gd_ctx *ctx, const char *what)

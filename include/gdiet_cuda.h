@@ -181,6 +181,77 @@ int gd_sketch_reads_batch(gd_ctx *ctx, int n, const int64_t *off, const int32_t 
                           int64_t *s2_off, mm128_t *s2, int64_t s2_cap, int64_t *s3_off, uint32_t *s3_ret,
                           mm128_t *s3, int64_t s3_cap);
 
+/* ------------------------------------------------------------------------------------------ */
+/* (3) the stages either side of the two kernels: device-resident index + short-read mapping   */
+/*     (SURVEY.md section 8 rows F1 "index lookup" and F2 "seed-hit sort + location voting")    */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Device-resident minimizer index: what mm_idx_gen builds (GDiet-ShortReads/index.c:389-420) -- every
+ * contig sketched with mm_sketch, the (minimizer, position) records grouped by minimizer with the
+ * positions of one minimizer ascending (index.c:216-271), the 4-bit packed reference mi->S
+ * (index.c:351-356) -- laid out for the GPU: one open-addressing table {minimizer -> first, count} over a
+ * flat position array instead of 2^14 khash buckets.  A lookup returns exactly what mm_idx_get returns
+ * (index.c:84-100): the count and the positions in ascending order. */
+typedef struct gd_index gd_index;
+
+/* Sketches n_seq contigs (ASCII, host buffers; contig i is rid i) on the device and builds the index
+ * there.  (The reference's bucket_bits only shapes its host hash tables; no lookup result depends on it.) */
+int gd_index_build(gd_ctx *ctx, int n_seq, const int64_t *off, const int32_t *len, const char *buf, int w, int k,
+                   const char *Z, int W, gd_index **out);
+void gd_index_destroy(gd_index *idx);
+/* "n_seq", "total_len", "n_minimizers" (records), "n_keys" (distinct minimizers), "table_slots",
+ * "device_bytes", "s_words" (uint32 words of the 4-bit reference) */
+int64_t gd_index_stat(const gd_index *idx, const char *key);
+/* mm_idx_get for a batch (host arrays): count[i] = occurrences of minier[i] (= mm128_t.x >> 8),
+ * first[i] = offset of its first position in the exported position array (-1 if absent). */
+int gd_index_get_batch(gd_ctx *ctx, const gd_index *idx, int64_t n, const uint64_t *minier, uint32_t *count,
+                       int64_t *first);
+/* Copies the index to host arrays (any pointer may be NULL): keys[n_keys] ascending, counts[n_keys],
+ * positions[n_minimizers] grouped by key in key order (each group ascending), S[s_words] = mi->S. */
+int gd_index_export(gd_ctx *ctx, const gd_index *idx, uint64_t *keys, uint32_t *counts, uint64_t *positions,
+                    uint32_t *S);
+/* mm_idx_cal_max_occ (GDiet-ShortReads/index.c:182-201): the value mm_mapopt_update stores in mid_occ. */
+int gd_index_cal_max_occ(gd_ctx *ctx, const gd_index *idx, float frac, int32_t *max_occ);
+
+/* The mm_mapopt_t fields the short-read path reads between mm_sketch2 and ksw_extd2
+ * (GDiet-ShortReads/minimap.h:142-205; defaults main.c:166-182, preset options.c:130-150). */
+typedef struct {
+	int32_t W;     /* pattern length (-W) */
+	char Z[64];    /* pattern (-Z), NUL padded */
+	float max_seeds; /* opt->max_seeds (mm_sketch2) */
+	int32_t frag_mode, max_frag_len; /* MM_F_FRAG_MODE, opt->max_frag_len: cap of mm_sketch3 (map.c:621-622) */
+	uint32_t bw;   /* band width / vote distance, already clamped as at map.c:624-631 */
+	float min_cnt, rec_threshold_frac; /* -n */
+	int32_t af_max_loc;                /* --AF_max_loc (<= 32) */
+	int32_t mid_occ, max_max_occ, occ_dist;
+	float q_occ_frac;
+	int32_t for_only, rev_only; /* MM_F_FOR_ONLY / MM_F_REV_ONLY (map.c:121-127) */
+	int32_t a, b, q, e, q2, e2, zdrop, end_bonus;
+} gd_sr_opt_t;
+
+/* One candidate location of one read, in the order of the reference's candidate loop (map.c:764), with
+ * the outcome of exact_match_sse / ksw_extd2 (flag KSW_EZ_APPROX_MAX) for it: everything mm_map_frag has
+ * in hand when it calls mm_update_extra (map.c:932-954). 64 bytes. */
+typedef struct {
+	int32_t rid, rs, re, qs, qe, rev; /* mm_reg1_t fields set at map.c:932-938 */
+	int32_t votes, first_q, last_q;   /* vt_t (map.c:433-440) */
+	int32_t exact;                    /* exact_match_sse said equal: no DP, CIGAR = <len>M (map.c:873-915) */
+	int32_t score, n_cigar;           /* ez.score, ez.n_cigar */
+	int32_t cigar_off;                /* first entry of this candidate in cigar[] */
+	int32_t reserved[3];
+} gd_sr_cand_t;
+
+/* mm_map_frag (GDiet-ShortReads/map.c:586-952) for a batch of single-segment short reads, from the
+ * read's ASCII up to the ksw_extz_t of every candidate: mm_sketch2 -> mm_get_shift -> mm_sketch3 ->
+ * mm_seed_mz_flt -> mm_collect_matches2 -> collect_seed_hits -> vote x2 -> window arithmetic ->
+ * exact_match_sse | ksw_extd2.  Read i is buf[off[i] .. off[i]+len[i]).  Results in input order:
+ *   cand[cand_off[i] .. cand_off[i+1])   candidates of read i
+ *   cigar[c.cigar_off .. +c.n_cigar)     BAM CIGAR of candidate c
+ * Returns GD_ERR_CAPACITY (with cand_off[n] / *n_cigar = required sizes) if an output is too small. */
+int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
+                    const gd_sr_opt_t *opt, int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar,
+                    int64_t cigar_cap, int64_t *n_cigar);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,133 @@
+"""GPU parity of the device-resident index and the short-read mapping stage against
+oracle/gd_oracle_map.c, the reference call trace (when oracle/_ref/GDiet_avx_sr travelled) and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+import maplib
+from oraclelib import cpu_has_avx512
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def M():
+    return maplib.MapOracle()
+
+
+def flat_reads(reads):
+    n, L = reads.shape
+    return np.arange(n, dtype=np.int64) * L, np.full(n, L, np.int32), np.ascontiguousarray(reads.reshape(-1))
+
+
+def test_index_matches_oracle(ctx, M):
+    contigs, _ = maplib.make_dataset(seed=1, n_reads=1)
+    for Z in ("10", "110"):
+        idx = ctx.index_build(contigs, 11, 21, Z)
+        mi = M.index_build(contigs, 11, 21, Z)
+        keys, counts, pos = M.index_arrays(mi)
+        dk, dc, dp, S = idx.export()
+        assert np.array_equal(dk, keys) and np.array_equal(dc, counts) and np.array_equal(dp, pos)
+        # mi->S: 4-bit codes, 8 per word, contigs back to back (index.c:351-356)
+        codes = np.concatenate([np.searchsorted(np.frombuffer(b"ACGT", np.uint8), c) for c in contigs]).astype(np.uint8)
+        nib = ((S[:, None] >> (4 * np.arange(8, dtype=np.uint32))[None, :]) & 0xf).reshape(-1)[: len(codes)]
+        assert np.array_equal(nib, codes)
+        # mm_idx_get: present and absent minimizers
+        rng = np.random.default_rng(0)
+        probe = np.concatenate([keys[rng.integers(0, len(keys), 2000)], rng.integers(0, 1 << 42, 2000, dtype=np.uint64)])
+        cnt, first = idx.get(probe)
+        starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        look = {int(k): (int(c), int(s)) for k, c, s in zip(keys, counts, starts)}
+        for m, c, f in zip(probe, cnt, first):
+            e = look.get(int(m))
+            assert (int(c), int(f)) == (e if e else (0, -1))
+        for f in (2e-4, 0.01, 0.5):
+            assert idx.cal_max_occ(f) == M.lib.gdo_index_cal_max_occ(mi, f)
+        idx.close()
+        M.lib.gdo_index_destroy(mi)
+
+
+CASES = [
+    (1, "10", 150, {}),
+    (2, "10", 150, dict(min_cnt=0.2, rec_frac=0.1)),
+    (3, "110", 150, dict(min_cnt=0.3)),
+    (4, "10", 400, dict(min_cnt=0.2, bw_min=500, bw_max=1500)),
+    (5, "10", 100, dict(min_cnt=0.1, bw_frac=0.1, bw_min=20, bw_max=50)),
+    (7, "10", 300, dict(min_cnt=0.2, bw_min=500, bw_max=1500, af_max_loc=2)),
+    (8, "10", 150, dict(min_cnt=0.2, mid_occ=2, max_max_occ=3, occ_dist=40)),   # mm_seed_select on the planted repeat
+    (9, "10", 150, dict(min_cnt=0.2, mid_occ=2, max_max_occ=2, occ_dist=0)),    # plain max_occ filter
+    (10, "10", 150, dict(min_cnt=0.1, for_only=1)),
+    (11, "10", 150, dict(min_cnt=0.1, rev_only=1)),
+]
+
+
+@pytest.mark.parametrize("seed,Z,read_len,okw", CASES)
+def test_sr_map_matches_oracle(ctx, M, seed, Z, read_len, okw):
+    contigs, reads = maplib.make_dataset(seed=seed, read_len=read_len, n_reads=1500)
+    o = maplib.sr_opt(Z=Z, qlen=read_len, **okw)
+    idx = ctx.index_build(contigs, 11, 21, Z)
+    mi = M.index_build(contigs, 11, 21, Z)
+    off, lens, buf = flat_reads(reads)
+    coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, o)
+    total = 0
+    for i, r in enumerate(reads):
+        oc, ocig, dbg = M.map_read(mi, r, o)
+        mine = cand[coff[i]:coff[i + 1]]
+        assert len(mine) == len(oc), "read %d: %d candidates, oracle %d (%s)" % (i, len(mine), len(oc), dbg)
+        for j, (a, b) in enumerate(zip(mine, oc)):
+            for f in ("rid", "rs", "re", "qs", "qe", "rev", "votes", "first_q", "last_q", "exact", "score", "n_cigar"):
+                assert int(a[f]) == int(b[f]), "read %d cand %d field %s: %d vs oracle %d (%s)" % (i, j, f, a[f], b[f], dbg)
+            ga = cig[int(a["cigar_off"]):int(a["cigar_off"]) + max(int(a["n_cigar"]), 0)]
+            gb = ocig[int(b["cigar_off"]):int(b["cigar_off"]) + max(int(b["n_cigar"]), 0)]
+            assert np.array_equal(ga, gb), "read %d cand %d cigar" % (i, j)
+        total += len(mine)
+    assert total > 700
+    idx.close()
+    M.lib.gdo_index_destroy(mi)
+
+
+@pytest.mark.skipif(not (maplib.have_ref_program() and cpu_has_avx512()), reason="needs oracle/_ref/GDiet_avx_sr and AVX-512")
+def test_sr_map_matches_reference_program(ctx):
+    """The device stage against the call trace of the unmodified reference program, config-1 flags."""
+    contigs, reads = maplib.make_dataset(seed=21, n_reads=4000, contig_lens=(1000000, 400000, 100000))
+    o = maplib.sr_opt()
+    _, tr = maplib.run_reference(contigs, reads, maplib.ref_cmdline(o, extra=["-r", "0.05,150,200"]))
+    idx = ctx.index_build(contigs, 11, 21, "10")
+    off, lens, buf = flat_reads(reads)
+    coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, o)
+    for i, t in enumerate(tr):
+        maplib.cands_equal_trace(cand[coff[i]:coff[i + 1]], cig, t["cands"], "read %d" % i)
+    idx.close()
+
+
+def test_sr_map_golden(ctx):
+    """Committed vectors generated from the reference program by tests/golden/make_golden_map.py."""
+    g = np.load(os.path.join(GOLDEN, "map_sr.npz"))
+    contigs, reads = maplib.make_dataset(seed=int(g["seed"]), n_reads=int(g["n_reads"]))
+    o = maplib.sr_opt(min_cnt=float(g["min_cnt"]), rec_frac=float(g["rec_frac"]))
+    idx = ctx.index_build(contigs, 11, 21, "10")
+    off, lens, buf = flat_reads(reads)
+    coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, o)
+    assert np.array_equal(coff, g["cand_off"])
+    for f in ("rid", "rs", "re", "qs", "qe", "rev", "exact", "score", "n_cigar"):
+        assert np.array_equal(cand[f], g[f]), f
+    mine = np.concatenate([cig[int(c["cigar_off"]):int(c["cigar_off"]) + max(int(c["n_cigar"]), 0)] for c in cand])
+    assert np.array_equal(mine, g["cigar"])
+    idx.close()
+
+
+def test_sr_map_empty_and_unmappable(ctx):
+    contigs, _ = maplib.make_dataset(seed=1, n_reads=1)
+    idx = ctx.index_build(contigs, 11, 21, "10")
+    o = maplib.sr_opt()
+    coff, cand, cig = ctx.sr_map_batch(idx, np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(1, np.uint8), o)
+    assert len(cand) == 0 and coff[0] == 0
+    junk = np.frombuffer(b"ACGT" * 40, np.uint8)[None, :150].repeat(7, 0).copy()
+    junk[3] = np.frombuffer(b"N" * 150, np.uint8)
+    off, lens, buf = flat_reads(junk)
+    coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, o)
+    assert len(cand) == 0 and np.all(coff == 0)
+    idx.close()

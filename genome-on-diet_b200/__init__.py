@@ -71,6 +71,63 @@ class gd_sr_opt_t(C.Structure):
                 ("zdrop", C.c_int32), ("end_bonus", C.c_int32)]
 
 
+class gd_sr_post_opt_t(C.Structure):
+    """include/gdiet_cuda.h: options of the host side after the DP (GDiet-ShortReads/map.c:954-984)."""
+    _fields_ = [(f, C.c_int32) for f in ("a", "b", "q", "e", "min_dp_max", "best_n", "no_print_2nd", "is_sr", "sam_hit_only",
+                                         "softclip", "n_threads")]
+
+
+def sr_post_options(n_threads=0, **kw):
+    """`-ax sr` values (GDiet-ShortReads/options.c:130-150)."""
+    o = gd_sr_post_opt_t(a=2, b=8, q=12, e=2, min_dp_max=40, best_n=20, no_print_2nd=1, is_sr=1, sam_hit_only=0, softclip=0,
+                         n_threads=n_threads)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def _cstr_array(strings):
+    arr = (C.c_char_p * len(strings))()
+    arr[:] = [x if isinstance(x, bytes) else x.encode() for x in strings]
+    return arr
+
+
+def sr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, contigs, opt):
+    """gd_sr_sam_batch: SAM records (bytes) of a mapped batch. contigs: list of ASCII uint8 arrays."""
+    L = load()
+    ref_len = np.array([len(c) for c in contigs], np.int32)
+    ref_off = np.zeros(len(contigs), np.int64)
+    ref_off[1:] = np.cumsum(ref_len[:-1].astype(np.int64))
+    ref = np.concatenate([np.ascontiguousarray(c, np.uint8) for c in contigs])
+    n_arr, s_arr = _cstr_array(names), _cstr_array(seq_names)
+    out, out_len = C.c_void_p(), C.c_size_t(0)
+    cand = np.ascontiguousarray(cand)
+    cigar = np.ascontiguousarray(cigar, np.uint32) if len(cigar) else np.zeros(1, np.uint32)
+    if len(cand) == 0:
+        cand = np.zeros(1, SR_CAND_DTYPE)
+    rc = L.gd_sr_sam_batch(len(lens), C.cast(n_arr, C.c_void_p), _ptr(off), _ptr(lens), _ptr(seq), _ptr(qual), _ptr(cand_off),
+                           _ptr(cand), _ptr(cigar), len(contigs), C.cast(s_arr, C.c_void_p), _ptr(ref_off), _ptr(ref_len), _ptr(ref),
+                           C.byref(opt), C.byref(out), C.byref(out_len))
+    if rc != GD_OK:
+        raise GdietError("gd_sr_sam_batch failed (%d)" % rc)
+    txt = C.string_at(out, out_len.value)
+    L.gd_free(out)
+    return txt
+
+
+def sam_header(seq_names, ref_len):
+    L = load()
+    s_arr = _cstr_array(seq_names)
+    ref_len = np.ascontiguousarray(ref_len, np.int32)
+    out, out_len = C.c_void_p(), C.c_size_t(0)
+    rc = L.gd_sam_header(len(seq_names), C.cast(s_arr, C.c_void_p), _ptr(ref_len), C.byref(out), C.byref(out_len))
+    if rc != GD_OK:
+        raise GdietError("gd_sam_header failed (%d)" % rc)
+    txt = C.string_at(out, out_len.value)
+    L.gd_free(out)
+    return txt
+
+
 SR_CAND_FIELDS = ["rid", "rs", "re", "qs", "qe", "rev", "votes", "first_q", "last_q", "exact", "score", "n_cigar", "cigar_off"]
 SR_CAND_DTYPE = np.dtype([(f, np.int32) for f in SR_CAND_FIELDS] + [("reserved", np.int32, 3)])
 
@@ -108,7 +165,7 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
-           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch"]
+           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free"]
 
 
 def load():
@@ -172,6 +229,13 @@ def load():
     L.gd_index_cal_max_occ.argtypes = [vp, vp, C.c_float, C.POINTER(C.c_int32)]
     L.gd_sr_map_batch.restype = i32
     L.gd_sr_map_batch.argtypes = [vp, vp, i32, vp, vp, vp, C.POINTER(gd_sr_opt_t), vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.gd_sr_sam_batch.restype = i32
+    L.gd_sr_sam_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
+                                  C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.gd_sam_header.restype = i32
+    L.gd_sam_header.argtypes = [i32, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.gd_free.restype = None
+    L.gd_free.argtypes = [vp]
     _lib = L
     return L
 

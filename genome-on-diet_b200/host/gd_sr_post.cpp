@@ -1,0 +1,411 @@
+// gd_sr_post.cpp -- host side after the DP: what GDiet-ShortReads/map.c:932-984 and
+// format.c:412-603 do with the ksw_extz_t of every candidate, for a batch of reads and on all host cores:
+//
+//   mm_update_extra + mm_fix_cigar   align.c:93-172,259-318   indel left-alignment, blen / mlen / n_ambi / dp_max
+//   candidate filter + ordering      map.c:956-978            clip / min_dp_max filter, insertion by score
+//   mm_set_sam_params                hit.c:494-557            primary / secondary / supplementary, mapq
+//   mm_write_sam3 (single segment)   format.c:349-410,412-603 one SAM line per reported location (or flag 4)
+//
+// This is HOST code of the product (plain C++, no CUDA): the reference keeps these steps on the CPU too.  Input is
+// exactly what gd_sr_map_batch returns plus the read / reference text the host already holds.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+#include "../../include/gdiet_cuda.h"
+
+namespace {
+
+enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3 };
+
+struct Reg { // the mm_reg1_t / mm_extra_t fields this path touches (minimap.h:105-131)
+	int32_t rid = 0, score = 0, qs = 0, qe = 0, rs = 0, re = 0, rev = 0;
+	int32_t id = 0, parent = 0, mapq = 0, sam_pri = 0, mlen = 0, blen = 0;
+	int32_t dp_score = 0, dp_max = 0, n_ambi = 0;
+	std::vector<uint32_t> cigar;
+};
+
+inline int nt4(unsigned char c)
+{ // seq_nt4_table, sketch.c:11-18
+	switch (c) {
+	case 'A': case 'a': case 0: return 0;
+	case 'C': case 'c': case 1: return 1;
+	case 'G': case 'g': case 2: return 2;
+	case 'T': case 't': case 'U': case 'u': case 3: return 3;
+	default: return 4;
+	}
+}
+
+struct CompTable { // seq_comp_table, bseq.c:11-28: IUPAC complement, case preserved, everything else unchanged
+	unsigned char t[256];
+	CompTable()
+	{
+		for (int i = 0; i < 256; ++i) t[i] = (unsigned char)i;
+		const char *a = "ACBDKRTU", *b = "TGVHMYAA";
+		for (int i = 0; a[i]; ++i) {
+			t[(int)a[i]] = b[i], t[(int)a[i] + 32] = b[i] + 32;
+			if (a[i] != 'T' && a[i] != 'U') t[(int)b[i]] = a[i], t[(int)b[i] + 32] = a[i] + 32;
+		}
+	}
+};
+const CompTable g_comp;
+
+inline float mg_log2(float x)
+{ // mmpriv.h:146-157
+	union {
+		float f;
+		uint32_t i;
+	} z = {x};
+	float log_2 = (float)((z.i >> 23) & 255) - 128;
+	z.i &= ~(255u << 23);
+	z.i += 127u << 23;
+	log_2 += (-0.34484843f * z.f + 2.02466578f) * z.f - 0.67487759f;
+	return log_2;
+}
+
+// align.c:93-172
+void fix_cigar(Reg &r, const uint8_t *qseq, const uint8_t *tseq, int *qshift, int *tshift)
+{
+	std::vector<uint32_t> &c = r.cigar;
+	int32_t toff = 0, qoff = 0;
+	bool shrink = false;
+	*qshift = *tshift = 0;
+	if (c.size() <= 1) return;
+	const uint32_t n = (uint32_t)c.size();
+	for (uint32_t k = 0; k < n; ++k) { // indel left alignment
+		const uint32_t op = c[k] & 0xf, len = c[k] >> 4;
+		if (len == 0) shrink = true;
+		if (op == OP_M) toff += len, qoff += len;
+		else if (op == OP_I || op == OP_D) {
+			if (k > 0 && k < n - 1 && (c[k - 1] & 0xf) == 0 && (c[k + 1] & 0xf) == 0) {
+				const int prev_len = (int)(c[k - 1] >> 4);
+				const uint8_t *s = op == OP_I ? qseq : tseq;
+				const int o = op == OP_I ? qoff : toff;
+				int l = 0;
+				while (l < prev_len && s[o - 1 - l] == s[o + (int)len - 1 - l]) ++l;
+				if (l > 0) c[k - 1] -= (uint32_t)l << 4, c[k + 1] += (uint32_t)l << 4, qoff -= l, toff -= l;
+				if (l == prev_len) shrink = true;
+			}
+			if (op == OP_I) qoff += len;
+			else toff += len;
+		} else if (op == OP_N) toff += len;
+	}
+	for (uint32_t k = 0; k + 2 < n; ++k) { // runs like 5I6D7I become one I and one D
+		if ((c[k] & 0xf) > 0 && (c[k] & 0xf) + (c[k + 1] & 0xf) == 3) {
+			uint32_t l, s[3] = {0, 0, 0};
+			for (l = k; l < n; ++l) {
+				const uint32_t op = c[l] & 0xf;
+				if (op == OP_I || op == OP_D || c[l] >> 4 == 0) s[op] += c[l] >> 4;
+				else break;
+			}
+			if (s[1] > 0 && s[2] > 0 && l - k > 2) {
+				c[k] = s[1] << 4 | OP_I, c[k + 1] = s[2] << 4 | OP_D;
+				for (k += 2; k < l; ++k) c[k] &= 0xf;
+				shrink = true;
+			}
+			k = l;
+		}
+	}
+	if (shrink) {
+		size_t l = 0;
+		for (size_t k = 0; k < c.size(); ++k) // squeeze out zero-length operations
+			if (c[k] >> 4 != 0) c[l++] = c[k];
+		c.resize(l);
+		l = 0;
+		for (size_t k = 0; k < c.size(); ++k) // merge equal neighbours
+			if (k == c.size() - 1 || (c[k] & 0xf) != (c[k + 1] & 0xf)) c[l++] = c[k];
+			else c[k + 1] += c[k] >> 4 << 4;
+		c.resize(l);
+	}
+	if ((c[0] & 0xf) == OP_I || (c[0] & 0xf) == OP_D) { // drop a leading I or D
+		const int32_t l = (int32_t)(c[0] >> 4);
+		if ((c[0] & 0xf) == OP_I) {
+			if (r.rev) r.qe -= l;
+			else r.qs += l;
+			*qshift = l;
+		} else r.rs += l, *tshift = l;
+		c.erase(c.begin());
+	}
+}
+
+// align.c:259-318 (is_eqx = 0)
+void update_extra(Reg &r, const uint8_t *qseq, const uint8_t *tseq, const int8_t *mat, int8_t q, int8_t e, int log_gap)
+{
+	int qshift, tshift;
+	int32_t toff = 0, qoff = 0;
+	double s = 0.0, mx = 0.0;
+	fix_cigar(r, qseq, tseq, &qshift, &tshift);
+	qseq += qshift, tseq += tshift;
+	r.blen = r.mlen = 0;
+	for (uint32_t cg : r.cigar) {
+		const uint32_t op = cg & 0xf, len = cg >> 4;
+		if (op == OP_M) {
+			int n_ambi = 0, n_diff = 0;
+			for (uint32_t l = 0; l < len; ++l) {
+				const int cq = qseq[qoff + l], ct = tseq[toff + l];
+				if (ct > 3 || cq > 3) ++n_ambi;
+				else if (ct != cq) ++n_diff;
+				// the reference indexes its 25-entry matrix with ct*5+cq even for cq == 7 (reverse-strand N);
+				// inside the array that is the entry of (ct+1, 2); beyond it the read is undefined -> 0 here
+				const int mi = ct * 5 + cq;
+				s += mi < 25 ? mat[mi] : 0;
+				if (s < 0) s = 0;
+				else mx = mx > s ? mx : s;
+			}
+			r.blen += len - n_ambi, r.mlen += len - (n_ambi + n_diff), r.n_ambi += n_ambi;
+			toff += len, qoff += len;
+		} else if (op == OP_I || op == OP_D) {
+			int n_ambi = 0;
+			const uint8_t *sq = op == OP_I ? qseq + qoff : tseq + toff;
+			for (uint32_t l = 0; l < len; ++l)
+				if (sq[l] > 3) ++n_ambi;
+			r.blen += len - n_ambi, r.n_ambi += n_ambi;
+			if (log_gap) s -= q + (double)e * mg_log2(1.0f + len);
+			else s -= q + e;
+			if (s < 0) s = 0;
+			if (op == OP_I) qoff += len;
+			else toff += len;
+		} else if (op == OP_N) toff += len;
+	}
+	r.dp_max = (int32_t)(mx + .499);
+}
+
+// hit.c:494-557
+void set_sam_params(std::vector<Reg> &regs, unsigned qlen, unsigned match_score, unsigned max_nb_sec)
+{
+	const int n_regs = (int)regs.size();
+	const int supp_threshold = (int)(0.8 * (float)(regs[0].qe - regs[0].qs));
+	unsigned nb_sec = 0;
+	int dp_max2 = 0;
+	regs[0].sam_pri = 1, regs[0].parent = regs[0].id;
+	for (int i = 1; i < n_regs; i++) {
+		regs[i].sam_pri = 0;
+		if (regs[i].qe - regs[i].qs > supp_threshold) nb_sec++, regs[i].mapq = 0, regs[i].parent = regs[i].id + 1, dp_max2 = regs[i].score;
+		else regs[i].mapq = 60, regs[i].parent = regs[i].id;
+	}
+	for (int i = 1; i < n_regs - 1; i++) { // supplementaries in front of secondaries, secondaries by score
+		if (regs[i].parent != regs[i].id) {
+			for (int j = i + 1; j < n_regs; j++) {
+				if (regs[j].parent == regs[j].id) {
+					std::swap(regs[i], regs[j]);
+					break;
+				} else if (regs[i].score < regs[j].score) std::swap(regs[i], regs[j]);
+			}
+		}
+	}
+	if (max_nb_sec < nb_sec) nb_sec = max_nb_sec;
+	uint32_t mapq;
+	if (nb_sec > 9) mapq = 0;
+	else if (nb_sec > 6) mapq = 1;
+	else if (nb_sec > 4) mapq = 2;
+	else if (nb_sec == 3) mapq = 3; // (the reference tests == 3 twice: 4 secondaries fall through to 60)
+	else if (nb_sec == 2) mapq = 5;
+	else if (nb_sec == 1) {
+		const int dp_max = regs[0].score;
+		const float identity = (float)regs[0].mlen / regs[0].blen;
+		mapq = (uint32_t)(54 * identity * (dp_max - dp_max2) / (qlen * match_score - dp_max2) + 5);
+	} else mapq = 60;
+	regs[0].mapq = (int32_t)(mapq & 0xff); // 8-bit field
+}
+
+inline void put_int(std::string &s, long v)
+{
+	char b[24];
+	snprintf(b, sizeof b, "%ld", v);
+	s += b;
+}
+
+void put_seq(std::string &s, const char *seq, int l, int rev, int comp)
+{ // sam_write_sq, format.c:349-360
+	if (!rev) {
+		s.append(seq, (size_t)l);
+		return;
+	}
+	for (int i = 0; i < l; ++i) {
+		const int c = seq[l - 1 - i];
+		s += (char)((c >= 0 && c < 128 && comp) ? g_comp.t[c] : c);
+	}
+}
+
+void put_tags(std::string &s, const Reg &r)
+{ // write_tags, format.c:302-338 (inv = 0, cnt = 0, subsc = 0, split = 0 on this path)
+	s += "\tNM:i:", put_int(s, r.blen - r.mlen + r.n_ambi);
+	s += "\tms:i:", put_int(s, r.dp_max);
+	s += "\tAS:i:", put_int(s, r.dp_score);
+	s += "\tnn:i:", put_int(s, r.n_ambi);
+	s += r.id == r.parent ? "\ttp:A:P" : "\ttp:A:S";
+	s += "\tcm:i:0\ts1:i:", put_int(s, r.score);
+	if (r.parent == r.id) s += "\ts2:i:0";
+	int32_t n_gap = 0, n_gapo = 0; // mm_event_identity, align.c:949-966
+	for (uint32_t cg : r.cigar)
+		if ((cg & 0xf) == OP_I || (cg & 0xf) == OP_D) ++n_gapo, n_gap += (int32_t)(cg >> 4);
+	const double div = 1.0 - (double)r.mlen / (r.blen + r.n_ambi - n_gap + n_gapo);
+	char b[32];
+	if (div == 0.0) b[0] = '0', b[1] = 0;
+	else snprintf(b, 16, "%.4f", div);
+	s += "\tde:f:", s += b;
+}
+
+struct Ctx {
+	int n;
+	const char *const *names;
+	const int64_t *off;
+	const int32_t *len;
+	const char *seq, *qual;
+	const int64_t *cand_off;
+	const gd_sr_cand_t *cand;
+	const uint32_t *cigar;
+	int n_seq;
+	const char *const *seq_names;
+	const int64_t *ref_off;
+	const int32_t *ref_len;
+	const char *ref;
+	const gd_sr_post_opt_t *o;
+};
+
+void one_read(const Ctx &C, int i, std::string &out)
+{
+	const gd_sr_post_opt_t &o = *C.o;
+	const int qlen = C.len[i];
+	const char *rd = C.seq + C.off[i], *ql = C.qual ? C.qual + C.off[i] : nullptr;
+	const char *name = C.names[i];
+	int8_t mat[25]; // map.c:861-865
+	const int g = o.a, bb = o.b < 0 ? o.b : -o.b;
+	for (int x = 0; x < 5; ++x)
+		for (int y = 0; y < 5; ++y) mat[x * 5 + y] = (int8_t)((x == 4 || y == 4) ? 0 : (x == y ? g : bb));
+	std::vector<Reg> regs;
+	std::vector<uint8_t> qs, ts;
+	for (int64_t ci = C.cand_off[i]; ci < C.cand_off[i + 1]; ++ci) { // map.c:932-978
+		const gd_sr_cand_t &c = C.cand[ci];
+		Reg r = Reg();
+		r.rid = c.rid, r.score = c.score, r.qs = c.qs, r.qe = c.qe, r.rs = c.rs, r.re = c.re, r.rev = c.rev;
+		r.dp_score = c.score;
+		if (c.n_cigar > 0) r.cigar.assign(C.cigar + c.cigar_off, C.cigar + c.cigar_off + c.n_cigar);
+		const int n = c.qe - c.qs, tl = c.re - c.rs;
+		qs.resize((size_t)n + 1), ts.resize((size_t)tl + 1);
+		for (int j = 0; j < n; ++j) qs[j] = (uint8_t)(c.rev ? nt4((unsigned char)rd[c.qe - 1 - j]) ^ 3 : nt4((unsigned char)rd[c.qs + j]));
+		const char *tp = C.ref + C.ref_off[c.rid] + c.rs;
+		for (int j = 0; j < tl; ++j) ts[j] = (uint8_t)nt4((unsigned char)tp[j]);
+		update_extra(r, qs.data(), ts.data(), mat, (int8_t)o.q, (int8_t)o.e, !o.is_sr);
+		const uint32_t clip0 = r.rev ? (uint32_t)(qlen - r.qe) : (uint32_t)r.qs, clip1 = r.rev ? (uint32_t)r.qs : (uint32_t)(qlen - r.qe);
+		if (!(clip0 < (uint32_t)qlen && clip1 < (uint32_t)qlen) || r.dp_score < o.min_dp_max) continue;
+		regs.push_back(std::move(r));
+		for (size_t k = regs.size() - 1; k > 0 && regs[k].score > regs[k - 1].score; --k) std::swap(regs[k], regs[k - 1]);
+	}
+	if (!regs.empty()) set_sam_params(regs, (unsigned)qlen, (unsigned)o.a, o.no_print_2nd ? 0u : (unsigned)o.best_n);
+	// ---- format.c:412-603 with n_seg == 1
+	if (regs.empty()) {
+		if (o.sam_hit_only) return;
+		out += name, out += "\t4\t*\t0\t0\t*\t*\t0\t0\t";
+		out.append(rd, (size_t)qlen), out += '\t';
+		if (ql) out.append(ql, (size_t)qlen);
+		else out += '*';
+		out += "\trl:i:0\n";
+		return;
+	}
+	for (size_t j = 0; j < regs.size(); ++j) {
+		const Reg &r = regs[j];
+		if (o.no_print_2nd && r.id != r.parent) continue; // map.c:1236
+		int flag = 0;
+		if (r.rev) flag |= 0x10;
+		if (r.parent != r.id) flag |= 0x100;
+		else if (!r.sam_pri) flag |= 0x800;
+		out += name, out += '\t', put_int(out, flag), out += '\t', out += C.seq_names[r.rid], out += '\t', put_int(out, r.rs + 1);
+		out += '\t', put_int(out, r.mapq), out += '\t';
+		const uint32_t clip0 = r.rev ? (uint32_t)(qlen - r.qe) : (uint32_t)r.qs, clip1 = r.rev ? (uint32_t)r.qs : (uint32_t)(qlen - r.qe);
+		const char clip_char = ((flag & 0x800) && !o.softclip) ? 'H' : 'S';
+		if (clip0) put_int(out, clip0), out += clip_char;
+		for (uint32_t cg : r.cigar) put_int(out, cg >> 4), out += "MIDNSHP=XB"[cg & 0xf];
+		if (clip1) put_int(out, clip1), out += clip_char;
+		out += "\t*\t0\t0\t";
+		if ((flag & 0x900) == 0 || o.softclip) {
+			put_seq(out, rd, qlen, r.rev, r.rev), out += '\t';
+			if (ql) put_seq(out, ql, qlen, r.rev, 0);
+			else out += '*';
+		} else if (flag & 0x100) out += "*\t*";
+		else {
+			put_seq(out, rd + r.qs, r.qe - r.qs, r.rev, r.rev), out += '\t';
+			if (ql) put_seq(out, ql + r.qs, r.qe - r.qs, r.rev, 0);
+			else out += '*';
+		}
+		put_tags(out, r);
+		if (r.parent == r.id && regs.size() > 1) { // SA tag, format.c:563-592
+			int n_sa = 0;
+			for (size_t k = 0; k < regs.size(); ++k)
+				if (k != j && regs[k].parent == regs[k].id) ++n_sa;
+			if (n_sa > 0) {
+				out += "\tSA:Z:";
+				for (size_t k = 0; k < regs.size(); ++k) {
+					const Reg &q = regs[k];
+					if (k == j || q.parent != q.id) continue;
+					int l_M, l_I = 0, l_D = 0;
+					if (q.qe - q.qs < q.re - q.rs) l_M = q.qe - q.qs, l_D = (q.re - q.rs) - l_M;
+					else l_M = q.re - q.rs, l_I = (q.qe - q.qs) - l_M;
+					const int clip5 = q.rev ? qlen - q.qe : q.qs, clip3 = q.rev ? q.qs : qlen - q.qe;
+					out += C.seq_names[q.rid], out += ',', put_int(out, q.rs + 1), out += ',', out += "+-"[q.rev], out += ',';
+					if (clip5) put_int(out, clip5), out += 'S';
+					if (l_M) put_int(out, l_M), out += 'M';
+					if (l_I) put_int(out, l_I), out += 'I';
+					if (l_D) put_int(out, l_D), out += 'D';
+					if (clip3) put_int(out, clip3), out += 'S';
+					out += ',', put_int(out, q.mapq), out += ',', put_int(out, q.blen - q.mlen + q.n_ambi), out += ';';
+				}
+			}
+		}
+		out += "\trl:i:0\n";
+	}
+}
+
+} // namespace
+
+extern "C" int gd_sam_header(int n_seq, const char *const *seq_names, const int32_t *ref_len, char **sam, size_t *sam_len)
+{ // mm_write_sam_hdr, format.c:128-137 (the @PG line carries the command line and is the caller's)
+	if (n_seq < 0 || !sam || !sam_len) return GD_ERR_ARG;
+	std::string s;
+	for (int i = 0; i < n_seq; ++i) s += "@SQ\tSN:", s += seq_names[i], s += "\tLN:", put_int(s, ref_len[i]), s += '\n';
+	*sam = (char *)malloc(s.size() + 1);
+	if (!*sam) return GD_ERR_ARG;
+	memcpy(*sam, s.c_str(), s.size() + 1);
+	*sam_len = s.size();
+	return GD_OK;
+}
+
+extern "C" void gd_free(void *p) { free(p); }
+
+extern "C" int gd_sr_sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                               const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar,
+                               int n_seq, const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len,
+                               const char *ref, const gd_sr_post_opt_t *opt, char **sam, size_t *sam_len)
+{
+	if (n < 0 || !opt || !sam || !sam_len || (n > 0 && (!names || !off || !len || !seq || !cand_off || !seq_names || !ref_off || !ref)))
+		return GD_ERR_ARG;
+	Ctx C = {n, names, off, len, seq, qual, cand_off, cand, cigar, n_seq, seq_names, ref_off, ref_len, ref, opt};
+	int nt = opt->n_threads > 0 ? opt->n_threads : (int)std::thread::hardware_concurrency();
+	nt = std::max(1, std::min(nt, (n + 255) / 256));
+	std::vector<std::string> parts((size_t)nt);
+	auto work = [&](int t) { // contiguous read ranges: the concatenation is in input order
+		const int64_t b = (int64_t)n * t / nt, e = (int64_t)n * (t + 1) / nt;
+		parts[t].reserve((size_t)(e - b) * 512);
+		for (int64_t i = b; i < e; ++i) one_read(C, (int)i, parts[t]);
+	};
+	if (nt == 1) work(0);
+	else {
+		std::vector<std::thread> th;
+		for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+		for (auto &x : th) x.join();
+	}
+	size_t total = 0;
+	for (auto &p : parts) total += p.size();
+	char *buf = (char *)malloc(total + 1);
+	if (!buf) return GD_ERR_ARG;
+	size_t w = 0;
+	for (auto &p : parts) memcpy(buf + w, p.data(), p.size()), w += p.size();
+	buf[total] = 0;
+	*sam = buf, *sam_len = total;
+	return GD_OK;
+}

@@ -252,6 +252,33 @@ int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off,
                     const gd_sr_opt_t *opt, int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar,
                     int64_t cigar_cap, int64_t *n_cigar);
 
+/* ------------------------------------------------------------------------------------------ */
+/* (4) host side after the DP -- plain C++, no GPU work            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+	int32_t a, b, q, e;   /* scoring (mm_update_extra, map.c:954) */
+	int32_t min_dp_max;   /* opt->min_dp_max (map.c:961) */
+	int32_t best_n;       /* opt->best_n (map.c:980) */
+	int32_t no_print_2nd; /* MM_F_NO_PRINT_2ND */
+	int32_t is_sr;        /* MM_F_SR: linear instead of log gap cost in dp_max (map.c:954) */
+	int32_t sam_hit_only; /* MM_F_SAM_HIT_ONLY: no record for unmapped reads */
+	int32_t softclip;     /* MM_F_SOFTCLIP */
+	int32_t n_threads;    /* host threads (0 = all cores) */
+} gd_sr_post_opt_t;
+
+/* For every read of a batch: mm_update_extra (+ mm_fix_cigar), the clip / min_dp_max filter and the ordering of
+ * map.c:956-978, mm_set_sam_params (hit.c:494-557) and mm_write_sam3 (format.c:412-603, single-segment reads):
+ * the SAM records of the batch, in input order, as one malloc'ed text (free with gd_free).
+ * names[i] / seq / qual (qual may be NULL) describe the reads like gd_sr_map_batch's off/len/buf; cand_off, cand,
+ * cigar are its outputs; seq_names / ref_off / ref_len / ref describe the contigs (ASCII) the index was built from. */
+int gd_sr_sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                    const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq,
+                    const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
+                    const gd_sr_post_opt_t *opt, char **sam, size_t *sam_len);
+/* the @SQ lines of mm_write_sam_hdr (format.c:128-137); the @PG line (command line) is the caller's */
+int gd_sam_header(int n_seq, const char *const *seq_names, const int32_t *ref_len, char **sam, size_t *sam_len);
+void gd_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,81 @@
+"""Host logic after the DP (mm_update_extra / mm_fix_cigar, candidate filter, mm_set_sam_params,
+mm_write_sam3) in libgdiet_cuda.so's plain-C++ part, fed with the ORACLE's candidates so that it runs without a GPU,
+against the SAM text of the unmodified reference program (golden fixture + live runs where oracle/_ref travelled)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import gdiet_b200 as gd
+import maplib
+from oraclelib import cpu_has_avx512
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def oracle_candidates(M, contigs, reads, o, Z="10"):
+    mi = M.index_build(contigs, 11, 21, Z)
+    cand_off, cands, cigs, base = [0], [], [], 0
+    for r in reads:
+        c, cig, _ = M.map_read(mi, r, o)
+        c = c.copy()
+        used = int(sum(max(int(x), 0) for x in c["n_cigar"]))
+        c["cigar_off"] += base
+        cands.append(c)
+        cigs.append(cig[:used])
+        base += used
+        cand_off.append(cand_off[-1] + len(c))
+    M.lib.gdo_index_destroy(mi)
+    return (np.array(cand_off, np.int64), np.concatenate(cands) if cands else np.zeros(0, maplib.CAND_DTYPE),
+            np.concatenate(cigs) if cigs else np.zeros(0, np.uint32))
+
+
+def our_sam(contigs, reads, cand_off, cand, cig, post):
+    n, L = reads.shape
+    names = ["r%d" % i for i in range(n)]
+    seq_names = ["chr%d" % (i + 1) for i in range(len(contigs))]
+    off = np.arange(n, dtype=np.int64) * L
+    lens = np.full(n, L, np.int32)
+    qual = np.full(n * L, ord("I"), np.uint8)
+    hdr = gd.sam_header(seq_names, [len(c) for c in contigs])
+    body = gd.sr_sam_batch(names, off, lens, np.ascontiguousarray(reads.reshape(-1)), qual, cand_off, cand, cig, seq_names, contigs, post)
+    return (hdr + body).decode().splitlines()
+
+
+def strip_pg(text):
+    return [l for l in text.splitlines() if not l.startswith("@PG")]
+
+
+def test_sam_golden():
+    g = np.load(os.path.join(GOLDEN, "map_sr.npz"))
+    with gzip.open(os.path.join(GOLDEN, "map_sr.sam.gz"), "rt") as f:
+        want = strip_pg(f.read())
+    contigs, reads = maplib.make_dataset(seed=int(g["seed"]), n_reads=int(g["n_reads"]))
+    o = maplib.sr_opt(min_cnt=float(g["min_cnt"]), rec_frac=float(g["rec_frac"]))
+    M = maplib.MapOracle()
+    cand_off, cand, cig = oracle_candidates(M, contigs, reads, o)
+    got = our_sam(contigs, reads, cand_off, cand, cig, gd.sr_post_options())
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a == b
+
+
+@pytest.mark.skipif(not (maplib.have_ref_program() and cpu_has_avx512()), reason="needs oracle/_ref/GDiet_avx_sr and AVX-512")
+@pytest.mark.parametrize("seed,read_len,extra,okw,pkw", [
+    (41, 150, ["-r", "0.05,150,200"], {}, {}),
+    (42, 150, ["-r", "0.05,150,200", "-n", "0.1", "--secondary=yes"], dict(min_cnt=0.1), dict(no_print_2nd=0)),
+    (43, 400, ["-n", "0.2"], dict(min_cnt=0.2, bw_min=500, bw_max=1500), {}),
+    (44, 100, ["-r", "0.1,20,50", "-n", "0.1", "-Y"], dict(min_cnt=0.1, bw_frac=0.1, bw_min=20, bw_max=50), dict(softclip=1)),
+])
+def test_sam_matches_reference_program(seed, read_len, extra, okw, pkw):
+    contigs, reads = maplib.make_dataset(seed=seed, read_len=read_len, n_reads=1500)
+    o = maplib.sr_opt(qlen=read_len, **okw)
+    sam, _ = maplib.run_reference(contigs, reads, maplib.ref_cmdline(o, extra=extra), trace=False, threads=2)
+    M = maplib.MapOracle()
+    cand_off, cand, cig = oracle_candidates(M, contigs, reads, o)
+    got = our_sam(contigs, reads, cand_off, cand, cig, gd.sr_post_options(**pkw))
+    want = strip_pg(sam)
+    assert len(got) == len(want)
+    bad = [(a, b) for a, b in zip(got, want) if a != b]
+    assert not bad, "%d differing SAM lines, first:\n%s\n%s" % (len(bad), bad[0][0], bad[0][1])

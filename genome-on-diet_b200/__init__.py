@@ -87,18 +87,42 @@ def sr_post_options(n_threads=0, **kw):
 
 
 def _cstr_array(strings):
+    if isinstance(strings, C.Array):
+        return strings
     arr = (C.c_char_p * len(strings))()
     arr[:] = [x if isinstance(x, bytes) else x.encode() for x in strings]
     return arr
 
 
-def sr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, contigs, opt):
-    """gd_sr_sam_batch: SAM records (bytes) of a mapped batch. contigs: list of ASCII uint8 arrays."""
+class SamText:
+    """The malloc'ed SAM text gd_sr_sam_batch returns (a C host writes it out and calls gd_free)."""
+
+    def __init__(self, ptr, n):
+        self.ptr, self.n = ptr, n
+
+    def bytes(self):
+        return C.string_at(self.ptr, self.n)
+
+    def free(self):
+        if self.ptr:
+            load().gd_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.free()
+
+
+def sr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, contigs, opt, raw=False, ref=None):
+    """gd_sr_sam_batch: SAM records of a mapped batch (bytes, or a SamText handle with raw=True).
+    contigs: list of ASCII uint8 arrays; ref = (ref_off, ref_len, concatenated buffer) may be passed to reuse it."""
     L = load()
-    ref_len = np.array([len(c) for c in contigs], np.int32)
-    ref_off = np.zeros(len(contigs), np.int64)
-    ref_off[1:] = np.cumsum(ref_len[:-1].astype(np.int64))
-    ref = np.concatenate([np.ascontiguousarray(c, np.uint8) for c in contigs])
+    if ref is not None:
+        ref_off, ref_len, ref = ref
+    else:
+        ref_len = np.array([len(c) for c in contigs], np.int32)
+        ref_off = np.zeros(len(contigs), np.int64)
+        ref_off[1:] = np.cumsum(ref_len[:-1].astype(np.int64))
+        ref = np.concatenate([np.ascontiguousarray(c, np.uint8) for c in contigs]) if len(contigs) > 1 else np.ascontiguousarray(contigs[0], np.uint8)
     n_arr, s_arr = _cstr_array(names), _cstr_array(seq_names)
     out, out_len = C.c_void_p(), C.c_size_t(0)
     cand = np.ascontiguousarray(cand)
@@ -106,12 +130,15 @@ def sr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, 
     if len(cand) == 0:
         cand = np.zeros(1, SR_CAND_DTYPE)
     rc = L.gd_sr_sam_batch(len(lens), C.cast(n_arr, C.c_void_p), _ptr(off), _ptr(lens), _ptr(seq), _ptr(qual), _ptr(cand_off),
-                           _ptr(cand), _ptr(cigar), len(contigs), C.cast(s_arr, C.c_void_p), _ptr(ref_off), _ptr(ref_len), _ptr(ref),
+                           _ptr(cand), _ptr(cigar), len(ref_len), C.cast(s_arr, C.c_void_p), _ptr(ref_off), _ptr(ref_len), _ptr(ref),
                            C.byref(opt), C.byref(out), C.byref(out_len))
     if rc != GD_OK:
         raise GdietError("gd_sr_sam_batch failed (%d)" % rc)
-    txt = C.string_at(out, out_len.value)
-    L.gd_free(out)
+    h = SamText(out, out_len.value)
+    if raw:
+        return h
+    txt = h.bytes()  # (one more copy, into a Python bytes object)
+    h.free()
     return txt
 
 

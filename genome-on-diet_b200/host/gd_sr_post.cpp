@@ -27,19 +27,28 @@ struct Reg { // the mm_reg1_t / mm_extra_t fields this path touches (minimap.h:1
 	int32_t rid = 0, score = 0, qs = 0, qe = 0, rs = 0, re = 0, rev = 0;
 	int32_t id = 0, parent = 0, mapq = 0, sam_pri = 0, mlen = 0, blen = 0;
 	int32_t dp_score = 0, dp_max = 0, n_ambi = 0;
-	std::vector<uint32_t> cigar;
+	uint32_t *cig = nullptr; // view into the calling thread's scratch (mm_extra_t::cigar)
+	uint32_t n_cig = 0;
 };
 
-inline int nt4(unsigned char c)
-{ // seq_nt4_table, sketch.c:11-18
-	switch (c) {
-	case 'A': case 'a': case 0: return 0;
-	case 'C': case 'c': case 1: return 1;
-	case 'G': case 'g': case 2: return 2;
-	case 'T': case 't': case 'U': case 'u': case 3: return 3;
-	default: return 4;
+struct CigView { // range-for over a Reg's CIGAR
+	const uint32_t *b, *e;
+	const uint32_t *begin() const { return b; }
+	const uint32_t *end() const { return e; }
+};
+inline CigView cigar_of(const Reg &r) { return CigView{r.cig, r.cig + r.n_cig}; }
+
+struct Nt4Table { // seq_nt4_table, sketch.c:11-18
+	uint8_t t[256];
+	Nt4Table()
+	{
+		for (int i = 0; i < 256; ++i) t[i] = 4;
+		t[0] = 0, t[1] = 1, t[2] = 2, t[3] = 3;
+		t['A'] = t['a'] = 0, t['C'] = t['c'] = 1, t['G'] = t['g'] = 2, t['T'] = t['t'] = t['U'] = t['u'] = 3;
 	}
-}
+};
+const Nt4Table g_nt4;
+inline int nt4(unsigned char c) { return g_nt4.t[c]; }
 
 struct CompTable { // seq_comp_table, bseq.c:11-28: IUPAC complement, case preserved, everything else unchanged
 	unsigned char t[256];
@@ -71,12 +80,12 @@ inline float mg_log2(float x)
 // align.c:93-172
 void fix_cigar(Reg &r, const uint8_t *qseq, const uint8_t *tseq, int *qshift, int *tshift)
 {
-	std::vector<uint32_t> &c = r.cigar;
+	uint32_t *c = r.cig;
 	int32_t toff = 0, qoff = 0;
 	bool shrink = false;
 	*qshift = *tshift = 0;
-	if (c.size() <= 1) return;
-	const uint32_t n = (uint32_t)c.size();
+	if (r.n_cig <= 1) return;
+	const uint32_t n = r.n_cig;
 	for (uint32_t k = 0; k < n; ++k) { // indel left alignment
 		const uint32_t op = c[k] & 0xf, len = c[k] >> 4;
 		if (len == 0) shrink = true;
@@ -112,15 +121,14 @@ void fix_cigar(Reg &r, const uint8_t *qseq, const uint8_t *tseq, int *qshift, in
 		}
 	}
 	if (shrink) {
-		size_t l = 0;
-		for (size_t k = 0; k < c.size(); ++k) // squeeze out zero-length operations
+		uint32_t l = 0, m = n;
+		for (uint32_t k = 0; k < m; ++k) // squeeze out zero-length operations
 			if (c[k] >> 4 != 0) c[l++] = c[k];
-		c.resize(l);
-		l = 0;
-		for (size_t k = 0; k < c.size(); ++k) // merge equal neighbours
-			if (k == c.size() - 1 || (c[k] & 0xf) != (c[k + 1] & 0xf)) c[l++] = c[k];
+		m = l, l = 0;
+		for (uint32_t k = 0; k < m; ++k) // merge equal neighbours
+			if (k == m - 1 || (c[k] & 0xf) != (c[k + 1] & 0xf)) c[l++] = c[k];
 			else c[k + 1] += c[k] >> 4 << 4;
-		c.resize(l);
+		r.n_cig = l;
 	}
 	if ((c[0] & 0xf) == OP_I || (c[0] & 0xf) == OP_D) { // drop a leading I or D
 		const int32_t l = (int32_t)(c[0] >> 4);
@@ -129,20 +137,22 @@ void fix_cigar(Reg &r, const uint8_t *qseq, const uint8_t *tseq, int *qshift, in
 			else r.qs += l;
 			*qshift = l;
 		} else r.rs += l, *tshift = l;
-		c.erase(c.begin());
+		++r.cig, --r.n_cig;
 	}
 }
 
-// align.c:259-318 (is_eqx = 0)
-void update_extra(Reg &r, const uint8_t *qseq, const uint8_t *tseq, const int8_t *mat, int8_t q, int8_t e, int log_gap)
+// align.c:259-318 (is_eqx = 0).  Acc = double is the reference's arithmetic; with the linear gap cost of the sr
+// preset every term is a small integer, for which Acc = int32_t gives the same values without the floating-point
+// dependency chain.
+template <class Acc> void update_extra_t(Reg &r, const uint8_t *qseq, const uint8_t *tseq, const int8_t *mat, int8_t q, int8_t e, int log_gap)
 {
 	int qshift, tshift;
 	int32_t toff = 0, qoff = 0;
-	double s = 0.0, mx = 0.0;
+	Acc s = 0, mx = 0;
 	fix_cigar(r, qseq, tseq, &qshift, &tshift);
 	qseq += qshift, tseq += tshift;
 	r.blen = r.mlen = 0;
-	for (uint32_t cg : r.cigar) {
+	for (uint32_t cg : cigar_of(r)) {
 		const uint32_t op = cg & 0xf, len = cg >> 4;
 		if (op == OP_M) {
 			int n_ambi = 0, n_diff = 0;
@@ -165,7 +175,7 @@ void update_extra(Reg &r, const uint8_t *qseq, const uint8_t *tseq, const int8_t
 			for (uint32_t l = 0; l < len; ++l)
 				if (sq[l] > 3) ++n_ambi;
 			r.blen += len - n_ambi, r.n_ambi += n_ambi;
-			if (log_gap) s -= q + (double)e * mg_log2(1.0f + len);
+			if (log_gap) s -= (Acc)(q + (double)e * mg_log2(1.0f + len));
 			else s -= q + e;
 			if (s < 0) s = 0;
 			if (op == OP_I) qoff += len;
@@ -174,11 +184,15 @@ void update_extra(Reg &r, const uint8_t *qseq, const uint8_t *tseq, const int8_t
 	}
 	r.dp_max = (int32_t)(mx + .499);
 }
+void update_extra(Reg &r, const uint8_t *qseq, const uint8_t *tseq, const int8_t *mat, int8_t q, int8_t e, int log_gap)
+{
+	if (log_gap) update_extra_t<double>(r, qseq, tseq, mat, q, e, 1);
+	else update_extra_t<int32_t>(r, qseq, tseq, mat, q, e, 0);
+}
 
 // hit.c:494-557
-void set_sam_params(std::vector<Reg> &regs, unsigned qlen, unsigned match_score, unsigned max_nb_sec)
+void set_sam_params(Reg *regs, int n_regs, unsigned qlen, unsigned match_score, unsigned max_nb_sec)
 {
-	const int n_regs = (int)regs.size();
 	const int supp_threshold = (int)(0.8 * (float)(regs[0].qe - regs[0].qs));
 	unsigned nb_sec = 0;
 	int dp_max2 = 0;
@@ -213,26 +227,57 @@ void set_sam_params(std::vector<Reg> &regs, unsigned qlen, unsigned match_score,
 	regs[0].mapq = (int32_t)(mapq & 0xff); // 8-bit field
 }
 
-inline void put_int(std::string &s, long v)
+struct Out { // append-only text buffer; need() once per record, then unchecked pointer bumps
+	char *b = nullptr;
+	size_t n = 0, cap = 0;
+	~Out() { free(b); }
+	void need(size_t k)
+	{
+		if (n + k <= cap) return;
+		cap = std::max(cap * 2, n + k + 4096);
+		b = (char *)realloc(b, cap);
+		if (!b) abort();
+	}
+	size_t size() const { return n; }
+	const char *data() const { return b; }
+	Out &operator+=(char c) { return b[n++] = c, *this; }
+	Out &operator+=(const char *s)
+	{
+		while (*s) b[n++] = *s++;
+		return *this;
+	}
+	void append(const char *s, size_t l) { memcpy(b + n, s, l), n += l; }
+};
+
+inline void put_int(Out &s, long v)
 {
 	char b[24];
-	snprintf(b, sizeof b, "%ld", v);
-	s += b;
+	int i = 24;
+	unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+	do b[--i] = (char)('0' + u % 10), u /= 10;
+	while (u);
+	if (v < 0) b[--i] = '-';
+	s.append(b + i, (size_t)(24 - i));
 }
 
-void put_seq(std::string &s, const char *seq, int l, int rev, int comp)
+void put_seq(Out &s, const char *seq, int l, int rev, int comp)
 { // sam_write_sq, format.c:349-360
 	if (!rev) {
 		s.append(seq, (size_t)l);
 		return;
 	}
-	for (int i = 0; i < l; ++i) {
-		const int c = seq[l - 1 - i];
-		s += (char)((c >= 0 && c < 128 && comp) ? g_comp.t[c] : c);
-	}
+	char *d = s.b + s.n;
+	if (comp)
+		for (int i = 0; i < l; ++i) {
+			const int c = seq[l - 1 - i];
+			d[i] = (char)((c >= 0 && c < 128) ? g_comp.t[c] : c);
+		}
+	else
+		for (int i = 0; i < l; ++i) d[i] = seq[l - 1 - i];
+	s.n += (size_t)l;
 }
 
-void put_tags(std::string &s, const Reg &r)
+void put_tags(Out &s, const Reg &r)
 { // write_tags, format.c:302-338 (inv = 0, cnt = 0, subsc = 0, split = 0 on this path)
 	s += "\tNM:i:", put_int(s, r.blen - r.mlen + r.n_ambi);
 	s += "\tms:i:", put_int(s, r.dp_max);
@@ -242,13 +287,24 @@ void put_tags(std::string &s, const Reg &r)
 	s += "\tcm:i:0\ts1:i:", put_int(s, r.score);
 	if (r.parent == r.id) s += "\ts2:i:0";
 	int32_t n_gap = 0, n_gapo = 0; // mm_event_identity, align.c:949-966
-	for (uint32_t cg : r.cigar)
+	for (uint32_t cg : cigar_of(r))
 		if ((cg & 0xf) == OP_I || (cg & 0xf) == OP_D) ++n_gapo, n_gap += (int32_t)(cg >> 4);
-	const double div = 1.0 - (double)r.mlen / (r.blen + r.n_ambi - n_gap + n_gapo);
-	char b[32];
-	if (div == 0.0) b[0] = '0', b[1] = 0;
-	else snprintf(b, 16, "%.4f", div);
-	s += "\tde:f:", s += b;
+	// "%.4f" of 1 - mlen/den: the value depends on two small integers, and neighbouring reads repeat them, so the
+	// printf result is kept in a small per-thread direct-mapped table
+	const int32_t den = r.blen + r.n_ambi - n_gap + n_gapo;
+	struct DeMemo {
+		int32_t mlen, den;
+		char txt[16];
+	};
+	static thread_local DeMemo memo[256];
+	DeMemo &m = memo[((uint32_t)r.mlen * 31u + (uint32_t)den) & 255u];
+	if (m.mlen != r.mlen || m.den != den || m.txt[0] == 0) {
+		const double div = 1.0 - (double)r.mlen / den;
+		m.mlen = r.mlen, m.den = den;
+		if (div == 0.0) m.txt[0] = '0', m.txt[1] = 0;
+		else snprintf(m.txt, 16, "%.4f", div);
+	}
+	s += "\tde:f:", s += (const char *)m.txt;
 }
 
 struct Ctx {
@@ -268,7 +324,13 @@ struct Ctx {
 	const gd_sr_post_opt_t *o;
 };
 
-void one_read(const Ctx &C, int i, std::string &out)
+struct Scratch { // per-thread, reused across reads
+	std::vector<Reg> regs;
+	std::vector<uint8_t> qs, ts;
+	std::vector<uint32_t> cig;
+};
+
+void one_read(const Ctx &C, int i, Out &out, Scratch &T)
 {
 	const gd_sr_post_opt_t &o = *C.o;
 	const int qlen = C.len[i];
@@ -278,29 +340,45 @@ void one_read(const Ctx &C, int i, std::string &out)
 	const int g = o.a, bb = o.b < 0 ? o.b : -o.b;
 	for (int x = 0; x < 5; ++x)
 		for (int y = 0; y < 5; ++y) mat[x * 5 + y] = (int8_t)((x == 4 || y == 4) ? 0 : (x == y ? g : bb));
-	std::vector<Reg> regs;
-	std::vector<uint8_t> qs, ts;
+	std::vector<Reg> &regs = T.regs;
+	std::vector<uint8_t> &qs = T.qs, &ts = T.ts;
+	regs.clear();
+	size_t ncig = 0;
+	for (int64_t ci = C.cand_off[i]; ci < C.cand_off[i + 1]; ++ci) ncig += C.cand[ci].n_cigar > 0 ? (size_t)C.cand[ci].n_cigar : 0;
+	if (T.cig.size() < ncig + 1) T.cig.resize(2 * ncig + 64);
+	uint32_t *cig_next = T.cig.data();
 	for (int64_t ci = C.cand_off[i]; ci < C.cand_off[i + 1]; ++ci) { // map.c:932-978
 		const gd_sr_cand_t &c = C.cand[ci];
 		Reg r = Reg();
 		r.rid = c.rid, r.score = c.score, r.qs = c.qs, r.qe = c.qe, r.rs = c.rs, r.re = c.re, r.rev = c.rev;
 		r.dp_score = c.score;
-		if (c.n_cigar > 0) r.cigar.assign(C.cigar + c.cigar_off, C.cigar + c.cigar_off + c.n_cigar);
+		if (c.n_cigar > 0) {
+			memcpy(cig_next, C.cigar + c.cigar_off, (size_t)c.n_cigar * 4);
+			r.cig = cig_next, r.n_cig = (uint32_t)c.n_cigar, cig_next += c.n_cigar;
+		}
 		const int n = c.qe - c.qs, tl = c.re - c.rs;
 		qs.resize((size_t)n + 1), ts.resize((size_t)tl + 1);
-		for (int j = 0; j < n; ++j) qs[j] = (uint8_t)(c.rev ? nt4((unsigned char)rd[c.qe - 1 - j]) ^ 3 : nt4((unsigned char)rd[c.qs + j]));
-		const char *tp = C.ref + C.ref_off[c.rid] + c.rs;
-		for (int j = 0; j < tl; ++j) ts[j] = (uint8_t)nt4((unsigned char)tp[j]);
+		{ // map.c:737-757
+			uint8_t *qd = qs.data(), *td = ts.data();
+			const unsigned char *src = (const unsigned char *)rd, *tp = (const unsigned char *)C.ref + C.ref_off[c.rid] + c.rs;
+			if (c.rev)
+				for (int j = 0; j < n; ++j) qd[j] = g_nt4.t[src[c.qe - 1 - j]] ^ 3;
+			else
+				for (int j = 0; j < n; ++j) qd[j] = g_nt4.t[src[c.qs + j]];
+			for (int j = 0; j < tl; ++j) td[j] = g_nt4.t[tp[j]];
+		}
 		update_extra(r, qs.data(), ts.data(), mat, (int8_t)o.q, (int8_t)o.e, !o.is_sr);
 		const uint32_t clip0 = r.rev ? (uint32_t)(qlen - r.qe) : (uint32_t)r.qs, clip1 = r.rev ? (uint32_t)r.qs : (uint32_t)(qlen - r.qe);
 		if (!(clip0 < (uint32_t)qlen && clip1 < (uint32_t)qlen) || r.dp_score < o.min_dp_max) continue;
-		regs.push_back(std::move(r));
+		regs.push_back(r);
 		for (size_t k = regs.size() - 1; k > 0 && regs[k].score > regs[k - 1].score; --k) std::swap(regs[k], regs[k - 1]);
 	}
-	if (!regs.empty()) set_sam_params(regs, (unsigned)qlen, (unsigned)o.a, o.no_print_2nd ? 0u : (unsigned)o.best_n);
+	if (!regs.empty()) set_sam_params(regs.data(), (int)regs.size(), (unsigned)qlen, (unsigned)o.a, o.no_print_2nd ? 0u : (unsigned)o.best_n);
 	// ---- format.c:412-603 with n_seg == 1
+	const size_t name_len = strlen(name);
 	if (regs.empty()) {
 		if (o.sam_hit_only) return;
+		out.need(name_len + 2 * (size_t)qlen + 64);
 		out += name, out += "\t4\t*\t0\t0\t*\t*\t0\t0\t";
 		out.append(rd, (size_t)qlen), out += '\t';
 		if (ql) out.append(ql, (size_t)qlen);
@@ -311,6 +389,7 @@ void one_read(const Ctx &C, int i, std::string &out)
 	for (size_t j = 0; j < regs.size(); ++j) {
 		const Reg &r = regs[j];
 		if (o.no_print_2nd && r.id != r.parent) continue; // map.c:1236
+		out.need(name_len + 2 * (size_t)qlen + 12 * (size_t)r.n_cig + 512 + strlen(C.seq_names[r.rid]));
 		int flag = 0;
 		if (r.rev) flag |= 0x10;
 		if (r.parent != r.id) flag |= 0x100;
@@ -320,7 +399,7 @@ void one_read(const Ctx &C, int i, std::string &out)
 		const uint32_t clip0 = r.rev ? (uint32_t)(qlen - r.qe) : (uint32_t)r.qs, clip1 = r.rev ? (uint32_t)r.qs : (uint32_t)(qlen - r.qe);
 		const char clip_char = ((flag & 0x800) && !o.softclip) ? 'H' : 'S';
 		if (clip0) put_int(out, clip0), out += clip_char;
-		for (uint32_t cg : r.cigar) put_int(out, cg >> 4), out += "MIDNSHP=XB"[cg & 0xf];
+		for (uint32_t cg : cigar_of(r)) put_int(out, cg >> 4), out += "MIDNSHP=XB"[cg & 0xf];
 		if (clip1) put_int(out, clip1), out += clip_char;
 		out += "\t*\t0\t0\t";
 		if ((flag & 0x900) == 0 || o.softclip) {
@@ -343,6 +422,7 @@ void one_read(const Ctx &C, int i, std::string &out)
 				for (size_t k = 0; k < regs.size(); ++k) {
 					const Reg &q = regs[k];
 					if (k == j || q.parent != q.id) continue;
+					out.need(strlen(C.seq_names[q.rid]) + 160);
 					int l_M, l_I = 0, l_D = 0;
 					if (q.qe - q.qs < q.re - q.rs) l_M = q.qe - q.qs, l_D = (q.re - q.rs) - l_M;
 					else l_M = q.re - q.rs, l_I = (q.qe - q.qs) - l_M;
@@ -357,11 +437,14 @@ void one_read(const Ctx &C, int i, std::string &out)
 				}
 			}
 		}
+		out.need(16);
 		out += "\trl:i:0\n";
 	}
 }
 
 } // namespace
+
+static void put_int(std::string &s, long v) { s += std::to_string(v); }
 
 extern "C" int gd_sam_header(int n_seq, const char *const *seq_names, const int32_t *ref_len, char **sam, size_t *sam_len)
 { // mm_write_sam_hdr, format.c:128-137 (the @PG line carries the command line and is the caller's)
@@ -387,24 +470,28 @@ extern "C" int gd_sr_sam_batch(int n, const char *const *names, const int64_t *o
 	Ctx C = {n, names, off, len, seq, qual, cand_off, cand, cigar, n_seq, seq_names, ref_off, ref_len, ref, opt};
 	int nt = opt->n_threads > 0 ? opt->n_threads : (int)std::thread::hardware_concurrency();
 	nt = std::max(1, std::min(nt, (n + 255) / 256));
-	std::vector<std::string> parts((size_t)nt);
+	std::vector<Out> parts((size_t)nt);
 	auto work = [&](int t) { // contiguous read ranges: the concatenation is in input order
 		const int64_t b = (int64_t)n * t / nt, e = (int64_t)n * (t + 1) / nt;
-		parts[t].reserve((size_t)(e - b) * 512);
-		for (int64_t i = b; i < e; ++i) one_read(C, (int)i, parts[t]);
+		Scratch T;
+		parts[t].need((size_t)(e - b) * 520 + 4096);
+		for (int64_t i = b; i < e; ++i) one_read(C, (int)i, parts[t], T);
 	};
-	if (nt == 1) work(0);
-	else {
-		std::vector<std::thread> th;
-		for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
-		for (auto &x : th) x.join();
-	}
-	size_t total = 0;
-	for (auto &p : parts) total += p.size();
+	auto run = [&](auto &&f) {
+		if (nt == 1) f(0);
+		else {
+			std::vector<std::thread> th;
+			for (int t = 0; t < nt; ++t) th.emplace_back(f, t);
+			for (auto &x : th) x.join();
+		}
+	};
+	run(work);
+	std::vector<size_t> at((size_t)nt + 1, 0);
+	for (int t = 0; t < nt; ++t) at[t + 1] = at[t] + parts[t].size();
+	const size_t total = at[nt];
 	char *buf = (char *)malloc(total + 1);
 	if (!buf) return GD_ERR_ARG;
-	size_t w = 0;
-	for (auto &p : parts) memcpy(buf + w, p.data(), p.size()), w += p.size();
+	run([&](int t) { memcpy(buf + at[t], parts[t].data(), parts[t].size()); }); // first touch + copy on every core
 	buf[total] = 0;
 	*sam = buf, *sam_len = total;
 	return GD_OK;

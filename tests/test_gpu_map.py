@@ -131,3 +131,22 @@ def test_sr_map_empty_and_unmappable(ctx):
     coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, o)
     assert len(cand) == 0 and np.all(coff == 0)
     idx.close()
+
+
+def test_sam_end_to_end_golden(ctx):
+    """Device mapping stage + host post-processing: the SAM text equals the reference program's, byte for byte."""
+    import gzip
+    import gdiet_b200 as gd
+    g = np.load(os.path.join(GOLDEN, "map_sr.npz"))
+    with gzip.open(os.path.join(GOLDEN, "map_sr.sam.gz"), "rt") as f:
+        want = [l for l in f.read().splitlines() if not l.startswith("@")]
+    contigs, reads = maplib.make_dataset(seed=int(g["seed"]), n_reads=int(g["n_reads"]))
+    o = maplib.sr_opt(min_cnt=float(g["min_cnt"]), rec_frac=float(g["rec_frac"]))
+    idx = ctx.index_build(contigs, 11, 21, "10")
+    off, lens, buf = flat_reads(reads)
+    coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, o)
+    names = ["r%d" % i for i in range(len(reads))]
+    qual = np.full(len(buf), ord("I"), np.uint8)
+    sam = gd.sr_sam_batch(names, off, lens, buf, qual, coff, cand, cig, ["chr1", "chr2", "chr3"], contigs, gd.sr_post_options())
+    assert sam.decode().splitlines() == want
+    idx.close()

@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""BASELINE config 1 end to end: `-ax sr -Z 10 -W 2 -k 21 -w 11 -r 0.05,150,200`, synthetic 150 bp reads against a
+synthetic reference.  Ours: index build on the device, then per batch gd_sr_map_batch (sketch -> lookup -> vote ->
+windows -> exact match / DP, all on the GPU) + gd_sr_sam_batch (post-processing + SAM text on the host cores); the
+SAM text is compared with the unmodified reference program (oracle/_ref/GDiet_avx_sr -t <cores>) run on the same
+files in the same process, whose [PROFILING]/Real-time lines give the CPU baseline.  Prints one JSON line."""
+import json, os, re, subprocess, sys, tempfile, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import gdiet_b200 as gd
+from gdiet_b200 import synth
+
+
+def main():
+    ref_mbp = float(sys.argv[1]) if len(sys.argv) > 1 else 5
+    n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
+    run_ref = (sys.argv[3] != "noref") if len(sys.argv) > 3 else True
+    cores = len(os.sched_getaffinity(0))
+    genome = synth.random_genome(int(ref_mbp * 1e6), seed=1)
+    reads = synth.sample_reads(genome, n_reads, 150, seed=2)
+    contigs = [genome]
+    name_list = ["r%d" % i for i in range(n_reads)]
+    names = gd._cstr_array(name_list)  # a C host already holds char* names
+    nb_ = max(1, min(8, n_reads // 100_000))
+    C_names = [gd._cstr_array(name_list[n_reads * b // nb_: n_reads * (b + 1) // nb_]) for b in range(nb_)]
+    off = np.arange(n_reads, dtype=np.int64) * 150
+    lens = np.full(n_reads, 150, np.int32)
+    buf = np.ascontiguousarray(reads.reshape(-1))
+    qual = np.full(n_reads * 150, ord("I"), np.uint8)
+    opt, post = gd.sr_options(), gd.sr_post_options()
+    ctx = gd.Context(0)
+    t0 = time.perf_counter()
+    idx = ctx.index_build(contigs, 11, 21, "10")
+    t_index = time.perf_counter() - t0
+    res = {}
+    for it in range(4):  # first pass warms the context's staging buffers
+        l0 = ctx.stat("kernel_launches")
+        t0 = time.perf_counter()
+        coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, opt, cand_cap=n_reads + 1024, cigar_cap=8 * n_reads + 1024)
+        t1 = time.perf_counter()
+        h = gd.sr_sam_batch(names, off, lens, buf, qual, coff, cand, cig, ["chr1"], contigs, post, raw=True)
+        t2 = time.perf_counter()
+        sam = h.bytes() if it == 3 else b""
+        h.free()
+        res = dict(map_s=t1 - t0, sam_s=t2 - t1, launches=ctx.stat("kernel_launches") - l0)
+    # ---- pipelined: the device stage of batch i+1 overlaps the host stage (post-processing + SAM text) of batch i
+    import threading, queue
+    nb = max(1, min(8, n_reads // 100_000))
+    bounds = [n_reads * b // nb for b in range(nb + 1)]
+    ctx2 = ctx
+
+    def producer(q):
+        for b in range(nb):
+            lo, hi = bounds[b], bounds[b + 1]
+            o_b = off[lo:hi] - off[lo]
+            r = ctx2.sr_map_batch(idx, o_b, lens[lo:hi], buf[off[lo]:off[lo] + (hi - lo) * 150], opt, cand_cap=(hi - lo) + 1024,
+                                  cigar_cap=8 * (hi - lo) + 1024)
+            q.put((b, r))
+        q.put(None)
+
+    pipe_s = None
+    for it in range(2):
+        q = queue.Queue(maxsize=2)
+        t0 = time.perf_counter()
+        th = threading.Thread(target=producer, args=(q,))
+        th.start()
+        total_bytes = 0
+        while True:
+            item = q.get()
+            if item is None:
+                break
+            b, (co, ca, cg) = item
+            lo, hi = bounds[b], bounds[b + 1]
+            h = gd.sr_sam_batch(gd._cstr_array(names[lo:hi]) if False else (C_names[b]), off[lo:hi] - off[lo], lens[lo:hi], buf[off[lo]:off[lo] + (hi - lo) * 150],
+                                qual[off[lo]:off[lo] + (hi - lo) * 150], co, ca, cg, ["chr1"], contigs, post, raw=True)
+            total_bytes += h.n
+            h.free()
+        th.join()
+        pipe_s = time.perf_counter() - t0
+    out = {"what": "config 1: sr end to end", "ref_bp": len(genome), "reads": n_reads, "index_build_s": round(t_index, 4),
+           "index_minimizers": idx.stat("n_minimizers"), "map_batch_s": round(res["map_s"], 4), "sam_s": round(res["sam_s"], 4),
+           "reads_per_s_serial": n_reads / (res["map_s"] + res["sam_s"]), "pipelined_s": round(pipe_s, 4), "pipeline_batches": nb,
+           "reads_per_s": n_reads / pipe_s, "reads_per_s_map_only": n_reads / res["map_s"],
+           "candidates": int(coff[-1]), "exact": int(cand["exact"].sum()), "gpu_launches_per_batch": res["launches"], "host_cores": cores}
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_avx_sr")
+    if run_ref and os.path.exists(ref_bin):
+        import maplib
+        tmp = tempfile.mkdtemp(prefix="gdref_")
+        fa, fq, samf = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq"), os.path.join(tmp, "out.sam")
+        maplib.write_fasta(fa, contigs)
+        maplib.write_fastq(fq, reads)
+        t0 = time.perf_counter()
+        p = subprocess.run([ref_bin, "-t", str(cores), "-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200",
+                            "-o", samf, fa, fq], capture_output=True, text=True)
+        wall = time.perf_counter() - t0
+        prof = dict(re.findall(r"\[PROFILING\] (.+?) time: (\d+) ns", p.stderr))
+        t_idx = int(prof.get("indexing", 0)) * 1e-9
+        want = [l for l in open(samf).read().splitlines() if not l.startswith("@")]
+        got = sam.decode().splitlines()
+        out["reference"] = {"wall_s": round(wall, 3), "indexing_s": round(t_idx, 3), "reads_per_s": n_reads / max(wall - t_idx, 1e-9),
+                            "threads": cores, "profile_thread_seconds": {k: round(int(v) * 1e-9, 3) for k, v in prof.items()}}
+        out["sam_identical"] = got == want
+        out["sam_lines"] = len(want)
+        if got != want:
+            bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+            out["sam_first_diff"] = [got[bad[0]][:300], want[bad[0]][:300]] if bad else ["length", "%d vs %d" % (len(got), len(want))]
+    print(json.dumps(out), flush=True)
+    idx.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -322,13 +322,22 @@ def ours(args, rank, world, local_rank):
                     sk["cpu_baseline"] = {"kind": "unavailable", "sample": str(e)}
         except Exception as e:
             sk = {"error": str(e)}
+    # ---- BASELINE config 1 (sr end to end: device mapping stage + host SAM records), rank 0, bounded
+    srm = None
+    if not args.no_sketch and world == 1:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import sr_map_bench
+            srm = sr_map_bench.run(ctx, 5, 100_000, run_ref=not args.no_cpu)
+        except Exception as e:
+            srm = {"error": str(e)}
     line = {"metric": "ksw_extd2 GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
             "data": "synthetic", "config": workload_config(args, n),
             "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
             "extra": {"ksw_group_lanes": ctx.stat("ksw_group"), "ksw_ring_columns": ctx.stat("ksw_ring"), "chunks_per_step": ctx.stat("ksw_chunks"),
-                      "zdropped_frac": float((ez["zdropped"] != 0).mean()), "cells_per_step": tot_cells, "sketch": sk}}
+                      "zdropped_frac": float((ez["zdropped"] != 0).mean()), "cells_per_step": tot_cells, "sketch": sk, "sr_map": srm}}
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()

@@ -71,6 +71,14 @@ class gd_sr_opt_t(C.Structure):
                 ("zdrop", C.c_int32), ("end_bonus", C.c_int32)]
 
 
+GD_INDEX_NBUF = 7
+
+
+class gd_index_meta_t(C.Structure):
+    _fields_ = [(f, C.c_int64) for f in ("n_seq", "total_len", "n_minimizers", "n_keys", "table_slots", "s_words")] + [
+        ("w", C.c_int32), ("k", C.c_int32)]
+
+
 class gd_sr_post_opt_t(C.Structure):
     """include/gdiet_cuda.h: options of the host side after the DP (GDiet-ShortReads/map.c:954-984)."""
     _fields_ = [(f, C.c_int32) for f in ("a", "b", "q", "e", "min_dp_max", "best_n", "no_print_2nd", "is_sr", "sam_hit_only",
@@ -192,7 +200,7 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
-           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free"]
+           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit"]
 
 
 def load():
@@ -256,6 +264,14 @@ def load():
     L.gd_index_cal_max_occ.argtypes = [vp, vp, C.c_float, C.POINTER(C.c_int32)]
     L.gd_sr_map_batch.restype = i32
     L.gd_sr_map_batch.argtypes = [vp, vp, i32, vp, vp, vp, C.POINTER(gd_sr_opt_t), vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.gd_index_meta.restype = i32
+    L.gd_index_meta.argtypes = [vp, C.POINTER(gd_index_meta_t)]
+    L.gd_index_alloc.restype = i32
+    L.gd_index_alloc.argtypes = [vp, C.POINTER(gd_index_meta_t), C.POINTER(vp)]
+    L.gd_index_buffers.restype = i32
+    L.gd_index_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.gd_index_commit.restype = i32
+    L.gd_index_commit.argtypes = [vp, vp]
     L.gd_sr_sam_batch.restype = i32
     L.gd_sr_sam_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
                                   C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -489,6 +505,26 @@ class Index:
         self.ctx._check(self.ctx.lib.gd_index_export(self.ctx.h, self.h, _ptr(keys), _ptr(counts), _ptr(pos), _ptr(S)),
                         "gd_index_export")
         return keys, counts, pos, S
+
+    def meta(self):
+        m = gd_index_meta_t()
+        self.ctx._check(self.ctx.lib.gd_index_meta(self.h, C.byref(m)), "gd_index_meta")
+        return m
+
+    def buffers(self):
+        """[(device pointer, bytes)] of the GD_INDEX_NBUF device buffers."""
+        ptrs, nb = (C.c_void_p * GD_INDEX_NBUF)(), (C.c_size_t * GD_INDEX_NBUF)()
+        self.ctx._check(self.ctx.lib.gd_index_buffers(self.h, ptrs, nb), "gd_index_buffers")
+        return [(int(ptrs[i] or 0), int(nb[i])) for i in range(GD_INDEX_NBUF)]
+
+    @staticmethod
+    def alloc(ctx, meta):
+        h = C.c_void_p()
+        ctx._check(ctx.lib.gd_index_alloc(ctx.h, C.byref(meta), C.byref(h)), "gd_index_alloc")
+        return Index(ctx, h)
+
+    def commit(self):
+        self.ctx._check(self.ctx.lib.gd_index_commit(self.ctx.h, self.h), "gd_index_commit")
 
     def cal_max_occ(self, frac):
         v = C.c_int32(0)

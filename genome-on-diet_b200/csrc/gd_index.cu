@@ -341,3 +341,75 @@ extern "C" int gd_index_cal_max_occ(gd_ctx *ctx, const gd_index *idx, float frac
 	*max_occ = (int32_t)(v + 1);
 	return GD_OK;
 }
+
+// --------------------------------------------------------------------------------------------
+// replication onto the other GPUs of the node: the index is built once, its device buffers are
+// broadcast by the caller's communicator (ncclBroadcast over NVLink), every GPU then maps its own read shard
+// --------------------------------------------------------------------------------------------
+extern "C" int gd_index_meta(const gd_index *idx, gd_index_meta_t *m)
+{
+	if (!idx || !m) return GD_ERR_ARG;
+	m->n_seq = idx->n_seq, m->total_len = idx->total_len, m->n_minimizers = idx->n_min, m->n_keys = idx->n_keys;
+	m->table_slots = idx->tab_slots, m->s_words = idx->s_words, m->w = idx->d.w, m->k = idx->d.k;
+	return GD_OK;
+}
+
+static void index_buffer_list(gd_index *idx, void **ptrs, size_t *bytes)
+{
+	ptrs[0] = idx->d_tab, bytes[0] = (size_t)idx->tab_slots * sizeof(IdxSlot);
+	ptrs[1] = idx->d_pos, bytes[1] = (size_t)idx->n_min * 8;
+	ptrs[2] = idx->d_S, bytes[2] = (size_t)idx->s_words * 4;
+	ptrs[3] = idx->d_seq_off, bytes[3] = (size_t)(idx->n_seq + 1) * 8;
+	ptrs[4] = idx->d_seq_len, bytes[4] = (size_t)idx->n_seq * 4;
+	ptrs[5] = idx->d_keys, bytes[5] = (size_t)idx->n_keys * 8;
+	ptrs[6] = idx->d_counts, bytes[6] = (size_t)idx->n_keys * 4;
+}
+
+extern "C" int gd_index_buffers(gd_index *idx, void **ptrs, size_t *bytes)
+{
+	if (!idx || !ptrs || !bytes) return GD_ERR_ARG;
+	index_buffer_list(idx, ptrs, bytes);
+	return GD_OK;
+}
+
+extern "C" int gd_index_alloc(gd_ctx *ctx, const gd_index_meta_t *m, gd_index **out)
+{
+	if (!ctx || !m || !out || m->n_seq <= 0 || m->table_slots <= 0 || (m->table_slots & (m->table_slots - 1))) {
+		if (ctx) ctx->err = "gd_index_alloc: bad argument";
+		return GD_ERR_ARG;
+	}
+	*out = nullptr;
+	cudaSetDevice(ctx->device);
+	gd_index *idx = new gd_index();
+	idx->device = ctx->device, idx->n_seq = m->n_seq, idx->total_len = m->total_len, idx->n_min = m->n_minimizers;
+	idx->n_keys = m->n_keys, idx->tab_slots = m->table_slots, idx->s_words = m->s_words;
+	idx->d.w = m->w, idx->d.k = m->k, idx->d.n_seq = (int32_t)m->n_seq;
+	void *ptrs[GD_INDEX_NBUF];
+	size_t bytes[GD_INDEX_NBUF];
+	index_buffer_list(idx, ptrs, bytes);
+	void **slots[GD_INDEX_NBUF] = {&idx->d_tab, &idx->d_pos, &idx->d_S, &idx->d_seq_off, &idx->d_seq_len, &idx->d_keys, &idx->d_counts};
+	for (int i = 0; i < GD_INDEX_NBUF; ++i) {
+		if (cudaMalloc(slots[i], bytes[i] + 16) != cudaSuccess) {
+			ctx->err = "gd_index_alloc: out of device memory";
+			gd_index_destroy(idx);
+			return GD_ERR_CUDA;
+		}
+		idx->device_bytes += bytes[i];
+	}
+	*out = idx;
+	return GD_OK;
+}
+
+extern "C" int gd_index_commit(gd_ctx *ctx, gd_index *idx)
+{ // after the buffers of an allocated index have been filled: host copies of the contig table, kernel view
+	if (!ctx || !idx) return GD_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	free(idx->h_seq_len), free(idx->h_seq_off);
+	idx->h_seq_len = (uint32_t *)malloc((size_t)idx->n_seq * 4), idx->h_seq_off = (uint64_t *)malloc((size_t)(idx->n_seq + 1) * 8);
+	GD_CUDA_OK(ctx, cudaMemcpy(idx->h_seq_len, idx->d_seq_len, (size_t)idx->n_seq * 4, cudaMemcpyDeviceToHost));
+	GD_CUDA_OK(ctx, cudaMemcpy(idx->h_seq_off, idx->d_seq_off, (size_t)(idx->n_seq + 1) * 8, cudaMemcpyDeviceToHost));
+	idx->d.tab = (const IdxSlot *)idx->d_tab, idx->d.tab_mask = (uint64_t)idx->tab_slots - 1;
+	idx->d.pos = (const uint64_t *)idx->d_pos, idx->d.S = (const uint32_t *)idx->d_S;
+	idx->d.seq_off = (const uint64_t *)idx->d_seq_off, idx->d.seq_len = (const uint32_t *)idx->d_seq_len;
+	return GD_OK;
+}

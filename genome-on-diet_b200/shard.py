@@ -54,3 +54,40 @@ def gather_in_order(local, device="cpu", group=None):
         return None, None
     out = np.concatenate([p.cpu().numpy()[: int(s)] for p, s in zip(parts, sizes)])
     return out, np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+class _DeviceBytes:
+    """A raw device buffer exposed through __cuda_array_interface__ so that torch can wrap it without a copy."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def broadcast_index(ctx, index, src=0, group=None, chunk_bytes=1 << 30):
+    """The one collective of the mapper: rank `src` has built the index (gd_index_build); every other
+    rank passes index=None and receives a replica in its own HBM.  The device buffers go over NCCL (NVLink /
+    NVSwitch) straight from and into the library's allocations, in chunks of at most chunk_bytes."""
+    import ctypes as C
+    import gdiet_b200 as gd
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", ctx.device)
+    names = [f for f, _ in gd.gd_index_meta_t._fields_]
+    meta_t = torch.zeros(len(names), dtype=torch.int64, device=dev)
+    if rank == src:
+        m = index.meta()
+        meta_t = torch.tensor([int(getattr(m, f)) for f in names], dtype=torch.int64, device=dev)
+    dist.broadcast(meta_t, src=src, group=group)
+    if rank != src:
+        m = gd.gd_index_meta_t(**{f: int(v) for f, v in zip(names, meta_t.tolist())})
+        index = gd.Index.alloc(ctx, m)
+    total = 0
+    for ptr, nbytes in index.buffers():
+        for o in range(0, nbytes, chunk_bytes):
+            n = min(chunk_bytes, nbytes - o)
+            t = torch.as_tensor(_DeviceBytes(ptr + o, n), device=dev)
+            dist.broadcast(t, src=src, group=group)
+            total += n
+    torch.cuda.synchronize(dev)
+    if rank != src:
+        index.commit()
+    return index, total

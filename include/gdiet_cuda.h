@@ -213,6 +213,20 @@ int gd_index_export(gd_ctx *ctx, const gd_index *idx, uint64_t *keys, uint32_t *
 /* mm_idx_cal_max_occ (GDiet-ShortReads/index.c:182-201): the value mm_mapopt_update stores in mid_occ. */
 int gd_index_cal_max_occ(gd_ctx *ctx, const gd_index *idx, float frac, int32_t *max_occ);
 
+/* Replication onto the other GPUs of a node: the index is built once; the caller broadcasts
+ * its GD_INDEX_NBUF device buffers with its own communicator (ncclBroadcast over NVLink) into an index allocated
+ * with the same meta data on every other GPU, then commits it.  Buffers: table, positions, 4-bit reference,
+ * contig offsets, contig lengths, distinct minimizers, their counts. */
+#define GD_INDEX_NBUF 7
+typedef struct {
+	int64_t n_seq, total_len, n_minimizers, n_keys, table_slots, s_words;
+	int32_t w, k;
+} gd_index_meta_t;
+int gd_index_meta(const gd_index *idx, gd_index_meta_t *meta);
+int gd_index_alloc(gd_ctx *ctx, const gd_index_meta_t *meta, gd_index **out);
+int gd_index_buffers(gd_index *idx, void **ptrs /* [GD_INDEX_NBUF] */, size_t *bytes /* [GD_INDEX_NBUF] */);
+int gd_index_commit(gd_ctx *ctx, gd_index *idx);
+
 /* The mm_mapopt_t fields the short-read path reads between mm_sketch2 and ksw_extd2
  * (GDiet-ShortReads/minimap.h:142-205; defaults main.c:166-182, preset options.c:130-150). */
 typedef struct {

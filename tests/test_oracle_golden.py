@@ -73,3 +73,28 @@ def test_exact_match(oracle):
     b = a.copy()
     b[6] = 2
     assert oracle.exact_match(a, b) == 0
+
+
+def test_map_oracle_matches_golden():
+    """oracle/gd_oracle_map.c against tests/golden/map_sr.npz (generated from the reference program's call trace by
+    tests/golden/make_golden_map.py): works on machines without oracle/_ref."""
+    import maplib
+    g = np.load(os.path.join(GOLD, "map_sr.npz"))
+    contigs, reads = maplib.make_dataset(seed=int(g["seed"]), n_reads=int(g["n_reads"]))
+    o = maplib.sr_opt(min_cnt=float(g["min_cnt"]), rec_frac=float(g["rec_frac"]))
+    M = maplib.MapOracle()
+    mi = M.index_build(contigs, 11, 21, "10")
+    k = 0
+    cig_at = 0
+    for i, r in enumerate(reads):
+        c, cig, _ = M.map_read(mi, r, o)
+        assert len(c) == g["cand_off"][i + 1] - g["cand_off"][i], "read %d" % i
+        for a in c:
+            for f in ("rid", "rs", "re", "qs", "qe", "rev", "exact", "score", "n_cigar"):
+                assert int(a[f]) == int(g[f][k]), "read %d field %s" % (i, f)
+            n = max(int(a["n_cigar"]), 0)
+            assert np.array_equal(cig[int(a["cigar_off"]):int(a["cigar_off"]) + n], g["cigar"][cig_at:cig_at + n])
+            cig_at += n
+            k += 1
+    assert k == len(g["rid"]) and k > 1500
+    M.lib.gdo_index_destroy(mi)

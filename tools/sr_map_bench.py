@@ -13,10 +13,7 @@ import gdiet_b200 as gd
 from gdiet_b200 import synth
 
 
-def main():
-    ref_mbp = float(sys.argv[1]) if len(sys.argv) > 1 else 5
-    n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
-    run_ref = (sys.argv[3] != "noref") if len(sys.argv) > 3 else True
+def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
     cores = len(os.sched_getaffinity(0))
     genome = synth.random_genome(int(ref_mbp * 1e6), seed=1)
     reads = synth.sample_reads(genome, n_reads, 150, seed=2)
@@ -30,7 +27,6 @@ def main():
     buf = np.ascontiguousarray(reads.reshape(-1))
     qual = np.full(n_reads * 150, ord("I"), np.uint8)
     opt, post = gd.sr_options(), gd.sr_post_options()
-    ctx = gd.Context(0)
     t0 = time.perf_counter()
     idx = ctx.index_build(contigs, 11, 21, "10")
     t_index = time.perf_counter() - t0
@@ -106,8 +102,16 @@ def main():
         if got != want:
             bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
             out["sam_first_diff"] = [got[bad[0]][:300], want[bad[0]][:300]] if bad else ["length", "%d vs %d" % (len(got), len(want))]
-    print(json.dumps(out), flush=True)
     idx.close()
+    return out
+
+
+def main():
+    ref_mbp = float(sys.argv[1]) if len(sys.argv) > 1 else 5
+    n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
+    run_ref = (sys.argv[3] != "noref") if len(sys.argv) > 3 else True
+    ctx = gd.Context(0)
+    print(json.dumps(run(ctx, ref_mbp, n_reads, run_ref)), flush=True)
     ctx.close()
 
 

@@ -200,7 +200,7 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
-           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit"]
+           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device"]
 
 
 def load():
@@ -252,6 +252,8 @@ def load():
                                         i64, vp, vp, vp, i64]
     L.gd_index_build.restype = i32
     L.gd_index_build.argtypes = [vp, i32, vp, vp, vp, i32, i32, C.c_char_p, i32, C.POINTER(vp)]
+    L.gd_index_build_device.restype = i32
+    L.gd_index_build_device.argtypes = [vp, i32, vp, vp, vp, i32, i32, C.c_char_p, i32, C.POINTER(vp)]
     L.gd_index_destroy.restype = None
     L.gd_index_destroy.argtypes = [vp]
     L.gd_index_stat.restype = i64
@@ -457,6 +459,16 @@ class Context:
         h = C.c_void_p()
         self._check(self.lib.gd_index_build(self.h, len(bufs), _ptr(off), _ptr(lens), _ptr(buf), w, k, Zb, len(Zb), C.byref(h)),
                     "gd_index_build")
+        return Index(self, h)
+
+    def index_build_device(self, off, lens, d_buf, w, k, Z):
+        """gd_index_build_device: off / lens are host arrays, d_buf a device pointer / CUDA tensor with the ASCII contigs."""
+        off = np.ascontiguousarray(off, np.int64)
+        lens = np.ascontiguousarray(lens, np.int32)
+        Zb = Z.encode() if isinstance(Z, str) else Z
+        h = C.c_void_p()
+        self._check(self.lib.gd_index_build_device(self.h, len(lens), _ptr(off), _ptr(lens), _ptr(d_buf), w, k, Zb, len(Zb), C.byref(h)),
+                    "gd_index_build_device")
         return Index(self, h)
 
     def sr_map_batch(self, index, off, lens, buf, opt, cand_cap=None, cigar_cap=None):

@@ -111,11 +111,12 @@ extern "C" void gd_index_destroy(gd_index *idx)
 	delete idx;
 }
 
-extern "C" int gd_index_build(gd_ctx *ctx, int n_seq, const int64_t *off, const int32_t *len, const char *buf, int w, int k,
-                              const char *Z, int W, gd_index **out)
+// off / len are host arrays; the ASCII sequence is in host memory (buf) or already in HBM (d_seq, not modified)
+static int index_build_core(gd_ctx *ctx, int n_seq, const int64_t *off, const int32_t *len, const char *buf, const char *d_seq,
+                            int w, int k, const char *Z, int W, gd_index **out)
 {
 	if (!ctx) return GD_ERR_ARG;
-	if (!out || n_seq <= 0 || !off || !len || !buf || !Z) {
+	if (!out || n_seq <= 0 || !off || !len || (!buf && !d_seq) || !Z) {
 		ctx->err = "gd_index_build: bad argument";
 		return GD_ERR_ARG;
 	}
@@ -154,13 +155,14 @@ extern "C" int gd_index_build(gd_ctx *ctx, int n_seq, const int64_t *off, const 
 	size_t tmp_bytes = 0;
 	int64_t h_total = 0, cap = 0;
 	const int64_t worst = total / W * ones + (int64_t)n_seq * ones + 16;
-	IDX_CUDA(cudaMalloc(&d_buf, (size_t)bytes + 16));
+	if (!d_seq) IDX_CUDA(cudaMalloc(&d_buf, (size_t)bytes + 16));
 	IDX_CUDA(cudaMalloc(&d_off, (size_t)n_seq * 8));
 	IDX_CUDA(cudaMalloc(&d_len, (size_t)n_seq * 4));
 	IDX_CUDA(cudaMalloc(&d_out_off, (size_t)(n_seq + 1) * 8));
 	IDX_CUDA(cudaMalloc(&idx->d_seq_off, (size_t)(n_seq + 1) * 8));
 	IDX_CUDA(cudaMalloc(&idx->d_seq_len, (size_t)n_seq * 4));
-	IDX_CUDA(cudaMemcpyAsync(d_buf, buf, (size_t)bytes, cudaMemcpyHostToDevice, s));
+	if (!d_seq) IDX_CUDA(cudaMemcpyAsync(d_buf, buf, (size_t)bytes, cudaMemcpyHostToDevice, s));
+	else d_buf = const_cast<char *>(d_seq);
 	IDX_CUDA(cudaMemcpyAsync(d_off, off, (size_t)n_seq * 8, cudaMemcpyHostToDevice, s));
 	IDX_CUDA(cudaMemcpyAsync(d_len, len, (size_t)n_seq * 4, cudaMemcpyHostToDevice, s));
 	IDX_CUDA(cudaMemcpyAsync(idx->d_seq_off, seq_off.data(), (size_t)(n_seq + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -182,7 +184,8 @@ extern "C" int gd_index_build(gd_ctx *ctx, int n_seq, const int64_t *off, const 
 		if (h_total <= cap) break;
 		cudaFree(d_xy), d_xy = nullptr, cap = worst;
 	}
-	cudaFree(d_buf), d_buf = nullptr;
+	if (!d_seq) cudaFree(d_buf);
+	d_buf = nullptr;
 	idx->n_min = h_total;
 	if (h_total > 0xffffffffll) {
 		ctx->err = "gd_index_build: more than 2^32 minimizers (split the reference like -I does)";
@@ -250,12 +253,24 @@ extern "C" int gd_index_build(gd_ctx *ctx, int n_seq, const int64_t *off, const 
 fail:
 	cudaStreamSynchronize(s);
 	{
-		void *tmps[] = {d_buf, d_off, d_len, d_out_off, d_xy, d_key, d_val, d_key2, d_first, d_tmp, d_nruns};
+		void *tmps[] = {d_seq ? nullptr : (void *)d_buf, d_off, d_len, d_out_off, d_xy, d_key, d_val, d_key2, d_first, d_tmp, d_nruns};
 		for (void *p : tmps)
 			if (p) cudaFree(p);
 	}
 	gd_index_destroy(idx);
 	return rc;
+}
+
+extern "C" int gd_index_build(gd_ctx *ctx, int n_seq, const int64_t *off, const int32_t *len, const char *buf, int w, int k,
+                              const char *Z, int W, gd_index **out)
+{
+	return index_build_core(ctx, n_seq, off, len, buf, nullptr, w, k, Z, W, out);
+}
+
+extern "C" int gd_index_build_device(gd_ctx *ctx, int n_seq, const int64_t *off, const int32_t *len, const char *d_buf, int w,
+                                     int k, const char *Z, int W, gd_index **out)
+{
+	return index_build_core(ctx, n_seq, off, len, nullptr, d_buf, w, k, Z, W, out);
 }
 
 extern "C" int64_t gd_index_stat(const gd_index *idx, const char *key)

@@ -21,7 +21,10 @@
 #include "gd_sketch.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <utility>
 #include <vector>
 
 using namespace gd;
@@ -529,11 +532,45 @@ template <class T> static int scan_u32(gd_ctx *ctx, const uint32_t *d_in, T *d_o
 	return GD_OK;
 }
 
+// GD_MAP_PROFILE=1: host-side wall time of every phase of a slice (each ends with the stream synchronised)
+struct SrPhaseClock {
+	bool on;
+	cudaStream_t s;
+	double t0;
+	std::vector<std::pair<const char *, double>> marks;
+	static double now()
+	{
+		struct timespec ts;
+		clock_gettime(CLOCK_MONOTONIC, &ts);
+		return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+	}
+	explicit SrPhaseClock(cudaStream_t st) : on(getenv("GD_MAP_PROFILE") != nullptr), s(st), t0(0)
+	{
+		if (on) t0 = now();
+	}
+	void mark(const char *what)
+	{
+		if (!on) return;
+		cudaStreamSynchronize(s);
+		const double t = now();
+		marks.push_back({what, t - t0});
+		t0 = t;
+	}
+	~SrPhaseClock()
+	{
+		if (!on) return;
+		fprintf(stderr, "[gd_sr_map slice]");
+		for (auto &m : marks) fprintf(stderr, " %s %.2f ms |", m.first, m.second);
+		fprintf(stderr, "\n");
+	}
+};
+
 static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
                         const gd_sr_opt_t *o, int64_t cand_base, int64_t cig_base, int64_t *cand_off, gd_sr_cand_t *cand,
                         int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cand_out, int64_t *n_cig_out)
 {
 	cudaStream_t s = ctx->stream;
+	SrPhaseClock clk(s);
 	int rc;
 	int64_t lo = INT64_MAX, hi = 0, sum_len = 0;
 	int max_len = 0;
@@ -563,6 +600,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_seq.p, buf + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s));
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_off.p, h_off, (size_t)n * 8, cudaMemcpyHostToDevice, s));
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_len.p, len, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+	clk.mark("scan+upload");
 	const int64_t *d_off = (const int64_t *)ctx->mp_off.p;
 	const int32_t *d_len = (const int32_t *)ctx->mp_len.p;
 	const char *d_buf = (const char *)ctx->mp_seq.p;
@@ -572,6 +610,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	                                     P.max_nb_seeds == 0xffffffffu ? 0u : P.max_nb_seeds, &K)))
 		return rc;
 	P.JW = K.JW, P.crop = K.crop;
+	clk.mark("sketch");
 	// ---- K1
 	if ((rc = gd_reserve(ctx, ctx->mp_seed_n, (size_t)K.raw_cap * 4))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_seed_first, (size_t)K.raw_cap * 4))) return rc;
@@ -589,6 +628,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, (int64_t *)ctx->mp_hoff.p + n, 8, cudaMemcpyDeviceToHost, s));
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
 	const int64_t n_hits = h_word[0];
+	clk.mark("seed");
 	// ---- K2
 	if ((rc = gd_reserve(ctx, ctx->mp_ht, (size_t)(n_hits + 1) * 8))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_hq, (size_t)(n_hits + 1) * 4))) return rc;
@@ -606,6 +646,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(cand_off, ctx->mp_coff.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
 	const int64_t nc = h_word[0];
+	clk.mark("vote");
 	*n_cand_out = nc, *n_cig_out = 0;
 	for (int i = 0; i <= n; ++i) cand_off[i] += cand_base;
 	if (nc == 0) return GD_OK;
@@ -628,6 +669,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, d_pair_off + nc, 8, cudaMemcpyDeviceToHost, s));
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
 	const int64_t np = h_word[0];
+	clk.mark("window");
 	// ---- DP on the candidates that are not exact matches (flag KSW_EZ_APPROX_MAX, map.c:867)
 	const int cig_stride = 2 * P.stride;
 	if (np > 0) {
@@ -652,6 +694,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 		                            (gd_extz_t *)ctx->mp_ez.p, (uint32_t *)ctx->mp_cig.p, cig_stride)))
 			return rc;
 	}
+	clk.mark("dp");
 	// ---- K4
 	if ((rc = gd_reserve(ctx, ctx->mp_ncand, (size_t)(nc + 1) * 4))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_coff, (size_t)(std::max<int64_t>(nc, n) + 2) * 8))) return rc;
@@ -663,6 +706,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, d_cig_off + nc, 8, cudaMemcpyDeviceToHost, s));
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
 	const int64_t ncig = h_word[0];
+	clk.mark("scores");
 	*n_cig_out = ncig;
 	const bool fits = cand_base + nc <= cand_cap && cig_base + ncig <= cigar_cap && cand && cigar;
 	if ((rc = gd_reserve(ctx, ctx->mp_cpool, (size_t)(ncig + 1) * 4))) return rc;
@@ -675,6 +719,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 		if (ncig) GD_CUDA_OK(ctx, cudaMemcpyAsync(cigar + cig_base, ctx->mp_cpool.p, (size_t)ncig * 4, cudaMemcpyDeviceToHost, s));
 	}
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
+	clk.mark("cigars+download");
 	if (fits && cig_base)
 		for (int64_t c = 0; c < nc; ++c) cand[cand_base + c].cigar_off += (int32_t)cig_base;
 	return GD_OK;

@@ -15,7 +15,7 @@ gd_ctx *gd_thread_ctx();
 // kernels
 // --------------------------------------------------------------------------------------------
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 16) gd_sketch_tile_kernel(const SketchParams S, SketchBatch B)
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 32) gd_sketch_tile_kernel(const SketchParams S, SketchBatch B)
 {
 	extern __shared__ __align__(16) uint8_t gd_sk_smem[];
 	if (B.tile_base) B.ntiles = B.tile_base[B.njobs];

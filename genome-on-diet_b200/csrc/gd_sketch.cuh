@@ -97,7 +97,7 @@ GD_HD int sk_halo_left(int w, int k) { return 2 * w + k - 3; }
 GD_HD int sk_tile_emit(int np, int w, int k) { return np - sk_halo_left(w, k) - (w - 1); }
 
 #define GD_SK_PADW 2 // zero words in front of the forward-packed codes (>= k bases)
-#define GD_SK_RAW 6144 // bytes of original sequence a tile can stage (2048 positions of "10", "110", "100", "101001" ...)
+#define GD_SK_RAW(THREADS) ((THREADS) * 24) // bytes of original sequence a tile can stage: three per loaded position ("10", "110", "100", "101001" ...); sparser patterns read global memory directly
 
 // Shared memory of one block.  SUF / PREM are indexed [p][t] (position 8t+p at p*THREADS+t) so that
 // the threads of a warp touch consecutive 8-byte words.
@@ -112,7 +112,7 @@ template <int THREADS> struct SketchSmem {
 	long long excl;
 	int32_t tile;
 	uint8_t ones_loc[64];      // copy of SketchParams::ones_loc (indexed per lane)
-	uint32_t raw[GD_SK_RAW / 4 + 2]; // the tile's slice of the ASCII sequence, staged with coalesced word loads
+	uint32_t raw[GD_SK_RAW(THREADS) / 4 + 2]; // the tile's slice of the ASCII sequence, staged with coalesced word loads
 };
 
 GD_DEV uint64_t sk_bits64(const uint32_t *wds, int bit)
@@ -171,7 +171,7 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 			const unsigned long long a0 = (unsigned long long)(seq + rlo);
 			const uint32_t lead = (uint32_t)(a0 & 3);
 			const uint32_t nbytes = rhi - rlo + 1 + lead;
-			if (nbytes <= GD_SK_RAW) {
+			if (nbytes <= GD_SK_RAW(THREADS)) {
 				staged = true, raw_lo = (long long)rlo - lead;
 				const uint32_t *gsrc = (const uint32_t *)(seq + raw_lo);
 				const uint32_t nfull = nbytes >> 2;

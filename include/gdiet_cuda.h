@@ -198,6 +198,9 @@ typedef struct gd_index gd_index;
  * there.  (The reference's bucket_bits only shapes its host hash tables; no lookup result depends on it.) */
 int gd_index_build(gd_ctx *ctx, int n_seq, const int64_t *off, const int32_t *len, const char *buf, int w, int k,
                    const char *Z, int W, gd_index **out);
+/* Same with the ASCII sequence already in HBM (d_buf is a device pointer and is not modified; off / len are host arrays). */
+int gd_index_build_device(gd_ctx *ctx, int n_seq, const int64_t *off, const int32_t *len, const char *d_buf, int w, int k,
+                          const char *Z, int W, gd_index **out);
 void gd_index_destroy(gd_index *idx);
 /* "n_seq", "total_len", "n_minimizers" (records), "n_keys" (distinct minimizers), "table_slots",
  * "device_bytes", "s_words" (uint32 words of the 4-bit reference) */

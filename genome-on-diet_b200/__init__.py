@@ -163,6 +163,29 @@ def sam_header(seq_names, ref_len):
     return txt
 
 
+class gd_lr_opt_t(C.Structure):
+    """include/gdiet_cuda.h: the mm_mapopt_t fields the long-read path reads (GDiet-LongReads/map.c:1273-1853)."""
+    _fields_ = [("W", C.c_int32), ("Z", C.c_char * 64), ("max_seeds", C.c_float), ("frag_mode", C.c_int32),
+                ("max_frag_len", C.c_int32), ("bw", C.c_uint32), ("mid_occ", C.c_int32), ("max_max_occ", C.c_int32),
+                ("occ_dist", C.c_int32), ("q_occ_frac", C.c_float), ("for_only", C.c_int32), ("rev_only", C.c_int32),
+                ("a", C.c_int32), ("b", C.c_int32), ("q", C.c_int32), ("e", C.c_int32), ("q2", C.c_int32), ("e2", C.c_int32),
+                ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("vt_dis", C.c_uint32), ("vt_nb_loc", C.c_uint32),
+                ("vt_cov", C.c_float), ("vt_df1", C.c_float), ("vt_df2", C.c_float), ("vt_f", C.c_float),
+                ("max_max_gap", C.c_uint32), ("max_min_gap", C.c_uint32)]
+
+
+def lr_options(preset="map-hifi", Z="10", bw=1000, mid_occ=50, **kw):
+    """`-ax map-hifi|map-ont -Z .. -W .. -r bw` (GDiet-LongReads/options.c:86-111, main.c:170-182). mid_occ is what
+    mm_mapopt_update derives from the index (gd_index_cal_max_occ clamped to [min_mid_occ, max_mid_occ])."""
+    sc = dict(a=1, b=4, q=6, e=2, q2=26, e2=1) if preset == "map-hifi" else dict(a=2, b=4, q=4, e=2, q2=24, e2=1)
+    o = gd_lr_opt_t(W=len(Z), Z=Z.encode(), max_seeds=0.1, frag_mode=0, max_frag_len=0, bw=bw, mid_occ=mid_occ, max_max_occ=4095,
+                    occ_dist=500, q_occ_frac=0.01, for_only=0, rev_only=0, zdrop=400, end_bonus=-1, vt_dis=100, vt_nb_loc=3,
+                    vt_cov=0.03, vt_df1=0.01, vt_df2=0.01, vt_f=0.05, max_max_gap=50000, max_min_gap=4000, **sc)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
 SR_CAND_FIELDS = ["rid", "rs", "re", "qs", "qe", "rev", "votes", "first_q", "last_q", "exact", "score", "n_cigar", "cigar_off"]
 SR_CAND_DTYPE = np.dtype([(f, np.int32) for f in SR_CAND_FIELDS] + [("reserved", np.int32, 3)])
 
@@ -200,7 +223,7 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
-           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device"]
+           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch"]
 
 
 def load():
@@ -274,6 +297,8 @@ def load():
     L.gd_index_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.gd_index_commit.restype = i32
     L.gd_index_commit.argtypes = [vp, vp]
+    L.gd_lr_map_batch.restype = i32
+    L.gd_lr_map_batch.argtypes = [vp, vp, i32, vp, vp, vp, C.POINTER(gd_lr_opt_t), vp, vp, i64, vp, i64, C.POINTER(i64)]
     L.gd_sr_sam_batch.restype = i32
     L.gd_sr_sam_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
                                   C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -471,8 +496,13 @@ class Context:
                     "gd_index_build_device")
         return Index(self, h)
 
-    def sr_map_batch(self, index, off, lens, buf, opt, cand_cap=None, cigar_cap=None):
+    def lr_map_batch(self, index, off, lens, buf, opt, cand_cap=None, cigar_cap=None):
+        """gd_lr_map_batch (long-read tree). Returns (cand_off[n+1], candidates (SR_CAND_DTYPE), cigar pool)."""
+        return self.sr_map_batch(index, off, lens, buf, opt, cand_cap, cigar_cap, fn=self.lib.gd_lr_map_batch, what="gd_lr_map_batch")
+
+    def sr_map_batch(self, index, off, lens, buf, opt, cand_cap=None, cigar_cap=None, fn=None, what="gd_sr_map_batch"):
         """gd_sr_map_batch. Returns (cand_off[n+1], candidates (SR_CAND_DTYPE), cigar pool)."""
+        fn = fn or self.lib.gd_sr_map_batch
         n = len(lens)
         cand_off = np.zeros(n + 1, np.int64)
         cand_cap = cand_cap or 2 * n + 64
@@ -481,13 +511,13 @@ class Context:
         while True:
             cand = np.zeros(cand_cap, SR_CAND_DTYPE)
             cig = np.zeros(cigar_cap, np.uint32)
-            rc = self.lib.gd_sr_map_batch(self.h, index.h, n, _ptr(off), _ptr(lens), _ptr(buf), C.byref(opt), _ptr(cand_off),
-                                          _ptr(cand), cand_cap, _ptr(cig), cigar_cap, C.byref(ncig))
+            rc = fn(self.h, index.h, n, _ptr(off), _ptr(lens), _ptr(buf), C.byref(opt), _ptr(cand_off), _ptr(cand), cand_cap,
+                    _ptr(cig), cigar_cap, C.byref(ncig))
             if rc == GD_ERR_CAPACITY:
                 cand_cap = max(cand_cap, int(cand_off[n]) + 16)
                 cigar_cap = max(cigar_cap, int(ncig.value) + 16)
                 continue
-            self._check(rc, "gd_sr_map_batch")
+            self._check(rc, what)
             return cand_off, cand[: int(cand_off[n])], cig[: int(ncig.value)]
 
 

@@ -39,6 +39,9 @@ struct SrParams {
 	float min_cnt, rec_frac, q_occ_frac;
 	int32_t af_max_loc, mid_occ, max_max_occ, occ_dist, for_only, rev_only, a;
 	int32_t stride; // bytes per candidate in the query / target code buffers
+	// long-read tree (GDiet-LongReads/map.c)
+	uint32_t vt_dis, vt_nb_loc, max_max_gap, max_min_gap;
+	float vt_cov, vt_df1, vt_df2, vt_f;
 };
 
 struct SrRead { // per-read state between K1 and K2
@@ -191,8 +194,12 @@ __global__ void __launch_bounds__(SR_WARPS * 32) gd_sr_seed_kernel(IndexDev I, S
 // --------------------------------------------------------------------------------------------
 // K2: hits, sort, vote, windows
 // --------------------------------------------------------------------------------------------
-// ascending sort of (target, query) by target with one warp; ties in target may end in any order (the vote
-// does not depend on it: tied hits join the same cluster and only min / max of their query positions are kept)
+// Ascending sort of (target, query) by target with one warp.  Ties in target are ordered by descending query
+// position: that is the order the reference's merge_sort leaves (map.c:176-255, merge_locations takes the later
+// run -- the seed with the larger query position -- on a tie), which the long-read vote_2 depends on.  (The
+// short-read vote does not depend on the tie order: tied hits join the same cluster and only the min / max of their
+// query positions are kept.)
+__device__ __forceinline__ bool hit_less(uint64_t at, uint32_t aq, uint64_t bt, uint32_t bq) { return at < bt || (at == bt && aq > bq); }
 __device__ void sr_sort_hits(uint64_t *t, uint32_t *q, int n, int lane)
 {
 	if (n <= 1) return;
@@ -204,7 +211,7 @@ __device__ void sr_sort_hits(uint64_t *t, uint32_t *q, int n, int lane)
 				const uint64_t ok = __shfl_xor_sync(0xffffffffu, key, j);
 				const uint32_t ov = __shfl_xor_sync(0xffffffffu, val, j);
 				const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
-				if (take_min ? ok < key : ok > key) key = ok, val = ov;
+				if (take_min ? hit_less(ok, ov, key, val) : hit_less(key, val, ok, ov)) key = ok, val = ov;
 			}
 		if (lane < n) t[lane] = key, q[lane] = val;
 		__syncwarp();
@@ -219,10 +226,8 @@ __device__ void sr_sort_hits(uint64_t *t, uint32_t *q, int n, int lane)
 			const int l = blk * k + o, h = blk * k + k - 1 - o;
 			if (h < n) {
 				const uint64_t a = t[l], b = t[h];
-				if (b < a) {
-					const uint32_t qa = q[l], qb = q[h];
-					t[l] = b, t[h] = a, q[l] = qb, q[h] = qa;
-				}
+				const uint32_t qa = q[l], qb = q[h];
+				if (hit_less(b, qb, a, qa)) t[l] = b, t[h] = a, q[l] = qb, q[h] = qa;
 			}
 		}
 		__syncwarp();
@@ -231,13 +236,54 @@ __device__ void sr_sort_hits(uint64_t *t, uint32_t *q, int n, int lane)
 				const int l = (p / j) * 2 * j + (p % j), h = l + j;
 				if (h < n) {
 					const uint64_t a = t[l], b = t[h];
-					if (b < a) {
-						const uint32_t qa = q[l], qb = q[h];
-						t[l] = b, t[h] = a, q[l] = qb, q[h] = qa;
-					}
+					const uint32_t qa = q[l], qb = q[h];
+					if (hit_less(b, qb, a, qa)) t[l] = b, t[h] = a, q[l] = qb, q[h] = qa;
 				}
 			}
 			__syncwarp();
+		}
+	}
+}
+
+// collect_seed_hits, map.c:284-311: the hits of every unfiltered seed, forward strand from the front of the read's
+// slice of the hit array, reverse strand from its back (the slice has room for exactly all of them)
+__device__ __forceinline__ void map_fill_hits(const IndexDev &I, const SrParams &P, uint32_t ext, const uint64_t *mv, const uint32_t *sn,
+                                              const uint32_t *sf, int n0, uint64_t *t, uint32_t *q, uint32_t na, uint32_t &nf, uint32_t &nr,
+                                              int lane)
+{
+	const uint32_t lt = (1u << lane) - 1;
+	auto put = [&](bool valid, uint64_t r, uint32_t qp) {
+		const uint32_t qpos = qp >> 1, loc = (uint32_t)r >> 1;
+		const uint32_t str = (uint32_t)(r & 1) ^ (qp & 1);
+		const bool keep = valid && !(str ? P.for_only : P.rev_only); // skip_seed, map.c:121-127
+		const uint32_t fm = __ballot_sync(0xffffffffu, keep && !str), rm = __ballot_sync(0xffffffffu, keep && str);
+		if (keep) {
+			if (str) {
+				const uint32_t slot = na - 1 - (nr + __popc(rm & lt));
+				t[slot] = (r >> 32) << 32 | (uint32_t)(loc + qpos), q[slot] = qpos;
+			} else {
+				const uint32_t slot = nf + __popc(fm & lt);
+				t[slot] = (r >> 32) << 32 | (uint32_t)(loc + ext - qpos), q[slot] = qpos;
+			}
+		}
+		nf += __popc(fm), nr += __popc(rm);
+	};
+	for (int e0 = 0; e0 < n0; e0 += 32) {
+		const int e = e0 + lane;
+		uint32_t c = e < n0 ? sn[e] : 0;
+		if (c & SR_FLT) c = 0;
+		const uint32_t qp = e < n0 ? (uint32_t)mv[2 * e + 1] : 0, first = e < n0 ? sf[e] : 0;
+		put(c == 1, c == 1 ? I.pos[first] : 0, qp);
+		uint32_t mm = __ballot_sync(0xffffffffu, c > 1);
+		while (mm) {
+			const int src = __ffs(mm) - 1;
+			mm &= mm - 1;
+			const uint32_t bc = __shfl_sync(0xffffffffu, c, src), bf = __shfl_sync(0xffffffffu, first, src);
+			const uint32_t bq = __shfl_sync(0xffffffffu, qp, src);
+			for (uint32_t j0 = 0; j0 < bc; j0 += 32) {
+				const uint32_t j = j0 + lane;
+				put(j < bc, j < bc ? I.pos[bf + j] : 0, bq);
+			}
 		}
 	}
 }
@@ -324,41 +370,7 @@ __global__ void __launch_bounds__(SR_WARPS * 32) gd_sr_vote_kernel(IndexDev I, S
 		uint64_t *t = ht + hoff;
 		uint32_t *q = hq + hoff;
 		uint32_t nf = 0, nr = 0;
-		// ---- collect_seed_hits, map.c:284-311: forward hits grow from the front, reverse hits from the back
-		auto put = [&](bool valid, uint64_t r, uint32_t qp) {
-			const uint32_t qpos = qp >> 1, loc = (uint32_t)r >> 1;
-			const uint32_t str = (uint32_t)(r & 1) ^ (qp & 1);
-			const bool keep = valid && !(str ? P.for_only : P.rev_only); // skip_seed, map.c:121-127
-			const uint32_t fm = __ballot_sync(0xffffffffu, keep && !str), rm = __ballot_sync(0xffffffffu, keep && str);
-			if (keep) {
-				if (str) {
-					const uint32_t slot = na - 1 - (nr + __popc(rm & lt));
-					t[slot] = (r >> 32) << 32 | (uint32_t)(loc + qpos), q[slot] = qpos;
-				} else {
-					const uint32_t slot = nf + __popc(fm & lt);
-					t[slot] = (r >> 32) << 32 | (uint32_t)(loc + R.ext - qpos), q[slot] = qpos;
-				}
-			}
-			nf += __popc(fm), nr += __popc(rm);
-		};
-		for (int e0 = 0; e0 < n0; e0 += 32) {
-			const int e = e0 + lane;
-			uint32_t c = e < n0 ? sn[e] : 0;
-			if (c & SR_FLT) c = 0;
-			const uint32_t qp = e < n0 ? (uint32_t)mv[2 * e + 1] : 0, first = e < n0 ? sf[e] : 0;
-			put(c == 1, c == 1 ? I.pos[first] : 0, qp);
-			uint32_t mm = __ballot_sync(0xffffffffu, c > 1);
-			while (mm) {
-				const int src = __ffs(mm) - 1;
-				mm &= mm - 1;
-				const uint32_t bc = __shfl_sync(0xffffffffu, c, src), bf = __shfl_sync(0xffffffffu, first, src);
-				const uint32_t bq = __shfl_sync(0xffffffffu, qp, src);
-				for (uint32_t j0 = 0; j0 < bc; j0 += 32) {
-					const uint32_t j = j0 + lane;
-					put(j < bc, j < bc ? I.pos[bf + j] : 0, bq);
-				}
-			}
-		}
+		map_fill_hits(I, P, R.ext, mv, sn, sf, n0, t, q, na, nf, nr, lane);
 		__syncwarp();
 		uint64_t *tr = t + (na - nr);
 		uint32_t *qr = q + (na - nr);
@@ -426,6 +438,267 @@ __global__ void __launch_bounds__(SR_WARPS * 32) gd_sr_vote_kernel(IndexDev I, S
 	}
 }
 
+// --------------------------------------------------------------------------------------------
+// K2, long-read tree (GDiet-LongReads/map.c:1052-1590,1654-1713): two voting rounds, density / score filters,
+// candidate chaining, windows.  The cluster scans are sequential by definition and run on lane 0 over 32-hit
+// chunks the warp stages in shared memory; everything after them works on at most vt_nb_loc + 2 candidates.
+// --------------------------------------------------------------------------------------------
+struct LrVt { // vt_t, LR/map.c:1032-1045 (next as an index, -1 = NULL)
+	uint32_t chrom_id;
+	int32_t ft, lt; // first / last target location
+	uint32_t fq, lq;
+	uint32_t score;
+	int32_t next;
+	uint32_t str, concat;
+};
+
+__device__ __forceinline__ uint64_t lr_loc(int str, uint64_t target, uint32_t query, int32_t ext)
+{ // LR/map.c:1064-1065
+	return str ? (target - query) : target - (uint64_t)(uint32_t)(ext - (int32_t)query);
+}
+
+__device__ __forceinline__ void lr_emit(LrVt *seqs, unsigned &out_len, unsigned max_loc, uint64_t ft, uint64_t lt, uint32_t fq, uint32_t lq,
+                                        unsigned counter, int str)
+{ // LR/map.c:1095-1131 / :1145-1179
+	if (out_len == max_loc) {
+		if (seqs[out_len - 1].score >= counter) return;
+	} else ++out_len;
+	LrVt v;
+	v.chrom_id = (uint32_t)(ft >> 32), v.ft = (int32_t)(uint32_t)ft, v.lt = (int32_t)(uint32_t)lt, v.fq = fq, v.lq = lq;
+	v.score = counter, v.next = -1, v.str = (uint32_t)str, v.concat = 0;
+	seqs[out_len - 1] = v;
+	for (unsigned k = out_len - 1; k > 0; k--) {
+		if (seqs[k].score > seqs[k - 1].score) {
+			const LrVt t = seqs[k];
+			seqs[k] = seqs[k - 1], seqs[k - 1] = t;
+		} else break;
+	}
+}
+
+// round == 1: vote (LR/map.c:1052-1182) into seqs / out_len;  round == 2: vote_2 (:1184-1271) into best, query range (qmin, qmax)
+template <int ROUND>
+__device__ void lr_vote(const uint64_t *ht, const uint32_t *hq, unsigned len, int str, LrVt *seqs, unsigned &out_len, LrVt &best,
+                        uint64_t *s_t, uint32_t *s_q, uint32_t dist, int32_t ext, unsigned max_loc, uint32_t cov_thr, uint32_t qmin,
+                        uint32_t qmax, int lane)
+{
+	if (len == 0) return;
+	unsigned counter = 0;
+	uint64_t ft = 0, lt = 0, ref_loc = 0;
+	uint32_t fq = 0, lq = 0;
+	auto close = [&]() {
+		if (ROUND == 1) {
+			if (lq - fq > cov_thr) lr_emit(seqs, out_len, max_loc, ft, lt, fq, lq, counter, str);
+		} else if (counter > best.score && lq < qmax && fq > qmin) {
+			best.chrom_id = (uint32_t)(ft >> 32), best.ft = (int32_t)(uint32_t)ft, best.lt = (int32_t)(uint32_t)lt;
+			best.fq = fq, best.lq = lq, best.score = counter, best.next = -1, best.str = (uint32_t)str, best.concat = 0;
+		}
+	};
+	for (unsigned c0 = 0; c0 < len; c0 += 32) {
+		if (c0 + lane < len) s_t[lane] = ht[c0 + lane], s_q[lane] = hq[c0 + lane];
+		__syncwarp();
+		if (lane == 0) {
+			const unsigned m = len - c0 < 32 ? len - c0 : 32;
+			for (unsigned j = 0; j < m; ++j) {
+				const uint64_t ct = s_t[j];
+				const uint32_t cq = s_q[j];
+				if (counter != 0 && ct - ref_loc <= dist) {
+					if (ROUND == 1 || (cq < qmax && cq > qmin)) {
+						const uint64_t l = lr_loc(str, ct, cq, ext);
+						counter++;
+						if (cq < fq) fq = cq, ref_loc = ct;
+						if (cq > lq) lq = cq;
+						if (l > lt) lt = l;
+						if (l < ft) ft = l;
+					}
+				} else {
+					if (counter != 0) close();
+					ft = lt = lr_loc(str, ct, cq, ext), fq = lq = cq, ref_loc = ct, counter = 1;
+				}
+			}
+		}
+		__syncwarp();
+	}
+	if (lane == 0) close();
+}
+
+__global__ void __launch_bounds__(SR_WARPS * 32) gd_lr_vote_kernel(IndexDev I, SrParams P, int n, const int32_t *len,
+                                                                  const int64_t *job_off, const uint64_t *raw,
+                                                                  const uint32_t *seed_n, const uint32_t *seed_first,
+                                                                  const SrRead *rd, const int64_t *hits_off, uint64_t *ht,
+                                                                  uint32_t *hq, gd_sr_cand_t *cand_tmp, uint32_t *n_cand, int *max_span)
+{
+	__shared__ uint64_t s_t[SR_WARPS][32];
+	__shared__ uint32_t s_q[SR_WARPS][32];
+	__shared__ LrVt s_seq[SR_WARPS][SR_MAX_LOC + 2];
+	__shared__ unsigned s_nb[SR_WARPS];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = (gridDim.x * blockDim.x) >> 5;
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+		const SrRead R = rd[i];
+		const int64_t base = job_off[(size_t)i * P.JW + R.shift];
+		const uint64_t *mv = raw + 2 * base;
+		const uint32_t *sn = seed_n + base, *sf = seed_first + base;
+		const int64_t hoff = hits_off[i];
+		const uint32_t na = (uint32_t)(hits_off[i + 1] - hoff);
+		uint64_t *t = ht + hoff;
+		uint32_t *q = hq + hoff;
+		uint32_t nf = 0, nr = 0;
+		map_fill_hits(I, P, R.ext, mv, sn, sf, (int)R.n0, t, q, na, nf, nr, lane);
+		__syncwarp();
+		uint64_t *tr = t + (na - nr);
+		uint32_t *qr = q + (na - nr);
+		sr_sort_hits(t, q, (int)nf, lane);
+		sr_sort_hits(tr, qr, (int)nr, lane);
+		const uint32_t qlen_sum = (uint32_t)len[i];
+		const int32_t ext = (int32_t)R.ext;
+		const int k = P.k;
+		const unsigned bw = P.bw;
+		const uint32_t cov_thr = (uint32_t)((float)qlen_sum * P.vt_cov);
+		LrVt *seqs = s_seq[wib];
+		LrVt best;
+		unsigned nb = 0;
+		// ---- first round, LR/map.c:1342-1347
+		lr_vote<1>(t, q, nf, 0, seqs, nb, best, s_t[wib], s_q[wib], P.vt_dis, ext, P.vt_nb_loc, cov_thr, 0, 0, lane);
+		lr_vote<1>(tr, qr, nr, 1, seqs, nb, best, s_t[wib], s_q[wib], P.vt_dis, ext, P.vt_nb_loc, cov_thr, 0, 0, lane);
+		uint32_t qrstart = qlen_sum, qrend = 0;
+		int need2a = 0, need2b = 0;
+		if (lane == 0) {
+			if (nb > 0) { // density filter, LR/map.c:1354-1362 (the assignment is the reference's: seqs[i] = seqs[kept])
+				unsigned df = 0;
+				for (unsigned c = 0; c < nb; c++)
+					if ((float)seqs[c].score > P.vt_df1 * (float)(seqs[c].lt - seqs[c].ft)) seqs[c] = seqs[df], df++;
+				nb = df;
+			}
+			if (nb > 0) { // LR/map.c:1371-1400
+				const unsigned filtering_threshold = (unsigned)((float)seqs[0].score * P.vt_f);
+				for (unsigned c = 0; c < nb; c++) {
+					if (seqs[c].score < filtering_threshold) {
+						nb = c;
+						break;
+					}
+					seqs[c].fq -= (uint32_t)(k - 1), seqs[c].ft -= (k - 1);
+					seqs[c].next = -1, seqs[c].concat = 0;
+					if (seqs[c].lq - seqs[c].fq + 0.5 * bw < seqs[c].lt - seqs[c].ft)
+						seqs[c].lt = (int32_t)(seqs[c].ft + seqs[c].lq - seqs[c].fq + 0.5 * bw);
+					if (seqs[c].fq < qrstart) qrstart = seqs[c].fq;
+					if (seqs[c].lq > qrend) qrend = seqs[c].lq;
+				}
+				need2a = qrstart > cov_thr, need2b = qlen_sum - qrend > cov_thr;
+			}
+		}
+		nb = __shfl_sync(0xffffffffu, nb, 0);
+		if (nb == 0) { // nothing survives the first round: the reference returns before the second one (LR/map.c:1349-1369)
+			if (lane == 0) n_cand[i] = 0;
+			__syncwarp();
+			continue;
+		}
+		need2a = __shfl_sync(0xffffffffu, need2a, 0), need2b = __shfl_sync(0xffffffffu, need2b, 0);
+		qrstart = __shfl_sync(0xffffffffu, qrstart, 0), qrend = __shfl_sync(0xffffffffu, qrend, 0);
+		// ---- second round on the uncovered ends of the read, LR/map.c:1402-1445
+		for (int pass = 0; pass < 2; ++pass) {
+			if (!(pass == 0 ? need2a : need2b)) continue;
+			const uint32_t qmin = pass == 0 ? 0u : qrend, qmax = pass == 0 ? qrstart : qlen_sum;
+			unsigned dummy = 0;
+			best.score = 0, best.chrom_id = 0, best.ft = best.lt = 0, best.fq = best.lq = 0, best.next = -1, best.str = 0, best.concat = 0;
+			lr_vote<2>(t, q, nf, 0, seqs, dummy, best, s_t[wib], s_q[wib], P.vt_dis, ext, 0, 0, qmin, qmax, lane);
+			lr_vote<2>(tr, qr, nr, 1, seqs, dummy, best, s_t[wib], s_q[wib], P.vt_dis, ext, 0, 0, qmin, qmax, lane);
+			if (lane == 0) {
+				best.fq -= (uint32_t)(k - 1), best.ft -= (k - 1);
+				if ((float)best.score > P.vt_df2 * (float)(best.lt - best.ft)) {
+					if (best.lq - best.fq + 0.5 * bw < best.lt - best.ft) best.lt = (int32_t)(best.ft + best.lq - best.fq + 0.5 * bw);
+					seqs[nb++] = best;
+				}
+			}
+		}
+		if (lane == 0) {
+			// ---- which candidates continue each other, LR/map.c:1467-1590
+			const unsigned G = P.max_max_gap, g = P.max_min_gap;
+			for (unsigned a = 0; a < nb; a++) {
+				LrVt &s1 = seqs[a];
+				for (unsigned b = 0; b < nb; b++) {
+					const LrVt &s2 = seqs[b];
+					if (b == a || s2.concat != 0 || s1.str != s2.str || s1.chrom_id != s2.chrom_id) continue;
+					bool take = false, better = false;
+					if (s1.str) {
+						if (s2.lq < s1.fq && s1.lt > s2.ft && s1.ft < s2.ft) {
+							take = s2.lq + G > s1.fq;
+							better = s1.next >= 0 && s2.lq > seqs[s1.next].lq;
+						} else if (s2.lq < s1.fq && s1.lt < s2.ft) {
+							take = (s2.lq + g > s1.fq || (uint32_t)s1.lt + g > (uint32_t)s2.ft) && s2.lq + G > s1.fq && (uint32_t)s1.lt + G > (uint32_t)s2.ft;
+							better = s1.next >= 0 && s2.lq > seqs[s1.next].lq;
+						} else if (s2.lq > s1.fq && s1.lt < s2.ft && s2.lq < s1.lq && s2.fq < s1.fq) {
+							take = (uint32_t)s1.lt + G > (uint32_t)s2.ft;
+							better = s1.next >= 0 && s2.lq < seqs[s1.next].lq;
+						}
+					} else {
+						if (s1.lq < s2.fq && s1.lt > s2.ft && s1.ft < s2.ft) {
+							take = s1.lq + G > s2.fq;
+							better = s1.next >= 0 && s2.fq < seqs[s1.next].fq;
+						} else if (s1.lq < s2.fq && s1.lt < s2.ft) {
+							take = (s1.lq + g > s2.fq || (uint32_t)s1.lt + g > (uint32_t)s2.ft) && (uint32_t)s1.lt + G > (uint32_t)s2.ft && s1.lq + G > s2.fq;
+							better = s1.next >= 0 && s2.fq < seqs[s1.next].fq;
+						} else if (s1.lq > s2.fq && s1.lt < s2.ft && s1.fq < s2.fq && s1.lq < s2.lq) {
+							take = (uint32_t)s1.lt + G > (uint32_t)s2.ft;
+							better = s1.next >= 0 && s2.fq < seqs[s1.next].fq;
+						}
+					}
+					if (take && (s1.next < 0 || better)) s1.next = (int32_t)b;
+				}
+				if (s1.next >= 0) { // adjust the boundaries of the pair, LR/map.c:1557-1589
+					LrVt &s2 = seqs[s1.next];
+					s2.concat = 1;
+					if (s1.str) {
+						if (s2.lq < s1.fq && s1.lt < s2.ft) {
+							const uint32_t diffq = s1.fq - s2.lq, difft = (uint32_t)(s2.ft - s1.lt), mn = difft > diffq ? diffq : difft;
+							s2.lq += mn, s1.lt += (int32_t)mn, s1.fq -= mn, s2.ft -= (int32_t)mn;
+						}
+					} else if (s1.lq < s2.fq && s1.lt < s2.ft) {
+						const uint32_t diffq = s2.fq - s1.lq, difft = (uint32_t)(s2.ft - s1.lt), mn = difft > diffq ? diffq : difft;
+						s1.lq += mn, s1.lt += (int32_t)mn, s2.fq -= mn, s2.ft -= (int32_t)mn;
+					}
+					if (s2.lt < s1.lt) s1.lt = s2.lt - 1;
+				}
+			}
+			s_nb[wib] = nb;
+		}
+		__syncwarp();
+		nb = s_nb[wib];
+		// ---- windows, LR/map.c:1654-1713 (one lane per candidate)
+		int span = 0;
+		if (lane < (int)nb) {
+			const LrVt v = seqs[lane];
+			const int str = (int)v.str;
+			const int32_t chrom_len = (int32_t)I.seq_len[v.chrom_id];
+			uint32_t target_start = (uint32_t)v.ft, target_end = (uint32_t)v.lt, query_start, query_end;
+			if (str) query_end = qlen_sum - 1 - v.fq, query_start = qlen_sum - 1 - v.lq;
+			else query_start = v.fq, query_end = v.lq;
+			if (!(qlen_sum > 300)) {
+				if (target_start < query_start) query_start -= target_start, target_start = 0;
+				else target_start -= query_start, query_start = 0;
+				if ((uint32_t)chrom_len + query_end < qlen_sum + target_end) query_end += (uint32_t)chrom_len - target_end - 1, target_end = (uint32_t)chrom_len - 1;
+				else target_end += qlen_sum - query_end - 1, query_end = qlen_sum - 1;
+			}
+			if (str) {
+				const uint32_t tmp = qlen_sum - 1 - query_start;
+				query_start = qlen_sum - 1 - query_end, query_end = tmp;
+			}
+			gd_sr_cand_t c;
+			c.rid = (int32_t)v.chrom_id, c.rs = (int32_t)target_start, c.re = (int32_t)target_end + 1, c.qs = (int32_t)query_start;
+			c.qe = (int32_t)query_end + 1, c.rev = str, c.votes = (int32_t)v.score, c.first_q = (int32_t)v.fq, c.last_q = (int32_t)v.lq;
+			c.exact = 0, c.score = 0, c.n_cigar = 0, c.cigar_off = 0;
+			c.reserved[0] = i, c.reserved[1] = v.next, c.reserved[2] = (int32_t)v.concat;
+			cand_tmp[(size_t)i * (P.vt_nb_loc + 2) + lane] = c;
+			const int ql = c.qe - c.qs, tl = c.re - c.rs;
+			span = ql > tl ? ql : tl;
+		}
+		span = __reduce_max_sync(0xffffffffu, span);
+		if (lane == 0) {
+			n_cand[i] = nb;
+			atomicMax(max_span, span);
+		}
+		__syncwarp();
+	}
+}
+
 // candidates of all reads, dense and in input order
 __global__ void gd_sr_compact_kernel(int n, int af, const gd_sr_cand_t *cand_tmp, const int64_t *cand_off, gd_sr_cand_t *cand)
 {
@@ -452,14 +725,15 @@ __global__ void __launch_bounds__(128) gd_sr_window_kernel(IndexDev I, SrParams 
 		const int i = c->reserved[0], qs = c->qs, qe = c->qe, rev = c->rev, n = qe - qs;
 		const char *rdp = buf + off[i];
 		const uint64_t tb = I.seq_off[c->rid] + (uint64_t)c->rs;
-		const int tl = c->re - c->rs; // == n for every window the arithmetic above produces
-		uint8_t *qo = qbuf + ci * P.stride, *to = tbuf + ci * P.stride;
-		int diff = 0;
-		for (int j = lane; j < n; j += 32) {
+		const int tl = c->re - c->rs; // == n for the short-read windows; independent for long reads
+		const int t_in = (int)I.seq_len[c->rid] - c->rs; // mm_idx_getseq clips at the contig end (index.c:157-166)
+		uint8_t *qo = qbuf + ci * (int64_t)P.stride, *to = tbuf + ci * (int64_t)P.stride;
+		int diff = n != tl;
+		for (int j = lane; j < n || j < tl; j += 32) {
 			// map.c:737-757: forward = nt4, reverse strand = reversed and ^3 (N becomes 7)
-			const int qc = rev ? (sk_nt4((unsigned char)rdp[qe - 1 - j]) ^ 3) : sk_nt4((unsigned char)rdp[qs + j]);
-			const int tc = j < tl ? (int)idx_base(I, tb + j) : 0;
-			qo[j] = (uint8_t)qc, to[j] = (uint8_t)tc;
+			int qc = 0, tc = 0;
+			if (j < n) qc = rev ? (sk_nt4((unsigned char)rdp[qe - 1 - j]) ^ 3) : sk_nt4((unsigned char)rdp[qs + j]), qo[j] = (uint8_t)qc;
+			if (j < tl) tc = j < t_in ? (int)idx_base(I, tb + j) : 0, to[j] = (uint8_t)tc;
 			diff |= qc != tc;
 		}
 		diff = __any_sync(0xffffffffu, diff);
@@ -472,14 +746,14 @@ __global__ void __launch_bounds__(128) gd_sr_window_kernel(IndexDev I, SrParams 
 }
 
 // DP work list: the candidates that were not exact matches
-__global__ void gd_sr_pairs_kernel(int64_t nc, int stride, const gd_sr_cand_t *cand, const int64_t *pair_off, int32_t *plen,
-                                   int64_t *poff, int32_t *pcand)
+__global__ void gd_sr_pairs_kernel(int64_t nc, int stride, const gd_sr_cand_t *cand, const int64_t *pair_off, int32_t *pqlen,
+                                   int32_t *ptlen, int64_t *poff)
 {
 	const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (ci >= nc) return;
 	if (pair_off[ci + 1] == pair_off[ci]) return;
 	const int64_t p = pair_off[ci];
-	plen[p] = cand[ci].qe - cand[ci].qs, poff[p] = ci * stride, pcand[p] = (int32_t)ci;
+	pqlen[p] = cand[ci].qe - cand[ci].qs, ptlen[p] = cand[ci].re - cand[ci].rs, poff[p] = ci * (int64_t)stride;
 }
 
 // K4a: scores and CIGAR lengths of every candidate
@@ -507,7 +781,8 @@ __global__ void __launch_bounds__(128) gd_sr_cigars_kernel(int64_t nc, gd_sr_can
 		gd_sr_cand_t *c = cand + ci;
 		const int64_t o = cig_off[ci];
 		const int m = (int)(cig_off[ci + 1] - o);
-		if (lane == 0) c->cigar_off = (int32_t)o, c->reserved[0] = 0;
+		if (lane == 0) // reserved[] leaves as {next, concat, 0} (long reads; zeros for short reads)
+			c->cigar_off = (int32_t)o, c->reserved[0] = c->reserved[1], c->reserved[1] = c->reserved[2], c->reserved[2] = 0;
 		if (o + m > pool_cap) continue;
 		if (c->exact) {
 			if (lane == 0) pool[o] = (uint32_t)(c->qe - c->qs) << 4; // <len>M
@@ -566,7 +841,7 @@ struct SrPhaseClock {
 };
 
 static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
-                        const gd_sr_opt_t *o, int64_t cand_base, int64_t cig_base, int64_t *cand_off, gd_sr_cand_t *cand,
+                        const gd_sr_opt_t *o, const gd_lr_opt_t *lr, int64_t cand_base, int64_t cig_base, int64_t *cand_off, gd_sr_cand_t *cand,
                         int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cand_out, int64_t *n_cig_out)
 {
 	cudaStream_t s = ctx->stream;
@@ -590,6 +865,9 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	P.af_max_loc = o->af_max_loc, P.mid_occ = o->mid_occ, P.max_max_occ = o->max_max_occ, P.occ_dist = o->occ_dist;
 	P.for_only = o->for_only, P.rev_only = o->rev_only, P.a = o->a;
 	P.stride = (max_len + 15) / 16 * 16;
+	const int per_read = lr ? (int)lr->vt_nb_loc + 2 : o->af_max_loc; // candidate slots per read
+	if (lr) P.vt_dis = lr->vt_dis, P.vt_nb_loc = lr->vt_nb_loc, P.max_max_gap = lr->max_max_gap, P.max_min_gap = lr->max_min_gap,
+		P.vt_cov = lr->vt_cov, P.vt_df1 = lr->vt_df1, P.vt_df2 = lr->vt_df2, P.vt_f = lr->vt_f;
 	// ---- reads up
 	if ((rc = gd_reserve(ctx, ctx->mp_seq, (size_t)(hi - lo) + 16))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_off, (size_t)n * 8))) return rc;
@@ -632,32 +910,46 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	// ---- K2
 	if ((rc = gd_reserve(ctx, ctx->mp_ht, (size_t)(n_hits + 1) * 8))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_hq, (size_t)(n_hits + 1) * 4))) return rc;
-	if ((rc = gd_reserve(ctx, ctx->mp_cand_tmp, (size_t)n * o->af_max_loc * sizeof(gd_sr_cand_t)))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_cand_tmp, (size_t)n * per_read * sizeof(gd_sr_cand_t)))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_ncand, (size_t)(n + 1) * 4))) return rc;
-	if ((rc = gd_reserve(ctx, ctx->mp_coff, (size_t)(n + 2) * 8))) return rc;
-	gd_sr_vote_kernel<<<blocks, SR_WARPS * 32, 0, s>>>(idx->d, P, n, d_len, K.job_off, K.raw, (const uint32_t *)ctx->mp_seed_n.p,
-	                                                 (const uint32_t *)ctx->mp_seed_first.p, (const SrRead *)ctx->mp_state.p,
-	                                                 (const int64_t *)ctx->mp_hoff.p, (uint64_t *)ctx->mp_ht.p, (uint32_t *)ctx->mp_hq.p,
-	                                                 (gd_sr_cand_t *)ctx->mp_cand_tmp.p, (uint32_t *)ctx->mp_ncand.p);
+	if ((rc = gd_reserve(ctx, ctx->mp_coff, (size_t)(n + 4) * 8))) return rc;
+	int *d_span = (int *)((int64_t *)ctx->mp_coff.p + n + 1); // widest query / target of any candidate (long reads)
+	if (lr) {
+		GD_CUDA_OK(ctx, cudaMemsetAsync(d_span, 0, 4, s));
+		gd_lr_vote_kernel<<<blocks, SR_WARPS * 32, 0, s>>>(idx->d, P, n, d_len, K.job_off, K.raw, (const uint32_t *)ctx->mp_seed_n.p,
+		                                                 (const uint32_t *)ctx->mp_seed_first.p, (const SrRead *)ctx->mp_state.p,
+		                                                 (const int64_t *)ctx->mp_hoff.p, (uint64_t *)ctx->mp_ht.p, (uint32_t *)ctx->mp_hq.p,
+		                                                 (gd_sr_cand_t *)ctx->mp_cand_tmp.p, (uint32_t *)ctx->mp_ncand.p, d_span);
+	} else
+		gd_sr_vote_kernel<<<blocks, SR_WARPS * 32, 0, s>>>(idx->d, P, n, d_len, K.job_off, K.raw, (const uint32_t *)ctx->mp_seed_n.p,
+		                                                 (const uint32_t *)ctx->mp_seed_first.p, (const SrRead *)ctx->mp_state.p,
+		                                                 (const int64_t *)ctx->mp_hoff.p, (uint64_t *)ctx->mp_ht.p, (uint32_t *)ctx->mp_hq.p,
+		                                                 (gd_sr_cand_t *)ctx->mp_cand_tmp.p, (uint32_t *)ctx->mp_ncand.p);
 	ctx->stat_launches++;
 	GD_CUDA_OK(ctx, cudaGetLastError());
 	if ((rc = scan_u32(ctx, (const uint32_t *)ctx->mp_ncand.p, (int64_t *)ctx->mp_coff.p, n))) return rc;
-	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, (int64_t *)ctx->mp_coff.p + n, 8, cudaMemcpyDeviceToHost, s));
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, (int64_t *)ctx->mp_coff.p + n, 16, cudaMemcpyDeviceToHost, s));
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(cand_off, ctx->mp_coff.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
 	const int64_t nc = h_word[0];
+	int max_q = max_len, max_t = max_len; // upper bounds of the DP shapes
+	if (lr) {
+		const int span = (int)(h_word[1] & 0xffffffff);
+		max_q = std::min(max_len, std::max(span, 1)), max_t = std::max(span, 1);
+		P.stride = (std::max(span, 1) + 15) / 16 * 16;
+	}
 	clk.mark("vote");
 	*n_cand_out = nc, *n_cig_out = 0;
 	for (int i = 0; i <= n; ++i) cand_off[i] += cand_base;
 	if (nc == 0) return GD_OK;
 	// ---- K3
 	if ((rc = gd_reserve(ctx, ctx->mp_cand, (size_t)nc * sizeof(gd_sr_cand_t)))) return rc;
-	if ((rc = gd_reserve(ctx, ctx->mp_qbuf, (size_t)nc * P.stride + 64))) return rc;
-	if ((rc = gd_reserve(ctx, ctx->mp_tbuf, (size_t)nc * P.stride + 64))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_qbuf, (size_t)nc * P.stride + 256))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_tbuf, (size_t)nc * P.stride + 256))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_cnt, (size_t)(std::max<int64_t>(nc, n) + 1) * 4))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_hoff, (size_t)(std::max<int64_t>(nc, n) + 2) * 8))) return rc;
 	gd_sr_cand_t *d_cand = (gd_sr_cand_t *)ctx->mp_cand.p;
-	gd_sr_compact_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, o->af_max_loc, (const gd_sr_cand_t *)ctx->mp_cand_tmp.p,
+	gd_sr_compact_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, per_read, (const gd_sr_cand_t *)ctx->mp_cand_tmp.p,
 	                                                   (const int64_t *)ctx->mp_coff.p, d_cand);
 	const int wblocks = (int)std::max<int64_t>(1, std::min<int64_t>((nc + 3) / 4, (int64_t)ctx->sms * 16));
 	gd_sr_window_kernel<<<wblocks, 128, 0, s>>>(idx->d, P, nc, d_off, d_len, d_buf, d_cand, (uint8_t *)ctx->mp_qbuf.p,
@@ -671,7 +963,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	const int64_t np = h_word[0];
 	clk.mark("window");
 	// ---- DP on the candidates that are not exact matches (flag KSW_EZ_APPROX_MAX, map.c:867)
-	const int cig_stride = 2 * P.stride;
+	const int cig_stride = max_q + max_t + 8;
 	if (np > 0) {
 		if (np > 0x7fffffff) {
 			ctx->err = "gd_sr_map_batch: too many DP pairs in one slice";
@@ -679,18 +971,18 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 		}
 		if ((rc = gd_reserve(ctx, ctx->mp_pair, (size_t)np * 16 + 64))) return rc;
 		if ((rc = gd_reserve(ctx, ctx->mp_ez, (size_t)np * sizeof(gd_extz_t)))) return rc;
-		if ((rc = gd_reserve(ctx, ctx->mp_cig, (size_t)np * cig_stride * 4))) return rc;
+		if ((rc = gd_reserve(ctx, ctx->mp_cig, (size_t)np * cig_stride * 4 + 64))) return rc;
 		int64_t *d_poff = (int64_t *)ctx->mp_pair.p;
-		int32_t *d_plen = (int32_t *)(d_poff + np), *d_pcand = d_plen + np;
-		gd_sr_pairs_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(nc, P.stride, d_cand, d_pair_off, d_plen, d_poff, d_pcand);
+		int32_t *d_pqlen = (int32_t *)(d_poff + np), *d_ptlen = d_pqlen + np;
+		gd_sr_pairs_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(nc, P.stride, d_cand, d_pair_off, d_pqlen, d_ptlen, d_poff);
 		ctx->stat_launches++;
 		int8_t mat[25]; // map.c:861-865
 		const int g = o->a, bb = o->b < 0 ? o->b : -o->b;
 		for (int x = 0; x < 5; ++x)
 			for (int y = 0; y < 5; ++y) mat[x * 5 + y] = (x == 4 || y == 4) ? 0 : (x == y ? g : bb);
 		gd_ksw_params_t prm = {5, mat, o->q, o->e, o->q2, o->e2, o->zdrop, o->end_bonus, 0x08};
-		if ((rc = gd_ksw_run_device(ctx, (int)np, d_plen, d_poff, (const uint8_t *)ctx->mp_qbuf.p, d_plen, d_poff,
-		                            (const uint8_t *)ctx->mp_tbuf.p, nullptr, (int)o->bw, max_len, max_len, (int)o->bw, &prm,
+		if ((rc = gd_ksw_run_device(ctx, (int)np, d_pqlen, d_poff, (const uint8_t *)ctx->mp_qbuf.p, d_ptlen, d_poff,
+		                            (const uint8_t *)ctx->mp_tbuf.p, nullptr, (int)o->bw, max_q, max_t, (int)o->bw, &prm,
 		                            (gd_extz_t *)ctx->mp_ez.p, (uint32_t *)ctx->mp_cig.p, cig_stride)))
 			return rc;
 	}
@@ -747,7 +1039,7 @@ extern "C" int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const in
 	for (int b = 0; b < n; b += slice) {
 		const int m = std::min(slice, n - b);
 		int64_t nc = 0, ng = 0;
-		int rc = sr_map_slice(ctx, idx, m, off + b, len + b, buf, o, cand_base, cig_base, cand_off + b, cand, cand_cap, cigar, cigar_cap, &nc, &ng);
+		int rc = sr_map_slice(ctx, idx, m, off + b, len + b, buf, o, nullptr, cand_base, cig_base, cand_off + b, cand, cand_cap, cigar, cigar_cap, &nc, &ng);
 		if (rc) return rc;
 		cand_base += nc, cig_base += ng;
 	}
@@ -758,6 +1050,51 @@ extern "C" int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const in
 	}
 	if (cand_base > cand_cap || cig_base > cigar_cap || (cand_base && !cand) || (cig_base && !cigar)) {
 		ctx->err = "gd_sr_map_batch: output buffer too small";
+		return GD_ERR_CAPACITY;
+	}
+	return GD_OK;
+}
+
+extern "C" int gd_lr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
+                               const gd_lr_opt_t *lr, int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar,
+                               int64_t cigar_cap, int64_t *n_cigar)
+{
+	if (!ctx) return GD_ERR_ARG;
+	if (!idx || !lr || n < 0 || !cand_off || (n > 0 && (!off || !len || !buf))) {
+		ctx->err = "gd_lr_map_batch: bad argument";
+		return GD_ERR_ARG;
+	}
+	if (lr->vt_nb_loc < 1 || lr->vt_nb_loc > SR_MAX_LOC || lr->W < 1 || lr->W > 63 || idx->device != ctx->device) {
+		ctx->err = "gd_lr_map_batch: need 1 <= vt_nb_loc <= 32, 1 <= W <= 63 and an index built on this device";
+		return GD_ERR_ARG;
+	}
+	gd_sr_opt_t o; // the fields both trees share
+	memset(&o, 0, sizeof(o));
+	o.W = lr->W, memcpy(o.Z, lr->Z, sizeof(o.Z)), o.max_seeds = lr->max_seeds, o.frag_mode = lr->frag_mode, o.max_frag_len = lr->max_frag_len;
+	o.bw = lr->bw, o.af_max_loc = (int32_t)lr->vt_nb_loc + 2, o.mid_occ = lr->mid_occ, o.max_max_occ = lr->max_max_occ, o.occ_dist = lr->occ_dist;
+	o.q_occ_frac = lr->q_occ_frac, o.for_only = lr->for_only, o.rev_only = lr->rev_only;
+	o.a = lr->a, o.b = lr->b, o.q = lr->q, o.e = lr->e, o.q2 = lr->q2, o.e2 = lr->e2, o.zdrop = lr->zdrop, o.end_bonus = lr->end_bonus;
+	cand_off[0] = 0;
+	if (n_cigar) *n_cigar = 0;
+	if (n == 0) return GD_OK;
+	cudaSetDevice(ctx->device);
+	int64_t cand_base = 0, cig_base = 0;
+	for (int b = 0; b < n;) { // slices of at most 64 Mbases (the sketch lists and hit arrays scale with the bases)
+		int m = 0;
+		int64_t bases = 0;
+		while (b + m < n && m < (1 << 18) && (m == 0 || bases + len[b + m] <= (64ll << 20))) bases += len[b + m], ++m;
+		int64_t nc = 0, ng = 0;
+		int rc = sr_map_slice(ctx, idx, m, off + b, len + b, buf, &o, lr, cand_base, cig_base, cand_off + b, cand, cand_cap, cigar, cigar_cap, &nc, &ng);
+		if (rc) return rc;
+		cand_base += nc, cig_base += ng, b += m;
+	}
+	if (n_cigar) *n_cigar = cig_base;
+	if (cig_base > 0x7fffffff) {
+		ctx->err = "gd_lr_map_batch: CIGAR pool of one call exceeds 2^31 entries; map fewer reads per call";
+		return GD_ERR_ARG;
+	}
+	if (cand_base > cand_cap || cig_base > cigar_cap || (cand_base && !cand) || (cig_base && !cigar)) {
+		ctx->err = "gd_lr_map_batch: output buffer too small";
 		return GD_ERR_CAPACITY;
 	}
 	return GD_OK;

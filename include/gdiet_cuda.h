@@ -269,6 +269,36 @@ int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off,
                     const gd_sr_opt_t *opt, int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar,
                     int64_t cigar_cap, int64_t *n_cigar);
 
+/* Long-read tree (GDiet-LongReads/map.c:1273-1853; defaults LR/main.c:170-182, presets LR/options.c:86-111): the
+ * mm_mapopt_t fields read between mm_sketch2 and ksw_extd2.  bw is opt->bw (-r); mid_occ is what mm_mapopt_update
+ * derives from the index (gd_index_cal_max_occ clamped to [min_mid_occ, max_mid_occ], LR/options.c:62-71). */
+typedef struct {
+	int32_t W;
+	char Z[64];
+	float max_seeds;
+	int32_t frag_mode, max_frag_len;
+	uint32_t bw;
+	int32_t mid_occ, max_max_occ, occ_dist;
+	float q_occ_frac;
+	int32_t for_only, rev_only;
+	int32_t a, b, q, e, q2, e2, zdrop, end_bonus;
+	uint32_t vt_dis, vt_nb_loc;          /* --vt_dis, --vt_nb_loc (<= 32) */
+	float vt_cov, vt_df1, vt_df2, vt_f;  /* --vt_cov, --vt_df1, --vt_df2, --vt_f */
+	uint32_t max_max_gap, max_min_gap;   /* --max_max_gap, --max_min_gap */
+} gd_lr_opt_t;
+
+/* mm_map_frag of the long-read tree for a batch of reads, from the read's ASCII up to the ksw_extz_t of every
+ * candidate (everything before mm_update_extra / concatenate_cigars, LR/map.c:1293-1805): both sketch calls,
+ * mm_get_shift, seed filters, collect_seed_hits with the merge-sort hit order (--sort=merge, the default of the
+ * long-read presets), vote x2, density and score filters, vote_2 x2 on the uncovered read ends, candidate chaining,
+ * window arithmetic, ksw_extd2 (flag KSW_EZ_APPROX_MAX, band bw).  Output as gd_sr_map_batch, candidates in the
+ * order of the loop at LR/map.c:1654; cand.reserved[0] = index (within the read) of the candidate that continues
+ * this one (vt_t::next, -1 = none), cand.reserved[1] = vt_t::concat; score == KSW_NEG_INF marks the candidates the
+ * reference drops at LR/map.c:1812. */
+int gd_lr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
+                    const gd_lr_opt_t *opt, int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar,
+                    int64_t cigar_cap, int64_t *n_cigar);
+
 /* ------------------------------------------------------------------------------------------ */
 /* (4) host side after the DP -- plain C++, no GPU work            */
 /* ------------------------------------------------------------------------------------------ */

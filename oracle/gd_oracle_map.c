@@ -432,3 +432,360 @@ int gdo_sr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_
 	if (dbg) *dbg = d;
 	return (int)n_out;
 }
+
+/* ========================================================================================== */
+/* Long reads: GDiet-LongReads/map.c:mm_map_frag (:1273-1853) up to (not including)           */
+/* mm_update_extra / concatenate_cigars                                                        */
+/* ========================================================================================== */
+typedef struct { /* vt_t, LR/map.c:1032-1045 */
+	uint32_t chrom_id;
+	int32_t first_target_loc, last_target_loc;
+	uint32_t first_query_loc, last_query_loc;
+	unsigned score;
+	int next; /* index into seqs[] instead of a pointer; -1 = NULL */
+	unsigned str, concat;
+} lvt_t;
+
+static int cmp_loc_merge(const void *a, const void *b)
+{ /* the order LR/map.c:merge_sort (:176-255) leaves: ascending target; on ties the later unit (= larger query
+     position, the seed list is position-ordered) first, because merge_locations takes the second run on a tie */
+	const loc_t *p = (const loc_t *)a, *q = (const loc_t *)b;
+	if (p->target != q->target) return p->target < q->target ? -1 : 1;
+	return p->query > q->query ? -1 : p->query < q->query;
+}
+
+static inline uint64_t lr_loc(int str, uint64_t target, uint32_t query, int32_t tmp_ext)
+{
+	return str ? (target - query) : target - (uint64_t)(int64_t)(tmp_ext - (int32_t)query);
+}
+
+static void lr_emit(lvt_t *seqs, unsigned *out_len, unsigned max_loc, uint64_t ft, uint64_t lt, uint32_t fq, uint32_t lq,
+                    unsigned counter, int str, int *skipped)
+{
+	unsigned k;
+	*skipped = 0;
+	if (*out_len == max_loc) {
+		if (seqs[*out_len - 1].score >= counter) { *skipped = 1; return; }
+	} else
+		++*out_len;
+	seqs[*out_len - 1].chrom_id = (uint32_t)(ft >> 32), seqs[*out_len - 1].first_target_loc = (int32_t)(uint32_t)ft;
+	seqs[*out_len - 1].last_target_loc = (int32_t)(uint32_t)lt, seqs[*out_len - 1].first_query_loc = fq;
+	seqs[*out_len - 1].last_query_loc = lq, seqs[*out_len - 1].str = str, seqs[*out_len - 1].score = counter;
+	seqs[*out_len - 1].next = -1, seqs[*out_len - 1].concat = 0;
+	for (k = *out_len - 1; k > 0; k--) {
+		if (seqs[k].score > seqs[k - 1].score) {
+			lvt_t t = seqs[k];
+			seqs[k] = seqs[k - 1], seqs[k - 1] = t;
+		} else
+			break;
+	}
+}
+
+/* LR/map.c:1052-1182 */
+static void lr_vote(const loc_t *loc, unsigned len, int str, lvt_t *seqs, unsigned *nb, uint32_t dist, int32_t tmp_ext,
+                    unsigned max_loc, uint32_t cov_thr)
+{
+	unsigned i, counter = 1, out_len = *nb;
+	uint64_t ft, lt, ref_loc;
+	uint32_t fq, lq;
+	int skipped;
+	if (len == 0) return;
+	ft = lt = lr_loc(str, loc[0].target, loc[0].query, tmp_ext), fq = lq = loc[0].query, ref_loc = loc[0].target;
+	for (i = 1; i < len; i++) {
+		loc_t cur = loc[i];
+		if (cur.target - ref_loc <= dist) {
+			uint64_t l = lr_loc(str, cur.target, cur.query, tmp_ext);
+			counter++;
+			if (cur.query < fq) fq = cur.query, ref_loc = cur.target;
+			if (cur.query > lq) lq = cur.query;
+			if (l > lt) lt = l;
+			if (l < ft) ft = l;
+		} else {
+			if (lq - fq > cov_thr) lr_emit(seqs, &out_len, max_loc, ft, lt, fq, lq, counter, str, &skipped);
+			ft = lt = lr_loc(str, cur.target, cur.query, tmp_ext), fq = lq = cur.query, ref_loc = cur.target, counter = 1;
+		}
+	}
+	if (lq - fq > cov_thr) lr_emit(seqs, &out_len, max_loc, ft, lt, fq, lq, counter, str, &skipped);
+	*nb = out_len;
+}
+
+/* LR/map.c:1184-1271 */
+static void lr_vote_2(const loc_t *loc, unsigned len, int str, lvt_t *vt, unsigned dist, int32_t tmp_ext, uint32_t min, uint32_t max)
+{
+	unsigned i, counter = 1;
+	uint64_t ft, lt, ref_loc;
+	uint32_t fq, lq;
+	lvt_t best = *vt;
+	if (len == 0) return;
+	ft = lt = lr_loc(str, loc[0].target, loc[0].query, tmp_ext), fq = lq = loc[0].query, ref_loc = loc[0].target;
+	for (i = 1; i <= len; i++) {
+		if (i < len && loc[i].target - ref_loc <= dist) {
+			loc_t cur = loc[i];
+			if (cur.query < max && cur.query > min) {
+				uint64_t l = lr_loc(str, cur.target, cur.query, tmp_ext);
+				counter++;
+				if (cur.query < fq) fq = cur.query, ref_loc = cur.target;
+				if (cur.query > lq) lq = cur.query;
+				if (l > lt) lt = l;
+				if (l < ft) ft = l;
+			}
+		} else {
+			if (counter > best.score && lq < max && fq > min) {
+				best.chrom_id = (uint32_t)(ft >> 32), best.first_target_loc = (int32_t)(uint32_t)ft;
+				best.last_target_loc = (int32_t)(uint32_t)lt, best.first_query_loc = fq, best.last_query_loc = lq;
+				best.str = str, best.score = counter, best.next = -1, best.concat = 0;
+			}
+			if (i < len) {
+				loc_t cur = loc[i];
+				ft = lt = lr_loc(str, cur.target, cur.query, tmp_ext), fq = lq = cur.query, ref_loc = cur.target, counter = 1;
+			}
+		}
+	}
+	*vt = best;
+}
+
+static void lr_second_round(const gdo_lr_opt_t *o, int k, const loc_t *a_for, unsigned n_for, const loc_t *a_rev, unsigned n_rev,
+                            int32_t tmp_ext, uint32_t min, uint32_t max, lvt_t *seqs, unsigned *nb)
+{ /* LR/map.c:1402-1445 */
+	lvt_t v2;
+	const unsigned bw = o->bw;
+	memset(&v2, 0, sizeof(v2));
+	v2.next = -1;
+	lr_vote_2(a_for, n_for, 0, &v2, o->vt_dis, tmp_ext, min, max);
+	lr_vote_2(a_rev, n_rev, 1, &v2, o->vt_dis, tmp_ext, min, max);
+	v2.first_query_loc -= (k - 1), v2.first_target_loc -= (k - 1);
+	if ((float)v2.score > o->vt_df2 * (float)(v2.last_target_loc - v2.first_target_loc)) {
+		if (v2.last_query_loc - v2.first_query_loc + 0.5 * bw < v2.last_target_loc - v2.first_target_loc)
+			v2.last_target_loc = v2.first_target_loc + v2.last_query_loc - v2.first_query_loc + 0.5 * bw;
+		seqs[(*nb)++] = v2;
+	}
+}
+
+int gdo_lr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_lr_opt_t *o, gdo_sr_cand_t *out, int out_cap,
+                    uint32_t *cigar, int cigar_cap, gdo_sr_dbg_t *dbg)
+{
+	const int k = mi->k, w = mi->w;
+	const unsigned qlen_sum = (unsigned)qlen, bw = o->bw;
+	long cap = qlen + 16, n3;
+	uint64_t *mv = (uint64_t *)malloc((size_t)cap * 16 * (o->W + 1));
+	uint32_t *counts = (uint32_t *)calloc(o->W + 1, 4);
+	unsigned shift = 0, max_hits = 0, s, i, j, nb = 0, n_for = 0, n_rev = 0, n_out = 0;
+	uint32_t max_nb_seeds = o->frag_mode ? (o->max_frag_len == 0 ? 800u : (uint32_t)o->max_frag_len) : UINT32_MAX;
+	uint32_t tmp_ext = 0, cov_thr, qrstart, qrend;
+	size_t n_mv, n_m0, n_m;
+	seed_t *m;
+	int64_t n_a = 0;
+	loc_t *a_for, *a_rev;
+	lvt_t *seqs;
+	int cig_used = 0;
+	uint8_t *qs_for, *qs_rev, *ts;
+	gdo_sr_dbg_t d;
+	memset(&d, 0, sizeof(d));
+	if (qlen <= 0) { free(mv), free(counts); if (dbg) *dbg = d; return 0; }
+	/* pattern alignment + seeding: identical to the short-read tree (LR/map.c:1293-1330) */
+	gdo_mm_sketch2(seq, qlen, w, k, 0, o->Z, o->W, o->max_seeds, mv, cap * (o->W + 1), counts);
+	{
+		uint64_t *p = mv;
+		for (s = 0; s < (unsigned)o->W; ++s) {
+			unsigned cur = 0;
+			for (j = 0; j < counts[s]; ++j) {
+				int t;
+				gdo_index_get(mi, p[2 * j] >> 8, &t);
+				cur += t;
+			}
+			if (cur > max_hits) shift = s, max_hits = cur;
+			p += 2 * counts[s];
+		}
+	}
+	d.shift = shift;
+	n3 = gdo_mm_sketch3(seq, (unsigned)qlen, w, k, 0, o->Z, o->W, (int)shift, max_nb_seeds, mv, cap, &tmp_ext);
+	n_mv = (size_t)n3;
+	d.tmp_extracted_len = tmp_ext;
+	if (o->q_occ_frac > 0.0f) n_mv = mz_flt(mv, n_mv, o->mid_occ, o->q_occ_frac);
+	d.n_mv = (uint32_t)n_mv;
+	m = (seed_t *)calloc(n_mv + 1, sizeof(seed_t));
+	for (i = 0, n_m0 = 0; i < n_mv; ++i) {
+		int t;
+		const uint64_t *cr = gdo_index_get(mi, mv[2 * i] >> 8, &t);
+		if (t == 0) continue;
+		m[n_m0].q_pos = (uint32_t)mv[2 * i + 1], m[n_m0].q_span = mv[2 * i] & 0xff, m[n_m0].cr = cr, m[n_m0].n = t;
+		m[n_m0++].flt = 0;
+	}
+	if (o->occ_dist > 0 && o->max_max_occ > o->mid_occ) seed_select((int32_t)n_m0, m, qlen, o->mid_occ, o->max_max_occ, o->occ_dist);
+	else
+		for (i = 0; i < n_m0; ++i)
+			if ((int32_t)m[i].n > o->mid_occ) m[i].flt = 1;
+	for (i = 0, n_m = 0; i < n_m0; ++i)
+		if (!m[i].flt) n_a += m[i].n, m[n_m++] = m[i];
+	a_for = (loc_t *)malloc((n_a + 1) * sizeof(loc_t)), a_rev = (loc_t *)malloc((n_a + 1) * sizeof(loc_t));
+	for (i = 0; i < n_m; ++i) {
+		uint32_t kk;
+		for (kk = 0; kk < m[i].n; ++kk) {
+			uint64_t r = m[i].cr[kk];
+			uint32_t qpos = m[i].q_pos >> 1, loc = (uint32_t)r >> 1;
+			unsigned str = (r & 1) ^ (m[i].q_pos & 1);
+			if (str ? o->for_only : o->rev_only) continue;
+			if (str) a_rev[n_rev].target = (r >> 32) << 32 | (uint32_t)(loc + qpos), a_rev[n_rev++].query = qpos;
+			else a_for[n_for].target = (r >> 32) << 32 | (uint32_t)(loc + tmp_ext - qpos), a_for[n_for++].query = qpos;
+		}
+	}
+	free(m), free(mv), free(counts);
+	qsort(a_for, n_for, sizeof(loc_t), cmp_loc_merge), qsort(a_rev, n_rev, sizeof(loc_t), cmp_loc_merge);
+	d.n_a_for = n_for, d.n_a_rev = n_rev;
+
+	/* first voting round + density filter, LR/map.c:1342-1369 */
+	cov_thr = (float)qlen_sum * o->vt_cov;
+	d.vt_threshold = cov_thr;
+	seqs = (lvt_t *)calloc(o->vt_nb_loc + 3, sizeof(lvt_t));
+	lr_vote(a_for, n_for, 0, seqs, &nb, o->vt_dis, (int32_t)tmp_ext, o->vt_nb_loc, cov_thr);
+	lr_vote(a_rev, n_rev, 1, seqs, &nb, o->vt_dis, (int32_t)tmp_ext, o->vt_nb_loc, cov_thr);
+	if (nb > 0) {
+		unsigned df = 0;
+		for (i = 0; i < nb; i++)
+			if ((float)seqs[i].score > o->vt_df1 * (float)(seqs[i].last_target_loc - seqs[i].first_target_loc)) seqs[i] = seqs[df], df++;
+		nb = df;
+	}
+	if (nb == 0) { free(a_for), free(a_rev), free(seqs); if (dbg) *dbg = d; return 0; }
+	/* score filter, k-mer start, band guard, covered query range, LR/map.c:1371-1400 */
+	{
+		const unsigned filtering_threshold = (float)seqs[0].score * o->vt_f;
+		qrstart = qlen_sum, qrend = 0;
+		for (i = 0; i < nb; i++) {
+			if (seqs[i].score < filtering_threshold) { nb = i; break; }
+			seqs[i].first_query_loc -= (k - 1), seqs[i].first_target_loc -= (k - 1);
+			seqs[i].next = -1, seqs[i].concat = 0;
+			if (seqs[i].last_query_loc - seqs[i].first_query_loc + 0.5 * bw < seqs[i].last_target_loc - seqs[i].first_target_loc)
+				seqs[i].last_target_loc = seqs[i].first_target_loc + seqs[i].last_query_loc - seqs[i].first_query_loc + 0.5 * bw;
+			if (seqs[i].first_query_loc < qrstart) qrstart = seqs[i].first_query_loc;
+			if (seqs[i].last_query_loc > qrend) qrend = seqs[i].last_query_loc;
+		}
+	}
+	/* second voting round on the uncovered ends, LR/map.c:1402-1445 */
+	if (qrstart > cov_thr) lr_second_round(o, k, a_for, n_for, a_rev, n_rev, (int32_t)tmp_ext, 0, qrstart, seqs, &nb);
+	if (qlen_sum - qrend > cov_thr) lr_second_round(o, k, a_for, n_for, a_rev, n_rev, (int32_t)tmp_ext, qrend, qlen_sum, seqs, &nb);
+	free(a_for), free(a_rev);
+	d.nb_potentials = nb;
+
+	/* which candidates continue each other, LR/map.c:1467-1590 */
+	{
+		const unsigned max_max_gap = o->max_max_gap, max_min_gap = o->max_min_gap;
+		for (i = 0; i < nb; i++) {
+			lvt_t *s1 = &seqs[i];
+			for (j = 0; j < nb; j++) {
+				lvt_t *s2 = &seqs[j];
+				int take = 0, better = 0;
+				if (j == i || s2->concat != 0 || s1->str != s2->str || s1->chrom_id != s2->chrom_id) continue;
+				if (s1->str) {
+					if (s2->last_query_loc < s1->first_query_loc && s1->last_target_loc > s2->first_target_loc &&
+					    s1->first_target_loc < s2->first_target_loc) {
+						take = s2->last_query_loc + max_max_gap > s1->first_query_loc;
+						better = s1->next >= 0 && s2->last_query_loc > seqs[s1->next].last_query_loc;
+					} else if (s2->last_query_loc < s1->first_query_loc && s1->last_target_loc < s2->first_target_loc) {
+						take = (s2->last_query_loc + max_min_gap > s1->first_query_loc ||
+						        s1->last_target_loc + max_min_gap > (unsigned)s2->first_target_loc) &&
+						       s2->last_query_loc + max_max_gap > s1->first_query_loc &&
+						       s1->last_target_loc + max_max_gap > (unsigned)s2->first_target_loc;
+						better = s1->next >= 0 && s2->last_query_loc > seqs[s1->next].last_query_loc;
+					} else if (s2->last_query_loc > s1->first_query_loc && s1->last_target_loc < s2->first_target_loc &&
+					           s2->last_query_loc < s1->last_query_loc && s2->first_query_loc < s1->first_query_loc) {
+						take = s1->last_target_loc + max_max_gap > (unsigned)s2->first_target_loc;
+						better = s1->next >= 0 && s2->last_query_loc < seqs[s1->next].last_query_loc;
+					}
+				} else {
+					if (s1->last_query_loc < s2->first_query_loc && s1->last_target_loc > s2->first_target_loc &&
+					    s1->first_target_loc < s2->first_target_loc) {
+						take = s1->last_query_loc + max_max_gap > s2->first_query_loc;
+						better = s1->next >= 0 && s2->first_query_loc < seqs[s1->next].first_query_loc;
+					} else if (s1->last_query_loc < s2->first_query_loc && s1->last_target_loc < s2->first_target_loc) {
+						take = (s1->last_query_loc + max_min_gap > s2->first_query_loc ||
+						        s1->last_target_loc + max_min_gap > (unsigned)s2->first_target_loc) &&
+						       s1->last_target_loc + max_max_gap > (unsigned)s2->first_target_loc &&
+						       s1->last_query_loc + max_max_gap > s2->first_query_loc;
+						better = s1->next >= 0 && s2->first_query_loc < seqs[s1->next].first_query_loc;
+					} else if (s1->last_query_loc > s2->first_query_loc && s1->last_target_loc < s2->first_target_loc &&
+					           s1->first_query_loc < s2->first_query_loc && s1->last_query_loc < s2->last_query_loc) {
+						take = s1->last_target_loc + max_max_gap > (unsigned)s2->first_target_loc;
+						better = s1->next >= 0 && s2->first_query_loc < seqs[s1->next].first_query_loc;
+					}
+				}
+				if (take && (s1->next < 0 || better)) s1->next = (int)j;
+			}
+			if (s1->next >= 0) {
+				lvt_t *s2 = &seqs[s1->next];
+				s2->concat = 1;
+				if (s1->str) {
+					if (s2->last_query_loc < s1->first_query_loc && s1->last_target_loc < s2->first_target_loc) {
+						const uint32_t diffq = s1->first_query_loc - s2->last_query_loc, difft = s2->first_target_loc - s1->last_target_loc;
+						const uint32_t mn = difft > diffq ? diffq : difft;
+						s2->last_query_loc += mn, s1->last_target_loc += mn, s1->first_query_loc -= mn, s2->first_target_loc -= mn;
+					}
+				} else {
+					if (s1->last_query_loc < s2->first_query_loc && s1->last_target_loc < s2->first_target_loc) {
+						const uint32_t diffq = s2->first_query_loc - s1->last_query_loc, difft = s2->first_target_loc - s1->last_target_loc;
+						const uint32_t mn = difft > diffq ? diffq : difft;
+						s1->last_query_loc += mn, s1->last_target_loc += mn, s2->first_query_loc -= mn, s2->first_target_loc -= mn;
+					}
+				}
+				if (s2->last_target_loc < s1->last_target_loc) s1->last_target_loc = s2->last_target_loc - 1;
+			}
+		}
+	}
+
+	/* windows + DP, LR/map.c:1654-1805 */
+	qs_for = (uint8_t *)malloc(qlen_sum), qs_rev = (uint8_t *)malloc(qlen_sum);
+	for (i = 0; i < qlen_sum; ++i) qs_for[i] = nt4c((unsigned char)seq[i]), qs_rev[qlen_sum - i - 1] = qs_for[i] ^ 3;
+	for (i = 0; i < nb && (int)n_out < out_cap; ++i) {
+		const int str = seqs[i].str;
+		const unsigned target_id = seqs[i].chrom_id;
+		uint32_t target_start = seqs[i].first_target_loc, target_end = seqs[i].last_target_loc, query_start, query_end, ql, tl, jj;
+		const uint8_t *qseq;
+		gdo_sr_cand_t *c = &out[n_out];
+		int8_t mat[25];
+		gdo_extz_t ez;
+		const int32_t chrom_len = (int32_t)mi->len[target_id];
+		if (str) query_end = qlen_sum - 1 - seqs[i].first_query_loc, query_start = qlen_sum - 1 - seqs[i].last_query_loc;
+		else query_start = seqs[i].first_query_loc, query_end = seqs[i].last_query_loc;
+		if (!(qlen_sum > 300)) {
+			if (target_start < query_start) query_start -= target_start, target_start = 0;
+			else target_start -= query_start, query_start = 0;
+			if ((uint32_t)chrom_len + query_end < qlen_sum + target_end) query_end += chrom_len - target_end - 1, target_end = chrom_len - 1;
+			else target_end += qlen_sum - query_end - 1, query_end = qlen_sum - 1;
+		}
+		qseq = str ? &qs_rev[query_start] : &qs_for[query_start];
+		ql = query_end - query_start + 1, tl = target_end - target_start + 1;
+		if (str) {
+			uint32_t tmp = qlen_sum - 1 - query_start;
+			query_start = qlen_sum - 1 - query_end, query_end = tmp;
+		}
+		ts = (uint8_t *)calloc((size_t)tl + 1, 1);
+		for (jj = 0; jj < tl; ++jj) { /* mm_idx_getseq: clipped at the contig end, index.c:157-166 */
+			int64_t p = (int64_t)target_start + jj;
+			if (p < chrom_len) ts[jj] = mi->codes[mi->offset[target_id] + p];
+		}
+		{
+			int g = o->a, bb = o->b < 0 ? o->b : -o->b, x, y;
+			for (x = 0; x < 5; ++x)
+				for (y = 0; y < 5; ++y) mat[x * 5 + y] = (x == 4 || y == 4) ? 0 : (x == y ? g : bb);
+		}
+		memset(c, 0, sizeof(*c));
+		c->rid = target_id, c->rs = target_start, c->re = target_end + 1, c->qs = query_start, c->qe = query_end + 1, c->rev = str;
+		c->votes = seqs[i].score, c->first_q = seqs[i].first_query_loc, c->last_q = seqs[i].last_query_loc;
+		c->reserved[0] = seqs[i].next, c->reserved[1] = seqs[i].concat;
+		c->cigar_off = cig_used;
+		if (qlen_sum < 300 && ql == tl && gdo_exact_match(ql, qseq, tl, ts)) {
+			c->exact = 1, c->score = qlen_sum * o->a, c->n_cigar = 1;
+			if (cig_used < cigar_cap) cigar[cig_used] = ql << 4;
+			cig_used += 1;
+		} else {
+			gdo_ksw_extd2(ql, qseq, tl, ts, 5, mat, o->q, o->e, o->q2, o->e2, bw, o->zdrop, o->end_bonus, 0x08, 1, &ez,
+			              cigar + cig_used, cigar_cap - cig_used);
+			c->score = ez.score, c->n_cigar = ez.n_cigar;
+			if (ez.n_cigar > 0) cig_used += ez.n_cigar;
+		}
+		free(ts);
+		++n_out;
+	}
+	free(qs_for), free(qs_rev), free(seqs);
+	if (dbg) *dbg = d;
+	return (int)n_out;
+}

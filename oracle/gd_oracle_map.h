@@ -46,6 +46,23 @@ typedef struct {
 	int32_t reserved[3];
 } gdo_sr_cand_t;
 
+/* long-read tree: the mm_mapopt_t fields GDiet-LongReads/map.c:1273-1853 reads (defaults LR/main.c:170-182);
+ * the SAME layout as gd_lr_opt_t of include/gdiet_cuda.h */
+typedef struct {
+	int32_t W;
+	char Z[64];
+	float max_seeds;
+	int32_t frag_mode, max_frag_len;
+	uint32_t bw; /* opt->bw (-r) */
+	int32_t mid_occ, max_max_occ, occ_dist;
+	float q_occ_frac;
+	int32_t for_only, rev_only;
+	int32_t a, b, q, e, q2, e2, zdrop, end_bonus;
+	uint32_t vt_dis, vt_nb_loc;
+	float vt_cov, vt_df1, vt_df2, vt_f;
+	uint32_t max_max_gap, max_min_gap;
+} gdo_lr_opt_t;
+
 typedef struct {
 	uint32_t shift, tmp_extracted_len, n_mv, n_a_for, n_a_rev, vt_threshold, nb_potentials, reserved;
 } gdo_sr_dbg_t;
@@ -59,6 +76,11 @@ int32_t gdo_index_cal_max_occ(const gdo_index_t *mi, float f);
 /* returns the number of candidates written to out[] (<= out_cap); CIGARs are appended to cigar[] */
 int gdo_sr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_sr_opt_t *o, gdo_sr_cand_t *out,
                     int out_cap, uint32_t *cigar, int cigar_cap, gdo_sr_dbg_t *dbg);
+
+/* long reads: candidates in the order of the loop at LR/map.c:1654; reserved[0] = index of the candidate this one is
+ * continued by (vt_t::next, -1 = none), reserved[1] = vt_t::concat */
+int gdo_lr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_lr_opt_t *o, gdo_sr_cand_t *out, int out_cap,
+                    uint32_t *cigar, int cigar_cap, gdo_sr_dbg_t *dbg);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ import gdiet_b200 as gd
 from gdiet_b200 import synth
 
 REF_SR = os.path.join(ORACLE_DIR, "_ref", "GDiet_avx_sr")
+REF_LR = os.path.join(ORACLE_DIR, "_ref", "GDiet_avx_lr")
 
 CAND_FIELDS = ["rid", "rs", "re", "qs", "qe", "rev", "votes", "first_q", "last_q", "exact", "score", "n_cigar", "cigar_off"]
 CAND_DTYPE = np.dtype([(f, np.int32) for f in CAND_FIELDS] + [("reserved", np.int32, 3)])
@@ -99,7 +100,46 @@ def have_ref_program():
     return os.path.exists(REF_SR)
 
 
-def run_reference(contigs, reads, flags, threads=1, trace=True, workdir=None):
+def make_long_dataset(seed=1, contig_lens=(1500000, 800000), n_reads=60, read_len=15000, sub=0.005, indel=0.005, sv_frac=0.3,
+                      len_jitter=0.2):
+    """HiFi / ONT-like reads (ragged lengths) with substitutions and indels; a fraction carries a large deletion or a
+    jump (so that the second voting round and the candidate chaining of LR/map.c:1402-1590 are exercised) and some are
+    chimeric or unmappable."""
+    rng = np.random.default_rng(seed)
+    contigs = [synth.random_genome(n, seed=seed * 100 + i) for i, n in enumerate(contig_lens)]
+    lut = np.zeros(256, np.uint8)
+    lut[synth.ACGTN] = np.arange(5)
+    reads = []
+    for i in range(n_reads):
+        L = int(read_len * (1 + len_jitter * (rng.random() - 0.5)))
+        u = rng.random()
+        if u < 0.04:
+            codes = rng.integers(0, 4, L).astype(np.uint8)
+        else:
+            ci = int(rng.integers(0, len(contigs)))
+            c = contigs[ci]
+            span = int(L * 1.15) + 8000
+            st = int(rng.integers(0, len(c) - span)) if rng.random() > 0.06 else int(rng.integers(0, 2) * (len(c) - span))
+            src = lut[c[st:st + span]]
+            if u < 0.04 + sv_frac:
+                cut = int(rng.integers(L // 4, 3 * L // 4))
+                gap = int(rng.choice([300, 1500, 5000]))
+                if rng.random() < 0.5:
+                    src = np.concatenate([src[:cut], src[cut + gap:]])           # deletion in the read
+                else:
+                    src = np.concatenate([src[:cut], rng.integers(0, 4, gap).astype(np.uint8), src[cut:]])  # insertion
+            elif u < 0.08 + sv_frac:
+                c2 = contigs[int(rng.integers(0, len(contigs)))]
+                st2 = int(rng.integers(0, len(c2) - L))
+                src = np.concatenate([src[:L // 2], lut[c2[st2:st2 + L]]])       # chimeric
+            codes = synth.mutate_codes(rng, src, sub + indel, sub=sub / (sub + indel), dele=indel / (sub + indel) / 2)[:L]
+        if rng.random() < 0.5:
+            codes = np.where(codes < 4, 3 - codes, 4)[::-1]
+        reads.append(synth.ACGTN[codes])
+    return contigs, reads
+
+
+def run_reference(contigs, reads, flags, threads=1, trace=True, workdir=None, program=None):
     """Runs the unmodified reference (GDiet_avx build) on the dataset; returns (sam_text, trace_records)."""
     tmp = workdir or tempfile.mkdtemp(prefix="gdref_")
     fa, fq, sam, tr = (os.path.join(tmp, x) for x in ("ref.fa", "reads.fq", "out.sam", "trace.bin"))
@@ -108,7 +148,7 @@ def run_reference(contigs, reads, flags, threads=1, trace=True, workdir=None):
     env = dict(os.environ)
     if trace:
         env["GDREF_TRACE"] = tr
-    subprocess.run([REF_SR, "-t", str(threads)] + flags + ["-o", sam, fa, fq], check=True, env=env,
+    subprocess.run([program or REF_SR, "-t", str(threads)] + flags + ["-o", sam, fa, fq], check=True, env=env,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     with open(sam) as f:
         sam_text = f.read()
@@ -158,7 +198,7 @@ def parse_trace(path):
         elif kind == 4:
             rid, score, qs, qe, rs, re_, rev = i32(7)
             c = reads[-1]["cands"][-1]
-            c.update(rid=rid, qs=qs, qe=qe, rs=rs, re=re_, rev=rev)
+            c.update(rid=rid, qs=qs, qe=qe, rs=rs, re=re_, rev=rev, has_extra=True)
             if c["exact"]:
                 c["score"] = score
                 c["cigar"] = np.array([len(c["q"]) << 4], np.uint32)
@@ -180,6 +220,9 @@ class MapOracle:
         L.gdo_index_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
         L.gdo_index_cal_max_occ.restype = C.c_int32
         L.gdo_index_cal_max_occ.argtypes = [C.c_void_p, C.c_float]
+        L.gdo_lr_map_read.restype = C.c_int
+        L.gdo_lr_map_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(gd.gd_lr_opt_t), C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_int, C.c_void_p]
         L.gdo_sr_map_read.restype = C.c_int
         L.gdo_sr_map_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(SrOpt), C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_int, C.c_void_p]
@@ -209,6 +252,14 @@ class MapOracle:
         return (np.ctypeslib.as_array(s.key, (nk,)).copy(), np.ctypeslib.as_array(s.cnt, (nk,)).copy(),
                 np.ctypeslib.as_array(s.pos, (npos,)).copy())
 
+    def lr_map_read(self, mi, seq, opt, cap=16):
+        out = np.zeros(cap, CAND_DTYPE)
+        cig = np.zeros(cap * (2 * len(seq) + 4096), np.uint32)
+        dbg = np.zeros(1, DBG_DTYPE)
+        n = self.lib.gdo_lr_map_read(mi, bytes(seq), len(seq), C.byref(opt), out.ctypes.data, cap, cig.ctypes.data, len(cig),
+                                     dbg.ctypes.data)
+        return out[:n], cig, dbg[0]
+
     def map_read(self, mi, seq, opt, cap=64):
         out = np.zeros(cap, CAND_DTYPE)
         cig = np.zeros(cap * (2 * len(seq) + 8), np.uint32)
@@ -216,6 +267,22 @@ class MapOracle:
         n = self.lib.gdo_sr_map_read(mi, bytes(seq), len(seq), C.byref(opt), out.ctypes.data, cap, cig.ctypes.data, len(cig),
                                      dbg.ctypes.data)
         return out[:n], cig, dbg[0]
+
+
+def lr_cands_equal_trace(cands, cig, tr_cands, what=""):
+    """Long reads: every DP call of the reference in order (lengths, score, CIGAR) and, where the reference went on to
+    mm_update_extra (score != KSW_NEG_INF), the candidate window."""
+    assert len(cands) == len(tr_cands), "%s: %d candidates, reference made %d DP calls" % (what, len(cands), len(tr_cands))
+    for j, (c, t) in enumerate(zip(cands, tr_cands)):
+        got = (int(c["qe"] - c["qs"]), int(c["re"] - c["rs"]), int(c["score"]), int(c["exact"]))
+        exp = (len(t["q"]), len(t["t"]), t["score"], t["exact"])
+        assert got == exp, "%s cand %d: got (qlen, tlen, score, exact) %s, reference %s" % (what, j, got, exp)
+        if t.get("has_extra"):
+            g2 = tuple(int(c[f]) for f in ("rid", "qs", "qe", "rs", "re", "rev"))
+            e2 = (t["rid"], t["qs"], t["qe"], t["rs"], t["re"], t["rev"])
+            assert g2 == e2, "%s cand %d: window %s, reference %s" % (what, j, g2, e2)
+        gc = cig[int(c["cigar_off"]):int(c["cigar_off"]) + max(int(c["n_cigar"]), 0)]
+        assert np.array_equal(gc, t["cigar"]), "%s cand %d cigar differs (%d vs %d entries)" % (what, j, len(gc), len(t["cigar"]))
 
 
 def cands_equal_trace(cands, cig, tr_cands, what=""):

@@ -150,3 +150,67 @@ def test_sam_end_to_end_golden(ctx):
     sam = gd.sr_sam_batch(names, off, lens, buf, qual, coff, cand, cig, ["chr1", "chr2", "chr3"], contigs, gd.sr_post_options())
     assert sam.decode().splitlines() == want
     idx.close()
+
+
+# ---- long-read tree ---------------------------------------------------------------------------------------------
+def flat_ragged(reads):
+    lens = np.array([len(r) for r in reads], np.int32)
+    off = np.zeros(len(reads), np.int64)
+    off[1:] = np.cumsum(lens[:-1].astype(np.int64))
+    return off, lens, np.concatenate(reads)
+
+
+@pytest.mark.skipif(not (maplib.have_ref_program() and cpu_has_avx512()), reason="needs oracle/_ref/GDiet_avx_lr and AVX-512")
+@pytest.mark.parametrize("case", [
+    (1, "map-hifi", 19, 19, 1000, 15000, 0.005, 0.005, 120, [], {}),
+    (3, "map-hifi", 19, 19, 400, 6000, 0.005, 0.005, 200, ["--vt_nb_loc=2"], dict(vt_nb_loc=2)),
+    (2, "map-ont", 15, 10, 1300, 20000, 0.03, 0.05, 100,
+     ["--vt_dis=1000", "--vt_nb_loc=3", "--vt_df1=0.007", "--vt_df2=0.007", "--max_min_gap=4000", "--vt_f=0.04", "--vt_cov", "0.3",
+      "--sort=merge", "--frag=no"], dict(vt_dis=1000, vt_df1=0.007, vt_df2=0.007, vt_f=0.04, vt_cov=0.3)),
+])
+def test_lr_map_matches_reference_program(ctx, case):
+    """gd_lr_map_batch against the call trace of the unmodified long-read reference program (HiFi- and ONT-like reads
+    with structural variation, chimeras and unmappable reads)."""
+    import gdiet_b200 as gd
+    seed, preset, k, w, bw, read_len, sub, indel, n_reads, extra, okw = case
+    contigs, reads = maplib.make_long_dataset(seed=seed, read_len=read_len, sub=sub, indel=indel, n_reads=n_reads)
+    flags = ["-ax", preset, "-Z", "10", "-W", "2", "-k", str(k), "-w", str(w), "-r", str(bw)] + list(extra)
+    _, tr = maplib.run_reference(contigs, reads, flags, program=maplib.REF_LR, threads=1)
+    idx = ctx.index_build(contigs, w, k, "10")
+    lo, hi = (50, 500) if preset == "map-hifi" else (10, 1000000)
+    mid = min(max(idx.cal_max_occ(2e-4), lo), hi)
+    o = gd.lr_options(preset, bw=bw, mid_occ=mid, **okw)
+    off, lens, buf = flat_ragged(reads)
+    coff, cand, cig = ctx.lr_map_batch(idx, off, lens, buf, o, cand_cap=8 * len(reads), cigar_cap=64 * len(reads) * 256)
+    n_cand = n_chain = 0
+    for i, t in enumerate(tr):
+        mine = cand[coff[i]:coff[i + 1]]
+        maplib.lr_cands_equal_trace(mine, cig, t["cands"], "read %d" % i)
+        n_cand += len(mine)
+        n_chain += int((mine["reserved"][:, 0] >= 0).sum()) if len(mine) else 0
+    assert n_cand >= len(reads) // 3 and n_chain > 0
+    idx.close()
+
+
+def test_lr_map_matches_oracle(ctx, M):
+    """... and against oracle/gd_oracle_map.c including vt_t::next / concat (no reference program needed)."""
+    import gdiet_b200 as gd
+    contigs, reads = maplib.make_long_dataset(seed=5, read_len=5000, sub=0.005, indel=0.005, n_reads=40)
+    idx = ctx.index_build(contigs, 19, 19, "10")
+    mi = M.index_build(contigs, 19, 19, "10")
+    o = gd.lr_options("map-hifi", bw=300, mid_occ=50)
+    off, lens, buf = flat_ragged(reads)
+    coff, cand, cig = ctx.lr_map_batch(idx, off, lens, buf, o, cand_cap=8 * len(reads), cigar_cap=len(reads) * 4096)
+    for i, r in enumerate(reads):
+        oc, ocig, dbg = M.lr_map_read(mi, r, o)
+        mine = cand[coff[i]:coff[i + 1]]
+        assert len(mine) == len(oc), "read %d: %d vs oracle %d (%s)" % (i, len(mine), len(oc), dbg)
+        for j, (a, b) in enumerate(zip(mine, oc)):
+            for f in ("rid", "rs", "re", "qs", "qe", "rev", "votes", "first_q", "last_q", "exact", "score", "n_cigar"):
+                assert int(a[f]) == int(b[f]), "read %d cand %d field %s: %d vs oracle %d" % (i, j, f, a[f], b[f])
+            assert tuple(a["reserved"][:2]) == tuple(b["reserved"][:2]), "read %d cand %d next/concat" % (i, j)
+            ga = cig[int(a["cigar_off"]):int(a["cigar_off"]) + max(int(a["n_cigar"]), 0)]
+            gb = ocig[int(b["cigar_off"]):int(b["cigar_off"]) + max(int(b["n_cigar"]), 0)]
+            assert np.array_equal(ga, gb), "read %d cand %d cigar" % (i, j)
+    idx.close()
+    M.lib.gdo_index_destroy(mi)

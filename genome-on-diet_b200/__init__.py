@@ -150,6 +150,18 @@ def sr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, 
     return txt
 
 
+def mmi_write(path, w, k, names, lens, keys, counts, positions, S, bucket_bits=14, flag=0):
+    """gd_mmi_write: the reference's .mmi file from the exported index arrays."""
+    L = load()
+    n_arr = _cstr_array(names)
+    lens = np.ascontiguousarray(lens, np.int32)
+    rc = L.gd_mmi_write(path.encode(), w, k, bucket_bits, flag, len(names), C.cast(n_arr, C.c_void_p), _ptr(lens), len(keys),
+                        _ptr(np.ascontiguousarray(keys, np.uint64)), _ptr(np.ascontiguousarray(counts, np.uint32)),
+                        _ptr(np.ascontiguousarray(positions, np.uint64)), _ptr(np.ascontiguousarray(S, np.uint32)))
+    if rc != GD_OK:
+        raise GdietError("gd_mmi_write failed (%d)" % rc)
+
+
 def sam_header(seq_names, ref_len):
     L = load()
     s_arr = _cstr_array(seq_names)
@@ -223,7 +235,7 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
-           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch"]
+           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write"]
 
 
 def load():
@@ -299,6 +311,8 @@ def load():
     L.gd_index_commit.argtypes = [vp, vp]
     L.gd_lr_map_batch.restype = i32
     L.gd_lr_map_batch.argtypes = [vp, vp, i32, vp, vp, vp, C.POINTER(gd_lr_opt_t), vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.gd_mmi_write.restype = i32
+    L.gd_mmi_write.argtypes = [C.c_char_p, i32, i32, i32, i32, i32, vp, vp, i64, vp, vp, vp, vp]
     L.gd_sr_sam_batch.restype = i32
     L.gd_sr_sam_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
                                   C.POINTER(vp), C.POINTER(C.c_size_t)]

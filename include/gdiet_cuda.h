@@ -326,6 +326,14 @@ int gd_sr_sam_batch(int n, const char *const *names, const int64_t *off, const i
 int gd_sam_header(int n_seq, const char *const *seq_names, const int32_t *ref_len, char **sam, size_t *sam_len);
 void gd_free(void *p);
 
+/* Row F4: the reference's `.mmi` index file (mm_idx_dump, GDiet-ShortReads/index.c:480-517) from the arrays
+ * gd_index_export returns -- byte for byte what `GDiet_avx -d` writes, including the slot order of the per-bucket
+ * khash tables (rebuilt like worker_post, index.c:216-271).  bucket_bits = mm_idxopt_t::bucket_bits (14), flag =
+ * mm_idx_t::flag (0 without -H). */
+int gd_mmi_write(const char *path, int w, int k, int bucket_bits, int flag, int n_seq, const char *const *names,
+                 const int32_t *lens, int64_t n_keys, const uint64_t *keys, const uint32_t *counts, const uint64_t *positions,
+                 const uint32_t *S);
+
 #ifdef __cplusplus
 }
 #endif

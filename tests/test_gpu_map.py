@@ -214,3 +214,22 @@ def test_lr_map_matches_oracle(ctx, M):
             assert np.array_equal(ga, gb), "read %d cand %d cigar" % (i, j)
     idx.close()
     M.lib.gdo_index_destroy(mi)
+
+
+@pytest.mark.skipif(not (maplib.have_ref_program() and cpu_has_avx512()), reason="needs oracle/_ref/GDiet_avx_sr and AVX-512")
+def test_device_index_dumps_the_reference_mmi(ctx):
+    """Row F4: the index built on the device, written with gd_mmi_write, is byte-identical to `GDiet_avx -d`."""
+    import hashlib
+    import tempfile
+    import gdiet_b200 as gd
+    from test_mmi import reference_mmi
+    contigs, _ = maplib.make_dataset(seed=12, contig_lens=(700000, 250000, 50001), n_reads=1)
+    tmp = tempfile.mkdtemp(prefix="gdmmi_")
+    want = reference_mmi(contigs, 21, 11, "10", tmp)
+    idx = ctx.index_build(contigs, 11, 21, "10")
+    keys, counts, pos, S = idx.export()
+    out = os.path.join(tmp, "ours.mmi")
+    gd.mmi_write(out, 11, 21, ["chr1", "chr2", "chr3"], [len(c) for c in contigs], keys, counts, pos, S)
+    got = open(out, "rb").read()
+    assert len(got) == len(want) and hashlib.md5(got).hexdigest() == hashlib.md5(want).hexdigest()
+    idx.close()

@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""BASELINE configs 3 / 4 (long reads), device mapping stage: `-ax map-hifi -Z 10 -W 2 -k 19 -w 19 -r 1000` on 15 kbp
+HiFi-like reads (1 % error) or `-ax map-ont -Z 10 -W 2 -k 15 -w 10 -r 1300` + the README voting flags on 50 kbp ONT-like
+reads (8 % error), against a synthetic reference.  gd_lr_map_batch does everything of LR/map.c:mm_map_frag up to the
+ksw_extz_t of every candidate on the GPU; the CIGAR stitching (concatenate_cigars) and SAM stay with the host program.
+Parity: the first `n_check` reads are compared with the call trace of the unmodified reference program (-t 1); the CPU
+baseline is the same program on all host cores over all reads ([PROFILING] thread-seconds and wall time).
+    python tools/lr_map_bench.py hifi|ont [ref_mbp] [n_reads] [n_check]"""
+import json, os, re, subprocess, sys, tempfile, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import gdiet_b200 as gd
+from gdiet_b200 import synth
+
+ONT_FLAGS = ["--vt_dis=1000", "--vt_nb_loc=3", "--vt_df1=0.007", "--vt_df2=0.007", "--max_min_gap=4000", "--vt_f=0.04", "--vt_cov", "0.3",
+             "--sort=merge", "--frag=no"]
+
+
+def band_cells(ql, tl, w):
+    """banded cells of one ksw_extd2 call: sum over anti-diagonals of en0 - st0 + 1"""
+    r = np.arange(ql + tl - 1, dtype=np.int64)
+    st = np.maximum(np.maximum(0, r - ql + 1), (r - w + 1) >> 1)
+    en = np.minimum(np.minimum(tl - 1, r), (r + w) >> 1)
+    return int(np.maximum(en - st + 1, 0).sum())
+
+
+def main():
+    kind = sys.argv[1] if len(sys.argv) > 1 else "hifi"
+    ref_mbp = float(sys.argv[2]) if len(sys.argv) > 2 else 100
+    n_reads = int(sys.argv[3]) if len(sys.argv) > 3 else (2000 if kind == "hifi" else 500)
+    n_check = int(sys.argv[4]) if len(sys.argv) > 4 else 100
+    if kind == "hifi":
+        preset, k, w, bw, L, sub, indel, extra, okw = "map-hifi", 19, 19, 1000, 15000, 0.005, 0.005, [], {}
+    else:
+        preset, k, w, bw, L, sub, indel, extra = "map-ont", 15, 10, 1300, 50000, 0.03, 0.05, ONT_FLAGS
+        okw = dict(vt_dis=1000, vt_df1=0.007, vt_df2=0.007, vt_f=0.04, vt_cov=0.3)
+    cores = len(os.sched_getaffinity(0))
+    rng = np.random.default_rng(5)
+    ncontig = 4
+    contigs = [synth.random_genome(int(ref_mbp * 1e6) // ncontig, seed=40 + i) for i in range(ncontig)]
+    lut = np.zeros(256, np.uint8)
+    lut[synth.ACGTN] = np.arange(5)
+    reads = []
+    for i in range(n_reads):
+        c = contigs[int(rng.integers(0, ncontig))]
+        st = int(rng.integers(0, len(c) - int(L * 1.2)))
+        codes = synth.mutate_codes(rng, lut[c[st:st + int(L * 1.2)]], sub + indel, sub=sub / (sub + indel), dele=indel / (sub + indel) / 2)[:L]
+        if rng.random() < 0.5:
+            codes = (3 - codes)[::-1]
+        reads.append(synth.ACGTN[codes])
+    lens = np.array([len(r) for r in reads], np.int32)
+    off = np.zeros(n_reads, np.int64)
+    off[1:] = np.cumsum(lens[:-1].astype(np.int64))
+    buf = np.concatenate(reads)
+    ctx = gd.Context(0)
+    ctx.set_option("time_kernels", 1)
+    t0 = time.perf_counter()
+    idx = ctx.index_build(contigs, w, k, "10")
+    t_index = time.perf_counter() - t0
+    lo, hi = (50, 500) if preset == "map-hifi" else (10, 1000000)
+    mid = min(max(idx.cal_max_occ(2e-4), lo), hi)
+    o = gd.lr_options(preset, bw=bw, mid_occ=mid, **okw)
+    tm = []
+    for it in range(3):
+        ctx.stat("ksw_dp_reset")
+        t0 = time.perf_counter()
+        coff, cand, cig = ctx.lr_map_batch(idx, off, lens, buf, o, cand_cap=6 * n_reads, cigar_cap=max(1 << 22, int(lens.sum()) // 4))
+        tm.append(time.perf_counter() - t0)
+        dp_us = ctx.stat("ksw_dp_us")
+    cells = sum(band_cells(int(c["qe"] - c["qs"]), int(c["re"] - c["rs"]), bw) for c in cand if not c["exact"])
+    out = {"what": "config %s: long-read mapping stage on the device" % ("3 (hifi)" if kind == "hifi" else "4 (ont, README voting flags)"),
+           "ref_bp": int(sum(len(c) for c in contigs)), "reads": n_reads, "read_len": L, "band": bw, "mid_occ": mid, "index_build_s": round(t_index, 3),
+           "map_batch_s": [round(x, 3) for x in tm], "reads_per_s": n_reads / min(tm), "bases_per_s": float(lens.sum()) / min(tm),
+           "candidates": int(coff[-1]), "mapped_reads": int((np.diff(coff) > 0).sum()), "chained": int((cand["reserved"][:, 0] >= 0).sum()),
+           "dp_cells": cells, "dp_kernel_ms": dp_us / 1e3, "dp_kernel_gcups": cells / (dp_us * 1e-6) / 1e9 if dp_us else None,
+           "stage_gcups": cells / min(tm) / 1e9, "host_cores": cores}
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_avx_lr")
+    if os.path.exists(ref_bin):
+        import maplib
+        flags = ["-ax", preset, "-Z", "10", "-W", "2", "-k", str(k), "-w", str(w), "-r", str(bw)] + extra
+        if n_check > 0:
+            _, tr = maplib.run_reference(contigs, reads[:n_check], flags, program=ref_bin, threads=1)
+            bad = 0
+            for i, t in enumerate(tr):
+                try:
+                    maplib.lr_cands_equal_trace(cand[coff[i]:coff[i + 1]], cig, t["cands"], "read %d" % i)
+                except AssertionError as e:
+                    bad += 1
+                    if bad <= 3:
+                        print(str(e)[:300], file=sys.stderr)
+            out["parity"] = {"reads_checked": len(tr), "dp_calls_checked": int(sum(len(t["cands"]) for t in tr)), "mismatching_reads": bad}
+        tmp = tempfile.mkdtemp(prefix="gdref_")
+        fa, fq = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq")
+        maplib.write_fasta(fa, contigs)
+        maplib.write_fastq(fq, reads)
+        t0 = time.perf_counter()
+        p = subprocess.run([ref_bin, "-t", str(cores)] + flags + ["-o", os.path.join(tmp, "out.sam"), fa, fq], capture_output=True, text=True)
+        wall = time.perf_counter() - t0
+        prof = dict(re.findall(r"\[PROFILING\] (.+?) time: (\d+) ns", p.stderr))
+        t_idx = int(prof.get("indexing", 0)) * 1e-9
+        out["reference"] = {"wall_s": round(wall, 2), "indexing_s": round(t_idx, 2), "reads_per_s": n_reads / max(wall - t_idx, 1e-9), "threads": cores,
+                            "profile_thread_seconds": {kk: round(int(v) * 1e-9, 2) for kk, v in prof.items()}}
+    print(json.dumps(out), flush=True)
+    idx.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -156,6 +156,9 @@ mm_pattern_t mm_sketch2(void *km, const char *str, int len, int w, int k, uint32
 unsigned mm_sketch3(void *km, const char *str, const unsigned len, int w, int k, uint32_t rid, int is_hpc, mm128_v *p,
                     const char *Z, int W, int shift2, uint32_t MAX_NB_SEEDS);
 
+/* the data symbol sketch.c exports next to its functions (GDiet-ShortReads/sketch.c:11-18) */
+extern unsigned char seq_nt4_table[256];
+
 /* Index-build sketching of n reference sequences (mm_sketch semantics, rid[i] stamped into y):
  * seqs are ASCII in buf at off[i], len[i].  Output minimizers are concatenated in input order:
  * out[out_off[i] .. out_off[i+1]).  Host buffers; returns GD_ERR_CAPACITY with out_off[n] set when

@@ -1,5 +1,8 @@
 // gd_ksw.cu -- kernels and launcher of the batched ksw_extd2 DP (see gd_ksw.cuh for the design).
 #include "gd_ctx.h"
+#include <mutex>
+#include <set>
+#include <utility>
 #include "gd_ksw_host.h"
 #include <algorithm>
 
@@ -225,7 +228,21 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 	const size_t smem = GD_KSW_LUT_BYTES + (size_t)groups_per_block * geo.group_smem;
 	const int mode = exact ? 2 : (flag & KSW_F_APPROX_DROP) ? 1 : 0;
 	dp_kernel_t kern = pick_kernel(G, right, mode, with_p);
-	GD_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	{ // Raise the kernel's dynamic shared-memory limit ONCE, to the device maximum: host threads with their own
+	  // contexts launch the same kernel with different sizes (one call per candidate in the drop-in path), and a
+	  // per-call limit set by one thread would be lowered by another between its set and its launch.
+		static std::mutex mu;
+		static std::set<std::pair<int, const void *>> raised;
+		std::lock_guard<std::mutex> lk(mu);
+		if (!raised.count(std::make_pair(ctx->device, (const void *)kern))) {
+			GD_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+			raised.insert(std::make_pair(ctx->device, (const void *)kern));
+		}
+	}
+	if (smem > ctx->smem_optin) {
+		ctx->err = "ksw_extd2: the column ring of this shape does not fit the shared memory of one block";
+		return GD_ERR_ARG;
+	}
 	int occ = 0;
 	GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
 	if (occ < 1) occ = 1;

@@ -233,3 +233,42 @@ def test_device_index_dumps_the_reference_mmi(ctx):
     got = open(out, "rb").read()
     assert len(got) == len(want) and hashlib.md5(got).hexdigest() == hashlib.md5(want).hexdigest()
     idx.close()
+
+
+def tandem_dataset(seed=7, unit=150, copies=90, n_reads=24, read_len=15000):
+    """Reads that cross a long tandem repeat: one minimizer value then occurs more than mid_occ times INSIDE a read
+    (mm_seed_mz_flt removes it, seed.c:5-29) and more than mid_occ times in the index (mm_seed_select, seed.c:67-113)."""
+    rng = np.random.default_rng(seed)
+    g = synth_genome(900000, seed)
+    u = g[1000:1000 + unit].copy()
+    st = 400000
+    g[st:st + unit * copies] = np.tile(u, copies)
+    lut = np.zeros(256, np.uint8)
+    lut[maplib.synth.ACGTN] = np.arange(5)
+    reads = []
+    for i in range(n_reads):
+        a = st - int(rng.integers(200, read_len - unit * copies - 200)) if i % 3 else int(rng.integers(0, len(g) - read_len))
+        codes = maplib.synth.mutate_codes(rng, lut[g[a:a + read_len + 400]], 0.002, sub=0.5, dele=0.25)[:read_len]
+        if rng.random() < 0.5:
+            codes = (3 - codes)[::-1]
+        reads.append(maplib.synth.ACGTN[codes])
+    return [g], reads
+
+
+def synth_genome(n, seed):
+    return maplib.synth.random_genome(n, seed=1000 + seed)
+
+
+@pytest.mark.skipif(not (maplib.have_ref_program() and cpu_has_avx512()), reason="needs oracle/_ref/GDiet_avx_lr and AVX-512")
+def test_lr_map_tandem_repeats_match_reference_program(ctx):
+    import gdiet_b200 as gd
+    contigs, reads = tandem_dataset()
+    flags = ["-ax", "map-hifi", "-Z", "10", "-W", "2", "-k", "19", "-w", "19", "-r", "1000", "-f", "60"]  # mid_occ = 60
+    _, tr = maplib.run_reference(contigs, reads, flags, program=maplib.REF_LR, threads=1)
+    idx = ctx.index_build(contigs, 19, 19, "10")
+    o = gd.lr_options("map-hifi", bw=1000, mid_occ=60)
+    off, lens, buf = flat_ragged(reads)
+    coff, cand, cig = ctx.lr_map_batch(idx, off, lens, buf, o, cand_cap=8 * len(reads), cigar_cap=64 * len(reads) * 256)
+    for i, t in enumerate(tr):
+        maplib.lr_cands_equal_trace(cand[coff[i]:coff[i + 1]], cig, t["cands"], "read %d" % i)
+    idx.close()

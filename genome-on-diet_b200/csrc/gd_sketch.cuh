@@ -136,6 +136,10 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 	if (tid < 2) sm->F2[NP / 16 + GD_SK_PADW + tid] = 0;
 	if (tid < 4) sm->R2[NP / 16 + tid] = 0;
 	for (int i = tid; i < 64; i += THREADS) sm->ones_loc[i] = S.ones_loc[i];
+	// Tiles are handed out in order by a global ticket, so every tile's predecessors are held by blocks that are already
+	// running: the look-back below can never wait for a block that is not resident.  (Drawing several consecutive tiles
+	// per atomic was tried for the one-warp tiles of short reads and dropped: the first tile of a batch then waits for the
+	// LAST tile of the previous block's batch, which serialises the blocks.)
 	for (;;) {
 		if (tid == 0) sm->tile = atomic_add(B.ticket, 1);
 		sync_block();
@@ -161,6 +165,12 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 		const long long i0 = chunk * S.TP; // first emit position of the tile
 		const long long B0 = i0 - HL;      // sparsified position held in slot 0
 		const int s0 = tid * 8;
+		// A job whose sparsified sequence is shorter than one full window run (w+k-1) cannot emit anything -- the cropped
+		// shift-0 job of mm_sketch2 on a 150 bp read is 15 bases long -- so its tile goes straight to the (empty) output scan.
+		uint32_t real[8], zbits = 0, emit = 0;
+		uint64_t X[8];
+		int cnt = 0;
+		if (dl >= full_run) {
 		// ---- phase 0: stage the original bytes the tile touches, [real(first position), real(last position)] ----
 		const long long jlo = B0 > 0 ? B0 : 0, jhi = (B0 + NP < dl ? B0 + NP : dl) - 1; // loaded positions inside the sequence
 		long long raw_lo = 0; // offset (relative to seq, may be -1..-3) of the first staged byte
@@ -181,7 +191,7 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 		}
 		sync_block();
 		// ---- phase 1: encode 8 positions per thread; positions outside [0,dl) count as N ----
-		uint32_t code = 0, nmask = 0, real[8];
+		uint32_t code = 0, nmask = 0;
 		{
 			const uint32_t raw_lo0 = jhi >= jlo ? sk_real((uint32_t)jlo, shift, S) : 0; // some byte of the sequence that is staged / exists
 			const uint8_t *src = staged ? (const uint8_t *)sm->raw - raw_lo : jhi >= jlo ? (const uint8_t *)seq : (const uint8_t *)sm->raw;
@@ -224,8 +234,8 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 		}
 		// ---- phase 2: the k-mers ending just before the chunk come out of the packed arrays; roll over the 8
 		// positions, hash (sketch.c:1660-1683) ----
-		uint64_t X[8];
-		uint32_t zbits = 0, fullbits = 0;
+
+		uint32_t fullbits = 0;
 		{
 			uint64_t rv = (~sk_bits64(sm->F2, 32 * GD_SK_PADW + 2 * (s0 - k))) & S.mask; // bases s0-k .. s0-1, complemented
 			uint64_t fw = sk_bits64(sm->R2, 2 * (NP - s0)) & S.mask;                       // bases s0-1 .. s0-k
@@ -248,8 +258,8 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 				X[p] = x;
 			}
 		}
-		uint32_t emit = 0;
-		int cnt = 0;
+
+
 		if (w >= 9) {
 			// ---- phase 3: minimum of every full window ending at e = s0+p.  The window starts in an earlier
 			// chunk (w-1 >= 8): own prefix minimum, whole chunks in between, suffix minimum of the first chunk ----
@@ -326,6 +336,7 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 				}
 			}
 		}
+		} // dl >= full_run
 		// ---- block exclusive scan of cnt ----
 		int inc = cnt;
 		for (int d = 1; d < 32; d <<= 1) {

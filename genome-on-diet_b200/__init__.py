@@ -120,6 +120,38 @@ class SamText:
         self.free()
 
 
+def lr_post_options(preset="map-hifi", n_threads=0, **kw):
+    """`-ax map-hifi | map-ont` values (GDiet-LongReads/options.c:86-111, main.c:181)."""
+    sc = dict(a=1, b=4, q=6, e=2, min_dp_max=200) if preset == "map-hifi" else dict(a=2, b=4, q=4, e=2, min_dp_max=40)
+    o = gd_sr_post_opt_t(best_n=5, no_print_2nd=0, is_sr=0, sam_hit_only=0, softclip=0, n_threads=n_threads, **sc)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def lr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, contigs, opt):
+    """gd_lr_sam_batch. Returns (SAM bytes, sam_off[n+1], needs_stitch[n])."""
+    L = load()
+    n = len(lens)
+    ref_len = np.array([len(c) for c in contigs], np.int32)
+    ref_off = np.zeros(len(contigs), np.int64)
+    ref_off[1:] = np.cumsum(ref_len[:-1].astype(np.int64))
+    ref = np.concatenate([np.ascontiguousarray(c, np.uint8) for c in contigs]) if len(contigs) > 1 else np.ascontiguousarray(contigs[0], np.uint8)
+    n_arr, s_arr = _cstr_array(names), _cstr_array(seq_names)
+    out, out_len = C.c_void_p(), C.c_size_t(0)
+    cand = np.ascontiguousarray(cand) if len(cand) else np.zeros(1, SR_CAND_DTYPE)
+    cigar = np.ascontiguousarray(cigar, np.uint32) if len(cigar) else np.zeros(1, np.uint32)
+    sam_off, stitch = np.zeros(n + 1, np.int64), np.zeros(max(n, 1), np.uint8)
+    rc = L.gd_lr_sam_batch(n, C.cast(n_arr, C.c_void_p), _ptr(off), _ptr(lens), _ptr(seq), _ptr(qual), _ptr(cand_off), _ptr(cand),
+                           _ptr(cigar), len(ref_len), C.cast(s_arr, C.c_void_p), _ptr(ref_off), _ptr(ref_len), _ptr(ref), C.byref(opt),
+                           C.byref(out), C.byref(out_len), _ptr(sam_off), _ptr(stitch))
+    if rc != GD_OK:
+        raise GdietError("gd_lr_sam_batch failed (%d)" % rc)
+    txt = C.string_at(out, out_len.value)
+    L.gd_free(out)
+    return txt, sam_off, stitch[:n]
+
+
 def sr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, contigs, opt, raw=False, ref=None):
     """gd_sr_sam_batch: SAM records of a mapped batch (bytes, or a SamText handle with raw=True).
     contigs: list of ASCII uint8 arrays; ref = (ref_off, ref_len, concatenated buffer) may be passed to reuse it."""
@@ -235,7 +267,7 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
-           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write"]
+           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write", "gd_lr_sam_batch"]
 
 
 def load():
@@ -316,6 +348,9 @@ def load():
     L.gd_sr_sam_batch.restype = i32
     L.gd_sr_sam_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
                                   C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.gd_lr_sam_batch.restype = i32
+    L.gd_lr_sam_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
+                                  C.POINTER(vp), C.POINTER(C.c_size_t), vp, vp]
     L.gd_sam_header.restype = i32
     L.gd_sam_header.argtypes = [i32, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.gd_free.restype = None

@@ -322,10 +322,13 @@ struct Ctx {
 	const int32_t *ref_len;
 	const char *ref;
 	const gd_sr_post_opt_t *o;
+	bool long_read;
 };
 
 struct Scratch { // per-thread, reused across reads
-	std::vector<Reg> regs;
+	std::vector<Reg> regs, all;
+	std::vector<int> valid;
+	bool stitch = false; // long reads: a chained pair of valid candidates needs concatenate_cigars (not done here)
 	std::vector<uint8_t> qs, ts;
 	std::vector<uint32_t> cig;
 };
@@ -333,6 +336,8 @@ struct Scratch { // per-thread, reused across reads
 void one_read(const Ctx &C, int i, Out &out, Scratch &T)
 {
 	const gd_sr_post_opt_t &o = *C.o;
+	const bool lr = C.long_read;
+	T.stitch = false;
 	const int qlen = C.len[i];
 	const char *rd = C.seq + C.off[i], *ql = C.qual ? C.qual + C.off[i] : nullptr;
 	const char *name = C.names[i];
@@ -343,6 +348,7 @@ void one_read(const Ctx &C, int i, Out &out, Scratch &T)
 	std::vector<Reg> &regs = T.regs;
 	std::vector<uint8_t> &qs = T.qs, &ts = T.ts;
 	regs.clear();
+	T.all.clear(), T.valid.clear();
 	size_t ncig = 0;
 	for (int64_t ci = C.cand_off[i]; ci < C.cand_off[i + 1]; ++ci) ncig += C.cand[ci].n_cigar > 0 ? (size_t)C.cand[ci].n_cigar : 0;
 	if (T.cig.size() < ncig + 1) T.cig.resize(2 * ncig + 64);
@@ -350,6 +356,10 @@ void one_read(const Ctx &C, int i, Out &out, Scratch &T)
 	for (int64_t ci = C.cand_off[i]; ci < C.cand_off[i + 1]; ++ci) { // map.c:932-978
 		const gd_sr_cand_t &c = C.cand[ci];
 		Reg r = Reg();
+		if (lr && c.score == -0x40000000) { // LR/map.c:1812: the candidate is dropped (valid = 0)
+			T.all.push_back(r), T.valid.push_back(0);
+			continue;
+		}
 		r.rid = c.rid, r.score = c.score, r.qs = c.qs, r.qe = c.qe, r.rs = c.rs, r.re = c.re, r.rev = c.rev;
 		r.dp_score = c.score;
 		if (c.n_cigar > 0) {
@@ -361,17 +371,37 @@ void one_read(const Ctx &C, int i, Out &out, Scratch &T)
 		{ // map.c:737-757
 			uint8_t *qd = qs.data(), *td = ts.data();
 			const unsigned char *src = (const unsigned char *)rd, *tp = (const unsigned char *)C.ref + C.ref_off[c.rid] + c.rs;
+			const int t_in = std::min(tl, C.ref_len ? C.ref_len[c.rid] - c.rs : tl); // mm_idx_getseq clips at the contig end
 			if (c.rev)
 				for (int j = 0; j < n; ++j) qd[j] = g_nt4.t[src[c.qe - 1 - j]] ^ 3;
 			else
 				for (int j = 0; j < n; ++j) qd[j] = g_nt4.t[src[c.qs + j]];
-			for (int j = 0; j < tl; ++j) td[j] = g_nt4.t[tp[j]];
+			for (int j = 0; j < t_in; ++j) td[j] = g_nt4.t[tp[j]];
+			for (int j = std::max(t_in, 0); j < tl; ++j) td[j] = 0;
 		}
 		update_extra(r, qs.data(), ts.data(), mat, (int8_t)o.q, (int8_t)o.e, !o.is_sr);
 		const uint32_t clip0 = r.rev ? (uint32_t)(qlen - r.qe) : (uint32_t)r.qs, clip1 = r.rev ? (uint32_t)r.qs : (uint32_t)(qlen - r.qe);
+		if (lr) { // LR/map.c:1843-1851: only the clip test here; chaining and the score filter follow
+			T.all.push_back(r), T.valid.push_back((clip0 < (uint32_t)qlen && clip1 < (uint32_t)qlen) ? 1 : 0);
+			continue;
+		}
 		if (!(clip0 < (uint32_t)qlen && clip1 < (uint32_t)qlen) || r.dp_score < o.min_dp_max) continue;
 		regs.push_back(r);
 		for (size_t k = regs.size() - 1; k > 0 && regs[k].score > regs[k - 1].score; --k) std::swap(regs[k], regs[k - 1]);
+	}
+	if (lr) {
+		const int64_t c0 = C.cand_off[i];
+		const int nc = (int)T.all.size();
+		for (int j = 0; j < nc; ++j) { // LR/map.c:1855-1874: a valid candidate continued by a valid one is stitched there
+			const int nx = C.cand[c0 + j].reserved[0];
+			if (T.valid[j] && nx >= 0 && nx < nc && T.valid[nx]) T.stitch = true;
+		}
+		if (T.stitch) return; // concatenate_cigars is the host program's (not restated): no record from here
+		for (int j = 0; j < nc; ++j) { // LR/map.c:1876-1910
+			if (!T.valid[j] || T.all[j].dp_score < o.min_dp_max) continue;
+			regs.push_back(T.all[j]);
+			for (size_t k = regs.size() - 1; k > 0 && regs[k].score > regs[k - 1].score; --k) std::swap(regs[k], regs[k - 1]);
+		}
 	}
 	if (!regs.empty()) set_sam_params(regs.data(), (int)regs.size(), (unsigned)qlen, (unsigned)o.a, o.no_print_2nd ? 0u : (unsigned)o.best_n);
 	// ---- format.c:412-603 with n_seg == 1
@@ -460,6 +490,11 @@ extern "C" int gd_sam_header(int n_seq, const char *const *seq_names, const int3
 
 extern "C" void gd_free(void *p) { free(p); }
 
+static int sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq, const char *qual,
+                     const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq, const char *const *seq_names,
+                     const int64_t *ref_off, const int32_t *ref_len, const char *ref, const gd_sr_post_opt_t *opt, char **sam,
+                     size_t *sam_len, bool long_read, int64_t *sam_off, uint8_t *needs_stitch);
+
 extern "C" int gd_sr_sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
                                const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar,
                                int n_seq, const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len,
@@ -467,7 +502,28 @@ extern "C" int gd_sr_sam_batch(int n, const char *const *names, const int64_t *o
 {
 	if (n < 0 || !opt || !sam || !sam_len || (n > 0 && (!names || !off || !len || !seq || !cand_off || !seq_names || !ref_off || !ref)))
 		return GD_ERR_ARG;
-	Ctx C = {n, names, off, len, seq, qual, cand_off, cand, cigar, n_seq, seq_names, ref_off, ref_len, ref, opt};
+	return sam_batch(n, names, off, len, seq, qual, cand_off, cand, cigar, n_seq, seq_names, ref_off, ref_len, ref, opt, sam, sam_len, false,
+	                 nullptr, nullptr);
+}
+
+extern "C" int gd_lr_sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                               const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar,
+                               int n_seq, const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len,
+                               const char *ref, const gd_sr_post_opt_t *opt, char **sam, size_t *sam_len, int64_t *sam_off,
+                               uint8_t *needs_stitch)
+{
+	if (n < 0 || !opt || !sam || !sam_len || (n > 0 && (!names || !off || !len || !seq || !cand_off || !seq_names || !ref_off || !ref)))
+		return GD_ERR_ARG;
+	return sam_batch(n, names, off, len, seq, qual, cand_off, cand, cigar, n_seq, seq_names, ref_off, ref_len, ref, opt, sam, sam_len, true,
+	                 sam_off, needs_stitch);
+}
+
+static int sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq, const char *qual,
+                     const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq, const char *const *seq_names,
+                     const int64_t *ref_off, const int32_t *ref_len, const char *ref, const gd_sr_post_opt_t *opt, char **sam,
+                     size_t *sam_len, bool long_read, int64_t *sam_off, uint8_t *needs_stitch)
+{
+	Ctx C = {n, names, off, len, seq, qual, cand_off, cand, cigar, n_seq, seq_names, ref_off, ref_len, ref, opt, long_read};
 	int nt = opt->n_threads > 0 ? opt->n_threads : (int)std::thread::hardware_concurrency();
 	nt = std::max(1, std::min(nt, (n + 255) / 256));
 	std::vector<Out> parts((size_t)nt);
@@ -475,7 +531,11 @@ extern "C" int gd_sr_sam_batch(int n, const char *const *names, const int64_t *o
 		const int64_t b = (int64_t)n * t / nt, e = (int64_t)n * (t + 1) / nt;
 		Scratch T;
 		parts[t].need((size_t)(e - b) * 520 + 4096);
-		for (int64_t i = b; i < e; ++i) one_read(C, (int)i, parts[t], T);
+		for (int64_t i = b; i < e; ++i) {
+			if (sam_off) sam_off[i] = (int64_t)parts[t].size(); // relative to the thread's part; rebased below
+			one_read(C, (int)i, parts[t], T);
+			if (needs_stitch) needs_stitch[i] = T.stitch ? 1 : 0;
+		}
 	};
 	auto run = [&](auto &&f) {
 		if (nt == 1) f(0);
@@ -489,6 +549,11 @@ extern "C" int gd_sr_sam_batch(int n, const char *const *names, const int64_t *o
 	std::vector<size_t> at((size_t)nt + 1, 0);
 	for (int t = 0; t < nt; ++t) at[t + 1] = at[t] + parts[t].size();
 	const size_t total = at[nt];
+	if (sam_off) {
+		for (int t = 0; t < nt; ++t)
+			for (int64_t i = (int64_t)n * t / nt, e = (int64_t)n * (t + 1) / nt; i < e; ++i) sam_off[i] += (int64_t)at[t];
+		sam_off[n] = (int64_t)total;
+	}
 	char *buf = (char *)malloc(total + 1);
 	if (!buf) return GD_ERR_ARG;
 	run([&](int t) { memcpy(buf + at[t], parts[t].data(), parts[t].size()); }); // first touch + copy on every core

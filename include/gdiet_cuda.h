@@ -325,6 +325,15 @@ int gd_sr_sam_batch(int n, const char *const *names, const int64_t *off, const i
                     const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq,
                     const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
                     const gd_sr_post_opt_t *opt, char **sam, size_t *sam_len);
+/* The same for the long-read tree (LR/map.c:1807-1912 without concatenate_cigars): candidates with score ==
+ * KSW_NEG_INF are dropped, mm_update_extra uses the logarithmic gap cost, the min_dp_max filter and the ordering follow
+ * the chaining step.  A read in which a valid candidate is continued by a valid candidate (cand.reserved[0] >= 0) needs
+ * the reference's CIGAR stitching, which is NOT restated here: needs_stitch[i] = 1 and no record is written for it, so
+ * the host program formats those reads itself; sam_off[0..n] (optional) gives every read's byte range in the text. */
+int gd_lr_sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                    const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq,
+                    const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
+                    const gd_sr_post_opt_t *opt, char **sam, size_t *sam_len, int64_t *sam_off, uint8_t *needs_stitch);
 /* the @SQ lines of mm_write_sam_hdr (format.c:128-137); the @PG line (command line) is the caller's */
 int gd_sam_header(int n_seq, const char *const *seq_names, const int32_t *ref_len, char **sam, size_t *sam_len);
 void gd_free(void *p);

@@ -79,3 +79,54 @@ def test_sam_matches_reference_program(seed, read_len, extra, okw, pkw):
     assert len(got) == len(want)
     bad = [(a, b) for a, b in zip(got, want) if a != b]
     assert not bad, "%d differing SAM lines, first:\n%s\n%s" % (len(bad), bad[0][0], bad[0][1])
+
+
+# ---- long-read tree -----------------------------------------------------------------------------------------------
+def lr_oracle_candidates(M, mi, reads, o):
+    cand_off, cands, cigs, base = [0], [], [], 0
+    for r in reads:
+        c, cig, _ = M.lr_map_read(mi, r, o)
+        c = c.copy()
+        used = int(sum(max(int(x), 0) for x in c["n_cigar"]))
+        c["cigar_off"] += base
+        cands.append(c)
+        cigs.append(cig[:used])
+        base += used
+        cand_off.append(cand_off[-1] + len(c))
+    return np.array(cand_off, np.int64), np.concatenate(cands), np.concatenate(cigs) if cigs else np.zeros(0, np.uint32)
+
+
+@pytest.mark.skipif(not (maplib.have_ref_program() and cpu_has_avx512()), reason="needs oracle/_ref/GDiet_avx_lr and AVX-512")
+@pytest.mark.parametrize("case", [
+    (1, "map-hifi", 19, 19, 1000, 15000, 0.005, 0.005, 30, [], {}),
+    (3, "map-hifi", 19, 19, 400, 6000, 0.005, 0.005, 60, ["--vt_nb_loc=2"], dict(vt_nb_loc=2)),
+])
+def test_lr_sam_matches_reference_program(case):
+    """gd_lr_sam_batch: every read that needs no CIGAR stitching gets exactly the reference program's SAM records; the
+    reads that do are flagged (and are the only ones that differ)."""
+    from test_oracle_map_lr_vs_ref import lr_setup
+    M = maplib.MapOracle()
+    contigs, reads, flags, mi, o = lr_setup(M, *case)
+    sam, _ = maplib.run_reference(contigs, reads, flags, program=maplib.REF_LR, trace=False, threads=2)
+    cand_off, cand, cig = lr_oracle_candidates(M, mi, reads, o)
+    M.lib.gdo_index_destroy(mi)
+    lens = np.array([len(r) for r in reads], np.int32)
+    off = np.zeros(len(reads), np.int64)
+    off[1:] = np.cumsum(lens[:-1].astype(np.int64))
+    buf = np.concatenate(reads)
+    names = ["r%d" % i for i in range(len(reads))]
+    txt, sam_off, stitch = gd.lr_sam_batch(names, off, lens, buf, np.full(len(buf), ord("I"), np.uint8), cand_off, cand, cig,
+                                           ["chr%d" % (i + 1) for i in range(len(contigs))], contigs, gd.lr_post_options(case[1]))
+    want = {}
+    for l in sam.splitlines():
+        if not l.startswith("@"):
+            want.setdefault(l.split("\t", 1)[0], []).append(l)
+    n_plain = 0
+    for i, nm in enumerate(names):
+        mine = txt[sam_off[i]:sam_off[i + 1]].decode().splitlines()
+        if stitch[i]:
+            assert mine == []
+            continue
+        assert mine == want[nm], "read %s:\n%s\n%s" % (nm, [m[:200] for m in mine], [m[:200] for m in want[nm]])
+        n_plain += 1
+    assert n_plain >= len(reads) // 2 and stitch.sum() > 0

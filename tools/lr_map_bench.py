@@ -76,6 +76,15 @@ def main():
            "candidates": int(coff[-1]), "mapped_reads": int((np.diff(coff) > 0).sum()), "chained": int((cand["reserved"][:, 0] >= 0).sum()),
            "dp_cells": cells, "dp_kernel_ms": dp_us / 1e3, "dp_kernel_gcups": cells / (dp_us * 1e-6) / 1e9 if dp_us else None,
            "stage_gcups": cells / min(tm) / 1e9, "host_cores": cores}
+    # ---- host stage: post-processing + SAM records (reads whose candidates need CIGAR stitching are flagged, not written)
+    names = gd._cstr_array(["r%d" % i for i in range(n_reads)])
+    qual = np.full(len(buf), ord("I"), np.uint8)
+    post = gd.lr_post_options(preset)
+    t0 = time.perf_counter()
+    sam_txt, sam_off, stitch = gd.lr_sam_batch(names, off, lens, buf, qual, coff, cand, cig, ["chr%d" % (i + 1) for i in range(ncontig)], contigs, post)
+    out["sam_s"] = round(time.perf_counter() - t0, 3)
+    out["reads_needing_stitch"] = int(stitch.sum())
+    out["reads_per_s_end_to_end"] = n_reads / (min(tm) + out["sam_s"])
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_avx_lr")
     if os.path.exists(ref_bin):
         import maplib
@@ -100,6 +109,20 @@ def main():
         wall = time.perf_counter() - t0
         prof = dict(re.findall(r"\[PROFILING\] (.+?) time: (\d+) ns", p.stderr))
         t_idx = int(prof.get("indexing", 0)) * 1e-9
+        want = {}
+        for l in open(os.path.join(tmp, "out.sam")).read().splitlines():
+            if not l.startswith("@"):
+                want.setdefault(l.split("\t", 1)[0], []).append(l)
+        same = diff = 0
+        for i in range(n_reads):
+            if stitch[i]:
+                continue
+            mine = sam_txt[sam_off[i]:sam_off[i + 1]].decode().splitlines()
+            if mine == want.get("r%d" % i, []):
+                same += 1
+            else:
+                diff += 1
+        out["sam"] = {"reads_identical": same, "reads_different": diff, "reads_left_to_host_stitching": int(stitch.sum())}
         out["reference"] = {"wall_s": round(wall, 2), "indexing_s": round(t_idx, 2), "reads_per_s": n_reads / max(wall - t_idx, 1e-9), "threads": cores,
                             "profile_thread_seconds": {kk: round(int(v) * 1e-9, 2) for kk, v in prof.items()}}
     print(json.dumps(out), flush=True)

@@ -1,7 +1,8 @@
 // gd_ksw.cu -- kernels and launcher of the batched ksw_extd2 DP (see gd_ksw.cuh for the design).
 #include "gd_ctx.h"
 #include <mutex>
-#include <set>
+#include <map>
+#include <tuple>
 #include <utility>
 #include "gd_ksw_host.h"
 #include <algorithm>
@@ -228,30 +229,42 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 	const size_t smem = GD_KSW_LUT_BYTES + (size_t)groups_per_block * geo.group_smem;
 	const int mode = exact ? 2 : (flag & KSW_F_APPROX_DROP) ? 1 : 0;
 	dp_kernel_t kern = pick_kernel(G, right, mode, with_p);
-	{ // Raise the kernel's dynamic shared-memory limit ONCE, to the device maximum: host threads with their own
-	  // contexts launch the same kernel with different sizes (one call per candidate in the drop-in path), and a
-	  // per-call limit set by one thread would be lowered by another between its set and its launch.
-		static std::mutex mu;
-		static std::set<std::pair<int, const void *>> raised;
-		std::lock_guard<std::mutex> lk(mu);
-		if (!raised.count(std::make_pair(ctx->device, (const void *)kern))) {
-			GD_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-			raised.insert(std::make_pair(ctx->device, (const void *)kern));
-		}
-	}
 	if (smem > ctx->smem_optin) {
 		ctx->err = "ksw_extd2: the column ring of this shape does not fit the shared memory of one block";
 		return GD_ERR_ARG;
 	}
+	{ // The kernel's dynamic shared-memory limit only ever grows (a high-water mark per device and kernel, under a lock):
+	  // host threads with their own contexts launch the same kernel with different sizes (one call per candidate in
+	  // the drop-in path), and a per-call setting by one thread could be lowered by another between its set and its launch.
+		static std::mutex mu;
+		static std::map<std::pair<int, const void *>, size_t> high;
+		std::lock_guard<std::mutex> lk(mu);
+		size_t &h = high[std::make_pair(ctx->device, (const void *)kern)];
+		if (smem > h) {
+			GD_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			h = smem;
+		}
+	}
 	int occ = 0;
-	GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+	{ // resident blocks per SM of this (kernel, block shape, shared memory): queried once, the launcher runs per batch
+		static std::mutex mu;
+		static std::map<std::tuple<int, const void *, int, size_t>, int> cache;
+		std::lock_guard<std::mutex> lk(mu);
+		const auto key = std::make_tuple(ctx->device, (const void *)kern, threads, smem);
+		auto it = cache.find(key);
+		if (it == cache.end()) {
+			GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+			cache[key] = occ;
+		} else occ = it->second;
+	}
 	if (occ < 1) occ = 1;
 	if (ctx->opt_ksw_blocks_per_sm > 0) occ = std::min<long>(occ, ctx->opt_ksw_blocks_per_sm);
 
 	// chunking: the backtrack arena is the only large scratch
 	size_t budget;
 	if (ctx->opt_p_budget_mb > 0) budget = (size_t)ctx->opt_p_budget_mb << 20;
-	else {
+	else if (!with_p || (size_t)n * (size_t)std::max<int64_t>(geo.p_stride, 1) + 64 <= ctx->parena.cap) budget = ctx->parena.cap; // fits as is
+	else { // the arena has to grow: size it from the memory that is free now (cudaMemGetInfo is not free, so only here)
 		size_t fr = 0, tot = 0;
 		GD_CUDA_OK(ctx, cudaMemGetInfo(&fr, &tot));
 		budget = std::max<size_t>(ctx->parena.cap, (size_t)(fr * 0.6));

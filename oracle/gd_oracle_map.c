@@ -208,13 +208,12 @@ typedef struct {
 	uint32_t first_query_loc, last_query_loc, str, score;
 } vt_t;
 
-static void vt_emit(vt_t *pot, unsigned *out_len, vt_t *recovery, int at_end, uint64_t target_loc, uint32_t fq,
+static void vt_emit(vt_t *pot, unsigned *out_len, vt_t *recovery, uint64_t target_loc, uint32_t fq,
                     uint32_t lq, unsigned counter, int str, int32_t tmp_ext, unsigned thr, unsigned max_loc,
                     unsigned rec_thr)
 {
 	vt_t v;
 	unsigned k;
-	(void)at_end;
 	v.chrom_id = (uint32_t)(target_loc >> 32);
 	v.target_loc = (int32_t)(target_loc & 0xffffffffu) + (str ? 0 : -tmp_ext);
 	v.first_query_loc = fq, v.last_query_loc = lq, v.str = str, v.score = counter;
@@ -250,11 +249,11 @@ static void vote(const loc_t *loc, unsigned len, int str, vt_t *pot, unsigned *n
 			if (cur.query < fq) target_loc = cur.target, fq = cur.query;
 			if (cur.query > lq) lq = cur.query;
 		} else {
-			vt_emit(pot, &out_len, recovery, 0, target_loc, fq, lq, counter, str, tmp_ext, thr, max_loc, rec_thr);
+			vt_emit(pot, &out_len, recovery, target_loc, fq, lq, counter, str, tmp_ext, thr, max_loc, rec_thr);
 			target_loc = cur.target, fq = lq = cur.query, counter = 1;
 		}
 	}
-	vt_emit(pot, &out_len, recovery, 1, target_loc, fq, lq, counter, str, tmp_ext, thr, max_loc, rec_thr);
+	vt_emit(pot, &out_len, recovery, target_loc, fq, lq, counter, str, tmp_ext, thr, max_loc, rec_thr);
 	*nb = out_len;
 }
 
@@ -266,7 +265,7 @@ int gdo_sr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_
 {
 	const int k = mi->k, w = mi->w;
 	unsigned qlen_sum = (unsigned)qlen;
-	long cap = qlen + 16, n2, n3;
+	long cap = qlen + 16, n3;
 	uint64_t *mv = (uint64_t *)malloc((size_t)cap * 16 * (o->W + 1));
 	uint32_t *counts = (uint32_t *)calloc(o->W + 1, 4);
 	unsigned shift = 0, max_hits = 0, s, i;
@@ -286,7 +285,7 @@ int gdo_sr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_
 	if (qlen <= 0) { free(mv), free(counts); if (dbg) *dbg = d; return 0; }
 
 	/* pattern alignment, map.c:609-615 + seed.c:166-194 */
-	n2 = gdo_mm_sketch2(seq, qlen, w, k, 0, o->Z, o->W, o->max_seeds, mv, cap * (o->W + 1), counts);
+	gdo_mm_sketch2(seq, qlen, w, k, 0, o->Z, o->W, o->max_seeds, mv, cap * (o->W + 1), counts);
 	{
 		uint64_t *p = mv;
 		for (s = 0; s < (unsigned)o->W; ++s) {
@@ -300,7 +299,6 @@ int gdo_sr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_
 			p += 2 * counts[s];
 		}
 	}
-	(void)n2;
 	d.shift = shift;
 
 	/* seeding, map.c:634-648 */
@@ -420,10 +418,9 @@ int gdo_sr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_
 			if (cig_used < cigar_cap) cigar[cig_used] = len << 4 | 0;
 			cig_used += 1;
 		} else {
-			int nc = gdo_ksw_extd2(len, qs, len, ts, 5, mat, o->q, o->e, o->q2, o->e2, o->bw, o->zdrop, o->end_bonus, 0x08, 1,
+			gdo_ksw_extd2(len, qs, len, ts, 5, mat, o->q, o->e, o->q2, o->e2, o->bw, o->zdrop, o->end_bonus, 0x08, 1,
 			                       &ez, cigar + cig_used, cigar_cap - cig_used);
 			c->score = ez.score, c->n_cigar = ez.n_cigar;
-			(void)nc;
 			if (ez.n_cigar > 0) cig_used += ez.n_cigar;
 		}
 		++n_out;

@@ -20,7 +20,7 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
     contigs = [genome]
     name_list = ["r%d" % i for i in range(n_reads)]
     names = gd._cstr_array(name_list)  # a C host already holds char* names
-    nb_ = max(1, min(4, n_reads // 250_000))
+    nb_ = max(1, min(8, n_reads // 125_000))
     C_names = [gd._cstr_array(name_list[n_reads * b // nb_: n_reads * (b + 1) // nb_]) for b in range(nb_)]
     off = np.arange(n_reads, dtype=np.int64) * 150
     lens = np.full(n_reads, 150, np.int32)
@@ -41,45 +41,75 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
         sam = h.bytes() if it == 3 else b""
         h.free()
         res = dict(map_s=t1 - t0, sam_s=t2 - t1, launches=ctx.stat("kernel_launches") - l0)
-    # ---- pipelined: the device stage of batch i+1 overlaps the host stage (post-processing + SAM text) of batch i
+    # ---- pipelined: two contexts on two host threads drive the device stage of alternate batches (their transfers and
+    # read-backs overlap each other's kernels); the main thread turns finished batches into SAM text IN INPUT ORDER on
+    # the remaining cores
     import threading, queue
-    nb = max(1, min(4, n_reads // 250_000))
+    nb = max(1, min(8, n_reads // 125_000))
     bounds = [n_reads * b // nb for b in range(nb + 1)]
-    ctx2 = ctx
+    ctx_p = gd.Context(ctx.device) if nb > 1 else None
 
-    def producer(q):
-        for b in range(nb):
+    def producer(c, parts, q):
+        for b in parts:
             lo, hi = bounds[b], bounds[b + 1]
-            o_b = off[lo:hi] - off[lo]
-            r = ctx2.sr_map_batch(idx, o_b, lens[lo:hi], buf[off[lo]:off[lo] + (hi - lo) * 150], opt, cand_cap=(hi - lo) + 1024,
-                                  cigar_cap=8 * (hi - lo) + 1024)
+            r = c.sr_map_batch(idx, off[lo:hi] - off[lo], lens[lo:hi], buf[off[lo]:off[lo] + (hi - lo) * 150], opt, cand_cap=(hi - lo) + 1024,
+                               cigar_cap=8 * (hi - lo) + 1024)
             q.put((b, r))
-        q.put(None)
 
     pipe_s = None
-    post_p = gd.sr_post_options(n_threads=max(1, cores - 2))  # leave cores to the thread that drives the GPU
+    post_p = gd.sr_post_options(n_threads=max(1, cores - 2))  # leave cores to the threads that drive the GPU
     for it in range(2):
-        q = queue.Queue(maxsize=2)
+        q = queue.Queue()
         t0 = time.perf_counter()
-        th = threading.Thread(target=producer, args=(q,))
-        th.start()
-        total_bytes = 0
-        while True:
-            item = q.get()
-            if item is None:
-                break
-            b, (co, ca, cg) = item
-            lo, hi = bounds[b], bounds[b + 1]
-            h = gd.sr_sam_batch(gd._cstr_array(names[lo:hi]) if False else (C_names[b]), off[lo:hi] - off[lo], lens[lo:hi], buf[off[lo]:off[lo] + (hi - lo) * 150],
-                                qual[off[lo]:off[lo] + (hi - lo) * 150], co, ca, cg, ["chr1"], contigs, post_p, raw=True)
-            total_bytes += h.n
-            h.free()
-        th.join()
+        ctxs = [ctx] + ([ctx_p] if ctx_p else [])
+        ths = [threading.Thread(target=producer, args=(c, range(k, nb, len(ctxs)), q)) for k, c in enumerate(ctxs)]
+        for t in ths:
+            t.start()
+        done, nxt, total_bytes = {}, 0, 0
+        while nxt < nb:
+            b, r = q.get()
+            done[b] = r
+            while nxt in done:
+                co, ca, cg = done.pop(nxt)
+                lo, hi = bounds[nxt], bounds[nxt + 1]
+                h = gd.sr_sam_batch(C_names[nxt], off[lo:hi] - off[lo], lens[lo:hi], buf[off[lo]:off[lo] + (hi - lo) * 150],
+                                    qual[off[lo]:off[lo] + (hi - lo) * 150], co, ca, cg, ["chr1"], contigs, post_p, raw=True)
+                total_bytes += h.n
+                h.free()
+                nxt += 1
+        for t in ths:
+            t.join()
         pipe_s = time.perf_counter() - t0
+    if ctx_p:
+        ctx_p.close()
+    # ---- device stage alone with TWO contexts on two host threads (one stream each, the index is shared read-only): the
+    # uploads / downloads / count read-backs of one context overlap the kernels of the other
+    dual_s = None
+    if n_reads >= 400_000:
+        ctx_b = gd.Context(ctx.device)
+        nb2 = 8
+        bounds2 = [n_reads * b // nb2 for b in range(nb2 + 1)]
+
+        def worker(c, parts):
+            for b in parts:
+                lo, hi = bounds2[b], bounds2[b + 1]
+                c.sr_map_batch(idx, off[lo:hi] - off[lo], lens[lo:hi], buf[off[lo]:off[lo] + (hi - lo) * 150], opt, cand_cap=(hi - lo) + 1024,
+                               cigar_cap=8 * (hi - lo) + 1024)
+
+        for it in range(3):
+            t0 = time.perf_counter()
+            ths = [threading.Thread(target=worker, args=(c, range(k, nb2, 2))) for k, c in enumerate((ctx, ctx_b))]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            dual_s = time.perf_counter() - t0
+        ctx_b.close()
     out = {"what": "config 1: sr end to end", "ref_bp": len(genome), "reads": n_reads, "index_build_s": round(t_index, 4),
            "index_minimizers": idx.stat("n_minimizers"), "map_batch_s": round(res["map_s"], 4), "sam_s": round(res["sam_s"], 4),
            "reads_per_s_serial": n_reads / (res["map_s"] + res["sam_s"]), "pipelined_s": round(pipe_s, 4), "pipeline_batches": nb,
            "reads_per_s": n_reads / min(pipe_s, res["map_s"] + res["sam_s"]), "reads_per_s_map_only": n_reads / res["map_s"],
+           "reads_per_s_map_only_two_contexts": (n_reads / dual_s) if dual_s else None,
            "candidates": int(coff[-1]), "exact": int(cand["exact"].sum()), "gpu_launches_per_batch": res["launches"], "host_cores": cores}
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_avx_sr")
     if run_ref and os.path.exists(ref_bin):

@@ -156,7 +156,22 @@ template <class Acc> void update_extra_t(Reg &r, const uint8_t *qseq, const uint
 		const uint32_t op = cg & 0xf, len = cg >> 4;
 		if (op == OP_M) {
 			int n_ambi = 0, n_diff = 0;
-			for (uint32_t l = 0; l < len; ++l) {
+			// Blocks of 8 identical unambiguous bases: with one positive match score on the whole diagonal the running sum
+			// only grows inside such a block, so adding 8 matches at once leaves s and the maximum exactly as the
+			// per-base steps would (integer accumulator only).
+			const bool fast = sizeof(Acc) == sizeof(int32_t) && mat[0] > 0 && mat[6] == mat[0] && mat[12] == mat[0] && mat[18] == mat[0];
+			uint32_t l = 0;
+			while (l < len) {
+				if (fast && l + 8 <= len) {
+					uint64_t a, b;
+					memcpy(&a, qseq + qoff + l, 8), memcpy(&b, tseq + toff + l, 8);
+					if (a == b && !(a & 0xfcfcfcfcfcfcfcfcull)) {
+						s += (Acc)(8 * mat[0]);
+						mx = mx > s ? mx : s;
+						l += 8;
+						continue;
+					}
+				}
 				const int cq = qseq[qoff + l], ct = tseq[toff + l];
 				if (ct > 3 || cq > 3) ++n_ambi;
 				else if (ct != cq) ++n_diff;
@@ -166,6 +181,7 @@ template <class Acc> void update_extra_t(Reg &r, const uint8_t *qseq, const uint
 				s += mi < 25 ? mat[mi] : 0;
 				if (s < 0) s = 0;
 				else mx = mx > s ? mx : s;
+				++l;
 			}
 			r.blen += len - n_ambi, r.mlen += len - (n_ambi + n_diff), r.n_ambi += n_ambi;
 			toff += len, qoff += len;

@@ -272,3 +272,40 @@ def test_lr_map_tandem_repeats_match_reference_program(ctx):
     for i, t in enumerate(tr):
         maplib.lr_cands_equal_trace(cand[coff[i]:coff[i + 1]], cig, t["cands"], "read %d" % i)
     idx.close()
+
+
+def test_sr_map_ragged_lowercase_and_tiny_reads(ctx, M):
+    """One batch with read lengths from 2 to 330 (some shorter than k, some longer than the 300-base switch of
+    map.c:776), lower-case bases and N runs: candidates equal the oracle's read by read."""
+    rng = np.random.default_rng(77)
+    contigs, base_reads = maplib.make_dataset(seed=13, read_len=330, n_reads=600)
+    reads = []
+    for i, r in enumerate(base_reads):
+        L = int(rng.choice([2, 5, 20, 21, 40, 75, 100, 149, 150, 151, 200, 299, 300, 301, 330]))
+        r = r[:L].copy()
+        if i % 3 == 0:
+            r = np.frombuffer(bytes(r).lower(), np.uint8).copy()
+        if i % 11 == 0 and L > 30:
+            r[10:14] = ord("N")
+        reads.append(r)
+    o = maplib.sr_opt(min_cnt=0.2, rec_frac=0.1, bw_min=150, bw_max=200)
+    idx = ctx.index_build(contigs, 11, 21, "10")
+    mi = M.index_build(contigs, 11, 21, "10")
+    off, lens, buf = flat_ragged(reads)
+    coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, o)
+    n_cand = 0
+    for i, r in enumerate(reads):
+        o_i = maplib.sr_opt(qlen=len(r), min_cnt=0.2, rec_frac=0.1, bw_min=150, bw_max=200)  # bw depends on the read length (map.c:624-631)
+        assert o_i.bw == o.bw
+        oc, ocig, dbg = M.map_read(mi, r, o)
+        mine = cand[coff[i]:coff[i + 1]]
+        assert len(mine) == len(oc), "read %d (len %d): %d candidates, oracle %d (%s)" % (i, len(r), len(mine), len(oc), dbg)
+        for j, (a, b) in enumerate(zip(mine, oc)):
+            for f in ("rid", "rs", "re", "qs", "qe", "rev", "votes", "exact", "score", "n_cigar"):
+                assert int(a[f]) == int(b[f]), "read %d (len %d) cand %d field %s: %d vs oracle %d" % (i, len(r), j, f, a[f], b[f])
+            assert np.array_equal(cig[int(a["cigar_off"]):int(a["cigar_off"]) + max(int(a["n_cigar"]), 0)],
+                                  ocig[int(b["cigar_off"]):int(b["cigar_off"]) + max(int(b["n_cigar"]), 0)])
+        n_cand += len(mine)
+    assert n_cand > 200
+    idx.close()
+    M.lib.gdo_index_destroy(mi)

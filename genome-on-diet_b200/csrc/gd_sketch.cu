@@ -186,8 +186,11 @@ static int make_params(gd_ctx *ctx, int w, int k, const char *Z, int W, SketchPa
 }
 
 // max_dl: upper bound of the sparsified length of any job; pos_total: upper bound of the sum.
+// fixed_stride > 0 (short jobs only, one tile per job): job j's records go to d_out[j * fixed_stride ..], its count to
+// d_out_cnt[j]; the caller sized d_out for njobs * fixed_stride records.
 static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const SketchJob *d_jobs, int64_t max_dl,
-                              int64_t pos_total, const char *d_buf, int64_t *d_out_off, uint64_t *d_out, int64_t out_cap)
+                              int64_t pos_total, const char *d_buf, int64_t *d_out_off, uint64_t *d_out, int64_t out_cap,
+                              int64_t fixed_stride = 0, int32_t *d_out_cnt = nullptr)
 {
 	cudaStream_t s = ctx->stream;
 	int rc;
@@ -198,10 +201,15 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 	const int tp_small = sk_tile_emit(256, S.w, S.k);
 	const bool small = tp_small > 0 && max_dl <= tp_small;
 	int64_t ntiles_bound;
+	if (fixed_stride > 0 && !small) {
+		ctx->err = "sketch: fixed-stride output needs one tile per job";
+		return GD_ERR_ARG;
+	}
 	if (small) {
 		S.TP = tp_small, S.one_tile_per_job = 1;
 		ntiles_bound = njobs;
 		B.ntiles = njobs, B.tile_base = nullptr;
+		B.fixed_stride = fixed_stride, B.out_cnt = d_out_cnt;
 	} else {
 		S.TP = sk_tile_emit(2048, S.w, S.k), S.one_tile_per_job = 0;
 		ntiles_bound = pos_total / S.TP + 2 * (int64_t)njobs + 2;
@@ -328,15 +336,16 @@ extern "C" int gd_sketch_ref_batch(gd_ctx *ctx, int n, const int64_t *off, const
 // final lengths of every list after the reference's caps (sketch.c:2010,2219-2222)
 __global__ void gd_sketch_read_counts_kernel(int n, int W, int crop, uint32_t cap2_const, uint32_t max_nb, const int32_t *len,
                                              const int64_t *job_off, const uint64_t *raw, int64_t *c3, int64_t *c2,
-                                             uint32_t *s3_ret, uint32_t *s2_counts)
+                                             uint32_t *s3_ret, uint32_t *s2_counts, const int32_t *job_cnt = nullptr)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const int JW = W + (crop ? 1 : 0);
 	const int64_t *jo = job_off + (size_t)i * JW;
+	const int32_t *jc = job_cnt ? job_cnt + (size_t)i * JW : nullptr; // fixed-stride lists carry their own counts
 	uint32_t cap2 = cap2_const; // 0 = uncapped
 	for (int s = 0; s < W; ++s) {
-		const int64_t cnt = jo[s + 1] - jo[s];
+		const int64_t cnt = jc ? (int64_t)jc[s] : jo[s + 1] - jo[s];
 		// mm_sketch3
 		int64_t n3 = (max_nb != 0 && cnt > (int64_t)max_nb) ? (int64_t)max_nb : cnt;
 		c3[(size_t)i * W + s] = n3;
@@ -345,7 +354,7 @@ __global__ void gd_sketch_read_counts_kernel(int n, int W, int crop, uint32_t ca
 		// mm_sketch2
 		int64_t n2;
 		if (crop && s == 0) {
-			n2 = jo[W + 1] - jo[W]; // the cropped shift-0 job, uncapped
+			n2 = jc ? (int64_t)jc[W] : jo[W + 1] - jo[W]; // the cropped shift-0 job, uncapped
 			cap2 = (uint32_t)n2;    // becomes the cap of every later shift
 		} else n2 = (cap2 != 0 && cnt > (int64_t)cap2) ? (int64_t)cap2 : cnt;
 		c2[(size_t)i * W + s] = n2;
@@ -407,44 +416,23 @@ extern "C" int gd_sketch_reads_batch(gd_ctx *ctx, int n, const int64_t *off, con
 		max_len = std::max<int64_t>(max_len, len[i]), sum_len += len[i];
 	}
 	const int crop = max_seeds < 1.0f ? 1 : 0;
-	const int JW = W + crop;
-	const uint32_t cap2_const = crop ? 0u : (uint32_t)max_seeds;
-	const int64_t njobs64 = (int64_t)n * JW;
-	if (njobs64 > 0x7fffffff) {
-		ctx->err = "gd_sketch_reads_batch: too many (read,shift) jobs in one call";
-		return GD_ERR_ARG;
-	}
-	const int njobs = (int)njobs64;
 	cudaStream_t s = ctx->stream;
-	const int64_t per_job = max_len / S.W * S.ones + S.ones;
-	const int64_t worst = (sum_len / S.W * S.ones + (int64_t)n * S.ones) * JW + 16;
 	if ((rc = gd_reserve(ctx, ctx->sk_seq, (size_t)bytes + 16))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->sk_off, (size_t)n * 8))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->sk_len, (size_t)n * 4))) return rc;
-	if ((rc = gd_reserve(ctx, ctx->sk_jobs, (size_t)njobs * sizeof(SketchJob)))) return rc;
-	if ((rc = gd_reserve(ctx, ctx->sk_out_off, (size_t)(njobs + 1) * 8))) return rc;
-	if ((rc = gd_reserve(ctx, ctx->sk_out, (size_t)worst * 16))) return rc;
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->sk_seq.p, buf, (size_t)bytes, cudaMemcpyHostToDevice, s));
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->sk_off.p, off, (size_t)n * 8, cudaMemcpyHostToDevice, s));
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->sk_len.p, len, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-	gd_sketch_read_jobs_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, (const int64_t *)ctx->sk_off.p, (const int32_t *)ctx->sk_len.p,
-	                                                       W, crop, max_seeds, (SketchJob *)ctx->sk_jobs.p);
-	ctx->stat_launches++;
-	rc = gd_sketch_run_jobs(ctx, S, njobs, (const SketchJob *)ctx->sk_jobs.p, per_job, worst, (const char *)ctx->sk_seq.p,
-	                        (int64_t *)ctx->sk_out_off.p, (uint64_t *)ctx->sk_out.p, worst);
-	if (rc) return rc;
-	// caps, offsets, gather
+	// every (read, shift) job + cap rules on the device (shared with the mapping stage)
+	GdReadSketch K;
+	if ((rc = gd_sketch_reads_device_raw(ctx, n, (const int64_t *)ctx->sk_off.p, (const int32_t *)ctx->sk_len.p, (const char *)ctx->sk_seq.p,
+	                                     max_len, sum_len, w, k, Z, W, max_seeds, max_nb_seeds, &K)))
+		return rc;
+	// offsets, gather
 	const size_t nq = (size_t)n * W;
-	// layout of cig-like scratch: c3[nq+1] | c2[nq+1] | ret[nq] | cnt2[nq] | per-read off2[n+1]
-	const size_t need = (nq + 1) * 8 * 2 + nq * 4 * 2 + (size_t)(n + 1) * 8 + 64;
-	if ((rc = gd_reserve(ctx, ctx->sk_rid, need))) return rc;
-	int64_t *c3 = (int64_t *)ctx->sk_rid.p, *c2 = c3 + nq + 1;
-	uint32_t *d_ret = (uint32_t *)(c2 + nq + 1), *d_cnt2 = d_ret + nq;
+	int64_t *c3 = const_cast<int64_t *>(K.c3), *c2 = const_cast<int64_t *>(K.c2);
+	uint32_t *d_ret = const_cast<uint32_t *>(K.ret3), *d_cnt2 = d_ret + nq;
 	int64_t *d_off2 = (int64_t *)(((uintptr_t)(d_cnt2 + nq) + 15) & ~(uintptr_t)15);
-	gd_sketch_read_counts_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, W, crop, cap2_const, max_nb_seeds, (const int32_t *)ctx->sk_len.p,
-	                                                         (const int64_t *)ctx->sk_out_off.p, (const uint64_t *)ctx->sk_out.p,
-	                                                         c3, c2, d_ret, d_cnt2);
-	ctx->stat_launches++;
 	if ((rc = gd_exclusive_scan(ctx, (int64_t)nq, c3, c3, ctx->sk_out2))) return rc;
 	if ((rc = gd_exclusive_scan(ctx, (int64_t)nq, c2, c2, ctx->sk_out2))) return rc;
 	gd_pick_stride_kernel<<<(n + 1 + 255) / 256, 256, 0, s>>>(n, W, c2, d_off2);
@@ -467,8 +455,7 @@ extern "C" int gd_sketch_reads_batch(gd_ctx *ctx, int n, const int64_t *off, con
 		if ((rc = gd_reserve(ctx, ctx->sk_state, g3 + g2 + 64))) return rc;
 		uint64_t *d3 = (uint64_t *)ctx->sk_state.p, *d2 = (uint64_t *)((char *)ctx->sk_state.p + g3);
 		int blocks = std::min((n + 7) / 8, ctx->sms * 8);
-		gd_sketch_read_gather_kernel<<<std::max(blocks, 1), 256, 0, s>>>(n, W, crop, (const int64_t *)ctx->sk_out_off.p,
-		                                                            (const uint64_t *)ctx->sk_out.p, c3, c2, s3 ? d3 : nullptr,
+		gd_sketch_read_gather_kernel<<<std::max(blocks, 1), 256, 0, s>>>(n, W, crop, K.job_off, K.raw, c3, c2, s3 ? d3 : nullptr,
 		                                                            tot[0], s2 ? d2 : nullptr, tot[1]);
 		ctx->stat_launches++;
 		GD_CUDA_OK(ctx, cudaGetLastError());
@@ -502,22 +489,32 @@ int gd_sketch_reads_device_raw(gd_ctx *ctx, int n, const int64_t *d_off, const i
 	const int njobs = (int)njobs64;
 	cudaStream_t s = ctx->stream;
 	const int64_t per_job = max_len / S.W * S.ones + S.ones;
-	const int64_t worst = (sum_len / S.W * S.ones + (int64_t)n * S.ones) * JW + 16;
+	int64_t worst = (sum_len / S.W * S.ones + (int64_t)n * S.ones) * JW + 16;
+	// Short reads (one warp-sized tile per job): every job gets its own slot of per_job records -- a position emits at most
+	// once -- so the tiles need neither the ordering ticket nor the look-back; the lists are addressed by job_off / counts.
+	const int tp_small = sk_tile_emit(256, S.w, S.k);
+	const bool fixed = tp_small > 0 && per_job <= tp_small && (int64_t)njobs * per_job * 16 <= (24ll << 30);
+	int32_t *d_cnt = nullptr;
+	if (fixed) {
+		worst = (int64_t)njobs * per_job;
+		if ((rc = gd_reserve(ctx, ctx->sk_misc, (size_t)njobs * 4 + 16))) return rc;
+		d_cnt = (int32_t *)ctx->sk_misc.p;
+	}
 	if ((rc = gd_reserve(ctx, ctx->sk_jobs, (size_t)njobs * sizeof(SketchJob)))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->sk_out_off, (size_t)(njobs + 1) * 8))) return rc;
-	if ((rc = gd_reserve(ctx, ctx->sk_out, (size_t)worst * 16))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->sk_out, (size_t)worst * 16 + 64))) return rc;
 	gd_sketch_read_jobs_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, d_off, d_len, W, crop, max_seeds, (SketchJob *)ctx->sk_jobs.p);
 	ctx->stat_launches++;
 	rc = gd_sketch_run_jobs(ctx, S, njobs, (const SketchJob *)ctx->sk_jobs.p, per_job, worst, d_buf, (int64_t *)ctx->sk_out_off.p,
-	                        (uint64_t *)ctx->sk_out.p, worst);
+	                        (uint64_t *)ctx->sk_out.p, worst, fixed ? per_job : 0, d_cnt);
 	if (rc) return rc;
 	const size_t nq = (size_t)n * W;
-	const size_t need = (nq + 1) * 8 * 2 + nq * 4 * 2 + 64;
+	const size_t need = (nq + 1) * 8 * 2 + nq * 4 * 2 + (size_t)(n + 1) * 8 + 128; // c3 | c2 | ret | cnt2 | per-read offsets (host API)
 	if ((rc = gd_reserve(ctx, ctx->sk_rid, need))) return rc;
 	int64_t *c3 = (int64_t *)ctx->sk_rid.p, *c2 = c3 + nq + 1;
 	uint32_t *d_ret = (uint32_t *)(c2 + nq + 1), *d_cnt2 = d_ret + nq;
 	gd_sketch_read_counts_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, W, crop, cap2_const, max_nb_seeds, d_len, (const int64_t *)ctx->sk_out_off.p,
-	                                                         (const uint64_t *)ctx->sk_out.p, c3, c2, d_ret, d_cnt2);
+	                                                         (const uint64_t *)ctx->sk_out.p, c3, c2, d_ret, d_cnt2, d_cnt);
 	ctx->stat_launches++;
 	GD_CUDA_OK(ctx, cudaGetLastError());
 	out->job_off = (const int64_t *)ctx->sk_out_off.p, out->raw = (const uint64_t *)ctx->sk_out.p;

@@ -48,6 +48,10 @@ struct SketchBatch {
 	int64_t *out_off;          // [njobs+1]
 	uint64_t *out;             // x,y pairs
 	int64_t out_cap;           // entries; records beyond are dropped but still counted
+	// Fixed-stride output (one tile per job only): job j writes at most fixed_stride records at out[j * fixed_stride ..]
+	// and its count to out_cnt[j].  No tile depends on another one then: no ticket, no look-back.
+	int64_t fixed_stride;      // 0 = dense output in job order (decoupled look-back)
+	int32_t *out_cnt;          // [njobs], fixed-stride mode
 };
 
 GD_DEV uint64_t sk_hash64(uint64_t key, uint64_t mask)
@@ -140,8 +144,9 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 	// running: the look-back below can never wait for a block that is not resident.  (Drawing several consecutive tiles
 	// per atomic was tried for the one-warp tiles of short reads and dropped: the first tile of a batch then waits for the
 	// LAST tile of the previous block's batch, which serialises the blocks.)
-	for (;;) {
-		if (tid == 0) sm->tile = atomic_add(B.ticket, 1);
+	const bool fixed = B.fixed_stride > 0;
+	for (long long round = 0;; ++round) {
+		if (tid == 0) sm->tile = fixed ? (int32_t)(block_idx() + round * grid_dim()) : atomic_add(B.ticket, 1);
 		sync_block();
 		const long long tile = sm->tile;
 		if (tile >= B.ntiles) break;
@@ -352,8 +357,14 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 			total += c;
 		}
 		const int local = wbase + inc - cnt;
-		// ---- decoupled look-back over tiles, 32 predecessors per probe (warp 0) ----
-		if (wid == 0) {
+		// ---- decoupled look-back over tiles, 32 predecessors per probe (warp 0); fixed-stride mode: the job's own slot ----
+		if (fixed) {
+			if (tid == 0) {
+				sm->excl = (long long)job * B.fixed_stride;
+				B.out_off[job] = sm->excl, B.out_cnt[job] = total;
+				if (tile == B.ntiles - 1) B.out_off[B.njobs] = (long long)B.njobs * B.fixed_stride;
+			}
+		} else if (wid == 0) {
 			long long excl = 0;
 			if (tile == 0) {
 				if (lane == 0) st_volatile(&B.status[0], (2ull << 62) | (unsigned long long)total);
@@ -394,7 +405,7 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 		for (int p = 0; p < 8; ++p)
 			if (emit >> p & 1) {
 				const long long dst = obase + o;
-				if (dst < B.out_cap) {
+				if (fixed ? (local + o < B.fixed_stride) : (dst < B.out_cap)) {
 					const uint64_t y = (uint64_t)J.rid << 32 | (uint64_t)real[p] << 1 | (uint64_t)(zbits >> p & 1);
 					B.out[2 * dst] = X[p];
 					B.out[2 * dst + 1] = y;

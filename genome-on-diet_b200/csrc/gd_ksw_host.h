@@ -86,8 +86,13 @@ static inline int ksw_pick_group(int max_qlen, int max_tlen, int max_w, bool exa
 	// per 50 kbp ONT pair), so narrow gangs leave the SMs short of warps -- widen the gang, up to a block of two
 	// warps per pair, until the launch has ~24 warps per SM.  (Measured: HiFi 2048 pairs 497 -> 600 GCUPS, ONT 512
 	// pairs 324 -> 434 GCUPS; four warps per pair and exact mode do not gain.)
-	if (!exact)
+	if (!exact) {
 		while (G >= 16 && G < 64 && (int64_t)npairs * G / 32 < (int64_t)sms * 24) G <<= 1;
+		// A handful of very long pairs (fewer blocks than twice the SMs): two warps per pair leave half of every SM's four
+		// schedulers idle, so the gang grows to four warps.  (ONT, 72 pairs of 50 kbp: 94 -> see profiles; with hundreds of
+		// pairs four warps per pair do not gain, measured.)
+		if (G == 64 && (int64_t)npairs < (int64_t)sms * 2) G = 128;
+	}
 	return G;
 }
 static inline KswGeom ksw_geometry(int max_qlen, int max_tlen, int max_w, bool exact, bool with_p, int G)

@@ -356,13 +356,21 @@ def ours(args, rank, world, local_rank):
             srm = sr_map_bench.run(ctx, 5, 100_000, run_ref=not args.no_cpu)
         except Exception as e:
             srm = {"error": str(e)}
+    # ---- BASELINE config 3 shape (hifi reads through the long-read mapping stage + host SAM records), bounded: 500 reads
+    lrm = None
+    if not args.no_sketch and world == 1:
+        try:
+            import lr_map_bench
+            lrm = lr_map_bench.run(ctx, "hifi", 50, 500, 0, run_ref=not args.no_cpu)
+        except Exception as e:
+            lrm = {"error": str(e)}
     line = {"metric": "ksw_extd2 GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
             "data": "synthetic", "config": workload_config(args, n),
             "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
             "extra": {"ksw_group_lanes": ctx.stat("ksw_group"), "ksw_ring_columns": ctx.stat("ksw_ring"), "chunks_per_step": ctx.stat("ksw_chunks"),
-                      "zdropped_frac": float((ez["zdropped"] != 0).mean()), "cells_per_step": tot_cells, "sketch": sk, "sr_map": srm}}
+                      "zdropped_frac": float((ez["zdropped"] != 0).mean()), "cells_per_step": tot_cells, "sketch": sk, "sr_map": srm, "lr_map": lrm}}
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()

@@ -31,6 +31,12 @@ def main():
     ref_mbp = float(sys.argv[2]) if len(sys.argv) > 2 else 100
     n_reads = int(sys.argv[3]) if len(sys.argv) > 3 else (2000 if kind == "hifi" else 500)
     n_check = int(sys.argv[4]) if len(sys.argv) > 4 else 100
+    ctx = gd.Context(0)
+    print(json.dumps(run(ctx, kind, ref_mbp, n_reads, n_check)), flush=True)
+    ctx.close()
+
+
+def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
     if kind == "hifi":
         preset, k, w, bw, L, sub, indel, extra, okw = "map-hifi", 19, 19, 1000, 15000, 0.005, 0.005, [], {}
     else:
@@ -54,7 +60,6 @@ def main():
     off = np.zeros(n_reads, np.int64)
     off[1:] = np.cumsum(lens[:-1].astype(np.int64))
     buf = np.concatenate(reads)
-    ctx = gd.Context(0)
     ctx.set_option("time_kernels", 1)
     t0 = time.perf_counter()
     idx = ctx.index_build(contigs, w, k, "10")
@@ -86,7 +91,7 @@ def main():
     out["reads_needing_stitch"] = int(stitch.sum())
     out["reads_per_s_end_to_end"] = n_reads / (min(tm) + out["sam_s"])
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_avx_lr")
-    if os.path.exists(ref_bin):
+    if run_ref and os.path.exists(ref_bin):
         import maplib
         flags = ["-ax", preset, "-Z", "10", "-W", "2", "-k", str(k), "-w", str(w), "-r", str(bw)] + extra
         if n_check > 0:
@@ -125,9 +130,9 @@ def main():
         out["sam"] = {"reads_identical": same, "reads_different": diff, "reads_left_to_host_stitching": int(stitch.sum())}
         out["reference"] = {"wall_s": round(wall, 2), "indexing_s": round(t_idx, 2), "reads_per_s": n_reads / max(wall - t_idx, 1e-9), "threads": cores,
                             "profile_thread_seconds": {kk: round(int(v) * 1e-9, 2) for kk, v in prof.items()}}
-    print(json.dumps(out), flush=True)
     idx.close()
-    ctx.close()
+    ctx.set_option("time_kernels", 0)
+    return out
 
 
 if __name__ == "__main__":

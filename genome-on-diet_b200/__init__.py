@@ -82,13 +82,13 @@ class gd_index_meta_t(C.Structure):
 class gd_sr_post_opt_t(C.Structure):
     """include/gdiet_cuda.h: options of the host side after the DP (GDiet-ShortReads/map.c:954-984)."""
     _fields_ = [(f, C.c_int32) for f in ("a", "b", "q", "e", "min_dp_max", "best_n", "no_print_2nd", "is_sr", "sam_hit_only",
-                                         "softclip", "n_threads")]
+                                         "softclip", "n_threads", "q2", "e2")]
 
 
 def sr_post_options(n_threads=0, **kw):
     """`-ax sr` values (GDiet-ShortReads/options.c:130-150)."""
     o = gd_sr_post_opt_t(a=2, b=8, q=12, e=2, min_dp_max=40, best_n=20, no_print_2nd=1, is_sr=1, sam_hit_only=0, softclip=0,
-                         n_threads=n_threads)
+                         n_threads=n_threads, q2=24, e2=1)
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -121,8 +121,10 @@ class SamText:
 
 
 def lr_post_options(preset="map-hifi", n_threads=0, **kw):
-    """`-ax map-hifi | map-ont` values (GDiet-LongReads/options.c:86-111, main.c:181)."""
-    sc = dict(a=1, b=4, q=6, e=2, min_dp_max=200) if preset == "map-hifi" else dict(a=2, b=4, q=4, e=2, min_dp_max=40)
+    """`-ax map-hifi | map-ont` values (GDiet-LongReads/options.c:86-111).  min_dp_max is 40 for every preset: the
+    long-read main() assigns it AFTER the option pass that applies -x (LR/main.c:134-160,181), so the preset's 200 is
+    overwritten; only -s changes it."""
+    sc = dict(a=1, b=4, q=6, e=2, q2=26, e2=1, min_dp_max=40) if preset == "map-hifi" else dict(a=2, b=4, q=4, e=2, q2=24, e2=1, min_dp_max=40)
     o = gd_sr_post_opt_t(best_n=5, no_print_2nd=0, is_sr=0, sam_hit_only=0, softclip=0, n_threads=n_threads, **sc)
     for k, v in kw.items():
         setattr(o, k, v)

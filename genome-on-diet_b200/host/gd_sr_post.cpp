@@ -341,10 +341,207 @@ struct Ctx {
 	bool long_read;
 };
 
+// ---- concatenate_cigars, LR/map.c:41-640: two chained candidates of one read become one record --------------------
+// rs is continued by re (same strand and contig).  Where the two alignments overlap -- on the query, else on the target --
+// every cut position is scored from the two CIGARs (prefix score of the first + remaining score of the second) and the
+// best cut joins them, with one I / D for whatever the other coordinate still lacks.  The reference's own evaluation is
+// kept as it is: the search compares al_start[p] + al_start[p] with the initial al_start[0] + al_end[0] (map.c:267,493).
+// qseq: the whole read in the strand's orientation (qs_for / qs_rev, map.c:1626-1643).  Returns 1 = not merged.
+struct GapCost {
+	uint32_t o1, e1, o2, e2;
+	uint32_t cost(uint32_t len) const { return std::min(o1 + len * e1, o2 + len * e2); }
+	void pick(uint32_t len, uint32_t &o, uint32_t &e) const
+	{
+		if (o1 + len * e1 < o2 + len * e2) o = o1, e = e1;
+		else o = o2, e = e2;
+	}
+};
+
+int concat_cigars(Reg &rs, const Reg &re, const uint8_t *qseq, int str, uint32_t read_len, const Ctx &C, uint32_t sc_mch, uint32_t sc_mis,
+                  const GapCost &G, std::vector<uint32_t> &store, std::vector<uint8_t> &tseq, std::vector<int> &al_s, std::vector<int> &al_e)
+{
+	const uint32_t tstart = (uint32_t)rs.rs, tend = (uint32_t)re.re, tstart_junc = (uint32_t)re.rs, tend_junc = (uint32_t)rs.re;
+	const uint32_t qstart = str ? read_len - rs.qe : rs.qs, qend = str ? read_len - re.qs : re.qe;
+	const uint32_t qstart_junc = str ? read_len - re.qe : re.qs, qend_junc = str ? read_len - rs.qs : rs.qe;
+	if (tend_junc <= tstart_junc && qend_junc <= qstart_junc) return 1; // they do not touch on either coordinate
+	if (tend_junc >= tend || tstart >= tstart_junc) return 1;           // one inside the other
+	if (qend_junc >= qend || qstart >= qstart_junc) return 1;
+	auto fetch = [&](int rid, uint32_t st, uint32_t en) { // mm_idx_getseq (index.c:157-166) into tseq
+		const uint32_t L = (uint32_t)C.ref_len[rid];
+		if (en > L) en = L;
+		tseq.assign((size_t)(en > st ? en - st : 0) + 8, 0);
+		const unsigned char *tp = (const unsigned char *)C.ref + C.ref_off[rid] + st;
+		for (uint32_t j = 0; st + j < en; ++j) tseq[j] = g_nt4.t[tp[j]];
+	};
+	uint32_t juncq, junct, cigar_pos;
+	int score;
+	const bool on_query = qend_junc > qstart_junc;
+	const uint32_t juncture_len = on_query ? qend_junc - qstart_junc : tend_junc - tstart_junc;
+	al_s.assign((size_t)juncture_len + 1, 0), al_e.assign((size_t)juncture_len + 1, 0);
+	// ---- prefix scores of the first alignment over the overlap: the coordinate that overlaps is `a` (query positions for
+	// on_query, target positions otherwise), the op that consumes only `a` is I (on_query) or D
+	{
+		fetch(rs.rid, tstart, tend_junc);
+		const uint32_t a_junc = on_query ? qstart_junc : tstart_junc - tstart; // first overlap position in the walk's `a` units
+		const uint32_t OP_A = on_query ? OP_I : OP_D, OP_B = on_query ? OP_D : OP_I;
+		int al = 0;
+		uint32_t toff = 0, qoff = qstart;
+		for (uint32_t i = 0; i < rs.n_cig; ++i) {
+			const uint32_t op = rs.cig[i] & 0xf, len = rs.cig[i] >> 4;
+			const uint32_t a = on_query ? qoff : toff;
+			if (op == OP_M) {
+				for (uint32_t j = 0; j < len; ++j) {
+					if (a + j >= a_junc) al_s[a + j - a_junc] = al;
+					if (qseq[qoff + j] == tseq[toff + j]) al += (int)sc_mch;
+					else al -= (int)sc_mis;
+				}
+				qoff += len, toff += len;
+			} else if (op == OP_A) {
+				uint32_t o, e;
+				G.pick(len, o, e);
+				if (a + len <= a_junc) al -= (int)G.cost(len);
+				else if (a < a_junc) {
+					al -= (int)(o + e * (a_junc - a));
+					for (uint32_t j = 0; j < a + len - a_junc; ++j) al_s[j] = al, al -= (int)e;
+				} else {
+					al_s[a - a_junc] = al;
+					al -= (int)(o + e);
+					for (uint32_t j = 1; j < len; ++j) al_s[a + j - a_junc] = al, al -= (int)e;
+				}
+				if (on_query) qoff += len;
+				else toff += len;
+			} else if (op == OP_B) {
+				al -= (int)G.cost(len);
+				if (on_query) toff += len;
+				else qoff += len;
+			} else if (op == OP_N) toff += len;
+		}
+	}
+	// ---- remaining scores of the second alignment over the overlap
+	{
+		fetch(re.rid, tstart_junc, tend);
+		const uint32_t OP_A = on_query ? OP_I : OP_D, OP_B = on_query ? OP_D : OP_I;
+		const uint32_t a_end = on_query ? qend_junc : tend_junc - tstart_junc; // end of the overlap in the walk's `a` units
+		const uint32_t a_base = on_query ? qstart_junc : 0;
+		int al = on_query ? re.score : 0;
+		uint32_t toff = 0, qoff = qstart_junc;
+		for (uint32_t i = 0; i < re.n_cig && (on_query ? qoff : toff) <= a_end; ++i) {
+			const uint32_t op = re.cig[i] & 0xf, len = re.cig[i] >> 4;
+			const uint32_t a = on_query ? qoff : toff;
+			if (op == OP_M) {
+				for (uint32_t j = 0; j < len && a + j < a_end; ++j) {
+					if (qseq[qoff + j] == tseq[toff + j]) al -= (int)sc_mch;
+					else al += (int)sc_mis;
+					al_e[a + j - a_base] = al;
+				}
+				qoff += len, toff += len;
+			} else if (op == OP_A) {
+				uint32_t o, e;
+				G.pick(len, o, e);
+				al += (int)o;
+				for (uint32_t j = 0; j < len && a + j < a_end; ++j) al += (int)e, al_e[a + j - a_base] = al;
+				if (on_query) qoff += len;
+				else toff += len;
+			} else if (op == OP_B) {
+				al += (int)G.cost(len);
+				if (on_query) toff += len;
+				else qoff += len;
+			} else if (op == OP_N) toff += len;
+		}
+	}
+	// ---- the cut (LR/map.c:262-274 / :488-499, evaluated exactly as written there)
+	{
+		int max_score = al_s[0] + al_e[0];
+		uint32_t best = 0;
+		for (uint32_t p = 1; p < juncture_len; ++p) {
+			const int total = al_s[p] + al_s[p];
+			if (total > max_score) max_score = total, best = p;
+		}
+		score = max_score;
+		if (on_query) juncq = best + qstart_junc, junct = 0;
+		else junct = best + tstart_junc, juncq = 0;
+	}
+	// ---- the first CIGAR up to the cut (LR/map.c:284-320 / :513-547); the result may be longer than either input
+	const size_t base = store.size();
+	store.resize(base + rs.n_cig + re.n_cig + 2);
+	uint32_t *out = store.data() + base;
+	memcpy(out, rs.cig, (size_t)rs.n_cig * 4);
+	{
+		uint32_t qoff = qstart, toffs = (uint32_t)rs.rs, i;
+		for (i = 0; i < rs.n_cig; ++i) {
+			const uint32_t op = out[i] & 0xf, len = out[i] >> 4;
+			if (op == OP_M) {
+				const bool hit = on_query ? qoff + len >= juncq : toffs + len >= junct;
+				if (hit) {
+					const uint32_t new_len = on_query ? juncq - qoff : junct - toffs;
+					out[i] = OP_M | (new_len << 4);
+					qoff += new_len, toffs += new_len;
+					++i;
+					break;
+				}
+				qoff += len, toffs += len;
+			} else if (op == OP_I) {
+				if (on_query && qoff + len >= juncq) { // move the cut in front of the insertion
+					juncq = qoff;
+					break;
+				}
+				qoff += len;
+			} else if (op == OP_D) {
+				if (!on_query && toffs + len >= junct) {
+					junct = toffs;
+					break;
+				}
+				toffs += len;
+			} else if (op == OP_N) toffs += len;
+		}
+		if (on_query) junct = toffs;
+		else juncq = qoff;
+		cigar_pos = i;
+	}
+	// ---- the second CIGAR from the cut on, with the joining I / D (LR/map.c:551-616)
+	{
+		uint32_t toffe = (uint32_t)re.rs, qoffend = qstart_junc, i = cigar_pos;
+		bool crossed = false;
+		for (uint32_t j = 0; j < re.n_cig; ++j) {
+			const uint32_t op = re.cig[j] & 0xf, len = re.cig[j] >> 4;
+			if (op == OP_M || op == OP_I || op == OP_D || op == OP_N) {
+				if (crossed) out[i++] = re.cig[j];
+				if (op == OP_M) qoffend += len, toffe += len;
+				else if (op == OP_I) qoffend += len;
+				else toffe += len;
+			}
+			if (!crossed && qoffend >= juncq && toffe >= junct) {
+				const uint32_t tar_len = toffe - junct, que_len = qoffend - juncq;
+				if (que_len > tar_len) {
+					const uint32_t l = que_len - tar_len;
+					score -= (int)G.cost(l);
+					out[i++] = OP_I | (l << 4);
+					if (tar_len != 0) out[i++] = OP_M | (tar_len << 4);
+				} else if (que_len < tar_len) {
+					const uint32_t l = tar_len - que_len;
+					score -= (int)G.cost(l);
+					out[i++] = OP_D | (l << 4);
+					if (que_len != 0) out[i++] = OP_M | (que_len << 4);
+				} else out[i++] = OP_M | (tar_len << 4);
+				crossed = true;
+			}
+		}
+		rs.cig = out, rs.n_cig = i;
+	}
+	rs.dp_score = score, rs.score = score;
+	if (str) rs.qs = re.qs;
+	else rs.qe = re.qe;
+	rs.re = re.re;
+	return 0;
+}
+
 struct Scratch { // per-thread, reused across reads
 	std::vector<Reg> regs, all;
-	std::vector<int> valid;
-	bool stitch = false; // long reads: a chained pair of valid candidates needs concatenate_cigars (not done here)
+	std::vector<int> valid, next;
+	std::vector<uint32_t> merged; // CIGARs produced by concat_cigars
+	std::vector<uint8_t> strand[2], tseq;
+	std::vector<int> al_s, al_e;
+	bool stitch = false; // (kept for the ABI: no read is left to the host any more)
 	std::vector<uint8_t> qs, ts;
 	std::vector<uint32_t> cig;
 };
@@ -408,11 +605,35 @@ void one_read(const Ctx &C, int i, Out &out, Scratch &T)
 	if (lr) {
 		const int64_t c0 = C.cand_off[i];
 		const int nc = (int)T.all.size();
-		for (int j = 0; j < nc; ++j) { // LR/map.c:1855-1874: a valid candidate continued by a valid one is stitched there
+		// LR/map.c:1855-1874: a valid candidate continued by a valid one absorbs it (concatenate_cigars), repeatedly
+		T.next.assign((size_t)nc, -1);
+		bool any_chain = false;
+		for (int j = 0; j < nc; ++j) {
 			const int nx = C.cand[c0 + j].reserved[0];
-			if (T.valid[j] && nx >= 0 && nx < nc && T.valid[nx]) T.stitch = true;
+			T.next[j] = (nx >= 0 && nx < nc) ? nx : -1;
+			any_chain |= T.valid[j] && T.next[j] >= 0 && T.valid[T.next[j]];
 		}
-		if (T.stitch) return; // concatenate_cigars is the host program's (not restated): no record from here
+		if (any_chain) {
+			for (int st = 0; st < 2; ++st) T.strand[st].resize((size_t)qlen + 8);
+			for (int j = 0; j < qlen; ++j) { // qs_for / qs_rev, LR/map.c:1626-1643
+				const uint8_t c = g_nt4.t[(unsigned char)rd[j]];
+				T.strand[0][j] = c, T.strand[1][qlen - 1 - j] = c ^ 3;
+			}
+			size_t room = 0;
+			for (int j = 0; j < nc; ++j) room += T.all[j].n_cig + 2;
+			T.merged.clear();
+			T.merged.reserve(room * (size_t)nc + 64); // views into it must stay valid: never reallocated below
+			const GapCost G = {(uint32_t)o.q, (uint32_t)o.e, (uint32_t)o.q2, (uint32_t)o.e2};
+			for (int j = 0; j < nc; ++j) {
+				while (T.valid[j] && T.next[j] >= 0 && T.valid[T.next[j]]) {
+					const int nx = T.next[j];
+					if (concat_cigars(T.all[j], T.all[nx], T.strand[T.all[j].rev ? 1 : 0].data(), T.all[j].rev, (uint32_t)qlen, C, (uint32_t)o.a,
+					                  (uint32_t)o.b, G, T.merged, T.tseq, T.al_s, T.al_e) == 0)
+						T.valid[nx] = 0, T.next[j] = T.next[nx];
+					else T.next[j] = -1;
+				}
+			}
+		}
 		for (int j = 0; j < nc; ++j) { // LR/map.c:1876-1910
 			if (!T.valid[j] || T.all[j].dp_score < o.min_dp_max) continue;
 			regs.push_back(T.all[j]);

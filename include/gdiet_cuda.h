@@ -314,6 +314,7 @@ typedef struct {
 	int32_t sam_hit_only; /* MM_F_SAM_HIT_ONLY: no record for unmapped reads */
 	int32_t softclip;     /* MM_F_SOFTCLIP */
 	int32_t n_threads;    /* host threads (0 = all cores) */
+	int32_t q2, e2;       /* second gap piece: the junction gaps of concatenate_cigars (long reads, LR/map.c:1864-1866) */
 } gd_sr_post_opt_t;
 
 /* For every read of a batch: mm_update_extra (+ mm_fix_cigar), the clip / min_dp_max filter and the ordering of
@@ -325,11 +326,11 @@ int gd_sr_sam_batch(int n, const char *const *names, const int64_t *off, const i
                     const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq,
                     const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
                     const gd_sr_post_opt_t *opt, char **sam, size_t *sam_len);
-/* The same for the long-read tree (LR/map.c:1807-1912 without concatenate_cigars): candidates with score ==
- * KSW_NEG_INF are dropped, mm_update_extra uses the logarithmic gap cost, the min_dp_max filter and the ordering follow
- * the chaining step.  A read in which a valid candidate is continued by a valid candidate (cand.reserved[0] >= 0) needs
- * the reference's CIGAR stitching, which is NOT restated here: needs_stitch[i] = 1 and no record is written for it, so
- * the host program formats those reads itself; sam_off[0..n] (optional) gives every read's byte range in the text. */
+/* The same for the long-read tree (LR/map.c:1807-1912): candidates with score == KSW_NEG_INF are dropped,
+ * mm_update_extra uses the logarithmic gap cost, a valid candidate that is continued by a valid candidate
+ * (cand.reserved[0] >= 0) absorbs it (concatenate_cigars, LR/map.c:41-640), then the min_dp_max filter and the ordering.
+ * sam_off[0..n] (optional) gives every read's byte range in the text; needs_stitch (optional) is kept for callers of the
+ * earlier interface and is always 0 now. */
 int gd_lr_sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
                     const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq,
                     const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,

@@ -309,3 +309,31 @@ def test_sr_map_ragged_lowercase_and_tiny_reads(ctx, M):
     assert n_cand > 200
     idx.close()
     M.lib.gdo_index_destroy(mi)
+
+
+@pytest.mark.skipif(not (maplib.have_ref_program() and cpu_has_avx512()), reason="needs oracle/_ref/GDiet_avx_lr and AVX-512")
+@pytest.mark.parametrize("preset,k,w,bw,read_len,sub,indel,extra,okw", [
+    ("map-hifi", 19, 19, 600, 7000, 0.005, 0.005, [], {}),
+    ("map-ont", 15, 10, 800, 9000, 0.02, 0.03,
+     ["--vt_dis=1000", "--vt_nb_loc=3", "--vt_df1=0.007", "--vt_df2=0.007", "--max_min_gap=4000", "--vt_f=0.04", "--vt_cov", "0.3",
+      "--sort=merge", "--frag=no"], dict(vt_dis=1000, vt_df1=0.007, vt_df2=0.007, vt_f=0.04, vt_cov=0.3)),
+])
+def test_lr_sam_end_to_end_matches_reference_program(ctx, preset, k, w, bw, read_len, sub, indel, extra, okw):
+    """Long reads end to end: gd_lr_map_batch on the device + gd_lr_sam_batch on the host (with CIGAR stitching of the
+    chained candidates) against the SAM of the unmodified reference program, on reads with structural variation."""
+    import gdiet_b200 as gd
+    contigs, reads = maplib.make_long_dataset(seed=61, read_len=read_len, sub=sub, indel=indel, n_reads=160, sv_frac=0.6)
+    flags = ["-ax", preset, "-Z", "10", "-W", "2", "-k", str(k), "-w", str(w), "-r", str(bw)] + list(extra)
+    sam, _ = maplib.run_reference(contigs, reads, flags, program=maplib.REF_LR, trace=False, threads=4)
+    idx = ctx.index_build(contigs, w, k, "10")
+    lo, hi = (50, 500) if preset == "map-hifi" else (10, 1000000)
+    o = gd.lr_options(preset, bw=bw, mid_occ=min(max(idx.cal_max_occ(2e-4), lo), hi), **okw)
+    off, lens, buf = flat_ragged(reads)
+    coff, cand, cig = ctx.lr_map_batch(idx, off, lens, buf, o, cand_cap=8 * len(reads), cigar_cap=64 * len(reads) * 256)
+    names = ["r%d" % i for i in range(len(reads))]
+    txt, sam_off, _ = gd.lr_sam_batch(names, off, lens, buf, np.full(len(buf), ord("I"), np.uint8), coff, cand, cig,
+                                      ["chr%d" % (i + 1) for i in range(len(contigs))], contigs, gd.lr_post_options(preset))
+    want = [l for l in sam.splitlines() if not l.startswith("@")]
+    assert txt.decode().splitlines() == want
+    assert int((cand["reserved"][:, 0] >= 0).sum()) > 10   # chained candidates were stitched
+    idx.close()

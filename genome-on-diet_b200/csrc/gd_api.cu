@@ -77,6 +77,7 @@ extern "C" int gd_init(int device, gd_ctx **out)
 extern "C" void gd_destroy(gd_ctx *ctx)
 {
 	if (!ctx) return;
+	if (ctx->peer) gd_destroy(ctx->peer), ctx->peer = nullptr;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	GdBuf *bufs[] = {&ctx->tpk, &ctx->qpk, &ctx->parena, &ctx->ticket, &ctx->cig_tmp, &ctx->cig_off, &ctx->cig_compact,
@@ -113,6 +114,7 @@ extern "C" int gd_set_option(gd_ctx *ctx, const char *key, long value)
 	else if (!strcmp(key, "sketch_chunk")) ctx->opt_sketch_chunk = value;
 	else if (!strcmp(key, "time_kernels")) ctx->opt_time_kernels = value;
 	else if (!strcmp(key, "ksw_slice")) ctx->opt_ksw_slice = value;
+	else if (!strcmp(key, "map_lanes")) ctx->opt_map_lanes = value;
 	else {
 		ctx->err = std::string("unknown option ") + key;
 		return GD_ERR_ARG;
@@ -136,7 +138,7 @@ extern "C" long gd_get_stat(const gd_ctx *cctx, const char *key)
 			return 0;
 		}
 	}
-	if (!strcmp(key, "kernel_launches")) return ctx->stat_launches;
+	if (!strcmp(key, "kernel_launches")) return ctx->stat_launches + (ctx->peer ? ctx->peer->stat_launches : 0);
 	if (!strcmp(key, "ksw_ring")) return ctx->stat_ksw_ring;
 	if (!strcmp(key, "ksw_group")) return ctx->stat_ksw_group;
 	if (!strcmp(key, "ksw_chunks")) return ctx->stat_ksw_chunks;

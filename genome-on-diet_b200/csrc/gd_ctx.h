@@ -35,6 +35,8 @@ struct gd_ctx {
 	long opt_sketch_chunk = 0;
 	long opt_ksw_slice = 0;    // pairs per pipeline slice of the host-buffer DP call (0 = auto)
 	long opt_time_kernels = 0; // 1: bracket every DP / sketch kernel launch with CUDA events (bench.py roofline)
+	long opt_map_lanes = 2;    // mapping stage: 2 = slices alternate between this context and a peer context on a helper thread
+	gd_ctx *peer = nullptr;    // the second lane of the mapping stage (created on first use)
 	// stats
 	long stat_launches = 0;
 	long stat_ksw_ring = 0, stat_ksw_group = 0, stat_ksw_chunks = 0;

@@ -21,8 +21,11 @@
 #include "gd_sketch.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <time.h>
 #include <utility>
 #include <vector>
@@ -840,10 +843,48 @@ struct SrPhaseClock {
 	}
 };
 
+// The slices of one call run on two lanes (the caller's context and a peer context on a helper thread, one stream each) so
+// that the transfers, the 8-byte read-backs and the small kernels of one slice overlap the DP kernel of the other.  Results
+// land in the caller's arrays in input order: a slice claims its output ranges when its sizes are known, in slice order.
+struct SliceOrder {
+	std::mutex mu;
+	std::condition_variable cv;
+	int next = 0;
+	bool failed = false;
+	int64_t cand_base = 0, cig_base = 0;
+	bool claim(int slice, int64_t nc, int64_t ncig, int64_t &cb, int64_t &gb)
+	{
+		std::unique_lock<std::mutex> lk(mu);
+		cv.wait(lk, [&] { return failed || next == slice; });
+		if (failed) return false;
+		cb = cand_base, gb = cig_base;
+		cand_base += nc, cig_base += ncig, ++next;
+		cv.notify_all();
+		return true;
+	}
+	void fail()
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		failed = true;
+		cv.notify_all();
+	}
+};
+struct SliceClaim { // a slice that returns before claiming (an error) must not leave the other lane waiting
+	SliceOrder &ord;
+	bool done = false;
+	explicit SliceClaim(SliceOrder &o) : ord(o) {}
+	~SliceClaim()
+	{
+		if (!done) ord.fail();
+	}
+};
+
 static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
-                        const gd_sr_opt_t *o, const gd_lr_opt_t *lr, int64_t cand_base, int64_t cig_base, int64_t *cand_off, gd_sr_cand_t *cand,
-                        int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cand_out, int64_t *n_cig_out)
+                        const gd_sr_opt_t *o, const gd_lr_opt_t *lr, SliceOrder &ord, int slice_index, int64_t *cand_off, gd_sr_cand_t *cand,
+                        int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap)
 {
+	SliceClaim claim(ord);
+	int64_t cand_base = 0, cig_base = 0;
 	cudaStream_t s = ctx->stream;
 	SrPhaseClock clk(s);
 	int rc;
@@ -872,8 +913,9 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	if ((rc = gd_reserve(ctx, ctx->mp_seq, (size_t)(hi - lo) + 16))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_off, (size_t)n * 8))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_len, (size_t)n * 4))) return rc;
-	if ((rc = gd_reserve_pinned(ctx, ctx->h_mp, (size_t)n * 8 + 64))) return rc;
+	if ((rc = gd_reserve_pinned(ctx, ctx->h_mp, (size_t)(2 * n + 2) * 8 + 64))) return rc;
 	int64_t *h_off = (int64_t *)ctx->h_mp.p;
+	int64_t *h_coff = h_off + n + 4; // this slice's candidate offsets, relative, until its output range is claimed
 	for (int i = 0; i < n; ++i) h_off[i] = off[i] - lo;
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_seq.p, buf + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s));
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_off.p, h_off, (size_t)n * 8, cudaMemcpyHostToDevice, s));
@@ -929,7 +971,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	GD_CUDA_OK(ctx, cudaGetLastError());
 	if ((rc = scan_u32(ctx, (const uint32_t *)ctx->mp_ncand.p, (int64_t *)ctx->mp_coff.p, n))) return rc;
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, (int64_t *)ctx->mp_coff.p + n, 16, cudaMemcpyDeviceToHost, s));
-	GD_CUDA_OK(ctx, cudaMemcpyAsync(cand_off, ctx->mp_coff.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_coff, ctx->mp_coff.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
 	const int64_t nc = h_word[0];
 	int max_q = max_len, max_t = max_len; // upper bounds of the DP shapes
@@ -939,9 +981,12 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 		P.stride = (std::max(span, 1) + 15) / 16 * 16;
 	}
 	clk.mark("vote");
-	*n_cand_out = nc, *n_cig_out = 0;
-	for (int i = 0; i <= n; ++i) cand_off[i] += cand_base;
-	if (nc == 0) return GD_OK;
+	if (nc == 0) {
+		if (!ord.claim(slice_index, 0, 0, cand_base, cig_base)) return GD_ERR_CUDA;
+		claim.done = true;
+		for (int i = 0; i <= n; ++i) cand_off[i] = cand_base;
+		return GD_OK;
+	}
 	// ---- K3
 	if ((rc = gd_reserve(ctx, ctx->mp_cand, (size_t)nc * sizeof(gd_sr_cand_t)))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_qbuf, (size_t)nc * P.stride + 256))) return rc;
@@ -999,7 +1044,9 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
 	const int64_t ncig = h_word[0];
 	clk.mark("scores");
-	*n_cig_out = ncig;
+	if (!ord.claim(slice_index, nc, ncig, cand_base, cig_base)) return GD_ERR_CUDA;
+	claim.done = true;
+	for (int i = 0; i <= n; ++i) cand_off[i] = h_coff[i] + cand_base; // (the shared boundary entry gets the same value from both neighbours)
 	const bool fits = cand_base + nc <= cand_cap && cig_base + ncig <= cigar_cap && cand && cigar;
 	if ((rc = gd_reserve(ctx, ctx->mp_cpool, (size_t)(ncig + 1) * 4))) return rc;
 	gd_sr_cigars_kernel<<<wblocks, 128, 0, s>>>(nc, d_cand, d_pair_off, d_cig_off, (const uint32_t *)ctx->mp_cig.p, cig_stride,
@@ -1015,6 +1062,41 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	if (fits && cig_base)
 		for (int64_t c = 0; c < nc; ++c) cand[cand_base + c].cigar_off += (int32_t)cig_base;
 	return GD_OK;
+}
+
+extern "C" int gd_init(int device, gd_ctx **ctx);
+
+static int run_slices(gd_ctx *ctx, const gd_index *idx, const std::vector<std::pair<int, int>> &slices, const int64_t *off,
+                      const int32_t *len, const char *buf, const gd_sr_opt_t *o, const gd_lr_opt_t *lr, int64_t *cand_off,
+                      gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cand, int64_t *n_cig)
+{
+	SliceOrder ord;
+	ctx->err.clear();
+	const int ns = (int)slices.size();
+	int lanes = (ns >= 2 && ctx->opt_map_lanes != 1) ? 2 : 1;
+	if (lanes == 2 && !ctx->peer && gd_init(ctx->device, &ctx->peer) != GD_OK) lanes = 1; // no second context: one lane
+	int rcs[2] = {GD_OK, GD_OK};
+	auto lane = [&](int L) {
+		gd_ctx *c = L == 0 ? ctx : ctx->peer;
+		cudaSetDevice(c->device);
+		for (int k = L; k < ns; k += lanes) {
+			const int b = slices[k].first, m = slices[k].second;
+			const int rc = sr_map_slice(c, idx, m, off + b, len + b, buf, o, lr, ord, k, cand_off + b, cand, cand_cap, cigar, cigar_cap);
+			if (rc) {
+				rcs[L] = rc;
+				ord.fail();
+				return;
+			}
+		}
+	};
+	if (lanes == 2) {
+		std::thread helper(lane, 1);
+		lane(0);
+		helper.join();
+		if (rcs[1] && ctx->err.empty()) ctx->err = ctx->peer->err;
+	} else lane(0);
+	*n_cand = ord.cand_base, *n_cig = ord.cig_base;
+	return rcs[0] ? rcs[0] : rcs[1];
 }
 
 extern "C" int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
@@ -1034,14 +1116,14 @@ extern "C" int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const in
 	if (n_cigar) *n_cigar = 0;
 	if (n == 0) return GD_OK;
 	cudaSetDevice(ctx->device);
-	const int slice = 1 << 18;
+	// slices: at most 2^18 reads, at least four per call when the batch is large enough to share between the two lanes
+	const int slice = std::max(32768, std::min(1 << 18, (n + 3) / 4));
+	std::vector<std::pair<int, int>> slices;
+	for (int b = 0; b < n; b += slice) slices.push_back({b, std::min(slice, n - b)});
 	int64_t cand_base = 0, cig_base = 0;
-	for (int b = 0; b < n; b += slice) {
-		const int m = std::min(slice, n - b);
-		int64_t nc = 0, ng = 0;
-		int rc = sr_map_slice(ctx, idx, m, off + b, len + b, buf, o, nullptr, cand_base, cig_base, cand_off + b, cand, cand_cap, cigar, cigar_cap, &nc, &ng);
+	{
+		int rc = run_slices(ctx, idx, slices, off, len, buf, o, nullptr, cand_off, cand, cand_cap, cigar, cigar_cap, &cand_base, &cig_base);
 		if (rc) return rc;
-		cand_base += nc, cig_base += ng;
 	}
 	if (n_cigar) *n_cigar = cig_base;
 	if (cig_base > 0x7fffffff) {
@@ -1079,14 +1161,22 @@ extern "C" int gd_lr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const in
 	if (n == 0) return GD_OK;
 	cudaSetDevice(ctx->device);
 	int64_t cand_base = 0, cig_base = 0;
-	for (int b = 0; b < n;) { // slices of at most 64 Mbases (the sketch lists and hit arrays scale with the bases)
-		int m = 0;
-		int64_t bases = 0;
-		while (b + m < n && m < (1 << 18) && (m == 0 || bases + len[b + m] <= (64ll << 20))) bases += len[b + m], ++m;
-		int64_t nc = 0, ng = 0;
-		int rc = sr_map_slice(ctx, idx, m, off + b, len + b, buf, &o, lr, cand_base, cig_base, cand_off + b, cand, cand_cap, cigar, cigar_cap, &nc, &ng);
+	std::vector<std::pair<int, int>> slices;
+	{ // slices of at most 64 Mbases (the sketch lists and hit arrays scale with the bases), a quarter of the batch if that is less
+		int64_t total = 0;
+		for (int i = 0; i < n; ++i) total += len[i];
+		const int64_t lim = std::max<int64_t>(4ll << 20, std::min<int64_t>(64ll << 20, total / 4 + 1));
+		for (int b = 0; b < n;) {
+			int m = 0;
+			int64_t bases = 0;
+			while (b + m < n && m < (1 << 18) && (m == 0 || bases + len[b + m] <= lim)) bases += len[b + m], ++m;
+			slices.push_back({b, m});
+			b += m;
+		}
+	}
+	{
+		int rc = run_slices(ctx, idx, slices, off, len, buf, &o, lr, cand_off, cand, cand_cap, cigar, cigar_cap, &cand_base, &cig_base);
 		if (rc) return rc;
-		cand_base += nc, cig_base += ng, b += m;
 	}
 	if (n_cigar) *n_cigar = cig_base;
 	if (cig_base > 0x7fffffff) {

@@ -1162,10 +1162,10 @@ extern "C" int gd_lr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const in
 	cudaSetDevice(ctx->device);
 	int64_t cand_base = 0, cig_base = 0;
 	std::vector<std::pair<int, int>> slices;
-	{ // slices of at most 64 Mbases (the sketch lists and hit arrays scale with the bases), a quarter of the batch if that is less
-		int64_t total = 0;
-		for (int i = 0; i < n; ++i) total += len[i];
-		const int64_t lim = std::max<int64_t>(4ll << 20, std::min<int64_t>(64ll << 20, total / 4 + 1));
+	{ // slices of at most 64 Mbases (the sketch lists and hit arrays scale with the bases).  Long reads are NOT cut finer to
+	  // feed the two lanes: their time is the DP, and the DP wants every pair of the batch in one launch (cutting 500 ONT
+	  // reads into four slices doubled the time of the stage).
+		const int64_t lim = 64ll << 20;
 		for (int b = 0; b < n;) {
 			int m = 0;
 			int64_t bases = 0;

@@ -269,7 +269,7 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
-           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write", "gd_lr_sam_batch"]
+           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write", "gd_lr_sam_batch", "gd_index_load_mmi", "gd_index_seq_name"]
 
 
 def load():
@@ -345,6 +345,10 @@ def load():
     L.gd_index_commit.argtypes = [vp, vp]
     L.gd_lr_map_batch.restype = i32
     L.gd_lr_map_batch.argtypes = [vp, vp, i32, vp, vp, vp, C.POINTER(gd_lr_opt_t), vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.gd_index_load_mmi.restype = i32
+    L.gd_index_load_mmi.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.gd_index_seq_name.restype = C.c_char_p
+    L.gd_index_seq_name.argtypes = [vp, i32]
     L.gd_mmi_write.restype = i32
     L.gd_mmi_write.argtypes = [C.c_char_p, i32, i32, i32, i32, i32, vp, vp, i64, vp, vp, vp, vp]
     L.gd_sr_sam_batch.restype = i32
@@ -537,6 +541,12 @@ class Context:
                     "gd_index_build")
         return Index(self, h)
 
+    def index_load_mmi(self, path):
+        """gd_index_load_mmi: a .mmi file (the reference's `-d` output or gd_mmi_write's) -> device index."""
+        h = C.c_void_p()
+        self._check(self.lib.gd_index_load_mmi(self.h, path.encode(), C.byref(h)), "gd_index_load_mmi")
+        return Index(self, h)
+
     def index_build_device(self, off, lens, d_buf, w, k, Z):
         """gd_index_build_device: off / lens are host arrays, d_buf a device pointer / CUDA tensor with the ASCII contigs."""
         off = np.ascontiguousarray(off, np.int64)
@@ -598,6 +608,9 @@ class Index:
         self.ctx._check(self.ctx.lib.gd_index_export(self.ctx.h, self.h, _ptr(keys), _ptr(counts), _ptr(pos), _ptr(S)),
                         "gd_index_export")
         return keys, counts, pos, S
+
+    def seq_names(self):
+        return [self.ctx.lib.gd_index_seq_name(self.h, i).decode() for i in range(self.stat("n_seq"))]
 
     def meta(self):
         m = gd_index_meta_t()

@@ -13,6 +13,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <string.h>
+#include <string>
 #include <vector>
 
 using namespace gd;
@@ -427,4 +428,75 @@ extern "C" int gd_index_commit(gd_ctx *ctx, gd_index *idx)
 	idx->d.pos = (const uint64_t *)idx->d_pos, idx->d.S = (const uint32_t *)idx->d_S;
 	idx->d.seq_off = (const uint64_t *)idx->d_seq_off, idx->d.seq_len = (const uint32_t *)idx->d_seq_len;
 	return GD_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// .mmi -> device index (row F4): the host part parses the file (host/gd_mmi.cpp), the arrays go up and the same table
+// insert kernel as in the build makes them searchable
+// --------------------------------------------------------------------------------------------
+struct GdMmiData {
+	int w = 0, k = 0, b = 0, flag = 0;
+	std::vector<std::string> names;
+	std::vector<int32_t> lens;
+	std::vector<uint64_t> keys, positions;
+	std::vector<uint32_t> counts, S;
+};
+int gd_mmi_parse(const char *path, GdMmiData &D);
+
+extern "C" int gd_index_load_mmi(gd_ctx *ctx, const char *path, gd_index **out)
+{
+	if (!ctx || !path || !out) return GD_ERR_ARG;
+	*out = nullptr;
+	GdMmiData D;
+	if (gd_mmi_parse(path, D) != GD_OK) {
+		ctx->err = std::string("gd_index_load_mmi: cannot read ") + path;
+		return GD_ERR_ARG;
+	}
+	gd_index_meta_t m;
+	m.n_seq = (int64_t)D.lens.size(), m.total_len = 0, m.n_minimizers = (int64_t)D.positions.size(), m.n_keys = (int64_t)D.keys.size();
+	for (int32_t l : D.lens) m.total_len += (uint32_t)l;
+	m.table_slots = 1024;
+	while (m.table_slots < 2 * m.n_keys) m.table_slots <<= 1;
+	m.s_words = (m.total_len + 7) / 8, m.w = D.w, m.k = D.k;
+	if (m.n_seq <= 0 || (int64_t)D.S.size() != m.s_words) {
+		ctx->err = "gd_index_load_mmi: the file has no sequences (index dumped with MM_I_NO_SEQ?)";
+		return GD_ERR_ARG;
+	}
+	gd_index *idx = nullptr;
+	int rc = gd_index_alloc(ctx, &m, &idx);
+	if (rc) return rc;
+	cudaStream_t s = ctx->stream;
+	std::vector<uint64_t> seq_off((size_t)m.n_seq + 1, 0), first((size_t)m.n_keys + 1, 0);
+	for (int64_t i = 0; i < m.n_seq; ++i) seq_off[i + 1] = seq_off[i] + (uint32_t)D.lens[i];
+	for (int64_t i = 0; i < m.n_keys; ++i) first[i + 1] = first[i] + D.counts[i];
+	uint64_t *d_first = nullptr;
+	auto up = [&](void *dst, const void *src, size_t bytes) { return bytes == 0 || cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s) == cudaSuccess; };
+	bool ok = cudaMalloc(&d_first, (size_t)(m.n_keys + 1) * 8) == cudaSuccess;
+	ok = ok && up(idx->d_pos, D.positions.data(), D.positions.size() * 8) && up(idx->d_S, D.S.data(), D.S.size() * 4) &&
+	     up(idx->d_seq_off, seq_off.data(), seq_off.size() * 8) && up(idx->d_seq_len, D.lens.data(), D.lens.size() * 4) &&
+	     up(idx->d_keys, D.keys.data(), D.keys.size() * 8) && up(idx->d_counts, D.counts.data(), D.counts.size() * 4) &&
+	     up(d_first, first.data(), first.size() * 8);
+	if (ok) {
+		gd_idx_clear_kernel<<<(unsigned)((m.table_slots + 255) / 256), 256, 0, s>>>(m.table_slots, (IdxSlot *)idx->d_tab);
+		if (m.n_keys > 0)
+			gd_idx_insert_kernel<<<(unsigned)((m.n_keys + 255) / 256), 256, 0, s>>>(m.n_keys, (const uint64_t *)idx->d_keys, (const uint32_t *)idx->d_counts,
+			                                                                     d_first, (IdxSlot *)idx->d_tab, (uint64_t)m.table_slots - 1);
+		ctx->stat_launches += 2;
+		ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess;
+	}
+	if (d_first) cudaFree(d_first);
+	if (!ok || (rc = gd_index_commit(ctx, idx)) != GD_OK) {
+		ctx->err = "gd_index_load_mmi: CUDA failure while uploading the index";
+		gd_index_destroy(idx);
+		return GD_ERR_CUDA;
+	}
+	idx->names = D.names;
+	*out = idx;
+	return GD_OK;
+}
+
+extern "C" const char *gd_index_seq_name(const gd_index *idx, int i)
+{
+	if (!idx || i < 0 || (size_t)i >= idx->names.size()) return "";
+	return idx->names[(size_t)i].c_str();
 }

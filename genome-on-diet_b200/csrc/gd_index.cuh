@@ -7,6 +7,8 @@
 // count and the positions of that minimizer in ascending order.
 #pragma once
 #include "gd_common.cuh"
+#include <string>
+#include <vector>
 
 namespace gd {
 
@@ -67,4 +69,5 @@ struct gd_index {
 	uint32_t *h_seq_len = nullptr;
 	uint64_t *h_seq_off = nullptr;
 	size_t device_bytes = 0;
+	std::vector<std::string> names; // contig names (only known when the index came from a .mmi file)
 };

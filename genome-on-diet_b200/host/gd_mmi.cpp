@@ -153,3 +153,81 @@ extern "C" int gd_mmi_write(const char *path, int w, int k, int bucket_bits, int
 	fclose(fp);
 	return bad ? GD_ERR_ARG : GD_OK;
 }
+
+// --------------------------------------------------------------------------------------------
+// reading (mm_idx_load, GDiet-ShortReads/index.c:519-571): the file back into the flat arrays the device index is
+// uploaded from -- keys ascending, counts, positions grouped by key.  Implemented in the host part; gd_index_load_mmi
+// (gd_index.cu) puts them into HBM.
+// --------------------------------------------------------------------------------------------
+#include <algorithm>
+
+struct GdMmiData {
+	int w = 0, k = 0, b = 0, flag = 0;
+	std::vector<std::string> names;
+	std::vector<int32_t> lens;
+	std::vector<uint64_t> keys, positions;
+	std::vector<uint32_t> counts, S;
+};
+
+int gd_mmi_parse(const char *path, GdMmiData &D)
+{
+	FILE *fp = fopen(path, "rb");
+	if (!fp) return GD_ERR_ARG;
+	char magic[4];
+	uint32_t x[5];
+	bool ok = fread(magic, 1, 4, fp) == 4 && !memcmp(magic, "MMI\2", 4) && fread(x, 4, 5, fp) == 5;
+	if (!ok) {
+		fclose(fp);
+		return GD_ERR_ARG;
+	}
+	D.w = (int)x[0], D.k = (int)x[1], D.b = (int)x[2], D.flag = (int)x[4];
+	uint64_t sum_len = 0;
+	for (uint32_t i = 0; ok && i < x[3]; ++i) {
+		uint8_t l = 0;
+		char nm[256];
+		int32_t len = 0;
+		ok = fread(&l, 1, 1, fp) == 1 && (l == 0 || fread(nm, 1, l, fp) == l) && fread(&len, 4, 1, fp) == 1;
+		D.names.emplace_back(nm, nm + l), D.lens.push_back(len), sum_len += (uint32_t)len;
+	}
+	struct Ent {
+		uint64_t key, a, n; // minimizer, first position (within its bucket's list, or the position itself), count
+		uint32_t bucket;
+	};
+	std::vector<Ent> ents;
+	std::vector<std::vector<uint64_t>> plists((size_t)1 << D.b);
+	for (uint32_t bk = 0; ok && bk < (1u << D.b); ++bk) {
+		int32_t n = 0;
+		uint32_t size = 0;
+		ok = fread(&n, 4, 1, fp) == 1;
+		if (ok && n > 0) plists[bk].resize((size_t)n), ok = fread(plists[bk].data(), 8, (size_t)n, fp) == (size_t)n;
+		ok = ok && fread(&size, 4, 1, fp) == 1;
+		for (uint32_t j = 0; ok && j < size; ++j) {
+			uint64_t kv[2];
+			ok = fread(kv, 8, 2, fp) == 2;
+			Ent e;
+			e.key = (kv[0] >> 1) << D.b | bk, e.bucket = bk; // index.c:246-258 inverted
+			if (kv[0] & 1) e.a = kv[1], e.n = 0;              // singleton: the value is the position
+			else e.a = kv[1] >> 32, e.n = (uint32_t)kv[1];
+			ents.push_back(e);
+		}
+	}
+	if (ok && !(D.flag & 0x2 /* MM_I_NO_SEQ */)) {
+		D.S.resize((size_t)((sum_len + 7) / 8));
+		ok = D.S.empty() || fread(D.S.data(), 4, D.S.size(), fp) == D.S.size();
+	}
+	fclose(fp);
+	if (!ok) return GD_ERR_ARG;
+	std::sort(ents.begin(), ents.end(), [](const Ent &p, const Ent &q) { return p.key < q.key; });
+	D.keys.reserve(ents.size()), D.counts.reserve(ents.size());
+	for (const Ent &e : ents) {
+		D.keys.push_back(e.key);
+		if (e.n == 0) D.counts.push_back(1), D.positions.push_back(e.a);
+		else {
+			D.counts.push_back((uint32_t)e.n);
+			const std::vector<uint64_t> &pl = plists[e.bucket];
+			if (e.a + e.n > pl.size()) return GD_ERR_ARG;
+			D.positions.insert(D.positions.end(), pl.begin() + (size_t)e.a, pl.begin() + (size_t)(e.a + e.n));
+		}
+	}
+	return GD_OK;
+}

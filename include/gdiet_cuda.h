@@ -347,6 +347,10 @@ void gd_free(void *p);
 int gd_mmi_write(const char *path, int w, int k, int bucket_bits, int flag, int n_seq, const char *const *names,
                  const int32_t *lens, int64_t n_keys, const uint64_t *keys, const uint32_t *counts, const uint64_t *positions,
                  const uint32_t *S);
+/* ... and the way back (mm_idx_load, index.c:519-571): a `.mmi` file written by the reference (`-d`) or by gd_mmi_write
+ * becomes a device-resident index; gd_index_seq_name returns the contig names stored in the file ("" for built indexes). */
+int gd_index_load_mmi(gd_ctx *ctx, const char *path, gd_index **out);
+const char *gd_index_seq_name(const gd_index *idx, int i);
 
 #ifdef __cplusplus
 }

@@ -337,3 +337,28 @@ def test_lr_sam_end_to_end_matches_reference_program(ctx, preset, k, w, bw, read
     assert txt.decode().splitlines() == want
     assert int((cand["reserved"][:, 0] >= 0).sum()) > 10   # chained candidates were stitched
     idx.close()
+
+
+@pytest.mark.skipif(not (maplib.have_ref_program() and cpu_has_avx512()), reason="needs oracle/_ref/GDiet_avx_sr and AVX-512")
+def test_index_loaded_from_the_reference_mmi_maps_like_the_built_one(ctx):
+    """Row F4, the way back: the reference program's own `-d` dump, loaded with gd_index_load_mmi, is the same device
+    index as the one built from the FASTA (same arrays, same contig names) and maps reads to the same candidates."""
+    import tempfile
+    from test_mmi import reference_mmi
+    contigs, reads = maplib.make_dataset(seed=14, contig_lens=(500000, 250000, 50001), n_reads=800)
+    tmp = tempfile.mkdtemp(prefix="gdmmi_")
+    open(os.path.join(tmp, "ref.mmi"), "wb").write(reference_mmi(contigs, 21, 11, "10", tmp))
+    built = ctx.index_build(contigs, 11, 21, "10")
+    loaded = ctx.index_load_mmi(os.path.join(tmp, "ref.mmi"))
+    assert loaded.seq_names() == ["chr1", "chr2", "chr3"]
+    for a, b in zip(built.export(), loaded.export()):
+        assert np.array_equal(a, b)
+    o = maplib.sr_opt(min_cnt=0.2, rec_frac=0.1)
+    off, lens, buf = flat_reads(reads)
+    r1 = ctx.sr_map_batch(built, off, lens, buf, o)
+    r2 = ctx.sr_map_batch(loaded, off, lens, buf, o)
+    for a, b in zip(r1, r2):
+        assert np.array_equal(a, b)
+    assert len(r1[1]) > 400
+    built.close()
+    loaded.close()

@@ -362,3 +362,29 @@ def test_index_loaded_from_the_reference_mmi_maps_like_the_built_one(ctx):
     assert len(r1[1]) > 400
     built.close()
     loaded.close()
+
+
+def test_sr_map_error_paths_and_capacity_retry(ctx, gd):
+    """Argument errors are reported (never a silent different answer) and a too-small output buffer yields
+    GD_ERR_CAPACITY with the required sizes, after which the same call succeeds."""
+    contigs, reads = maplib.make_dataset(seed=15, n_reads=600)
+    idx = ctx.index_build(contigs, 11, 21, "10")
+    off, lens, buf = flat_reads(reads)
+    o = maplib.sr_opt(min_cnt=0.2, rec_frac=0.1)
+    want = ctx.sr_map_batch(idx, off, lens, buf, o)
+    got = ctx.sr_map_batch(idx, off, lens, buf, o, cand_cap=8, cigar_cap=8)      # wrapper retries with the reported sizes
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    bad = maplib.sr_opt(af_max_loc=0)
+    with pytest.raises(gd.GdietError):
+        ctx.sr_map_batch(idx, off, lens, buf, bad)
+    short = lens.copy()
+    short[5] = 1                                                                  # shorter than the pattern
+    with pytest.raises(gd.GdietError):
+        ctx.sr_map_batch(idx, off, short, buf, o)
+    with pytest.raises(gd.GdietError):
+        ctx.index_load_mmi("/nonexistent/file.mmi")
+    again = ctx.sr_map_batch(idx, off, lens, buf, o)                              # the context is still usable
+    for a, b in zip(want, again):
+        assert np.array_equal(a, b)
+    idx.close()

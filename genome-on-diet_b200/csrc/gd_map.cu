@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(SR_WARPS * 32) gd_sr_seed_kernel(IndexDev I, S
                                                                   const int64_t *c2, const uint32_t *ret3, uint32_t *seed_n,
                                                                   uint32_t *seed_first, SrRead *rd, uint32_t *n_hits)
 {
+	__shared__ uint32_t s_cnt[SR_WARPS][1024];
 	const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
 	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
 		const int64_t *jo = job_off + (size_t)i * P.JW;
@@ -149,15 +150,32 @@ __global__ void __launch_bounds__(SR_WARPS * 32) gd_sr_seed_kernel(IndexDev I, S
 		uint32_t removed = 0;
 		for (int e = lane; e < n0; e += 32) sn[e] = 0;
 		__syncwarp();
-		if (P.q_occ_frac > 0.f && P.mid_occ > 0 && n0 > P.mid_occ) { // mm_seed_mz_flt (rare: reads with > mid_occ seeds)
-			for (int e0 = 0; e0 < n0; ++e0) {
-				const uint64_t x = mv[2 * e0];
-				uint32_t c = 0;
-				for (int e = lane; e < n0; e += 32) c += mv[2 * e] == x;
-				c = warp_sum(c);
-				if ((int)c > P.mid_occ && (float)(int)c > (float)n0 * P.q_occ_frac) {
-					if (lane == 0) sn[e0] = SR_FLT;
-					++removed;
+		if (P.q_occ_frac > 0.f && P.mid_occ > 0 && n0 > P.mid_occ) {
+			// mm_seed_mz_flt (seed.c:5-29): a minimizer value that occurs more than mid_occ times (and in more than q_occ_frac
+			// of the seeds) INSIDE the read loses all its seeds.  Every long read comes here (thousands of seeds), but
+			// almost no value qualifies: a 1024-counter table in shared memory (an upper bound of every value's count) picks
+			// the few seeds that need the exact count, which the warp then does over the whole list.
+			uint32_t *cnt = s_cnt[threadIdx.x >> 5];
+			for (int j = lane; j < 1024; j += 32) cnt[j] = 0;
+			__syncwarp();
+			for (int e = lane; e < n0; e += 32) atomicAdd(&cnt[(uint32_t)((mv[2 * e] * 0x9E3779B97F4A7C15ull) >> 54)], 1u);
+			__syncwarp();
+			for (int e0 = 0; e0 < n0; e0 += 32) {
+				const int e = e0 + lane;
+				const uint64_t xe = e < n0 ? mv[2 * e] : 0;
+				uint32_t cand = __ballot_sync(0xffffffffu, e < n0 && (int)cnt[(uint32_t)((xe * 0x9E3779B97F4A7C15ull) >> 54)] > P.mid_occ);
+				while (cand) {
+					const int src = __ffs(cand) - 1;
+					cand &= cand - 1;
+					const uint64_t x = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)xe, src) |
+					                   (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(xe >> 32), src) << 32;
+					uint32_t c = 0;
+					for (int j = lane; j < n0; j += 32) c += mv[2 * j] == x;
+					c = warp_sum(c);
+					if ((int)c > P.mid_occ && (float)(int)c > (float)n0 * P.q_occ_frac) {
+						if (lane == 0) sn[e0 + src] = SR_FLT;
+						++removed;
+					}
 				}
 			}
 			__syncwarp();

@@ -89,8 +89,9 @@ static inline int ksw_pick_group(int max_qlen, int max_tlen, int max_w, bool exa
 	if (!exact) {
 		while (G >= 16 && G < 64 && (int64_t)npairs * G / 32 < (int64_t)sms * 24) G <<= 1;
 		// A handful of very long pairs (fewer blocks than twice the SMs): two warps per pair leave half of every SM's four
-		// schedulers idle, so the gang grows to four warps.  (ONT, 72 pairs of 50 kbp: 94 -> see profiles; with hundreds of
-		// pairs four warps per pair do not gain, measured.)
+		// schedulers idle, so the gang grows to four warps.  (ONT, 72 pairs of 50 kbp: 94 -> 109 GCUPS; with hundreds of pairs four
+		// warps per pair do not gain, and eight warps per pair -- one step per 1300-wide row instead of two -- gained only 2 %:
+		// the per-row barriers and bookkeeping, not the number of steps, bound so few pairs.)
 		if (G == 64 && (int64_t)npairs < (int64_t)sms * 2) G = 128;
 	}
 	return G;

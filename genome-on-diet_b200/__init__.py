@@ -154,7 +154,29 @@ def lr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, 
     return txt, sam_off, stitch[:n]
 
 
-def sr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, contigs, opt, raw=False, ref=None):
+class SamParts:
+    """The pieces gd_sr_sam_batch_parts returns (input order); bytes() joins them, free() releases them."""
+
+    def __init__(self, parts, lens, n):
+        self.parts, self.lens, self.count = parts, lens, n
+        self.n = sum(int(lens[i]) for i in range(n))
+
+    def bytes(self):
+        return b"".join(C.string_at(self.parts[i], self.lens[i]) for i in range(self.count))
+
+    def free(self):
+        if self.parts:
+            L = load()
+            for i in range(self.count):
+                L.gd_free(self.parts[i])
+            L.gd_free(C.cast(self.parts, C.c_void_p)), L.gd_free(C.cast(self.lens, C.c_void_p))
+            self.parts = None
+
+    def __del__(self):
+        self.free()
+
+
+def sr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, contigs, opt, raw=False, ref=None, parts=False):
     """gd_sr_sam_batch: SAM records of a mapped batch (bytes, or a SamText handle with raw=True).
     contigs: list of ASCII uint8 arrays; ref = (ref_off, ref_len, concatenated buffer) may be passed to reuse it."""
     L = load()
@@ -171,6 +193,14 @@ def sr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, 
     cigar = np.ascontiguousarray(cigar, np.uint32) if len(cigar) else np.zeros(1, np.uint32)
     if len(cand) == 0:
         cand = np.zeros(1, SR_CAND_DTYPE)
+    if parts:
+        pp, pl, pn = C.POINTER(C.c_void_p)(), C.POINTER(C.c_size_t)(), C.c_int32(0)
+        rc = L.gd_sr_sam_batch_parts(len(lens), C.cast(n_arr, C.c_void_p), _ptr(off), _ptr(lens), _ptr(seq), _ptr(qual), _ptr(cand_off),
+                                     _ptr(cand), _ptr(cigar), len(ref_len), C.cast(s_arr, C.c_void_p), _ptr(ref_off), _ptr(ref_len),
+                                     _ptr(ref), C.byref(opt), C.byref(pp), C.byref(pl), C.byref(pn))
+        if rc != GD_OK:
+            raise GdietError("gd_sr_sam_batch_parts failed (%d)" % rc)
+        return SamParts(pp, pl, pn.value)
     rc = L.gd_sr_sam_batch(len(lens), C.cast(n_arr, C.c_void_p), _ptr(off), _ptr(lens), _ptr(seq), _ptr(qual), _ptr(cand_off),
                            _ptr(cand), _ptr(cigar), len(ref_len), C.cast(s_arr, C.c_void_p), _ptr(ref_off), _ptr(ref_len), _ptr(ref),
                            C.byref(opt), C.byref(out), C.byref(out_len))
@@ -269,7 +299,7 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
-           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write", "gd_lr_sam_batch", "gd_index_load_mmi", "gd_index_seq_name"]
+           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write", "gd_lr_sam_batch", "gd_index_load_mmi", "gd_index_seq_name", "gd_sr_sam_batch_parts"]
 
 
 def load():
@@ -354,6 +384,9 @@ def load():
     L.gd_sr_sam_batch.restype = i32
     L.gd_sr_sam_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
                                   C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.gd_sr_sam_batch_parts.restype = i32
+    L.gd_sr_sam_batch_parts.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
+                                        C.POINTER(C.POINTER(vp)), C.POINTER(C.POINTER(C.c_size_t)), C.POINTER(i32)]
     L.gd_lr_sam_batch.restype = i32
     L.gd_lr_sam_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
                                   C.POINTER(vp), C.POINTER(C.c_size_t), vp, vp]

@@ -730,7 +730,8 @@ extern "C" void gd_free(void *p) { free(p); }
 static int sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq, const char *qual,
                      const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq, const char *const *seq_names,
                      const int64_t *ref_off, const int32_t *ref_len, const char *ref, const gd_sr_post_opt_t *opt, char **sam,
-                     size_t *sam_len, bool long_read, int64_t *sam_off, uint8_t *needs_stitch);
+                     size_t *sam_len, bool long_read, int64_t *sam_off, uint8_t *needs_stitch, char ***parts_out = nullptr,
+                     size_t **part_len = nullptr, int *n_parts = nullptr);
 
 extern "C" int gd_sr_sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
                                const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar,
@@ -741,6 +742,18 @@ extern "C" int gd_sr_sam_batch(int n, const char *const *names, const int64_t *o
 		return GD_ERR_ARG;
 	return sam_batch(n, names, off, len, seq, qual, cand_off, cand, cigar, n_seq, seq_names, ref_off, ref_len, ref, opt, sam, sam_len, false,
 	                 nullptr, nullptr);
+}
+
+extern "C" int gd_sr_sam_batch_parts(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                                     const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar,
+                                     int n_seq, const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len,
+                                     const char *ref, const gd_sr_post_opt_t *opt, char ***parts, size_t **part_len, int *n_parts)
+{
+	if (n < 0 || !opt || !parts || !part_len || !n_parts ||
+	    (n > 0 && (!names || !off || !len || !seq || !cand_off || !seq_names || !ref_off || !ref)))
+		return GD_ERR_ARG;
+	return sam_batch(n, names, off, len, seq, qual, cand_off, cand, cigar, n_seq, seq_names, ref_off, ref_len, ref, opt, nullptr, nullptr,
+	                 false, nullptr, nullptr, parts, part_len, n_parts);
 }
 
 extern "C" int gd_lr_sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
@@ -758,7 +771,8 @@ extern "C" int gd_lr_sam_batch(int n, const char *const *names, const int64_t *o
 static int sam_batch(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq, const char *qual,
                      const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq, const char *const *seq_names,
                      const int64_t *ref_off, const int32_t *ref_len, const char *ref, const gd_sr_post_opt_t *opt, char **sam,
-                     size_t *sam_len, bool long_read, int64_t *sam_off, uint8_t *needs_stitch)
+                     size_t *sam_len, bool long_read, int64_t *sam_off, uint8_t *needs_stitch, char ***parts_out, size_t **part_len,
+                     int *n_parts)
 {
 	Ctx C = {n, names, off, len, seq, qual, cand_off, cand, cigar, n_seq, seq_names, ref_off, ref_len, ref, opt, long_read};
 	int nt = opt->n_threads > 0 ? opt->n_threads : (int)std::thread::hardware_concurrency();
@@ -790,6 +804,14 @@ static int sam_batch(int n, const char *const *names, const int64_t *off, const 
 		for (int t = 0; t < nt; ++t)
 			for (int64_t i = (int64_t)n * t / nt, e = (int64_t)n * (t + 1) / nt; i < e; ++i) sam_off[i] += (int64_t)at[t];
 		sam_off[n] = (int64_t)total;
+	}
+	if (parts_out) { // hand the per-thread pieces over as they are (input order): nothing is copied
+		*parts_out = (char **)malloc(sizeof(char *) * (size_t)nt), *part_len = (size_t *)malloc(sizeof(size_t) * (size_t)nt);
+		if (!*parts_out || !*part_len) return GD_ERR_ARG;
+		for (int t = 0; t < nt; ++t) (*parts_out)[t] = parts[t].b, (*part_len)[t] = parts[t].n, parts[t].b = nullptr;
+		*n_parts = nt;
+		if (sam_len) *sam_len = total;
+		return GD_OK;
 	}
 	char *buf = (char *)malloc(total + 1);
 	if (!buf) return GD_ERR_ARG;

@@ -327,6 +327,13 @@ int gd_sr_sam_batch(int n, const char *const *names, const int64_t *off, const i
                     const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq,
                     const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
                     const gd_sr_post_opt_t *opt, char **sam, size_t *sam_len);
+/* Same records, handed over as the pieces the worker threads produced (in input order) instead of one concatenated
+ * text, so that a host that writes them out (fwrite / writev, map.c:1208-1256) saves the copy: parts[0..n_parts) with
+ * part_len[] bytes each; free every piece and both arrays with gd_free. */
+int gd_sr_sam_batch_parts(int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                          const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq,
+                          const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
+                          const gd_sr_post_opt_t *opt, char ***parts, size_t **part_len, int *n_parts);
 /* The same for the long-read tree (LR/map.c:1807-1912): candidates with score == KSW_NEG_INF are dropped,
  * mm_update_extra uses the logarithmic gap cost, a valid candidate that is continued by a valid candidate
  * (cand.reserved[0] >= 0) absorbs it (concatenate_cigars, LR/map.c:41-640), then the min_dp_max filter and the ordering.

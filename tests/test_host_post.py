@@ -43,6 +43,21 @@ def our_sam(contigs, reads, cand_off, cand, cig, post):
     return (hdr + body).decode().splitlines()
 
 
+def test_sam_parts_equal_the_concatenated_text():
+    g = np.load(os.path.join(GOLDEN, "map_sr.npz"))
+    contigs, reads = maplib.make_dataset(seed=int(g["seed"]), n_reads=int(g["n_reads"]))
+    o = maplib.sr_opt(min_cnt=float(g["min_cnt"]), rec_frac=float(g["rec_frac"]))
+    cand_off, cand, cig = oracle_candidates(maplib.MapOracle(), contigs, reads, o)
+    n, L = reads.shape
+    names = ["r%d" % i for i in range(n)]
+    args = (names, np.arange(n, dtype=np.int64) * L, np.full(n, L, np.int32), np.ascontiguousarray(reads.reshape(-1)),
+            np.full(n * L, ord("I"), np.uint8), cand_off, cand, cig, ["chr1", "chr2", "chr3"], contigs, gd.sr_post_options(n_threads=5))
+    whole = gd.sr_sam_batch(*args)
+    parts = gd.sr_sam_batch(*args, parts=True)
+    assert parts.count == 5 and parts.bytes() == whole
+    parts.free()
+
+
 def strip_pg(text):
     return [l for l in text.splitlines() if not l.startswith("@PG")]
 

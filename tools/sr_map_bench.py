@@ -36,7 +36,7 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
         t0 = time.perf_counter()
         coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, opt, cand_cap=n_reads + 1024, cigar_cap=8 * n_reads + 1024)
         t1 = time.perf_counter()
-        h = gd.sr_sam_batch(names, off, lens, buf, qual, coff, cand, cig, ["chr1"], contigs, post, raw=True)
+        h = gd.sr_sam_batch(names, off, lens, buf, qual, coff, cand, cig, ["chr1"], contigs, post, parts=True)  # what a host writes out
         t2 = time.perf_counter()
         sam = h.bytes() if it == 3 else b""
         h.free()
@@ -73,7 +73,7 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
                 co, ca, cg = done.pop(nxt)
                 lo, hi = bounds[nxt], bounds[nxt + 1]
                 h = gd.sr_sam_batch(C_names[nxt], off[lo:hi] - off[lo], lens[lo:hi], buf[off[lo]:off[lo] + (hi - lo) * 150],
-                                    qual[off[lo]:off[lo] + (hi - lo) * 150], co, ca, cg, ["chr1"], contigs, post_p, raw=True)
+                                    qual[off[lo]:off[lo] + (hi - lo) * 150], co, ca, cg, ["chr1"], contigs, post_p, parts=True)
                 total_bytes += h.n
                 h.free()
                 nxt += 1

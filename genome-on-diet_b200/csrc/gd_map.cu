@@ -45,6 +45,7 @@ struct SrParams {
 	// long-read tree (GDiet-LongReads/map.c)
 	uint32_t vt_dis, vt_nb_loc, max_max_gap, max_min_gap;
 	float vt_cov, vt_df1, vt_df2, vt_f;
+	int32_t cnt_table; // the seed kernel was launched with its shared-memory counter table (mm_seed_mz_flt prefilter)
 };
 
 struct SrRead { // per-read state between K1 and K2
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(SR_WARPS * 32) gd_sr_seed_kernel(IndexDev I, S
                                                                   const int64_t *c2, const uint32_t *ret3, uint32_t *seed_n,
                                                                   uint32_t *seed_first, SrRead *rd, uint32_t *n_hits)
 {
-	__shared__ uint32_t s_cnt[SR_WARPS][1024];
+	extern __shared__ uint32_t s_cnt_dyn[]; // SR_WARPS x 1024 counters when P.cnt_table (long reads / small mid_occ), else nothing
 	const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
 	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
 		const int64_t *jo = job_off + (size_t)i * P.JW;
@@ -155,15 +156,18 @@ __global__ void __launch_bounds__(SR_WARPS * 32) gd_sr_seed_kernel(IndexDev I, S
 			// of the seeds) INSIDE the read loses all its seeds.  Every long read comes here (thousands of seeds), but
 			// almost no value qualifies: a 1024-counter table in shared memory (an upper bound of every value's count) picks
 			// the few seeds that need the exact count, which the warp then does over the whole list.
-			uint32_t *cnt = s_cnt[threadIdx.x >> 5];
-			for (int j = lane; j < 1024; j += 32) cnt[j] = 0;
-			__syncwarp();
-			for (int e = lane; e < n0; e += 32) atomicAdd(&cnt[(uint32_t)((mv[2 * e] * 0x9E3779B97F4A7C15ull) >> 54)], 1u);
-			__syncwarp();
+			uint32_t *cnt = s_cnt_dyn + (size_t)(threadIdx.x >> 5) * 1024;
+			if (P.cnt_table) {
+				for (int j = lane; j < 1024; j += 32) cnt[j] = 0;
+				__syncwarp();
+				for (int e = lane; e < n0; e += 32) atomicAdd(&cnt[(uint32_t)((mv[2 * e] * 0x9E3779B97F4A7C15ull) >> 54)], 1u);
+				__syncwarp();
+			}
 			for (int e0 = 0; e0 < n0; e0 += 32) {
 				const int e = e0 + lane;
 				const uint64_t xe = e < n0 ? mv[2 * e] : 0;
-				uint32_t cand = __ballot_sync(0xffffffffu, e < n0 && (int)cnt[(uint32_t)((xe * 0x9E3779B97F4A7C15ull) >> 54)] > P.mid_occ);
+				// (without the table every seed is a candidate: the exact count decides)
+				uint32_t cand = __ballot_sync(0xffffffffu, e < n0 && (!P.cnt_table || (int)cnt[(uint32_t)((xe * 0x9E3779B97F4A7C15ull) >> 54)] > P.mid_occ));
 				while (cand) {
 					const int src = __ffs(cand) - 1;
 					cand &= cand - 1;
@@ -956,7 +960,8 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	if ((rc = gd_reserve(ctx, ctx->mp_cnt, (size_t)(n + 1) * 4))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->mp_hoff, (size_t)(n + 2) * 8))) return rc;
 	const int blocks = std::max(1, std::min((n + SR_WARPS - 1) / SR_WARPS, ctx->sms * 16));
-	gd_sr_seed_kernel<<<blocks, SR_WARPS * 32, 0, s>>>(idx->d, P, n, d_len, K.job_off, K.raw, K.c3, K.c2, K.ret3,
+	P.cnt_table = (lr || max_len / o->W > o->mid_occ) ? 1 : 0; // only reads that can have more than mid_occ seeds need it
+	gd_sr_seed_kernel<<<blocks, SR_WARPS * 32, P.cnt_table ? SR_WARPS * 4096 : 0, s>>>(idx->d, P, n, d_len, K.job_off, K.raw, K.c3, K.c2, K.ret3,
 	                                                 (uint32_t *)ctx->mp_seed_n.p, (uint32_t *)ctx->mp_seed_first.p,
 	                                                 (SrRead *)ctx->mp_state.p, (uint32_t *)ctx->mp_cnt.p);
 	ctx->stat_launches++;
@@ -1026,7 +1031,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	const int64_t np = h_word[0];
 	clk.mark("window");
 	// ---- DP on the candidates that are not exact matches (flag KSW_EZ_APPROX_MAX, map.c:867)
-	const int cig_stride = max_q + max_t + 8;
+	const int cig_stride = (max_q + max_t + 8 + 31) & ~31; // rows of the DP's CIGAR scratch start on 128-byte lines
 	if (np > 0) {
 		if (np > 0x7fffffff) {
 			ctx->err = "gd_sr_map_batch: too many DP pairs in one slice";

@@ -707,7 +707,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 						if (C.zdrop >= 0 && res.max - H0 > C.zdrop + l * C.e2) res.zdropped = 1, stop = 1;
 					}
 				}
-				if (r == nrows - 1 && en0 == tlen - 1) res.score = H0;
+				if (!stop && r == nrows - 1 && en0 == tlen - 1) res.score = H0; // a Z-drop on the last row leaves before the score is set (ksw2_extd2_sse.c:380-382)
 			}
 		} else { // ksw2_extd2_sse.c:323-366
 			// the cells kept out of the bulk update: scan tail (H += v) and column en0 (H[en0-1] + u[en0])

@@ -18,7 +18,7 @@ def emu():
 
 
 def _check(emu, oracle, P, w, scn, flag, G, force_literal_max=False):
-    sc = synth.SCORING[scn]
+    sc = synth.SCORING[scn] if isinstance(scn, str) else scn
     mat = synth.score_matrix(sc["a"], sc["b"])
     res, cig = emu.ksw_batch(P, w, mat, sc, flag | (0x100 if force_literal_max else 0), G)
     for i in range(P["n"]):
@@ -36,6 +36,18 @@ def test_emu_ksw_ragged(emu, oracle, flag):
     for G, scn in ((4, "sr"), (8, "map-hifi"), (16, "map-ont"), (32, "sr")):
         w = rng.choice([-1, 5, 10, 20, 33, 37, 100, 150, 400], P["n"]).astype(np.int32)
         _check(emu, oracle, P, w, scn, flag, G)
+
+
+@pytest.mark.parametrize("flag", [0x18, 0x58])
+def test_emu_ksw_approx_drop_on_last_row(emu, oracle, flag):
+    """KSW_EZ_APPROX_DROP: a Z-drop on the last anti-diagonal leaves the loop before ez->score is set
+    (ksw2_extd2_sse.c:380-382); tiny pairs and small Z-drop values reach that row (found by tools/ksw_fuzz.py)"""
+    P = synth.ragged_pairs(60, seed=9, max_len=8)
+    w = np.random.default_rng(1).choice([-1, 1, 5, 33], P["n"]).astype(np.int32)
+    for zdrop in (0, 5):
+        sc = dict(synth.SCORING["sr"], zdrop=zdrop)
+        for G in (4, 32):
+            _check(emu, oracle, P, w, sc, flag, G)
 
 
 @pytest.mark.parametrize("G,wv", [(4, 10), (8, 37), (32, 64), (32, 5)])

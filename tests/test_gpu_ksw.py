@@ -67,6 +67,23 @@ def test_swapped_gap_pieces_and_qe_seed(ctx, oracle):
         assert_batch_equal(ez, coff, cig, exp)
 
 
+@pytest.mark.parametrize("flag", [0x18, 0x58])
+def test_approx_drop_on_last_row(ctx, oracle, flag):
+    """KSW_EZ_APPROX_DROP: a Z-drop on the last anti-diagonal leaves before ez->score is set (ksw2_extd2_sse.c:380-382)"""
+    for max_len, zdrop in ((8, 0), (8, 5), (40, 5), (150, 40)):
+        P = synth.ragged_pairs(400, seed=max_len + zdrop, max_len=max_len)
+        w = np.random.default_rng(zdrop).choice([-1, 1, 2, 5, 33, 100], P["n"]).astype(np.int32)
+        sc = dict(synth.SCORING["sr"], zdrop=zdrop)
+        exp = oracle_batch(oracle, P, w, sc, flag)
+        assert any(e[0]["zdropped"] and e[0]["score"] < -(1 << 29) for e in exp)
+        for G in (0, 4, 32):
+            ctx.set_option("ksw_group", G)
+            ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"],
+                                                params(sc, flag), w=w)
+            assert_batch_equal(ez, coff, cig, exp, what="flag %#x G %d zdrop %d" % (flag, G, zdrop))
+    ctx.set_option("ksw_group", 0)
+
+
 def test_long_banded_pairs_ring_wrap(ctx, oracle):
     """HiFi/ONT-like shapes at a size the oracle finishes in seconds; the column ring wraps hundreds of times"""
     for n, qlen, edit, wv, scn in ((6, 3000, 0.08, 200, "map-ont"), (4, 4000, 0.01, 500, "map-hifi")):

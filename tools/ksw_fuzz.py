@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--pairs", type=int, default=200)
+    ap.add_argument("--long", action="store_true", help="long pairs (1..12 kbp, bands 50..1300): block-per-pair gangs, ring wrap")
     a = ap.parse_args()
     O = Oracle()
     ctx = gd.Context(0)
@@ -53,8 +54,14 @@ def main():
         sc = draw_scoring(rng)
         flag = int(rng.choice(FLAGS))
         max_len = int(rng.choice([8, 40, 150, 300, 700]))
-        P = synth.ragged_pairs(a.pairs, seed=int(rng.integers(1 << 30)), max_len=max_len)
-        w = rng.choice([-1, 0, 1, 3, 5, 10, 20, 33, 37, 64, 100, 150, 400, 1000], P["n"]).astype(np.int32)
+        if a.long:
+            max_len = int(rng.choice([1000, 3000, 6000, 12000]))
+            P = synth.long_pairs(int(rng.integers(2, 9)), max_len, float(rng.choice([0.01, 0.08, 0.15])),
+                                 seed=int(rng.integers(1 << 30)), tlen_extra=float(rng.choice([0.0, 0.01, 0.05])))
+            w = rng.choice([50, 151, 500, 1000, 1300], P["n"]).astype(np.int32)
+        else:
+            P = synth.ragged_pairs(a.pairs, seed=int(rng.integers(1 << 30)), max_len=max_len)
+            w = rng.choice([-1, 0, 1, 3, 5, 10, 20, 33, 37, 64, 100, 150, 400, 1000], P["n"]).astype(np.int32)
         G = int(rng.choice([0, 4, 8, 16, 32]))
         exp = oracle_batch(O, P, w, sc, flag)
         ctx.set_option("ksw_group", G)

@@ -31,7 +31,7 @@ KSW_NEG_INF = -0x40000000
 GD_OK, GD_ERR_NO_DEVICE, GD_ERR_CUDA, GD_ERR_ARG, GD_ERR_CAPACITY = 0, 1, 2, 3, 4
 
 EXTZ_FIELDS = ["max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end"]
-GD_EXTZ_DTYPE = np.dtype([(f, np.int32) for f in EXTZ_FIELDS + ["tb_i", "tb_j", "rows_done", "r0", "r1"]])
+GD_EXTZ_DTYPE = np.dtype([(f, np.int32) for f in EXTZ_FIELDS + ["tb_i", "tb_j", "rows_done", "lead64", "r1"]])
 MM128_DTYPE = np.dtype([("x", np.uint64), ("y", np.uint64)])
 
 

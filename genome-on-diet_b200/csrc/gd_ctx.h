@@ -46,7 +46,7 @@ struct gd_ctx {
 	double tm_dp_us = 0, tm_sketch_us = 0;
 	long tm_dp_n = 0, tm_sketch_n = 0;
 	// DP scratch
-	GdBuf tpk, qpk, parena, ticket, cig_tmp, cig_off, cig_compact, res;
+	GdBuf tpk, qpk, parena, ticket, cig_tmp, cig_off, cig_compact, res, lead64_scr, lead64_list;
 	GdBuf d_qlen, d_tlen, d_w, d_qoff, d_toff, d_qbuf, d_tbuf;
 	GdPinned h_stage, h_res, h_cig, h_misc;
 	// sketch scratch

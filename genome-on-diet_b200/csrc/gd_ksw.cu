@@ -62,6 +62,16 @@ __global__ void __launch_bounds__(128) gd_ksw_traceback_warp_kernel(const KswBat
 	if (lp < B.n) ksw_traceback_warp(B, flag, lp, cigar, stride, tiles[wid], lane);
 }
 
+// the pairs whose walk entered the AVX-512 build's lead-in cells (normally none): one block per pair, see ksw_lead64_pair
+__global__ void __launch_bounds__(128) gd_ksw_lead64_kernel(const KswConsts C, const KswBatch B, const KswLead64 L)
+{
+	const int cnt = L.list[0];
+	for (int k = blockIdx.x; k < cnt; k += gridDim.x) {
+		ksw_lead64_pair(C, B, L, L.list[1 + k], L.scratch + (size_t)blockIdx.x * L.slot_bytes, threadIdx.x, blockDim.x);
+		__syncthreads();
+	}
+}
+
 __global__ void gd_ksw_nocigar_kernel(int n, KswResult *res)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -281,6 +291,21 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 	if ((rc = gd_reserve(ctx, ctx->qpk, (size_t)chunk * geo.q_stride + 64))) return rc;
 	if (with_p && (rc = gd_reserve(ctx, ctx->parena, (size_t)chunk * geo.p_stride + 64))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->ticket, 256))) return rc;
+	// scratch of the lead-in model (gd_ksw_lead64_kernel): a few block slots, each the state columns + the 64-lane backtrack rows of one pair
+	KswLead64 L64;
+	int l64_blocks = 0;
+	if (with_p) {
+		const int mq = std::max(max_qlen, 1), mt = std::max(max_tlen, 1);
+		L64.T64 = (mt + 63) / 64 * 64;
+		L64.ncol64 = ((std::min(std::min(mq, mt), max_w + 1) + 63) / 64 + 1) * 64;
+		L64.slot_bytes = ((int64_t)10 * L64.T64 + (int64_t)(mq + mt - 1) * L64.ncol64 + 255) / 256 * 256;
+		l64_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(chunk, ctx->sms), ((int64_t)128 << 20) / L64.slot_bytes));
+		if ((rc = gd_reserve(ctx, ctx->lead64_scr, (size_t)l64_blocks * L64.slot_bytes))) return rc;
+		if ((rc = gd_reserve(ctx, ctx->lead64_list, ((size_t)chunk + 4) * sizeof(int32_t)))) return rc;
+		L64.list = (const int32_t *)ctx->lead64_list.p, L64.scratch = (uint8_t *)ctx->lead64_scr.p;
+		L64.qoff = d_qoff, L64.toff = d_toff, L64.qbuf = d_qbuf, L64.tbuf = d_tbuf;
+		L64.cigar = d_cigar, L64.stride = cigar_stride;
+	}
 
 	ctx->stat_ksw_ring = geo.ring, ctx->stat_ksw_group = G, ctx->stat_ksw_chunks = 0;
 	cudaStream_t s = ctx->stream;
@@ -294,8 +319,10 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 		B.res = (KswResult *)d_ez, B.ticket = (int32_t *)ctx->ticket.p;
 		B.hot = (const KswHot *)((uint8_t *)ctx->ticket.p + 64);
 		B.ring = geo.ring, B.group_smem = geo.group_smem;
+		B.lead64 = with_p ? (int32_t *)ctx->lead64_list.p : nullptr;
 
 		GD_CUDA_OK(ctx, cudaMemsetAsync(ctx->ticket.p, 0, 4, s));
+		if (with_p) GD_CUDA_OK(ctx, cudaMemsetAsync(ctx->lead64_list.p, 0, 4, s));
 		{
 			int blocks = std::min((cn + 3) / 4, ctx->sms * 16);
 			gd_ksw_pack_kernel<<<blocks, 128, 0, s>>>(cn, base, d_qlen, d_qoff, d_qbuf, d_tlen, d_toff, d_tbuf,
@@ -310,8 +337,9 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 		if (with_p) {
 			if (max_qlen + max_tlen >= 2048) gd_ksw_traceback_warp_kernel<<<(cn + 3) / 4, 128, 0, s>>>(B, flag, d_cigar, cigar_stride);
 			else gd_ksw_traceback_kernel<<<(cn + 127) / 128, 128, 0, s>>>(B, flag, d_cigar, cigar_stride);
+			gd_ksw_lead64_kernel<<<l64_blocks, 128, 0, s>>>(C, B, L64); // blocks leave at once unless a walk reported a pair
 		}
-		ctx->stat_launches += with_p ? 3 : 2;
+		ctx->stat_launches += with_p ? 4 : 2;
 		ctx->stat_ksw_chunks++;
 	}
 	GD_CUDA_OK(ctx, cudaGetLastError());

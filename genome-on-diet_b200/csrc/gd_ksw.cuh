@@ -67,7 +67,8 @@ struct KswResult {
 	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end;
 	int32_t tb_i, tb_j; // traceback start cell (target, query) or -1: filled by the DP kernel
 	int32_t rows_done;  // anti-diagonals executed (for cell accounting)
-	int32_t pad0, pad1;
+	int32_t lead64;     // 1: the walk entered the AVX-512 build's lead-in cells (see ksw_lead64_pair); CIGAR from that model
+	int32_t pad1;
 };
 
 // Batch-uniform constants, precomputed on the host (gd_ksw_make_consts).
@@ -105,6 +106,7 @@ struct KswBatch {
 	const KswHot *hot;   // sweep constants in device memory (see KswHot)
 	int32_t ring;        // R: columns per ring (multiple of 8)
 	int32_t group_smem;  // bytes of shared memory per group
+	int32_t *lead64;     // [0]: number of, [1..]: chunk-local pairs whose walk entered the AVX-512 lead-in cells (may be NULL)
 };
 
 GD_DEV uint32_t pack16(int v) { return ((uint32_t)(v & 0xff) << 8) | ((uint32_t)(v & 0xff) << 24); }
@@ -398,7 +400,7 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 	KswResult res;
 	res.max = 0, res.zdropped = 0, res.max_q = res.max_t = res.mqe_t = res.mte_q = -1;
 	res.score = res.mqe = res.mte = GD_KSW_NEG_INF, res.n_cigar = 0, res.reach_end = 0;
-	res.tb_i = res.tb_j = -1, res.rows_done = 0, res.pad0 = res.pad1 = 0;
+	res.tb_i = res.tb_j = -1, res.rows_done = 0, res.lead64 = res.pad1 = 0;
 
 	for (;;) {
 		// ================= fetch: groups without a pair take the next ticket =================
@@ -803,13 +805,186 @@ GD_DEV void ksw_pack_pair(const uint8_t *GD_RESTRICT q, int qlen, const uint8_t 
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The AVX-512 build's lead-in cells.  ksw_extd2_avx512 works on 64-cell vectors: the first vector of a row
+// starts at stv = st0/64*64 and every lane of it is computed and stored (ksw2_extd2_avx.c:242,383,442-476),
+// so the cells of [stv, st) -- st = st0/16*16, where the SSE build starts -- get state and backtrack bytes of
+// their own, and off[r] = stv makes ksw_backtrack READ those bytes where the SSE build forces an insertion
+// (ksw2.h:136).  No true cell ever depends on them (the boundary is blended into the lane of column st and
+// last_st stays 16-aligned, :36,99,884), so scores, maxima and Z-drop are those of the 16-aligned sweep above,
+// and a walk reaches them only by a deletion step off the band's left edge out of a cell that starts at a
+// 16- but not 64-aligned column -- impossible with the presets (-q-2e < min score is needed), seen with random
+// scoring and bands <= 3.  The walkers therefore only DETECT the case (one compare on the forced-insertion
+// branch) and the few pairs that hit it are redone by ksw_lead64_pair: a literal cell-at-a-time model of the
+// 64-lane rows (the lane-0 left neighbour of a first vector that starts left of st is byte 15 of its own
+// 128-bit lane, i.e. column stv+15 of the previous row: index[0] = 15, :88-93), one thread block per pair,
+// state in global scratch, followed by the walk over its own backtrack rows.
+struct KswLead64 {
+	const int32_t *list;  // [0] = count, [1..] = chunk-local pair numbers (KswBatch::lead64)
+	const int64_t *qoff, *toff;
+	const uint8_t *qbuf, *tbuf; // raw byte codes of the caller's batch
+	uint8_t *scratch;     // per block: 10 * T64 state bytes, then the backtrack rows
+	int64_t slot_bytes;
+	int32_t T64, ncol64;  // launch-wide upper bounds the slots are sized for
+	uint32_t *cigar;
+	int32_t stride;
+};
+
+template <class BT> GD_DEV void ksw_lead64_report(const BT &B, KswResult *res, int lp)
+{
+	res->lead64 = 1;
+	if (B.lead64) {
+		const int k = atomic_add(B.lead64, 1);
+		B.lead64[1 + k] = lp;
+	}
+}
+
+struct CigOut { // run-length CIGAR writer of the walkers (ksw_push_cigar, ksw2.h:100-111), walk order
+	uint32_t *cig;
+	int stride, n, overflow;
+	uint32_t cur;
+	GD_MEM void push(uint32_t op, uint32_t len)
+	{
+		if (cur && (cur & 0xf) == op) cur += len << 4;
+		else {
+			flush();
+			cur = len << 4 | op;
+		}
+	}
+	GD_MEM void flush()
+	{
+		if (!cur) return;
+		if (n < stride) cig[n] = cur;
+		else overflow = 1;
+		++n, cur = 0;
+	}
+};
+
+// One block redoes one pair.  `tid`/`nt`: thread and block size; every thread owns the columns t with t % nt == tid.
+GD_DEV void ksw_lead64_pair(const KswConsts &C, const KswBatch &B, const KswLead64 &L, int lp, uint8_t *scr, int tid, int nt)
+{
+	const int pair = B.base + lp;
+	KswResult *res = &B.res[pair];
+	const int qlen = B.qlen[pair], tlen = B.tlen[pair];
+	int w = B.w ? B.w[pair] : B.w_all;
+	if (w < 0) w = imax(tlen, qlen);
+	const uint8_t *query = L.qbuf + L.qoff[pair], *target = L.tbuf + L.toff[pair];
+	const int T64 = (tlen + 63) & ~63;
+	const int ncol64 = ((imin(imin(qlen, tlen), w + 1) + 63) / 64 + 1) * 64; // ksw2_extd2_avx.c:145-146
+	const bool right = (C.flag & KSW_F_RIGHT) != 0;
+	// state: x, v, x2 of the previous and the current row (ping-pong: a cell reads its left neighbour's old values),
+	// u, y, y2, s in place (same column, same thread)
+	int8_t *xa = (int8_t *)scr, *va = xa + L.T64, *x2a = va + L.T64, *xb = x2a + L.T64, *vb = xb + L.T64, *x2b = vb + L.T64;
+	int8_t *u = x2b + L.T64, *y = u + L.T64, *y2 = y + L.T64, *s = y2 + L.T64;
+	uint8_t *p = (uint8_t *)(s + L.T64);
+	const int8_t i1 = (int8_t)(-C.q - C.e), i2 = (int8_t)(-C.q2 - C.e2);
+	const int8_t mch = (int8_t)hi8(C.MCH16), mis = (int8_t)(C.MIS4 & 0xff), scn = (int8_t)(C.SCN4 & 0xff);
+	const int8_t q1 = (int8_t)C.q, q21 = (int8_t)C.q2, qe = (int8_t)(C.q + C.e), qe2 = (int8_t)(C.q2 + C.e2);
+	for (int t = tid; t < T64; t += nt)
+		xa[t] = va[t] = xb[t] = vb[t] = u[t] = y[t] = i1, x2a[t] = x2b[t] = y2[t] = i2, s[t] = 0;
+	sync_block();
+	const int nrows = res->rows_done; // rows the sweep executed (a Z-drop leaves the loop early)
+	int last_st = -1, last_en = -1;
+	for (int r = 0; r < nrows; ++r) {
+		Bounds b;
+		if (!row_bounds(r, qlen, tlen, w, b)) break;
+		const int st = b.st, en = b.en, stv = b.st0 & ~63;
+		const int gd = gap_delta(r, C);
+		int8_t bx1 = i1, bx21 = i2, bv1 = i1; // ksw2_extd2_sse.c:149-159
+		if (st > 0) {
+			if (st - 1 >= last_st && st - 1 <= last_en) bx1 = xa[st - 1], bx21 = x2a[st - 1], bv1 = va[st - 1];
+		} else bv1 = (int8_t)gd;
+		const int ext_end = imin(b.st0 + (((b.en0 - b.st0) >> 4) + 1) * 16, T64); // the score row is rewritten on [st0, ext_end)
+		for (int t = stv + ((tid - stv) % nt + nt) % nt; t <= imax(en, ext_end - 1); t += nt) {
+			if (t >= b.st0 && t < ext_end) { // xor-table rule, ksw2_extd2_avx.c:187-208,312-313; zero padding outside the sequences
+				const int qi = r - t;
+				const uint32_t tc = t < tlen ? target[t] : 0, qc = (qi >= 0 && qi < qlen) ? query[qi] : 0;
+				const uint32_t idx = tc ^ (qc == 4 ? 8u : qc);
+				s[t] = (idx & 0x80) ? 0 : (idx & 15) == 0 ? mch : (idx & 15) < 4 ? mis : (idx & 15) < 13 ? scn : 0;
+			}
+			if (t > en) continue;
+			int8_t x1, v1, x21;
+			if (t == st) x1 = bx1, v1 = bv1, x21 = bx21;
+			else if (t == stv) x1 = xa[stv + 15], v1 = va[stv + 15], x21 = x2a[stv + 15];
+			else x1 = xa[t - 1], v1 = va[t - 1], x21 = x2a[t - 1];
+			int8_t yt = y[t], y2t = y2[t], ut = u[t];
+			if (t == r && en >= r) yt = i1, y2t = i2, ut = (int8_t)gd; // ksw2_extd2_sse.c:160-163
+			int8_t z = s[t], a = (int8_t)(x1 + v1), bb = (int8_t)(yt + ut), a2 = (int8_t)(x21 + v1), b2 = (int8_t)(y2t + ut);
+			uint32_t d = 0;
+			if (!right) {
+				if (a > z) d = 1, z = a;
+				if (bb > z) d = 2, z = bb;
+				if (a2 > z) d = 3, z = a2;
+				if (b2 > z) d = 4, z = b2;
+			} else {
+				if (a >= z) d = 1, z = a;
+				if (bb >= z) d = 2, z = bb;
+				if (a2 >= z) d = 3, z = a2;
+				if (b2 >= z) d = 4, z = b2;
+			}
+			if (z > mch) z = mch;
+			u[t] = (int8_t)(z - v1), vb[t] = (int8_t)(z - ut);
+			const int8_t tq = (int8_t)(z - q1), tq2 = (int8_t)(z - q21);
+			a = (int8_t)(a - tq), bb = (int8_t)(bb - tq), a2 = (int8_t)(a2 - tq2), b2 = (int8_t)(b2 - tq2);
+			if (!right) {
+				if (a > 0) d |= 0x08; else a = 0;
+				if (bb > 0) d |= 0x10; else bb = 0;
+				if (a2 > 0) d |= 0x20; else a2 = 0;
+				if (b2 > 0) d |= 0x40; else b2 = 0;
+			} else {
+				if (a >= 0) d |= 0x08; else a = 0;
+				if (bb >= 0) d |= 0x10; else bb = 0;
+				if (a2 >= 0) d |= 0x20; else a2 = 0;
+				if (b2 >= 0) d |= 0x40; else b2 = 0;
+			}
+			xb[t] = (int8_t)(a - qe), y[t] = (int8_t)(bb - qe), x2b[t] = (int8_t)(a2 - qe2), y2[t] = (int8_t)(b2 - qe2);
+			p[(size_t)r * ncol64 + (t - stv)] = (uint8_t)d;
+		}
+		sync_block();
+		int8_t *sw;
+		sw = xa, xa = xb, xb = sw, sw = va, va = vb, vb = sw, sw = x2a, x2a = x2b, x2b = sw;
+		last_st = st, last_en = en;
+	}
+	if (tid != 0) return;
+	// the walk (ksw_backtrack, ksw2.h:115-163) with off[r] = stv, off_end[r] = en (ksw2_extd2_avx.c:442,524)
+	CigOut co;
+	co.cig = L.cigar + (size_t)pair * L.stride, co.stride = L.stride, co.n = 0, co.overflow = 0, co.cur = 0;
+	int i = res->tb_i, j = res->tb_j, state = 0;
+	while (i >= 0 && j >= 0) {
+		const int r = i + j;
+		int force = -1;
+		Bounds bd;
+		row_bounds(r, qlen, tlen, w, bd);
+		const int stv = bd.st0 & ~63;
+		if (i < stv) force = 2;
+		if (i > bd.en) force = 1;
+		const uint32_t cell = force < 0 ? p[(size_t)r * ncol64 + (i - stv)] : 0;
+		if (state == 0) state = cell & 7;
+		else if (!((cell >> (state + 2)) & 1)) state = 0;
+		if (state == 0) state = cell & 7;
+		if (force >= 0) state = force;
+		if (state == 0) co.push(0, 1), --i, --j;
+		else if (state == 1 || state == 3) co.push(2, 1), --i;
+		else co.push(1, 1), --j;
+	}
+	if (i >= 0) co.push(2, (uint32_t)(i + 1));
+	if (j >= 0) co.push(1, (uint32_t)(j + 1));
+	co.flush();
+	if (!co.overflow && !(C.flag & KSW_F_REV_CIGAR))
+		for (int k = 0; k < co.n >> 1; ++k) {
+			const uint32_t t = co.cig[k];
+			co.cig[k] = co.cig[co.n - 1 - k], co.cig[co.n - 1 - k] = t;
+		}
+	res->n_cigar = co.overflow ? -co.n : co.n;
+}
+
 // One thread per pair: walk the backtrack matrix (ksw_backtrack, ksw2.h:115-163 with is_rot=1)
 // and emit the run-length CIGAR in walk order (i.e. reversed) into cig_tmp[pair*stride ...].
 GD_DEV void ksw_traceback_one(const KswBatch &B, int flag, int lp, uint32_t *cig_out, int stride)
 {
 	const int pair = B.base + lp;
 	KswResult *res = &B.res[pair];
-	int i = res->tb_i, j = res->tb_j, n = 0, state = 0, overflow = 0;
+	int i = res->tb_i, j = res->tb_j, n = 0, state = 0, overflow = 0, lead64 = 0;
 	if (i < 0 || j < 0) {
 		res->n_cigar = 0;
 		return;
@@ -825,7 +1000,7 @@ GD_DEV void ksw_traceback_one(const KswBatch &B, int flag, int lp, uint32_t *cig
 		int r = i + j, force = -1;
 		Bounds bd;
 		row_bounds(r, qlen, tlen, w, bd);
-		if (i < bd.st) force = 2;
+		if (i < bd.st) force = 2, lead64 |= i >= (bd.st0 & ~63);
 		if (i > bd.en) force = 1;
 		const int cc = i - bd.st;
 		uint32_t cell = force < 0 ? p[(size_t)r * ncol16 + (cc & ~7) + chunk_pos(cc & 7)] : 0;
@@ -880,6 +1055,7 @@ GD_DEV void ksw_traceback_one(const KswBatch &B, int flag, int lp, uint32_t *cig
 			cig[k] = cig[n - 1 - k], cig[n - 1 - k] = t;
 		}
 	res->n_cigar = overflow ? -n : n;
+	if (lead64) ksw_lead64_report(B, res, lp);
 }
 
 // Same walk for long pairs, one WARP per pair: the backtrack bytes the path can touch next (32 rows x 80
@@ -893,7 +1069,7 @@ GD_DEV void ksw_traceback_warp(const KswBatch &B, int flag, int lp, uint32_t *ci
 {
 	const int pair = B.base + lp;
 	KswResult *res = &B.res[pair];
-	int i = res->tb_i, j = res->tb_j, n = 0, state = 0, overflow = 0;
+	int i = res->tb_i, j = res->tb_j, n = 0, state = 0, overflow = 0, lead64 = 0;
 	if (i < 0 || j < 0) {
 		if (lane == 0) res->n_cigar = 0;
 		return;
@@ -930,7 +1106,7 @@ GD_DEV void ksw_traceback_warp(const KswBatch &B, int flag, int lp, uint32_t *ci
 			int force = -1;
 			Bounds bd;
 			row_bounds(r, qlen, tlen, w, bd);
-			if (i < bd.st) force = 2;
+			if (i < bd.st) force = 2, lead64 |= i >= (bd.st0 & ~63);
 			if (i > bd.en) force = 1;
 			const int cc = i - wlo; // 0..79
 			const uint8_t *row = (const uint8_t *)(tile + (r_top - r) * GD_KSW_TB_CHUNKS);
@@ -992,6 +1168,7 @@ GD_DEV void ksw_traceback_warp(const KswBatch &B, int flag, int lp, uint32_t *ci
 			cig[k] = cig[n - 1 - k], cig[n - 1 - k] = t;
 		}
 	if (lane == 0) res->n_cigar = overflow ? -n : n;
+	if (lane == 0 && lead64) ksw_lead64_report(B, res, lp);
 }
 
 } // namespace gd

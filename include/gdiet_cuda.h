@@ -62,7 +62,9 @@ typedef struct {
 	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end;
 	int32_t tb_i, tb_j; /* traceback start cell (target, query), -1 = none */
 	int32_t rows_done;  /* anti-diagonals executed */
-	int32_t reserved[2];
+	int32_t lead64;     /* 1: the walk read cells the AVX-512 build computes left of the 16-aligned row start
+	                       (ksw2_extd2_avx.c:242,442); the CIGAR comes from the literal 64-lane model */
+	int32_t reserved;
 } gd_extz_t;
 
 /* Scoring / control arguments of ksw_extd2_sse(), batch-uniform (GDiet-ShortReads/ksw2.h:42-59). */

@@ -105,6 +105,10 @@ int gdo_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 	int8_t q = (int8_t)q_, e = (int8_t)e_, q2 = (int8_t)q2_, e2 = (int8_t)e2_;
 	const int with_cigar = !(flag & F_SCORE_ONLY), approx = !!(flag & F_APPROX_MAX), right = !!(flag & F_RIGHT);
 	int T16, ncol16, nrows, r, t, long_thres, long_diff, min_sc, last_st = -1, last_en = -1;
+	/* score_rule: 0 = SSE build, 1 = AVX-512 build (the parity target), 3 = AVX-512 score row on the SSE build's
+	 * 16-aligned rows (test aid: tells which pairs the lead-in cells change).  score_rule == 1 is the AVX-512 build: besides its xor-table score row, it works on 64-cell vectors whose first one
+	 * starts at st0 rounded down to 64 (ksw2_extd2_avx.c:242,383); see the core loop below */
+	const int lead = score_rule == 1 ? 64 : 16;
 	int8_t *u, *v, *x, *y, *x2, *y2, *s, sc_mch, sc_mis, sc_N, qe, qe2, pmat[16];
 	int32_t *H = 0, H0 = 0;
 	int H0_t = 0;
@@ -128,10 +132,10 @@ int gdo_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 	pmat[0] = sc_mch, pmat[1] = pmat[2] = pmat[3] = sc_mis;
 	for (t = 4; t <= 12; ++t) pmat[t] = sc_N;
 	if (w < 0) w = tlen > qlen ? tlen : qlen;
-	T16 = (tlen + 15) / 16 * 16;
+	T16 = (tlen + lead - 1) / lead * lead; /* state arrays: tlen_ vectors (ksw2_extd2_sse.c:91, ksw2_extd2_avx.c:144) */
 	ncol16 = qlen < tlen ? qlen : tlen;
-	ncol16 = ((ncol16 < w + 1 ? ncol16 : w + 1) + 15) / 16 + 1;
-	ncol16 *= 16;
+	ncol16 = ((ncol16 < w + 1 ? ncol16 : w + 1) + lead - 1) / lead + 1; /* ksw2_extd2_sse.c:92-93, ksw2_extd2_avx.c:145-146 */
+	ncol16 *= lead;
 	for (t = 1, min_sc = mat[1]; t < m * m; ++t) min_sc = min_sc < mat[t] ? min_sc : mat[t];
 	if (-min_sc > 2 * (q + e)) return 0;
 
@@ -156,8 +160,8 @@ int gdo_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 	}
 
 	for (r = 0; r < nrows; ++r) {
-		int st0 = 0, en0 = tlen - 1, st, en, ext_end;
-		int8_t x1, x21, v1;
+		int st0 = 0, en0 = tlen - 1, st, en, ext_end, stv;
+		int8_t x1, x21, v1, bx1, bx21, bv1;
 		if (st0 < r - qlen + 1) st0 = r - qlen + 1;
 		if (en0 > r) en0 = r;
 		if (st0 < (r - w + 1) >> 1) st0 = (r - w + 1) >> 1;
@@ -185,7 +189,7 @@ int gdo_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 			for (t = st0; t < ext_end && t < T16; ++t) {
 				int qi = r - t; /* query index of cell (r,t); outside [0,qlen) reads zero padding */
 				uint8_t tc = t < tlen ? target[t] : 0, qc = (qi >= 0 && qi < qlen) ? query[qi] : 0;
-				if (score_rule == 0) {
+				if (!(score_rule & 1)) {
 					s[t] = (tc == m - 1 || qc == m - 1) ? sc_N : (tc == qc ? sc_mch : sc_mis);
 				} else {
 					uint8_t idx = tc ^ (qc == 4 ? 8 : qc);
@@ -198,13 +202,25 @@ int gdo_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 				s[t] = mat[target[t] * m + qc];
 			}
 		}
-		/* core update over the rounded range */
-		if (with_cigar) off[r] = st, off_end[r] = en;
-		for (t = st; t <= en; ++t) {
-			int8_t z = s[t], a = w8(x1 + v1), b = w8(y[t] + u[t]), a2 = w8(x21 + v1), b2 = w8(y2[t] + u[t]);
-			int8_t u_old = u[t], tq, tq2;
+		/* core update over the rounded range.  The AVX-512 build starts its first 64-cell vector at stv = st0/64*64 and
+		 * stores every lane of it (ksw2_extd2_avx.c:242,383,442-476,497-553): the cells of [stv, st) are updated like
+		 * any other cell -- from the stale scores and the state left in those columns -- their backtrack bytes are
+		 * written, and off[r] = stv, so ksw_backtrack reads them where the SSE build forces an insertion
+		 * (ksw2.h:136).  The boundary x1/v1/x21 is blended into the lane of column st (mskc_ar, :36,99); lane 0 of
+		 * that vector receives byte 15 of its own 128-bit lane from the in-lane byte shuffle (index[0] = 15, :88-93),
+		 * i.e. the previous row's x/v/x2 of column stv+15.  Nothing a later row reads as a true cell depends on these
+		 * columns (st never decreases and last_st stays 16-aligned, :884). */
+		stv = st0 / lead * lead;
+		bx1 = x1, bv1 = v1, bx21 = x21;
+		if (stv < st) x1 = x[stv + 15], v1 = v[stv + 15], x21 = x2[stv + 15];
+		if (with_cigar) off[r] = stv, off_end[r] = en;
+		for (t = stv; t <= en; ++t) {
+			int8_t z, a, b, a2, b2, u_old, tq, tq2, nx1, nv1, nx21;
 			uint8_t d = 0;
-			int8_t nx1 = x[t], nv1 = v[t], nx21 = x2[t]; /* become the left neighbours of column t+1 */
+			if (t == st) x1 = bx1, v1 = bv1, x21 = bx21;
+			z = s[t], a = w8(x1 + v1), b = w8(y[t] + u[t]), a2 = w8(x21 + v1), b2 = w8(y2[t] + u[t]);
+			u_old = u[t];
+			nx1 = x[t], nv1 = v[t], nx21 = x2[t]; /* become the left neighbours of column t+1 */
 			if (!right) {
 				if (a > z) d = 1, z = a;
 				if (b > z) d = 2, z = b;
@@ -233,7 +249,7 @@ int gdo_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 				if (b2 >= 0) d |= 0x40; else b2 = 0;
 			}
 			x[t] = w8(a - qe), y[t] = w8(b - qe), x2[t] = w8(a2 - qe2), y2[t] = w8(b2 - qe2);
-			if (with_cigar) p[(size_t)r * ncol16 + (t - st)] = d;
+			if (with_cigar) p[(size_t)r * ncol16 + (t - stv)] = d;
 			x1 = nx1, v1 = nv1, x21 = nx21;
 		}
 		/* score tracking */

@@ -4,6 +4,7 @@
 #define GD_HOST_EMU 1
 #include "simt_emu.h"
 #include "gd_ksw_host.h"
+#include <algorithm>
 #include <vector>
 
 using namespace gd;
@@ -43,7 +44,7 @@ static void dispatch(const KswConsts &C, const KswBatch &B, int threads, bool ri
 extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, const uint8_t *qbuf, const int32_t *tlen,
                              const int64_t *toff, const uint8_t *tbuf, const int32_t *w, int m, const int8_t *mat,
                              int q, int e, int q2, int e2, int zdrop, int end_bonus, int flag, int G, int threads,
-                             KswResult *res, uint32_t *cigar, int cigar_stride)
+                             KswResult *res, uint32_t *cigar, int cigar_stride, int *lead64_count)
 {
 	KswConsts C = ksw_make_consts(m, mat, q, e, q2, e2, zdrop, end_bonus, flag & 0xff);
 	C.force_slow_max = (flag >> 8) & 1; // test hook: bit 8 of the emulator's flag argument
@@ -79,8 +80,23 @@ extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, co
 	case 128: dispatch<128>(C, B, threads, right, exact, with_p); break;
 	default: return -1;
 	}
-	if (with_p)
+	std::vector<int32_t> l64(n + 4, 0);
+	B.lead64 = l64.data();
+	if (with_p) {
 		for (int i = 0; i < n; ++i) ksw_traceback_one(B, flag, i, cigar, cigar_stride);
+		// the pairs whose walk entered the AVX-512 lead-in cells: the slow model, one 64-thread block per pair
+		KswLead64 L;
+		L.list = l64.data(), L.qoff = qoff, L.toff = toff, L.qbuf = qbuf, L.tbuf = tbuf;
+		L.T64 = (max_t + 63) / 64 * 64;
+		L.ncol64 = ((std::min(std::min(max_q, max_t), max_w + 1) + 63) / 64 + 1) * 64;
+		L.slot_bytes = (int64_t)10 * L.T64 + (int64_t)(max_q + max_t - 1) * L.ncol64;
+		L.cigar = cigar, L.stride = cigar_stride;
+		std::vector<uint8_t> scr((size_t)L.slot_bytes, 0x55);
+		L.scratch = scr.data();
+		for (int k = 0; k < l64[0]; ++k)
+			emu::launch(1, 64, 0, [&]() { ksw_lead64_pair(C, B, L, l64[1 + k], scr.data(), emu::thread_idx(), 64); });
+	}
+	if (lead64_count) *lead64_count = l64[0];
 	if (emu::rowmax_mismatches()) return -2; // fast row maximum disagreed with the literal scan
 	return 0;
 }

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 EMU_DIR = os.path.join(HERE, "emu")
 CSRC = os.path.join(ROOT, "genome-on-diet_b200", "csrc")
-RES = np.dtype([(f, np.int32) for f in EXTZ_FIELDS + ["tb_i", "tb_j", "rows_done", "pad0", "pad1"]])
+RES = np.dtype([(f, np.int32) for f in EXTZ_FIELDS + ["tb_i", "tb_j", "rows_done", "lead64", "pad1"]])
 
 
 def build():
@@ -30,7 +30,7 @@ class Emu:
         L = self.lib = C.CDLL(build())
         L.emu_ksw_batch.restype = C.c_int
         L.emu_ksw_batch.argtypes = [C.c_int, i32p, i64p, u8p, i32p, i64p, u8p, i32p, C.c_int, i8p] + [C.c_int] * 9 + [
-            C.c_void_p, C.c_void_p, C.c_int]
+            C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.emu_sketch_jobs.restype = C.c_long
         L.emu_sketch_jobs.argtypes = [C.c_int, i64p, i32p, i32p, u32p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int,
                                       C.c_int, C.c_int, i64p, u64p, C.c_int64]
@@ -40,11 +40,13 @@ class Emu:
         res = np.zeros(n, RES)
         stride = int((P["qlen"] + P["tlen"]).max()) + 8
         cig = np.zeros(n * stride, np.uint32)
+        l64 = C.c_int(0)
         rc = self.lib.emu_ksw_batch(n, P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"],
                                     np.ascontiguousarray(w, np.int32), 5, mat, sc["q"], sc["e"], sc["q2"], sc["e2"],
                                     sc["zdrop"], sc["end_bonus"], flag, G, threads, res.ctypes.data_as(C.c_void_p),
-                                    cig.ctypes.data_as(C.c_void_p), stride)
+                                    cig.ctypes.data_as(C.c_void_p), stride, C.byref(l64))
         assert rc == 0
+        self.last_lead64 = int(l64.value)
         return res, cig.reshape(n, stride)
 
     def sketch_jobs(self, seqs, shifts, rids, w, k, Z, small, grid=3):

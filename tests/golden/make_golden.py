@@ -112,6 +112,56 @@ def sketch_cases():
     print("sketch golden:", len(seqs), "cases")
 
 
+
+
+def ksw_lead64_cases():
+    """Narrow bands + scorings with b > q + 2e: the walks that step off the band's left edge into the AVX-512 build's
+    lead-in cells (off[r] rounded down to 64, ksw2_extd2_avx.c:242,442; read by ksw_backtrack, ksw2.h:136).  Kept: every
+    pair on which ksw_extd2_avx512 and ksw_extd2_sse return different CIGARs, plus as many on which they agree.
+    Every case carries its own scoring values.  Writes tests/golden/ksw_lead64_golden.npz."""
+    rng = np.random.default_rng(64)
+    R = Ref("avx")
+    flags = [0x08, 0x00, 0x0a, 0x88, 0x40, 0x18]
+    qs, ts, meta, ezs, cigs = [], [], [], [], []
+    n_diff = n_same = 0
+    while n_diff < 48:
+        e = int(rng.integers(1, 3))
+        q = int(rng.integers(1, 4))
+        b = int(rng.integers(q + 2 * e + 1, 2 * (q + e) + 1))
+        sc = dict(a=int(rng.integers(1, 5)), b=b, q=q, e=e, q2=int(rng.integers(6, 30)), e2=1, zdrop=int(rng.choice([400, 40])),
+                  end_bonus=int(rng.choice([0, 5])))
+        mat = synth.score_matrix(sc["a"], sc["b"])
+        P = synth.ragged_pairs(40, seed=int(rng.integers(1 << 30)), max_len=300)
+        flag = int(rng.choice(flags))
+        for i in range(P["n"]):
+            qq = P["qbuf"][P["qoff"][i]:P["qoff"][i] + P["qlen"][i]]
+            tt = P["tbuf"][P["toff"][i]:P["toff"][i] + P["tlen"][i]]
+            if 7 in qq:
+                continue
+            w = int(rng.choice([0, 1, 2, 3, 5]))
+            ez, cig = R.ksw_extd2(qq, tt, mat, sc["q"], sc["e"], sc["q2"], sc["e2"], w, sc["zdrop"], sc["end_bonus"], flag)
+            ez0, cig0 = R.ksw_extd2(qq, tt, mat, sc["q"], sc["e"], sc["q2"], sc["e2"], w, sc["zdrop"], sc["end_bonus"], flag, which=0)
+            differ = ez != ez0 or not np.array_equal(cig, cig0)
+            if not differ and n_same >= n_diff:
+                continue
+            n_diff += differ
+            n_same += not differ
+            qs.append(qq), ts.append(tt), cigs.append(cig)
+            meta.append([flag, w, sc["a"], sc["b"], sc["q"], sc["e"], sc["q2"], sc["e2"], sc["zdrop"], sc["end_bonus"], int(differ)])
+            ezs.append([ez[f] for f in EXTZ_FIELDS])
+    P = synth.pack_pairs(qs, ts)
+    coff = np.zeros(len(cigs) + 1, np.int64)
+    coff[1:] = np.cumsum([len(c) for c in cigs])
+    np.savez_compressed(os.path.join(HERE, "ksw_lead64_golden.npz"), qbuf=P["qbuf"], qoff=P["qoff"], qlen=P["qlen"],
+                        tbuf=P["tbuf"], toff=P["toff"], tlen=P["tlen"], meta=np.array(meta, np.int32),
+                        ez=np.array(ezs, np.int32), cigar_off=coff, cigar=np.concatenate(cigs).astype(np.uint32))
+    print("ksw lead64 golden:", len(qs), "cases,", n_diff, "with AVX-512 != SSE")
+
+
 if __name__ == "__main__":
-    ksw_cases()
-    sketch_cases()
+    if "lead64" in sys.argv[1:]:  # only the file added in round 2
+        ksw_lead64_cases()
+    else:
+        ksw_cases()
+        sketch_cases()
+        ksw_lead64_cases()

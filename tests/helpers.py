@@ -44,3 +44,18 @@ def cigar_spans(cig):
     ops = cig & 0xf
     lens = (cig >> 4).astype(np.int64)
     return int(lens[(ops == 0) | (ops == 1)].sum()), int(lens[(ops == 0) | (ops == 2)].sum())
+
+
+def lead64_golden_cases():
+    """tests/golden/ksw_lead64_golden.npz -> (q, t, scoring dict, flag, w, differs-from-SSE, ez list, cigar) per case"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ksw_lead64_golden.npz"))
+    out = []
+    for i in range(len(g["qlen"])):
+        q = g["qbuf"][g["qoff"][i]:g["qoff"][i] + g["qlen"][i]]
+        t = g["tbuf"][g["toff"][i]:g["toff"][i] + g["tlen"][i]]
+        flag, w, a, b, gq, ge, gq2, ge2, zdrop, end_bonus, differ = (int(x) for x in g["meta"][i])
+        sc = dict(a=a, b=b, q=gq, e=ge, q2=gq2, e2=ge2, zdrop=zdrop, end_bonus=end_bonus)
+        out.append((q, t, sc, flag, w, differ, [int(x) for x in g["ez"][i]],
+                    g["cigar"][g["cigar_off"][i]:g["cigar_off"][i + 1]]))
+    return out

@@ -59,6 +59,22 @@ def test_emu_ksw_ring_wrap(emu, oracle, G, wv):
         _check(emu, oracle, P, w, "map-ont", flag, G)
 
 
+def test_emu_ksw_lead64_golden(emu):
+    """the walk kernels detect a step into the AVX-512 build's lead-in cells and ksw_lead64_pair redoes those pairs:
+    reference vectors (ksw_extd2_avx512) on which the SSE build answers differently"""
+    from helpers import lead64_golden_cases
+    cases = lead64_golden_cases()
+    redone = 0
+    for i, (q, t, sc, flag, w, differ, ez_exp, cig_exp) in enumerate(cases):
+        P = synth.pack_pairs([q], [t])
+        res, cig = emu.ksw_batch(P, np.array([w], np.int32), synth.score_matrix(sc["a"], sc["b"]), sc, flag, (4, 8, 32)[i % 3])
+        assert [int(res[0][f]) for f in EXTZ_FIELDS] == ez_exp, "case %d" % i
+        assert np.array_equal(cig[0][:ez_exp[EXTZ_FIELDS.index("n_cigar")]], cig_exp), "case %d" % i
+        assert not differ or emu.last_lead64 == 1
+        redone += emu.last_lead64
+    assert redone >= 40
+
+
 def _tie_pairs(n, seed):
     """low-complexity pairs (short tandem repeats, homopolymers): many equal scores along an anti-diagonal,
     which is what the reference's 4-lane row-maximum tie order is sensitive to"""

@@ -38,6 +38,49 @@ def test_golden_vectors_through_batch_abi(ctx):
     ctx.set_option("ksw_group", 0)
 
 
+def test_lead64_golden_vectors(ctx):
+    """reference vectors (ksw_extd2_avx512) whose walk reads the AVX-512 build's lead-in cells (off[r] rounded down to 64):
+    through the batch ABI and through the drop-in symbol"""
+    from helpers import lead64_golden_cases
+    ni = EXTZ_FIELDS.index("n_cigar")
+    redone = 0
+    for i, (q, t, sc, flag, w, differ, ez_exp, cig_exp) in enumerate(lead64_golden_cases()):
+        P = synth.pack_pairs([q, q], [t, t])
+        ctx.set_option("ksw_group", (0, 4, 32)[i % 3])
+        ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], params(sc, flag), w_all=w)
+        for k in range(2):
+            assert [int(ez[k][f]) for f in EXTZ_FIELDS] == ez_exp, "case %d" % i
+            assert np.array_equal(cig[coff[k]:coff[k + 1]], cig_exp), "case %d" % i
+        redone += int(ez[0]["lead64"])
+        assert not differ or int(ez[0]["lead64"]) == 1
+        if i % 4 == 0:
+            e1, c1 = gd.ksw_extd2(q, t, synth.score_matrix(sc["a"], sc["b"]), sc["q"], sc["e"], sc["q2"], sc["e2"], w, sc["zdrop"],
+                                  sc["end_bonus"], flag, entry="ksw_extd2_avx512")
+            assert [e1[f] for f in EXTZ_FIELDS] == ez_exp and np.array_equal(c1, cig_exp), "drop-in case %d" % i
+    ctx.set_option("ksw_group", 0)
+    assert redone >= 40
+
+
+def test_narrow_band_random_scoring_sweep(ctx, oracle):
+    """bounded slice of tools/ksw_fuzz.py --narrow: bands 0..5, scorings with b > q + 2e, every gang size"""
+    rng = np.random.default_rng(640)
+    redone = pairs = 0
+    for it in range(24):
+        e, q = int(rng.integers(1, 3)), int(rng.integers(1, 4))
+        sc = dict(a=int(rng.integers(1, 5)), b=int(rng.integers(q + 2 * e + 1, 2 * (q + e) + 1)), q=q, e=e,
+                  q2=int(rng.integers(6, 30)), e2=1, zdrop=int(rng.choice([400, 40])), end_bonus=int(rng.choice([0, 5])))
+        P = synth.ragged_pairs(150, seed=int(rng.integers(1 << 30)), max_len=int(rng.choice([150, 300, 700])))
+        w = rng.choice([0, 1, 2, 3, 5], P["n"]).astype(np.int32)
+        flag = int(rng.choice([0x08, 0x00, 0x0a, 0x88, 0x40, 0x18, 0xc2]))
+        ctx.set_option("ksw_group", int(rng.choice([0, 4, 8, 16, 32])))
+        ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], params(sc, flag), w=w)
+        assert_batch_equal(ez, coff, cig, oracle_batch(oracle, P, w, sc, flag), what="round %d flag %#x" % (it, flag))
+        redone += int(ez["lead64"].sum())
+        pairs += P["n"]
+    ctx.set_option("ksw_group", 0)
+    assert pairs == 3600 and redone >= 1
+
+
 @pytest.mark.parametrize("flag", [0x08, 0x00, 0x18, 0x40, 0x48, 0xc2, 0x01, 0x0a, 0x42, 0x80])
 def test_ragged_pairs_vs_oracle(ctx, oracle, flag):
     P = synth.ragged_pairs(300, seed=100 + flag, max_len=260)

@@ -37,6 +37,22 @@ def test_ksw_oracle_matches_golden(oracle):
         assert np.array_equal(cig, g["cigar"][g["cigar_off"][i]:g["cigar_off"][i + 1]]), "case %d" % i
 
 
+def test_ksw_oracle_matches_lead64_golden(oracle):
+    """narrow bands + scorings with b > q + 2e: the walk reads the AVX-512 build's lead-in cells (off[r] rounded down to
+    64, ksw2_extd2_avx.c:242,442); on half of the cases the SSE build returns a different CIGAR"""
+    from helpers import lead64_golden_cases
+    cases = lead64_golden_cases()
+    assert sum(c[5] for c in cases) >= 40
+    n16 = 0
+    for i, (q, t, sc, flag, w, differ, ez_exp, cig_exp) in enumerate(cases):
+        args = (q, t, synth.score_matrix(sc["a"], sc["b"]), sc["q"], sc["e"], sc["q2"], sc["e2"], w, sc["zdrop"], sc["end_bonus"], flag)
+        ez, cig = oracle.ksw_extd2(*args)
+        assert [ez[f] for f in EXTZ_FIELDS] == ez_exp and np.array_equal(cig, cig_exp), "case %d" % i
+        ez16, cig16 = oracle.ksw_extd2(*args, score_rule=3)  # the 16-aligned rows of the SSE build
+        n16 += [ez16[f] for f in EXTZ_FIELDS] != ez_exp or not np.array_equal(cig16, cig_exp)
+    assert n16 == sum(c[5] for c in cases)
+
+
 def test_sketch_oracle_matches_golden(oracle):
     g = load_sketch_golden()
     pats = [str(p) for p in g["patterns"]]

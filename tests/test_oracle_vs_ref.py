@@ -30,6 +30,28 @@ def test_ksw_oracle_vs_reference_sse_and_avx512(oracle, ref_avx):
         assert _same(ref_avx.ksw_extd2(*args, which=0), oracle.ksw_extd2(*args, score_rule=0)), "sse case %d" % i
 
 
+def test_ksw_oracle_vs_reference_narrow_bands_random_scoring(oracle, ref_avx):
+    """bands 0..5 with scorings that let a walk leave the band on the left (b > q + 2e): the AVX-512 build reads its
+    lead-in cells there (off[r] rounded down to 64), the SSE build forces an insertion; both must be reproduced"""
+    rng = np.random.default_rng(64)
+    n_diff = 0
+    for it in range(160):
+        e, q = int(rng.integers(1, 3)), int(rng.integers(1, 4))
+        sc = dict(a=int(rng.integers(1, 5)), b=int(rng.integers(q + 2 * e + 1, 2 * (q + e) + 1)), q=q, e=e,
+                  q2=int(rng.integers(6, 30)), e2=1, zdrop=int(rng.choice([400, 40])), end_bonus=int(rng.choice([0, 5])))
+        mat = synth.score_matrix(sc["a"], sc["b"])
+        P = synth.ragged_pairs(40, seed=int(rng.integers(1 << 30)), max_len=300)
+        flag = int(rng.choice([0x08, 0x00, 0x0a, 0x88, 0x40, 0x18]))
+        for i in range(P["n"]):
+            qq, tt = pair(P, i)
+            args = (qq, tt, mat, sc["q"], sc["e"], sc["q2"], sc["e2"], int(rng.choice([0, 1, 2, 3, 5])), sc["zdrop"], sc["end_bonus"], flag)
+            ra, rs = ref_avx.ksw_extd2(*args), ref_avx.ksw_extd2(*args, which=0)
+            assert _same(ra, oracle.ksw_extd2(*args, score_rule=1)), "avx512 round %d case %d" % (it, i)
+            assert _same(rs, oracle.ksw_extd2(*args, score_rule=0)), "sse round %d case %d" % (it, i)
+            n_diff += 7 not in qq and not _same(ra, rs)
+    assert n_diff >= 8  # the sweep does reach the lead-in cells
+
+
 def test_ksw_oracle_vs_reference_long_band(oracle, ref_avx):
     P = synth.long_pairs(2, 3000, 0.08, seed=5, tlen_extra=0.02)
     sc = synth.SCORING["map-ont"]

@@ -68,7 +68,7 @@ class gd_sr_opt_t(C.Structure):
                 ("af_max_loc", C.c_int32), ("mid_occ", C.c_int32), ("max_max_occ", C.c_int32), ("occ_dist", C.c_int32),
                 ("q_occ_frac", C.c_float), ("for_only", C.c_int32), ("rev_only", C.c_int32),
                 ("a", C.c_int32), ("b", C.c_int32), ("q", C.c_int32), ("e", C.c_int32), ("q2", C.c_int32), ("e2", C.c_int32),
-                ("zdrop", C.c_int32), ("end_bonus", C.c_int32)]
+                ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("bw_frac", C.c_float), ("bw_min", C.c_uint32), ("bw_max", C.c_uint32)]
 
 
 GD_INDEX_NBUF = 7
@@ -268,7 +268,8 @@ SR_CAND_DTYPE = np.dtype([(f, np.int32) for f in SR_CAND_FIELDS] + [("reserved",
 
 def sr_options(Z="10", qlen=150, bw_frac=0.05, bw_min=150, bw_max=200, min_cnt=2.0, rec_frac=0.0, af_max_loc=20, **kw):
     """What `-ax sr -Z .. -W .. -r bw_frac,bw_min,bw_max -n min_cnt,rec_frac` leaves in mm_mapopt_t
-    (GDiet-ShortReads/options.c:130-150, main.c:166-182), with the band clamped as at map.c:624-631."""
+    (GDiet-ShortReads/options.c:130-150, main.c:166-182).  The band is computed per read from bw_frac, bw_min, bw_max as at
+    map.c:624-631 (`bw`, the value for a read of `qlen` bases, is only used when bw_max is set to 0)."""
     bw = int(np.float32(qlen * np.float32(bw_frac)))
     if bw_min > bw:
         bw = bw_min
@@ -276,7 +277,8 @@ def sr_options(Z="10", qlen=150, bw_frac=0.05, bw_min=150, bw_max=200, min_cnt=2
         bw = bw_max
     o = gd_sr_opt_t(W=len(Z), Z=Z.encode(), max_seeds=0.1, frag_mode=1, max_frag_len=800, bw=bw, min_cnt=min_cnt,
                     rec_threshold_frac=rec_frac, af_max_loc=af_max_loc, mid_occ=1000, max_max_occ=4095, occ_dist=500,
-                    q_occ_frac=0.01, for_only=0, rev_only=0, a=2, b=8, q=12, e=2, q2=24, e2=1, zdrop=100, end_bonus=10)
+                    q_occ_frac=0.01, for_only=0, rev_only=0, a=2, b=8, q=12, e=2, q2=24, e2=1, zdrop=100, end_bonus=10,
+                    bw_frac=bw_frac, bw_min=bw_min, bw_max=bw_max)
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -295,7 +297,7 @@ def build(verbose=False):
 _lib = None
 
 # every symbol include/gdiet_cuda.h declares
-EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat", "gd_stream", "ksw_extd2_sse",
+EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat", "gd_stream", "gd_thread_ctx_pool_size", "ksw_extd2_sse",
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
@@ -323,6 +325,8 @@ def load():
     L.gd_get_stat.argtypes = [vp, C.c_char_p]
     L.gd_stream.restype = vp
     L.gd_stream.argtypes = [vp]
+    L.gd_thread_ctx_pool_size.restype = C.c_long
+    L.gd_thread_ctx_pool_size.argtypes = [C.c_int]
     ksw_args = [vp, i32, vp, i32, vp, C.c_int8, vp, C.c_int8, C.c_int8, C.c_int8, C.c_int8, i32, i32, i32, i32,
                 C.POINTER(ksw_extz_t)]
     for name in ("ksw_extd2_sse", "ksw_extd2_avx512"):

@@ -2,6 +2,7 @@
 // batched DP entry point and the drop-in ksw_extd2_sse / ksw_extd2_avx512 symbols.
 #include "gd_ctx.h"
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -320,19 +321,52 @@ extern "C" int gd_ksw_extd2_batch(gd_ctx *ctx, int n, const int32_t *qlen, const
 }
 
 // ---- drop-in single-call entry points (GDiet-ShortReads/ksw2.h:68-69, ksw2_extd2_avx.h:38) ----
+// The reference's kt_for / kt_pipeline start fresh pthreads for every mini-batch and join them (kthread.c:54-69,
+// 139-160), so a context bound to the thread for good would be leaked once per worker and batch -- with its
+// streams, events and grow-only device / pinned buffers.  Contexts therefore live in a per-device pool: a thread
+// checks one out on its first drop-in call and its thread_local holder hands it back (buffers and all) when the
+// thread exits; the next batch's workers reuse them.
+namespace {
+std::mutex g_pool_mu;
+std::map<int, std::vector<gd_ctx *>> g_pool;
+struct ThreadCtx {
+	gd_ctx *ctx = nullptr;
+	~ThreadCtx()
+	{
+		if (!ctx) return;
+		cudaSetDevice(ctx->device);
+		cudaStreamSynchronize(ctx->stream);
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		g_pool[ctx->device].push_back(ctx);
+	}
+};
+} // namespace
+
 gd_ctx *gd_thread_ctx()
 {
-	static thread_local gd_ctx *tctx = nullptr;
-	if (!tctx) {
+	static thread_local ThreadCtx t;
+	if (!t.ctx) {
 		int dev = 0;
 		const char *env = getenv("GDIET_DEVICE");
 		if (env) dev = atoi(env);
-		if (gd_init(dev, &tctx) != GD_OK) {
+		{
+			std::lock_guard<std::mutex> lk(g_pool_mu);
+			std::vector<gd_ctx *> &v = g_pool[dev];
+			if (!v.empty()) t.ctx = v.back(), v.pop_back();
+		}
+		if (t.ctx) cudaSetDevice(dev);
+		else if (gd_init(dev, &t.ctx) != GD_OK) {
 			fprintf(stderr, "[gdiet_cuda] FATAL: %s (there is no CPU fallback)\n", gd_strerror(nullptr));
 			abort();
 		}
 	}
-	return tctx;
+	return t.ctx;
+}
+
+extern "C" long gd_thread_ctx_pool_size(int device)
+{ // contexts parked in the pool of `device` (tests: the pool, not the number of threads ever started, bounds the footprint)
+	std::lock_guard<std::mutex> lk(g_pool_mu);
+	return (long)g_pool[device].size();
 }
 
 static void extd2_one(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m,

@@ -39,6 +39,8 @@ using namespace gd;
 struct SrParams {
 	int32_t W, JW, crop, k, frag_mode;
 	uint32_t max_nb_seeds, bw;
+	float bw_frac;          // short reads: per-read band (map.c:624-631) when bw_max > 0
+	uint32_t bw_min, bw_max;
 	float min_cnt, rec_frac, q_occ_frac;
 	int32_t af_max_loc, mid_occ, max_max_occ, occ_dist, for_only, rev_only, a;
 	int32_t stride; // bytes per candidate in the query / target code buffers
@@ -47,6 +49,16 @@ struct SrParams {
 	float vt_cov, vt_df1, vt_df2, vt_f;
 	int32_t cnt_table; // the seed kernel was launched with its shared-memory counter table (mm_seed_mz_flt prefilter)
 };
+
+// band width / vote distance of a short read of `qlen` bases, map.c:624-631
+__host__ __device__ static inline uint32_t sr_read_bw(const SrParams &P, int qlen)
+{
+	if (P.bw_max == 0) return P.bw;
+	uint32_t bw = (uint32_t)((float)qlen * P.bw_frac);
+	if (P.bw_min > bw) bw = P.bw_min;
+	else if (P.bw_max < bw) bw = P.bw_max;
+	return bw;
+}
 
 struct SrRead { // per-read state between K1 and K2
 	uint32_t shift, n0, n_mv, ext;
@@ -411,8 +423,9 @@ __global__ void __launch_bounds__(SR_WARPS * 32) gd_sr_vote_kernel(IndexDev I, S
 		S.out_len = 0;
 		S.recovery.score = 0, S.recovery.chrom_id = 0, S.recovery.target_loc = 0, S.recovery.fq = S.recovery.lq = S.recovery.str = 0;
 		SrVt *pot = s_pot[wib];
-		sr_vote(t, q, nf, 0, pot, S, s_t[wib], s_q[wib], P.bw, (int32_t)R.ext, thr, (unsigned)P.af_max_loc, rec_thr, lane);
-		sr_vote(tr, qr, nr, 1, pot, S, s_t[wib], s_q[wib], P.bw, (int32_t)R.ext, thr, (unsigned)P.af_max_loc, rec_thr, lane);
+		const uint32_t bw = sr_read_bw(P, (int)qlen_sum);
+		sr_vote(t, q, nf, 0, pot, S, s_t[wib], s_q[wib], bw, (int32_t)R.ext, thr, (unsigned)P.af_max_loc, rec_thr, lane);
+		sr_vote(tr, qr, nr, 1, pot, S, s_t[wib], s_q[wib], bw, (int32_t)R.ext, thr, (unsigned)P.af_max_loc, rec_thr, lane);
 		if (lane == 0 && S.out_len == 0 && S.recovery.score != 0) pot[0] = S.recovery, S.out_len = 1; // map.c:692-699
 		const unsigned nb = __shfl_sync(0xffffffffu, S.out_len, 0);
 		__syncwarp();
@@ -772,13 +785,14 @@ __global__ void __launch_bounds__(128) gd_sr_window_kernel(IndexDev I, SrParams 
 
 // DP work list: the candidates that were not exact matches
 __global__ void gd_sr_pairs_kernel(int64_t nc, int stride, const gd_sr_cand_t *cand, const int64_t *pair_off, int32_t *pqlen,
-                                   int32_t *ptlen, int64_t *poff)
+                                   int32_t *ptlen, int64_t *poff, int32_t *pw, SrParams P, const int32_t *len)
 {
 	const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (ci >= nc) return;
 	if (pair_off[ci + 1] == pair_off[ci]) return;
 	const int64_t p = pair_off[ci];
 	pqlen[p] = cand[ci].qe - cand[ci].qs, ptlen[p] = cand[ci].re - cand[ci].rs, poff[p] = ci * (int64_t)stride;
+	if (pw) pw[p] = (int32_t)sr_read_bw(P, len[cand[ci].reserved[0]]); // the band of the candidate's read (map.c:624-631,923)
 }
 
 // K4a: scores and CIGAR lengths of every candidate
@@ -911,8 +925,9 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	SrPhaseClock clk(s);
 	int rc;
 	int64_t lo = INT64_MAX, hi = 0, sum_len = 0;
-	int max_len = 0;
+	int max_len = 0, min_len = INT32_MAX;
 	for (int i = 0; i < n; ++i) {
+		min_len = std::min(min_len, len[i]);
 		if (len[i] < o->W || off[i] < 0) {
 			ctx->err = "gd_sr_map_batch: read shorter than the pattern";
 			return GD_ERR_ARG;
@@ -924,7 +939,8 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	memset(&P, 0, sizeof(P));
 	P.W = o->W, P.k = idx->d.k, P.frag_mode = o->frag_mode;
 	P.max_nb_seeds = o->frag_mode ? (o->max_frag_len == 0 ? 800u : (uint32_t)o->max_frag_len) : 0xffffffffu; // map.c:621-622
-	P.bw = o->bw, P.min_cnt = o->min_cnt, P.rec_frac = o->rec_threshold_frac, P.q_occ_frac = o->q_occ_frac;
+	P.bw = o->bw, P.bw_frac = lr ? 0.f : o->bw_frac, P.bw_min = lr ? 0u : o->bw_min, P.bw_max = lr ? 0u : o->bw_max;
+	P.min_cnt = o->min_cnt, P.rec_frac = o->rec_threshold_frac, P.q_occ_frac = o->q_occ_frac;
 	P.af_max_loc = o->af_max_loc, P.mid_occ = o->mid_occ, P.max_max_occ = o->max_max_occ, P.occ_dist = o->occ_dist;
 	P.for_only = o->for_only, P.rev_only = o->rev_only, P.a = o->a;
 	P.stride = (max_len + 15) / 16 * 16;
@@ -1037,12 +1053,14 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 			ctx->err = "gd_sr_map_batch: too many DP pairs in one slice";
 			return GD_ERR_ARG;
 		}
-		if ((rc = gd_reserve(ctx, ctx->mp_pair, (size_t)np * 16 + 64))) return rc;
+		if ((rc = gd_reserve(ctx, ctx->mp_pair, (size_t)np * 20 + 64))) return rc;
 		if ((rc = gd_reserve(ctx, ctx->mp_ez, (size_t)np * sizeof(gd_extz_t)))) return rc;
 		if ((rc = gd_reserve(ctx, ctx->mp_cig, (size_t)np * cig_stride * 4 + 64))) return rc;
 		int64_t *d_poff = (int64_t *)ctx->mp_pair.p;
 		int32_t *d_pqlen = (int32_t *)(d_poff + np), *d_ptlen = d_pqlen + np;
-		gd_sr_pairs_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(nc, P.stride, d_cand, d_pair_off, d_pqlen, d_ptlen, d_poff);
+		int32_t *d_pw = P.bw_max > 0 ? d_ptlen + np : nullptr; // per-pair band when it depends on the read length
+		const int max_bw = (int)std::max(sr_read_bw(P, max_len), sr_read_bw(P, min_len));
+		gd_sr_pairs_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(nc, P.stride, d_cand, d_pair_off, d_pqlen, d_ptlen, d_poff, d_pw, P, d_len);
 		ctx->stat_launches++;
 		int8_t mat[25]; // map.c:861-865
 		const int g = o->a, bb = o->b < 0 ? o->b : -o->b;
@@ -1050,7 +1068,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 			for (int y = 0; y < 5; ++y) mat[x * 5 + y] = (x == 4 || y == 4) ? 0 : (x == y ? g : bb);
 		gd_ksw_params_t prm = {5, mat, o->q, o->e, o->q2, o->e2, o->zdrop, o->end_bonus, 0x08};
 		if ((rc = gd_ksw_run_device(ctx, (int)np, d_pqlen, d_poff, (const uint8_t *)ctx->mp_qbuf.p, d_ptlen, d_poff,
-		                            (const uint8_t *)ctx->mp_tbuf.p, nullptr, (int)o->bw, max_q, max_t, (int)o->bw, &prm,
+		                            (const uint8_t *)ctx->mp_tbuf.p, d_pw, (int)o->bw, max_q, max_t, max_bw, &prm,
 		                            (gd_extz_t *)ctx->mp_ez.p, (uint32_t *)ctx->mp_cig.p, cig_stride)))
 			return rc;
 	}

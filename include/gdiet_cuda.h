@@ -100,6 +100,7 @@ const char *gd_strerror(const gd_ctx *ctx); /* ctx may be NULL: last init error 
 int gd_set_option(gd_ctx *ctx, const char *key, long value);
 long gd_get_stat(const gd_ctx *ctx, const char *key);
 void *gd_stream(gd_ctx *ctx); /* the cudaStream_t all work of this context is issued on */
+long gd_thread_ctx_pool_size(int device); /* contexts of exited drop-in threads parked for reuse on `device` */
 
 /* ------------------------------------------------------------------------------------------ */
 /* (1) DP                                                                                      */
@@ -109,7 +110,14 @@ void *gd_stream(gd_ctx *ctx); /* the cudaStream_t all work of this context is is
  * GDiet-ShortReads/ksw2.h:68-69 and GDiet-ShortReads/ksw2_extd2_avx.h:38.  ez->cigar is (re)allocated
  * with krealloc(km, ...) when the host program provides kalloc, else realloc (km must then be NULL);
  * the caller frees it with kfree(km, ez->cigar) exactly as at GDiet-ShortReads/map.c:952.
- * Both names run the same kernel; scoring of codes > 4 follows ksw_extd2_avx512 (the GDiet_avx build). */
+ * Both names run the same kernel and BOTH answer like ksw_extd2_avx512 (the GDiet_avx build, the parity target):
+ * codes > 4 (the 7 a reverse-complemented N becomes, map.c:737-757) score by its xor table
+ * (ksw2_extd2_avx.c:187-208; the SSE file's compare rule, ksw2_extd2_sse.c:166-180, scores them as mismatches), and the
+ * walk reads the cells that build computes left of the 16-aligned row start (off[r] rounded down to 64, :242,442).  A
+ * host built WITHOUT AVX-512 that links this library therefore gets GDiet_avx's output, not its own CPU build's,
+ * on reads that hold N and on walks that leave a narrow band.
+ * The calling thread's context comes from a per-device pool and goes back to it when the thread exits (kt_for starts
+ * fresh threads per mini-batch): gd_thread_ctx_pool_size(). */
 void ksw_extd2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m,
                    const int8_t *mat, int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus,
                    int flag, ksw_extz_t *ez);
@@ -243,13 +251,17 @@ typedef struct {
 	char Z[64];    /* pattern (-Z), NUL padded */
 	float max_seeds; /* opt->max_seeds (mm_sketch2) */
 	int32_t frag_mode, max_frag_len; /* MM_F_FRAG_MODE, opt->max_frag_len: cap of mm_sketch3 (map.c:621-622) */
-	uint32_t bw;   /* band width / vote distance, already clamped as at map.c:624-631 */
+	uint32_t bw;   /* band width / vote distance of every read of the batch (used when bw_max == 0) */
 	float min_cnt, rec_threshold_frac; /* -n */
 	int32_t af_max_loc;                /* --AF_max_loc (<= 32) */
 	int32_t mid_occ, max_max_occ, occ_dist;
 	float q_occ_frac;
 	int32_t for_only, rev_only; /* MM_F_FOR_ONLY / MM_F_REV_ONLY (map.c:121-127) */
 	int32_t a, b, q, e, q2, e2, zdrop, end_bonus;
+	/* -r bw_frac,bw_min,bw_max: with bw_max > 0 the band and vote distance are computed PER READ as at map.c:624-631,
+	 * bw = (unsigned)(len * bw_frac) clamped to [bw_min, bw_max], and `bw` above is ignored */
+	float bw_frac;
+	uint32_t bw_min, bw_max;
 } gd_sr_opt_t;
 
 /* One candidate location of one read, in the order of the reference's candidate loop (map.c:764), with

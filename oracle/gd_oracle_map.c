@@ -265,6 +265,7 @@ int gdo_sr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_
 {
 	const int k = mi->k, w = mi->w;
 	unsigned qlen_sum = (unsigned)qlen;
+	unsigned bw = o->bw;
 	long cap = qlen + 16, n3;
 	uint64_t *mv = (uint64_t *)malloc((size_t)cap * 16 * (o->W + 1));
 	uint32_t *counts = (uint32_t *)calloc(o->W + 1, 4);
@@ -338,6 +339,11 @@ int gdo_sr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_
 	qsort(a_for, n_for, sizeof(loc_t), cmp_loc), qsort(a_rev, n_rev, sizeof(loc_t), cmp_loc);
 	d.n_a_for = n_for, d.n_a_rev = n_rev;
 
+	if (o->bw_max > 0) { /* map.c:624-631: the band and vote distance of THIS read */
+		bw = (unsigned)(float)(qlen * o->bw_frac);
+		if (o->bw_min > bw) bw = o->bw_min;
+		else if (o->bw_max < bw) bw = o->bw_max;
+	}
 	/* voting, map.c:665-699 */
 	{
 		int frag = o->frag_mode && tmp_ext < qlen_sum;
@@ -347,8 +353,8 @@ int gdo_sr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_
 	}
 	d.vt_threshold = vt_threshold;
 	pot = (vt_t *)calloc(o->af_max_loc + 1, sizeof(vt_t));
-	vote(a_for, n_for, 0, pot, &nb, o->bw, (int32_t)tmp_ext, &recovery, vt_threshold, o->af_max_loc, vt_rec_threshold);
-	vote(a_rev, n_rev, 1, pot, &nb, o->bw, (int32_t)tmp_ext, &recovery, vt_threshold, o->af_max_loc, vt_rec_threshold);
+	vote(a_for, n_for, 0, pot, &nb, bw, (int32_t)tmp_ext, &recovery, vt_threshold, o->af_max_loc, vt_rec_threshold);
+	vote(a_rev, n_rev, 1, pot, &nb, bw, (int32_t)tmp_ext, &recovery, vt_threshold, o->af_max_loc, vt_rec_threshold);
 	free(a_for), free(a_rev), free(mv), free(counts);
 	if (nb == 0) {
 		if (recovery.score == 0) { free(pot); if (dbg) *dbg = d; return 0; }
@@ -418,7 +424,7 @@ int gdo_sr_map_read(const gdo_index_t *mi, const char *seq, int qlen, const gdo_
 			if (cig_used < cigar_cap) cigar[cig_used] = len << 4 | 0;
 			cig_used += 1;
 		} else {
-			gdo_ksw_extd2(len, qs, len, ts, 5, mat, o->q, o->e, o->q2, o->e2, o->bw, o->zdrop, o->end_bonus, 0x08, 1,
+			gdo_ksw_extd2(len, qs, len, ts, 5, mat, o->q, o->e, o->q2, o->e2, (int)bw, o->zdrop, o->end_bonus, 0x08, 1,
 			                       &ez, cigar + cig_used, cigar_cap - cig_used);
 			c->score = ez.score, c->n_cigar = ez.n_cigar;
 			if (ez.n_cigar > 0) cig_used += ez.n_cigar;

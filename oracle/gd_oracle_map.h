@@ -27,12 +27,14 @@ typedef struct {
 	char Z[64];
 	float max_seeds;
 	int32_t frag_mode, max_frag_len;
-	uint32_t bw; /* already clamped as at map.c:624-631 */
+	uint32_t bw; /* used when bw_max == 0 */
 	float min_cnt, rec_threshold_frac;
 	int32_t af_max_loc, mid_occ, max_max_occ, occ_dist;
 	float q_occ_frac;
 	int32_t for_only, rev_only;
 	int32_t a, b, q, e, q2, e2, zdrop, end_bonus;
+	float bw_frac; /* -r bw_frac,bw_min,bw_max: per-read band, map.c:624-631 (when bw_max > 0) */
+	uint32_t bw_min, bw_max;
 } gdo_sr_opt_t;
 
 /* one candidate location of one read, in the order of the reference's candidate loop (map.c:764);

@@ -188,6 +188,33 @@ def test_dropin_symbols_match_oracle(oracle):
             assert ez == exp[0] and np.array_equal(cig, exp[1]), (i, entry)
 
 
+def test_dropin_thread_contexts_are_pooled(oracle):
+    """kt_for starts fresh threads for every mini-batch (kthread.c:54-69): the drop-in symbols must not leave one context
+    (streams, events, device and pinned buffers) behind per thread ever started"""
+    import threading
+    L = gd.load()
+    P = synth.ragged_pairs(8, seed=5, max_len=120)
+    sc = synth.SCORING["sr"]
+    mat = synth.score_matrix(sc["a"], sc["b"])
+    bad = []
+
+    def work(i):
+        q, t = pair(P, i % P["n"])
+        exp = oracle.ksw_extd2(q, t, mat, sc["q"], sc["e"], sc["q2"], sc["e2"], 50, sc["zdrop"], sc["end_bonus"], 0x08)
+        ez, cig = gd.ksw_extd2(q, t, mat, sc["q"], sc["e"], sc["q2"], sc["e2"], 50, sc["zdrop"], sc["end_bonus"], 0x08)
+        if ez != exp[0] or not np.array_equal(cig, exp[1]):
+            bad.append(i)
+
+    for batch in range(6):  # six "mini-batches" of three fresh worker threads each
+        ths = [threading.Thread(target=work, args=(3 * batch + k,)) for k in range(3)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        assert 1 <= L.gd_thread_ctx_pool_size(0) <= 3, "18 threads so far must have shared at most 3 contexts"
+    assert not bad
+
+
 def test_empty_and_degenerate_inputs(ctx):
     sc = synth.SCORING["sr"]
     z = np.zeros(0, np.int32)

@@ -276,7 +276,8 @@ def test_lr_map_tandem_repeats_match_reference_program(ctx):
 
 def test_sr_map_ragged_lowercase_and_tiny_reads(ctx, M):
     """One batch with read lengths from 2 to 330 (some shorter than k, some longer than the 300-base switch of
-    map.c:776), lower-case bases and N runs: candidates equal the oracle's read by read."""
+    map.c:776), lower-case bases and N runs, and a band that depends on the read length (-r 0.25,20,60: map.c:624-631
+    computes it per read): candidates equal the oracle's read by read."""
     rng = np.random.default_rng(77)
     contigs, base_reads = maplib.make_dataset(seed=13, read_len=330, n_reads=600)
     reads = []
@@ -288,15 +289,13 @@ def test_sr_map_ragged_lowercase_and_tiny_reads(ctx, M):
         if i % 11 == 0 and L > 30:
             r[10:14] = ord("N")
         reads.append(r)
-    o = maplib.sr_opt(min_cnt=0.2, rec_frac=0.1, bw_min=150, bw_max=200)
+    o = maplib.sr_opt(min_cnt=0.2, rec_frac=0.1, bw_frac=0.25, bw_min=20, bw_max=60)
     idx = ctx.index_build(contigs, 11, 21, "10")
     mi = M.index_build(contigs, 11, 21, "10")
     off, lens, buf = flat_ragged(reads)
     coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, o)
     n_cand = 0
     for i, r in enumerate(reads):
-        o_i = maplib.sr_opt(qlen=len(r), min_cnt=0.2, rec_frac=0.1, bw_min=150, bw_max=200)  # bw depends on the read length (map.c:624-631)
-        assert o_i.bw == o.bw
         oc, ocig, dbg = M.map_read(mi, r, o)
         mine = cand[coff[i]:coff[i + 1]]
         assert len(mine) == len(oc), "read %d (len %d): %d candidates, oracle %d (%s)" % (i, len(r), len(mine), len(oc), dbg)

@@ -46,6 +46,25 @@ def test_map_oracle_matches_reference_trace(M, seed, Z, read_len, extra, okw):
     assert n_cand > len(reads) // 2
 
 
+def test_map_oracle_mixed_read_lengths_per_read_band(M):
+    """-r 0.25,20,60 on reads of 60..300 bases: the clamp of map.c:624-631 is not saturated, so the band and the vote
+    distance differ from read to read inside one run"""
+    rng = np.random.default_rng(5)
+    contigs, base = maplib.make_dataset(seed=12, read_len=300, n_reads=900)
+    reads = [r[:int(rng.integers(60, 301))].copy() for r in base]
+    o = maplib.sr_opt(min_cnt=0.2, rec_frac=0.1, bw_frac=0.25, bw_min=20, bw_max=60)
+    _, tr = maplib.run_reference(contigs, reads, maplib.ref_cmdline(o, extra=["-r", "0.25,20,60", "-n", "0.2,0.1"]))
+    mi = M.index_build(contigs, 11, 21, "10")
+    bands, n_cand = set(), 0
+    for i, (r, t) in enumerate(zip(reads, tr)):
+        c, cig, _ = M.map_read(mi, r, o)
+        maplib.cands_equal_trace(c, cig, t["cands"], "read %d (len %d)" % (i, len(r)))
+        bands.update(int(x["w"]) for x in t["cands"] if not x["exact"])
+        n_cand += len(c)
+    M.lib.gdo_index_destroy(mi)
+    assert n_cand > 400 and len(bands) > 20 and min(bands) == 20 and max(bands) == 60
+
+
 def test_reference_sam_is_deterministic_across_threads():
     """the SAM (minus @PG) does not depend on -t; the golden SAM fixtures rely on it."""
     contigs, reads = maplib.make_dataset(seed=1, n_reads=400)

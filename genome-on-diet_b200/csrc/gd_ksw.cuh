@@ -41,6 +41,22 @@
 #ifndef GD_KSW_PREFETCH
 #define GD_KSW_PREFETCH 0 // 1: load the next step's chunk before computing the current one
 #endif
+// Three experiments that ncu's bank-conflict / partial-sector findings suggested (round 2), measured with tools/ksw_kbench.cu on a
+// B200 (profiles/r2_kbench_variants.txt; 262,144 pairs of 150x200, live / exact mode, DP kernel alone, identical results) and
+// left OFF because every one of them is slower: the kernel is bound by the integer-ALU pipe (67 % busy at 10 warps per SM), not
+// by shared-memory wavefronts or HBM.
+//   base 541.8 / 382.0 GCUPS;  ST16 539.4 / 378.2;  NBSHFL 476.9 / 338.7 (SHFL costs more than a 4-way conflicted 2-byte load);
+//   P32 534.0 / 370.4 (HBM reads 11.9 -> 0.6 KB per pair, writes 38.6 -> 35.4 KB: the read-modify-write of partial sectors is gone,
+//   but HBM was at 10 % of its bandwidth to begin with);  all three 467.3 / 333.7;  all + PREFETCH 433.9 / 307.7.
+#ifndef GD_KSW_ST16
+#define GD_KSW_ST16 0 // 1: score bytes + target codes of a record move as ONE 16-byte access (8-byte accesses of 4 groups collide on 2 banks)
+#endif
+#ifndef GD_KSW_NBSHFL
+#define GD_KSW_NBSHFL 0 // 1: the left neighbour's (x,v) / (x2,u) slot comes from the neighbour lane's registers (SHFL) instead of a 2-byte shared load (4-way conflict)
+#endif
+#ifndef GD_KSW_P32
+#define GD_KSW_P32 0 // 1: backtrack rows are pitched and padded to whole 32-byte sectors (no partial-sector writes -> no read-modify-write in HBM)
+#endif
 #ifndef GD_KSW_HOTMEM
 #define GD_KSW_HOTMEM 1 // 1: sweep constants come from device memory (stay in registers) instead of the constant bank
 #endif
@@ -190,9 +206,13 @@ GD_DEV bool row_bounds(int r, int qlen, int tlen, int w, Bounds &b)
 }
 
 GD_DEV int ksw_ncol16(int qlen, int tlen, int w)
-{ // row pitch of the backtrack matrix (ksw2_extd2_sse.c:92-94)
+{ // row pitch of the backtrack matrix (ksw2_extd2_sse.c:92-94), rounded up to whole 32-byte sectors
 	int n = imin(imin(qlen, tlen), w + 1);
-	return ((n + 15) / 16 + 1) * 16;
+	n = ((n + 15) / 16 + 1) * 16;
+#if GD_KSW_P32
+	n = (n + 31) & ~31;
+#endif
+	return n;
 }
 
 // Shared memory of one group: a ring of NR = R/8 chunk records followed by the staged sequences.
@@ -530,6 +550,11 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 				*(pc + REC_B + 1) = (uint8_t)(C.INIT_B >> 8);                      // x2 (high byte of B)
 			}
 		}
+#if GD_KSW_P32
+		// rows end on a 32-byte sector: a row of an odd number of 16-cell blocks gets 16 zero bytes behind it, so HBM never
+		// sees a partially written sector (which costs a read-modify-write)
+		if (WITH_P && active && li == 1 && ((en - st + 1) & 16)) *(uint4 *)(prow + (en - st + 1)) = rep4(0u);
+#endif
 		// Exact mode: column en0 (H[en0-1] + u[en0]) and the <= 3 columns of the scalar tail of the reference's
 		// row scan are kept out of the bulk update.  Lane li < 4 of the group owns column en0-3+li.
 		bool sp = false, sp_en0 = false;
@@ -586,12 +611,29 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 				uint8_t *const rc = ring + kk * REC;
 				uint8_t *const rp = ring + (kk == 0 ? NR - 1 : kk - 1) * REC; // record of the left neighbour chunk
 				const int tb = cc << 3;
+#if GD_KSW_ST16
+				{
+					const uint4 st = *(const uint4 *)(rc + REC_S); // REC_S and REC_T are adjacent
+					in.old.x = st.x, in.old.y = st.y, in.tw.x = st.z, in.tw.y = st.w;
+				}
+#else
 				in.tw = *(const uint2 *)(rc + REC_T);
+				in.old = *(const uint2 *)(rc + REC_S);
+#endif
 				const uint32_t *qw = (const uint32_t *)(qsm + ((qshift + tb) & ~3));
 				in.q0 = qw[0], in.q1 = qw[1], in.q2 = qw[2];
-				in.old = *(const uint2 *)(rc + REC_S);
 				in.SA = *(const uint4 *)(rc + REC_A), in.SB = *(const uint4 *)(rc + REC_B), in.SC = *(const uint4 *)(rc + REC_C);
+#if GD_KSW_NBSHFL
+				{ // lane li-1 of the gang holds the chunk to the left (its last slot = column tb-1); the first lane of a warp's
+				  // gang segment, and the lane on the row's first chunk (whose left neighbour is the boundary slot), read the ring
+					const uint32_t na = shfl_up(0xffffffffu, in.SA.w, 1, G <= 32 ? G : 32), nb = shfl_up(0xffffffffu, in.SB.w, 1, G <= 32 ? G : 32);
+					in.am1 = na >> 16, in.bm1 = nb >> 16;
+					if ((lane & ((G <= 32 ? G : 32) - 1)) == 0 || cc == cbeg)
+						in.am1 = *(const uint16_t *)(rp + REC_A + 14), in.bm1 = *(const uint16_t *)(rp + REC_B + 14);
+				}
+#else
 				in.am1 = *(const uint16_t *)(rp + REC_A + 14), in.bm1 = *(const uint16_t *)(rp + REC_B + 14);
+#endif
 				if (EXACT) in.ha = *(const uint4 *)(rc + REC_H), in.hb = *(const uint4 *)(rc + REC_H + 16);
 			};
 #if GD_KSW_PREFETCH
@@ -645,9 +687,15 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 				             prmt(SB.w, 0, 0x2404), y3, y23, u3, v3, x3, x23, zt3, fa3, fb3, fa23, fb23);
 				Gang<G>::sync(); // every lane has read its left neighbour's old column before anybody stores
 				if (cvalid) {
+#if GD_KSW_ST16
+					uint4 sv; // the target codes go back unchanged: one conflict-free 16-byte store
+					sv.x = sw0, sv.y = sw1, sv.z = in.tw.x, sv.w = in.tw.y;
+					*(uint4 *)(rc + REC_S) = sv;
+#else
 					uint2 sv;
 					sv.x = sw0, sv.y = sw1;
 					*(uint2 *)(rc + REC_S) = sv;
+#endif
 				}
 				if (core) {
 					uint4 o; // repack: selector 0x3715 = (hi.b3, lo.b3, hi.b1, lo.b1)

@@ -108,7 +108,11 @@ static inline KswGeom ksw_geometry(int max_qlen, int max_tlen, int max_w, bool e
 	g.t_stride = T16;
 	g.q_stride = (max_qlen + 15) / 16 * 16 + 64;
 	g.group_smem = ksw_group_smem_bytes(g.ring, exact, G <= 8 ? g.q_stride : 0); // the target travels in the ring records
-	g.p_stride = with_p ? (int64_t)(max_qlen + max_tlen - 1) * ncol16 : 0;
+	int pitch = ncol16; // the kernel's row pitch (ksw_ncol16)
+#if GD_KSW_P32
+	pitch = (pitch + 31) & ~31;
+#endif
+	g.p_stride = with_p ? (int64_t)(max_qlen + max_tlen - 1) * pitch : 0;
 	return g;
 }
 

@@ -76,7 +76,8 @@ int main(int argc, char **argv)
 		int st0 = std::max(std::max(0, r - qlen + 1), (r - w + 1) >> 1), en0 = std::min(std::min(tlen - 1, r), (r + w) >> 1);
 		cells += en0 - st0 + 1;
 	}
-	printf("variant PREFETCH=%d HOTMEM=%d  n=%d cells/pair=%ld\n", GD_KSW_PREFETCH, GD_KSW_HOTMEM, n, cells);
+	printf("variant PREFETCH=%d HOTMEM=%d ST16=%d NBSHFL=%d P32=%d  n=%d cells/pair=%ld\n", GD_KSW_PREFETCH, GD_KSW_HOTMEM, GD_KSW_ST16, GD_KSW_NBSHFL,
+	       GD_KSW_P32, n, cells);
 	for (int flag : {0x08, 0x00}) {
 		const bool exact = !(flag & 8);
 		KswConsts C = ksw_make_consts(5, mat, 12, 2, 24, 1, 100, 10, flag);
@@ -101,7 +102,7 @@ int main(int argc, char **argv)
 			KswBatch B;
 			B.n = n, B.base = 0, B.qlen = dql, B.tlen = dtl, B.w = 0, B.w_all = w, B.tpk = tpk, B.qpk = qpk, B.t_stride = geo.t_stride;
 			B.q_stride = geo.q_stride, B.p = p, B.p_stride = geo.p_stride, B.res = res, B.ticket = ticket, B.ring = geo.ring;
-			B.group_smem = geo.group_smem, B.hot = (const KswHot *)((uint8_t *)ticket + 64);
+			B.group_smem = geo.group_smem, B.hot = (const KswHot *)((uint8_t *)ticket + 64), B.lead64 = nullptr;
 			cudaEvent_t e0, e1;
 			CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 			float best_ms = 1e9;

@@ -301,7 +301,10 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "ksw_extd2_avx512", "gd_ksw_extd2_batch", "gd_ksw_extd2_batch_device", "gd_exact_match_batch_device",
            "mm_sketch", "mm_sketch2", "mm_sketch3", "gd_sketch_ref_batch", "gd_sketch_ref_batch_device",
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
-           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write", "gd_lr_sam_batch", "gd_index_load_mmi", "gd_index_seq_name", "gd_sr_sam_batch_parts"]
+           "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write", "gd_lr_sam_batch", "gd_index_load_mmi", "gd_index_seq_name", "gd_sr_sam_batch_parts",
+           "gd_pinned_alloc", "gd_pinned_free", "gd_multi_init", "gd_multi_destroy", "gd_multi_size", "gd_multi_ctx", "gd_multi_index",
+           "gd_multi_strerror", "gd_multi_index_bcast", "gd_multi_stat", "gd_multi_sr_map_batch", "gd_multi_lr_map_batch",
+           "gd_multi_sr_map_sam", "gd_multi_lr_map_sam"]
 
 
 def load():
@@ -388,6 +391,34 @@ def load():
     L.gd_sr_sam_batch.restype = i32
     L.gd_sr_sam_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
                                   C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.gd_pinned_alloc.restype = vp
+    L.gd_pinned_alloc.argtypes = [C.c_size_t]
+    L.gd_pinned_free.restype = None
+    L.gd_pinned_free.argtypes = [vp]
+    L.gd_multi_init.restype = i32
+    L.gd_multi_init.argtypes = [i32, vp, C.POINTER(vp)]
+    L.gd_multi_destroy.restype = None
+    L.gd_multi_destroy.argtypes = [vp]
+    L.gd_multi_size.restype = i32
+    L.gd_multi_size.argtypes = [vp]
+    L.gd_multi_ctx.restype = vp
+    L.gd_multi_ctx.argtypes = [vp, i32]
+    L.gd_multi_index.restype = vp
+    L.gd_multi_index.argtypes = [vp, i32]
+    L.gd_multi_strerror.restype = C.c_char_p
+    L.gd_multi_strerror.argtypes = [vp]
+    L.gd_multi_index_bcast.restype = i32
+    L.gd_multi_index_bcast.argtypes = [vp, vp, i32]
+    L.gd_multi_stat.restype = C.c_double
+    L.gd_multi_stat.argtypes = [vp, C.c_char_p]
+    L.gd_multi_sr_map_batch.restype = i32
+    L.gd_multi_sr_map_batch.argtypes = [vp, i32, vp, vp, vp, C.POINTER(gd_sr_opt_t), vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.gd_multi_lr_map_batch.restype = i32
+    L.gd_multi_lr_map_batch.argtypes = [vp, i32, vp, vp, vp, C.POINTER(gd_lr_opt_t), vp, vp, i64, vp, i64, C.POINTER(i64)]
+    for fn, ot in ((L.gd_multi_sr_map_sam, gd_sr_opt_t), (L.gd_multi_lr_map_sam, gd_lr_opt_t)):
+        fn.restype = i32
+        fn.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.POINTER(ot), C.POINTER(gd_sr_post_opt_t), i32, vp, vp, vp, vp,
+                       C.POINTER(C.POINTER(vp)), C.POINTER(C.POINTER(C.c_size_t)), C.POINTER(i32)]
     L.gd_sr_sam_batch_parts.restype = i32
     L.gd_sr_sam_batch_parts.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(gd_sr_post_opt_t),
                                         C.POINTER(C.POINTER(vp)), C.POINTER(C.POINTER(C.c_size_t)), C.POINTER(i32)]
@@ -451,7 +482,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.gd_destroy(self.h)
+            if getattr(self, "_owned", True):  # (views handed out by Multi.ctx() belong to the gd_multi)
+                self.lib.gd_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -619,11 +651,86 @@ class Context:
             return cand_off, cand[: int(cand_off[n])], cig[: int(ncig.value)]
 
 
+class Multi:
+    """gd_multi: several GPUs of one box from one process -- index broadcast, contiguous read shards, input-order results."""
+
+    def __init__(self, n_dev):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.gd_multi_init(int(n_dev), None, C.byref(h))
+        if rc != GD_OK:
+            raise GdietError("gd_multi_init(%d) failed: %s" % (n_dev, self.lib.gd_strerror(None).decode()))
+        self.h, self.n = h, int(n_dev)
+
+    def _check(self, rc, what):
+        if rc != GD_OK:
+            raise GdietError("%s failed (%d): %s" % (what, rc, self.lib.gd_multi_strerror(self.h).decode()))
+
+    def ctx(self, i):
+        """a non-owning Context view of device i's gd_ctx"""
+        c = Context.__new__(Context)
+        c.lib, c.h, c.device, c._owned = self.lib, C.c_void_p(self.lib.gd_multi_ctx(self.h, i)), i, False
+        return c
+
+    def index_bcast(self, index):
+        """index lives on ctx(0); the handle belongs to the Multi afterwards"""
+        self._check(self.lib.gd_multi_index_bcast(self.h, index.h, 1), "gd_multi_index_bcast")
+        index.h = None
+        return {k: self.lib.gd_multi_stat(self.h, k.encode()) for k in ("bcast_seconds", "bcast_bytes", "bcast_path")}
+
+    def index(self, i):
+        return Index(self.ctx(i), C.c_void_p(self.lib.gd_multi_index(self.h, i)), owned=False)
+
+    def map_batch(self, off, lens, buf, opt, cand_cap=None, cigar_cap=None):
+        """gd_multi_sr_map_batch / gd_multi_lr_map_batch (by the type of opt): same results as one device."""
+        fn = self.lib.gd_multi_lr_map_batch if isinstance(opt, gd_lr_opt_t) else self.lib.gd_multi_sr_map_batch
+        n = len(lens)
+        cand_off = np.zeros(n + 1, np.int64)
+        cand_cap = cand_cap or 2 * n + 64
+        cigar_cap = cigar_cap or 16 * n + 1024
+        ncig = C.c_int64(0)
+        while True:
+            cand = np.zeros(cand_cap, SR_CAND_DTYPE)
+            cig = np.zeros(cigar_cap, np.uint32)
+            rc = fn(self.h, n, _ptr(off), _ptr(lens), _ptr(buf), C.byref(opt), _ptr(cand_off), _ptr(cand), cand_cap, _ptr(cig), cigar_cap,
+                    C.byref(ncig))
+            if rc == GD_ERR_CAPACITY:
+                cand_cap, cigar_cap = max(cand_cap, int(cand_off[n]) + 16), max(cigar_cap, int(ncig.value) + 16)
+                continue
+            self._check(rc, "gd_multi_map_batch")
+            return cand_off, cand[: int(cand_off[n])], cig[: int(ncig.value)]
+
+    def map_sam(self, names, off, lens, seq, qual, opt, post, seq_names, contigs):
+        """gd_multi_sr_map_sam / gd_multi_lr_map_sam: the SAM text of the batch (pieces joined in input order)."""
+        fn = self.lib.gd_multi_lr_map_sam if isinstance(opt, gd_lr_opt_t) else self.lib.gd_multi_sr_map_sam
+        bufs = [np.ascontiguousarray(c, np.uint8) for c in contigs]
+        rlen = np.array([len(b) for b in bufs], np.int32)
+        roff = np.zeros(len(bufs), np.int64)
+        roff[1:] = np.cumsum(rlen[:-1].astype(np.int64))
+        ref = np.concatenate(bufs) if len(bufs) > 1 else bufs[0]
+        parts, plen, npart = C.POINTER(C.c_void_p)(), C.POINTER(C.c_size_t)(), C.c_int(0)
+        n_arr, s_arr = _cstr_array(names), _cstr_array(seq_names)
+        self._check(fn(self.h, len(lens), C.cast(n_arr, C.c_void_p), _ptr(off), _ptr(lens), _ptr(seq), _ptr(qual), C.byref(opt), C.byref(post),
+                       len(bufs), C.cast(s_arr, C.c_void_p), _ptr(roff), _ptr(rlen), _ptr(ref), C.byref(parts), C.byref(plen), C.byref(npart)),
+                    "gd_multi_map_sam")
+        out = []
+        for i in range(npart.value):
+            out.append(C.string_at(parts[i], plen[i]))
+            self.lib.gd_free(parts[i])
+        self.lib.gd_free(C.cast(parts, C.c_void_p)), self.lib.gd_free(C.cast(plen, C.c_void_p))
+        return b"".join(out)
+
+    def close(self):
+        if self.h:
+            self.lib.gd_multi_destroy(self.h)
+            self.h = None
+
+
 class Index:
     """gd_index: the device-resident minimizer index (mm_idx_t of GDiet-ShortReads/minimap.h:86-96)."""
 
-    def __init__(self, ctx, h):
-        self.ctx, self.h = ctx, h
+    def __init__(self, ctx, h, owned=True):
+        self.ctx, self.h, self.owned = ctx, h, owned
 
     def stat(self, key):
         return int(self.ctx.lib.gd_index_stat(self.h, key.encode()))
@@ -676,7 +783,8 @@ class Index:
 
     def close(self):
         if getattr(self, "h", None):
-            self.ctx.lib.gd_index_destroy(self.h)
+            if getattr(self, "owned", True):
+                self.ctx.lib.gd_index_destroy(self.h)
             self.h = None
 
     def __del__(self):

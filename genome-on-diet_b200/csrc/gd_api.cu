@@ -105,6 +105,21 @@ extern "C" void gd_destroy(gd_ctx *ctx)
 	delete ctx;
 }
 
+// page-locked host memory for a host's read / reference staging buffers (uploads from it run at PCIe speed and overlap)
+extern "C" void *gd_pinned_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void gd_pinned_free(void *p)
+{
+	if (p) cudaFreeHost(p);
+}
+
 extern "C" const char *gd_strerror(const gd_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
 
 extern "C" int gd_set_option(gd_ctx *ctx, const char *key, long value)

@@ -35,6 +35,7 @@ using namespace gd;
 #define SR_FLT 0x80000000u // seed filtered (mm_seed_mz_flt / mm_seed_select / max_occ)
 #define SR_WARPS 4         // warps per block of the per-read kernels
 #define SR_MAX_LOC 32
+#define SR_ABORTED (-1000) // internal: this lane only gave up because the other lane of the call failed
 
 struct SrParams {
 	int32_t W, JW, crop, k, frag_mode;
@@ -1021,7 +1022,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	}
 	clk.mark("vote");
 	if (nc == 0) {
-		if (!ord.claim(slice_index, 0, 0, cand_base, cig_base)) return GD_ERR_CUDA;
+		if (!ord.claim(slice_index, 0, 0, cand_base, cig_base)) return SR_ABORTED;
 		claim.done = true;
 		for (int i = 0; i <= n; ++i) cand_off[i] = cand_base;
 		return GD_OK;
@@ -1085,7 +1086,7 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
 	const int64_t ncig = h_word[0];
 	clk.mark("scores");
-	if (!ord.claim(slice_index, nc, ncig, cand_base, cig_base)) return GD_ERR_CUDA;
+	if (!ord.claim(slice_index, nc, ncig, cand_base, cig_base)) return SR_ABORTED;
 	claim.done = true;
 	for (int i = 0; i <= n; ++i) cand_off[i] = h_coff[i] + cand_base; // (the shared boundary entry gets the same value from both neighbours)
 	const bool fits = cand_base + nc <= cand_cap && cig_base + ncig <= cigar_cap && cand && cigar;
@@ -1134,10 +1135,13 @@ static int run_slices(gd_ctx *ctx, const gd_index *idx, const std::vector<std::p
 		std::thread helper(lane, 1);
 		lane(0);
 		helper.join();
-		if (rcs[1] && ctx->err.empty()) ctx->err = ctx->peer->err;
 	} else lane(0);
 	*n_cand = ord.cand_base, *n_cig = ord.cig_base;
-	return rcs[0] ? rcs[0] : rcs[1];
+	// the code (and message) of the lane that actually failed, not of the one that merely bailed out after it
+	const int L = (rcs[0] && rcs[0] != SR_ABORTED) ? 0 : (rcs[1] && rcs[1] != SR_ABORTED) ? 1 : -1;
+	if (L == 1) ctx->err = ctx->peer->err;
+	if (L < 0) return (rcs[0] || rcs[1]) ? GD_ERR_CUDA : GD_OK;
+	return rcs[L];
 }
 
 extern "C" int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,

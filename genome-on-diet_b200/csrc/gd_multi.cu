@@ -1,0 +1,415 @@
+// gd_multi.cu -- several B200s of one box driven from ONE host process (the C host of INTEGRATION.md level 2).
+//
+// What the reference does with kt_for over host cores (GDiet-ShortReads/map.c:1045-1092,1206; order restored by
+// kt_pipeline, kthread.c:101-115), this does over GPUs:
+//   * one gd_ctx per device (gd_multi_init);
+//   * the index is built (or loaded) ONCE on the first device and broadcast into replicas on the others
+//     (gd_multi_index_bcast): NCCL's ncclBroadcast over NVLink when libnccl.so.2 can be loaded at run time (it is
+//     dlopen'ed, so the library has no link-time dependency and shares the copy a host such as PyTorch already
+//     loaded), else direct peer copies (cudaMemcpyPeerAsync, also NVLink);
+//   * a mini-batch of reads is cut into contiguous shards, one per device, every shard is mapped by its own host
+//     thread on its own device, and the results are handed back in INPUT ORDER -- either merged into the caller's
+//     arrays (gd_multi_sr_map_batch / gd_multi_lr_map_batch) or, with the host stage included, as the SAM text
+//     pieces of the shards in order (gd_multi_sr_map_sam / gd_multi_lr_map_sam).
+// There is no data-path collective besides the one broadcast: reads are independent.
+#include "gd_ctx.h"
+#include <dlfcn.h>
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+#include <string.h>
+
+// the few NCCL declarations used (nccl.h, NCCL 2.x ABI) -- resolved with dlsym
+typedef struct ncclComm *gd_ncclComm_t;
+typedef int (*nccl_comm_init_all_t)(gd_ncclComm_t *, int, const int *);
+typedef int (*nccl_group_t)(void);
+typedef int (*nccl_bcast_t)(const void *, void *, size_t, int /*ncclDataType_t*/, int, gd_ncclComm_t, cudaStream_t);
+typedef int (*nccl_comm_destroy_t)(gd_ncclComm_t);
+typedef const char *(*nccl_errstr_t)(int);
+
+struct gd_multi {
+	std::vector<gd_ctx *> ctx;
+	std::vector<gd_index *> idx; // idx[0] is the caller's (not owned unless own_root)
+	bool own_root = false;
+	std::string err;
+	// NCCL (optional)
+	void *nccl_lib = nullptr;
+	std::vector<gd_ncclComm_t> comms;
+	nccl_comm_init_all_t p_init_all = nullptr;
+	nccl_group_t p_group_start = nullptr, p_group_end = nullptr;
+	nccl_bcast_t p_bcast = nullptr;
+	nccl_comm_destroy_t p_destroy = nullptr;
+	nccl_errstr_t p_errstr = nullptr;
+	// stats of the last broadcast
+	double bcast_s = 0;
+	int64_t bcast_bytes = 0;
+	int bcast_path = 0; // 1 = ncclBroadcast, 2 = peer copies
+	// per-shard host staging of the merged calls
+	struct Shard {
+		std::vector<int64_t> cand_off;
+		std::vector<gd_sr_cand_t> cand;
+		std::vector<uint32_t> cigar;
+		int64_t n_cand = 0, n_cig = 0;
+		int rc = GD_OK;
+	};
+	std::vector<Shard> sh;
+};
+
+extern "C" int gd_init(int device, gd_ctx **ctx);
+extern "C" void gd_destroy(gd_ctx *ctx);
+
+static bool multi_load_nccl(gd_multi *m)
+{
+	if (getenv("GDIET_NO_NCCL")) return false;
+	const char *names[] = {"libnccl.so.2", "libnccl.so"};
+	for (const char *nm : names)
+		if ((m->nccl_lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+	if (!m->nccl_lib) return false;
+	m->p_init_all = (nccl_comm_init_all_t)dlsym(m->nccl_lib, "ncclCommInitAll");
+	m->p_group_start = (nccl_group_t)dlsym(m->nccl_lib, "ncclGroupStart");
+	m->p_group_end = (nccl_group_t)dlsym(m->nccl_lib, "ncclGroupEnd");
+	m->p_bcast = (nccl_bcast_t)dlsym(m->nccl_lib, "ncclBroadcast");
+	m->p_destroy = (nccl_comm_destroy_t)dlsym(m->nccl_lib, "ncclCommDestroy");
+	m->p_errstr = (nccl_errstr_t)dlsym(m->nccl_lib, "ncclGetErrorString");
+	return m->p_init_all && m->p_group_start && m->p_group_end && m->p_bcast && m->p_destroy;
+}
+
+extern "C" int gd_multi_init(int n_dev, const int *devices, gd_multi **out)
+{
+	if (!out || n_dev < 1) return GD_ERR_ARG;
+	*out = nullptr;
+	gd_multi *m = new gd_multi();
+	for (int i = 0; i < n_dev; ++i) {
+		gd_ctx *c = nullptr;
+		const int rc = gd_init(devices ? devices[i] : i, &c);
+		if (rc != GD_OK) {
+			for (gd_ctx *x : m->ctx) gd_destroy(x);
+			delete m;
+			return rc;
+		}
+		m->ctx.push_back(c);
+	}
+	m->idx.assign(n_dev, nullptr);
+	m->sh.resize(n_dev);
+	*out = m;
+	return GD_OK;
+}
+
+extern "C" void gd_multi_destroy(gd_multi *m)
+{
+	if (!m) return;
+	for (size_t i = 0; i < m->idx.size(); ++i)
+		if (m->idx[i] && (i > 0 || m->own_root)) gd_index_destroy(m->idx[i]);
+	for (gd_ncclComm_t c : m->comms)
+		if (c && m->p_destroy) m->p_destroy(c);
+	for (gd_ctx *c : m->ctx) gd_destroy(c);
+	// the NCCL library stays loaded: other users of the process (e.g. PyTorch) may share it
+	delete m;
+}
+
+extern "C" int gd_multi_size(const gd_multi *m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" gd_ctx *gd_multi_ctx(gd_multi *m, int i) { return (m && i >= 0 && (size_t)i < m->ctx.size()) ? m->ctx[i] : nullptr; }
+extern "C" const gd_index *gd_multi_index(const gd_multi *m, int i) { return (m && i >= 0 && (size_t)i < m->idx.size()) ? m->idx[i] : nullptr; }
+extern "C" const char *gd_multi_strerror(const gd_multi *m) { return m ? m->err.c_str() : "gd_multi: null handle"; }
+
+extern "C" double gd_multi_stat(const gd_multi *m, const char *key)
+{
+	if (!m || !key) return -1;
+	if (!strcmp(key, "bcast_seconds")) return m->bcast_s;
+	if (!strcmp(key, "bcast_bytes")) return (double)m->bcast_bytes;
+	if (!strcmp(key, "bcast_path")) return m->bcast_path;
+	return -1;
+}
+
+// The index of the first device (built with gd_index_build* or loaded with gd_index_load_mmi on gd_multi_ctx(m, 0))
+// is replicated on every other device.  take_ownership: gd_multi_destroy frees root too.
+extern "C" int gd_multi_index_bcast(gd_multi *m, gd_index *root, int take_ownership)
+{
+	if (!m || !root) return GD_ERR_ARG;
+	const int n = (int)m->ctx.size();
+	for (int i = 1; i < n; ++i)
+		if (m->idx[i]) gd_index_destroy(m->idx[i]), m->idx[i] = nullptr;
+	if (m->idx[0] && m->own_root && m->idx[0] != root) gd_index_destroy(m->idx[0]);
+	m->idx[0] = root, m->own_root = take_ownership != 0;
+	m->bcast_s = 0, m->bcast_bytes = 0, m->bcast_path = 0;
+	if (n == 1) return GD_OK;
+	gd_index_meta_t meta;
+	int rc;
+	if ((rc = gd_index_meta(root, &meta))) return rc;
+	void *src[GD_INDEX_NBUF];
+	size_t bytes[GD_INDEX_NBUF];
+	gd_index_buffers(root, src, bytes);
+	std::vector<std::vector<void *>> dst(n, std::vector<void *>(GD_INDEX_NBUF, nullptr));
+	for (int i = 1; i < n; ++i) {
+		if ((rc = gd_index_alloc(m->ctx[i], &meta, &m->idx[i]))) {
+			m->err = std::string("gd_multi_index_bcast: ") + gd_strerror(m->ctx[i]);
+			return rc;
+		}
+		size_t b2[GD_INDEX_NBUF];
+		gd_index_buffers(m->idx[i], dst[i].data(), b2);
+	}
+	// the root's buffers are complete once its stream has drained
+	cudaSetDevice(m->ctx[0]->device);
+	cudaStreamSynchronize(m->ctx[0]->stream);
+	if (m->comms.empty() && !m->nccl_lib && multi_load_nccl(m)) {
+		std::vector<int> devs(n);
+		for (int i = 0; i < n; ++i) devs[i] = m->ctx[i]->device;
+		m->comms.assign(n, nullptr);
+		const int e = m->p_init_all(m->comms.data(), n, devs.data());
+		if (e != 0) {
+			fprintf(stderr, "[gdiet_cuda] ncclCommInitAll failed (%s): broadcasting the index with peer copies\n",
+			        m->p_errstr ? m->p_errstr(e) : "?");
+			m->comms.clear();
+		}
+	}
+	cudaEvent_t e0, e1;
+	cudaSetDevice(m->ctx[0]->device);
+	cudaEventCreate(&e0), cudaEventCreate(&e1);
+	cudaEventRecord(e0, m->ctx[0]->stream);
+	bool ok = true;
+	if (!m->comms.empty()) { // one grouped ncclBroadcast per buffer: every rank of the group is a device of this process
+		m->bcast_path = 1;
+		for (int b = 0; b < GD_INDEX_NBUF && ok; ++b) {
+			if (!bytes[b]) continue;
+			m->p_group_start();
+			for (int i = 0; i < n; ++i) {
+				void *buf = i == 0 ? src[b] : dst[i][b];
+				const int e = m->p_bcast(buf, buf, bytes[b], /*ncclUint8*/ 1, 0, m->comms[i], m->ctx[i]->stream);
+				if (e != 0) ok = false, m->err = std::string("ncclBroadcast: ") + (m->p_errstr ? m->p_errstr(e) : "?");
+			}
+			const int e = m->p_group_end();
+			if (e != 0) ok = false, m->err = std::string("ncclGroupEnd: ") + (m->p_errstr ? m->p_errstr(e) : "?");
+			m->bcast_bytes += (int64_t)bytes[b];
+		}
+	} else { // peer copies, each on the receiver's stream
+		m->bcast_path = 2;
+		for (int i = 1; i < n; ++i) {
+			cudaSetDevice(m->ctx[i]->device);
+			for (int b = 0; b < GD_INDEX_NBUF; ++b)
+				if (bytes[b] && cudaMemcpyPeerAsync(dst[i][b], m->ctx[i]->device, src[b], m->ctx[0]->device, bytes[b], m->ctx[i]->stream) != cudaSuccess)
+					ok = false, m->err = "gd_multi_index_bcast: cudaMemcpyPeerAsync failed";
+		}
+		for (int b = 0; b < GD_INDEX_NBUF; ++b) m->bcast_bytes += (int64_t)bytes[b];
+	}
+	for (int i = 0; i < n; ++i) {
+		cudaSetDevice(m->ctx[i]->device);
+		if (cudaStreamSynchronize(m->ctx[i]->stream) != cudaSuccess) ok = false, m->err = "gd_multi_index_bcast: stream failed";
+	}
+	cudaSetDevice(m->ctx[0]->device);
+	cudaEventRecord(e1, m->ctx[0]->stream);
+	cudaEventSynchronize(e1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	m->bcast_s = ms * 1e-3;
+	cudaEventDestroy(e0), cudaEventDestroy(e1);
+	if (!ok) return GD_ERR_CUDA;
+	for (int i = 1; i < n; ++i)
+		if ((rc = gd_index_commit(m->ctx[i], m->idx[i]))) {
+			m->err = std::string("gd_multi_index_bcast: ") + gd_strerror(m->ctx[i]);
+			return rc;
+		}
+	return GD_OK;
+}
+
+// contiguous shards with (nearly) equal numbers of bases: shard j = reads [cut[j], cut[j+1])
+static std::vector<int> shard_cuts(int n, const int32_t *len, int parts)
+{
+	std::vector<int> cut(parts + 1, n);
+	int64_t total = 0;
+	for (int i = 0; i < n; ++i) total += len[i];
+	cut[0] = 0;
+	int64_t acc = 0;
+	int j = 1;
+	for (int i = 0; i < n && j < parts; ++i) {
+		acc += len[i];
+		while (j < parts && acc * parts >= total * j) cut[j++] = i + 1;
+	}
+	for (; j < parts; ++j) cut[j] = n;
+	return cut;
+}
+
+template <class OPT, class FN>
+static int multi_map(gd_multi *m, int n, const int64_t *off, const int32_t *len, const char *buf, const OPT *opt, FN map_fn,
+                     int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cigar)
+{
+	if (!m || n < 0 || !cand_off || !opt || (n > 0 && (!off || !len || !buf))) return GD_ERR_ARG;
+	const int G = (int)m->ctx.size();
+	for (int i = 0; i < G; ++i)
+		if (!m->idx[i]) {
+			m->err = "gd_multi: no index (gd_multi_index_bcast first)";
+			return GD_ERR_ARG;
+		}
+	const std::vector<int> cut = shard_cuts(n, len, G);
+	auto work = [&](int j) {
+		gd_multi::Shard &S = m->sh[j];
+		const int b = cut[j], cnt = cut[j + 1] - cut[j];
+		S.n_cand = S.n_cig = 0, S.rc = GD_OK;
+		S.cand_off.assign((size_t)cnt + 1, 0);
+		if (cnt == 0) return;
+		cudaSetDevice(m->ctx[j]->device);
+		if (S.cand.size() < (size_t)cnt * 2) S.cand.resize((size_t)cnt * 2);
+		if (S.cigar.size() < (size_t)cnt * 16) S.cigar.resize((size_t)cnt * 16);
+		for (int attempt = 0; attempt < 2; ++attempt) {
+			int64_t ncig = 0;
+			S.rc = map_fn(m->ctx[j], m->idx[j], cnt, off + b, len + b, buf, opt, S.cand_off.data(), S.cand.data(), (int64_t)S.cand.size(),
+			              S.cigar.data(), (int64_t)S.cigar.size(), &ncig);
+			S.n_cand = S.cand_off[cnt], S.n_cig = ncig;
+			if (S.rc != GD_ERR_CAPACITY) break;
+			S.cand.resize((size_t)S.n_cand + 16), S.cigar.resize((size_t)S.n_cig + 16);
+		}
+	};
+	std::vector<std::thread> th;
+	for (int j = 1; j < G; ++j) th.emplace_back(work, j);
+	work(0);
+	for (std::thread &t : th) t.join();
+	for (int j = 0; j < G; ++j)
+		if (m->sh[j].rc) {
+			m->err = std::string("gd_multi: device ") + std::to_string(m->ctx[j]->device) + ": " + gd_strerror(m->ctx[j]);
+			return m->sh[j].rc;
+		}
+	// input-order hand-back: shard j's records go behind those of shards 0..j-1 (offsets shifted), copied by G threads
+	std::vector<int64_t> cb(G + 1, 0), gb(G + 1, 0);
+	for (int j = 0; j < G; ++j) cb[j + 1] = cb[j] + m->sh[j].n_cand, gb[j + 1] = gb[j] + m->sh[j].n_cig;
+	if (n_cigar) *n_cigar = gb[G];
+	cand_off[n] = cb[G];
+	if (cb[G] > cand_cap || gb[G] > cigar_cap || (cb[G] && !cand) || (gb[G] && !cigar)) {
+		m->err = "gd_multi: output buffer too small";
+		return GD_ERR_CAPACITY;
+	}
+	if (gb[G] > 0x7fffffff) {
+		m->err = "gd_multi: CIGAR pool of one call exceeds 2^31 entries; map fewer reads per call";
+		return GD_ERR_ARG;
+	}
+	auto merge = [&](int j) {
+		const gd_multi::Shard &S = m->sh[j];
+		const int b = cut[j], cnt = cut[j + 1] - cut[j];
+		for (int i = 0; i < cnt; ++i) cand_off[b + i] = S.cand_off[i] + cb[j];
+		for (int64_t c = 0; c < S.n_cand; ++c) {
+			gd_sr_cand_t x = S.cand[(size_t)c];
+			x.cigar_off += (int32_t)gb[j];
+			cand[cb[j] + c] = x;
+		}
+		if (S.n_cig) memcpy(cigar + gb[j], S.cigar.data(), (size_t)S.n_cig * 4);
+	};
+	th.clear();
+	for (int j = 1; j < G; ++j) th.emplace_back(merge, j);
+	merge(0);
+	for (std::thread &t : th) t.join();
+	return GD_OK;
+}
+
+extern "C" int gd_multi_sr_map_batch(gd_multi *m, int n, const int64_t *off, const int32_t *len, const char *buf, const gd_sr_opt_t *opt,
+                                     int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap,
+                                     int64_t *n_cigar)
+{
+	return multi_map(m, n, off, len, buf, opt, gd_sr_map_batch, cand_off, cand, cand_cap, cigar, cigar_cap, n_cigar);
+}
+
+extern "C" int gd_multi_lr_map_batch(gd_multi *m, int n, const int64_t *off, const int32_t *len, const char *buf, const gd_lr_opt_t *opt,
+                                     int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap,
+                                     int64_t *n_cigar)
+{
+	return multi_map(m, n, off, len, buf, opt, gd_lr_map_batch, cand_off, cand, cand_cap, cigar, cigar_cap, n_cigar);
+}
+
+// Mapping + host stage per shard: the SAM text of the mini-batch as pieces in input order (free each piece and both
+// arrays with gd_free).  Every shard thread drives its device, then turns its candidates into SAM records with
+// post->n_threads / n_devices host threads -- no merge of the candidate arrays, no second pass over the text.
+template <class OPT, class FN>
+static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                         const char *qual, const OPT *opt, FN map_fn, bool lr, const gd_sr_post_opt_t *post, int n_seq,
+                         const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref, char ***parts,
+                         size_t **part_len, int *n_parts)
+{
+	if (!m || n < 0 || !opt || !post || !parts || !part_len || !n_parts) return GD_ERR_ARG;
+	const int G = (int)m->ctx.size();
+	for (int i = 0; i < G; ++i)
+		if (!m->idx[i]) {
+			m->err = "gd_multi: no index (gd_multi_index_bcast first)";
+			return GD_ERR_ARG;
+		}
+	*parts = nullptr, *part_len = nullptr, *n_parts = 0;
+	const std::vector<int> cut = shard_cuts(n, len, G);
+	std::vector<std::vector<std::pair<char *, size_t>>> out(G);
+	gd_sr_post_opt_t po = *post;
+	int total_threads = post->n_threads > 0 ? post->n_threads : (int)std::thread::hardware_concurrency();
+	po.n_threads = std::max(1, total_threads / G);
+	auto work = [&](int j) {
+		gd_multi::Shard &S = m->sh[j];
+		const int b = cut[j], cnt = cut[j + 1] - cut[j];
+		S.rc = GD_OK;
+		if (cnt == 0) return;
+		cudaSetDevice(m->ctx[j]->device);
+		S.cand_off.assign((size_t)cnt + 1, 0);
+		if (S.cand.size() < (size_t)cnt * 2) S.cand.resize((size_t)cnt * 2);
+		if (S.cigar.size() < (size_t)cnt * 16) S.cigar.resize((size_t)cnt * 16);
+		for (int attempt = 0; attempt < 2; ++attempt) {
+			int64_t ncig = 0;
+			S.rc = map_fn(m->ctx[j], m->idx[j], cnt, off + b, len + b, seq, opt, S.cand_off.data(), S.cand.data(), (int64_t)S.cand.size(),
+			              S.cigar.data(), (int64_t)S.cigar.size(), &ncig);
+			S.n_cand = S.cand_off[cnt], S.n_cig = ncig;
+			if (S.rc != GD_ERR_CAPACITY) break;
+			S.cand.resize((size_t)S.n_cand + 16), S.cigar.resize((size_t)S.n_cig + 16);
+		}
+		if (S.rc) return;
+		if (lr) {
+			char *txt = nullptr;
+			size_t tl = 0;
+			S.rc = gd_lr_sam_batch(cnt, names + b, off + b, len + b, seq, qual, S.cand_off.data(), S.cand.data(), S.cigar.data(), n_seq,
+			                       seq_names, ref_off, ref_len, ref, &po, &txt, &tl, nullptr, nullptr);
+			if (!S.rc) out[j].push_back({txt, tl});
+		} else {
+			char **pp = nullptr;
+			size_t *pl = nullptr;
+			int np = 0;
+			S.rc = gd_sr_sam_batch_parts(cnt, names + b, off + b, len + b, seq, qual, S.cand_off.data(), S.cand.data(), S.cigar.data(),
+			                             n_seq, seq_names, ref_off, ref_len, ref, &po, &pp, &pl, &np);
+			if (!S.rc) {
+				for (int k = 0; k < np; ++k) out[j].push_back({pp[k], pl[k]});
+				gd_free(pp), gd_free(pl);
+			}
+		}
+	};
+	std::vector<std::thread> th;
+	for (int j = 1; j < G; ++j) th.emplace_back(work, j);
+	work(0);
+	for (std::thread &t : th) t.join();
+	int rc = GD_OK;
+	for (int j = 0; j < G && !rc; ++j)
+		if (m->sh[j].rc) {
+			rc = m->sh[j].rc;
+			m->err = std::string("gd_multi: device ") + std::to_string(m->ctx[j]->device) + ": " + gd_strerror(m->ctx[j]);
+		}
+	size_t np = 0;
+	for (int j = 0; j < G; ++j) np += out[j].size();
+	if (rc) {
+		for (int j = 0; j < G; ++j)
+			for (auto &pr : out[j]) gd_free(pr.first);
+		return rc;
+	}
+	*parts = (char **)malloc((np + 1) * sizeof(char *)), *part_len = (size_t *)malloc((np + 1) * sizeof(size_t));
+	size_t k = 0;
+	for (int j = 0; j < G; ++j)
+		for (auto &pr : out[j]) (*parts)[k] = pr.first, (*part_len)[k] = pr.second, ++k;
+	*n_parts = (int)np;
+	return GD_OK;
+}
+
+extern "C" int gd_multi_sr_map_sam(gd_multi *m, int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                                   const char *qual, const gd_sr_opt_t *opt, const gd_sr_post_opt_t *post, int n_seq,
+                                   const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
+                                   char ***parts, size_t **part_len, int *n_parts)
+{
+	return multi_map_sam(m, n, names, off, len, seq, qual, opt, gd_sr_map_batch, false, post, n_seq, seq_names, ref_off, ref_len, ref, parts,
+	                     part_len, n_parts);
+}
+
+extern "C" int gd_multi_lr_map_sam(gd_multi *m, int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                                   const char *qual, const gd_lr_opt_t *opt, const gd_sr_post_opt_t *post, int n_seq,
+                                   const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
+                                   char ***parts, size_t **part_len, int *n_parts)
+{
+	return multi_map_sam(m, n, names, off, len, seq, qual, opt, gd_lr_map_batch, true, post, n_seq, seq_names, ref_off, ref_len, ref, parts,
+	                     part_len, n_parts);
+}

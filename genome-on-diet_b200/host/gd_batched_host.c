@@ -1,0 +1,237 @@
+/* gd_batched_host.c -- the batched host of INTEGRATION.md level 2: ONE file that, compiled next to the UNMODIFIED
+ * reference sources of either tree (GDiet-ShortReads or, with -DGD_HOST_LR, GDiet-LongReads) and linked against
+ * libgdiet_cuda.so, replaces the mapping pipeline of map.c:
+ *
+ *   mm_map_file_frag()    map.c:1301-1322 (LR/map.c:2185-2206)   -- this file provides the symbol; map.c is compiled
+ *                                                                    with -Dmm_map_file_frag=gdref_cpu_mm_map_file_frag
+ *   worker_pipeline()     map.c:1165-1281   step 0 read a mini-batch, step 1 map it, step 2 write it out
+ *   worker_for()          map.c:1045-1092   one mm_map_frag per read on -t host threads
+ *
+ * Here step 0 reads the mini-batch with the reference's own reader (mm_bseq_read3, bseq.c) and flattens it into one
+ * pinned buffer; step 1 hands the WHOLE mini-batch to the device path -- sketching, index lookups, voting, windows,
+ * ksw_extd2, CIGARs (gd_sr_map_batch / gd_lr_map_batch) -- and to the library's threaded restatement of the post-DP host
+ * phase (mm_update_extra ... mm_write_sam3), on every GPU named by GDIET_GPUS (gd_multi_*: contiguous read shards, one
+ * per device, SAM pieces handed back in input order); step 2 writes the pieces.  The three steps run under the
+ * reference's kt_pipeline (kthread.c:71-160), so reading batch i+1, mapping batch i and writing batch i-1 overlap
+ * exactly as in the reference, and the output order is the input order.
+ *
+ * Everything else is the reference's: option parsing, index reading (main.c, index.c, with mm_sketch resolved to the
+ * library's drop-in), the SAM header (format.c), FASTA/FASTQ parsing (bseq.c).  The device index is built from the
+ * sequences the reference's index holds (mm_idx_getseq), so an .mmi made with -d works as well.
+ *
+ * What the device path does not cover is refused with an error, never mapped differently: paired / multi-segment
+ * input, PAF output, --split-prefix, --cs / --MD / --eqx / -y, splice mode, and (long reads) --sort=radix|heap.
+ */
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "minimap.h"
+#include "mmpriv.h"
+#include "bseq.h"
+#include "kthread.h"
+#include "gdiet_cuda.h" /* after minimap.h: its guards skip the types the reference already defines */
+
+typedef struct {
+	const mm_mapopt_t *opt;
+	const mm_idx_t *mi;
+	mm_bseq_file_t *fp;
+	int n_threads, n_processed;
+	int64_t mini_batch_size;
+	gd_multi *gm;
+	/* contigs as ASCII (the host stage counts mismatches against them, align.c:259-318) */
+	int n_ref;
+	const char **ref_names;
+	int64_t *ref_off;
+	int32_t *ref_len;
+	char *ref;
+#ifdef GD_HOST_LR
+	gd_lr_opt_t mo;
+#else
+	gd_sr_opt_t mo;
+#endif
+	gd_sr_post_opt_t po;
+	double t_map, t_read, t_write;
+	int64_t n_reads, n_bases;
+} gdh_pipeline_t;
+
+typedef struct {
+	int n;
+	mm_bseq1_t *seq;
+	const char **names;
+	int64_t *off;
+	int32_t *len;
+	char *buf, *qual; /* flattened reads / qualities */
+	char **parts;
+	size_t *part_len;
+	int n_parts;
+} gdh_step_t;
+
+static void gdh_die(const char *what)
+{
+	fprintf(stderr, "[gdiet_cuda] ERROR: %s\n", what);
+	exit(1);
+}
+
+static void *gdh_worker(void *shared, int step, void *in)
+{
+	gdh_pipeline_t *p = (gdh_pipeline_t *)shared;
+	if (step == 0) { /* read a mini-batch (map.c:1168-1199) and flatten it */
+		const int with_qual = !!(p->opt->flag & MM_F_OUT_SAM) && !(p->opt->flag & MM_F_NO_QUAL);
+		double t0 = realtime();
+		gdh_step_t *s = (gdh_step_t *)calloc(1, sizeof(gdh_step_t));
+		int i;
+		int64_t tot = 0, o = 0;
+		s->seq = mm_bseq_read3(p->fp, p->mini_batch_size, with_qual, 0, 0, &s->n);
+		if (!s->seq) {
+			free(s);
+			return 0;
+		}
+		for (i = 0; i < s->n; ++i) s->seq[i].rid = p->n_processed++, tot += s->seq[i].l_seq;
+		s->names = (const char **)malloc(sizeof(char *) * s->n);
+		s->off = (int64_t *)malloc(sizeof(int64_t) * s->n), s->len = (int32_t *)malloc(sizeof(int32_t) * s->n);
+		s->buf = (char *)gd_pinned_alloc((size_t)tot + 16); /* pinned: the upload of step 1 runs at PCIe speed */
+		s->qual = with_qual ? (char *)malloc((size_t)tot + 16) : 0;
+		for (i = 0; i < s->n && s->qual; ++i)
+			if (!s->seq[i].qual) free(s->qual), s->qual = 0; /* FASTA input: no quality strings ('*' in SAM) */
+		for (i = 0; i < s->n; ++i) {
+			const mm_bseq1_t *t = &s->seq[i];
+			if (i > 0 && mm_qname_same(s->seq[i - 1].name, t->name))
+				gdh_die("paired / multi-segment reads are not covered by the batched device path (use the GDiet_cuda build)");
+			s->names[i] = t->name, s->off[i] = o, s->len[i] = t->l_seq;
+			memcpy(s->buf + o, t->seq, t->l_seq);
+			if (s->qual) memcpy(s->qual + o, t->qual, t->l_seq);
+			o += t->l_seq;
+		}
+		p->n_reads += s->n, p->n_bases += tot, p->t_read += realtime() - t0;
+		return s;
+	} else if (step == 1) { /* map + post-process the whole mini-batch on the GPUs (replaces kt_for(worker_for), map.c:1206) */
+		gdh_step_t *s = (gdh_step_t *)in;
+		double t0 = realtime();
+		int rc;
+#ifdef GD_HOST_LR
+		rc = gd_multi_lr_map_sam(p->gm, s->n, s->names, s->off, s->len, s->buf, s->qual, &p->mo, &p->po, p->n_ref, p->ref_names, p->ref_off,
+		                         p->ref_len, p->ref, &s->parts, &s->part_len, &s->n_parts);
+#else
+		rc = gd_multi_sr_map_sam(p->gm, s->n, s->names, s->off, s->len, s->buf, s->qual, &p->mo, &p->po, p->n_ref, p->ref_names, p->ref_off,
+		                         p->ref_len, p->ref, &s->parts, &s->part_len, &s->n_parts);
+#endif
+		if (rc != GD_OK) gdh_die(gd_multi_strerror(p->gm));
+		p->t_map += realtime() - t0;
+		return s;
+	} else if (step == 2) { /* write (map.c:1208-1256 + the frees of :1257-1278) */
+		gdh_step_t *s = (gdh_step_t *)in;
+		double t0 = realtime();
+		int i;
+		for (i = 0; i < s->n_parts; ++i) {
+			if (s->part_len[i]) mm_err_fwrite(s->parts[i], 1, s->part_len[i], stdout);
+			gd_free(s->parts[i]);
+		}
+		gd_free(s->parts), gd_free(s->part_len);
+		for (i = 0; i < s->n; ++i) {
+			free(s->seq[i].seq), free(s->seq[i].name);
+			if (s->seq[i].qual) free(s->seq[i].qual);
+			if (s->seq[i].comment) free(s->seq[i].comment);
+		}
+		free(s->seq), free(s->names), free(s->off), free(s->len), free(s->qual);
+		gd_pinned_free(s->buf);
+		p->t_write += realtime() - t0;
+		if (mm_verbose >= 3)
+			fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", __func__, realtime() - mm_realtime0,
+			        cputime() / (realtime() - mm_realtime0), s->n);
+		free(s);
+	}
+	return 0;
+}
+
+static void gdh_options(gdh_pipeline_t *p)
+{
+	const mm_mapopt_t *opt = p->opt;
+	memset(&p->mo, 0, sizeof(p->mo)), memset(&p->po, 0, sizeof(p->po));
+	if (opt->pattern_len < 1 || opt->pattern_len > 63) gdh_die("pattern length (-W) must be 1..63");
+	p->mo.W = opt->pattern_len, memcpy(p->mo.Z, opt->pattern, opt->pattern_len);
+	p->mo.max_seeds = opt->max_seeds, p->mo.frag_mode = !!(opt->flag & MM_F_FRAG_MODE), p->mo.max_frag_len = opt->max_frag_len;
+	p->mo.mid_occ = opt->mid_occ, p->mo.max_max_occ = opt->max_max_occ, p->mo.occ_dist = opt->occ_dist, p->mo.q_occ_frac = opt->q_occ_frac;
+	p->mo.for_only = !!(opt->flag & MM_F_FOR_ONLY), p->mo.rev_only = !!(opt->flag & MM_F_REV_ONLY);
+	p->mo.a = opt->a, p->mo.b = opt->b, p->mo.q = opt->q, p->mo.e = opt->e, p->mo.q2 = opt->q2, p->mo.e2 = opt->e2;
+	p->mo.zdrop = opt->zdrop, p->mo.end_bonus = opt->end_bonus;
+#ifdef GD_HOST_LR
+	p->mo.bw = opt->bw; /* LR/map.c:1374 */
+	p->mo.vt_dis = opt->vt_dis, p->mo.vt_nb_loc = opt->vt_nb_loc, p->mo.vt_cov = opt->vt_cov, p->mo.vt_df1 = opt->vt_df1;
+	p->mo.vt_df2 = opt->vt_df2, p->mo.vt_f = opt->vt_f, p->mo.max_max_gap = opt->max_max_gap, p->mo.max_min_gap = opt->max_min_gap;
+	if (opt->flag & (MM_F_RADIX_SORT | MM_F_HEAP_SORT)) gdh_die("--sort=radix|heap is not covered by the long-read device path (the presets use merge)");
+#else
+	p->mo.bw_frac = opt->bw_frac, p->mo.bw_min = (uint32_t)opt->bw_min, p->mo.bw_max = (uint32_t)opt->bw_max; /* per read, map.c:624-631 */
+	if (opt->bw_max <= 0) gdh_die("-r: bw_max must be positive");
+	p->mo.min_cnt = opt->min_cnt, p->mo.rec_threshold_frac = opt->rec_threshold_frac, p->mo.af_max_loc = opt->AF_max_loc;
+#endif
+	p->po.a = opt->a, p->po.b = opt->b, p->po.q = opt->q, p->po.e = opt->e, p->po.q2 = opt->q2, p->po.e2 = opt->e2;
+	p->po.min_dp_max = opt->min_dp_max, p->po.best_n = opt->best_n, p->po.no_print_2nd = !!(opt->flag & MM_F_NO_PRINT_2ND);
+	p->po.is_sr = !!(opt->flag & MM_F_SR), p->po.sam_hit_only = !!(opt->flag & MM_F_SAM_HIT_ONLY), p->po.softclip = !!(opt->flag & MM_F_SOFTCLIP);
+	p->po.n_threads = p->n_threads;
+}
+
+static void gdh_refuse_uncovered(const mm_mapopt_t *opt, int n_segs)
+{
+	if (n_segs != 1) gdh_die("paired / multi-file input is not covered by the batched device path (use the GDiet_cuda build)");
+	if (!(opt->flag & MM_F_OUT_SAM) || !(opt->flag & MM_F_CIGAR)) gdh_die("the batched device path writes SAM with CIGAR (-a); PAF output is not covered");
+	if (opt->split_prefix) gdh_die("--split-prefix is not covered by the batched device path");
+	if (opt->flag & (MM_F_OUT_CS | MM_F_OUT_MD | MM_F_EQX | MM_F_COPY_COMMENT | MM_F_SPLICE | MM_F_OUT_CS_LONG | MM_F_NO_DIAG | MM_F_NO_DUAL))
+		gdh_die("--cs / --MD / --eqx / -y / splice mode / -X are not covered by the batched device path");
+	if (opt->sdust_thres > 0) gdh_die("-T (sdust) is not covered by the batched device path");
+}
+
+int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_mapopt_t *opt, int n_threads)
+{
+	gdh_pipeline_t pl;
+	int i, n_gpus = 1, rc;
+	const char *env = getenv("GDIET_GPUS");
+	int64_t tot = 0;
+	double t0;
+	gd_index *gi = 0;
+	if (n_segs < 1) return -1;
+	gdh_refuse_uncovered(opt, n_segs);
+	memset(&pl, 0, sizeof(pl));
+	if ((pl.fp = mm_bseq_open(fn[0])) == 0) {
+		if (mm_verbose >= 1) fprintf(stderr, "ERROR: failed to open file '%s': %s\n", fn[0], strerror(errno));
+		return -1;
+	}
+	pl.opt = opt, pl.mi = idx, pl.n_threads = n_threads > 1 ? n_threads : 1, pl.mini_batch_size = opt->mini_batch_size;
+	gdh_options(&pl);
+	if (env && atoi(env) > 0) n_gpus = atoi(env);
+	if ((rc = gd_multi_init(n_gpus, 0, &pl.gm)) != GD_OK) gdh_die("no usable CUDA device (there is no CPU fallback in this build)");
+
+	/* the contigs the reference's index holds, as ASCII: the device index is built from them, and the host stage reads them */
+	t0 = realtime();
+	pl.n_ref = (int)idx->n_seq;
+	pl.ref_names = (const char **)malloc(sizeof(char *) * pl.n_ref);
+	pl.ref_off = (int64_t *)malloc(sizeof(int64_t) * pl.n_ref), pl.ref_len = (int32_t *)malloc(sizeof(int32_t) * pl.n_ref);
+	for (i = 0; i < pl.n_ref; ++i) pl.ref_names[i] = idx->seq[i].name, pl.ref_off[i] = tot, pl.ref_len[i] = (int32_t)idx->seq[i].len, tot += idx->seq[i].len;
+	pl.ref = (char *)gd_pinned_alloc((size_t)tot + 16);
+	if (idx->flag & MM_I_NO_SEQ) gdh_die("the index holds no sequences (built with --idx-no-seq)");
+	for (i = 0; i < pl.n_ref; ++i) { /* S is 4-bit packed, 8 bases per word (index.c:157-166) */
+		const uint64_t st = idx->seq[i].offset;
+		char *dst = pl.ref + pl.ref_off[i];
+		uint32_t j;
+		for (j = 0; j < idx->seq[i].len; ++j) dst[j] = "ACGTN"[(idx->S[(st + j) >> 3] >> (((st + j) & 7) << 2)) & 0xf];
+	}
+	if ((rc = gd_index_build(gd_multi_ctx(pl.gm, 0), pl.n_ref, pl.ref_off, pl.ref_len, pl.ref, idx->w, idx->k, opt->pattern, opt->pattern_len, &gi)) != GD_OK)
+		gdh_die(gd_strerror(gd_multi_ctx(pl.gm, 0)));
+	if ((rc = gd_multi_index_bcast(pl.gm, gi, 1)) != GD_OK) gdh_die(gd_multi_strerror(pl.gm));
+	if (mm_verbose >= 3)
+		fprintf(stderr, "[M::%s::%.3f*%.2f] device index on %d GPU(s) in %.3f s (broadcast %.0f MB in %.3f s, %s)\n", __func__,
+		        realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), n_gpus, realtime() - t0, gd_multi_stat(pl.gm, "bcast_bytes") / 1e6,
+		        gd_multi_stat(pl.gm, "bcast_seconds"), gd_multi_stat(pl.gm, "bcast_path") == 1 ? "ncclBroadcast" : n_gpus > 1 ? "peer copies" : "single GPU");
+
+	t0 = realtime();
+	kt_pipeline(n_threads == 1 ? 1 : 3, gdh_worker, &pl, 3); /* reader, mapper and writer overlap (map.c:1316-1317) */
+	if (mm_verbose >= 3)
+		fprintf(stderr, "[M::%s] %ld reads, %ld bases in %.3f s: %.0f reads/s (step seconds: read %.3f, map %.3f, write %.3f)\n", __func__,
+		        (long)pl.n_reads, (long)pl.n_bases, realtime() - t0, pl.n_reads / (realtime() - t0 + 1e-9), pl.t_read, pl.t_map, pl.t_write);
+
+	gd_multi_destroy(pl.gm);
+	gd_pinned_free(pl.ref);
+	free(pl.ref_names), free(pl.ref_off), free(pl.ref_len);
+	mm_bseq_close(pl.fp);
+	return 0;
+}

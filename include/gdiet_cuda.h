@@ -100,6 +100,8 @@ const char *gd_strerror(const gd_ctx *ctx); /* ctx may be NULL: last init error 
 int gd_set_option(gd_ctx *ctx, const char *key, long value);
 long gd_get_stat(const gd_ctx *ctx, const char *key);
 void *gd_stream(gd_ctx *ctx); /* the cudaStream_t all work of this context is issued on */
+void *gd_pinned_alloc(size_t bytes); /* page-locked host memory for read / reference staging (NULL on failure) */
+void gd_pinned_free(void *p);
 long gd_thread_ctx_pool_size(int device); /* contexts of exited drop-in threads parked for reuse on `device` */
 
 /* ------------------------------------------------------------------------------------------ */
@@ -372,6 +374,44 @@ int gd_mmi_write(const char *path, int w, int k, int bucket_bits, int flag, int 
  * becomes a device-resident index; gd_index_seq_name returns the contig names stored in the file ("" for built indexes). */
 int gd_index_load_mmi(gd_ctx *ctx, const char *path, gd_index **out);
 const char *gd_index_seq_name(const gd_index *idx, int i);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (5) several GPUs of one box from one host process                     */
+/* ------------------------------------------------------------------------------------------ */
+/* What kt_for does over host cores (GDiet-ShortReads/map.c:1045-1092,1206) with the order kt_pipeline restores
+ * (kthread.c:101-115): one context per device, the index built or loaded ONCE on the first device and broadcast to the
+ * others, every mini-batch cut into contiguous read shards (one per device, equal bases), each shard mapped by its own
+ * host thread, results handed back in input order.  No data-path collective besides the broadcast. */
+typedef struct gd_multi gd_multi;
+int gd_multi_init(int n_dev, const int *devices /* NULL: 0..n_dev-1 */, gd_multi **out);
+void gd_multi_destroy(gd_multi *m);
+int gd_multi_size(const gd_multi *m);
+gd_ctx *gd_multi_ctx(gd_multi *m, int i);              /* context of device i (build / load the index on i = 0) */
+const gd_index *gd_multi_index(const gd_multi *m, int i);
+const char *gd_multi_strerror(const gd_multi *m);
+/* root lives on gd_multi_ctx(m, 0); replicas are created on every other device and filled with ncclBroadcast over NVLink
+ * (libnccl.so.2 is dlopen'ed at run time -- no link-time dependency; GDIET_NO_NCCL=1 or a missing library selects direct
+ * peer copies, cudaMemcpyPeerAsync).  take_ownership != 0: gd_multi_destroy frees root as well.
+ * gd_multi_stat: "bcast_seconds", "bcast_bytes", "bcast_path" (1 = NCCL, 2 = peer copies) of the last broadcast. */
+int gd_multi_index_bcast(gd_multi *m, gd_index *root, int take_ownership);
+double gd_multi_stat(const gd_multi *m, const char *key);
+/* gd_sr_map_batch / gd_lr_map_batch over all devices: same arguments, same results (input order, dense arrays) */
+int gd_multi_sr_map_batch(gd_multi *m, int n, const int64_t *off, const int32_t *len, const char *buf, const gd_sr_opt_t *opt,
+                          int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap,
+                          int64_t *n_cigar);
+int gd_multi_lr_map_batch(gd_multi *m, int n, const int64_t *off, const int32_t *len, const char *buf, const gd_lr_opt_t *opt,
+                          int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap,
+                          int64_t *n_cigar);
+/* mapping + the host stage of (4) per shard: the SAM records of the mini-batch as text pieces in input order (what
+ * pipeline step 2, map.c:1208-1256, writes out); free every piece and both arrays with gd_free */
+int gd_multi_sr_map_sam(gd_multi *m, int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                        const char *qual, const gd_sr_opt_t *opt, const gd_sr_post_opt_t *post, int n_seq,
+                        const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
+                        char ***parts, size_t **part_len, int *n_parts);
+int gd_multi_lr_map_sam(gd_multi *m, int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
+                        const char *qual, const gd_lr_opt_t *opt, const gd_sr_post_opt_t *post, int n_seq,
+                        const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
+                        char ***parts, size_t **part_len, int *n_parts);
 
 #ifdef __cplusplus
 }

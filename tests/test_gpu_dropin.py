@@ -49,3 +49,77 @@ def test_reference_program_on_the_drop_in_symbols_long_reads():
     want = run(maplib.REF_LR, flags, fa, fq, os.path.join(tmp, "cpu.sam"), 2)
     got = run(CUDA_LR, flags, fa, fq, os.path.join(tmp, "gpu.sam"), 2)
     assert len(got) == len(want) and got == want
+
+
+# ---- Level 2: the batched host (genome-on-diet_b200/host/gd_batched_host.c) in place of map.c's pipeline ----------------
+BATCHED_SR = os.path.join(ORACLE_DIR, "_ref", "GDiet_cuda_batched_sr")
+BATCHED_LR = os.path.join(ORACLE_DIR, "_ref", "GDiet_cuda_batched_lr")
+
+
+def n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def run_env(prog, flags, fa, fq, out, threads, env):
+    p = subprocess.run([prog, "-t", str(threads)] + flags + ["-o", out, fa, fq], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, **env))
+    assert p.returncode == 0, p.stderr[-2000:]
+    return [l for l in open(out).read().splitlines() if not l.startswith("@PG")], p.stderr
+
+
+@pytest.mark.skipif(not (os.path.exists(BATCHED_SR) and maplib.have_ref_program() and cpu_has_avx512()),
+                    reason="needs oracle/_ref/GDiet_cuda_batched_sr + GDiet_avx_sr (built where /root/reference exists)")
+@pytest.mark.parametrize("flags,read_len,ragged", [
+    (["-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200"], 150, False),             # BASELINE config 1
+    (["-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.25,20,60", "-n", "0.2,0.1"], 300, True),  # band per read
+])
+def test_batched_host_short_reads_sam_identical(flags, read_len, ragged):
+    """FASTQ in, SAM file out through the batched C host (reader -> gd_multi_sr_map_sam -> writer under kt_pipeline), with a
+    mini-batch size (-K) that cuts the input into several batches: byte-identical to GDiet_avx"""
+    import numpy as np
+    contigs, reads = maplib.make_dataset(seed=61, n_reads=6000, read_len=read_len)
+    if ragged:
+        rng = np.random.default_rng(3)
+        reads = [r[:int(rng.integers(60, read_len + 1))].copy() for r in reads]
+    tmp = tempfile.mkdtemp(prefix="gdbatch_")
+    fa, fq = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq")
+    maplib.write_fasta(fa, contigs)
+    maplib.write_fastq(fq, reads)
+    want = run(maplib.REF_SR, flags, fa, fq, os.path.join(tmp, "cpu.sam"), 2)
+    got, _ = run_env(BATCHED_SR, flags + ["-K", "200k"], fa, fq, os.path.join(tmp, "gpu.sam"), 3, {"GDIET_GPUS": "1"})
+    assert len(got) == len(want) and got == want
+    if n_gpus() >= 2:  # read shards on two devices, index broadcast, SAM pieces in input order
+        for env in ({"GDIET_GPUS": "2"}, {"GDIET_GPUS": "2", "GDIET_NO_NCCL": "1"}):
+            got2, err = run_env(BATCHED_SR, flags + ["-K", "200k"], fa, fq, os.path.join(tmp, "gpu2.sam"), 4, env)
+            assert got2 == want, err[-1000:]
+
+
+@pytest.mark.skipif(not (os.path.exists(BATCHED_LR) and os.path.exists(maplib.REF_LR) and cpu_has_avx512()),
+                    reason="needs oracle/_ref/GDiet_cuda_batched_lr + GDiet_avx_lr")
+def test_batched_host_long_reads_sam_identical():
+    """BASELINE config 3 shape (HiFi-like reads, -ax map-hifi -r 1000) through the batched C host of the long-read tree"""
+    contigs, reads = maplib.make_long_dataset(seed=62, read_len=9000, n_reads=60)
+    tmp = tempfile.mkdtemp(prefix="gdbatch_")
+    fa, fq = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq")
+    maplib.write_fasta(fa, contigs)
+    maplib.write_fastq(fq, reads)
+    flags = ["-ax", "map-hifi", "-Z", "10", "-W", "2", "-k", "19", "-w", "19", "-r", "1000"]
+    want = run(maplib.REF_LR, flags, fa, fq, os.path.join(tmp, "cpu.sam"), 2)
+    got, _ = run_env(BATCHED_LR, flags + ["-K", "200k"], fa, fq, os.path.join(tmp, "gpu.sam"), 3, {"GDIET_GPUS": "1"})
+    assert len(got) == len(want) and got == want
+    if n_gpus() >= 2:
+        got2, err = run_env(BATCHED_LR, flags + ["-K", "200k"], fa, fq, os.path.join(tmp, "gpu2.sam"), 4, {"GDIET_GPUS": "2"})
+        assert got2 == want, err[-1000:]
+
+
+def test_batched_host_refuses_what_the_device_path_does_not_cover():
+    if not os.path.exists(BATCHED_SR):
+        pytest.skip("needs oracle/_ref/GDiet_cuda_batched_sr")
+    contigs, reads = maplib.make_dataset(seed=63, n_reads=20)
+    tmp = tempfile.mkdtemp(prefix="gdbatch_")
+    fa, fq = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq")
+    maplib.write_fasta(fa, contigs)
+    maplib.write_fastq(fq, reads)
+    p = subprocess.run([BATCHED_SR, "-x", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", fa, fq], capture_output=True, text=True, timeout=300)
+    assert p.returncode != 0 and "PAF output is not covered" in p.stderr   # no -a: an error, not a different answer

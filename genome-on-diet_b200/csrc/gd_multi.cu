@@ -62,6 +62,9 @@ extern "C" void gd_destroy(gd_ctx *ctx);
 static bool multi_load_nccl(gd_multi *m)
 {
 	if (getenv("GDIET_NO_NCCL")) return false;
+	// NCCL writes its version / debug lines to stdout, which is where the host program writes the SAM records (-o reopens
+	// stdout, main.c): send them to stderr unless the user chose a file
+	setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
 	const char *names[] = {"libnccl.so.2", "libnccl.so"};
 	for (const char *nm : names)
 		if ((m->nccl_lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;

@@ -14,6 +14,7 @@
 // There is no data-path collective besides the one broadcast: reads are independent.
 #include "gd_ctx.h"
 #include <dlfcn.h>
+#include <unistd.h>
 #include <algorithm>
 #include <string>
 #include <thread>
@@ -62,9 +63,6 @@ extern "C" void gd_destroy(gd_ctx *ctx);
 static bool multi_load_nccl(gd_multi *m)
 {
 	if (getenv("GDIET_NO_NCCL")) return false;
-	// NCCL writes its version / debug lines to stdout, which is where the host program writes the SAM records (-o reopens
-	// stdout, main.c): send them to stderr unless the user chose a file
-	setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
 	const char *names[] = {"libnccl.so.2", "libnccl.so"};
 	for (const char *nm : names)
 		if ((m->nccl_lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
@@ -155,6 +153,11 @@ extern "C" int gd_multi_index_bcast(gd_multi *m, gd_index *root, int take_owners
 	// the root's buffers are complete once its stream has drained
 	cudaSetDevice(m->ctx[0]->device);
 	cudaStreamSynchronize(m->ctx[0]->stream);
+	// NCCL writes its version / debug lines to stdout, which is where the host program writes its SAM records (-o reopens
+	// stdout, main.c): while NCCL initialises and broadcasts, file descriptor 1 points at stderr
+	fflush(stdout);
+	const int saved_stdout = dup(1);
+	if (saved_stdout >= 0) dup2(2, 1);
 	if (m->comms.empty() && !m->nccl_lib && multi_load_nccl(m)) {
 		std::vector<int> devs(n);
 		for (int i = 0; i < n; ++i) devs[i] = m->ctx[i]->device;
@@ -199,6 +202,8 @@ extern "C" int gd_multi_index_bcast(gd_multi *m, gd_index *root, int take_owners
 		cudaSetDevice(m->ctx[i]->device);
 		if (cudaStreamSynchronize(m->ctx[i]->stream) != cudaSuccess) ok = false, m->err = "gd_multi_index_bcast: stream failed";
 	}
+	fflush(stdout);
+	if (saved_stdout >= 0) dup2(saved_stdout, 1), close(saved_stdout);
 	cudaSetDevice(m->ctx[0]->device);
 	cudaEventRecord(e1, m->ctx[0]->stream);
 	cudaEventSynchronize(e1);

@@ -143,10 +143,12 @@ def reference_arm(args, rank, world):
     n = int(min(args.pairs, max(4096, 4096 * 3.0 / max(dt, 1e-3))))
     P = make_pairs(n, seed=3)
     times, cells = [], 0
+    from oraclelib import EXTZ_DTYPE
+    pre_out = (np.zeros(n, EXTZ_DTYPE), np.zeros(n * (QLEN + TLEN), np.uint32))  # allocated (and touched) outside the timed steps
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         ez, _ = R.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], mat, sc["q"], sc["e"], sc["q2"],
-                                  sc["e2"], BAND, sc["zdrop"], sc["end_bonus"], args.flag, cores, cigar_stride=QLEN + TLEN)
+                                  sc["e2"], BAND, sc["zdrop"], sc["end_bonus"], args.flag, cores, cigar_stride=QLEN + TLEN, out=pre_out)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
@@ -278,12 +280,24 @@ def ours(args, rank, world, local_rank):
     h2d = int(sum(P[k].nbytes for k in ("qlen", "qoff", "qbuf", "tlen", "toff", "tbuf")))
     d2h = int(n * 64 + (n + 1) * 8 + int(coff_h[n]) * 4)
     assert np.array_equal(ez_h["score"], ez["score"]), "device-resident and host-buffer arms disagree"
+    cig_h = out["cigar"]
 
     # ---- max over ranks ------------------------------------------------------------------------
     # time = MAX over ranks, work = SUM over ranks (genome-on-diet_b200/shard.py; no data-path collective)
     from gdiet_b200 import shard
     (dev_ms, e2e_ms), (tot_cells, launches, h2d, d2h) = shard.reduce_timing([dev_ms, e2e_ms], [cells_step, launches, h2d, d2h],
                                                                               device=dev if dist else "cpu")
+    # ---- the mapping path, STRONG-scaled over the ranks (every rank takes part; see tools/map_strong_bench.py) ------------
+    ms_out = None
+    if not args.no_map_strong:
+        del d, d_ez, d_cig
+        torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import map_strong_bench
+            ms_out = map_strong_bench.run(ctx, rank, world, dist, dev, args.map_reads, args.map_genome_bp, cores=host_threads())
+        except Exception as e:  # (stage failures are agreed on by all ranks inside run(): nobody is left waiting)
+            ms_out = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -329,18 +343,23 @@ def ours(args, rank, world, local_rank):
     roof["hbm"]["frac"] = roof["hbm"]["achieved_gbs"] / roof["hbm"]["peak_gbs"]
 
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ------------------------------------------
-    cpu = None
+    cpu = parity = None
     if world == 1 and not args.no_cpu:
         try:
-            cpu = cpu_baseline_sample(args, P)
+            cpu, parity = cpu_baseline_sample(args, P, ez_h, coff_h, cig_h)
         except Exception as e:  # the checker being absent must not hide the GPU number
             cpu = {"value": None, "unit": "GCUPS", "cores": host_threads(), "kind": "unavailable", "sample": str(e)}
 
+    zd = None
+    try:
+        zd = zdrop_subset(ctx, args)
+    except Exception as e:
+        zd = {"error": str(e)}
     sk = None
     if not args.no_sketch:
         try:
             sk = sketch_extra(ctx, stream, dev, peaks)
-            if world == 1 and not args.no_cpu:
+            if not args.no_cpu:  # (rank 0, at every N)
                 try:
                     sk["cpu_baseline"] = sketch_cpu_baseline()
                 except Exception as e:
@@ -368,9 +387,10 @@ def ours(args, rank, world, local_rank):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
             "data": "synthetic", "config": workload_config(args, n),
             "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
             "extra": {"ksw_group_lanes": ctx.stat("ksw_group"), "ksw_ring_columns": ctx.stat("ksw_ring"), "chunks_per_step": ctx.stat("ksw_chunks"),
-                      "zdropped_frac": float((ez["zdropped"] != 0).mean()), "cells_per_step": tot_cells, "sketch": sk, "sr_map": srm, "lr_map": lrm}}
+                      "zdropped_frac": float((ez["zdropped"] != 0).mean()), "cells_per_step": tot_cells, "zdrop_subset": zd, "sketch": sk,
+                      "sr_map": srm, "lr_map": lrm, "map_strong": ms_out}}
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
@@ -396,8 +416,24 @@ def sketch_cpu_baseline():
         R.mm_sketch_batch(off, lens, g, 11, 21, "10", cores)
         tot += time.perf_counter() - t0
         passes += 1
-    return {"value": passes * L * nc / tot / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "reference",
-            "sample": "%d passes of mm_sketch (%s build) over %d contigs of %d bp on %d threads, %.1f s" % (passes, variant, nc, L, cores, tot)}
+    out = {"value": passes * L * nc / tot / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "reference",
+           "sample": "%d passes of mm_sketch (%s build) over %d contigs of %d bp on %d threads, %.1f s" % (passes, variant, nc, L, cores, tot)}
+    # ... and on 150 bp reads (one mm_sketch call per read, all threads)
+    rl = 150
+    nr = min(2_000_000, len(g) // rl)
+    r_off = np.arange(nr, dtype=np.int64) * rl
+    r_len = np.full(nr, rl, np.int32)
+    R.mm_sketch_batch(r_off, r_len, g, 11, 21, "10", cores)
+    tot, passes = 0.0, 0
+    while tot < 3.0 and passes < 64:
+        t0 = time.perf_counter()
+        R.mm_sketch_batch(r_off, r_len, g, 11, 21, "10", cores)
+        tot += time.perf_counter() - t0
+        passes += 1
+    out["reads"] = {"value": passes * nr * rl / tot / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "reference",
+                    "sample": "%d passes of ONE mm_sketch call per 150 bp read over %d reads on %d threads (mm_sketch2 + mm_sketch3 make ~2.1 such passes per read)" % (
+                        passes, nr, cores)}
+    return out
 
 
 def sketch_extra(ctx, stream, dev, peaks):
@@ -431,15 +467,77 @@ def sketch_extra(ctx, stream, dev, peaks):
     nmin, bases = int(d_oo[-1].item()), nc * L
     algo = bases + 16 * nmin
     hbm = (peaks or {}).get("hbm_gbs", 6650.0)
-    return {"workload": "mm_sketch of %d x %d bp synthetic contigs, -Z 10 -W 2 -k 21 -w 11, device resident" % (nc, L),
-            "gbases_per_s_call": bases / best_dt / 1e9, "gbases_per_s_kernel": bases / (best_us * 1e-6) / 1e9, "minimizers": nmin,
-            "roofline": {"bound": "hbm", "achieved": algo / (best_us * 1e-6) / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": algo / (best_us * 1e-6) / 1e9 / hbm,
-                         "note": "integer work (~100 ops per sparsified base) keeps this kernel ALU/latency bound, far below the HBM roofline"}}
+    out = {"workload": "mm_sketch of %d x %d bp synthetic contigs, -Z 10 -W 2 -k 21 -w 11, device resident" % (nc, L),
+           "gbases_per_s_call": bases / best_dt / 1e9, "gbases_per_s_kernel": bases / (best_us * 1e-6) / 1e9, "minimizers": nmin,
+           "roofline": {"bound": "hbm", "achieved": algo / (best_us * 1e-6) / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": algo / (best_us * 1e-6) / 1e9 / hbm,
+                        "note": "integer work (~100 ops per sparsified base) keeps this kernel ALU/latency bound, far below the HBM roofline"}}
+    # ---- end to end through the host-buffer calls (pinned host ASCII in, minimizers out on the host) ----------------------
+    import ctypes as C
+    import gdiet_b200 as gd
+    lib = ctx.lib
+    h_seq = torch.empty(nc * L, dtype=torch.uint8).pin_memory()
+    h_seq.copy_(seq)
+    del seq, d_out
+    h_off = np.arange(nc, dtype=np.int64) * L
+    h_len = np.full(nc, L, np.int32)
+    h_rid = np.arange(nc, dtype=np.uint32)
+    h_oo = np.zeros(nc + 1, np.int64)
+    h_out = torch.zeros(cap * 2, dtype=torch.int64).pin_memory().numpy()
+    best = None
+    for it in range(4):
+        t0 = time.perf_counter()
+        rc = lib.gd_sketch_ref_batch(ctx.h, nc, gd._ptr(h_off), gd._ptr(h_len), gd._ptr(h_rid), gd._ptr(h_seq.numpy()), 11, 21, b"10", 2,
+                                     gd._ptr(h_oo), gd._ptr(h_out), cap)
+        dt = time.perf_counter() - t0
+        ctx._check(rc, "gd_sketch_ref_batch")
+        if it and (best is None or dt < best):
+            best = dt
+    out["e2e"] = {"value": bases / best / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": int(bases + nc * 16), "d2h_bytes_per_step": int(h_oo[nc]) * 16,
+                  "call": "gd_sketch_ref_batch: pinned host ASCII -> mm128_t records on the host", "identical_to_device_arm": int(h_oo[nc]) == nmin}
+    del h_seq, h_out
+    # ---- read sketching (mm_sketch2 + mm_sketch3 of every shift, the per-read calls of map.c:74-99) for 2 M reads of 150 bp
+    nr, rl = 2_000_000, 150
+    g = torch.randint(0, 4, (nr * rl,), dtype=torch.uint8, device=dev)
+    h_reads = torch.empty(nr * rl, dtype=torch.uint8).pin_memory()
+    h_reads.copy_(torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)[g.long()])
+    del g
+    r_off = np.arange(nr, dtype=np.int64) * rl
+    r_len = np.full(nr, rl, np.int32)
+    W = 2
+    s2_counts = torch.zeros(nr * W, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    s3_ret = torch.zeros(nr * W, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    s2_off = torch.zeros(nr + 1, dtype=torch.int64).pin_memory().numpy()
+    s3_off = torch.zeros(nr * W + 1, dtype=torch.int64).pin_memory().numpy()
+    rcap = nr * 40
+    s2 = torch.zeros(rcap * 2, dtype=torch.int64).pin_memory().numpy()
+    s3 = torch.zeros(rcap * 2, dtype=torch.int64).pin_memory().numpy()
+    ctx.set_option("time_kernels", 1)
+    best, best_us = None, None
+    for it in range(4):
+        ctx.stat("sketch_reset")
+        t0 = time.perf_counter()
+        rc = lib.gd_sketch_reads_batch(ctx.h, nr, gd._ptr(r_off), gd._ptr(r_len), gd._ptr(h_reads.numpy()), 11, 21, b"10", W, C.c_float(0.1), 800,
+                                       gd._ptr(s2_counts), gd._ptr(s2_off), gd._ptr(s2), rcap, gd._ptr(s3_off), gd._ptr(s3_ret), gd._ptr(s3), rcap)
+        dt = time.perf_counter() - t0
+        ctx._check(rc, "gd_sketch_reads_batch")
+        us = ctx.stat("sketch_us")
+        if it and (best is None or dt < best):
+            best, best_us = dt, us
+    ctx.set_option("time_kernels", 0)
+    out["reads"] = {"workload": "%d reads x %d bp: mm_sketch2 + mm_sketch3 for both shifts, cap 800" % (nr, rl),
+                    "gbases_per_s_kernel": nr * rl / (best_us * 1e-6) / 1e9 if best_us else None,
+                    "e2e": {"value": nr * rl / best / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": int(nr * rl + nr * 12),
+                            "d2h_bytes_per_step": int((int(s3_off[nr * W]) + int(s2_off[nr])) * 16 + nr * W * 8 + (nr * W + nr + 2) * 8),
+                            "call": "gd_sketch_reads_batch: pinned host ASCII -> the lists of every read and shift on the host"}}
+    return out
 
 
-def cpu_baseline_sample(args, P):
-    from oraclelib import Ref, cpu_has_avx512
+def cpu_baseline_sample(args, P, ez_gpu=None, coff_gpu=None, cig_gpu=None):
+    """The unmodified reference on all host threads: ~12 s of passes over the first n pairs of the step (the baseline
+    figure), and -- when the GPU's results are handed in -- ONE pass over ALL pairs of the step whose ksw_extz_t fields and
+    CIGARs are compared with the GPU's, pair by pair (`parity` in the JSON line)."""
+    from oraclelib import Ref, cpu_has_avx512, EXTZ_DTYPE, EXTZ_FIELDS
     import gdiet_b200  # noqa: F401
     from gdiet_b200 import synth
     variant = "avx" if cpu_has_avx512() else "scalar"
@@ -448,23 +546,81 @@ def cpu_baseline_sample(args, P):
     sc = synth.SCORING["sr"]
     mat = synth.score_matrix(sc["a"], sc["b"])
     pre = band_prefix(QLEN, TLEN, BAND)
+    stride = QLEN + TLEN
+    N = len(P["qlen"])
+    buf = (np.zeros(N, EXTZ_DTYPE), np.zeros(N * stride, np.uint32))
 
     def run(n):
         t0 = time.perf_counter()
         R.ksw_extd2_batch(P["qlen"][:n], P["qoff"][:n], P["qbuf"], P["tlen"][:n], P["toff"][:n], P["tbuf"], mat, sc["q"], sc["e"], sc["q2"],
-                          sc["e2"], BAND, sc["zdrop"], sc["end_bonus"], args.flag, cores, cigar_stride=QLEN + TLEN)
+                          sc["e2"], BAND, sc["zdrop"], sc["end_bonus"], args.flag, cores, cigar_stride=stride, out=buf)
         return time.perf_counter() - t0
 
     dt = run(4096)
-    n = int(min(len(P["qlen"]), max(4096, 4096 * 4.0 / max(dt, 1e-3))))
+    n = int(min(N, max(4096, 4096 * 4.0 / max(dt, 1e-3))))
     # ~12 s of CPU work: repeat passes over the first n pairs of the step
     passes, tot = 0, 0.0
     while tot < 12.0 and passes < 64:
         tot += run(n)
         passes += 1
-    return {"value": passes * n * int(pre[-1]) / tot / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
-            "sample": "%d passes over the first %d pairs of the step, ksw_extd2_%s via oracle/_ref on %d threads, %.1f s" % (
-                passes, n, "avx512" if variant == "avx" else "sse", cores, tot)}
+    cpu = {"value": passes * n * int(pre[-1]) / tot / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
+           "sample": "%d passes over the first %d pairs of the step, ksw_extd2_%s via oracle/_ref on %d threads, %.1f s" % (
+               passes, n, "avx512" if variant == "avx" else "sse", cores, tot)}
+    parity = None
+    if ez_gpu is not None:
+        if n < N:
+            run(N)  # one pass over every pair of the step
+        ez_ref, cig_ref = buf
+        bad = np.zeros(N, bool)
+        for f in EXTZ_FIELDS:
+            bad |= ez_ref[f][:N] != ez_gpu[f][:N]
+        ncg = np.clip(ez_ref["n_cigar"][:N], 0, stride).astype(np.int64)
+        flat = cig_ref.reshape(N, stride)[np.arange(stride)[None, :] < ncg[:, None]]  # row-major: the pairs' CIGARs back to back
+        total = int(coff_gpu[N])
+        cig_same = len(flat) == total and bool(np.array_equal(flat, cig_gpu[:total]))
+        if not cig_same and len(flat) == total:  # which pairs
+            d = np.nonzero(flat != cig_gpu[:total])[0]
+            bad[np.unique(np.searchsorted(coff_gpu[1:N + 1], d, side="right"))] = True
+        parity = {"checked_pairs": int(N), "mismatching_pairs": int(bad.sum()) if (cig_same or len(flat) == total) else -1,
+                  "fields": "max zdropped max_q max_t mqe mqe_t mte mte_q score n_cigar reach_end + every CIGAR entry",
+                  "cigar_entries": total, "against": "ksw_extd2_%s of the unmodified reference (oracle/_ref) on the same pairs, flag %#x" % (
+                      "avx512" if variant == "avx" else "sse", args.flag)}
+    return cpu, parity
+
+
+def zdrop_subset(ctx, args):
+    """a 30 %-edit subset of the config-2 shape so that Z-drop fires; GPU (host-buffer call) against the
+    unmodified reference on every pair."""
+    import gdiet_b200 as gd
+    from gdiet_b200 import synth
+    from oraclelib import Ref, cpu_has_avx512, EXTZ_FIELDS
+    n = 100_000
+    P = synth.ksw_pairs_fast(n, QLEN, TLEN, 0.30, seed=4)
+    sc = synth.SCORING["sr"]
+    mat = synth.score_matrix(sc["a"], sc["b"])
+    prm = gd.KswParams(mat, sc["q"], sc["e"], sc["q2"], sc["e2"], sc["zdrop"], sc["end_bonus"], args.flag)
+    ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], prm, w_all=BAND)
+    t0 = time.perf_counter()
+    ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], prm, w_all=BAND)
+    dt = time.perf_counter() - t0
+    pre = band_prefix(QLEN, TLEN, BAND)
+    cells = int(pre[np.clip(ez["rows_done"], 0, len(pre) - 1)].sum())
+    out = {"pairs": n, "edits": 0.30, "flag": args.flag, "zdropped_frac": float((ez["zdropped"] != 0).mean()), "cells": cells,
+           "gcups_e2e": cells / dt / 1e9}
+    if not args.no_cpu:
+        variant = "avx" if cpu_has_avx512() else "scalar"
+        R = Ref(variant)
+        stride = QLEN + TLEN
+        ez_r, cig_r = R.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], mat, sc["q"], sc["e"], sc["q2"],
+                                        sc["e2"], BAND, sc["zdrop"], sc["end_bonus"], args.flag, host_threads(), cigar_stride=stride)
+        bad = np.zeros(n, bool)
+        for f in EXTZ_FIELDS:
+            bad |= ez_r[f] != ez[f]
+        ncg = np.clip(ez_r["n_cigar"], 0, stride).astype(np.int64)
+        flat = cig_r.reshape(n, stride)[np.arange(stride)[None, :] < ncg[:, None]]
+        out["parity"] = {"checked_pairs": n, "mismatching_pairs": int(bad.sum()),
+                         "cigars_identical": len(flat) == int(coff[n]) and bool(np.array_equal(flat, cig[:int(coff[n])]))}
+    return out
 
 
 def main():
@@ -477,6 +633,9 @@ def main():
     ap.add_argument("--flag", type=lambda s: int(s, 0), default=0x00)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sketch", action="store_true")
+    ap.add_argument("--no-map-strong", action="store_true", help="skip extra.map_strong (10 M reads vs the 3.1 Gbp index, strong-scaled over the ranks)")
+    ap.add_argument("--map-reads", type=int, default=10_000_000)
+    ap.add_argument("--map-genome-bp", type=int, default=3_100_000_000)
     ap.add_argument("--group", type=int, default=0, help="lanes per pair (0 = auto)")
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     args = ap.parse_args()

@@ -188,12 +188,17 @@ class Ref(_DPMixin):
                            end_bonus, flag)
 
     def ksw_extd2_batch(self, qlen, qoff, qbuf, tlen, toff, tbuf, mat, gapo, gape, gapo2, gape2, w, zdrop, end_bonus,
-                        flag, n_threads, cigar_stride=0, which=None):
+                        flag, n_threads, cigar_stride=0, which=None, out=None):
+        """out = (ez, cig) preallocated by the caller (a timed loop must not pay for a fresh 1.4 GB array per step)"""
         if which is None:
             which = 1 if self.variant == "avx" else 0
         n = len(qlen)
-        ez = np.zeros(n, EXTZ_DTYPE)
-        cig = np.zeros(n * cigar_stride, np.uint32) if cigar_stride else None
+        if out is not None:
+            ez, cig = out
+            assert len(ez) >= n and (not cigar_stride or len(cig) >= n * cigar_stride)
+        else:
+            ez = np.zeros(n, EXTZ_DTYPE)
+            cig = np.zeros(n * cigar_stride, np.uint32) if cigar_stride else None
         m = int(round(len(mat) ** 0.5))
         self.lib.ref_ksw_extd2_batch(which, n, qlen, qoff, qbuf, tlen, toff, tbuf, m, mat, gapo, gape, gapo2, gape2, w,
                                      zdrop, end_bonus, flag, ez.ctypes.data_as(C.c_void_p),

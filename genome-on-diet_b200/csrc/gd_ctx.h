@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <string>
 #include <utility>
 #include <vector>
@@ -110,7 +111,7 @@ static inline int gd_reserve(gd_ctx *ctx, GdBuf &b, size_t bytes)
 	if (bytes <= b.cap) return GD_OK;
 	if (b.p) GD_CUDA_OK(ctx, cudaFree(b.p));
 	b.p = nullptr, b.cap = 0;
-	size_t want = bytes + bytes / 8 + 256;
+	size_t want = bytes + std::min<size_t>(bytes / 8, (size_t)256 << 20) + 256; // (slack: at most 256 MB)
 	GD_CUDA_OK(ctx, cudaMalloc(&b.p, want));
 	b.cap = want;
 	return GD_OK;

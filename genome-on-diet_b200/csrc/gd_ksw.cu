@@ -277,8 +277,10 @@ int gd_ksw_run_device(gd_ctx *ctx, int n, const int32_t *d_qlen, const int64_t *
 	else { // the arena has to grow: size it from the memory that is free now (cudaMemGetInfo is not free, so only here)
 		size_t fr = 0, tot = 0;
 		GD_CUDA_OK(ctx, cudaMemGetInfo(&fr, &tot));
-		budget = std::max<size_t>(ctx->parena.cap, (size_t)(fr * 0.6));
-		budget = std::min<size_t>(budget, (size_t)96 << 30);
+		// (a call of the mapping stage runs its slices on two contexts: each may take at most 40 % of what is free, and never
+		// more than 64 GB -- the first lane used to leave too little for the second: out of memory at 20,000 HiFi reads)
+		budget = std::max<size_t>(ctx->parena.cap, (size_t)(fr * 0.4));
+		budget = std::min<size_t>(budget, (size_t)64 << 30);
 	}
 	int chunk = n;
 	if (with_p) {

@@ -9,6 +9,7 @@
 // This is HOST code of the product (plain C++, no CUDA): the reference keeps these steps on the CPU too.  Input is
 // exactly what gd_sr_map_batch returns plus the read / reference text the host already holds.
 #include <math.h>
+#include <sys/mman.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -251,6 +252,20 @@ struct Out { // append-only text buffer; need() once per record, then unchecked 
 	{
 		if (n + k <= cap) return;
 		cap = std::max(cap * 2, n + k + 4096);
+		static const bool huge = !(getenv("GDIET_SAM_HUGEPAGES") && atoi(getenv("GDIET_SAM_HUGEPAGES")) == 0);
+		if (huge && cap >= ((size_t)8 << 20)) {
+			// Large text buffers: 2 MB aligned and marked for transparent huge pages.  Every worker thread first-touches
+			// hundreds of MB of fresh memory per batch; with 4 KB pages that is one page fault per 9 records, all of them
+			// taking the process's address-space lock (GDIET_SAM_HUGEPAGES=0 switches this off; tools/sam_stage_bench.py).
+			cap = (cap + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+			void *nb = nullptr;
+			if (posix_memalign(&nb, (size_t)2 << 20, cap) != 0) abort();
+			madvise(nb, cap, MADV_HUGEPAGE);
+			if (n) memcpy(nb, b, n);
+			free(b);
+			b = (char *)nb;
+			return;
+		}
 		b = (char *)realloc(b, cap);
 		if (!b) abort();
 	}

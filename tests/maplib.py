@@ -78,12 +78,18 @@ def make_dataset(seed=1, contig_lens=(300000, 200000, 100000), n_reads=3000, rea
 
 
 def write_fasta(path, contigs):
-    with open(path, "w") as f:
+    with open(path, "wb") as f:
         for i, c in enumerate(contigs):
-            f.write(">chr%d\n" % (i + 1))
-            s = c.tobytes().decode()
-            for j in range(0, len(s), 80):
-                f.write(s[j:j + 80] + "\n")
+            f.write(b">chr%d\n" % (i + 1))
+            c = np.ascontiguousarray(c, np.uint8)
+            rows = len(c) // 80
+            if rows:  # 80 bases per line, laid out with numpy (a 3.1 Gbp genome is 39 M lines)
+                out = np.empty((rows, 81), np.uint8)
+                out[:, :80] = c[:rows * 80].reshape(rows, 80)
+                out[:, 80] = 10
+                f.write(out.tobytes())
+            if len(c) > rows * 80:
+                f.write(c[rows * 80:].tobytes() + b"\n")
 
 
 def write_fastq(path, reads):

@@ -304,7 +304,7 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write", "gd_lr_sam_batch", "gd_index_load_mmi", "gd_index_seq_name", "gd_sr_sam_batch_parts",
            "gd_pinned_alloc", "gd_pinned_free", "gd_multi_init", "gd_multi_destroy", "gd_multi_size", "gd_multi_ctx", "gd_multi_index",
            "gd_multi_strerror", "gd_multi_index_bcast", "gd_multi_stat", "gd_multi_sr_map_batch", "gd_multi_lr_map_batch",
-           "gd_multi_sr_map_sam", "gd_multi_lr_map_sam"]
+           "gd_multi_sr_map_sam", "gd_multi_lr_map_sam", "gd_sr_map_sam_batch"]
 
 
 def load():
@@ -415,6 +415,9 @@ def load():
     L.gd_multi_sr_map_batch.argtypes = [vp, i32, vp, vp, vp, C.POINTER(gd_sr_opt_t), vp, vp, i64, vp, i64, C.POINTER(i64)]
     L.gd_multi_lr_map_batch.restype = i32
     L.gd_multi_lr_map_batch.argtypes = [vp, i32, vp, vp, vp, C.POINTER(gd_lr_opt_t), vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.gd_sr_map_sam_batch.restype = i32
+    L.gd_sr_map_sam_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, C.POINTER(gd_sr_opt_t), C.POINTER(gd_sr_post_opt_t), i32, vp,
+                                      C.POINTER(C.POINTER(vp)), C.POINTER(C.POINTER(C.c_size_t)), C.POINTER(i32)]
     for fn, ot in ((L.gd_multi_sr_map_sam, gd_sr_opt_t), (L.gd_multi_lr_map_sam, gd_lr_opt_t)):
         fn.restype = i32
         fn.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.POINTER(ot), C.POINTER(gd_sr_post_opt_t), i32, vp, vp, vp, vp,
@@ -630,6 +633,21 @@ class Context:
         """gd_lr_map_batch (long-read tree). Returns (cand_off[n+1], candidates (SR_CAND_DTYPE), cigar pool)."""
         return self.sr_map_batch(index, off, lens, buf, opt, cand_cap, cigar_cap, fn=self.lib.gd_lr_map_batch, what="gd_lr_map_batch")
 
+    def sr_map_sam_batch(self, index, names, off, lens, seq, qual, opt, post, seq_names, join=True):
+        """gd_sr_map_sam_batch: reads in, SAM text out (the post-DP stage runs on the device).  names / seq_names: lists of
+        str or ctypes char* arrays.  Returns the text (bytes), or with join=False the list of (address, length) pieces, which
+        stay valid until the call after the next one."""
+        n_arr, s_arr = _cstr_array(names), _cstr_array(seq_names)
+        parts, plen, npart = C.POINTER(C.c_void_p)(), C.POINTER(C.c_size_t)(), C.c_int(0)
+        self._check(self.lib.gd_sr_map_sam_batch(self.h, index.h, len(lens), C.cast(n_arr, C.c_void_p), _ptr(off), _ptr(lens), _ptr(seq),
+                                                 _ptr(qual), C.byref(opt), C.byref(post), len(s_arr), C.cast(s_arr, C.c_void_p),
+                                                 C.byref(parts), C.byref(plen), C.byref(npart)), "gd_sr_map_sam_batch")
+        pieces = [(int(parts[i] or 0), int(plen[i])) for i in range(npart.value)]
+        self.lib.gd_free(C.cast(parts, C.c_void_p)), self.lib.gd_free(C.cast(plen, C.c_void_p))
+        if not join:
+            return pieces
+        return b"".join(C.string_at(a, l) for a, l in pieces)
+
     def sr_map_batch(self, index, off, lens, buf, opt, cand_cap=None, cigar_cap=None, fn=None, what="gd_sr_map_batch"):
         """gd_sr_map_batch. Returns (cand_off[n+1], candidates (SR_CAND_DTYPE), cigar pool)."""
         fn = fn or self.lib.gd_sr_map_batch
@@ -713,10 +731,7 @@ class Multi:
         self._check(fn(self.h, len(lens), C.cast(n_arr, C.c_void_p), _ptr(off), _ptr(lens), _ptr(seq), _ptr(qual), C.byref(opt), C.byref(post),
                        len(bufs), C.cast(s_arr, C.c_void_p), _ptr(roff), _ptr(rlen), _ptr(ref), C.byref(parts), C.byref(plen), C.byref(npart)),
                     "gd_multi_map_sam")
-        out = []
-        for i in range(npart.value):
-            out.append(C.string_at(parts[i], plen[i]))
-            self.lib.gd_free(parts[i])
+        out = [C.string_at(parts[i], plen[i]) for i in range(npart.value)]  # (the pieces belong to the handle)
         self.lib.gd_free(C.cast(parts, C.c_void_p)), self.lib.gd_free(C.cast(plen, C.c_void_p))
         return b"".join(out)
 

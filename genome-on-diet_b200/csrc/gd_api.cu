@@ -88,10 +88,12 @@ extern "C" void gd_destroy(gd_ctx *ctx)
 	                 &ctx->mp_seq, &ctx->mp_off, &ctx->mp_len, &ctx->mp_seed_n, &ctx->mp_seed_first, &ctx->mp_state, &ctx->mp_hoff,
 	                 &ctx->mp_ht, &ctx->mp_hq, &ctx->mp_cand_tmp, &ctx->mp_ncand, &ctx->mp_coff, &ctx->mp_cand, &ctx->mp_qbuf,
 	                 &ctx->mp_tbuf, &ctx->mp_pair, &ctx->mp_ez, &ctx->mp_cig, &ctx->mp_cnt, &ctx->mp_cpool, &ctx->mp_tmp,
-	                 &ctx->lead64_scr, &ctx->lead64_list};
+	                 &ctx->lead64_scr, &ctx->lead64_list, &ctx->mp_names, &ctx->mp_qual, &ctx->mp_rnames, &ctx->mp_rcoff, &ctx->mp_cpool2,
+	                 &ctx->mp_slen, &ctx->mp_soff, &ctx->mp_text};
 	for (GdBuf *b : bufs)
 		if (b->p) cudaFree(b->p);
-	GdPinned *pins[] = {&ctx->h_stage, &ctx->h_res, &ctx->h_cig, &ctx->h_misc, &ctx->h_sk_stage, &ctx->h_sk_out, &ctx->h_sk_misc, &ctx->h_mp};
+	GdPinned *pins[] = {&ctx->h_stage, &ctx->h_res, &ctx->h_cig, &ctx->h_misc, &ctx->h_sk_stage, &ctx->h_sk_out, &ctx->h_sk_misc, &ctx->h_mp,
+	                    &ctx->h_names, &ctx->h_sam[0], &ctx->h_sam[1]};
 	for (GdPinned *b : pins)
 		if (b->p) cudaFreeHost(b->p);
 	for (int i = 0; i < 4; ++i)

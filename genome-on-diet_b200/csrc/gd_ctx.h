@@ -57,6 +57,12 @@ struct gd_ctx {
 	GdBuf mp_seq, mp_off, mp_len, mp_seed_n, mp_seed_first, mp_state, mp_hoff, mp_ht, mp_hq, mp_cand_tmp, mp_ncand, mp_coff, mp_cand,
 	    mp_qbuf, mp_tbuf, mp_pair, mp_ez, mp_cig, mp_cnt, mp_cpool, mp_tmp;
 	GdPinned h_mp;
+	// SAM text produced on the device (gd_sr_map_sam_batch): per-slice scratch, and two pinned text buffers that alternate
+	// between calls (the pieces of a call stay valid until the call after the next one)
+	GdBuf mp_names, mp_qual, mp_rnames, mp_rcoff, mp_cpool2, mp_slen, mp_soff, mp_text;
+	GdPinned h_names, h_sam[2];
+	size_t h_sam_used[2] = {0, 0};
+	long sam_calls = 0;
 };
 
 #define GD_CUDA_OK(ctx, call)                                                                          \

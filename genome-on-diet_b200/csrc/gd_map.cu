@@ -19,12 +19,14 @@
 #include "gd_ctx.h"
 #include "gd_index.cuh"
 #include "gd_sketch.cuh"
+#include "gd_sam_core.h"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <string>
 #include <thread>
 #include <time.h>
 #include <utility>
@@ -834,6 +836,70 @@ __global__ void __launch_bounds__(128) gd_sr_cigars_kernel(int64_t nc, gd_sr_can
 }
 
 // --------------------------------------------------------------------------------------------
+// K5: the post-DP stage ON THE DEVICE (short reads): mm_update_extra ... mm_write_sam3 for every read of the slice, one
+// thread per read running gd_sam_core.h.  A count pass (on a scratch copy of the CIGAR pool: mm_fix_cigar edits CIGARs in
+// place) gives every read's text length, a scan the offsets, the write pass the dense SAM text -- which is all that crosses
+// PCIe back to the host (430 B per 150 bp read) instead of the candidates + CIGARs and 2 us of host CPU per read.
+// --------------------------------------------------------------------------------------------
+struct SamDev {
+	int n;
+	const int64_t *off;
+	const int32_t *len;
+	const char *seq, *qual; // qual may be NULL
+	const char *names;
+	const int64_t *name_off;
+	const int64_t *coff;         // candidates of read i: cand[coff[i] .. coff[i+1])
+	const gd_sr_cand_t *cand;
+	uint32_t *pool;              // CIGAR pool the cand[].cigar_off index (edited in place)
+	const uint8_t *qbuf, *tbuf;  // code strings of candidate c at c * stride
+	int64_t stride;
+	gdsam::RefNames ref;
+	gd_sr_post_opt_t post;
+};
+GD_DEV gdsam::ReadIn sam_read_in(const SamDev &D, int i)
+{
+	gdsam::ReadIn R;
+	const int64_t c0 = D.coff[i];
+	R.name = D.names + D.name_off[i], R.seq = D.seq + D.off[i], R.qual = D.qual ? D.qual + D.off[i] : nullptr;
+	R.qlen = D.len[i], R.n_cand = (int)(D.coff[i + 1] - c0);
+	R.cand = D.cand + c0, R.cigar = D.pool;
+	R.qcodes = D.qbuf + c0 * D.stride, R.tcodes = D.tbuf + c0 * D.stride, R.stride = D.stride;
+	return R;
+}
+__global__ void __launch_bounds__(128) gd_sam_count_kernel(SamDev D, uint32_t *text_len)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= D.n) return;
+	const gdsam::ReadIn R = sam_read_in(D, i);
+	gdsam::Sink s = {nullptr, 0};
+	gdsam::one_read(R, D.post, D.ref, s);
+	text_len[i] = (uint32_t)s.n;
+}
+__global__ void __launch_bounds__(128) gd_sam_write_kernel(SamDev D, const int64_t *text_off, char *text)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= D.n) return;
+	const gdsam::ReadIn R = sam_read_in(D, i);
+	gdsam::Sink s = {text + text_off[i], 0};
+	gdsam::one_read(R, D.post, D.ref, s);
+}
+
+// What a call in SAM mode (gd_sr_map_sam_batch) carries through its slices.
+struct SamJob {
+	const char *const *names; // of the call's reads (host)
+	const char *qual;         // same layout as the reads' buffer, or NULL
+	gd_sr_post_opt_t post;
+	std::string rblob;        // contig names, NUL separated
+	std::vector<int32_t> rnoff;
+	int gen;                  // which of the two pinned text buffers of every lane this call fills
+	struct Piece {
+		int lane;
+		size_t off, len;
+	};
+	std::vector<Piece> pieces; // by slice index; resolved to pointers when the call ends (a lane buffer may have grown)
+};
+
+// --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
 template <class T> static int scan_u32(gd_ctx *ctx, const uint32_t *d_in, T *d_out, int64_t n)
@@ -916,9 +982,90 @@ struct SliceClaim { // a slice that returns before claiming (an error) must not 
 	}
 };
 
+// SAM mode: the slice's reads -> SAM text in the lane's pinned buffer (sam->pieces[slice_index]); see K5
+static int sam_stage(gd_ctx *ctx, int lane, int n, const int64_t *off, const int32_t *len, int64_t lo, int64_t hi, const int64_t *h_coff,
+                     int64_t nc, int64_t ncig, int64_t stride, SamJob *sam, int first_read, int slice_index)
+{
+	cudaStream_t s = ctx->stream;
+	int rc;
+	// read names of the slice: one blob + offsets, through pinned staging
+	size_t nbytes = 0;
+	for (int i = 0; i < n; ++i) nbytes += strlen(sam->names[first_read + i]) + 1;
+	const size_t off_bytes = (size_t)(n + 1) * 8;
+	if ((rc = gd_reserve_pinned(ctx, ctx->h_names, off_bytes + nbytes + 64))) return rc;
+	int64_t *h_noff = (int64_t *)ctx->h_names.p;
+	char *h_blob = (char *)ctx->h_names.p + off_bytes;
+	size_t at = 0;
+	for (int i = 0; i < n; ++i) {
+		const char *nm = sam->names[first_read + i];
+		const size_t l = strlen(nm) + 1;
+		h_noff[i] = (int64_t)at;
+		memcpy(h_blob + at, nm, l), at += l;
+	}
+	h_noff[n] = (int64_t)at;
+	if ((rc = gd_reserve(ctx, ctx->mp_names, off_bytes + nbytes + 64))) return rc;
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_names.p, ctx->h_names.p, off_bytes + nbytes, cudaMemcpyHostToDevice, s));
+	if (sam->qual) {
+		if ((rc = gd_reserve(ctx, ctx->mp_qual, (size_t)(hi - lo) + 16))) return rc;
+		GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_qual.p, sam->qual + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s));
+	}
+	// contig names + the per-read candidate offsets (the device copy was reused for the CIGAR offsets)
+	const size_t rn_bytes = sam->rnoff.size() * 4, rb_bytes = sam->rblob.size();
+	if ((rc = gd_reserve(ctx, ctx->mp_rnames, rn_bytes + rb_bytes + 64))) return rc;
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_rnames.p, sam->rnoff.data(), rn_bytes, cudaMemcpyHostToDevice, s));
+	GD_CUDA_OK(ctx, cudaMemcpyAsync((char *)ctx->mp_rnames.p + rn_bytes, sam->rblob.data(), rb_bytes, cudaMemcpyHostToDevice, s));
+	if ((rc = gd_reserve(ctx, ctx->mp_rcoff, off_bytes))) return rc;
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_rcoff.p, h_coff, off_bytes, cudaMemcpyHostToDevice, s));
+	if ((rc = gd_reserve(ctx, ctx->mp_cpool2, (size_t)(ncig + 1) * 4))) return rc;
+	if (ncig) GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->mp_cpool2.p, ctx->mp_cpool.p, (size_t)ncig * 4, cudaMemcpyDeviceToDevice, s));
+	if ((rc = gd_reserve(ctx, ctx->mp_slen, (size_t)(n + 1) * 4))) return rc;
+	if ((rc = gd_reserve(ctx, ctx->mp_soff, (size_t)(n + 2) * 8))) return rc;
+	SamDev D;
+	D.n = n, D.off = (const int64_t *)ctx->mp_off.p, D.len = (const int32_t *)ctx->mp_len.p, D.seq = (const char *)ctx->mp_seq.p;
+	D.qual = sam->qual ? (const char *)ctx->mp_qual.p : nullptr;
+	D.name_off = (const int64_t *)ctx->mp_names.p, D.names = (const char *)ctx->mp_names.p + off_bytes;
+	D.coff = (const int64_t *)ctx->mp_rcoff.p, D.cand = (const gd_sr_cand_t *)ctx->mp_cand.p;
+	D.pool = (uint32_t *)ctx->mp_cpool2.p; // the count pass edits the copy
+	D.qbuf = (const uint8_t *)ctx->mp_qbuf.p, D.tbuf = (const uint8_t *)ctx->mp_tbuf.p, D.stride = stride;
+	D.ref.off = (const int32_t *)ctx->mp_rnames.p, D.ref.blob = (const char *)ctx->mp_rnames.p + rn_bytes;
+	D.post = sam->post;
+	(void)nc;
+	const int blocks = (n + 127) / 128;
+	gd_sam_count_kernel<<<blocks, 128, 0, s>>>(D, (uint32_t *)ctx->mp_slen.p);
+	ctx->stat_launches++;
+	GD_CUDA_OK(ctx, cudaGetLastError());
+	if ((rc = scan_u32(ctx, (const uint32_t *)ctx->mp_slen.p, (int64_t *)ctx->mp_soff.p, n))) return rc;
+	int64_t *h_word = (int64_t *)ctx->h_mp.p;
+	GD_CUDA_OK(ctx, cudaMemcpyAsync(h_word, (int64_t *)ctx->mp_soff.p + n, 8, cudaMemcpyDeviceToHost, s));
+	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
+	const size_t total = (size_t)h_word[0];
+	if ((rc = gd_reserve(ctx, ctx->mp_text, total + 16))) return rc;
+	D.pool = (uint32_t *)ctx->mp_cpool.p;
+	gd_sam_write_kernel<<<blocks, 128, 0, s>>>(D, (const int64_t *)ctx->mp_soff.p, (char *)ctx->mp_text.p);
+	ctx->stat_launches++;
+	GD_CUDA_OK(ctx, cudaGetLastError());
+	// the lane's pinned text buffer of this call's generation: append (grown geometrically, earlier pieces move with it)
+	GdPinned &hb = ctx->h_sam[sam->gen];
+	size_t &used = ctx->h_sam_used[sam->gen];
+	if (used + total + 1 > hb.cap) {
+		GdPinned nb;
+		const size_t want = std::max<size_t>((used + total) * 2, (size_t)64 << 20);
+		GD_CUDA_OK(ctx, cudaHostAlloc(&nb.p, want, cudaHostAllocPortable));
+		nb.cap = want;
+		if (used) memcpy(nb.p, hb.p, used);
+		if (hb.p) cudaFreeHost(hb.p);
+		hb = nb;
+	}
+	if (total) GD_CUDA_OK(ctx, cudaMemcpyAsync((char *)hb.p + used, ctx->mp_text.p, total, cudaMemcpyDeviceToHost, s));
+	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
+	sam->pieces[slice_index] = {lane, used, total};
+	used += total;
+	return GD_OK;
+}
+
 static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
                         const gd_sr_opt_t *o, const gd_lr_opt_t *lr, SliceOrder &ord, int slice_index, int64_t *cand_off, gd_sr_cand_t *cand,
-                        int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap)
+                        int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap, SamJob *sam = nullptr, int lane = 0, int first_read = 0)
 {
 	SliceClaim claim(ord);
 	int64_t cand_base = 0, cig_base = 0;
@@ -1022,6 +1169,10 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	}
 	clk.mark("vote");
 	if (nc == 0) {
+		if (sam) { // every read of the slice is unmapped: flag-4 records
+			claim.done = true;
+			return sam_stage(ctx, lane, n, off, len, lo, hi, h_coff, 0, 0, P.stride, sam, first_read, slice_index);
+		}
 		if (!ord.claim(slice_index, 0, 0, cand_base, cig_base)) return SR_ABORTED;
 		claim.done = true;
 		for (int i = 0; i <= n; ++i) cand_off[i] = cand_base;
@@ -1086,6 +1237,21 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));
 	const int64_t ncig = h_word[0];
 	clk.mark("scores");
+	if (sam) { // SAM mode: nothing of this slice depends on the others; the text is produced on the device
+		if (ncig > 0x7fffffff) {
+			ctx->err = "gd_sr_map_sam_batch: CIGAR pool of one slice exceeds 2^31 entries";
+			return GD_ERR_ARG;
+		}
+		if ((rc = gd_reserve(ctx, ctx->mp_cpool, (size_t)(ncig + 1) * 4))) return rc;
+		gd_sr_cigars_kernel<<<wblocks, 128, 0, s>>>(nc, d_cand, d_pair_off, d_cig_off, (const uint32_t *)ctx->mp_cig.p, cig_stride,
+		                                          (uint32_t *)ctx->mp_cpool.p, ncig);
+		ctx->stat_launches++;
+		GD_CUDA_OK(ctx, cudaGetLastError());
+		claim.done = true;
+		rc = sam_stage(ctx, lane, n, off, len, lo, hi, h_coff, nc, ncig, P.stride, sam, first_read, slice_index);
+		clk.mark("sam");
+		return rc;
+	}
 	if (!ord.claim(slice_index, nc, ncig, cand_base, cig_base)) return SR_ABORTED;
 	claim.done = true;
 	for (int i = 0; i <= n; ++i) cand_off[i] = h_coff[i] + cand_base; // (the shared boundary entry gets the same value from both neighbours)
@@ -1110,7 +1276,8 @@ extern "C" int gd_init(int device, gd_ctx **ctx);
 
 static int run_slices(gd_ctx *ctx, const gd_index *idx, const std::vector<std::pair<int, int>> &slices, const int64_t *off,
                       const int32_t *len, const char *buf, const gd_sr_opt_t *o, const gd_lr_opt_t *lr, int64_t *cand_off,
-                      gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cand, int64_t *n_cig)
+                      gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cand, int64_t *n_cig,
+                      SamJob *sam = nullptr)
 {
 	SliceOrder ord;
 	ctx->err.clear();
@@ -1123,7 +1290,8 @@ static int run_slices(gd_ctx *ctx, const gd_index *idx, const std::vector<std::p
 		cudaSetDevice(c->device);
 		for (int k = L; k < ns; k += lanes) {
 			const int b = slices[k].first, m = slices[k].second;
-			const int rc = sr_map_slice(c, idx, m, off + b, len + b, buf, o, lr, ord, k, cand_off + b, cand, cand_cap, cigar, cigar_cap);
+			const int rc = sr_map_slice(c, idx, m, off + b, len + b, buf, o, lr, ord, k, cand_off ? cand_off + b : nullptr, cand, cand_cap, cigar,
+			                            cigar_cap, sam, L, b);
 			if (rc) {
 				rcs[L] = rc;
 				ord.fail();
@@ -1179,6 +1347,59 @@ extern "C" int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const in
 		ctx->err = "gd_sr_map_batch: output buffer too small";
 		return GD_ERR_CAPACITY;
 	}
+	return GD_OK;
+}
+
+// Reads in, SAM records out: gd_sr_map_batch with the post-DP stage on the device (K5).  The text comes back as pieces in
+// input order (one per slice) that live in pinned buffers OWNED BY THE CONTEXT: they stay valid until the call after the
+// next one on this context (two generations alternate, so a host can write batch i out while batch i+1 is mapped); the
+// caller frees only the two arrays, with gd_free.
+extern "C" int gd_sr_map_sam_batch(gd_ctx *ctx, const gd_index *idx, int n, const char *const *names, const int64_t *off, const int32_t *len,
+                                   const char *seq, const char *qual, const gd_sr_opt_t *o, const gd_sr_post_opt_t *post, int n_seq,
+                                   const char *const *seq_names, char ***parts, size_t **part_len, int *n_parts)
+{
+	if (!ctx) return GD_ERR_ARG;
+	if (!idx || !o || !post || n < 0 || !parts || !part_len || !n_parts || n_seq < 1 || !seq_names || (n > 0 && (!names || !off || !len || !seq))) {
+		ctx->err = "gd_sr_map_sam_batch: bad argument";
+		return GD_ERR_ARG;
+	}
+	if (o->af_max_loc < 1 || o->af_max_loc > SR_MAX_LOC || o->W < 1 || o->W > 63 || idx->device != ctx->device) {
+		ctx->err = "gd_sr_map_sam_batch: need 1 <= af_max_loc <= 32, 1 <= W <= 63 and an index built on this device";
+		return GD_ERR_ARG;
+	}
+	if (!post->is_sr) {
+		ctx->err = "gd_sr_map_sam_batch: the device SAM stage implements the linear gap cost of MM_F_SR (short reads)";
+		return GD_ERR_ARG;
+	}
+	*parts = nullptr, *part_len = nullptr, *n_parts = 0;
+	if (n == 0) return GD_OK;
+	cudaSetDevice(ctx->device);
+	SamJob job;
+	job.names = names, job.qual = qual, job.post = *post;
+	for (int i = 0; i < n_seq; ++i) {
+		job.rnoff.push_back((int32_t)job.rblob.size());
+		job.rblob += seq_names[i], job.rblob.push_back('\0');
+	}
+	job.gen = (int)(ctx->sam_calls++ & 1);
+	ctx->h_sam_used[job.gen] = 0;
+	if (ctx->peer) ctx->peer->h_sam_used[job.gen] = 0;
+	const int slice = std::max(32768, std::min(1 << 18, (n + 3) / 4));
+	std::vector<std::pair<int, int>> slices;
+	for (int b = 0; b < n; b += slice) slices.push_back({b, std::min(slice, n - b)});
+	job.pieces.assign(slices.size(), SamJob::Piece{0, 0, 0});
+	int64_t cb = 0, gb = 0;
+	const bool had_peer = ctx->peer != nullptr;
+	int rc = run_slices(ctx, idx, slices, off, len, seq, o, nullptr, nullptr, nullptr, 0, nullptr, 0, &cb, &gb, &job);
+	if (!had_peer && ctx->peer) (void)0; // (a peer created during this call started with h_sam_used == 0)
+	if (rc) return rc;
+	const size_t np = job.pieces.size();
+	*parts = (char **)malloc((np + 1) * sizeof(char *)), *part_len = (size_t *)malloc((np + 1) * sizeof(size_t));
+	if (!*parts || !*part_len) return GD_ERR_ARG;
+	for (size_t k = 0; k < np; ++k) {
+		gd_ctx *c = job.pieces[k].lane == 0 ? ctx : ctx->peer;
+		(*parts)[k] = (char *)c->h_sam[job.gen].p + job.pieces[k].off, (*part_len)[k] = job.pieces[k].len;
+	}
+	*n_parts = (int)np;
 	return GD_OK;
 }
 

@@ -55,6 +55,10 @@ struct gd_multi {
 		int rc = GD_OK;
 	};
 	std::vector<Shard> sh;
+	// text pieces of the *_map_sam calls belong to the handle: host-made (malloc'ed) pieces are freed two calls later, like the
+	// device-made ones (pinned buffers of the contexts) are reused then
+	std::vector<char *> owned[2];
+	long sam_calls = 0;
 };
 
 extern "C" int gd_init(int device, gd_ctx **ctx);
@@ -102,6 +106,8 @@ extern "C" void gd_multi_destroy(gd_multi *m)
 	if (!m) return;
 	for (size_t i = 0; i < m->idx.size(); ++i)
 		if (m->idx[i] && (i > 0 || m->own_root)) gd_index_destroy(m->idx[i]);
+	for (int g = 0; g < 2; ++g)
+		for (char *p : m->owned[g]) gd_free(p);
 	for (gd_ncclComm_t c : m->comms)
 		if (c && m->p_destroy) m->p_destroy(c);
 	for (gd_ctx *c : m->ctx) gd_destroy(c);
@@ -321,9 +327,11 @@ extern "C" int gd_multi_lr_map_batch(gd_multi *m, int n, const int64_t *off, con
 	return multi_map(m, n, off, len, buf, opt, gd_lr_map_batch, cand_off, cand, cand_cap, cigar, cigar_cap, n_cigar);
 }
 
-// Mapping + host stage per shard: the SAM text of the mini-batch as pieces in input order (free each piece and both
-// arrays with gd_free).  Every shard thread drives its device, then turns its candidates into SAM records with
-// post->n_threads / n_devices host threads -- no merge of the candidate arrays, no second pass over the text.
+// Mapping + the post-DP stage per shard: the SAM text of the mini-batch as pieces in input order.  Short reads: the whole
+// stage runs on the device (gd_sr_map_sam_batch), only text crosses PCIe.  Long reads: gd_lr_map_batch, then the threaded
+// host stage (gd_lr_sam_batch: concatenate_cigars and the logarithmic gap cost stay on the CPU) with post->n_threads /
+// n_devices threads per shard.  The pieces BELONG TO THE HANDLE and stay valid until the call after the next one (a host
+// writes batch i out while batch i+1 is mapped); the caller frees only the two arrays with gd_free.
 template <class OPT, class FN>
 static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
                          const char *qual, const OPT *opt, FN map_fn, bool lr, const gd_sr_post_opt_t *post, int n_seq,
@@ -340,6 +348,10 @@ static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int
 	*parts = nullptr, *part_len = nullptr, *n_parts = 0;
 	const std::vector<int> cut = shard_cuts(n, len, G);
 	std::vector<std::vector<std::pair<char *, size_t>>> out(G);
+	std::vector<std::vector<char *>> host_made(G);
+	const int gen = (int)(m->sam_calls++ & 1);
+	for (char *p : m->owned[gen]) gd_free(p); // the pieces handed out two calls ago
+	m->owned[gen].clear();
 	gd_sr_post_opt_t po = *post;
 	int total_threads = post->n_threads > 0 ? post->n_threads : (int)std::thread::hardware_concurrency();
 	po.n_threads = std::max(1, total_threads / G);
@@ -349,6 +361,18 @@ static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int
 		S.rc = GD_OK;
 		if (cnt == 0) return;
 		cudaSetDevice(m->ctx[j]->device);
+		if (!lr) { // short reads: reads in, text out
+			char **pp = nullptr;
+			size_t *pl = nullptr;
+			int np = 0;
+			S.rc = gd_sr_map_sam_batch(m->ctx[j], m->idx[j], cnt, names + b, off + b, len + b, seq, qual, (const gd_sr_opt_t *)opt, &po, n_seq,
+			                           seq_names, &pp, &pl, &np);
+			if (!S.rc) {
+				for (int k = 0; k < np; ++k) out[j].push_back({pp[k], pl[k]});
+				gd_free(pp), gd_free(pl);
+			}
+			return;
+		}
 		S.cand_off.assign((size_t)cnt + 1, 0);
 		if (S.cand.size() < (size_t)cnt * 2) S.cand.resize((size_t)cnt * 2);
 		if (S.cigar.size() < (size_t)cnt * 16) S.cigar.resize((size_t)cnt * 16);
@@ -361,23 +385,11 @@ static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int
 			S.cand.resize((size_t)S.n_cand + 16), S.cigar.resize((size_t)S.n_cig + 16);
 		}
 		if (S.rc) return;
-		if (lr) {
-			char *txt = nullptr;
-			size_t tl = 0;
-			S.rc = gd_lr_sam_batch(cnt, names + b, off + b, len + b, seq, qual, S.cand_off.data(), S.cand.data(), S.cigar.data(), n_seq,
-			                       seq_names, ref_off, ref_len, ref, &po, &txt, &tl, nullptr, nullptr);
-			if (!S.rc) out[j].push_back({txt, tl});
-		} else {
-			char **pp = nullptr;
-			size_t *pl = nullptr;
-			int np = 0;
-			S.rc = gd_sr_sam_batch_parts(cnt, names + b, off + b, len + b, seq, qual, S.cand_off.data(), S.cand.data(), S.cigar.data(),
-			                             n_seq, seq_names, ref_off, ref_len, ref, &po, &pp, &pl, &np);
-			if (!S.rc) {
-				for (int k = 0; k < np; ++k) out[j].push_back({pp[k], pl[k]});
-				gd_free(pp), gd_free(pl);
-			}
-		}
+		char *txt = nullptr;
+		size_t tl = 0;
+		S.rc = gd_lr_sam_batch(cnt, names + b, off + b, len + b, seq, qual, S.cand_off.data(), S.cand.data(), S.cigar.data(), n_seq, seq_names,
+		                       ref_off, ref_len, ref, &po, &txt, &tl, nullptr, nullptr);
+		if (!S.rc) out[j].push_back({txt, tl}), host_made[j].push_back(txt);
 	};
 	std::vector<std::thread> th;
 	for (int j = 1; j < G; ++j) th.emplace_back(work, j);
@@ -391,11 +403,9 @@ static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int
 		}
 	size_t np = 0;
 	for (int j = 0; j < G; ++j) np += out[j].size();
-	if (rc) {
-		for (int j = 0; j < G; ++j)
-			for (auto &pr : out[j]) gd_free(pr.first);
-		return rc;
-	}
+	for (int j = 0; j < G; ++j)
+		for (char *p : host_made[j]) m->owned[gen].push_back(p);
+	if (rc) return rc;
 	*parts = (char **)malloc((np + 1) * sizeof(char *)), *part_len = (size_t *)malloc((np + 1) * sizeof(size_t));
 	size_t k = 0;
 	for (int j = 0; j < G; ++j)

@@ -8,10 +8,11 @@
  *   worker_for()          map.c:1045-1092   one mm_map_frag per read on -t host threads
  *
  * Here step 0 reads the mini-batch with the reference's own reader (mm_bseq_read3, bseq.c) and flattens it into one
- * pinned buffer; step 1 hands the WHOLE mini-batch to the device path -- sketching, index lookups, voting, windows,
- * ksw_extd2, CIGARs (gd_sr_map_batch / gd_lr_map_batch) -- and to the library's threaded restatement of the post-DP host
- * phase (mm_update_extra ... mm_write_sam3), on every GPU named by GDIET_GPUS (gd_multi_*: contiguous read shards, one
- * per device, SAM pieces handed back in input order); step 2 writes the pieces.  The three steps run under the
+ * pinned buffer; step 1 hands the WHOLE mini-batch to the device path on every GPU named by GDIET_GPUS (gd_multi_*:
+ * contiguous read shards, one per device, SAM pieces handed back in input order) -- sketching, index lookups, voting,
+ * windows, ksw_extd2, CIGARs and, for short reads, the post-DP phase too (mm_update_extra ... mm_write_sam3 run on the
+ * device, gd_sr_map_sam_batch: only SAM text comes back); the long-read tree finishes with the library's threaded host
+ * restatement of that phase (gd_lr_sam_batch); step 2 writes the pieces.  The three steps run under the
  * reference's kt_pipeline (kthread.c:71-160), so reading batch i+1, mapping batch i and writing batch i-1 overlap
  * exactly as in the reference, and the output order is the input order.
  *
@@ -123,10 +124,8 @@ static void *gdh_worker(void *shared, int step, void *in)
 		gdh_step_t *s = (gdh_step_t *)in;
 		double t0 = realtime();
 		int i;
-		for (i = 0; i < s->n_parts; ++i) {
+		for (i = 0; i < s->n_parts; ++i) /* (the pieces belong to the gd_multi handle: valid until the batch after the next one) */
 			if (s->part_len[i]) mm_err_fwrite(s->parts[i], 1, s->part_len[i], stdout);
-			gd_free(s->parts[i]);
-		}
 		gd_free(s->parts), gd_free(s->part_len);
 		for (i = 0; i < s->n; ++i) {
 			free(s->seq[i].seq), free(s->seq[i].name);

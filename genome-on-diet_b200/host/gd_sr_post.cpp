@@ -796,7 +796,12 @@ static int sam_batch(int n, const char *const *names, const int64_t *off, const 
 	auto work = [&](int t) { // contiguous read ranges: the concatenation is in input order
 		const int64_t b = (int64_t)n * t / nt, e = (int64_t)n * (t + 1) / nt;
 		Scratch T;
-		parts[t].need((size_t)(e - b) * 520 + 4096);
+		{ // one allocation per thread: an estimate of its text (the flag-4 line of an unmapped 50 kbp read alone is 100 kB), so that
+		  // the buffer is not grown -- and copied -- again and again
+			size_t est = 4096;
+			for (int64_t i = b; i < e; ++i) est += 2 * (size_t)len[i] + 96 + (size_t)(cand_off[i + 1] - cand_off[i]) * ((size_t)len[i] / 8 + 384);
+			parts[t].need(est);
+		}
 		for (int64_t i = b; i < e; ++i) {
 			if (sam_off) sam_off[i] = (int64_t)parts[t].size(); // relative to the thread's part; rebased below
 			one_read(C, (int)i, parts[t], T);

@@ -350,6 +350,15 @@ int gd_sr_sam_batch_parts(int n, const char *const *names, const int64_t *off, c
                           const char *qual, const int64_t *cand_off, const gd_sr_cand_t *cand, const uint32_t *cigar, int n_seq,
                           const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,
                           const gd_sr_post_opt_t *opt, char ***parts, size_t **part_len, int *n_parts);
+/* Reads in, SAM records out: gd_sr_map_batch followed ON THE DEVICE by what gd_sr_sam_batch does on the host
+ * (mm_update_extra + mm_fix_cigar, the filter and ordering of map.c:956-978, mm_set_sam_params, mm_write_sam3 for
+ * single-segment reads; post->is_sr must be set: linear gap cost).  One thread per read runs csrc/gd_sam_core.h; only the
+ * text crosses PCIe.  The pieces (input order) live in pinned buffers OWNED BY THE CONTEXT and stay valid until the call
+ * after the next one on this context; free only the two arrays with gd_free.  Byte-identical to gd_sr_sam_batch. */
+int gd_sr_map_sam_batch(gd_ctx *ctx, const gd_index *idx, int n, const char *const *names, const int64_t *off, const int32_t *len,
+                        const char *seq, const char *qual, const gd_sr_opt_t *opt, const gd_sr_post_opt_t *post, int n_seq,
+                        const char *const *seq_names, char ***parts, size_t **part_len, int *n_parts);
+
 /* The same for the long-read tree (LR/map.c:1807-1912): candidates with score == KSW_NEG_INF are dropped,
  * mm_update_extra uses the logarithmic gap cost, a valid candidate that is continued by a valid candidate
  * (cand.reserved[0] >= 0) absorbs it (concatenate_cigars, LR/map.c:41-640), then the min_dp_max filter and the ordering.
@@ -402,8 +411,10 @@ int gd_multi_sr_map_batch(gd_multi *m, int n, const int64_t *off, const int32_t 
 int gd_multi_lr_map_batch(gd_multi *m, int n, const int64_t *off, const int32_t *len, const char *buf, const gd_lr_opt_t *opt,
                           int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap,
                           int64_t *n_cigar);
-/* mapping + the host stage of (4) per shard: the SAM records of the mini-batch as text pieces in input order (what
- * pipeline step 2, map.c:1208-1256, writes out); free every piece and both arrays with gd_free */
+/* mapping + the post-DP stage per shard: the SAM records of the mini-batch as text pieces in input order (what pipeline
+ * step 2, map.c:1208-1256, writes out).  Short reads: gd_sr_map_sam_batch on every device (the text is made on the GPU);
+ * long reads: gd_lr_map_batch + gd_lr_sam_batch.  The pieces BELONG TO THE HANDLE and stay valid until the call after the
+ * next one; free only the two arrays with gd_free.  ref_off / ref_len / ref are read by the long-read host stage only. */
 int gd_multi_sr_map_sam(gd_multi *m, int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
                         const char *qual, const gd_sr_opt_t *opt, const gd_sr_post_opt_t *post, int n_seq,
                         const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,

@@ -17,7 +17,7 @@ RES = np.dtype([(f, np.int32) for f in EXTZ_FIELDS + ["tb_i", "tb_j", "rows_done
 
 def build():
     so = os.path.join(EMU_DIR, "libgd_emu.so")
-    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_ksw.cpp", "emu_sketch.cpp")]
+    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_ksw.cpp", "emu_sketch.cpp", "emu_sam.cpp")]
     deps = srcs + [os.path.join(EMU_DIR, "simt_emu.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)
                                                               if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
@@ -31,6 +31,11 @@ class Emu:
         L.emu_ksw_batch.restype = C.c_int
         L.emu_ksw_batch.argtypes = [C.c_int, i32p, i64p, u8p, i32p, i64p, u8p, i32p, C.c_int, i8p] + [C.c_int] * 9 + [
             C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.emu_sam_batch.restype = C.c_int
+        L.emu_sam_batch.argtypes = [C.c_int] + [C.c_void_p] * 8 + [C.c_int64, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_void_p),
+                                                                                                         C.POINTER(C.c_size_t)]
+        L.emu_sam_check_fixed4.restype = C.c_long
+        L.emu_sam_check_fixed4.argtypes = [C.c_int]
         L.emu_sketch_jobs.restype = C.c_long
         L.emu_sketch_jobs.argtypes = [C.c_int, i64p, i32p, i32p, u32p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int,
                                       C.c_int, C.c_int, i64p, u64p, C.c_int64]
@@ -48,6 +53,27 @@ class Emu:
         assert rc == 0
         self.last_lead64 = int(l64.value)
         return res, cig.reshape(n, stride)
+
+    def sam_batch(self, names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, contigs, opt):
+        """csrc/gd_sam_core.h (the per-read SAM stage of the GPU path) run on the host; same arguments as gd.sr_sam_batch"""
+        import gdiet_b200 as gd
+        ref_len = np.array([len(c) for c in contigs], np.int32)
+        ref_off = np.zeros(len(contigs), np.int64)
+        ref_off[1:] = np.cumsum(ref_len[:-1].astype(np.int64))
+        ref = np.concatenate([np.ascontiguousarray(c, np.uint8) for c in contigs])
+        n_arr, s_arr = gd._cstr_array(names), gd._cstr_array(seq_names)
+        cand = np.ascontiguousarray(cand) if len(cand) else np.zeros(1, gd.SR_CAND_DTYPE)
+        cig = np.ascontiguousarray(cigar, np.uint32) if len(cigar) else np.zeros(1, np.uint32)
+        out, out_len = C.c_void_p(), C.c_size_t(0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        rc = self.lib.emu_sam_batch(len(lens), C.cast(n_arr, C.c_void_p), p(off), p(lens), p(seq), p(qual), p(cand_off), p(cand), p(cig),
+                                    len(cigar), len(contigs), C.cast(s_arr, C.c_void_p), p(ref_off), p(ref_len), p(ref), C.byref(opt),
+                                    C.byref(out), C.byref(out_len))
+        assert rc == 0, rc
+        txt = C.string_at(out, out_len.value)
+        self.lib.emu_sam_check_fixed4.argtypes  # (keep the handle alive)
+        C.CDLL(None).free(out)
+        return txt
 
     def sketch_jobs(self, seqs, shifts, rids, w, k, Z, small, grid=3):
         buf = b"".join(seqs)

@@ -1,5 +1,6 @@
 """GPU parity of the device-resident index and the short-read mapping stage against
 oracle/gd_oracle_map.c, the reference call trace (when oracle/_ref/GDiet_avx_sr travelled) and the golden fixtures."""
+import ctypes
 import os
 
 import numpy as np
@@ -386,4 +387,60 @@ def test_sr_map_error_paths_and_capacity_retry(ctx, gd):
     again = ctx.sr_map_batch(idx, off, lens, buf, o)                              # the context is still usable
     for a, b in zip(want, again):
         assert np.array_equal(a, b)
+    idx.close()
+
+
+# ---- the post-DP stage on the device (gd_sr_map_sam_batch) ----------------------------------------------------------------
+@pytest.mark.parametrize("seed,okw,pkw,ragged", [
+    (1, {}, {}, False),
+    (2, dict(min_cnt=0.2, rec_frac=0.1), dict(no_print_2nd=0, best_n=5), False),
+    (7, dict(min_cnt=0.2, bw_min=500, bw_max=1500, af_max_loc=2), dict(softclip=1), True),
+    (8, dict(min_cnt=0.2, mid_occ=2, max_max_occ=3, occ_dist=40), dict(sam_hit_only=1, no_print_2nd=0), False),
+    (13, dict(min_cnt=0.2, rec_frac=0.1, bw_frac=0.25, bw_min=20, bw_max=60), {}, True),
+])
+def test_device_sam_stage_equals_host_stage(ctx, seed, okw, pkw, ragged):
+    """reads -> SAM text entirely on the device must be byte-identical to gd_sr_map_batch + the host stage gd_sr_sam_batch (which
+    is pinned against the reference program's SAM): multi-candidate reads, secondaries printed, soft clips, N, ragged
+    lengths, lower case, with and without qualities, several slices and both lanes"""
+    import gdiet_b200 as gd
+    rng = np.random.default_rng(seed)
+    contigs, reads = maplib.make_dataset(seed=seed, n_reads=70000 if seed == 1 else 4000)
+    rl = list(reads)
+    if ragged:
+        rl = [r[:int(rng.integers(30, 151))].copy() for r in rl]
+        rl = [np.frombuffer(bytes(r).lower(), np.uint8).copy() if i % 5 == 0 else r for i, r in enumerate(rl)]
+    o = maplib.sr_opt(**okw)
+    idx = ctx.index_build(contigs, 11, 21, "10")
+    off, lens, buf = flat_ragged(rl)
+    qual = (33 + (np.arange(len(buf)) % 41)).astype(np.uint8)
+    names = ["q%d/x" % i for i in range(len(rl))]
+    seq_names = ["chr%d" % (i + 1) for i in range(len(contigs))]
+    post = gd.sr_post_options(n_threads=4, **pkw)
+    coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, o)
+    for q in (qual, None):
+        want = gd.sr_sam_batch(names, off, lens, buf, q, coff, cand, cig, seq_names, contigs, post)
+        got = ctx.sr_map_sam_batch(idx, names, off, lens, buf, q, o, post, seq_names)
+        assert len(got) == len(want) and got == want
+    # pieces of the previous call stay valid during the next one (two generations)
+    p1 = ctx.sr_map_sam_batch(idx, names, off, lens, buf, qual, o, post, seq_names, join=False)
+    first = b"".join(ctypes.string_at(a, l) for a, l in p1)
+    ctx.sr_map_sam_batch(idx, names[:100], off[:100], lens[:100], buf, qual, o, post, seq_names, join=False)
+    assert b"".join(ctypes.string_at(a, l) for a, l in p1) == first
+    idx.close()
+
+
+def test_device_sam_stage_unmappable_and_empty(ctx):
+    import gdiet_b200 as gd
+    contigs, _ = maplib.make_dataset(seed=1, n_reads=1)
+    idx = ctx.index_build(contigs, 11, 21, "10")
+    o, post = maplib.sr_opt(), gd.sr_post_options(n_threads=2)
+    junk = np.frombuffer(b"ACGT" * 40, np.uint8)[None, :150].repeat(5, 0).copy()
+    junk[2] = np.frombuffer(b"N" * 150, np.uint8)
+    off, lens, buf = flat_reads(junk)
+    names = ["j%d" % i for i in range(5)]
+    got = ctx.sr_map_sam_batch(idx, names, off, lens, buf, None, o, post, ["chr1", "chr2", "chr3"])
+    coff, cand, cig = ctx.sr_map_batch(idx, off, lens, buf, o)
+    assert got == gd.sr_sam_batch(names, off, lens, buf, None, coff, cand, cig, ["chr1", "chr2", "chr3"], contigs, post)
+    assert got.count(b"\n") == 5 and b"\t4\t*\t0\t0\t*" in got
+    assert ctx.sr_map_sam_batch(idx, [], np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(1, np.uint8), None, o, post, ["chr1", "chr2", "chr3"]) == b""
     idx.close()

@@ -150,3 +150,33 @@ def test_lr_sam_matches_reference_program(case):
             first_bad = first_bad or (nm, [m[:300] for m in mine], [m[:300] for m in want[nm]])
     assert bad == 0, "%d reads differ, first: %s" % (bad, first_bad)
     assert n_chain > 0 and stitch.sum() == 0      # reads with chained candidates went through concatenate_cigars
+
+
+def test_sam_core_of_the_gpu_path_equals_the_host_stage():
+    """csrc/gd_sam_core.h -- what the GPU runs with one thread per read (gd_sr_map_sam_batch) -- executed on the host against
+    gd_sr_sam_batch on oracle candidates: every option set of the short-read tests, N-holding and ragged reads, reads with
+    several candidates (repeat), soft clips, secondary records printed"""
+    from emulib import Emu
+    E = Emu()
+    assert E.lib.emu_sam_check_fixed4(700) == 0  # "%.4f" by exact integer rounding == printf for every mlen/den up to 700
+    M = maplib.MapOracle()
+    rng = np.random.default_rng(9)
+    for seed, okw, pkw, ragged in ((1, {}, {}, False), (2, dict(min_cnt=0.2, rec_frac=0.1), dict(no_print_2nd=0, best_n=5), False),
+                                   (7, dict(min_cnt=0.2, bw_min=500, bw_max=1500, af_max_loc=2), dict(softclip=1), True),
+                                   (8, dict(min_cnt=0.2, mid_occ=2, max_max_occ=3, occ_dist=40), dict(sam_hit_only=1, no_print_2nd=0), False)):
+        contigs, reads = maplib.make_dataset(seed=seed, n_reads=1200)
+        rl = [r[:int(rng.integers(40, 151))].copy() for r in reads] if ragged else list(reads)
+        o = maplib.sr_opt(**okw)
+        cand_off, cand, cig = oracle_candidates(M, contigs, rl, o)
+        lens = np.array([len(r) for r in rl], np.int32)
+        off = np.zeros(len(rl), np.int64)
+        off[1:] = np.cumsum(lens[:-1].astype(np.int64))
+        buf = np.concatenate(rl)
+        qual = (33 + (np.arange(len(buf)) % 40)).astype(np.uint8)
+        names = ["read_%d" % i for i in range(len(rl))]
+        seq_names = ["chr%d" % (i + 1) for i in range(len(contigs))]
+        post = gd.sr_post_options(n_threads=3, **pkw)
+        for q in (qual, None):
+            want = gd.sr_sam_batch(names, off, lens, buf, q, cand_off, cand, cig, seq_names, contigs, post)
+            got = E.sam_batch(names, off, lens, buf, q, cand_off, cand, cig, seq_names, contigs, post)
+            assert got == want, "seed %d" % seed

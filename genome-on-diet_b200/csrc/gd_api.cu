@@ -261,60 +261,65 @@ extern "C" int gd_ksw_extd2_batch(gd_ctx *ctx, int n, const int32_t *qlen, const
 	auto release = [&]() {
 		for (int k = 0; k < nsl; ++k) ctx->tm_pool.push_back(ev_up[k]), ctx->tm_pool.push_back(ev_done[k]);
 	};
-	GD_CUDA_OK(ctx, cudaMemsetAsync(d_run, 0, 8, s));
-	// the previous call's kernels may still read the staging buffers: uploads start after them
-	GD_CUDA_OK(ctx, cudaEventRecord(ev_done[0], s));
-	GD_CUDA_OK(ctx, cudaStreamWaitEvent(up, ev_done[0], 0));
-	for (int k = 0; k < nsl; ++k) { // ---- enqueue everything
-		const Sl &S = sl[k];
-		GD_CUDA_OK(ctx, cudaMemcpyAsync((int32_t *)ctx->d_qlen.p + S.b, qlen + S.b, (size_t)S.n * 4, cudaMemcpyHostToDevice, up));
-		GD_CUDA_OK(ctx, cudaMemcpyAsync((int32_t *)ctx->d_tlen.p + S.b, tlen + S.b, (size_t)S.n * 4, cudaMemcpyHostToDevice, up));
-		GD_CUDA_OK(ctx, cudaMemcpyAsync((int64_t *)ctx->d_qoff.p + S.b, qoff + S.b, (size_t)S.n * 8, cudaMemcpyHostToDevice, up));
-		GD_CUDA_OK(ctx, cudaMemcpyAsync((int64_t *)ctx->d_toff.p + S.b, toff + S.b, (size_t)S.n * 8, cudaMemcpyHostToDevice, up));
-		if (w) GD_CUDA_OK(ctx, cudaMemcpyAsync((int32_t *)ctx->d_w.p + S.b, w + S.b, (size_t)S.n * 4, cudaMemcpyHostToDevice, up));
-		if (S.q1 > S.q0)
-			GD_CUDA_OK(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_qbuf.p + S.q0, qbuf + S.q0, (size_t)(S.q1 - S.q0), cudaMemcpyHostToDevice, up));
-		if (S.t1 > S.t0)
-			GD_CUDA_OK(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_tbuf.p + S.t0, tbuf + S.t0, (size_t)(S.t1 - S.t0), cudaMemcpyHostToDevice, up));
-		GD_CUDA_OK(ctx, cudaEventRecord(ev_up[k], up));
-		GD_CUDA_OK(ctx, cudaStreamWaitEvent(s, ev_up[k], 0));
-		uint32_t *tmp = want_cigar ? (uint32_t *)ctx->cig_tmp.p + (size_t)(k & 1) * slice * stride : nullptr;
-		gd_extz_t *d_res = (gd_extz_t *)ctx->res.p + S.b;
-		rc = gd_ksw_run_device(ctx, S.n, (const int32_t *)ctx->d_qlen.p + S.b, (const int64_t *)ctx->d_qoff.p + S.b,
-		                       (const uint8_t *)ctx->d_qbuf.p, (const int32_t *)ctx->d_tlen.p + S.b,
-		                       (const int64_t *)ctx->d_toff.p + S.b, (const uint8_t *)ctx->d_tbuf.p,
-		                       w ? (const int32_t *)ctx->d_w.p + S.b : nullptr, w_all, S.max_q, S.max_t, S.max_w, prm, d_res, tmp,
-		                       stride);
-		if (rc) {
-			release();
-			return rc;
-		}
-		if (cigar_off) {
-			rc = gd_ksw_compact_cigars(ctx, S.n, d_res, want_pool ? tmp : nullptr, stride, (int64_t *)ctx->cig_off.p + S.b,
-			                           want_pool ? (uint32_t *)ctx->cig_compact.p : nullptr, cigar_cap, d_run, h_end + k + 1);
-			if (rc) {
-				release();
-				return rc;
-			}
-		}
-		GD_CUDA_OK(ctx, cudaEventRecord(ev_done[k], s));
-	}
-	h_end[0] = 0;
 	int status = GD_OK;
-	for (int k = 0; k < nsl; ++k) { // ---- results come down slice by slice while later slices compute
-		const Sl &S = sl[k];
-		GD_CUDA_OK(ctx, cudaStreamWaitEvent(down, ev_done[k], 0));
-		GD_CUDA_OK(ctx, cudaMemcpyAsync(ez + S.b, (gd_extz_t *)ctx->res.p + S.b, (size_t)S.n * sizeof(gd_extz_t), cudaMemcpyDeviceToHost, down));
-		if (cigar_off) {
-			GD_CUDA_OK(ctx, cudaMemcpyAsync(cigar_off + S.b, (int64_t *)ctx->cig_off.p + S.b, (size_t)(S.n + 1) * 8, cudaMemcpyDeviceToHost, down));
-			GD_CUDA_OK(ctx, cudaEventSynchronize(ev_done[k])); // h_end[k+1] is valid now
-			if (h_end[k + 1] < 0) status = GD_ERR_ARG, h_end[k + 1] = -1 - h_end[k + 1]; // stride overflow inside the slice
-			const int64_t lo = h_end[k], hi = h_end[k + 1];
-			if (want_pool && hi > lo) {
-				if (hi > cigar_cap) status = status == GD_OK ? GD_ERR_CAPACITY : status;
-				else GD_CUDA_OK(ctx, cudaMemcpyAsync(cigar + lo, (uint32_t *)ctx->cig_compact.p + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, down));
+	// Every failure leaves through ONE exit that drains the three streams before the caller may free or reuse qbuf, ez,
+	// cigar_off and cigar (copies that touch them can still be in flight) and gives the slice events back to the pool.
+	auto work = [&]() -> int {
+		GD_CUDA_OK(ctx, cudaMemsetAsync(d_run, 0, 8, s));
+		// the previous call's kernels may still read the staging buffers: uploads start after them
+		GD_CUDA_OK(ctx, cudaEventRecord(ev_done[0], s));
+		GD_CUDA_OK(ctx, cudaStreamWaitEvent(up, ev_done[0], 0));
+		for (int k = 0; k < nsl; ++k) { // ---- enqueue everything
+			const Sl &S = sl[k];
+			GD_CUDA_OK(ctx, cudaMemcpyAsync((int32_t *)ctx->d_qlen.p + S.b, qlen + S.b, (size_t)S.n * 4, cudaMemcpyHostToDevice, up));
+			GD_CUDA_OK(ctx, cudaMemcpyAsync((int32_t *)ctx->d_tlen.p + S.b, tlen + S.b, (size_t)S.n * 4, cudaMemcpyHostToDevice, up));
+			GD_CUDA_OK(ctx, cudaMemcpyAsync((int64_t *)ctx->d_qoff.p + S.b, qoff + S.b, (size_t)S.n * 8, cudaMemcpyHostToDevice, up));
+			GD_CUDA_OK(ctx, cudaMemcpyAsync((int64_t *)ctx->d_toff.p + S.b, toff + S.b, (size_t)S.n * 8, cudaMemcpyHostToDevice, up));
+			if (w) GD_CUDA_OK(ctx, cudaMemcpyAsync((int32_t *)ctx->d_w.p + S.b, w + S.b, (size_t)S.n * 4, cudaMemcpyHostToDevice, up));
+			if (S.q1 > S.q0)
+				GD_CUDA_OK(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_qbuf.p + S.q0, qbuf + S.q0, (size_t)(S.q1 - S.q0), cudaMemcpyHostToDevice, up));
+			if (S.t1 > S.t0)
+				GD_CUDA_OK(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_tbuf.p + S.t0, tbuf + S.t0, (size_t)(S.t1 - S.t0), cudaMemcpyHostToDevice, up));
+			GD_CUDA_OK(ctx, cudaEventRecord(ev_up[k], up));
+			GD_CUDA_OK(ctx, cudaStreamWaitEvent(s, ev_up[k], 0));
+			uint32_t *tmp = want_cigar ? (uint32_t *)ctx->cig_tmp.p + (size_t)(k & 1) * slice * stride : nullptr;
+			gd_extz_t *d_res = (gd_extz_t *)ctx->res.p + S.b;
+			rc = gd_ksw_run_device(ctx, S.n, (const int32_t *)ctx->d_qlen.p + S.b, (const int64_t *)ctx->d_qoff.p + S.b,
+			                       (const uint8_t *)ctx->d_qbuf.p, (const int32_t *)ctx->d_tlen.p + S.b,
+			                       (const int64_t *)ctx->d_toff.p + S.b, (const uint8_t *)ctx->d_tbuf.p,
+			                       w ? (const int32_t *)ctx->d_w.p + S.b : nullptr, w_all, S.max_q, S.max_t, S.max_w, prm, d_res, tmp,
+			                       stride);
+			if (rc) return rc;
+			if (cigar_off) {
+				rc = gd_ksw_compact_cigars(ctx, S.n, d_res, want_pool ? tmp : nullptr, stride, (int64_t *)ctx->cig_off.p + S.b,
+				                           want_pool ? (uint32_t *)ctx->cig_compact.p : nullptr, cigar_cap, d_run, h_end + k + 1);
+				if (rc) return rc;
+			}
+			GD_CUDA_OK(ctx, cudaEventRecord(ev_done[k], s));
+		}
+		h_end[0] = 0;
+		for (int k = 0; k < nsl; ++k) { // ---- results come down slice by slice while later slices compute
+			const Sl &S = sl[k];
+			GD_CUDA_OK(ctx, cudaStreamWaitEvent(down, ev_done[k], 0));
+			GD_CUDA_OK(ctx, cudaMemcpyAsync(ez + S.b, (gd_extz_t *)ctx->res.p + S.b, (size_t)S.n * sizeof(gd_extz_t), cudaMemcpyDeviceToHost, down));
+			if (cigar_off) {
+				GD_CUDA_OK(ctx, cudaMemcpyAsync(cigar_off + S.b, (int64_t *)ctx->cig_off.p + S.b, (size_t)(S.n + 1) * 8, cudaMemcpyDeviceToHost, down));
+				GD_CUDA_OK(ctx, cudaEventSynchronize(ev_done[k])); // h_end[k+1] is valid now
+				if (h_end[k + 1] < 0) status = GD_ERR_ARG, h_end[k + 1] = -1 - h_end[k + 1]; // stride overflow inside the slice
+				const int64_t lo = h_end[k], hi = h_end[k + 1];
+				if (want_pool && hi > lo) {
+					if (hi > cigar_cap) status = status == GD_OK ? GD_ERR_CAPACITY : status;
+					else GD_CUDA_OK(ctx, cudaMemcpyAsync(cigar + lo, (uint32_t *)ctx->cig_compact.p + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, down));
+				}
 			}
 		}
+		return GD_OK;
+	};
+	rc = work();
+	if (rc) {
+		cudaStreamSynchronize(up), cudaStreamSynchronize(s), cudaStreamSynchronize(down);
+		release();
+		return rc;
 	}
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(down));
 	GD_CUDA_OK(ctx, cudaStreamSynchronize(s));

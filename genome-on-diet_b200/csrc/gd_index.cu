@@ -458,6 +458,10 @@ extern "C" int gd_index_load_mmi(gd_ctx *ctx, const char *path, gd_index **out)
 	m.table_slots = 1024;
 	while (m.table_slots < 2 * m.n_keys) m.table_slots <<= 1;
 	m.s_words = (m.total_len + 7) / 8, m.w = D.w, m.k = D.k;
+	if (m.n_minimizers > 0xffffffffll) { // the table stores the first position of a minimizer as uint32 (like the build path)
+		ctx->err = "gd_index_load_mmi: more than 2^32 minimizers in one index part";
+		return GD_ERR_ARG;
+	}
 	if (m.n_seq <= 0 || (int64_t)D.S.size() != m.s_words) {
 		ctx->err = "gd_index_load_mmi: the file has no sequences (index dumped with MM_I_NO_SEQ?)";
 		return GD_ERR_ARG;

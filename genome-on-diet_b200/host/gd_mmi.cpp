@@ -94,6 +94,9 @@ extern "C" int gd_mmi_write(const char *path, int w, int k, int bucket_bits, int
 	if (!path || n_seq < 0 || n_keys < 0 || (n_keys > 0 && (!keys || !counts || !positions))) return GD_ERR_ARG;
 	int b = bucket_bits;
 	if (k * 2 < b) b = k * 2; // mm_idx_init, index.c:48
+	// mm_idx_dump writes S iff !(flag & MM_I_NO_SEQ) (index.c:515) and mm_idx_load reads it by the same test: keep the two in step
+	if (S) flag &= ~0x2;
+	else flag |= 0x2;
 	FILE *fp = fopen(path, "wb");
 	if (!fp) return GD_ERR_ARG;
 	const uint32_t hdr[5] = {(uint32_t)w, (uint32_t)k, (uint32_t)b, (uint32_t)n_seq, (uint32_t)flag};
@@ -181,6 +184,10 @@ int gd_mmi_parse(const char *path, GdMmiData &D)
 		return GD_ERR_ARG;
 	}
 	D.w = (int)x[0], D.k = (int)x[1], D.b = (int)x[2], D.flag = (int)x[4];
+	if (D.k < 1 || D.k > 28 || D.w < 1 || D.w > 255 || D.b < 0 || D.b > 28 || D.b > 2 * D.k) { // a corrupt header must not size an allocation
+		fclose(fp);
+		return GD_ERR_ARG;
+	}
 	uint64_t sum_len = 0;
 	for (uint32_t i = 0; ok && i < x[3]; ++i) {
 		uint8_t l = 0;

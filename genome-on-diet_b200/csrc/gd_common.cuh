@@ -69,10 +69,6 @@ GD_DEV uint64_t brev64(uint64_t x) { return __brevll(x); }
 GD_DEV void fence() { __threadfence(); }
 template <class T> GD_DEV T ld_volatile(const T *p) { return *(const volatile T *)p; }
 template <class T> GD_DEV void st_volatile(T *p, T v) { *(volatile T *)p = v; }
-GD_DEV double bits_to_double(uint64_t b) { return __longlong_as_double((long long)b); }
-GD_DEV uint64_t double_to_bits(double d) { return (uint64_t)__double_as_longlong(d); }
-GD_DEV double dmin(double a, double b) { return fmin(a, b); } // DMNMX
-GD_DEV double dmax(double a, double b) { return fmax(a, b); }
 #else
 // ---- emulation (tests/emu/simt_emu.h supplies the scheduler-backed collectives) ----
 GD_DEV uint32_t vadd2(uint32_t a, uint32_t b)
@@ -157,20 +153,6 @@ template <class T> GD_DEV T ld_volatile(const T *p)
 	return *p;
 }
 template <class T> GD_DEV void st_volatile(T *p, T v) { *p = v; }
-GD_DEV double bits_to_double(uint64_t b)
-{
-	double d;
-	memcpy(&d, &b, 8);
-	return d;
-}
-GD_DEV uint64_t double_to_bits(double d)
-{
-	uint64_t b;
-	memcpy(&b, &d, 8);
-	return b;
-}
-GD_DEV double dmin(double a, double b) { return a < b ? a : b; }
-GD_DEV double dmax(double a, double b) { return a > b ? a : b; }
 #endif
 
 GD_DEV int imin(int a, int b) { return a < b ? a : b; }

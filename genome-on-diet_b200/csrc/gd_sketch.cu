@@ -14,13 +14,12 @@ gd_ctx *gd_thread_ctx();
 // --------------------------------------------------------------------------------------------
 // kernels
 // --------------------------------------------------------------------------------------------
-// F52: k <= 22, the records fit 52 bits and the window minima / maxima run on the FP64 pipe (SkX<true>)
-template <int THREADS, bool F52>
+template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 32) gd_sketch_tile_kernel(const SketchParams S, SketchBatch B)
 {
 	extern __shared__ __align__(16) uint8_t gd_sk_smem[];
 	if (B.tile_base) B.ntiles = B.tile_base[B.njobs];
-	sketch_tile_body<THREADS, F52>(S, B, (SketchSmem<THREADS> *)gd_sk_smem);
+	sketch_tile_body<THREADS>(S, B, (SketchSmem<THREADS> *)gd_sk_smem);
 }
 
 // jobs for index-build sketching: one per sequence, shift 0
@@ -225,11 +224,9 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 	GD_CUDA_OK(ctx, cudaMemsetAsync(ctx->sk_state.p, 0, (size_t)ntiles_bound * 8 + 64, s));
 	B.status = (unsigned long long *)ctx->sk_state.p;
 	B.ticket = (int32_t *)((char *)ctx->sk_state.p + (size_t)ntiles_bound * 8);
-	static const bool f52_on = !(getenv("GDIET_SK_F52") && atoi(getenv("GDIET_SK_F52")) == 0); // (developer switch for A/B timing)
-	const bool f52 = f52_on && S.k <= 22;
 	if (small) {
 		typedef SketchSmem<32> SM;
-		auto kern = f52 ? gd_sketch_tile_kernel<32, true> : gd_sketch_tile_kernel<32, false>;
+		auto kern = gd_sketch_tile_kernel<32>;
 		int occ = 0;
 		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, sizeof(SM)));
 		int blocks = (int)std::min<int64_t>(ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));
@@ -237,7 +234,7 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 		kern<<<std::max(blocks, 1), 32, sizeof(SM), s>>>(S, B);
 	} else {
 		typedef SketchSmem<256> SM;
-		auto kern = f52 ? gd_sketch_tile_kernel<256, true> : gd_sketch_tile_kernel<256, false>;
+		auto kern = gd_sketch_tile_kernel<256>;
 		int occ = 0;
 		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, sizeof(SM)));
 		int blocks = (int)std::min<int64_t>(ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));

@@ -55,41 +55,16 @@ struct SketchBatch {
 };
 
 GD_DEV uint64_t sk_hash64(uint64_t key, uint64_t mask)
-{ // GDiet-ShortReads/sketch.c:25-34.  The shift-and-add stages are multiplications by constants modulo 2^64
-  // (~key + (key << 21) = key * (2^21 - 1) - 1; key + (key << 3) + (key << 8) = key * 265; ... * 21; ... * (2^31 + 1)): a 64 x 32-bit
-  // product is two IMADs on the FMA pipe where the shifts and 64-bit adds were eight instructions on the integer pipe.
-	key = (key * 0x1fffffull - 1ull) & mask;
+{ // GDiet-ShortReads/sketch.c:25-34
+	key = (~key + (key << 21)) & mask;
 	key = key ^ key >> 24;
-	key = (key * 265ull) & mask;
+	key = ((key + (key << 3)) + (key << 8)) & mask;
 	key = key ^ key >> 14;
-	key = (key * 21ull) & mask;
+	key = ((key + (key << 2)) + (key << 4)) & mask;
 	key = key ^ key >> 28;
-	key = (key * 0x80000001ull) & mask;
+	key = (key + (key << 31)) & mask;
 	return key;
 }
-
-// Window minima / maxima compare 64-bit records X = hash << 8 | k.  For k <= 22 they are below 2^52, and 2^52 + X is an
-// exactly representable double whose order is X's order: with the bits 0x4330000000000000 | X the minima and maxima are
-// one DMNMX each (FP64 pipe) instead of a two-instruction 64-bit compare and two selects on the integer pipe.
-template <bool F52> struct SkX;
-template <> struct SkX<false> {
-	typedef uint64_t T;
-	static GD_MEM T enc(uint64_t x) { return x; }
-	static GD_MEM uint64_t dec(T v) { return v; }
-	static GD_MEM T maxv() { return 0xffffffffffffffffull; }
-	static GD_MEM T zero() { return 0; }
-	static GD_MEM T mn(T a, T b) { return a < b ? a : b; }
-	static GD_MEM T mx(T a, T b) { return a > b ? a : b; }
-};
-template <> struct SkX<true> {
-	typedef double T;
-	static GD_MEM T enc(uint64_t x) { return bits_to_double(0x4330000000000000ull | x); }
-	static GD_MEM uint64_t dec(T v) { return double_to_bits(v) & 0x000fffffffffffffull; }
-	static GD_MEM T maxv() { return bits_to_double(0x433fffffffffffffull); }
-	static GD_MEM T zero() { return bits_to_double(0x4330000000000000ull); }
-	static GD_MEM T mn(T a, T b) { return dmin(a, b); }
-	static GD_MEM T mx(T a, T b) { return dmax(a, b); }
-};
 
 GD_DEV int sk_nt4(unsigned c)
 { // seq_nt4_table, GDiet-ShortReads/sketch.c:11-18, branch-free: A/a C/c G/g T/t U/u -> 0 1 2 3 3, bytes 0..3 map to
@@ -153,12 +128,9 @@ GD_DEV uint64_t sk_bits64(const uint32_t *wds, int bit)
 GD_DEV uint64_t sk_min64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 GD_DEV uint64_t sk_max64(uint64_t a, uint64_t b) { return a > b ? a : b; }
 
-template <int THREADS, bool F52>
+template <int THREADS>
 GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, SketchSmem<THREADS> *sm)
 {
-	typedef SkX<F52> XV;
-	typedef typename XV::T xt;
-	xt *const SUF = (xt *)sm->SUF, *const PREM = (xt *)sm->PREM;
 	const int NP = THREADS * 8;
 	const int tid = thread_idx(), lane = tid & 31, wid = tid >> 5;
 	const int w = S.w, k = S.k, full_run = w + k - 1;
@@ -201,7 +173,7 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 		// A job whose sparsified sequence is shorter than one full window run (w+k-1) cannot emit anything -- the cropped
 		// shift-0 job of mm_sketch2 on a 150 bp read is 15 bases long -- so its tile goes straight to the (empty) output scan.
 		uint32_t real[8], zbits = 0, emit = 0;
-		xt X[8];
+		uint64_t X[8];
 		int cnt = 0;
 		if (dl >= full_run) {
 		// ---- phase 0: stage the original bytes the tile touches, [real(first position), real(last position)] ----
@@ -281,10 +253,10 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 				rv = (rv >> 2) | (3ull ^ c) << (2 * (k - 1));
 				if (nmask >> p & 1) lastn = sp;
 				const int run = sp - lastn;
-				xt x = XV::maxv();
+				uint64_t x = GD_SK_MAXU64;
 				if (run >= k && fw != rv) {
 					const int z = fw < rv ? 0 : 1;
-					x = XV::enc(sk_hash64(z ? rv : fw, S.mask) << 8 | (uint64_t)k);
+					x = sk_hash64(z ? rv : fw, S.mask) << 8 | (uint64_t)k;
 					zbits |= (uint32_t)z << p;
 				}
 				if (run >= full_run) fullbits |= 1u << p;
@@ -296,75 +268,75 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 		if (w >= 9) {
 			// ---- phase 3: minimum of every full window ending at e = s0+p.  The window starts in an earlier
 			// chunk (w-1 >= 8): own prefix minimum, whole chunks in between, suffix minimum of the first chunk ----
-			xt pre[8], M[8];
+			uint64_t pre[8], M[8];
 			{
-				xt suf = XV::maxv(), pr = XV::maxv();
+				uint64_t suf = GD_SK_MAXU64, pr = GD_SK_MAXU64;
 #pragma unroll
-				for (int p = 7; p >= 0; --p) suf = XV::mn(suf, X[p]), SUF[p * THREADS + tid] = suf;
+				for (int p = 7; p >= 0; --p) suf = sk_min64(suf, X[p]), sm->SUF[p * THREADS + tid] = suf;
 #pragma unroll
-				for (int p = 0; p < 8; ++p) pr = XV::mn(pr, X[p]), pre[p] = pr;
+				for (int p = 0; p < 8; ++p) pr = sk_min64(pr, X[p]), pre[p] = pr;
 			}
 			sync_block();
 #pragma unroll
 			for (int p = 0; p < 8; ++p) {
 				const int a = s0 + p - (w - 1); // first position of the window
-				xt m = XV::zero();              // zero = "no full window ends here" (X >= 1 always)
+				uint64_t m = 0;                 // 0 = "no full window ends here" (X >= 1 always)
 				if ((fullbits >> p & 1) && a >= 0) {
 					const int ta = a >> 3;
-					m = XV::mn(pre[p], SUF[(a & 7) * THREADS + ta]);
+					m = sk_min64(pre[p], sm->SUF[(a & 7) * THREADS + ta]);
 #pragma unroll 1
-					for (int c = ta + 1; c < tid; ++c) m = XV::mn(m, SUF[c]); // SUF[0][c] = minimum of chunk c
-					if (m == XV::maxv()) m = XV::zero();
+					for (int c = ta + 1; c < tid; ++c) m = sk_min64(m, sm->SUF[c]); // SUF[0][c] = minimum of chunk c
+					if (m == GD_SK_MAXU64) m = 0;
 				}
 				M[p] = m;
 			}
 			// ---- phase 4: X(i) is emitted iff it equals the largest full-window minimum among the windows that
 			// contain i, i.e. the maximum of M over [i, i+w-1]: own suffix maximum, whole chunks, prefix maximum ----
-			xt sufm[8];
+			uint64_t sufm[8];
 			{
-				xt pm = XV::zero(), sx = XV::zero();
+				uint64_t pm = 0, sx = 0;
 #pragma unroll
-				for (int p = 0; p < 8; ++p) pm = XV::mx(pm, M[p]), PREM[p * THREADS + tid] = pm;
+				for (int p = 0; p < 8; ++p) pm = sk_max64(pm, M[p]), sm->PREM[p * THREADS + tid] = pm;
 #pragma unroll
-				for (int p = 7; p >= 0; --p) sx = XV::mx(sx, M[p]), sufm[p] = sx;
+				for (int p = 7; p >= 0; --p) sx = sk_max64(sx, M[p]), sufm[p] = sx;
 			}
 			sync_block();
 #pragma unroll
 			for (int p = 0; p < 8; ++p) {
 				const int sp = s0 + p;
-				if (sp >= HL && sp < HL + S.TP && B0 + sp < dl && X[p] != XV::maxv()) {
+				if (sp >= HL && sp < HL + S.TP && B0 + sp < dl && X[p] != GD_SK_MAXU64) {
 					const int b = sp + w - 1, tb = b >> 3; // last position of the last window; b < NP in the emit range
-					xt mx = XV::mx(sufm[p], PREM[(b & 7) * THREADS + tb]);
+					uint64_t mx = sk_max64(sufm[p], sm->PREM[(b & 7) * THREADS + tb]);
 #pragma unroll 1
-					for (int c = tid + 1; c < tb; ++c) mx = XV::mx(mx, PREM[7 * THREADS + c]); // PREM[7][c] = maximum of chunk c
+					for (int c = tid + 1; c < tb; ++c) mx = sk_max64(mx, sm->PREM[7 * THREADS + c]); // PREM[7][c] = maximum of chunk c
 					if (mx == X[p]) emit |= 1u << p, ++cnt;
 				}
 			}
 		} else {
 			// ---- small windows (w <= 8): direct scans over X and M in shared memory ----
 #pragma unroll
-			for (int p = 0; p < 8; ++p) SUF[p * THREADS + tid] = X[p];
+			for (int p = 0; p < 8; ++p) sm->SUF[p * THREADS + tid] = X[p];
 			sync_block();
 #pragma unroll
 			for (int p = 0; p < 8; ++p) {
 				const int sp = s0 + p;
-				xt m = XV::zero();
+				uint64_t m = 0;
 				if ((fullbits >> p & 1) && sp >= w - 1) {
-					m = XV::maxv();
+					m = GD_SK_MAXU64;
 #pragma unroll 1
-					for (int d = 0; d < w; ++d) m = XV::mn(m, SUF[((sp - d) & 7) * THREADS + ((sp - d) >> 3)]);
-					if (m == XV::maxv()) m = XV::zero();
+					for (int d = 0; d < w; ++d) m = sk_min64(m, sm->SUF[((sp - d) & 7) * THREADS + ((sp - d) >> 3)]);
+					if (m == GD_SK_MAXU64) m = 0;
 				}
-				PREM[p * THREADS + tid] = m;
+				sm->PREM[p * THREADS + tid] = m;
 			}
 			sync_block();
 #pragma unroll
 			for (int p = 0; p < 8; ++p) {
 				const int sp = s0 + p;
-				if (sp >= HL && sp < HL + S.TP && B0 + sp < dl && X[p] != XV::maxv()) {
-					xt mx = XV::zero();
+				if (sp >= HL && sp < HL + S.TP && B0 + sp < dl && X[p] != GD_SK_MAXU64) {
+					uint64_t mx = 0;
 #pragma unroll 1
-					for (int d = 0; d < w; ++d) mx = XV::mx(mx, PREM[((sp + d) & 7) * THREADS + ((sp + d) >> 3)]);
+					for (int d = 0; d < w; ++d) mx = sk_max64(mx, sm->PREM[((sp + d) & 7) * THREADS + ((sp + d) >> 3)]);
 					if (mx == X[p]) emit |= 1u << p, ++cnt;
 				}
 			}
@@ -435,7 +407,7 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 				const long long dst = obase + o;
 				if (fixed ? (local + o < B.fixed_stride) : (dst < B.out_cap)) {
 					const uint64_t y = (uint64_t)J.rid << 32 | (uint64_t)real[p] << 1 | (uint64_t)(zbits >> p & 1);
-					B.out[2 * dst] = XV::dec(X[p]);
+					B.out[2 * dst] = X[p];
 					B.out[2 * dst + 1] = y;
 				}
 				++o;

@@ -9,13 +9,9 @@ using namespace gd;
 
 template <int THREADS>
 static void run_tiles(const SketchParams &S, SketchBatch &B, int grid)
-{ // like the launcher: k <= 22 takes the 52-bit (FP64 minima) variant
-	if (S.k <= 22)
-		emu::launch(grid, THREADS, sizeof(SketchSmem<THREADS>),
-		            [&]() { sketch_tile_body<THREADS, true>(S, B, (SketchSmem<THREADS> *)emu::smem()); });
-	else
-		emu::launch(grid, THREADS, sizeof(SketchSmem<THREADS>),
-		            [&]() { sketch_tile_body<THREADS, false>(S, B, (SketchSmem<THREADS> *)emu::smem()); });
+{
+	emu::launch(grid, THREADS, sizeof(SketchSmem<THREADS>),
+	            [&]() { sketch_tile_body<THREADS>(S, B, (SketchSmem<THREADS> *)emu::smem()); });
 }
 
 // jobs: n x {seq_off, len, shift, rid}; small != 0 forces the one-tile-per-job configuration

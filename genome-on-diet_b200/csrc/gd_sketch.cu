@@ -15,7 +15,7 @@ gd_ctx *gd_thread_ctx();
 // kernels
 // --------------------------------------------------------------------------------------------
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 32) gd_sketch_tile_kernel(const SketchParams S, SketchBatch B)
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) gd_sketch_tile_kernel(const SketchParams S, SketchBatch B)
 {
 	extern __shared__ __align__(16) uint8_t gd_sk_smem[];
 	if (B.tile_base) B.ntiles = B.tile_base[B.njobs];
@@ -200,6 +200,11 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 	// short reads: one warp-sized tile (256 positions) per job; otherwise 2048-position tiles
 	const int tp_small = sk_tile_emit(256, S.w, S.k);
 	const bool small = tp_small > 0 && max_dl <= tp_small;
+	// threads per block of the large tiles (8 positions per thread): smaller blocks wait less at the five block-wide barriers
+	// of a tile, larger ones spend less of a tile on its halo of 3w+k-4 positions (developer switch GDIET_SK_THREADS = 64 | 128 | 256)
+	static const int big_env = getenv("GDIET_SK_THREADS") ? atoi(getenv("GDIET_SK_THREADS")) : 0;
+	int big_threads = (big_env == 64 || big_env == 128 || big_env == 256) ? big_env : 256;
+	while (big_threads < 256 && sk_tile_emit(big_threads * 8, S.w, S.k) < big_threads * 4) big_threads *= 2; // wide windows need wide tiles
 	int64_t ntiles_bound;
 	if (fixed_stride > 0 && !small) {
 		ctx->err = "sketch: fixed-stride output needs one tile per job";
@@ -211,7 +216,7 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 		B.ntiles = njobs, B.tile_base = nullptr;
 		B.fixed_stride = fixed_stride, B.out_cnt = d_out_cnt;
 	} else {
-		S.TP = sk_tile_emit(2048, S.w, S.k), S.one_tile_per_job = 0;
+		S.TP = sk_tile_emit(big_threads * 8, S.w, S.k), S.one_tile_per_job = 0;
 		ntiles_bound = pos_total / S.TP + 2 * (int64_t)njobs + 2;
 		if ((rc = gd_reserve(ctx, ctx->sk_misc, (size_t)(njobs + 1) * 8))) return rc;
 		int64_t *tb = (int64_t *)ctx->sk_misc.p;
@@ -224,23 +229,19 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 	GD_CUDA_OK(ctx, cudaMemsetAsync(ctx->sk_state.p, 0, (size_t)ntiles_bound * 8 + 64, s));
 	B.status = (unsigned long long *)ctx->sk_state.p;
 	B.ticket = (int32_t *)((char *)ctx->sk_state.p + (size_t)ntiles_bound * 8);
-	if (small) {
-		typedef SketchSmem<32> SM;
-		auto kern = gd_sketch_tile_kernel<32>;
+	auto launch = [&](auto kern, int threads, size_t smem) -> int {
 		int occ = 0;
-		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, sizeof(SM)));
+		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
 		int blocks = (int)std::min<int64_t>(ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));
 		GdKernelTimer tm(ctx, &ctx->tm_sketch);
-		kern<<<std::max(blocks, 1), 32, sizeof(SM), s>>>(S, B);
-	} else {
-		typedef SketchSmem<256> SM;
-		auto kern = gd_sketch_tile_kernel<256>;
-		int occ = 0;
-		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, sizeof(SM)));
-		int blocks = (int)std::min<int64_t>(ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));
-		GdKernelTimer tm(ctx, &ctx->tm_sketch);
-		kern<<<std::max(blocks, 1), 256, sizeof(SM), s>>>(S, B);
-	}
+		kern<<<std::max(blocks, 1), threads, smem, s>>>(S, B);
+		return GD_OK;
+	};
+	if (small) rc = launch(gd_sketch_tile_kernel<32>, 32, sizeof(SketchSmem<32>));
+	else if (big_threads == 64) rc = launch(gd_sketch_tile_kernel<64>, 64, sizeof(SketchSmem<64>));
+	else if (big_threads == 128) rc = launch(gd_sketch_tile_kernel<128>, 128, sizeof(SketchSmem<128>));
+	else rc = launch(gd_sketch_tile_kernel<256>, 256, sizeof(SketchSmem<256>));
+	if (rc) return rc;
 	ctx->stat_launches++;
 	GD_CUDA_OK(ctx, cudaGetLastError());
 	return GD_OK;

@@ -111,7 +111,17 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
            "reads_per_s": n_reads / min(pipe_s, res["map_s"] + res["sam_s"]), "reads_per_s_map_only": n_reads / res["map_s"],
            "reads_per_s_map_only_two_contexts": (n_reads / dual_s) if dual_s else None,
            "candidates": int(coff[-1]), "exact": int(cand["exact"].sum()), "gpu_launches_per_batch": res["launches"], "host_cores": cores}
+    # ---- reads in, SAM text out with the post-DP stage on the device (gd_sr_map_sam_batch)
+    for it in range(3):
+        t0 = time.perf_counter()
+        pieces = ctx.sr_map_sam_batch(idx, names, off, lens, buf, qual, opt, post, ["chr1"], join=False)
+        dev_s = time.perf_counter() - t0
+    import ctypes
+    out["map_sam_device_s"] = round(dev_s, 4)
+    out["reads_per_s_device_sam"] = n_reads / dev_s
+    out["device_sam_identical_to_host_stage"] = b"".join(ctypes.string_at(a, l) for a, l in pieces) == sam
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_avx_sr")
+    batched_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_cuda_batched_sr")
     if run_ref and os.path.exists(ref_bin):
         import maplib
         tmp = tempfile.mkdtemp(prefix="gdref_")
@@ -130,6 +140,23 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
                             "threads": cores, "profile_thread_seconds": {k: round(int(v) * 1e-9, 3) for k, v in prof.items()}}
         out["sam_identical"] = got == want
         out["sam_lines"] = len(want)
+        # ---- the batched C host (INTEGRATION.md level 2): the same program with genome-on-diet_b200/host/gd_batched_host.c in place
+        # of map.c's pipeline -- FASTQ parsing, mapping on the GPU, SAM file written, one process, same flags
+        if os.path.exists(batched_bin):
+            samb = os.path.join(tmp, "batched.sam")
+            t0 = time.perf_counter()
+            pb = subprocess.run([batched_bin, "-t", str(cores), "-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200",
+                                 "-o", samb, fa, fq], capture_output=True, text=True, env=dict(os.environ, GDIET_GPUS="1"))
+            wall_b = time.perf_counter() - t0
+            mm = re.search(r"\[M::mm_map_file_frag\] (\d+) reads, \d+ bases in ([0-9.]+) s", pb.stderr)
+            ix = re.search(r"\[PROFILING\] indexing time: (\d+) ns", pb.stderr)
+            gotb = [l for l in open(samb).read().splitlines() if not l.startswith("@")] if pb.returncode == 0 else []
+            out["batched_host"] = {"binary": "oracle/_ref/GDiet_cuda_batched_sr (unmodified reference sources + gd_batched_host.c)", "returncode": pb.returncode,
+                                   "wall_s": round(wall_b, 3), "indexing_s": round(int(ix.group(1)) * 1e-9, 3) if ix else None,
+                                   "map_pipeline_s": float(mm.group(2)) if mm else None,
+                                   "reads_per_s_pipeline": (n_reads / float(mm.group(2))) if mm else None,
+                                   "note": "map_pipeline_s = FASTQ parse + GPU mapping + SAM file write under kt_pipeline (after the index and the CUDA context exist)",
+                                   "sam_identical": gotb == want}
         if got != want:
             bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
             out["sam_first_diff"] = [got[bad[0]][:300], want[bad[0]][:300]] if bad else ["length", "%d vs %d" % (len(got), len(want))]

@@ -1383,6 +1383,19 @@ extern "C" int gd_sr_map_sam_batch(gd_ctx *ctx, const gd_index *idx, int n, cons
 	job.gen = (int)(ctx->sam_calls++ & 1);
 	ctx->h_sam_used[job.gen] = 0;
 	if (ctx->peer) ctx->peer->h_sam_used[job.gen] = 0;
+	{ // size this generation's pinned text buffers once, from an estimate of the text (2 x bases + ~200 B per read, half of it per
+	  // lane): page-locking memory is slow, and a buffer that grows is page-locked again and again and copied each time
+		size_t est = 0;
+		for (int i = 0; i < n; ++i) est += 2 * (size_t)len[i] + 200;
+		est = est / 2 + est / 8 + ((size_t)1 << 20);
+		for (gd_ctx *c : {ctx, ctx->peer}) {
+			if (!c || c->h_sam[job.gen].cap >= est) continue;
+			if (c->h_sam[job.gen].p) cudaFreeHost(c->h_sam[job.gen].p);
+			c->h_sam[job.gen].p = nullptr, c->h_sam[job.gen].cap = 0;
+			if (cudaHostAlloc(&c->h_sam[job.gen].p, est, cudaHostAllocPortable) == cudaSuccess) c->h_sam[job.gen].cap = est;
+			else cudaGetLastError(), c->h_sam[job.gen].p = nullptr; // (sam_stage grows it on demand)
+		}
+	}
 	const int slice = std::max(32768, std::min(1 << 18, (n + 3) / 4));
 	std::vector<std::pair<int, int>> slices;
 	for (int b = 0; b < n; b += slice) slices.push_back({b, std::min(slice, n - b)});

@@ -63,10 +63,42 @@ typedef struct {
 	int64_t *off;
 	int32_t *len;
 	char *buf, *qual; /* flattened reads / qualities */
+	size_t buf_cap, qual_cap;
 	char **parts;
 	size_t *part_len;
 	int n_parts;
 } gdh_step_t;
+
+/* Page-locking memory is slow (tens of ms per 100 MB): the read buffers of the mini-batches in flight (at most three under
+ * kt_pipeline, a read and a quality buffer each) come from a small pool instead of a fresh gd_pinned_alloc per batch. */
+#include <pthread.h>
+static struct {
+	pthread_mutex_t mu;
+	char *p[8];
+	size_t cap[8];
+} gdh_pool = {PTHREAD_MUTEX_INITIALIZER, {0}, {0}};
+static char *gdh_buf_get(size_t bytes, size_t *cap)
+{
+	int i, best = -1;
+	char *p = 0;
+	pthread_mutex_lock(&gdh_pool.mu);
+	for (i = 0; i < 8; ++i)
+		if (gdh_pool.p[i] && gdh_pool.cap[i] >= bytes && (best < 0 || gdh_pool.cap[i] < gdh_pool.cap[best])) best = i;
+	if (best >= 0) p = gdh_pool.p[best], *cap = gdh_pool.cap[best], gdh_pool.p[best] = 0;
+	pthread_mutex_unlock(&gdh_pool.mu);
+	if (p) return p;
+	*cap = bytes + bytes / 4 + 4096;
+	return (char *)gd_pinned_alloc(*cap);
+}
+static void gdh_buf_put(char *p, size_t cap)
+{
+	int i;
+	pthread_mutex_lock(&gdh_pool.mu);
+	for (i = 0; i < 8 && p; ++i)
+		if (!gdh_pool.p[i]) gdh_pool.p[i] = p, gdh_pool.cap[i] = cap, p = 0;
+	pthread_mutex_unlock(&gdh_pool.mu);
+	if (p) gd_pinned_free(p);
+}
 
 static void gdh_die(const char *what)
 {
@@ -91,10 +123,11 @@ static void *gdh_worker(void *shared, int step, void *in)
 		for (i = 0; i < s->n; ++i) s->seq[i].rid = p->n_processed++, tot += s->seq[i].l_seq;
 		s->names = (const char **)malloc(sizeof(char *) * s->n);
 		s->off = (int64_t *)malloc(sizeof(int64_t) * s->n), s->len = (int32_t *)malloc(sizeof(int32_t) * s->n);
-		s->buf = (char *)gd_pinned_alloc((size_t)tot + 16); /* pinned: the upload of step 1 runs at PCIe speed */
-		s->qual = with_qual ? (char *)malloc((size_t)tot + 16) : 0;
+		s->buf = gdh_buf_get((size_t)tot + 16, &s->buf_cap); /* pinned: the upload of step 1 runs at PCIe speed */
+		if (!s->buf) gdh_die("out of page-locked memory");
+		s->qual = with_qual ? gdh_buf_get((size_t)tot + 16, &s->qual_cap) : 0;
 		for (i = 0; i < s->n && s->qual; ++i)
-			if (!s->seq[i].qual) free(s->qual), s->qual = 0; /* FASTA input: no quality strings ('*' in SAM) */
+			if (!s->seq[i].qual) gdh_buf_put(s->qual, s->qual_cap), s->qual = 0; /* FASTA input: no quality strings ('*' in SAM) */
 		for (i = 0; i < s->n; ++i) {
 			const mm_bseq1_t *t = &s->seq[i];
 			if (i > 0 && mm_qname_same(s->seq[i - 1].name, t->name))
@@ -132,8 +165,9 @@ static void *gdh_worker(void *shared, int step, void *in)
 			if (s->seq[i].qual) free(s->seq[i].qual);
 			if (s->seq[i].comment) free(s->seq[i].comment);
 		}
-		free(s->seq), free(s->names), free(s->off), free(s->len), free(s->qual);
-		gd_pinned_free(s->buf);
+		free(s->seq), free(s->names), free(s->off), free(s->len);
+		if (s->qual) gdh_buf_put(s->qual, s->qual_cap);
+		gdh_buf_put(s->buf, s->buf_cap);
 		p->t_write += realtime() - t0;
 		if (mm_verbose >= 3)
 			fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", __func__, realtime() - mm_realtime0,

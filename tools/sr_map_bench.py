@@ -146,7 +146,7 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
             samb = os.path.join(tmp, "batched.sam")
             t0 = time.perf_counter()
             pb = subprocess.run([batched_bin, "-t", str(cores), "-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200",
-                                 "-o", samb, fa, fq], capture_output=True, text=True, env=dict(os.environ, GDIET_GPUS="1"))
+                                 "-K", "30M", "-o", samb, fa, fq], capture_output=True, text=True, env=dict(os.environ, GDIET_GPUS="1"))
             wall_b = time.perf_counter() - t0
             mm = re.search(r"\[M::mm_map_file_frag\] (\d+) reads, \d+ bases in ([0-9.]+) s", pb.stderr)
             ix = re.search(r"\[PROFILING\] indexing time: (\d+) ns", pb.stderr)
@@ -155,6 +155,7 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
                                    "wall_s": round(wall_b, 3), "indexing_s": round(int(ix.group(1)) * 1e-9, 3) if ix else None,
                                    "map_pipeline_s": float(mm.group(2)) if mm else None,
                                    "reads_per_s_pipeline": (n_reads / float(mm.group(2))) if mm else None,
+                                   "summary": (re.search(r"\[M::mm_map_file_frag\] .*", pb.stderr) or [""])[0][:300], "mini_batch": "-K 30M (200 k reads per batch)",
                                    "note": "map_pipeline_s = FASTQ parse + GPU mapping + SAM file write under kt_pipeline (after the index and the CUDA context exist)",
                                    "sam_identical": gotb == want}
         if got != want:

@@ -24,7 +24,11 @@
  * input, PAF output, --split-prefix, --cs / --MD / --eqx / -y, splice mode, and (long reads) --sort=radix|heap.
  */
 #include <errno.h>
+#include <fcntl.h>
 #include <stdio.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 #include "minimap.h"
@@ -36,7 +40,10 @@
 typedef struct {
 	const mm_mapopt_t *opt;
 	const mm_idx_t *mi;
-	mm_bseq_file_t *fp;
+	mm_bseq_file_t *fp;        /* the reference's reader (gzip / stdin input) */
+	const char *map;           /* or: the whole plain-text file mapped read-only, parsed in place */
+	size_t map_len, map_pos;
+	int map_last;              /* kseq's last_char: a header character already consumed (0 = none) */
 	int n_threads, n_processed;
 	int64_t mini_batch_size;
 	gd_multi *gm;
@@ -60,6 +67,7 @@ typedef struct {
 	int n;
 	mm_bseq1_t *seq;
 	const char **names;
+	char *name_blob;           /* mapped-file reader: the names of the batch, NUL separated */
 	int64_t *off;
 	int32_t *len;
 	char *buf, *qual; /* flattened reads / qualities */
@@ -106,6 +114,159 @@ static void gdh_die(const char *what)
 	exit(1);
 }
 
+/* ---- mini-batch reader over a memory-mapped plain-text FASTA/FASTQ file -------------------------------------------------
+ * The reference reads with kseq.h over gzread: three mallocs and a byte-wise state machine per record, about 1.2 M short
+ * reads/s on one thread -- which bounds the whole pipeline once mapping runs on a GPU.  This reader applies the SAME rules
+ * (kseq_read, kseq.h:193-232; mm_bseq_read3, bseq.c:73-113; kseq2bseq, bseq.c:58-71) to the mapped file with memchr and
+ * writes bases and qualities straight into the pinned mini-batch buffers:
+ *   a record starts at the next '>' or '@'; the name ends at the first white space; sequence lines run until a line that
+ *   starts with '>', '+' or '@' (empty lines skipped, a trailing CR dropped); after '+' quality lines are appended until
+ *   they are as long as the sequence; U/u become T/t; a batch ends with the record that brings it to >= -K bases.
+ * A record whose quality length differs from its sequence length ends the batch like kseq's -2 (with the reference's
+ * warning).  gzip or stdin input keeps the reference's reader. */
+typedef struct {
+	char *p;
+	size_t n, cap;
+} gdh_str_t;
+static void gdh_str_need(gdh_str_t *s, size_t extra, int pinned, size_t *pool_cap)
+{
+	if (s->n + extra + 1 <= s->cap) return;
+	{
+		size_t want = (s->n + extra + 1) * 2;
+		char *np;
+		if (pinned) {
+			size_t cap2 = 0;
+			np = gdh_buf_get(want, &cap2);
+			if (!np) { fprintf(stderr, "[gdiet_cuda] ERROR: out of page-locked memory\n"); exit(1); }
+			if (s->n) memcpy(np, s->p, s->n);
+			if (s->p) gdh_buf_put(s->p, *pool_cap);
+			*pool_cap = cap2, s->cap = cap2;
+		} else {
+			np = (char *)realloc(s->p, want);
+			s->cap = want;
+		}
+		s->p = np;
+	}
+}
+static inline int gdh_isspace(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+/* appends the rest of the current line (without the newline, a trailing CR dropped when the string is longer than one
+ * character: ks_getuntil2, kseq.h:146) to dst; returns 0 at end of file with nothing read */
+static int gdh_line(gdh_pipeline_t *p, gdh_str_t *dst, size_t base, int pinned, size_t *pool_cap)
+{ /* base: where the current record's string starts in dst (the CR rule looks at that string's length) */
+	const char *b = p->map + p->map_pos, *e;
+	size_t l;
+	if (p->map_pos >= p->map_len) return 0;
+	e = (const char *)memchr(b, '\n', p->map_len - p->map_pos);
+	l = e ? (size_t)(e - b) : p->map_len - p->map_pos;
+	gdh_str_need(dst, l, pinned, pool_cap);
+	memcpy(dst->p + dst->n, b, l), dst->n += l;
+	p->map_pos += l + (e ? 1 : 0);
+	if (dst->n - base > 1 && dst->p[dst->n - 1] == '\r') --dst->n;
+	return 1;
+}
+
+static int gdh_read_mapped(gdh_pipeline_t *p, gdh_step_t *s, int with_qual)
+{
+	gdh_str_t seq = {0, 0, 0}, qual = {0, 0, 0}, names = {0, 0, 0};
+	size_t seq_pool = 0, qual_pool = 0, dummy = 0;
+	int64_t size = 0, *off = 0;
+	int32_t *len = 0;
+	int64_t *noff = 0;
+	int n = 0, m = 0, any_qual = 0, all_qual = 1, bad = 0, i;
+	const size_t guess = (size_t)(p->mini_batch_size < (int64_t)(p->map_len - p->map_pos) ? p->mini_batch_size : (int64_t)(p->map_len - p->map_pos)) + 65536;
+	gdh_str_need(&seq, guess, 1, &seq_pool);
+	if (with_qual) gdh_str_need(&qual, guess, 1, &qual_pool);
+	while (1) {
+		size_t l0, q0;
+		int c = p->map_last;
+		if (c == 0) { /* jump to the next header line (kseq.h:197-201) */
+			const char *b = p->map + p->map_pos, *e = p->map + p->map_len;
+			while (b < e && *b != '>' && *b != '@') ++b;
+			if (b >= e) { p->map_pos = p->map_len; break; }
+			p->map_pos = (size_t)(b - p->map) + 1;
+		}
+		p->map_last = 0;
+		if (p->map_pos >= p->map_len) break; /* ks_getuntil on an exhausted stream: normal exit */
+		if (n == m) {
+			m = m ? m * 2 : 4096;
+			off = (int64_t *)realloc(off, sizeof(int64_t) * m), len = (int32_t *)realloc(len, sizeof(int32_t) * m);
+			noff = (int64_t *)realloc(noff, sizeof(int64_t) * (m + 1));
+		}
+		{ /* name: up to the first white space; the rest of the header line is the comment (not copied) */
+			const char *b = p->map + p->map_pos, *e = p->map + p->map_len, *q = b;
+			while (q < e && !gdh_isspace((unsigned char)*q)) ++q;
+			if (q == b) fprintf(stderr, "[WARNING]\033[1;31m empty sequence name in the input.\033[0m\n");
+			gdh_str_need(&names, (size_t)(q - b) + 1, 0, &dummy);
+			noff[n] = (int64_t)names.n;
+			memcpy(names.p + names.n, b, (size_t)(q - b)), names.n += (size_t)(q - b), names.p[names.n++] = 0;
+			p->map_pos = (size_t)(q - p->map) + (q < e ? 1 : 0);
+			if (q < e && *q != '\n') { /* skip the comment */
+				const char *nl = (const char *)memchr(q, '\n', (size_t)(e - q));
+				p->map_pos = nl ? (size_t)(nl - p->map) + 1 : p->map_len;
+			}
+		}
+		l0 = seq.n, q0 = qual.n;
+		c = -1;
+		while (p->map_pos < p->map_len) { /* sequence lines (kseq.h:209-213) */
+			c = (unsigned char)p->map[p->map_pos++];
+			if (c == '>' || c == '+' || c == '@') break;
+			if (c == '\n') { c = -1; continue; }
+			--p->map_pos; /* the character belongs to the line: first character + rest of the line, as kseq appends them */
+			gdh_line(p, &seq, l0, 1, &seq_pool);
+			c = -1;
+		}
+		if (c == '>' || c == '@') p->map_last = c;
+		off[n] = (int64_t)l0, len[n] = (int32_t)(seq.n - l0);
+		for (i = 0; i < len[n]; ++i) /* U -> T, bseq.c:66-68 */
+			if (seq.p[l0 + i] == 'u' || seq.p[l0 + i] == 'U') --seq.p[l0 + i];
+		if (c == '+') { /* FASTQ: skip the '+' line, then quality lines until they cover the sequence (kseq.h:226-230) */
+			const char *nl = p->map_pos < p->map_len ? (const char *)memchr(p->map + p->map_pos, '\n', p->map_len - p->map_pos) : 0;
+			gdh_str_t *qd = with_qual ? &qual : 0;
+			gdh_str_t scratch = {0, 0, 0};
+			if (!nl) { bad = 1; break; } /* no quality string */
+			p->map_pos = (size_t)(nl - p->map) + 1;
+			if (!qd) qd = &scratch;
+			{
+				const size_t qstart = qd->n;
+				while (gdh_line(p, qd, qstart, qd == &qual, &qual_pool) && qd->n - qstart < (size_t)len[n]);
+				if (qd->n - qstart != (size_t)len[n]) bad = 1;
+			}
+			free(scratch.p);
+			if (bad) break;
+			any_qual = 1;
+		} else all_qual = 0;
+		if (with_qual && qual.n - q0 != (size_t)len[n]) { /* a FASTA record among FASTQ ones: keep the two buffers in step */
+			gdh_str_need(&qual, (size_t)len[n], 1, &qual_pool);
+			qual.n = q0 + (size_t)len[n];
+		}
+		size += len[n], ++n;
+		if (size >= p->mini_batch_size) break;
+	}
+	if (bad) { /* kseq returns -2: the record is dropped, the batch ends here, the next call resynchronises on a header */
+		seq.n = n < m && off ? (size_t)off[n] : seq.n;
+		if (n) fprintf(stderr, "[WARNING]\033[1;31m failed to parse the FASTA/FASTQ record next to '%s'. Continue anyway.\033[0m\n", names.p + noff[n - 1]);
+		else fprintf(stderr, "[WARNING]\033[1;31m failed to parse the first FASTA/FASTQ record. Continue anyway.\033[0m\n");
+		p->map_last = 0;
+	}
+	if (n == 0) {
+		if (seq.p) gdh_buf_put(seq.p, seq_pool);
+		if (qual.p) gdh_buf_put(qual.p, qual_pool);
+		free(names.p), free(off), free(len), free(noff);
+		return 0;
+	}
+	s->n = n, s->off = off, s->len = len, s->buf = seq.p, s->buf_cap = seq_pool;
+	s->name_blob = names.p;
+	s->names = (const char **)malloc(sizeof(char *) * n);
+	for (i = 0; i < n; ++i) s->names[i] = names.p + noff[i];
+	free(noff);
+	if (with_qual && any_qual && all_qual) s->qual = qual.p, s->qual_cap = qual_pool; /* mm_write_sam3 prints '*' for reads without qualities */
+	else if (qual.p) gdh_buf_put(qual.p, qual_pool);
+	if (with_qual && any_qual && !all_qual)
+		gdh_die("a mini-batch mixes FASTA and FASTQ records: not covered by the batched device path");
+	return n;
+}
+
 static void *gdh_worker(void *shared, int step, void *in)
 {
 	gdh_pipeline_t *p = (gdh_pipeline_t *)shared;
@@ -115,6 +276,19 @@ static void *gdh_worker(void *shared, int step, void *in)
 		gdh_step_t *s = (gdh_step_t *)calloc(1, sizeof(gdh_step_t));
 		int i;
 		int64_t tot = 0, o = 0;
+		if (p->map) {
+			if (!gdh_read_mapped(p, s, with_qual)) {
+				free(s);
+				return 0;
+			}
+			for (i = 0; i < s->n; ++i) {
+				tot += s->len[i];
+				if (i > 0 && mm_qname_same(s->names[i - 1], s->names[i]))
+					gdh_die("paired / multi-segment reads are not covered by the batched device path (use the GDiet_cuda build)");
+			}
+			p->n_processed += s->n, p->n_reads += s->n, p->n_bases += tot, p->t_read += realtime() - t0;
+			return s;
+		}
 		s->seq = mm_bseq_read3(p->fp, p->mini_batch_size, with_qual, 0, 0, &s->n);
 		if (!s->seq) {
 			free(s);
@@ -160,12 +334,12 @@ static void *gdh_worker(void *shared, int step, void *in)
 		for (i = 0; i < s->n_parts; ++i) /* (the pieces belong to the gd_multi handle: valid until the batch after the next one) */
 			if (s->part_len[i]) mm_err_fwrite(s->parts[i], 1, s->part_len[i], stdout);
 		gd_free(s->parts), gd_free(s->part_len);
-		for (i = 0; i < s->n; ++i) {
+		for (i = 0; s->seq && i < s->n; ++i) {
 			free(s->seq[i].seq), free(s->seq[i].name);
 			if (s->seq[i].qual) free(s->seq[i].qual);
 			if (s->seq[i].comment) free(s->seq[i].comment);
 		}
-		free(s->seq), free(s->names), free(s->off), free(s->len);
+		free(s->seq), free(s->names), free(s->off), free(s->len), free(s->name_blob);
 		if (s->qual) gdh_buf_put(s->qual, s->qual_cap);
 		gdh_buf_put(s->buf, s->buf_cap);
 		p->t_write += realtime() - t0;
@@ -225,7 +399,23 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 	if (n_segs < 1) return -1;
 	gdh_refuse_uncovered(opt, n_segs);
 	memset(&pl, 0, sizeof(pl));
-	if ((pl.fp = mm_bseq_open(fn[0])) == 0) {
+	{ /* a regular, uncompressed file is mapped and parsed in place; gzip / stdin input goes through the reference's reader */
+		struct stat st;
+		int fd = strcmp(fn[0], "-") ? open(fn[0], O_RDONLY) : -1;
+		if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 2 && !getenv("GDIET_REF_READER")) {
+			void *mp = mmap(0, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+			if (mp != MAP_FAILED) {
+				const unsigned char *u = (const unsigned char *)mp;
+				if (u[0] == 0x1f && u[1] == 0x8b) munmap(mp, (size_t)st.st_size); /* gzip */
+				else {
+					madvise(mp, (size_t)st.st_size, MADV_SEQUENTIAL);
+					pl.map = (const char *)mp, pl.map_len = (size_t)st.st_size;
+				}
+			}
+		}
+		if (fd >= 0) close(fd);
+	}
+	if (!pl.map && (pl.fp = mm_bseq_open(fn[0])) == 0) {
 		if (mm_verbose >= 1) fprintf(stderr, "ERROR: failed to open file '%s': %s\n", fn[0], strerror(errno));
 		return -1;
 	}
@@ -265,6 +455,7 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 	gd_multi_destroy(pl.gm);
 	gd_pinned_free(pl.ref);
 	free(pl.ref_names), free(pl.ref_off), free(pl.ref_len);
-	mm_bseq_close(pl.fp);
+	if (pl.fp) mm_bseq_close(pl.fp);
+	if (pl.map) munmap((void *)pl.map, pl.map_len);
 	return 0;
 }

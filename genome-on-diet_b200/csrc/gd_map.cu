@@ -1380,7 +1380,11 @@ extern "C" int gd_sr_map_sam_batch(gd_ctx *ctx, const gd_index *idx, int n, cons
 		job.rnoff.push_back((int32_t)job.rblob.size());
 		job.rblob += seq_names[i], job.rblob.push_back('\0');
 	}
+	const bool prof = getenv("GD_MAP_PROFILE") != nullptr;
+	const double tp0 = prof ? SrPhaseClock::now() : 0;
 	job.gen = (int)(ctx->sam_calls++ & 1);
+	const int slice = std::max(32768, std::min(1 << 18, (n + 3) / 4));
+	if (n > slice && ctx->opt_map_lanes != 1 && !ctx->peer) gd_init(ctx->device, &ctx->peer); // the second lane exists before its text buffers are sized
 	ctx->h_sam_used[job.gen] = 0;
 	if (ctx->peer) ctx->peer->h_sam_used[job.gen] = 0;
 	{ // size this generation's pinned text buffers once, from an estimate of the text (2 x bases + ~200 B per read, half of it per
@@ -1396,14 +1400,15 @@ extern "C" int gd_sr_map_sam_batch(gd_ctx *ctx, const gd_index *idx, int n, cons
 			else cudaGetLastError(), c->h_sam[job.gen].p = nullptr; // (sam_stage grows it on demand)
 		}
 	}
-	const int slice = std::max(32768, std::min(1 << 18, (n + 3) / 4));
 	std::vector<std::pair<int, int>> slices;
 	for (int b = 0; b < n; b += slice) slices.push_back({b, std::min(slice, n - b)});
 	job.pieces.assign(slices.size(), SamJob::Piece{0, 0, 0});
 	int64_t cb = 0, gb = 0;
 	const bool had_peer = ctx->peer != nullptr;
+	const double tp1 = prof ? SrPhaseClock::now() : 0;
 	int rc = run_slices(ctx, idx, slices, off, len, seq, o, nullptr, nullptr, nullptr, 0, nullptr, 0, &cb, &gb, &job);
-	if (!had_peer && ctx->peer) (void)0; // (a peer created during this call started with h_sam_used == 0)
+	(void)had_peer; // (a peer created during this call started with h_sam_used == 0)
+	if (prof) fprintf(stderr, "[gd_sr_map_sam_batch] %d reads, %zu slices: prologue %.2f ms, slices %.2f ms\n", n, slices.size(), tp1 - tp0, SrPhaseClock::now() - tp1);
 	if (rc) return rc;
 	const size_t np = job.pieces.size();
 	*parts = (char **)malloc((np + 1) * sizeof(char *)), *part_len = (size_t *)malloc((np + 1) * sizeof(size_t));

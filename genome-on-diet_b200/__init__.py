@@ -131,14 +131,21 @@ def lr_post_options(preset="map-hifi", n_threads=0, **kw):
     return o
 
 
-def lr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, contigs, opt):
-    """gd_lr_sam_batch. Returns (SAM bytes, sam_off[n+1], needs_stitch[n])."""
-    L = load()
-    n = len(lens)
+def flat_ref(contigs):
+    """(ref_off, ref_len, one concatenated buffer) of a list of contigs: what a C host already holds; pass it as ref= to the
+    *_sam_batch wrappers so that a timed call does not concatenate gigabytes of reference again"""
     ref_len = np.array([len(c) for c in contigs], np.int32)
     ref_off = np.zeros(len(contigs), np.int64)
     ref_off[1:] = np.cumsum(ref_len[:-1].astype(np.int64))
     ref = np.concatenate([np.ascontiguousarray(c, np.uint8) for c in contigs]) if len(contigs) > 1 else np.ascontiguousarray(contigs[0], np.uint8)
+    return ref_off, ref_len, ref
+
+
+def lr_sam_batch(names, off, lens, seq, qual, cand_off, cand, cigar, seq_names, contigs, opt, ref=None):
+    """gd_lr_sam_batch. Returns (SAM bytes, sam_off[n+1], needs_stitch[n])."""
+    L = load()
+    n = len(lens)
+    ref_off, ref_len, ref = ref if ref is not None else flat_ref(contigs)
     n_arr, s_arr = _cstr_array(names), _cstr_array(seq_names)
     out, out_len = C.c_void_p(), C.c_size_t(0)
     cand = np.ascontiguousarray(cand) if len(cand) else np.zeros(1, SR_CAND_DTYPE)

@@ -49,6 +49,8 @@ GD_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 	return r;
 }
 GD_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+// acc + (signed byte `byte` of v): one IDP.4A (dot product with a one-hot byte vector) instead of a sign-extending PRMT and an add
+GD_DEV uint32_t add_sbyte(uint32_t acc, uint32_t v, int byte) { return (uint32_t)__dp4a((int)v, (int)(1u << (8 * byte)), (int)acc); }
 GD_DEV uint32_t shfl_idx(uint32_t mask, uint32_t v, int src, int width) { return __shfl_sync(mask, v, src, width); }
 GD_DEV uint32_t shfl_xor(uint32_t mask, uint32_t v, int lm, int width) { return __shfl_xor_sync(mask, v, lm, width); }
 GD_DEV uint32_t shfl_up(uint32_t mask, uint32_t v, int d, int width) { return __shfl_up_sync(mask, v, d, width); }
@@ -114,6 +116,7 @@ GD_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh)
 	uint64_t v = ((uint64_t)hi << 32) | lo;
 	return (uint32_t)(v >> (sh & 31));
 }
+GD_DEV uint32_t add_sbyte(uint32_t acc, uint32_t v, int byte) { return acc + (uint32_t)(int32_t)(int8_t)(v >> (8 * byte)); }
 GD_DEV uint32_t shfl_idx(uint32_t mask, uint32_t v, int src, int width) { return emu::shfl_idx(mask, v, src, width); }
 GD_DEV uint32_t shfl_xor(uint32_t mask, uint32_t v, int lm, int width) { return emu::shfl_xor(mask, v, lm, width); }
 GD_DEV uint32_t shfl_up(uint32_t mask, uint32_t v, int d, int width) { return emu::shfl_up(mask, v, d, width); }

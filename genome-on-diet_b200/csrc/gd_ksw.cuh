@@ -57,6 +57,12 @@
 #ifndef GD_KSW_P32
 #define GD_KSW_P32 0 // 1: backtrack rows are pitched and padded to whole 32-byte sectors (no partial-sector writes -> no read-modify-write in HBM)
 #endif
+#ifndef GD_KSW_DP4A
+#define GD_KSW_DP4A 1 // 1: exact mode adds v to the 32-bit H column with IDP.4A (one instruction, not on the integer pipe) instead of PRMT + IADD
+#endif
+#ifndef GD_KSW_NOTIMAD
+#define GD_KSW_NOTIMAD 0 // 1: the three bitwise complements of a cell pair are IMADs (x * -1 - 1) instead of LOP3s
+#endif
 #ifndef GD_KSW_HOTMEM
 #define GD_KSW_HOTMEM 1 // 1: sweep constants come from device memory (stay in registers) instead of the constant bank
 #endif
@@ -147,9 +153,17 @@ GD_DEV void cell2(const CT &C, uint32_t s, uint32_t xt1, uint32_t vt1, uint32_t 
 	zt = vmax3(vmax3(s, a, b), a2, b2);
 	const uint32_t z = vmin2(zt & 0xff00ff00u, C.MCH16);
 	const uint32_t z1 = fma_add(z, C.ONE, 0x00010001u); // low bytes of z are 0: no carry between the halves
+#if GD_KSW_NOTIMAD
+	// ~x = x * (-1) - 1 (mod 2^32): an IMAD on the FMA pipe instead of a LOP3 on the integer pipe; C.ONE is opaque to the compiler
+	const uint32_t m1 = 0u - C.ONE;
+	u_new = vadd2(z1, fma_add(vt1, m1, 0xffffffffu)); // z - v[t-1]
+	v_new = vadd2(z1, fma_add(ut, m1, 0xffffffffu));  // z - u[t]
+	const uint32_t nz = fma_add(z, m1, 0xffffffffu);
+#else
 	u_new = vadd2(z1, ~vt1); // z - v[t-1]
 	v_new = vadd2(z1, ~ut);  // z - u[t]
 	const uint32_t nz = ~z;
+#endif
 	const uint32_t nzq = vadd2(nz, C.Q1), nzq2 = vadd2(nz, C.Q21); // q - z, q2 - z
 	uint32_t ma, mb, ma2, mb2;
 	if (!RIGHT) { // continuation iff value > 0  <=> high byte of max(value,0) >= 1
@@ -714,10 +728,17 @@ GD_DEV void ksw_warp_body(const KswConsts &C, const KswBatch &B, uint8_t *smem_w
 				}
 				if (EXACT) { // H[t] += v[t] on the whole chunk; columns outside [st0,en1) hold sentinels
 					uint4 ha = in.ha, hb = in.hb;
+#if GD_KSW_DP4A
+					ha.x = add_sbyte(ha.x, v0, 1), hb.x = add_sbyte(hb.x, v0, 3); // v of columns (c, c+4) sits in bytes 1 and 3
+					ha.y = add_sbyte(ha.y, v1, 1), hb.y = add_sbyte(hb.y, v1, 3);
+					ha.z = add_sbyte(ha.z, v2, 1), hb.z = add_sbyte(hb.z, v2, 3);
+					ha.w = add_sbyte(ha.w, v3, 1), hb.w = add_sbyte(hb.w, v3, 3);
+#else
 					ha.x += prmt(v0, 0, 0x9991), hb.x += prmt(v0, 0, 0xbbb3);
 					ha.y += prmt(v1, 0, 0x9991), hb.y += prmt(v1, 0, 0xbbb3);
 					ha.z += prmt(v2, 0, 0x9991), hb.z += prmt(v2, 0, 0xbbb3);
 					ha.w += prmt(v3, 0, 0x9991), hb.w += prmt(v3, 0, 0xbbb3);
+#endif
 					// keys: (score relative to the previous row's maximum) << 16 | priority of the column
 					const uint32_t nb2 = (uint32_t)((0 - d) & 0xffff) * 0x10001u;
 					const uint32_t p0 = vadd2(pk0, nb2), p1 = vadd2(pk1, nb2), p2 = vadd2(pk2, nb2), p3 = vadd2(pk3, nb2);

@@ -1321,8 +1321,10 @@ extern "C" int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const in
 		ctx->err = "gd_sr_map_batch: bad argument";
 		return GD_ERR_ARG;
 	}
-	if (o->af_max_loc < 1 || o->af_max_loc > SR_MAX_LOC || o->W < 1 || o->W > 63 || idx->device != ctx->device) {
-		ctx->err = "gd_sr_map_batch: need 1 <= af_max_loc <= 32, 1 <= W <= 63 and an index built on this device";
+	if (o->af_max_loc < 1 || o->af_max_loc > SR_MAX_LOC || o->W < 2 || o->W > 63 || idx->device != ctx->device) {
+		// (W = 1, `-Z 1`: the reference's mm_sketch2 then walks one shift more than the pattern has, sketch.c:2143-2225, and maps a
+		// shifted copy of the read; that path is not pinned against the reference, so it is refused rather than answered differently)
+		ctx->err = "gd_sr_map_batch: need 1 <= af_max_loc <= 32, 2 <= W <= 63 and an index built on this device";
 		return GD_ERR_ARG;
 	}
 	cand_off[0] = 0;
@@ -1363,8 +1365,8 @@ extern "C" int gd_sr_map_sam_batch(gd_ctx *ctx, const gd_index *idx, int n, cons
 		ctx->err = "gd_sr_map_sam_batch: bad argument";
 		return GD_ERR_ARG;
 	}
-	if (o->af_max_loc < 1 || o->af_max_loc > SR_MAX_LOC || o->W < 1 || o->W > 63 || idx->device != ctx->device) {
-		ctx->err = "gd_sr_map_sam_batch: need 1 <= af_max_loc <= 32, 1 <= W <= 63 and an index built on this device";
+	if (o->af_max_loc < 1 || o->af_max_loc > SR_MAX_LOC || o->W < 2 || o->W > 63 || idx->device != ctx->device) {
+		ctx->err = "gd_sr_map_sam_batch: need 1 <= af_max_loc <= 32, 2 <= W <= 63 and an index built on this device";
 		return GD_ERR_ARG;
 	}
 	if (!post->is_sr) {
@@ -1430,8 +1432,8 @@ extern "C" int gd_lr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const in
 		ctx->err = "gd_lr_map_batch: bad argument";
 		return GD_ERR_ARG;
 	}
-	if (lr->vt_nb_loc < 1 || lr->vt_nb_loc > SR_MAX_LOC || lr->W < 1 || lr->W > 63 || idx->device != ctx->device) {
-		ctx->err = "gd_lr_map_batch: need 1 <= vt_nb_loc <= 32, 1 <= W <= 63 and an index built on this device";
+	if (lr->vt_nb_loc < 1 || lr->vt_nb_loc > SR_MAX_LOC || lr->W < 2 || lr->W > 63 || idx->device != ctx->device) {
+		ctx->err = "gd_lr_map_batch: need 1 <= vt_nb_loc <= 32, 2 <= W <= 63 (pattern length 1 is not pinned: refused) and an index built on this device";
 		return GD_ERR_ARG;
 	}
 	gd_sr_opt_t o; // the fields both trees share

@@ -402,6 +402,10 @@ extern "C" int gd_sketch_reads_batch(gd_ctx *ctx, int n, const int64_t *off, con
 	}
 	if (s2_off) s2_off[0] = 0;
 	if (s3_off) s3_off[0] = 0;
+	if (W == 1) { // mm_sketch2 with a pattern of length 1 walks one shift more than the pattern has (sketch.c:2143-2225): not pinned -> refused
+		ctx->err = "gd_sketch_reads_batch: pattern length W = 1 is not supported (the reference's mm_sketch2 is not pinned for it)";
+		return GD_ERR_ARG;
+	}
 	if (n == 0) return GD_OK;
 	cudaSetDevice(ctx->device);
 	SketchParams S;

@@ -355,7 +355,7 @@ static void gdh_options(gdh_pipeline_t *p)
 {
 	const mm_mapopt_t *opt = p->opt;
 	memset(&p->mo, 0, sizeof(p->mo)), memset(&p->po, 0, sizeof(p->po));
-	if (opt->pattern_len < 1 || opt->pattern_len > 63) gdh_die("pattern length (-W) must be 1..63");
+	if (opt->pattern_len < 2 || opt->pattern_len > 63) gdh_die("pattern length (-W) must be 2..63 on the batched device path");
 	p->mo.W = opt->pattern_len, memcpy(p->mo.Z, opt->pattern, opt->pattern_len);
 	p->mo.max_seeds = opt->max_seeds, p->mo.frag_mode = !!(opt->flag & MM_F_FRAG_MODE), p->mo.max_frag_len = opt->max_frag_len;
 	p->mo.mid_occ = opt->mid_occ, p->mo.max_max_occ = opt->max_max_occ, p->mo.occ_dist = opt->occ_dist, p->mo.q_occ_frac = opt->q_occ_frac;

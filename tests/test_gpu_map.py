@@ -429,6 +429,21 @@ def test_device_sam_stage_equals_host_stage(ctx, seed, okw, pkw, ragged):
     idx.close()
 
 
+def test_pattern_of_length_one_is_refused(ctx):
+    """W = 1: mm_sketch2 walks one shift more than the pattern has (sketch.c:2143-2225); not pinned against the reference, so
+    the mapping stage and the read-sketch entry refuse it instead of answering differently"""
+    import gdiet_b200 as gd
+    contigs, reads = maplib.make_dataset(seed=1, n_reads=8)
+    idx = ctx.index_build(contigs, 11, 21, "1")
+    off, lens, buf = flat_reads(reads)
+    o = maplib.sr_opt(Z="1")
+    with pytest.raises(gd.GdietError):
+        ctx.sr_map_batch(idx, off, lens, buf, o)
+    with pytest.raises(gd.GdietError):
+        ctx.sketch_reads_batch(off, lens, buf, 11, 21, "1", 0.1, 800)
+    idx.close()
+
+
 def test_device_sam_stage_unmappable_and_empty(ctx):
     import gdiet_b200 as gd
     contigs, _ = maplib.make_dataset(seed=1, n_reads=1)

@@ -69,7 +69,7 @@ def main():
         Z = "".join(rng.choice(["0", "1"], W))
         if "1" not in Z:
             Z = "1" + Z[1:]
-        reads_mode = bool(rng.random() < 0.5)
+        reads_mode = bool(rng.random() < 0.5) and W > 1  # (the reads entry refuses W = 1: mm_sketch2 is not pinned for it)
         max_len = int(rng.choice([30, 150, 400, 3000] if reads_mode else [30, 400, 3000, 20000]))
         seqs = [s for s in draw_seqs(rng, 24, max_len)]
         if reads_mode:

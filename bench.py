@@ -13,9 +13,15 @@ CIGARs produced.  A "step" is one pass of the hot path (pack -> DP -> traceback)
              16x2 add rate measured live by gd_ubench; plus the backtrack bytes against MEASURED_PEAKS
   cpu_baseline  the unmodified reference (oracle/_ref, ksw_extd2_avx512 when the host has AVX-512) on all
              host threads over a bounded sample of the same pairs
+  parity     every pair of the step compared with the reference's result (all ksw_extz_t fields + CIGARs)
+  extra      zdrop_subset (30 % edits: Z-drop fires; parity on every pair), sketch (mm_sketch of 200 Mbp: kernel,
+             host-buffer end to end, read sketching, CPU baselines), sr_map / lr_map (configs 1 / 3 end to end at N = 1,
+             SAM compared with GDiet_avx run in the same process, the batched C host binary), map_strong (10 M reads
+             against a 3.1 Gbp index, STRONG-scaled over the ranks: index built on rank 0, NCCL broadcast, read
+             shards, SAM text made on the devices and gathered in input order, hash compared with one GPU)
 
 `--impl reference` times only that CPU reference arm.  With torchrun (N>1) every rank maps its own
-1M-pair shard (weak scaling, no data-path collective); time is the max over ranks.
+1M-pair shard for the headline metric (weak scaling, no data-path collective); time is the max over ranks.
 """
 import argparse
 import json

@@ -81,6 +81,24 @@ def test_narrow_band_random_scoring_sweep(ctx, oracle):
     assert pairs == 3600 and redone >= 1
 
 
+def test_random_scoring_flags_bands_sweep(ctx, oracle):
+    """bounded slice of tools/ksw_fuzz.py: scoring values, flags, bands, lengths and gang sizes drawn at random (the other
+    parity tests fix them to the reference's presets); 40 rounds of 120 pairs"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLD), "..", "tools"))
+    import ksw_fuzz as kf
+    rng = np.random.default_rng(2026)
+    for it in range(40):
+        sc = kf.draw_scoring(rng)
+        flag = int(rng.choice(kf.FLAGS))
+        P = synth.ragged_pairs(120, seed=int(rng.integers(1 << 30)), max_len=int(rng.choice([8, 40, 150, 300, 700])))
+        w = rng.choice([-1, 0, 1, 3, 5, 10, 20, 33, 37, 64, 100, 150, 400, 1000], P["n"]).astype(np.int32)
+        ctx.set_option("ksw_group", int(rng.choice([0, 4, 8, 16, 32])))
+        ez, coff, cig = ctx.ksw_extd2_batch(P["qlen"], P["qoff"], P["qbuf"], P["tlen"], P["toff"], P["tbuf"], params(sc, flag), w=w)
+        assert_batch_equal(ez, coff, cig if not (flag & 1) else None, oracle_batch(oracle, P, w, sc, flag), what="round %d flag %#x %s" % (it, flag, sc))
+    ctx.set_option("ksw_group", 0)
+
+
 @pytest.mark.parametrize("flag", [0x08, 0x00, 0x18, 0x40, 0x48, 0xc2, 0x01, 0x0a, 0x42, 0x80])
 def test_ragged_pairs_vs_oracle(ctx, oracle, flag):
     P = synth.ragged_pairs(300, seed=100 + flag, max_len=260)

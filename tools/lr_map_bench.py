@@ -131,6 +131,22 @@ def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
             else:
                 diff += 1
         out["sam"] = {"reads_identical": same, "reads_different": diff, "reads_left_to_host_stitching": int(stitch.sum())}
+        # ---- the batched C host of the long-read tree (INTEGRATION.md level 2): FASTQ file in, SAM file out, same flags
+        batched_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_cuda_batched_lr")
+        if os.path.exists(batched_bin):
+            samb = os.path.join(tmp, "batched.sam")
+            t0 = time.perf_counter()
+            pb = subprocess.run([batched_bin, "-t", str(cores)] + flags + ["-o", samb, fa, fq], capture_output=True, text=True,
+                                env=dict(os.environ, GDIET_GPUS="1"))
+            wall_b = time.perf_counter() - t0
+            mm = re.search(r"\[M::mm_map_file_frag\] (\d+) reads, \d+ bases in ([0-9.]+) s.*", pb.stderr)
+            ix = re.search(r"\[PROFILING\] indexing time: (\d+) ns", pb.stderr)
+            strip = lambda path: [l for l in open(path).read().splitlines() if not l.startswith("@PG")]
+            out["batched_host"] = {"binary": "oracle/_ref/GDiet_cuda_batched_lr (unmodified reference sources + gd_batched_host.c)", "returncode": pb.returncode,
+                                   "wall_s": round(wall_b, 2), "indexing_s": round(int(ix.group(1)) * 1e-9, 2) if ix else None,
+                                   "map_pipeline_s": float(mm.group(2)) if mm else None,
+                                   "reads_per_s_pipeline": (n_reads / float(mm.group(2))) if mm else None, "summary": mm.group(0)[:300] if mm else pb.stderr[-300:],
+                                   "sam_file_identical": pb.returncode == 0 and strip(samb) == strip(os.path.join(tmp, "out.sam"))}
         out["reference"] = {"wall_s": round(wall, 2), "indexing_s": round(t_idx, 2), "reads_per_s": n_reads / max(wall - t_idx, 1e-9), "threads": cores,
                             "profile_thread_seconds": {kk: round(int(v) * 1e-9, 2) for kk, v in prof.items()}}
     idx.close()

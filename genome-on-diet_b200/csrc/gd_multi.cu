@@ -21,6 +21,15 @@
 #include <vector>
 #include <string.h>
 
+// long-read shards are cut into device slices of at least this many reads and bases (gd_multi_lr_map_sam; the
+// environment variables GDIET_LR_SLICE_READS / GDIET_LR_SLICE_BASES override them, for tests)
+#ifndef GD_LR_SLICE_READS
+#define GD_LR_SLICE_READS 4096
+#endif
+#ifndef GD_LR_SLICE_BASES
+#define GD_LR_SLICE_BASES (48ll << 20)
+#endif
+
 // the few NCCL declarations used (nccl.h, NCCL 2.x ABI) -- resolved with dlsym
 typedef struct ncclComm *gd_ncclComm_t;
 typedef int (*nccl_comm_init_all_t)(gd_ncclComm_t *, int, const int *);
@@ -53,6 +62,7 @@ struct gd_multi {
 		std::vector<uint32_t> cigar;
 		int64_t n_cand = 0, n_cig = 0;
 		int rc = GD_OK;
+		bool host_err = false; // rc came from the host SAM stage, not from the device
 	};
 	std::vector<Shard> sh;
 	// text pieces of the *_map_sam calls belong to the handle: host-made (malloc'ed) pieces are freed two calls later, like the
@@ -358,7 +368,7 @@ static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int
 	auto work = [&](int j) {
 		gd_multi::Shard &S = m->sh[j];
 		const int b = cut[j], cnt = cut[j + 1] - cut[j];
-		S.rc = GD_OK;
+		S.rc = GD_OK, S.host_err = false;
 		if (cnt == 0) return;
 		cudaSetDevice(m->ctx[j]->device);
 		if (!lr) { // short reads: reads in, text out
@@ -373,23 +383,59 @@ static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int
 			}
 			return;
 		}
-		S.cand_off.assign((size_t)cnt + 1, 0);
-		if (S.cand.size() < (size_t)cnt * 2) S.cand.resize((size_t)cnt * 2);
-		if (S.cigar.size() < (size_t)cnt * 16) S.cigar.resize((size_t)cnt * 16);
-		for (int attempt = 0; attempt < 2; ++attempt) {
-			int64_t ncig = 0;
-			S.rc = map_fn(m->ctx[j], m->idx[j], cnt, off + b, len + b, seq, opt, S.cand_off.data(), S.cand.data(), (int64_t)S.cand.size(),
-			              S.cigar.data(), (int64_t)S.cigar.size(), &ncig);
-			S.n_cand = S.cand_off[cnt], S.n_cig = ncig;
-			if (S.rc != GD_ERR_CAPACITY) break;
-			S.cand.resize((size_t)S.n_cand + 16), S.cigar.resize((size_t)S.n_cig + 16);
+		// Long reads: the shard goes through the device in slices of >= GD_LR_SLICE_READS reads and >= GD_LR_SLICE_BASES bases
+		// (smaller launches leave the DP kernel short of pairs), and the host SAM stage of slice s runs on its own thread while
+		// slice s+1 is on the device.  Every slice keeps its own records, so nothing is shared between the two sides.
+		std::vector<int> sc(1, 0);
+		{
+			const char *e1 = getenv("GDIET_LR_SLICE_READS"), *e2 = getenv("GDIET_LR_SLICE_BASES");
+			const int64_t min_reads = e1 ? std::max(1ll, atoll(e1)) : GD_LR_SLICE_READS, min_bases = e2 ? atoll(e2) : GD_LR_SLICE_BASES;
+			int64_t bases = 0, total = 0;
+			for (int i = 0; i < cnt; ++i) total += len[b + i];
+			for (int i = 0, r = 0; i < cnt; ++i) {
+				bases += len[b + i], total -= len[b + i], ++r;
+				if (r >= min_reads && bases >= min_bases && cnt - 1 - i >= min_reads && total >= min_bases)
+					sc.push_back(i + 1), bases = 0, r = 0;
+			}
+			sc.push_back(cnt);
 		}
-		if (S.rc) return;
-		char *txt = nullptr;
-		size_t tl = 0;
-		S.rc = gd_lr_sam_batch(cnt, names + b, off + b, len + b, seq, qual, S.cand_off.data(), S.cand.data(), S.cigar.data(), n_seq, seq_names,
-		                       ref_off, ref_len, ref, &po, &txt, &tl, nullptr, nullptr);
-		if (!S.rc) out[j].push_back({txt, tl}), host_made[j].push_back(txt);
+		const int ns = (int)sc.size() - 1;
+		struct Slice {
+			std::vector<int64_t> coff;
+			std::vector<gd_sr_cand_t> cand;
+			std::vector<uint32_t> cig;
+			char *txt = nullptr;
+			size_t tl = 0;
+			int rc = GD_OK;
+			std::thread sam;
+		};
+		std::vector<Slice> sl(ns);
+		for (int s = 0; s < ns && !S.rc; ++s) {
+			Slice &L = sl[s];
+			const int sb = b + sc[s], scnt = sc[s + 1] - sc[s];
+			L.coff.assign((size_t)scnt + 1, 0);
+			L.cand.resize((size_t)scnt * 2), L.cig.resize((size_t)scnt * 16);
+			for (int attempt = 0; attempt < 2; ++attempt) {
+				int64_t ncig = 0;
+				S.rc = map_fn(m->ctx[j], m->idx[j], scnt, off + sb, len + sb, seq, opt, L.coff.data(), L.cand.data(), (int64_t)L.cand.size(),
+				              L.cig.data(), (int64_t)L.cig.size(), &ncig);
+				if (S.rc != GD_ERR_CAPACITY) break;
+				L.cand.resize((size_t)L.coff[scnt] + 16), L.cig.resize((size_t)ncig + 16);
+			}
+			if (S.rc) break;
+			L.sam = std::thread([&, sb, scnt, s]() {
+				Slice &M = sl[s];
+				M.rc = gd_lr_sam_batch(scnt, names + sb, off + sb, len + sb, seq, qual, M.coff.data(), M.cand.data(), M.cig.data(), n_seq,
+				                       seq_names, ref_off, ref_len, ref, &po, &M.txt, &M.tl, nullptr, nullptr);
+			});
+		}
+		for (Slice &L : sl)
+			if (L.sam.joinable()) L.sam.join();
+		for (Slice &L : sl) {
+			if (L.txt) host_made[j].push_back(L.txt); // owned by the handle also on failure, freed two calls on
+			if (!S.rc && L.rc) S.rc = L.rc, S.host_err = true;
+			if (!S.rc && L.txt) out[j].push_back({L.txt, L.tl});
+		}
 	};
 	std::vector<std::thread> th;
 	for (int j = 1; j < G; ++j) th.emplace_back(work, j);
@@ -399,7 +445,8 @@ static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int
 	for (int j = 0; j < G && !rc; ++j)
 		if (m->sh[j].rc) {
 			rc = m->sh[j].rc;
-			m->err = std::string("gd_multi: device ") + std::to_string(m->ctx[j]->device) + ": " + gd_strerror(m->ctx[j]);
+			m->err = m->sh[j].host_err ? std::string("gd_multi: host SAM stage of shard ") + std::to_string(j) + " failed"
+			                           : std::string("gd_multi: device ") + std::to_string(m->ctx[j]->device) + ": " + gd_strerror(m->ctx[j]);
 		}
 	size_t np = 0;
 	for (int j = 0; j < G; ++j) np += out[j].size();

@@ -75,3 +75,28 @@ def test_multi_long_reads_equal_single_device(ctx):
     assert np.array_equal(got[1]["reserved"], want[1]["reserved"])
     M.close()
     idx1.close()
+
+
+def test_multi_long_read_sam_in_slices_equals_one_batch(ctx, monkeypatch):
+    """gd_multi_lr_map_sam cuts a long-read shard into device slices whose host SAM stage overlaps the next slice's mapping;
+    the text of 6 slices equals the single-batch text (device stage + gd_lr_sam_batch on the whole batch)."""
+    contigs, reads = maplib.make_long_dataset(seed=73, read_len=6000, n_reads=50, sv_frac=0.5)
+    off, lens, buf = flat(reads)
+    qual = np.full(len(buf), ord("I"), np.uint8)
+    names = ["r%d" % i for i in range(len(reads))]
+    seq_names = ["chr%d" % (i + 1) for i in range(len(contigs))]
+    o = gd.lr_options("map-hifi", bw=600, mid_occ=50)
+    post = gd.lr_post_options("map-hifi")
+    idx1 = ctx.index_build(contigs, 19, 19, "10")
+    coff, cand, cig = ctx.lr_map_batch(idx1, off, lens, buf, o, cand_cap=8 * len(reads), cigar_cap=1 << 22)
+    want, _, _ = gd.lr_sam_batch(names, off, lens, buf, qual, coff, cand, cig, seq_names, contigs, post)
+    assert len(want) > 50 * 6000
+    M = gd.Multi(1)
+    M.index_bcast(M.ctx(0).index_build(contigs, 19, 19, "10"))
+    whole = M.map_sam(names, off, lens, buf, qual, o, post, seq_names, contigs)
+    monkeypatch.setenv("GDIET_LR_SLICE_READS", "8")
+    monkeypatch.setenv("GDIET_LR_SLICE_BASES", "0")
+    sliced = M.map_sam(names, off, lens, buf, qual, o, post, seq_names, contigs)
+    assert whole == bytes(want) and sliced == bytes(want)
+    M.close()
+    idx1.close()

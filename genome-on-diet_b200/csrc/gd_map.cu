@@ -1459,6 +1459,18 @@ extern "C" int gd_lr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const in
 			slices.push_back({b, m});
 			b += m;
 		}
+		// ... except when one slice is all there is and it is large: its DP would run as several arena-limited launches one
+		// after the other on one lane (15 kbp reads, band 1000: ~60 MB of backtrack per pair, ~1,000 pairs per launch = 7 warps
+		// per SM); two halves on the two lanes keep twice as many pairs in flight
+		if (slices.size() == 1 && n >= 2048) {
+			int64_t total = 0, half = 0;
+			for (int i = 0; i < n; ++i) total += len[i];
+			if (total >= (32ll << 20)) {
+				int m = 0;
+				while (m < n - 1 && half + len[m] <= total / 2) half += len[m], ++m;
+				if (m > 0) slices[0] = {0, m}, slices.push_back({m, n - m});
+			}
+		}
 	}
 	{
 		int rc = run_slices(ctx, idx, slices, off, len, buf, &o, lr, cand_off, cand, cand_cap, cigar, cigar_cap, &cand_base, &cig_base);

@@ -16,8 +16,10 @@
 #include <dlfcn.h>
 #include <unistd.h>
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 #include <string.h>
 
@@ -27,7 +29,7 @@
 #define GD_LR_SLICE_READS 4096
 #endif
 #ifndef GD_LR_SLICE_BASES
-#define GD_LR_SLICE_BASES (48ll << 20)
+#define GD_LR_SLICE_BASES (128ll << 20) // two 64 Mbase slices of gd_lr_map_batch: both of its lanes stay busy
 #endif
 
 // the few NCCL declarations used (nccl.h, NCCL 2.x ABI) -- resolved with dlsym
@@ -272,8 +274,14 @@ static int multi_map(gd_multi *m, int n, const int64_t *off, const int32_t *len,
 		S.cand_off.assign((size_t)cnt + 1, 0);
 		if (cnt == 0) return;
 		cudaSetDevice(m->ctx[j]->device);
+		size_t want_cig = (size_t)cnt * 16;
+		if (std::is_same<OPT, gd_lr_opt_t>::value) { // long reads: CIGARs grow with the bases; an undersized pool maps the shard twice
+			int64_t bases = 0;
+			for (int i = 0; i < cnt; ++i) bases += len[b + i];
+			want_cig = std::max(want_cig, (size_t)std::min<int64_t>(std::max<int64_t>(cigar_cap, 0), bases / 3 + (int64_t)cnt * 64));
+		}
 		if (S.cand.size() < (size_t)cnt * 2) S.cand.resize((size_t)cnt * 2);
-		if (S.cigar.size() < (size_t)cnt * 16) S.cigar.resize((size_t)cnt * 16);
+		if (S.cigar.size() < want_cig) S.cigar.resize(want_cig);
 		for (int attempt = 0; attempt < 2; ++attempt) {
 			int64_t ncig = 0;
 			S.rc = map_fn(m->ctx[j], m->idx[j], cnt, off + b, len + b, buf, opt, S.cand_off.data(), S.cand.data(), (int64_t)S.cand.size(),
@@ -402,31 +410,48 @@ static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int
 		const int ns = (int)sc.size() - 1;
 		struct Slice {
 			std::vector<int64_t> coff;
-			std::vector<gd_sr_cand_t> cand;
-			std::vector<uint32_t> cig;
+			gd_sr_cand_t *cand = nullptr; // malloc'ed, not value-initialised: only the pages the records reach are touched
+			uint32_t *cig = nullptr;
+			int64_t cand_cap = 0, cig_cap = 0;
 			char *txt = nullptr;
 			size_t tl = 0;
 			int rc = GD_OK;
 			std::thread sam;
+			~Slice() { free(cand), free(cig); }
 		};
 		std::vector<Slice> sl(ns);
+		const bool prof = getenv("GD_MAP_PROFILE") != nullptr;
+		auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 		for (int s = 0; s < ns && !S.rc; ++s) {
 			Slice &L = sl[s];
 			const int sb = b + sc[s], scnt = sc[s + 1] - sc[s];
+			const double t0 = now();
 			L.coff.assign((size_t)scnt + 1, 0);
-			L.cand.resize((size_t)scnt * 2), L.cig.resize((size_t)scnt * 16);
+			// a CIGAR of a long read holds up to a few operations per ten bases (8 % error ONT reads: ~0.16 per base); too small a
+			// pool means mapping the slice twice, so start above that
+			int64_t sbases = 0;
+			for (int i = 0; i < scnt; ++i) sbases += len[sb + i];
+			L.cand_cap = (int64_t)scnt * 4 + 64, L.cig_cap = sbases / 3 + (int64_t)scnt * 64 + 1024;
 			for (int attempt = 0; attempt < 2; ++attempt) {
+				free(L.cand), free(L.cig);
+				L.cand = (gd_sr_cand_t *)malloc((size_t)L.cand_cap * sizeof(gd_sr_cand_t)), L.cig = (uint32_t *)malloc((size_t)L.cig_cap * 4);
+				if (!L.cand || !L.cig) {
+					S.rc = GD_ERR_ARG, S.host_err = true;
+					break;
+				}
 				int64_t ncig = 0;
-				S.rc = map_fn(m->ctx[j], m->idx[j], scnt, off + sb, len + sb, seq, opt, L.coff.data(), L.cand.data(), (int64_t)L.cand.size(),
-				              L.cig.data(), (int64_t)L.cig.size(), &ncig);
+				S.rc = map_fn(m->ctx[j], m->idx[j], scnt, off + sb, len + sb, seq, opt, L.coff.data(), L.cand, L.cand_cap, L.cig, L.cig_cap, &ncig);
 				if (S.rc != GD_ERR_CAPACITY) break;
-				L.cand.resize((size_t)L.coff[scnt] + 16), L.cig.resize((size_t)ncig + 16);
+				L.cand_cap = L.coff[scnt] + 16, L.cig_cap = ncig + 16;
 			}
 			if (S.rc) break;
+			if (prof) fprintf(stderr, "[gd_multi] device %d slice %d/%d: %d reads mapped in %.3f s\n", m->ctx[j]->device, s + 1, ns, scnt, now() - t0);
 			L.sam = std::thread([&, sb, scnt, s]() {
 				Slice &M = sl[s];
-				M.rc = gd_lr_sam_batch(scnt, names + sb, off + sb, len + sb, seq, qual, M.coff.data(), M.cand.data(), M.cig.data(), n_seq,
+				const double t1 = now();
+				M.rc = gd_lr_sam_batch(scnt, names + sb, off + sb, len + sb, seq, qual, M.coff.data(), M.cand, M.cig, n_seq,
 				                       seq_names, ref_off, ref_len, ref, &po, &M.txt, &M.tl, nullptr, nullptr);
+				if (prof) fprintf(stderr, "[gd_multi] device %d slice %d/%d: host SAM stage %.3f s (%d threads)\n", m->ctx[j]->device, s + 1, ns, now() - t1, po.n_threads);
 			});
 		}
 		for (Slice &L : sl)

@@ -46,6 +46,8 @@ typedef struct {
 	int map_last;              /* kseq's last_char: a header character already consumed (0 = none) */
 	int n_threads, n_processed;
 	int64_t mini_batch_size;
+	int64_t sub_bases; /* long reads: a mini-batch also ends at >= sub_bases bases and >= sub_reads reads (0: only at -K) */
+	int sub_reads;
 	gd_multi *gm;
 	/* contigs as ASCII (the host stage counts mismatches against them, align.c:259-318) */
 	int n_ref;
@@ -107,6 +109,16 @@ static void gdh_buf_put(char *p, size_t cap)
 	pthread_mutex_unlock(&gdh_pool.mu);
 	if (p) gd_pinned_free(p);
 }
+
+#ifdef GD_HOST_LR /* the long-read host stage reads the qualities on the CPU only: plain memory, nothing to page-lock */
+#define GDH_QUAL_PINNED 0
+static char *gdh_qbuf_get(size_t bytes, size_t *cap) { *cap = bytes; return (char *)malloc(bytes); }
+static void gdh_qbuf_put(char *p, size_t cap) { (void)cap; free(p); }
+#else /* short reads: the device SAM stage reads them over PCIe */
+#define GDH_QUAL_PINNED 1
+#define gdh_qbuf_get gdh_buf_get
+#define gdh_qbuf_put gdh_buf_put
+#endif
 
 static void gdh_die(const char *what)
 {
@@ -174,9 +186,13 @@ static int gdh_read_mapped(gdh_pipeline_t *p, gdh_step_t *s, int with_qual)
 	int32_t *len = 0;
 	int64_t *noff = 0;
 	int n = 0, m = 0, any_qual = 0, all_qual = 1, bad = 0, i;
-	const size_t guess = (size_t)(p->mini_batch_size < (int64_t)(p->map_len - p->map_pos) ? p->mini_batch_size : (int64_t)(p->map_len - p->map_pos)) + 65536;
+	const int64_t left = (int64_t)(p->map_len - p->map_pos);
+	int64_t want = p->mini_batch_size < left ? p->mini_batch_size : left; /* bases of the batch are at most the bytes left in the file */
+	size_t guess;
+	if (p->sub_bases > 0 && p->sub_bases + p->sub_bases / 4 < want) want = p->sub_bases + p->sub_bases / 4; /* the usual end of a long-read batch */
+	guess = (size_t)want + 65536;
 	gdh_str_need(&seq, guess, 1, &seq_pool);
-	if (with_qual) gdh_str_need(&qual, guess, 1, &qual_pool);
+	if (with_qual) gdh_str_need(&qual, guess, GDH_QUAL_PINNED, &qual_pool);
 	while (1) {
 		size_t l0, q0;
 		int c = p->map_last;
@@ -229,7 +245,7 @@ static int gdh_read_mapped(gdh_pipeline_t *p, gdh_step_t *s, int with_qual)
 			if (!qd) qd = &scratch;
 			{
 				const size_t qstart = qd->n;
-				while (gdh_line(p, qd, qstart, qd == &qual, &qual_pool) && qd->n - qstart < (size_t)len[n]);
+				while (gdh_line(p, qd, qstart, qd == &qual && GDH_QUAL_PINNED, &qual_pool) && qd->n - qstart < (size_t)len[n]);
 				if (qd->n - qstart != (size_t)len[n]) bad = 1;
 			}
 			free(scratch.p);
@@ -237,11 +253,12 @@ static int gdh_read_mapped(gdh_pipeline_t *p, gdh_step_t *s, int with_qual)
 			any_qual = 1;
 		} else all_qual = 0;
 		if (with_qual && qual.n - q0 != (size_t)len[n]) { /* a FASTA record among FASTQ ones: keep the two buffers in step */
-			gdh_str_need(&qual, (size_t)len[n], 1, &qual_pool);
+			gdh_str_need(&qual, (size_t)len[n], GDH_QUAL_PINNED, &qual_pool);
 			qual.n = q0 + (size_t)len[n];
 		}
 		size += len[n], ++n;
 		if (size >= p->mini_batch_size) break;
+		if (p->sub_bases > 0 && size >= p->sub_bases && n >= p->sub_reads) break;
 	}
 	if (bad) { /* kseq returns -2: the record is dropped, the batch ends here, the next call resynchronises on a header */
 		seq.n = n < m && off ? (size_t)off[n] : seq.n;
@@ -251,7 +268,7 @@ static int gdh_read_mapped(gdh_pipeline_t *p, gdh_step_t *s, int with_qual)
 	}
 	if (n == 0) {
 		if (seq.p) gdh_buf_put(seq.p, seq_pool);
-		if (qual.p) gdh_buf_put(qual.p, qual_pool);
+		if (qual.p) gdh_qbuf_put(qual.p, qual_pool);
 		free(names.p), free(off), free(len), free(noff);
 		return 0;
 	}
@@ -261,7 +278,7 @@ static int gdh_read_mapped(gdh_pipeline_t *p, gdh_step_t *s, int with_qual)
 	for (i = 0; i < n; ++i) s->names[i] = names.p + noff[i];
 	free(noff);
 	if (with_qual && any_qual && all_qual) s->qual = qual.p, s->qual_cap = qual_pool; /* mm_write_sam3 prints '*' for reads without qualities */
-	else if (qual.p) gdh_buf_put(qual.p, qual_pool);
+	else if (qual.p) gdh_qbuf_put(qual.p, qual_pool);
 	if (with_qual && any_qual && !all_qual)
 		gdh_die("a mini-batch mixes FASTA and FASTQ records: not covered by the batched device path");
 	return n;
@@ -299,9 +316,9 @@ static void *gdh_worker(void *shared, int step, void *in)
 		s->off = (int64_t *)malloc(sizeof(int64_t) * s->n), s->len = (int32_t *)malloc(sizeof(int32_t) * s->n);
 		s->buf = gdh_buf_get((size_t)tot + 16, &s->buf_cap); /* pinned: the upload of step 1 runs at PCIe speed */
 		if (!s->buf) gdh_die("out of page-locked memory");
-		s->qual = with_qual ? gdh_buf_get((size_t)tot + 16, &s->qual_cap) : 0;
+		s->qual = with_qual ? gdh_qbuf_get((size_t)tot + 16, &s->qual_cap) : 0;
 		for (i = 0; i < s->n && s->qual; ++i)
-			if (!s->seq[i].qual) gdh_buf_put(s->qual, s->qual_cap), s->qual = 0; /* FASTA input: no quality strings ('*' in SAM) */
+			if (!s->seq[i].qual) gdh_qbuf_put(s->qual, s->qual_cap), s->qual = 0; /* FASTA input: no quality strings ('*' in SAM) */
 		for (i = 0; i < s->n; ++i) {
 			const mm_bseq1_t *t = &s->seq[i];
 			if (i > 0 && mm_qname_same(s->seq[i - 1].name, t->name))
@@ -340,7 +357,7 @@ static void *gdh_worker(void *shared, int step, void *in)
 			if (s->seq[i].comment) free(s->seq[i].comment);
 		}
 		free(s->seq), free(s->names), free(s->off), free(s->len), free(s->name_blob);
-		if (s->qual) gdh_buf_put(s->qual, s->qual_cap);
+		if (s->qual) gdh_qbuf_put(s->qual, s->qual_cap);
 		gdh_buf_put(s->buf, s->buf_cap);
 		p->t_write += realtime() - t0;
 		if (mm_verbose >= 3)
@@ -422,6 +439,17 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 	pl.opt = opt, pl.mi = idx, pl.n_threads = n_threads > 1 ? n_threads : 1, pl.mini_batch_size = opt->mini_batch_size;
 	gdh_options(&pl);
 	if (env && atoi(env) > 0) n_gpus = atoi(env);
+#ifdef GD_HOST_LR
+	/* -K 500M (the long-read default) often makes a whole file ONE mini-batch: nothing of the three pipeline steps overlaps then.
+	 * Records are independent and written in input order, so the text does not depend on where batches end: a batch is also
+	 * closed once it holds enough work for the devices (per GPU: two 64 Mbase slices would be better for one call, but 64 Mbases
+	 * and 4,096 reads keep the DP launches full while the reader and the writer run beside the device). */
+	{
+		const char *e = getenv("GDIET_LR_BATCH_BASES"), *e2 = getenv("GDIET_LR_BATCH_READS"); /* (0 bases: only -K ends a batch) */
+		pl.sub_bases = e ? atoll(e) : (int64_t)n_gpus * (64ll << 20);
+		pl.sub_reads = e2 ? atoi(e2) : n_gpus * 4096;
+	}
+#endif
 	if ((rc = gd_multi_init(n_gpus, 0, &pl.gm)) != GD_OK) gdh_die("no usable CUDA device (there is no CPU fallback in this build)");
 
 	/* the contigs the reference's index holds, as ASCII: the device index is built from them, and the host stage reads them */
@@ -458,4 +486,11 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 	if (pl.fp) mm_bseq_close(pl.fp);
 	if (pl.map) munmap((void *)pl.map, pl.map_len);
 	return 0;
+}
+
+/* main.c calls this one-file form whenever the preset is not in fragment mode (every long-read preset; main.c:652-656 of the
+ * long-read tree, map.c:2254): it has to land in the device pipeline too, not in the renamed CPU one. */
+int mm_map_file(const mm_idx_t *idx, const char *fn, const mm_mapopt_t *opt, int n_threads)
+{
+	return mm_map_file_frag(idx, 1, &fn, opt, n_threads);
 }

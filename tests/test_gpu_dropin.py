@@ -2,7 +2,7 @@
 without sketch.c and ksw2_extd2_avx.c and linked against libgdiet_cuda.so instead (oracle/_ref/GDiet_cuda_sr|lr), so that
 its mm_sketch / mm_sketch2 / mm_sketch3 / ksw_extd2_avx512 calls run on the GPU through the library's drop-in symbols.
 Its SAM output must equal the SAM of the all-CPU build (oracle/_ref/GDiet_avx_sr|lr) byte for byte."""
-import os
+import os, re
 import subprocess
 import tempfile
 
@@ -65,6 +65,11 @@ def run_env(prog, flags, fa, fq, out, threads, env):
     p = subprocess.run([prog, "-t", str(threads)] + flags + ["-o", out, fa, fq], capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, **env))
     assert p.returncode == 0, p.stderr[-2000:]
+    # the device pipeline ran, and the reference's CPU mapping code (still linked, under another name) did not: its [PROFILING]
+    # counters stay at zero
+    assert "[M::mm_map_file_frag]" in p.stderr and "step seconds" in p.stderr, p.stderr[-2000:]
+    for m in re.finditer(r"\[PROFILING\] (seeding|voting|sequence alignment|pattern alignment) time: (\d+) ns", p.stderr):
+        assert int(m.group(2)) == 0, m.group(0)
     return [l for l in open(out).read().splitlines() if not l.startswith("@PG")], p.stderr
 
 
@@ -108,6 +113,10 @@ def test_batched_host_long_reads_sam_identical():
     want = run(maplib.REF_LR, flags, fa, fq, os.path.join(tmp, "cpu.sam"), 2)
     got, _ = run_env(BATCHED_LR, flags + ["-K", "200k"], fa, fq, os.path.join(tmp, "gpu.sam"), 3, {"GDIET_GPUS": "1"})
     assert len(got) == len(want) and got == want
+    # the long-read host also closes a mini-batch once it holds enough work for the devices (here: 7 reads and 50 kbases)
+    got3, err3 = run_env(BATCHED_LR, flags, fa, fq, os.path.join(tmp, "gpu3.sam"), 3,
+                         {"GDIET_GPUS": "1", "GDIET_LR_BATCH_BASES": "50000", "GDIET_LR_BATCH_READS": "7"})
+    assert got3 == want and len(re.findall(r"mapped \d+ sequences", err3)) >= 6, err3[-1000:]
     if n_gpus() >= 2:
         got2, err = run_env(BATCHED_LR, flags + ["-K", "200k"], fa, fq, os.path.join(tmp, "gpu2.sam"), 4, {"GDIET_GPUS": "2"})
         assert got2 == want, err[-1000:]

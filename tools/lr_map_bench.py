@@ -60,6 +60,55 @@ def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
     off = np.zeros(n_reads, np.int64)
     off[1:] = np.cumsum(lens[:-1].astype(np.int64))
     buf = np.concatenate(reads)
+    # ---- whole programs, file to file, BEFORE this process takes device memory for its own contexts (the DP backtrack arena is sized
+    # from what is free: a second process next to a loaded one would get small launches): the unmodified reference on all host
+    # cores, then the batched C host of the long-read tree (INTEGRATION.md level 2) with the same flags
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_avx_lr")
+    flags = ["-ax", preset, "-Z", "10", "-W", "2", "-k", str(k), "-w", str(w), "-r", str(bw)] + extra
+    file_runs = {}
+    if run_ref and os.path.exists(ref_bin):
+        import maplib
+        tmp = tempfile.mkdtemp(prefix="gdref_")
+        fa, fq = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq")
+        maplib.write_fasta(fa, contigs)
+        maplib.write_fastq(fq, reads)
+        t0 = time.perf_counter()
+        p = subprocess.run([ref_bin, "-t", str(cores)] + flags + ["-o", os.path.join(tmp, "out.sam"), fa, fq], capture_output=True, text=True)
+        wall = time.perf_counter() - t0
+        prof = dict(re.findall(r"\[PROFILING\] (.+?) time: (\d+) ns", p.stderr))
+        t_idx = int(prof.get("indexing", 0)) * 1e-9
+        # ---- the batched C host of the long-read tree (INTEGRATION.md level 2): FASTQ file in, SAM file out, same flags
+        batched_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_cuda_batched_lr")
+        if os.path.exists(batched_bin):
+            strip = lambda path: [l for l in open(path).read().splitlines() if not l.startswith("@PG")]
+            want_sam = strip(os.path.join(tmp, "out.sam"))
+
+            def run_batched(extra, env, prefix=()):
+                samb = os.path.join(tmp, "batched.sam")
+                t0 = time.perf_counter()
+                pb = subprocess.run(list(prefix) + [batched_bin, "-t", str(cores)] + flags + extra + ["-o", samb, fa, fq], capture_output=True, text=True,
+                                    env=dict(os.environ, GDIET_GPUS="1", **env))
+                wall_b = time.perf_counter() - t0
+                mm = re.search(r"\[M::mm_map_file_frag\] (\d+) reads, \d+ bases in ([0-9.]+) s.*", pb.stderr)
+                ix = re.search(r"\[PROFILING\] indexing time: (\d+) ns", pb.stderr)
+                r = {"flags": extra, "env": env, "returncode": pb.returncode, "wall_s": round(wall_b, 2),
+                     "indexing_s": round(int(ix.group(1)) * 1e-9, 2) if ix else None, "map_pipeline_s": float(mm.group(2)) if mm else None,
+                     "reads_per_s_pipeline": (n_reads / float(mm.group(2))) if mm else None,
+                     "summary": mm.group(0)[:300] if mm else pb.stderr[-300:],
+                     "sam_file_identical": pb.returncode == 0 and strip(samb) == want_sam}
+                if "GD_MAP_PROFILE" in env:
+                    r["profile"] = [l for l in pb.stderr.splitlines() if l.startswith("[gd_")][:80]
+                return r
+
+            file_runs["batched_host"] = dict(binary="oracle/_ref/GDiet_cuda_batched_lr (unmodified reference sources + gd_batched_host.c)",
+                                       **run_batched([], {}))
+            if os.environ.get("LR_BATCHED_NCU"):  # per-kernel durations of the same command (launch list; not a timing run)
+                file_runs["batched_host_ncu"] = run_batched([], {}, ("ncu", "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "--csv",
+                                                               "--log-file", os.environ["LR_BATCHED_NCU"]))
+            if os.environ.get("LR_BATCHED_PROBE"):  # where the time of the file-to-file pipeline goes: mini-batch size, device slices
+                file_runs["batched_host_probe"] = [run_batched(f, e) for f, e in (
+                    ([], {"GD_MAP_PROFILE": "1"}), (["-K", "100M"], {}), (["-K", "50M"], {}), (["-K", "50M"], {"GD_MAP_PROFILE": "1"}),
+                    ([], {"GDIET_LR_SLICE_READS": "100000000"}))]
     ctx.set_option("time_kernels", 1)
     t0 = time.perf_counter()
     idx = ctx.index_build(contigs, w, k, "10")
@@ -93,10 +142,7 @@ def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
         out["sam_s"] = round(time.perf_counter() - t0, 3)
     out["reads_needing_stitch"] = int(stitch.sum())
     out["reads_per_s_end_to_end"] = n_reads / (min(tm) + out["sam_s"])
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_avx_lr")
     if run_ref and os.path.exists(ref_bin):
-        import maplib
-        flags = ["-ax", preset, "-Z", "10", "-W", "2", "-k", str(k), "-w", str(w), "-r", str(bw)] + extra
         if n_check > 0:
             _, tr = maplib.run_reference(contigs, reads[:n_check], flags, program=ref_bin, threads=1)
             bad = 0
@@ -108,15 +154,6 @@ def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
                     if bad <= 3:
                         print(str(e)[:300], file=sys.stderr)
             out["parity"] = {"reads_checked": len(tr), "dp_calls_checked": int(sum(len(t["cands"]) for t in tr)), "mismatching_reads": bad}
-        tmp = tempfile.mkdtemp(prefix="gdref_")
-        fa, fq = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq")
-        maplib.write_fasta(fa, contigs)
-        maplib.write_fastq(fq, reads)
-        t0 = time.perf_counter()
-        p = subprocess.run([ref_bin, "-t", str(cores)] + flags + ["-o", os.path.join(tmp, "out.sam"), fa, fq], capture_output=True, text=True)
-        wall = time.perf_counter() - t0
-        prof = dict(re.findall(r"\[PROFILING\] (.+?) time: (\d+) ns", p.stderr))
-        t_idx = int(prof.get("indexing", 0)) * 1e-9
         want = {}
         for l in open(os.path.join(tmp, "out.sam")).read().splitlines():
             if not l.startswith("@"):
@@ -131,22 +168,7 @@ def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
             else:
                 diff += 1
         out["sam"] = {"reads_identical": same, "reads_different": diff, "reads_left_to_host_stitching": int(stitch.sum())}
-        # ---- the batched C host of the long-read tree (INTEGRATION.md level 2): FASTQ file in, SAM file out, same flags
-        batched_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_cuda_batched_lr")
-        if os.path.exists(batched_bin):
-            samb = os.path.join(tmp, "batched.sam")
-            t0 = time.perf_counter()
-            pb = subprocess.run([batched_bin, "-t", str(cores)] + flags + ["-o", samb, fa, fq], capture_output=True, text=True,
-                                env=dict(os.environ, GDIET_GPUS="1"))
-            wall_b = time.perf_counter() - t0
-            mm = re.search(r"\[M::mm_map_file_frag\] (\d+) reads, \d+ bases in ([0-9.]+) s.*", pb.stderr)
-            ix = re.search(r"\[PROFILING\] indexing time: (\d+) ns", pb.stderr)
-            strip = lambda path: [l for l in open(path).read().splitlines() if not l.startswith("@PG")]
-            out["batched_host"] = {"binary": "oracle/_ref/GDiet_cuda_batched_lr (unmodified reference sources + gd_batched_host.c)", "returncode": pb.returncode,
-                                   "wall_s": round(wall_b, 2), "indexing_s": round(int(ix.group(1)) * 1e-9, 2) if ix else None,
-                                   "map_pipeline_s": float(mm.group(2)) if mm else None,
-                                   "reads_per_s_pipeline": (n_reads / float(mm.group(2))) if mm else None, "summary": mm.group(0)[:300] if mm else pb.stderr[-300:],
-                                   "sam_file_identical": pb.returncode == 0 and strip(samb) == strip(os.path.join(tmp, "out.sam"))}
+        out.update(file_runs)
         out["reference"] = {"wall_s": round(wall, 2), "indexing_s": round(t_idx, 2), "reads_per_s": n_reads / max(wall - t_idx, 1e-9), "threads": cores,
                             "profile_thread_seconds": {kk: round(int(v) * 1e-9, 2) for kk, v in prof.items()}}
     idx.close()

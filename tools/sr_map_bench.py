@@ -143,21 +143,32 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
         # ---- the batched C host (INTEGRATION.md level 2): the same program with genome-on-diet_b200/host/gd_batched_host.c in place
         # of map.c's pipeline -- FASTQ parsing, mapping on the GPU, SAM file written, one process, same flags
         if os.path.exists(batched_bin):
-            samb = os.path.join(tmp, "batched.sam")
-            t0 = time.perf_counter()
-            pb = subprocess.run([batched_bin, "-t", str(cores), "-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200",
-                                 "-K", "30M", "-o", samb, fa, fq], capture_output=True, text=True, env=dict(os.environ, GDIET_GPUS="1"))
-            wall_b = time.perf_counter() - t0
-            mm = re.search(r"\[M::mm_map_file_frag\] (\d+) reads, \d+ bases in ([0-9.]+) s", pb.stderr)
-            ix = re.search(r"\[PROFILING\] indexing time: (\d+) ns", pb.stderr)
-            gotb = [l for l in open(samb).read().splitlines() if not l.startswith("@")] if pb.returncode == 0 else []
-            out["batched_host"] = {"binary": "oracle/_ref/GDiet_cuda_batched_sr (unmodified reference sources + gd_batched_host.c)", "returncode": pb.returncode,
-                                   "wall_s": round(wall_b, 3), "indexing_s": round(int(ix.group(1)) * 1e-9, 3) if ix else None,
-                                   "map_pipeline_s": float(mm.group(2)) if mm else None,
-                                   "reads_per_s_pipeline": (n_reads / float(mm.group(2))) if mm else None,
-                                   "summary": (re.search(r"\[M::mm_map_file_frag\] .*", pb.stderr) or [""])[0][:300], "mini_batch": "-K 30M (200 k reads per batch)",
-                                   "note": "map_pipeline_s = FASTQ parse + GPU mapping + SAM file write under kt_pipeline (after the index and the CUDA context exist)",
-                                   "sam_identical": gotb == want}
+            def run_batched(kflag, env):
+                samb = os.path.join(tmp, "batched.sam")
+                t0 = time.perf_counter()
+                pb = subprocess.run([batched_bin, "-t", str(cores), "-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200"]
+                                    + kflag + ["-o", samb, fa, fq], capture_output=True, text=True, env=dict(os.environ, GDIET_GPUS="1", **env))
+                wall_b = time.perf_counter() - t0
+                mm = re.search(r"\[M::mm_map_file_frag\] (\d+) reads, \d+ bases in ([0-9.]+) s", pb.stderr)
+                ix = re.search(r"\[PROFILING\] indexing time: (\d+) ns", pb.stderr)
+                gotb = [l for l in open(samb).read().splitlines() if not l.startswith("@")] if pb.returncode == 0 else []
+                r = {"flags": kflag, "returncode": pb.returncode,
+                     "wall_s": round(wall_b, 3), "indexing_s": round(int(ix.group(1)) * 1e-9, 3) if ix else None,
+                     "map_pipeline_s": float(mm.group(2)) if mm else None,
+                     "reads_per_s_pipeline": (n_reads / float(mm.group(2))) if mm else None,
+                     "summary": (re.search(r"\[M::mm_map_file_frag\] .*", pb.stderr) or [""])[0][:300],
+                     "sam_identical": gotb == want}
+                if "GD_MAP_PROFILE" in env:
+                    r["profile"] = [l for l in pb.stderr.splitlines() if l.startswith("[gd_")][:60]
+                return r
+
+            out["batched_host"] = dict(binary="oracle/_ref/GDiet_cuda_batched_sr (unmodified reference sources + gd_batched_host.c)",
+                                       mini_batch="-K 30M (200 k reads per batch)",
+                                       note="map_pipeline_s = FASTQ parse + GPU mapping + SAM file write under kt_pipeline (after the index and the CUDA context exist)",
+                                       **run_batched(["-K", "30M"], {}))
+            if os.environ.get("SR_BATCHED_PROBE"):  # mini-batch size and the phases of one call
+                out["batched_host_probe"] = [run_batched(k, e) for k, e in (([], {}), (["-K", "30M"], {"GD_MAP_PROFILE": "1"}), (["-K", "150M"], {}),
+                                                                             (["-K", "500M"], {}), (["-K", "500M"], {"GD_MAP_PROFILE": "1"}))]
         if got != want:
             bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
             out["sam_first_diff"] = [got[bad[0]][:300], want[bad[0]][:300]] if bad else ["length", "%d vs %d" % (len(got), len(want))]

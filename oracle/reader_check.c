@@ -2,7 +2,8 @@
  * The mini-batch reader of genome-on-diet_b200/host/gd_batched_host.c (mapped file, memchr) against the reference's
  * own reader (mm_bseq_read3 over kseq.h, GDiet-ShortReads/bseq.c:73-113) on the same file and -K: every batch must hold
  * the same reads with the same names, bases and qualities.  No GPU needed (nothing of the library is called).
- *     reader_check <file> <mini_batch_bases>      prints "OK <batches> <reads>" or the first difference */
+ *     reader_check <file> <mini_batch_bases> [threads]     prints "OK <batches> <reads> <batches read by the several-thread
+ *                                                          reader>" or the first difference */
 #include <stdlib.h>
 #define gd_pinned_alloc(n) malloc(n) /* no GPU here: the batch buffers are plain memory in this check */
 #define gd_pinned_free(p) free(p)
@@ -19,10 +20,24 @@ int main(int argc, char **argv)
 	if (argc < 3) return 2;
 	memset(&pl, 0, sizeof(pl)), memset(&opt, 0, sizeof(opt));
 	pl.opt = &opt, pl.mini_batch_size = atol(argv[2]);
+	pl.n_threads = argc > 3 ? atoi(argv[3]) : 1;
 	fd = open(argv[1], O_RDONLY);
 	if (fd < 0 || fstat(fd, &st) != 0) return 2;
 	pl.map = st.st_size ? (const char *)mmap(0, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0) : "";
 	pl.map_len = (size_t)st.st_size;
+	if (argc > 4 && !strcmp(argv[4], "time")) { /* the product reader alone: reads per second (no comparison) */
+		double t0 = realtime();
+		for (;;) {
+			gdh_step_t s;
+			memset(&s, 0, sizeof(s));
+			if (gdh_read_mapped(&pl, &s, 1) == 0) break;
+			reads += s.n, ++batches;
+			free(s.buf), free(s.qual), free(s.off), free(s.len), free(s.names), free(s.name_blob);
+		}
+		printf("TIME %d batches %ld reads %.3f s %.0f reads/s (%ld batches on several threads)\n", batches, reads, realtime() - t0,
+		       reads / (realtime() - t0 + 1e-9), pl.n_par_batches);
+		return 0;
+	}
 	fp = mm_bseq_open(argv[1]);
 	for (;;) {
 		gdh_step_t s;
@@ -48,6 +63,6 @@ int main(int argc, char **argv)
 		free(r);
 		reads += n, ++batches;
 	}
-	printf("OK %d %ld\n", batches, reads);
+	printf("OK %d %ld %ld\n", batches, reads, pl.n_par_batches);
 	return 0;
 }

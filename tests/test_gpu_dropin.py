@@ -122,6 +122,25 @@ def test_batched_host_long_reads_sam_identical():
         assert got2 == want, err[-1000:]
 
 
+@pytest.mark.skipif(not (os.path.exists(BATCHED_LR) and os.path.exists(maplib.REF_LR) and cpu_has_avx512()),
+                    reason="needs oracle/_ref/GDiet_cuda_batched_lr + GDiet_avx_lr")
+def test_batched_host_ont_flags_sam_identical():
+    """BASELINE config 4's flag set (-ax map-ont -r 1300 -s ... + the README's voting flags) through the batched C host: every
+    vt_* option, --max_min_gap, --sort=merge, --frag=no and -s reach the device stage and the host SAM stage as the reference's
+    mm_mapopt_t holds them; reads with structural variation so that chained candidates are stitched."""
+    contigs, reads = maplib.make_long_dataset(seed=63, read_len=9000, sub=0.02, indel=0.03, n_reads=80, sv_frac=0.5)
+    tmp = tempfile.mkdtemp(prefix="gdbatch_")
+    fa, fq = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq")
+    maplib.write_fasta(fa, contigs)
+    maplib.write_fastq(fq, reads)
+    flags = ["-ax", "map-ont", "-Z", "10", "-W", "2", "-k", "15", "-w", "10", "-r", "800", "-s", "3000", "--vt_dis=1000", "--vt_nb_loc=3",
+             "--vt_df1=0.007", "--vt_df2=0.007", "--max_min_gap=4000", "--vt_f=0.04", "--vt_cov", "0.3", "--sort=merge", "--frag=no"]
+    want = run(maplib.REF_LR, flags, fa, fq, os.path.join(tmp, "cpu.sam"), 2)
+    got, _ = run_env(BATCHED_LR, flags, fa, fq, os.path.join(tmp, "gpu.sam"), 3, {"GDIET_GPUS": "1"})
+    mapped = sum(1 for l in want if not l.startswith("@") and l.split("\t")[2] != "*")
+    assert got == want and mapped >= 20, (len(got), len(want), mapped)
+
+
 def test_batched_host_refuses_what_the_device_path_does_not_cover():
     if not os.path.exists(BATCHED_SR):
         pytest.skip("needs oracle/_ref/GDiet_cuda_batched_sr")

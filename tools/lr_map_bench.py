@@ -5,7 +5,7 @@ reads (8 % error), against a synthetic reference.  gd_lr_map_batch does everythi
 ksw_extz_t of every candidate on the GPU; the CIGAR stitching (concatenate_cigars) and SAM stay with the host program.
 Parity: the first `n_check` reads are compared with the call trace of the unmodified reference program (-t 1); the CPU
 baseline is the same program on all host cores over all reads ([PROFILING] thread-seconds and wall time).
-    python tools/lr_map_bench.py hifi|ont [ref_mbp] [n_reads] [n_check]"""
+    python tools/lr_map_bench.py hifi|ont|ont-asis [ref_mbp] [n_reads] [n_check]"""
 import json, os, re, subprocess, sys, tempfile, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -39,9 +39,11 @@ def main():
 def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
     if kind == "hifi":
         preset, k, w, bw, L, sub, indel, extra, okw = "map-hifi", 19, 19, 1000, 15000, 0.005, 0.005, [], {}
-    else:
-        preset, k, w, bw, L, sub, indel, extra = "map-ont", 15, 10, 1300, 50000, 0.03, 0.05, ONT_FLAGS
+    elif kind == "ont":  # BASELINE config 4's flags (-r 1300 -s 35000) + the README's voting flags (SURVEY.md finding 6)
+        preset, k, w, bw, L, sub, indel, extra = "map-ont", 15, 10, 1300, 50000, 0.03, 0.05, ONT_FLAGS + ["-s", "35000"]
         okw = dict(vt_dis=1000, vt_df1=0.007, vt_df2=0.007, vt_f=0.04, vt_cov=0.3)
+    else:  # "ont-asis": config 4 exactly as BASELINE writes it -- the long-read tree's default voting thresholds reject every read
+        preset, k, w, bw, L, sub, indel, extra, okw = "map-ont", 15, 10, 1300, 50000, 0.03, 0.05, ["-s", "35000"], {}
     cores = len(os.sched_getaffinity(0))
     rng = np.random.default_rng(5)
     ncontig = 4
@@ -124,7 +126,7 @@ def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
         tm.append(time.perf_counter() - t0)
         dp_us = ctx.stat("ksw_dp_us")
     cells = sum(band_cells(int(c["qe"] - c["qs"]), int(c["re"] - c["rs"]), bw) for c in cand if not c["exact"])
-    out = {"what": "config %s: long-read mapping stage on the device" % ("3 (hifi)" if kind == "hifi" else "4 (ont, README voting flags)"),
+    out = {"what": "config %s: long-read mapping stage on the device" % ({"hifi": "3 (hifi)", "ont": "4 (ont, -s 35000 + README voting flags)"}.get(kind, "4 exactly as written (ont, -s 35000, default voting thresholds: nothing maps)")),
            "ref_bp": int(sum(len(c) for c in contigs)), "reads": n_reads, "read_len": L, "band": bw, "mid_occ": mid, "index_build_s": round(t_index, 3),
            "map_batch_s": [round(x, 3) for x in tm], "reads_per_s": n_reads / min(tm), "bases_per_s": float(lens.sum()) / min(tm),
            "candidates": int(coff[-1]), "mapped_reads": int((np.diff(coff) > 0).sum()), "chained": int((cand["reserved"][:, 0] >= 0).sum()),
@@ -134,6 +136,8 @@ def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
     names = gd._cstr_array(["r%d" % i for i in range(n_reads)])
     qual = np.full(len(buf), ord("I"), np.uint8)
     post = gd.lr_post_options(preset)
+    if kind != "hifi":
+        post.min_dp_max = 35000  # -s 35000
     ref = gd.flat_ref(contigs)  # (a C host holds the reference as one buffer already)
     for it in range(2):
         t0 = time.perf_counter()

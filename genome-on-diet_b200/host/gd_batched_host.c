@@ -16,9 +16,18 @@
  * reference's kt_pipeline (kthread.c:71-160), so reading batch i+1, mapping batch i and writing batch i-1 overlap
  * exactly as in the reference, and the output order is the input order.
  *
- * Everything else is the reference's: option parsing, index reading (main.c, index.c, with mm_sketch resolved to the
- * library's drop-in), the SAM header (format.c), FASTA/FASTQ parsing (bseq.c).  The device index is built from the
- * sequences the reference's index holds (mm_idx_getseq), so an .mmi made with -d works as well.
+ * and, on the index side (index.c is compiled with these four names renamed away in the same manner):
+ *
+ *   mm_idx_reader_read()  index.c:624-640   a FASTA reference is read with the reference's reader, but the minimizer index
+ *                                           is built ON THE DEVICE (gd_index_build, ~1 s for 3.1 Gbp) instead of mm_idx_gen's
+ *                                           sketch + sort + 2^b host hash tables (19 s on 16 threads), which the device path
+ *                                           never looks at; the mm_idx_t that main.c gets holds names, lengths, w, k, flags
+ *   mm_idx_cal_max_occ()  index.c:190-210   answered by the device index (mm_mapopt_update calls it for mid_occ)
+ *   mm_idx_stat(), mm_idx_destroy()         the statistics line comes from the device index; destroy also drops the device side
+ *   (an .mmi file, -d, and homopolymer-compressed indexing keep the reference's code: the host tables ARE the file format)
+ *
+ * Everything else is the reference's: option parsing (main.c), the SAM header (format.c), FASTA/FASTQ parsing of gzip / stdin
+ * input (bseq.c).  With an index that came from an .mmi the device index is built from the sequences it holds (mm_idx_getseq).
  *
  * What the device path does not cover is refused with an error, never mapped differently: paired / multi-segment
  * input, PAF output, --split-prefix, --cs / --MD / --eqx / -y, splice mode, and (long reads) --sort=radix|heap.
@@ -35,6 +44,7 @@
 #include "mmpriv.h"
 #include "bseq.h"
 #include "kthread.h"
+#include "kalloc.h"
 #include "gdiet_cuda.h" /* after minimap.h: its guards skip the types the reference already defines */
 
 typedef struct {
@@ -559,6 +569,144 @@ static void *gdh_worker(void *shared, int step, void *in)
 	return 0;
 }
 
+/* ---- devices and the index part that is alive (main.c: read a part, map every query file against it, destroy it) ---------- */
+static struct {
+	gd_multi *gm;
+	int n_gpus;
+	const mm_idx_t *mi;   /* the part the fields below belong to (0: none) */
+	char *ref;            /* its contigs as ASCII, back to back: the device index is built from them, the long-read host stage reads them */
+	int64_t *ref_off;
+	int32_t *ref_len;
+	const char **ref_names;
+	int n_ref;
+} gdh_dev;
+
+static void gdh_devices(void)
+{
+	const char *env = getenv("GDIET_GPUS");
+	if (gdh_dev.gm) return;
+	gdh_dev.n_gpus = env && atoi(env) > 0 ? atoi(env) : 1;
+	if (gd_multi_init(gdh_dev.n_gpus, 0, &gdh_dev.gm) != GD_OK) gdh_die("no usable CUDA device (there is no CPU fallback in this build)");
+}
+
+static void gdh_drop_part(void)
+{
+	free(gdh_dev.ref), free(gdh_dev.ref_off), free(gdh_dev.ref_len), free((void *)gdh_dev.ref_names);
+	gdh_dev.ref = 0, gdh_dev.ref_off = 0, gdh_dev.ref_len = 0, gdh_dev.ref_names = 0, gdh_dev.n_ref = 0, gdh_dev.mi = 0;
+}
+
+/* names / offsets from mi->seq, then the device index from gdh_dev.ref on the first GPU, broadcast to the others */
+static void gdh_device_index(const mm_idx_t *mi, const char *pattern, int pattern_len)
+{
+	gd_index *gi = 0;
+	int64_t tot = 0;
+	uint32_t i;
+	const double t0 = realtime();
+	gdh_devices();
+	gdh_dev.n_ref = (int)mi->n_seq;
+	gdh_dev.ref_names = (const char **)malloc(sizeof(char *) * (mi->n_seq + 1));
+	gdh_dev.ref_off = (int64_t *)malloc(sizeof(int64_t) * (mi->n_seq + 1)), gdh_dev.ref_len = (int32_t *)malloc(sizeof(int32_t) * (mi->n_seq + 1));
+	for (i = 0; i < mi->n_seq; ++i)
+		gdh_dev.ref_names[i] = mi->seq[i].name, gdh_dev.ref_off[i] = tot, gdh_dev.ref_len[i] = (int32_t)mi->seq[i].len, tot += mi->seq[i].len;
+	if (gd_index_build(gd_multi_ctx(gdh_dev.gm, 0), gdh_dev.n_ref, gdh_dev.ref_off, gdh_dev.ref_len, gdh_dev.ref, mi->w, mi->k, pattern, pattern_len, &gi) != GD_OK)
+		gdh_die(gd_strerror(gd_multi_ctx(gdh_dev.gm, 0)));
+	if (gd_multi_index_bcast(gdh_dev.gm, gi, 1) != GD_OK) gdh_die(gd_multi_strerror(gdh_dev.gm));
+	gdh_dev.mi = mi;
+	if (mm_verbose >= 3)
+		fprintf(stderr, "[M::%s::%.3f*%.2f] device index on %d GPU(s) in %.3f s (broadcast %.0f MB in %.3f s, %s)\n", __func__,
+		        realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), gdh_dev.n_gpus, realtime() - t0,
+		        gd_multi_stat(gdh_dev.gm, "bcast_bytes") / 1e6, gd_multi_stat(gdh_dev.gm, "bcast_seconds"),
+		        gd_multi_stat(gdh_dev.gm, "bcast_path") == 1 ? "ncclBroadcast" : gdh_dev.n_gpus > 1 ? "peer copies" : "single GPU");
+}
+
+#ifndef GDH_READER_ONLY /* (oracle/reader_check.c compiles this file for its reader alone) */
+/* the reference's functions of these names, compiled from index.c under other names (oracle/Makefile build_prog_batched) */
+mm_idx_t *gdref_cpu_mm_idx_reader_read(mm_idx_reader_t *r, int n_threads);
+int32_t gdref_cpu_mm_idx_cal_max_occ(const mm_idx_t *mi, float f);
+void gdref_cpu_mm_idx_stat(const mm_idx_t *mi);
+void gdref_cpu_mm_idx_destroy(mm_idx_t *mi);
+mm_idx_t *mm_idx_init(int w, int k, int b, int flag); /* index.c:46 (not in a header) */
+
+/* mm_idx_reader_read (index.c:624-640) for a FASTA reference: what mm_idx_gen's step 0 does (index.c:309-364: names, lengths,
+ * offsets; up to -I bases per part) with the bases kept as ASCII, then the device index instead of steps 1-2 + mm_idx_post. */
+mm_idx_t *mm_idx_reader_read(mm_idx_reader_t *r, int n_threads)
+{
+	mm_idx_t *mi;
+	uint64_t sum_len = 0, cap = 0;
+	if (r->is_idx || r->fp_out || (r->opt.flag & MM_I_HPC) || getenv("GDIET_REF_INDEX")) return gdref_cpu_mm_idx_reader_read(r, n_threads);
+	if (r->fp.seq == 0 || mm_bseq_eof(r->fp.seq)) return 0;
+	gdh_drop_part();
+	mi = mm_idx_init(r->opt.w, r->opt.k, r->opt.bucket_bits, r->opt.flag);
+	while (sum_len <= r->opt.batch_size) {
+		int n = 0, i;
+		mm_bseq1_t *seq = mm_bseq_read(r->fp.seq, r->opt.mini_batch_size, 0, &n);
+		uint32_t old_m, m;
+		uint64_t add = 0;
+		if (!seq) break;
+		old_m = mi->n_seq, m = mi->n_seq + n;
+		kroundup32(m);
+		kroundup32(old_m);
+		if (old_m != m) mi->seq = (mm_idx_seq_t *)krealloc(mi->km, mi->seq, m * sizeof(mm_idx_seq_t));
+		for (i = 0; i < n; ++i) add += seq[i].l_seq;
+		if (sum_len + add + 16 > cap) {
+			cap = (sum_len + add) + (sum_len + add) / 2 + 4096;
+			if (!(gdh_dev.ref = (char *)realloc(gdh_dev.ref, cap))) gdh_die("out of memory for the reference sequences");
+		}
+		for (i = 0; i < n; ++i) {
+			mm_idx_seq_t *t = &mi->seq[mi->n_seq++];
+			if (!(mi->flag & MM_I_NO_NAME)) {
+				t->name = (char *)kmalloc(mi->km, strlen(seq[i].name) + 1);
+				strcpy(t->name, seq[i].name);
+			} else t->name = 0;
+			t->len = seq[i].l_seq, t->offset = sum_len, t->is_alt = 0;
+			memcpy(gdh_dev.ref + sum_len, seq[i].seq, seq[i].l_seq);
+			sum_len += seq[i].l_seq;
+			if (seq[i].l_seq == 0 && mm_verbose >= 2) fprintf(stderr, "[WARNING] the length database sequence '%s' is 0\n", seq[i].name);
+			free(seq[i].seq), free(seq[i].name);
+		}
+		free(seq);
+	}
+	if (mm_verbose >= 3)
+		fprintf(stderr, "[M::%s::%.3f*%.2f] read %u reference sequences, %ld bases\n", __func__, realtime() - mm_realtime0,
+		        cputime() / (realtime() - mm_realtime0), mi->n_seq, (long)sum_len);
+	/* (mi->S stays empty: nothing on this path reads it; the flag word is left alone because main.c tests MM_I_NO_SEQ) */
+	gdh_device_index(mi, r->opt.pattern, r->opt.pattern_len);
+	mi->index = r->n_parts++;
+	return mi;
+}
+
+int32_t mm_idx_cal_max_occ(const mm_idx_t *mi, float f)
+{
+	int32_t v = 0;
+	if (mi != gdh_dev.mi) return gdref_cpu_mm_idx_cal_max_occ(mi, f);
+	if (f <= 0.) return INT32_MAX;
+	if (gd_index_cal_max_occ(gd_multi_ctx(gdh_dev.gm, 0), gd_multi_index(gdh_dev.gm, 0), f, &v) != GD_OK) gdh_die(gd_strerror(gd_multi_ctx(gdh_dev.gm, 0)));
+	return v;
+}
+
+void mm_idx_stat(const mm_idx_t *mi)
+{
+	const gd_index *gi;
+	int64_t keys, recs, len;
+	if (mi != gdh_dev.mi) {
+		gdref_cpu_mm_idx_stat(mi);
+		return;
+	}
+	gi = gd_multi_index(gdh_dev.gm, 0);
+	keys = gd_index_stat(gi, "n_keys"), recs = gd_index_stat(gi, "n_minimizers"), len = gd_index_stat(gi, "total_len");
+	fprintf(stderr, "[M::%s] kmer size: %d; skip: %d; is_hpc: %d; #seq: %d\n", __func__, mi->k, mi->w, mi->flag & MM_I_HPC, mi->n_seq);
+	fprintf(stderr, "[M::%s::%.3f*%.2f] (device index) distinct minimizers: %ld; average occurrences: %.3lf; average spacing: %.3lf; total length: %ld\n",
+	        __func__, realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), (long)keys, keys ? (double)recs / keys : 0.0,
+	        recs ? (double)len / recs : 0.0, (long)len);
+}
+
+void mm_idx_destroy(mm_idx_t *mi)
+{
+	if (mi && mi == gdh_dev.mi) gdh_drop_part(); /* (the device copies go when the next part is broadcast, or with the process) */
+	gdref_cpu_mm_idx_destroy(mi);
+}
+#endif
+
 static void gdh_options(gdh_pipeline_t *p)
 {
 	const mm_mapopt_t *opt = p->opt;
@@ -599,11 +747,7 @@ static void gdh_refuse_uncovered(const mm_mapopt_t *opt, int n_segs)
 int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_mapopt_t *opt, int n_threads)
 {
 	gdh_pipeline_t pl;
-	int i, n_gpus = 1, rc;
-	const char *env = getenv("GDIET_GPUS");
-	int64_t tot = 0;
 	double t0;
-	gd_index *gi = 0;
 	if (n_segs < 1) return -1;
 	gdh_refuse_uncovered(opt, n_segs);
 	memset(&pl, 0, sizeof(pl));
@@ -633,7 +777,7 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 	pl.par_min_bytes = getenv("GDIET_READER_THREADS_MIN_BYTES") ? (size_t)atoll(getenv("GDIET_READER_THREADS_MIN_BYTES"))
 	                   : n_threads >= 4 ? (size_t)1 << 20 : (size_t)-1;
 	gdh_options(&pl);
-	if (env && atoi(env) > 0) n_gpus = atoi(env);
+	gdh_devices();
 #ifdef GD_HOST_LR
 	/* -K 500M (the long-read default) often makes a whole file ONE mini-batch: nothing of the three pipeline steps overlaps then.
 	 * Records are independent and written in input order, so the text does not depend on where batches end: a batch is also
@@ -641,33 +785,27 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 	 * and 4,096 reads keep the DP launches full while the reader and the writer run beside the device). */
 	{
 		const char *e = getenv("GDIET_LR_BATCH_BASES"), *e2 = getenv("GDIET_LR_BATCH_READS"); /* (0 bases: only -K ends a batch) */
-		pl.sub_bases = e ? atoll(e) : (int64_t)n_gpus * (64ll << 20);
-		pl.sub_reads = e2 ? atoi(e2) : n_gpus * 4096;
+		pl.sub_bases = e ? atoll(e) : (int64_t)gdh_dev.n_gpus * (64ll << 20);
+		pl.sub_reads = e2 ? atoi(e2) : gdh_dev.n_gpus * 4096;
 	}
 #endif
-	if ((rc = gd_multi_init(n_gpus, 0, &pl.gm)) != GD_OK) gdh_die("no usable CUDA device (there is no CPU fallback in this build)");
-
-	/* the contigs the reference's index holds, as ASCII: the device index is built from them, and the host stage reads them */
-	t0 = realtime();
-	pl.n_ref = (int)idx->n_seq;
-	pl.ref_names = (const char **)malloc(sizeof(char *) * pl.n_ref);
-	pl.ref_off = (int64_t *)malloc(sizeof(int64_t) * pl.n_ref), pl.ref_len = (int32_t *)malloc(sizeof(int32_t) * pl.n_ref);
-	for (i = 0; i < pl.n_ref; ++i) pl.ref_names[i] = idx->seq[i].name, pl.ref_off[i] = tot, pl.ref_len[i] = (int32_t)idx->seq[i].len, tot += idx->seq[i].len;
-	pl.ref = (char *)gd_pinned_alloc((size_t)tot + 16);
-	if (idx->flag & MM_I_NO_SEQ) gdh_die("the index holds no sequences (built with --idx-no-seq)");
-	for (i = 0; i < pl.n_ref; ++i) { /* S is 4-bit packed, 8 bases per word (index.c:157-166) */
-		const uint64_t st = idx->seq[i].offset;
-		char *dst = pl.ref + pl.ref_off[i];
-		uint32_t j;
-		for (j = 0; j < idx->seq[i].len; ++j) dst[j] = "ACGTN"[(idx->S[(st + j) >> 3] >> (((st + j) & 7) << 2)) & 0xf];
+	if (gdh_dev.mi != idx) { /* the index came from an .mmi (or the reference's mm_idx_gen): the contigs it holds, as ASCII */
+		uint32_t i;
+		uint64_t tot = 0;
+		if (idx->flag & MM_I_NO_SEQ) gdh_die("the index holds no sequences (built with --idx-no-seq)");
+		gdh_drop_part();
+		for (i = 0; i < idx->n_seq; ++i) tot += idx->seq[i].len;
+		if (!(gdh_dev.ref = (char *)malloc((size_t)tot + 16))) gdh_die("out of memory for the reference sequences");
+		for (i = 0, tot = 0; i < idx->n_seq; tot += idx->seq[i++].len) { /* S is 4-bit packed, 8 bases per word (index.c:157-166) */
+			const uint64_t st = idx->seq[i].offset;
+			char *dst = gdh_dev.ref + tot;
+			uint32_t j;
+			for (j = 0; j < idx->seq[i].len; ++j) dst[j] = "ACGTN"[(idx->S[(st + j) >> 3] >> (((st + j) & 7) << 2)) & 0xf];
+		}
+		gdh_device_index(idx, opt->pattern, opt->pattern_len);
 	}
-	if ((rc = gd_index_build(gd_multi_ctx(pl.gm, 0), pl.n_ref, pl.ref_off, pl.ref_len, pl.ref, idx->w, idx->k, opt->pattern, opt->pattern_len, &gi)) != GD_OK)
-		gdh_die(gd_strerror(gd_multi_ctx(pl.gm, 0)));
-	if ((rc = gd_multi_index_bcast(pl.gm, gi, 1)) != GD_OK) gdh_die(gd_multi_strerror(pl.gm));
-	if (mm_verbose >= 3)
-		fprintf(stderr, "[M::%s::%.3f*%.2f] device index on %d GPU(s) in %.3f s (broadcast %.0f MB in %.3f s, %s)\n", __func__,
-		        realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), n_gpus, realtime() - t0, gd_multi_stat(pl.gm, "bcast_bytes") / 1e6,
-		        gd_multi_stat(pl.gm, "bcast_seconds"), gd_multi_stat(pl.gm, "bcast_path") == 1 ? "ncclBroadcast" : n_gpus > 1 ? "peer copies" : "single GPU");
+	pl.gm = gdh_dev.gm, pl.n_ref = gdh_dev.n_ref, pl.ref_names = gdh_dev.ref_names, pl.ref_off = gdh_dev.ref_off, pl.ref_len = gdh_dev.ref_len;
+	pl.ref = gdh_dev.ref;
 
 	t0 = realtime();
 	kt_pipeline(n_threads == 1 ? 1 : 3, gdh_worker, &pl, 3); /* reader, mapper and writer overlap (map.c:1316-1317) */
@@ -675,9 +813,6 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 		fprintf(stderr, "[M::%s] %ld reads, %ld bases in %.3f s: %.0f reads/s (step seconds: read %.3f, map %.3f, write %.3f)\n", __func__,
 		        (long)pl.n_reads, (long)pl.n_bases, realtime() - t0, pl.n_reads / (realtime() - t0 + 1e-9), pl.t_read, pl.t_map, pl.t_write);
 
-	gd_multi_destroy(pl.gm);
-	gd_pinned_free(pl.ref);
-	free(pl.ref_names), free(pl.ref_off), free(pl.ref_len);
 	if (pl.fp) mm_bseq_close(pl.fp);
 	if (pl.map) munmap((void *)pl.map, pl.map_len);
 	return 0;

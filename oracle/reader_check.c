@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #define gd_pinned_alloc(n) malloc(n) /* no GPU here: the batch buffers are plain memory in this check */
 #define gd_pinned_free(p) free(p)
+#define GDH_READER_ONLY
 #include "../genome-on-diet_b200/host/gd_batched_host.c"
 
 int main(int argc, char **argv)

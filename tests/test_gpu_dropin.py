@@ -100,6 +100,37 @@ def test_batched_host_short_reads_sam_identical(flags, read_len, ragged):
             assert got2 == want, err[-1000:]
 
 
+@pytest.mark.skipif(not (os.path.exists(BATCHED_SR) and maplib.have_ref_program() and cpu_has_avx512()),
+                    reason="needs oracle/_ref/GDiet_cuda_batched_sr + GDiet_avx_sr (built where /root/reference exists)")
+def test_batched_host_index_paths():
+    """Where the batched host's index comes from: (a) a FASTA reference -- read by the host, index built on the device, no host
+    hash tables (the statistics line says so); (b) the same forced through the reference's mm_idx_gen (GDIET_REF_INDEX);
+    (c) an .mmi written by the reference program (-d): loaded by the reference's code, device index built from the sequences
+    it holds; (d) a reference cut into several index parts (-I): every part is mapped in turn as main.c loops.  SAM identical
+    to GDiet_avx each time."""
+    contigs, reads = maplib.make_dataset(seed=64, n_reads=3000, read_len=150)  # three contigs, 300 / 200 / 100 kbp
+    tmp = tempfile.mkdtemp(prefix="gdbatch_")
+    fa, fq, mmi = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq"), os.path.join(tmp, "ref.mmi")
+    maplib.write_fasta(fa, contigs)
+    maplib.write_fastq(fq, reads)
+    flags = ["-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200"]
+    want = run(maplib.REF_SR, flags, fa, fq, os.path.join(tmp, "cpu.sam"), 2)
+    got, err = run_env(BATCHED_SR, flags, fa, fq, os.path.join(tmp, "a.sam"), 3, {"GDIET_GPUS": "1"})
+    assert got == want and "(device index) distinct minimizers" in err and "device index on 1 GPU" in err, err[-1500:]
+    got, err = run_env(BATCHED_SR, flags, fa, fq, os.path.join(tmp, "b.sam"), 3, {"GDIET_GPUS": "1", "GDIET_REF_INDEX": "1"})
+    assert got == want and "(device index) distinct minimizers" not in err and "device index on 1 GPU" in err, err[-1500:]
+    p = subprocess.run([maplib.REF_SR, "-t", "2", "-x", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-d", mmi, fa],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and os.path.getsize(mmi) > 1000, p.stderr[-1000:]
+    want_mmi = run(maplib.REF_SR, flags, mmi, fq, os.path.join(tmp, "cpu_mmi.sam"), 2)
+    got, err = run_env(BATCHED_SR, flags, mmi, fq, os.path.join(tmp, "c.sam"), 3, {"GDIET_GPUS": "1"})
+    assert got == want_mmi and "device index on 1 GPU" in err, err[-1500:]
+    part = ["-I", str(max(len(c) for c in contigs) + 10)]  # every contig its own part (a part closes once it EXCEEDS -I bases)
+    want_parts = run(maplib.REF_SR, flags + part, fa, fq, os.path.join(tmp, "cpu_parts.sam"), 2)
+    got, err = run_env(BATCHED_SR, flags + part, fa, fq, os.path.join(tmp, "d.sam"), 3, {"GDIET_GPUS": "1"})
+    assert got == want_parts and err.count("device index on 1 GPU") >= 2, err[-1500:]
+
+
 @pytest.mark.skipif(not (os.path.exists(BATCHED_LR) and os.path.exists(maplib.REF_LR) and cpu_has_avx512()),
                     reason="needs oracle/_ref/GDiet_cuda_batched_lr + GDiet_avx_lr")
 def test_batched_host_long_reads_sam_identical():

@@ -33,6 +33,7 @@
  * input, PAF output, --split-prefix, --cs / --MD / --eqx / -y, splice mode, and (long reads) --sort=radix|heap.
  */
 #include <errno.h>
+#include <pthread.h>
 #include <fcntl.h>
 #include <stdio.h>
 #include <sys/mman.h>
@@ -56,6 +57,7 @@ typedef struct {
 	int map_last;              /* kseq's last_char: a header character already consumed (0 = none) */
 	int n_threads, n_processed;
 	int64_t mini_batch_size;
+	int plain_buffers;    /* the batch's bases go to plain memory (the reference reader of the index side), not to pinned buffers */
 	size_t par_min_bytes; /* the several-thread reader needs at least this many bytes per batch (smaller batches: one thread) */
 	long n_par_batches;   /* mini-batches read by the several-thread reader */
 	int64_t sub_bases; /* long reads: a mini-batch also ends at >= sub_bases bases and >= sub_reads reads (0: only at -K) */
@@ -75,6 +77,12 @@ typedef struct {
 	gd_sr_post_opt_t po;
 	double t_map, t_read, t_write;
 	int64_t n_reads, n_bases;
+	/* The text pieces of a mini-batch stay valid until the call after the next one (two alternating buffers per device), and
+	 * kt_pipeline lets batch b+2 enter the mapping step as soon as batch b+1 has LEFT it -- batch b may still be in the middle of
+	 * its write.  So the mapping step of batch b waits until batch b-2 has been written. */
+	pthread_mutex_t order_mu;
+	pthread_cond_t order_cv;
+	long n_batches, n_written;
 } gdh_pipeline_t;
 
 typedef struct {
@@ -89,6 +97,7 @@ typedef struct {
 	char **parts;
 	size_t *part_len;
 	int n_parts;
+	long batch; /* 0, 1, 2 ... in input order */
 } gdh_step_t;
 
 /* Page-locking memory is slow (tens of ms per 100 MB): the read buffers of the mini-batches in flight (at most three under
@@ -205,8 +214,8 @@ static int gdh_read_mapped(gdh_pipeline_t *p, gdh_step_t *s, int with_qual)
 	size_t guess;
 	if (p->sub_bases > 0 && p->sub_bases + p->sub_bases / 4 < want) want = p->sub_bases + p->sub_bases / 4; /* the usual end of a long-read batch */
 	guess = (size_t)want + 65536;
-	if ((i = gdh_read_fastq_par(p, s, with_qual)) >= 0) return i; /* strict four-line FASTQ: several threads */
-	gdh_str_need(&seq, guess, 1, &seq_pool);
+	if (!p->plain_buffers && (i = gdh_read_fastq_par(p, s, with_qual)) >= 0) return i; /* strict four-line FASTQ: several threads */
+	gdh_str_need(&seq, guess, !p->plain_buffers, &seq_pool);
 	if (with_qual) gdh_str_need(&qual, guess, GDH_QUAL_PINNED, &qual_pool);
 	while (1) {
 		size_t l0, q0;
@@ -244,7 +253,7 @@ static int gdh_read_mapped(gdh_pipeline_t *p, gdh_step_t *s, int with_qual)
 			if (c == '>' || c == '+' || c == '@') break;
 			if (c == '\n') { c = -1; continue; }
 			--p->map_pos; /* the character belongs to the line: first character + rest of the line, as kseq appends them */
-			gdh_line(p, &seq, l0, 1, &seq_pool);
+			gdh_line(p, &seq, l0, !p->plain_buffers, &seq_pool);
 			c = -1;
 		}
 		if (c == '>' || c == '@') p->map_last = c;
@@ -282,7 +291,8 @@ static int gdh_read_mapped(gdh_pipeline_t *p, gdh_step_t *s, int with_qual)
 		p->map_last = 0;
 	}
 	if (n == 0) {
-		if (seq.p) gdh_buf_put(seq.p, seq_pool);
+		if (seq.p && !p->plain_buffers) gdh_buf_put(seq.p, seq_pool);
+		else free(seq.p);
 		if (qual.p) gdh_qbuf_put(qual.p, qual_pool);
 		free(names.p), free(off), free(len), free(noff);
 		return 0;
@@ -505,6 +515,7 @@ static void *gdh_worker(void *shared, int step, void *in)
 					gdh_die("paired / multi-segment reads are not covered by the batched device path (use the GDiet_cuda build)");
 			}
 			p->n_processed += s->n, p->n_reads += s->n, p->n_bases += tot, p->t_read += realtime() - t0;
+			s->batch = p->n_batches++;
 			return s;
 		}
 		s->seq = mm_bseq_read3(p->fp, p->mini_batch_size, with_qual, 0, 0, &s->n);
@@ -530,11 +541,16 @@ static void *gdh_worker(void *shared, int step, void *in)
 			o += t->l_seq;
 		}
 		p->n_reads += s->n, p->n_bases += tot, p->t_read += realtime() - t0;
+		s->batch = p->n_batches++;
 		return s;
 	} else if (step == 1) { /* map + post-process the whole mini-batch on the GPUs (replaces kt_for(worker_for), map.c:1206) */
 		gdh_step_t *s = (gdh_step_t *)in;
-		double t0 = realtime();
+		double t0;
 		int rc;
+		pthread_mutex_lock(&p->order_mu);
+		while (p->n_written < s->batch - 1) pthread_cond_wait(&p->order_cv, &p->order_mu); /* batch b-2 is on disk: its text buffers are free */
+		pthread_mutex_unlock(&p->order_mu);
+		t0 = realtime();
 #ifdef GD_HOST_LR
 		rc = gd_multi_lr_map_sam(p->gm, s->n, s->names, s->off, s->len, s->buf, s->qual, &p->mo, &p->po, p->n_ref, p->ref_names, p->ref_off,
 		                         p->ref_len, p->ref, &s->parts, &s->part_len, &s->n_parts);
@@ -561,6 +577,10 @@ static void *gdh_worker(void *shared, int step, void *in)
 		if (s->qual) gdh_qbuf_put(s->qual, s->qual_cap);
 		gdh_buf_put(s->buf, s->buf_cap);
 		p->t_write += realtime() - t0;
+		pthread_mutex_lock(&p->order_mu);
+		++p->n_written;
+		pthread_cond_broadcast(&p->order_cv);
+		pthread_mutex_unlock(&p->order_mu);
 		if (mm_verbose >= 3)
 			fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", __func__, realtime() - mm_realtime0,
 			        cputime() / (realtime() - mm_realtime0), s->n);
@@ -584,9 +604,20 @@ static struct {
 static void gdh_devices(void)
 {
 	const char *env = getenv("GDIET_GPUS");
+	const double t0 = realtime();
 	if (gdh_dev.gm) return;
 	gdh_dev.n_gpus = env && atoi(env) > 0 ? atoi(env) : 1;
 	if (gd_multi_init(gdh_dev.n_gpus, 0, &gdh_dev.gm) != GD_OK) gdh_die("no usable CUDA device (there is no CPU fallback in this build)");
+	if (mm_verbose >= 3)
+		fprintf(stderr, "[M::%s::%.3f*%.2f] %d CUDA device(s) ready in %.3f s\n", __func__, realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0),
+		        gdh_dev.n_gpus, realtime() - t0);
+}
+/* creating the CUDA contexts takes a second or two: it runs beside the reading of the reference */
+static void *gdh_devices_thread(void *arg)
+{
+	(void)arg;
+	gdh_devices();
+	return 0;
 }
 
 static void gdh_drop_part(void)
@@ -627,49 +658,124 @@ void gdref_cpu_mm_idx_stat(const mm_idx_t *mi);
 void gdref_cpu_mm_idx_destroy(mm_idx_t *mi);
 mm_idx_t *mm_idx_init(int w, int k, int b, int flag); /* index.c:46 (not in a header) */
 
+/* The reference file itself: mm_idx_reader_open does not keep the name, so the open / eof / close trio is wrapped as well and a
+ * regular uncompressed file is mapped and parsed by the reader of this file (same kseq rules as for the reads; the
+ * reference's reader needs 7 s for 3.1 GB).  gzip / stdin references, .mmi files, -d and -H keep the reference's reader. */
+mm_idx_reader_t *gdref_cpu_mm_idx_reader_open(const char *fn, const mm_idxopt_t *opt, const char *fn_out);
+int gdref_cpu_mm_idx_reader_eof(const mm_idx_reader_t *r);
+void gdref_cpu_mm_idx_reader_close(mm_idx_reader_t *r);
+static struct {
+	const mm_idx_reader_t *r;
+	const char *map;
+	size_t len, pos;
+	int last;
+} gdh_refmap;
+
+mm_idx_reader_t *mm_idx_reader_open(const char *fn, const mm_idxopt_t *opt, const char *fn_out)
+{
+	mm_idx_reader_t *r = gdref_cpu_mm_idx_reader_open(fn, opt, fn_out);
+	struct stat st;
+	int fd;
+	if (!r || r->is_idx || fn_out || (opt->flag & MM_I_HPC) || getenv("GDIET_REF_INDEX") || getenv("GDIET_REF_READER") || !strcmp(fn, "-")) return r;
+	if ((fd = open(fn, O_RDONLY)) < 0) return r;
+	if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 2) {
+		void *mp = mmap(0, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+		if (mp != MAP_FAILED) {
+			const unsigned char *u = (const unsigned char *)mp;
+			if (u[0] == 0x1f && u[1] == 0x8b) munmap(mp, (size_t)st.st_size); /* gzip */
+			else {
+				madvise(mp, (size_t)st.st_size, MADV_SEQUENTIAL);
+				gdh_refmap.r = r, gdh_refmap.map = (const char *)mp, gdh_refmap.len = (size_t)st.st_size, gdh_refmap.pos = 0, gdh_refmap.last = 0;
+			}
+		}
+	}
+	close(fd);
+	return r;
+}
+
+int mm_idx_reader_eof(const mm_idx_reader_t *r)
+{
+	if (r && r == gdh_refmap.r) return gdh_refmap.pos >= gdh_refmap.len && gdh_refmap.last == 0;
+	return gdref_cpu_mm_idx_reader_eof(r);
+}
+
+void mm_idx_reader_close(mm_idx_reader_t *r)
+{
+	if (r && r == gdh_refmap.r) munmap((void *)gdh_refmap.map, gdh_refmap.len), memset(&gdh_refmap, 0, sizeof(gdh_refmap));
+	gdref_cpu_mm_idx_reader_close(r);
+}
+
+/* one mini-batch of reference sequences: from the mapped file, or through the reference's reader */
+typedef struct {
+	int n;
+	gdh_step_t st;       /* mapped file */
+	mm_bseq1_t *seq;     /* reference's reader */
+} gdh_refbatch_t;
+static int gdh_ref_next(mm_idx_reader_t *r, int64_t mini, gdh_refbatch_t *b)
+{
+	memset(b, 0, sizeof(*b));
+	if (r == gdh_refmap.r) {
+		gdh_pipeline_t q;
+		memset(&q, 0, sizeof(q));
+		q.map = gdh_refmap.map, q.map_len = gdh_refmap.len, q.map_pos = gdh_refmap.pos, q.map_last = gdh_refmap.last;
+		q.mini_batch_size = mini, q.n_threads = 1, q.plain_buffers = 1;
+		b->n = gdh_read_mapped(&q, &b->st, 0);
+		gdh_refmap.pos = q.map_pos, gdh_refmap.last = q.map_last;
+	} else b->seq = mm_bseq_read(r->fp.seq, mini, 0, &b->n);
+	return b->n;
+}
+
 /* mm_idx_reader_read (index.c:624-640) for a FASTA reference: what mm_idx_gen's step 0 does (index.c:309-364: names, lengths,
  * offsets; up to -I bases per part) with the bases kept as ASCII, then the device index instead of steps 1-2 + mm_idx_post. */
 mm_idx_t *mm_idx_reader_read(mm_idx_reader_t *r, int n_threads)
 {
 	mm_idx_t *mi;
 	uint64_t sum_len = 0, cap = 0;
+	pthread_t dev_thread;
+	int have_thread = 0;
+	const int64_t mini = (uint64_t)r->opt.mini_batch_size < r->opt.batch_size ? r->opt.mini_batch_size : (int64_t)r->opt.batch_size; /* index.c:394 */
 	if (r->is_idx || r->fp_out || (r->opt.flag & MM_I_HPC) || getenv("GDIET_REF_INDEX")) return gdref_cpu_mm_idx_reader_read(r, n_threads);
-	if (r->fp.seq == 0 || mm_bseq_eof(r->fp.seq)) return 0;
+	if (r == gdh_refmap.r ? mm_idx_reader_eof(r) : (r->fp.seq == 0 || mm_bseq_eof(r->fp.seq))) return 0;
 	gdh_drop_part();
+	if (!gdh_dev.gm) have_thread = pthread_create(&dev_thread, 0, gdh_devices_thread, 0) == 0;
 	mi = mm_idx_init(r->opt.w, r->opt.k, r->opt.bucket_bits, r->opt.flag);
-	while (sum_len <= r->opt.batch_size) {
-		int n = 0, i;
-		mm_bseq1_t *seq = mm_bseq_read(r->fp.seq, r->opt.mini_batch_size, 0, &n);
+	while (sum_len <= r->opt.batch_size) { /* (index.c:311-314: a part is closed by the first mini-batch that takes it past -I) */
+		gdh_refbatch_t b;
+		int n, i;
 		uint32_t old_m, m;
 		uint64_t add = 0;
-		if (!seq) break;
+		if ((n = gdh_ref_next(r, mini, &b)) <= 0) break;
 		old_m = mi->n_seq, m = mi->n_seq + n;
 		kroundup32(m);
 		kroundup32(old_m);
 		if (old_m != m) mi->seq = (mm_idx_seq_t *)krealloc(mi->km, mi->seq, m * sizeof(mm_idx_seq_t));
-		for (i = 0; i < n; ++i) add += seq[i].l_seq;
+		for (i = 0; i < n; ++i) add += b.seq ? b.seq[i].l_seq : b.st.len[i];
 		if (sum_len + add + 16 > cap) {
 			cap = (sum_len + add) + (sum_len + add) / 2 + 4096;
 			if (!(gdh_dev.ref = (char *)realloc(gdh_dev.ref, cap))) gdh_die("out of memory for the reference sequences");
 		}
 		for (i = 0; i < n; ++i) {
 			mm_idx_seq_t *t = &mi->seq[mi->n_seq++];
+			const char *name = b.seq ? b.seq[i].name : b.st.names[i];
+			const uint32_t l = b.seq ? (uint32_t)b.seq[i].l_seq : (uint32_t)b.st.len[i];
 			if (!(mi->flag & MM_I_NO_NAME)) {
-				t->name = (char *)kmalloc(mi->km, strlen(seq[i].name) + 1);
-				strcpy(t->name, seq[i].name);
+				t->name = (char *)kmalloc(mi->km, strlen(name) + 1);
+				strcpy(t->name, name);
 			} else t->name = 0;
-			t->len = seq[i].l_seq, t->offset = sum_len, t->is_alt = 0;
-			memcpy(gdh_dev.ref + sum_len, seq[i].seq, seq[i].l_seq);
-			sum_len += seq[i].l_seq;
-			if (seq[i].l_seq == 0 && mm_verbose >= 2) fprintf(stderr, "[WARNING] the length database sequence '%s' is 0\n", seq[i].name);
-			free(seq[i].seq), free(seq[i].name);
+			t->len = l, t->offset = sum_len, t->is_alt = 0;
+			memcpy(gdh_dev.ref + sum_len, b.seq ? b.seq[i].seq : b.st.buf + b.st.off[i], l);
+			sum_len += l;
+			if (l == 0 && mm_verbose >= 2) fprintf(stderr, "[WARNING] the length database sequence '%s' is 0\n", name);
+			if (b.seq) free(b.seq[i].seq), free(b.seq[i].name);
 		}
-		free(seq);
+		if (b.seq) free(b.seq);
+		else free(b.st.buf), free(b.st.off), free(b.st.len), free((void *)b.st.names), free(b.st.name_blob);
 	}
 	if (mm_verbose >= 3)
 		fprintf(stderr, "[M::%s::%.3f*%.2f] read %u reference sequences, %ld bases\n", __func__, realtime() - mm_realtime0,
 		        cputime() / (realtime() - mm_realtime0), mi->n_seq, (long)sum_len);
 	/* (mi->S stays empty: nothing on this path reads it; the flag word is left alone because main.c tests MM_I_NO_SEQ) */
+	if (have_thread) pthread_join(dev_thread, 0);
 	gdh_device_index(mi, r->opt.pattern, r->opt.pattern_len);
 	mi->index = r->n_parts++;
 	return mi;
@@ -751,6 +857,7 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 	if (n_segs < 1) return -1;
 	gdh_refuse_uncovered(opt, n_segs);
 	memset(&pl, 0, sizeof(pl));
+	pthread_mutex_init(&pl.order_mu, 0), pthread_cond_init(&pl.order_cv, 0);
 	{ /* a regular, uncompressed file is mapped and parsed in place; gzip / stdin input goes through the reference's reader */
 		struct stat st;
 		int fd = strcmp(fn[0], "-") ? open(fn[0], O_RDONLY) : -1;
@@ -779,14 +886,14 @@ int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_
 	gdh_options(&pl);
 	gdh_devices();
 #ifdef GD_HOST_LR
-	/* -K 500M (the long-read default) often makes a whole file ONE mini-batch: nothing of the three pipeline steps overlaps then.
-	 * Records are independent and written in input order, so the text does not depend on where batches end: a batch is also
-	 * closed once it holds enough work for the devices (per GPU: two 64 Mbase slices would be better for one call, but 64 Mbases
-	 * and 4,096 reads keep the DP launches full while the reader and the writer run beside the device). */
+	/* Optional (GDIET_LR_BATCH_BASES / GDIET_LR_BATCH_READS): close a mini-batch before -K once it holds that many bases AND
+	 * reads.  Records are independent and written in input order, so the text does not depend on where batches end.  Off by
+	 * default: measured on configs 3 and 4 it buys nothing (reading and writing are ~10 % of the mapping time) and an ONT batch
+	 * cut in two leaves the second DP launch with a fifth of the pairs. */
 	{
-		const char *e = getenv("GDIET_LR_BATCH_BASES"), *e2 = getenv("GDIET_LR_BATCH_READS"); /* (0 bases: only -K ends a batch) */
-		pl.sub_bases = e ? atoll(e) : (int64_t)gdh_dev.n_gpus * (64ll << 20);
-		pl.sub_reads = e2 ? atoi(e2) : gdh_dev.n_gpus * 4096;
+		const char *e = getenv("GDIET_LR_BATCH_BASES"), *e2 = getenv("GDIET_LR_BATCH_READS");
+		pl.sub_bases = e ? atoll(e) : 0;
+		pl.sub_reads = e2 ? atoi(e2) : 0;
 	}
 #endif
 	if (gdh_dev.mi != idx) { /* the index came from an .mmi (or the reference's mm_idx_gen): the contigs it holds, as ASCII */

@@ -103,8 +103,8 @@ def test_batched_host_short_reads_sam_identical(flags, read_len, ragged):
 @pytest.mark.skipif(not (os.path.exists(BATCHED_SR) and maplib.have_ref_program() and cpu_has_avx512()),
                     reason="needs oracle/_ref/GDiet_cuda_batched_sr + GDiet_avx_sr (built where /root/reference exists)")
 def test_batched_host_index_paths():
-    """Where the batched host's index comes from: (a) a FASTA reference -- read by the host, index built on the device, no host
-    hash tables (the statistics line says so); (b) the same forced through the reference's mm_idx_gen (GDIET_REF_INDEX);
+    """Where the batched host's index comes from: (a) a FASTA reference -- mapped and parsed by the host file (a gzip one: read
+    through the reference's reader), index built on the device, no host hash tables (the statistics line says so); (b) the same forced through the reference's mm_idx_gen (GDIET_REF_INDEX);
     (c) an .mmi written by the reference program (-d): loaded by the reference's code, device index built from the sequences
     it holds; (d) a reference cut into several index parts (-I): every part is mapped in turn as main.c loops.  SAM identical
     to GDiet_avx each time."""
@@ -119,6 +119,11 @@ def test_batched_host_index_paths():
     assert got == want and "(device index) distinct minimizers" in err and "device index on 1 GPU" in err, err[-1500:]
     got, err = run_env(BATCHED_SR, flags, fa, fq, os.path.join(tmp, "b.sam"), 3, {"GDIET_GPUS": "1", "GDIET_REF_INDEX": "1"})
     assert got == want and "(device index) distinct minimizers" not in err and "device index on 1 GPU" in err, err[-1500:]
+    import gzip
+    with open(fa, "rb") as f, gzip.open(fa + ".gz", "wb", compresslevel=1) as g:  # a gzip reference goes through the reference's reader
+        g.write(f.read())
+    got, err = run_env(BATCHED_SR, flags, fa + ".gz", fq, os.path.join(tmp, "gz.sam"), 3, {"GDIET_GPUS": "1"})
+    assert got == want and "(device index) distinct minimizers" in err, err[-1500:]
     p = subprocess.run([maplib.REF_SR, "-t", "2", "-x", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-d", mmi, fa],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and os.path.getsize(mmi) > 1000, p.stderr[-1000:]

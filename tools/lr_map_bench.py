@@ -98,6 +98,7 @@ def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
                      "reads_per_s_pipeline": (n_reads / float(mm.group(2))) if mm else None,
                      "summary": mm.group(0)[:300] if mm else pb.stderr[-300:],
                      "sam_file_identical": pb.returncode == 0 and strip(samb) == want_sam}
+                r["log"] = [l[:160] for l in pb.stderr.splitlines() if l.startswith("[M::") and "mapped" not in l][:24]  # (time stamps of the phases)
                 if "GD_MAP_PROFILE" in env:
                     r["profile"] = [l for l in pb.stderr.splitlines() if l.startswith("[gd_")][:80]
                 return r
@@ -108,9 +109,9 @@ def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
                 file_runs["batched_host_ncu"] = run_batched([], {}, ("ncu", "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "--csv",
                                                                "--log-file", os.environ["LR_BATCHED_NCU"]))
             if os.environ.get("LR_BATCHED_PROBE"):  # where the time of the file-to-file pipeline goes: mini-batch size, device slices
+                sub = {"GDIET_LR_BATCH_BASES": str(64 << 20), "GDIET_LR_BATCH_READS": "4096"}
                 file_runs["batched_host_probe"] = [run_batched(f, e) for f, e in (
-                    ([], {"GD_MAP_PROFILE": "1"}), (["-K", "100M"], {}), (["-K", "50M"], {}), (["-K", "50M"], {"GD_MAP_PROFILE": "1"}),
-                    ([], {"GDIET_LR_SLICE_READS": "100000000"}))]
+                    ([], {}), ([], sub), ([], {}), ([], sub), ([], {"GD_MAP_PROFILE": "1"}), ([], dict(sub, GD_MAP_PROFILE="1")))]
     ctx.set_option("time_kernels", 1)
     t0 = time.perf_counter()
     idx = ctx.index_build(contigs, w, k, "10")

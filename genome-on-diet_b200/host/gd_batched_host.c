@@ -725,6 +725,112 @@ static int gdh_ref_next(mm_idx_reader_t *r, int64_t mini, gdh_refbatch_t *b)
 	return b->n;
 }
 
+/* A FASTA reference that fits one index part (the usual case: -I 4G) is parsed on several threads: the lines that start with
+ * '>' cut the file into records (kseq ends a sequence at such a line, kseq.h:209), every record goes through the reader above on
+ * its own byte range, and the pieces are copied to their places.  A line that starts with '@' or '+' (FASTQ, where a quality
+ * line may start with '>') or a record that does not come back as exactly one sequence sends the file to the one-thread path. */
+typedef struct {
+	const char *map;
+	size_t len;
+	int n_threads;
+	size_t **starts;    /* per scan range: the record starts found in it */
+	int *n_starts, *bad;
+	size_t *rec_beg, *rec_end;
+	gdh_step_t *rec;    /* per record: what the reader made of it */
+	int *rec_bad;
+	char *dst;
+	uint64_t *dst_off;
+} gdh_refpar_t;
+static void gdh_refpar_scan(void *data, long i, int tid)
+{
+	gdh_refpar_t *P = (gdh_refpar_t *)data;
+	const size_t lo = P->len / (size_t)P->n_threads * (size_t)i, hi = i + 1 == P->n_threads ? P->len : P->len / (size_t)P->n_threads * (size_t)(i + 1);
+	const char *q = P->map + lo, *e = P->map + hi;
+	int n = 0, m = 0;
+	size_t *a = 0;
+	(void)tid;
+	if (lo > 0) { /* the first line start inside the range */
+		q = (const char *)memchr(P->map + lo - 1, '\n', hi - (lo - 1));
+		q = q ? q + 1 : e;
+	}
+	while (q < e) {
+		const char *nl;
+		if (*q == '>') {
+			if (n == m) m = m ? m * 2 : 64, a = (size_t *)realloc(a, sizeof(size_t) * m);
+			a[n++] = (size_t)(q - P->map);
+		} else if (*q == '@' || *q == '+') P->bad[i] = 1;
+		nl = (const char *)memchr(q, '\n', (size_t)(P->map + P->len - q));
+		if (!nl) break;
+		q = nl + 1;
+	}
+	P->starts[i] = a, P->n_starts[i] = n;
+}
+static void gdh_refpar_parse(void *data, long i, int tid)
+{
+	gdh_refpar_t *P = (gdh_refpar_t *)data;
+	gdh_pipeline_t q;
+	(void)tid;
+	memset(&q, 0, sizeof(q));
+	q.map = P->map, q.map_len = P->rec_end[i], q.map_pos = P->rec_beg[i], q.mini_batch_size = INT64_MAX, q.n_threads = 1, q.plain_buffers = 1;
+	if (gdh_read_mapped(&q, &P->rec[i], 0) != 1 || q.map_pos < q.map_len || q.map_last != 0) P->rec_bad[i] = 1;
+}
+static void gdh_refpar_copy(void *data, long i, int tid)
+{
+	gdh_refpar_t *P = (gdh_refpar_t *)data;
+	(void)tid;
+	memcpy(P->dst + P->dst_off[i], P->rec[i].buf + P->rec[i].off[0], (size_t)P->rec[i].len[0]);
+}
+/* fills mi->seq / gdh_dev.ref from the whole mapped file; 0 = not this way (nothing has changed) */
+static int gdh_ref_parallel(mm_idx_reader_t *r, mm_idx_t *mi, int n_threads, uint64_t *sum_len_out)
+{
+	gdh_refpar_t P;
+	int T = n_threads < 16 ? n_threads : 16, i, n_rec = 0, k = 0, ok = 1;
+	uint64_t sum = 0;
+	if (r != gdh_refmap.r || gdh_refmap.pos != 0 || gdh_refmap.last != 0 || T < 4 || gdh_refmap.len < (getenv("GDIET_REF_PAR_MIN_BYTES") ? (size_t)atoll(getenv("GDIET_REF_PAR_MIN_BYTES")) : (size_t)4 << 20) ||
+	    (uint64_t)gdh_refmap.len > r->opt.batch_size || gdh_refmap.map[0] != '>' || getenv("GDIET_REF_ONE_THREAD")) return 0;
+	memset(&P, 0, sizeof(P));
+	P.map = gdh_refmap.map, P.len = gdh_refmap.len, P.n_threads = T;
+	P.starts = (size_t **)calloc(T, sizeof(size_t *)), P.n_starts = (int *)calloc(T, sizeof(int)), P.bad = (int *)calloc(T, sizeof(int));
+	kt_for(T, gdh_refpar_scan, &P, T);
+	for (i = 0; i < T; ++i) n_rec += P.n_starts[i], ok &= !P.bad[i];
+	if (ok && n_rec > 0) {
+		P.rec_beg = (size_t *)malloc(sizeof(size_t) * n_rec), P.rec_end = (size_t *)malloc(sizeof(size_t) * n_rec);
+		P.rec = (gdh_step_t *)calloc(n_rec, sizeof(gdh_step_t)), P.rec_bad = (int *)calloc(n_rec, sizeof(int));
+		P.dst_off = (uint64_t *)malloc(sizeof(uint64_t) * n_rec);
+		for (i = 0; i < T; ++i) {
+			int j;
+			for (j = 0; j < P.n_starts[i]; ++j) P.rec_beg[k++] = P.starts[i][j];
+		}
+		for (i = 0; i < n_rec; ++i) P.rec_end[i] = i + 1 < n_rec ? P.rec_beg[i + 1] : P.len;
+		kt_for(T, gdh_refpar_parse, &P, n_rec);
+		for (i = 0; i < n_rec; ++i) ok &= !P.rec_bad[i];
+		if (ok) {
+			for (i = 0; i < n_rec; ++i) P.dst_off[i] = sum, sum += (uint64_t)P.rec[i].len[0];
+			if (!(gdh_dev.ref = (char *)malloc((size_t)sum + 16))) gdh_die("out of memory for the reference sequences");
+			P.dst = gdh_dev.ref;
+			kt_for(T, gdh_refpar_copy, &P, n_rec);
+			mi->seq = (mm_idx_seq_t *)krealloc(mi->km, mi->seq, ((size_t)n_rec + 1) * sizeof(mm_idx_seq_t));
+			for (i = 0; i < n_rec; ++i) {
+				mm_idx_seq_t *t = &mi->seq[mi->n_seq++];
+				const char *name = P.rec[i].names[0];
+				if (!(mi->flag & MM_I_NO_NAME)) {
+					t->name = (char *)kmalloc(mi->km, strlen(name) + 1);
+					strcpy(t->name, name);
+				} else t->name = 0;
+				t->len = (uint32_t)P.rec[i].len[0], t->offset = P.dst_off[i], t->is_alt = 0;
+				if (t->len == 0 && mm_verbose >= 2) fprintf(stderr, "[WARNING] the length database sequence '%s' is 0\n", name);
+			}
+			gdh_refmap.pos = gdh_refmap.len, gdh_refmap.last = 0;
+			*sum_len_out = sum;
+		}
+		for (i = 0; i < n_rec; ++i)
+			free(P.rec[i].buf), free(P.rec[i].off), free(P.rec[i].len), free((void *)P.rec[i].names), free(P.rec[i].name_blob);
+	} else ok = 0;
+	for (i = 0; i < T; ++i) free(P.starts[i]);
+	free(P.starts), free(P.n_starts), free(P.bad), free(P.rec_beg), free(P.rec_end), free(P.rec), free(P.rec_bad), free(P.dst_off);
+	return ok;
+}
+
 /* mm_idx_reader_read (index.c:624-640) for a FASTA reference: what mm_idx_gen's step 0 does (index.c:309-364: names, lengths,
  * offsets; up to -I bases per part) with the bases kept as ASCII, then the device index instead of steps 1-2 + mm_idx_post. */
 mm_idx_t *mm_idx_reader_read(mm_idx_reader_t *r, int n_threads)
@@ -732,14 +838,15 @@ mm_idx_t *mm_idx_reader_read(mm_idx_reader_t *r, int n_threads)
 	mm_idx_t *mi;
 	uint64_t sum_len = 0, cap = 0;
 	pthread_t dev_thread;
-	int have_thread = 0;
+	int have_thread = 0, par = 0;
 	const int64_t mini = (uint64_t)r->opt.mini_batch_size < r->opt.batch_size ? r->opt.mini_batch_size : (int64_t)r->opt.batch_size; /* index.c:394 */
 	if (r->is_idx || r->fp_out || (r->opt.flag & MM_I_HPC) || getenv("GDIET_REF_INDEX")) return gdref_cpu_mm_idx_reader_read(r, n_threads);
 	if (r == gdh_refmap.r ? mm_idx_reader_eof(r) : (r->fp.seq == 0 || mm_bseq_eof(r->fp.seq))) return 0;
 	gdh_drop_part();
 	if (!gdh_dev.gm) have_thread = pthread_create(&dev_thread, 0, gdh_devices_thread, 0) == 0;
 	mi = mm_idx_init(r->opt.w, r->opt.k, r->opt.bucket_bits, r->opt.flag);
-	while (sum_len <= r->opt.batch_size) { /* (index.c:311-314: a part is closed by the first mini-batch that takes it past -I) */
+	if (gdh_ref_parallel(r, mi, n_threads, &sum_len)) cap = sum_len + 16, par = 1;
+	else while (sum_len <= r->opt.batch_size) { /* (index.c:311-314: a part is closed by the first mini-batch that takes it past -I) */
 		gdh_refbatch_t b;
 		int n, i;
 		uint32_t old_m, m;
@@ -772,8 +879,8 @@ mm_idx_t *mm_idx_reader_read(mm_idx_reader_t *r, int n_threads)
 		else free(b.st.buf), free(b.st.off), free(b.st.len), free((void *)b.st.names), free(b.st.name_blob);
 	}
 	if (mm_verbose >= 3)
-		fprintf(stderr, "[M::%s::%.3f*%.2f] read %u reference sequences, %ld bases\n", __func__, realtime() - mm_realtime0,
-		        cputime() / (realtime() - mm_realtime0), mi->n_seq, (long)sum_len);
+		fprintf(stderr, "[M::%s::%.3f*%.2f] read %u reference sequences, %ld bases%s\n", __func__, realtime() - mm_realtime0,
+		        cputime() / (realtime() - mm_realtime0), mi->n_seq, (long)sum_len, par ? " (records parsed on several threads)" : "");
 	/* (mi->S stays empty: nothing on this path reads it; the flag word is left alone because main.c tests MM_I_NO_SEQ) */
 	if (have_thread) pthread_join(dev_thread, 0);
 	gdh_device_index(mi, r->opt.pattern, r->opt.pattern_len);

@@ -119,6 +119,20 @@ def test_batched_host_index_paths():
     assert got == want and "(device index) distinct minimizers" in err and "device index on 1 GPU" in err, err[-1500:]
     got, err = run_env(BATCHED_SR, flags, fa, fq, os.path.join(tmp, "b.sam"), 3, {"GDIET_GPUS": "1", "GDIET_REF_INDEX": "1"})
     assert got == want and "(device index) distinct minimizers" not in err and "device index on 1 GPU" in err, err[-1500:]
+    # the same reference with 60-column lines, CRLF in one record, blank lines and an empty record, parsed record-wise on several threads
+    fa60 = os.path.join(tmp, "ref60.fa")
+    with open(fa60, "wb") as f:
+        for i, c in enumerate(contigs):
+            nl = b"\r\n" if i == 1 else b"\n"
+            f.write(b">chr%d some description" % (i + 1) + nl)
+            b = bytes(c)
+            f.write(b"".join(b[j:j + 60] + nl for j in range(0, len(b), 60)))
+            if i == 0:
+                f.write(b"\n\n")
+    got, err = run_env(BATCHED_SR, flags, fa60, fq, os.path.join(tmp, "p.sam"), 4, {"GDIET_GPUS": "1", "GDIET_REF_PAR_MIN_BYTES": "0"})
+    assert got == want and "records parsed on several threads" in err, err[-1500:]
+    got, err = run_env(BATCHED_SR, flags, fa60, fq, os.path.join(tmp, "p1.sam"), 4, {"GDIET_GPUS": "1", "GDIET_REF_ONE_THREAD": "1"})
+    assert got == want and "records parsed on several threads" not in err, err[-1500:]
     import gzip
     with open(fa, "rb") as f, gzip.open(fa + ".gz", "wb", compresslevel=1) as g:  # a gzip reference goes through the reference's reader
         g.write(f.read())

@@ -109,9 +109,9 @@ def run(ctx, kind="hifi", ref_mbp=100, n_reads=2000, n_check=100, run_ref=True):
                 file_runs["batched_host_ncu"] = run_batched([], {}, ("ncu", "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "--csv",
                                                                "--log-file", os.environ["LR_BATCHED_NCU"]))
             if os.environ.get("LR_BATCHED_PROBE"):  # where the time of the file-to-file pipeline goes: mini-batch size, device slices
-                sub = {"GDIET_LR_BATCH_BASES": str(64 << 20), "GDIET_LR_BATCH_READS": "4096"}
+                eager = {"CUDA_MODULE_LOADING": "EAGER"}
                 file_runs["batched_host_probe"] = [run_batched(f, e) for f, e in (
-                    ([], {}), ([], sub), ([], {}), ([], sub), ([], {"GD_MAP_PROFILE": "1"}), ([], dict(sub, GD_MAP_PROFILE="1")))]
+                    ([], {}), ([], eager), ([], {}), ([], eager), ([], {"GD_MAP_PROFILE": "1"}), ([], dict(eager, GD_MAP_PROFILE="1")))]
     ctx.set_option("time_kernels", 1)
     t0 = time.perf_counter()
     idx = ctx.index_build(contigs, w, k, "10")

@@ -26,6 +26,55 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
     lens = np.full(n_reads, 150, np.int32)
     buf = np.ascontiguousarray(reads.reshape(-1))
     qual = np.full(n_reads * 150, ord("I"), np.uint8)
+    # ---- whole programs, file to file, BEFORE this process takes device memory for its own contexts (a second process next to a
+    # loaded one gets what is left of the HBM and shares the page-locking path): the unmodified reference, then the batched C host
+    file_runs, want = {}, None
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_avx_sr")
+    batched_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_cuda_batched_sr")
+    if run_ref and os.path.exists(ref_bin):
+        import maplib
+        tmp = tempfile.mkdtemp(prefix="gdref_")
+        fa, fq, samf = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq"), os.path.join(tmp, "out.sam")
+        maplib.write_fasta(fa, contigs)
+        maplib.write_fastq(fq, reads)
+        t0 = time.perf_counter()
+        p = subprocess.run([ref_bin, "-t", str(cores), "-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200",
+                            "-o", samf, fa, fq], capture_output=True, text=True)
+        wall = time.perf_counter() - t0
+        prof = dict(re.findall(r"\[PROFILING\] (.+?) time: (\d+) ns", p.stderr))
+        t_idx = int(prof.get("indexing", 0)) * 1e-9
+        want = [l for l in open(samf).read().splitlines() if not l.startswith("@")]
+        file_runs["reference"] = {"wall_s": round(wall, 3), "indexing_s": round(t_idx, 3), "reads_per_s": n_reads / max(wall - t_idx, 1e-9),
+                            "threads": cores, "profile_thread_seconds": {k: round(int(v) * 1e-9, 3) for k, v in prof.items()}}
+        # ---- the batched C host (INTEGRATION.md level 2): the same program with genome-on-diet_b200/host/gd_batched_host.c in place
+        # of map.c's pipeline -- FASTQ parsing, mapping on the GPU, SAM file written, one process, same flags
+        if os.path.exists(batched_bin):
+            def run_batched(kflag, env):
+                samb = os.path.join(tmp, "batched.sam")
+                t0 = time.perf_counter()
+                pb = subprocess.run([batched_bin, "-t", str(cores), "-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200"]
+                                    + kflag + ["-o", samb, fa, fq], capture_output=True, text=True, env=dict(os.environ, GDIET_GPUS="1", **env))
+                wall_b = time.perf_counter() - t0
+                mm = re.search(r"\[M::mm_map_file_frag\] (\d+) reads, \d+ bases in ([0-9.]+) s", pb.stderr)
+                ix = re.search(r"\[PROFILING\] indexing time: (\d+) ns", pb.stderr)
+                gotb = [l for l in open(samb).read().splitlines() if not l.startswith("@")] if pb.returncode == 0 else []
+                r = {"flags": kflag, "returncode": pb.returncode,
+                     "wall_s": round(wall_b, 3), "indexing_s": round(int(ix.group(1)) * 1e-9, 3) if ix else None,
+                     "map_pipeline_s": float(mm.group(2)) if mm else None,
+                     "reads_per_s_pipeline": (n_reads / float(mm.group(2))) if mm else None,
+                     "summary": (re.search(r"\[M::mm_map_file_frag\] .*", pb.stderr) or [""])[0][:300],
+                     "sam_identical": gotb == want}
+                if "GD_MAP_PROFILE" in env:
+                    r["profile"] = [l for l in pb.stderr.splitlines() if l.startswith("[gd_")][:60]
+                return r
+
+            file_runs["batched_host"] = dict(binary="oracle/_ref/GDiet_cuda_batched_sr (unmodified reference sources + gd_batched_host.c)",
+                                       mini_batch="-K 30M (200 k reads per batch)",
+                                       note="map_pipeline_s = FASTQ parse + GPU mapping + SAM file write under kt_pipeline (after the index and the CUDA context exist)",
+                                       **run_batched(["-K", "30M"], {}))
+            if os.environ.get("SR_BATCHED_PROBE"):  # mini-batch size and the phases of one call
+                file_runs["batched_host_probe"] = [run_batched(k, e) for k, e in (([], {}), (["-K", "30M"], {"GD_MAP_PROFILE": "1"}), (["-K", "150M"], {}),
+                                                                             (["-K", "500M"], {}), (["-K", "500M"], {"GD_MAP_PROFILE": "1"}))]
     opt, post = gd.sr_options(), gd.sr_post_options()
     t0 = time.perf_counter()
     idx = ctx.index_build(contigs, 11, 21, "10")
@@ -120,55 +169,12 @@ def run(ctx, ref_mbp=5, n_reads=100_000, run_ref=True):
     out["map_sam_device_s"] = round(dev_s, 4)
     out["reads_per_s_device_sam"] = n_reads / dev_s
     out["device_sam_identical_to_host_stage"] = b"".join(ctypes.string_at(a, l) for a, l in pieces) == sam
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_avx_sr")
-    batched_bin = os.path.join(ROOT, "oracle", "_ref", "GDiet_cuda_batched_sr")
-    if run_ref and os.path.exists(ref_bin):
-        import maplib
-        tmp = tempfile.mkdtemp(prefix="gdref_")
-        fa, fq, samf = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "reads.fq"), os.path.join(tmp, "out.sam")
-        maplib.write_fasta(fa, contigs)
-        maplib.write_fastq(fq, reads)
-        t0 = time.perf_counter()
-        p = subprocess.run([ref_bin, "-t", str(cores), "-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200",
-                            "-o", samf, fa, fq], capture_output=True, text=True)
-        wall = time.perf_counter() - t0
-        prof = dict(re.findall(r"\[PROFILING\] (.+?) time: (\d+) ns", p.stderr))
-        t_idx = int(prof.get("indexing", 0)) * 1e-9
-        want = [l for l in open(samf).read().splitlines() if not l.startswith("@")]
+    if want is not None:
         got = sam.decode().splitlines()
-        out["reference"] = {"wall_s": round(wall, 3), "indexing_s": round(t_idx, 3), "reads_per_s": n_reads / max(wall - t_idx, 1e-9),
-                            "threads": cores, "profile_thread_seconds": {k: round(int(v) * 1e-9, 3) for k, v in prof.items()}}
+        out.update(file_runs)
         out["sam_identical"] = got == want
         out["sam_lines"] = len(want)
-        # ---- the batched C host (INTEGRATION.md level 2): the same program with genome-on-diet_b200/host/gd_batched_host.c in place
-        # of map.c's pipeline -- FASTQ parsing, mapping on the GPU, SAM file written, one process, same flags
-        if os.path.exists(batched_bin):
-            def run_batched(kflag, env):
-                samb = os.path.join(tmp, "batched.sam")
-                t0 = time.perf_counter()
-                pb = subprocess.run([batched_bin, "-t", str(cores), "-ax", "sr", "-Z", "10", "-W", "2", "-k", "21", "-w", "11", "-r", "0.05,150,200"]
-                                    + kflag + ["-o", samb, fa, fq], capture_output=True, text=True, env=dict(os.environ, GDIET_GPUS="1", **env))
-                wall_b = time.perf_counter() - t0
-                mm = re.search(r"\[M::mm_map_file_frag\] (\d+) reads, \d+ bases in ([0-9.]+) s", pb.stderr)
-                ix = re.search(r"\[PROFILING\] indexing time: (\d+) ns", pb.stderr)
-                gotb = [l for l in open(samb).read().splitlines() if not l.startswith("@")] if pb.returncode == 0 else []
-                r = {"flags": kflag, "returncode": pb.returncode,
-                     "wall_s": round(wall_b, 3), "indexing_s": round(int(ix.group(1)) * 1e-9, 3) if ix else None,
-                     "map_pipeline_s": float(mm.group(2)) if mm else None,
-                     "reads_per_s_pipeline": (n_reads / float(mm.group(2))) if mm else None,
-                     "summary": (re.search(r"\[M::mm_map_file_frag\] .*", pb.stderr) or [""])[0][:300],
-                     "sam_identical": gotb == want}
-                if "GD_MAP_PROFILE" in env:
-                    r["profile"] = [l for l in pb.stderr.splitlines() if l.startswith("[gd_")][:60]
-                return r
-
-            out["batched_host"] = dict(binary="oracle/_ref/GDiet_cuda_batched_sr (unmodified reference sources + gd_batched_host.c)",
-                                       mini_batch="-K 30M (200 k reads per batch)",
-                                       note="map_pipeline_s = FASTQ parse + GPU mapping + SAM file write under kt_pipeline (after the index and the CUDA context exist)",
-                                       **run_batched(["-K", "30M"], {}))
-            if os.environ.get("SR_BATCHED_PROBE"):  # mini-batch size and the phases of one call
-                out["batched_host_probe"] = [run_batched(k, e) for k, e in (([], {}), (["-K", "30M"], {"GD_MAP_PROFILE": "1"}), (["-K", "150M"], {}),
-                                                                             (["-K", "500M"], {}), (["-K", "500M"], {"GD_MAP_PROFILE": "1"}))]
+    if want is not None:
         if got != want:
             bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
             out["sam_first_diff"] = [got[bad[0]][:300], want[bad[0]][:300]] if bad else ["length", "%d vs %d" % (len(got), len(want))]

@@ -60,6 +60,8 @@ extern "C" int gd_init(int device, gd_ctx **out)
 		return GD_ERR_NO_DEVICE;
 	}
 	gd_ctx *ctx = new gd_ctx();
+	if (const char *e = getenv("GDIET_MAP_LANES")) // lanes of the mapping stage (contexts + host threads that drive alternate slices)
+		if (atol(e) >= 1 && atol(e) <= 8) ctx->opt_map_lanes = atol(e);
 	ctx->device = device;
 	ctx->sms = prop.multiProcessorCount;
 	ctx->smem_optin = prop.sharedMemPerBlockOptin;
@@ -157,7 +159,11 @@ extern "C" long gd_get_stat(const gd_ctx *cctx, const char *key)
 			return 0;
 		}
 	}
-	if (!strcmp(key, "kernel_launches")) return ctx->stat_launches + (ctx->peer ? ctx->peer->stat_launches : 0);
+	if (!strcmp(key, "kernel_launches")) {
+		long t = 0;
+		for (const gd_ctx *c = ctx; c; c = c->peer) t += c->stat_launches; // every lane of the mapping stage
+		return t;
+	}
 	if (!strcmp(key, "ksw_ring")) return ctx->stat_ksw_ring;
 	if (!strcmp(key, "ksw_group")) return ctx->stat_ksw_group;
 	if (!strcmp(key, "ksw_chunks")) return ctx->stat_ksw_chunks;

@@ -946,8 +946,8 @@ struct SrPhaseClock {
 	}
 };
 
-// The slices of one call run on two lanes (the caller's context and a peer context on a helper thread, one stream each) so
-// that the transfers, the 8-byte read-backs and the small kernels of one slice overlap the DP kernel of the other.  Results
+// The slices of one call run on several lanes (the caller's context and a chain of peer contexts on helper threads, one stream
+// each) so that the transfers, the 8-byte read-backs and the small kernels of one slice overlap the DP kernel of the others.  Results
 // land in the caller's arrays in input order: a slice claims its output ranges when its sizes are known, in slice order.
 struct SliceOrder {
 	std::mutex mu;
@@ -1274,6 +1274,20 @@ static int sr_map_slice(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *
 
 extern "C" int gd_init(int device, gd_ctx **ctx);
 
+// lane L of a context: the context itself, its peer, the peer's peer ... (created on first use, destroyed with the context)
+static gd_ctx *lane_ctx(gd_ctx *ctx, int L)
+{
+	while (L-- > 0 && ctx) ctx = ctx->peer;
+	return ctx;
+}
+static int map_lanes(gd_ctx *ctx, int64_t want)
+{
+	int have = 1;
+	for (gd_ctx *c = ctx; have < want; ++have, c = c->peer)
+		if (!c->peer && gd_init(ctx->device, &c->peer) != GD_OK) break; // no further context: fewer lanes
+	return have;
+}
+
 static int run_slices(gd_ctx *ctx, const gd_index *idx, const std::vector<std::pair<int, int>> &slices, const int64_t *off,
                       const int32_t *len, const char *buf, const gd_sr_opt_t *o, const gd_lr_opt_t *lr, int64_t *cand_off,
                       gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cand, int64_t *n_cig,
@@ -1282,11 +1296,11 @@ static int run_slices(gd_ctx *ctx, const gd_index *idx, const std::vector<std::p
 	SliceOrder ord;
 	ctx->err.clear();
 	const int ns = (int)slices.size();
-	int lanes = (ns >= 2 && ctx->opt_map_lanes != 1) ? 2 : 1;
-	if (lanes == 2 && !ctx->peer && gd_init(ctx->device, &ctx->peer) != GD_OK) lanes = 1; // no second context: one lane
-	int rcs[2] = {GD_OK, GD_OK};
+	// long reads: two lanes at most (every lane owns a backtrack arena of tens of GB)
+	const int lanes = map_lanes(ctx, std::min<int64_t>(ns, lr ? std::min<long>(ctx->opt_map_lanes, 2) : ctx->opt_map_lanes));
+	std::vector<int> rcs((size_t)lanes, GD_OK);
 	auto lane = [&](int L) {
-		gd_ctx *c = L == 0 ? ctx : ctx->peer;
+		gd_ctx *c = lane_ctx(ctx, L);
 		cudaSetDevice(c->device);
 		for (int k = L; k < ns; k += lanes) {
 			const int b = slices[k].first, m = slices[k].second;
@@ -1299,17 +1313,23 @@ static int run_slices(gd_ctx *ctx, const gd_index *idx, const std::vector<std::p
 			}
 		}
 	};
-	if (lanes == 2) {
-		std::thread helper(lane, 1);
+	{
+		std::vector<std::thread> helpers;
+		for (int L = 1; L < lanes; ++L) helpers.emplace_back(lane, L);
 		lane(0);
-		helper.join();
-	} else lane(0);
+		for (std::thread &t : helpers) t.join();
+	}
 	*n_cand = ord.cand_base, *n_cig = ord.cig_base;
-	// the code (and message) of the lane that actually failed, not of the one that merely bailed out after it
-	const int L = (rcs[0] && rcs[0] != SR_ABORTED) ? 0 : (rcs[1] && rcs[1] != SR_ABORTED) ? 1 : -1;
-	if (L == 1) ctx->err = ctx->peer->err;
-	if (L < 0) return (rcs[0] || rcs[1]) ? GD_ERR_CUDA : GD_OK;
-	return rcs[L];
+	// the code (and message) of the lane that actually failed, not of one that merely bailed out after it
+	bool any = false;
+	for (int L = 0; L < lanes; ++L) {
+		any |= rcs[L] != GD_OK;
+		if (rcs[L] && rcs[L] != SR_ABORTED) {
+			if (L > 0) ctx->err = lane_ctx(ctx, L)->err;
+			return rcs[L];
+		}
+	}
+	return any ? GD_ERR_CUDA : GD_OK;
 }
 
 extern "C" int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
@@ -1331,8 +1351,9 @@ extern "C" int gd_sr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const in
 	if (n_cigar) *n_cigar = 0;
 	if (n == 0) return GD_OK;
 	cudaSetDevice(ctx->device);
-	// slices: at most 2^18 reads, at least four per call when the batch is large enough to share between the two lanes
-	const int slice = std::max(32768, std::min(1 << 18, (n + 3) / 4));
+	// slices: at most 2^18 reads, at least two per lane when the batch is large enough to share between the lanes
+	const int per_call = 2 * (int)std::max<long>(2, std::min<long>(ctx->opt_map_lanes, 8));
+	const int slice = std::max(32768, std::min(1 << 18, (n + per_call - 1) / per_call));
 	std::vector<std::pair<int, int>> slices;
 	for (int b = 0; b < n; b += slice) slices.push_back({b, std::min(slice, n - b)});
 	int64_t cand_base = 0, cig_base = 0;
@@ -1385,16 +1406,18 @@ extern "C" int gd_sr_map_sam_batch(gd_ctx *ctx, const gd_index *idx, int n, cons
 	const bool prof = getenv("GD_MAP_PROFILE") != nullptr;
 	const double tp0 = prof ? SrPhaseClock::now() : 0;
 	job.gen = (int)(ctx->sam_calls++ & 1);
-	const int slice = std::max(32768, std::min(1 << 18, (n + 3) / 4));
-	if (n > slice && ctx->opt_map_lanes != 1 && !ctx->peer) gd_init(ctx->device, &ctx->peer); // the second lane exists before its text buffers are sized
-	ctx->h_sam_used[job.gen] = 0;
-	if (ctx->peer) ctx->peer->h_sam_used[job.gen] = 0;
-	{ // size this generation's pinned text buffers once, from an estimate of the text (2 x bases + ~200 B per read, half of it per
-	  // lane): page-locking memory is slow, and a buffer that grows is page-locked again and again and copied each time
+	const int per_call = 2 * (int)std::max<long>(2, std::min<long>(ctx->opt_map_lanes, 8)); // two slices per lane, as in gd_sr_map_batch
+	const int slice = std::max(32768, std::min(1 << 18, (n + per_call - 1) / per_call));
+	const int n_slices = (n + slice - 1) / slice;
+	const int lanes = map_lanes(ctx, std::min<int64_t>(n_slices, ctx->opt_map_lanes)); // the lanes exist before their text buffers are sized
+	for (gd_ctx *c = ctx; c; c = c->peer) c->h_sam_used[job.gen] = 0;
+	{ // size this generation's pinned text buffers once, from an estimate of the text (2 x bases + ~200 B per read, a lane's share
+	  // of it per lane): page-locking memory is slow, and a buffer that grows is page-locked again and again and copied each time
 		size_t est = 0;
 		for (int i = 0; i < n; ++i) est += 2 * (size_t)len[i] + 200;
-		est = est / 2 + est / 8 + ((size_t)1 << 20);
-		for (gd_ctx *c : {ctx, ctx->peer}) {
+		est = est / (size_t)lanes + est / 8 + ((size_t)1 << 20);
+		for (int L = 0; L < lanes; ++L) {
+			gd_ctx *c = lane_ctx(ctx, L);
 			if (!c || c->h_sam[job.gen].cap >= est) continue;
 			if (c->h_sam[job.gen].p) cudaFreeHost(c->h_sam[job.gen].p);
 			c->h_sam[job.gen].p = nullptr, c->h_sam[job.gen].cap = 0;
@@ -1406,17 +1429,15 @@ extern "C" int gd_sr_map_sam_batch(gd_ctx *ctx, const gd_index *idx, int n, cons
 	for (int b = 0; b < n; b += slice) slices.push_back({b, std::min(slice, n - b)});
 	job.pieces.assign(slices.size(), SamJob::Piece{0, 0, 0});
 	int64_t cb = 0, gb = 0;
-	const bool had_peer = ctx->peer != nullptr;
 	const double tp1 = prof ? SrPhaseClock::now() : 0;
 	int rc = run_slices(ctx, idx, slices, off, len, seq, o, nullptr, nullptr, nullptr, 0, nullptr, 0, &cb, &gb, &job);
-	(void)had_peer; // (a peer created during this call started with h_sam_used == 0)
 	if (prof) fprintf(stderr, "[gd_sr_map_sam_batch] %d reads, %zu slices: prologue %.2f ms, slices %.2f ms\n", n, slices.size(), tp1 - tp0, SrPhaseClock::now() - tp1);
 	if (rc) return rc;
 	const size_t np = job.pieces.size();
 	*parts = (char **)malloc((np + 1) * sizeof(char *)), *part_len = (size_t *)malloc((np + 1) * sizeof(size_t));
 	if (!*parts || !*part_len) return GD_ERR_ARG;
 	for (size_t k = 0; k < np; ++k) {
-		gd_ctx *c = job.pieces[k].lane == 0 ? ctx : ctx->peer;
+		gd_ctx *c = lane_ctx(ctx, job.pieces[k].lane);
 		(*parts)[k] = (char *)c->h_sam[job.gen].p + job.pieces[k].off, (*part_len)[k] = job.pieces[k].len;
 	}
 	*n_parts = (int)np;

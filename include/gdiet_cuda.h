@@ -92,8 +92,8 @@ int gd_init(int device, gd_ctx **ctx);
 void gd_destroy(gd_ctx *ctx);
 const char *gd_strerror(const gd_ctx *ctx); /* ctx may be NULL: last init error */
 /* options: "ksw_group" (lanes per pair: 0=auto,4,8,16,32), "p_budget_mb" (backtrack arena),
- * "ksw_blocks_per_sm" (0=auto), "map_lanes" (mapping stage: 2 = the slices of a call alternate between this context and a
- * peer context on a helper thread [default], 1 = one lane), "time_kernels" (1: bracket the DP / sketch kernel launches with CUDA
+ * "ksw_blocks_per_sm" (0=auto), "map_lanes" (mapping stage: the slices of a call are dealt to this many contexts, each driven by its own
+ * host thread: 1..8, default 4 or the environment variable GDIET_MAP_LANES; long reads use two at most), "time_kernels" (1: bracket the DP / sketch kernel launches with CUDA
  * events).  stats: "kernel_launches", "ksw_ring", "ksw_group", "ksw_chunks", "device_sms"; with
  * "time_kernels": "ksw_dp_us", "ksw_dp_launches", "sketch_us", "sketch_launches" (cumulative device
  * time of the hot kernels; reading one waits for the recorded launches), "ksw_dp_reset" */

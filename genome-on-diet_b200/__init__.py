@@ -310,7 +310,7 @@ EXPORTS = ["gd_init", "gd_destroy", "gd_strerror", "gd_set_option", "gd_get_stat
            "gd_sketch_reads_batch", "gd_index_build", "gd_index_destroy", "gd_index_stat", "gd_index_get_batch",
            "gd_index_export", "gd_index_cal_max_occ", "gd_sr_map_batch", "gd_sr_sam_batch", "gd_sam_header", "gd_free", "gd_index_meta", "gd_index_alloc", "gd_index_buffers", "gd_index_commit", "gd_index_build_device", "gd_lr_map_batch", "gd_mmi_write", "gd_lr_sam_batch", "gd_index_load_mmi", "gd_index_seq_name", "gd_sr_sam_batch_parts",
            "gd_pinned_alloc", "gd_pinned_free", "gd_multi_init", "gd_multi_destroy", "gd_multi_size", "gd_multi_ctx", "gd_multi_index",
-           "gd_multi_strerror", "gd_multi_index_bcast", "gd_multi_stat", "gd_multi_sr_map_batch", "gd_multi_lr_map_batch",
+           "gd_multi_strerror", "gd_multi_index_bcast", "gd_multi_stat", "gd_multi_prepare_sam", "gd_sr_map_sam_prepare", "gd_multi_sr_map_batch", "gd_multi_lr_map_batch",
            "gd_multi_sr_map_sam", "gd_multi_lr_map_sam", "gd_sr_map_sam_batch"]
 
 

@@ -1444,6 +1444,28 @@ extern "C" int gd_sr_map_sam_batch(gd_ctx *ctx, const gd_index *idx, int n, cons
 	return GD_OK;
 }
 
+// The lanes of the mapping stage and the pinned text buffers of both generations of gd_sr_map_sam_batch, ahead of the first call
+// (a one-shot host program does this beside its index build: creating contexts and page-locking memory is 0.1-0.3 s).
+// text_bytes: what one call is expected to write (SAM text of one mini-batch).
+extern "C" int gd_sr_map_sam_prepare(gd_ctx *ctx, size_t text_bytes)
+{
+	if (!ctx) return GD_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	const int lanes = map_lanes(ctx, ctx->opt_map_lanes);
+	const size_t est = text_bytes / (size_t)lanes + text_bytes / 8 + ((size_t)1 << 20);
+	for (int L = 0; L < lanes; ++L) {
+		gd_ctx *c = lane_ctx(ctx, L);
+		for (int gen = 0; gen < 2; ++gen) {
+			if (c->h_sam[gen].cap >= est) continue;
+			if (c->h_sam[gen].p) cudaFreeHost(c->h_sam[gen].p);
+			c->h_sam[gen].p = nullptr, c->h_sam[gen].cap = 0;
+			if (cudaHostAlloc(&c->h_sam[gen].p, est, cudaHostAllocPortable) == cudaSuccess) c->h_sam[gen].cap = est;
+			else cudaGetLastError(), c->h_sam[gen].p = nullptr; // (the stage grows it on demand)
+		}
+	}
+	return GD_OK;
+}
+
 extern "C" int gd_lr_map_batch(gd_ctx *ctx, const gd_index *idx, int n, const int64_t *off, const int32_t *len, const char *buf,
                                const gd_lr_opt_t *lr, int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar,
                                int64_t cigar_cap, int64_t *n_cigar)

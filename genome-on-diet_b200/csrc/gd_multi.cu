@@ -486,6 +486,16 @@ static int multi_map_sam(gd_multi *m, int n, const char *const *names, const int
 	return GD_OK;
 }
 
+extern "C" int gd_multi_prepare_sam(gd_multi *m, size_t text_bytes)
+{
+	if (!m) return GD_ERR_ARG;
+	const int G = (int)m->ctx.size();
+	std::vector<std::thread> th;
+	for (int j = 0; j < G; ++j) th.emplace_back([&, j]() { gd_sr_map_sam_prepare(m->ctx[j], text_bytes / (size_t)G + 1); });
+	for (std::thread &t : th) t.join();
+	return GD_OK;
+}
+
 extern "C" int gd_multi_sr_map_sam(gd_multi *m, int n, const char *const *names, const int64_t *off, const int32_t *len, const char *seq,
                                    const char *qual, const gd_sr_opt_t *opt, const gd_sr_post_opt_t *post, int n_seq,
                                    const char *const *seq_names, const int64_t *ref_off, const int32_t *ref_len, const char *ref,

@@ -404,6 +404,11 @@ const char *gd_multi_strerror(const gd_multi *m);
  * gd_multi_stat: "bcast_seconds", "bcast_bytes", "bcast_path" (1 = NCCL, 2 = peer copies) of the last broadcast. */
 int gd_multi_index_bcast(gd_multi *m, gd_index *root, int take_ownership);
 double gd_multi_stat(const gd_multi *m, const char *key);
+/* Optional, ahead of the first gd_multi_sr_map_sam: create the lanes of every device and page-lock the SAM text buffers for
+ * calls that write about text_bytes each (a one-shot host runs this beside its index build; otherwise the first two calls pay).
+ * gd_sr_map_sam_prepare is the same for one context. */
+int gd_multi_prepare_sam(gd_multi *m, size_t text_bytes);
+int gd_sr_map_sam_prepare(gd_ctx *ctx, size_t text_bytes);
 /* gd_sr_map_batch / gd_lr_map_batch over all devices: same arguments, same results (input order, dense arrays) */
 int gd_multi_sr_map_batch(gd_multi *m, int n, const int64_t *off, const int32_t *len, const char *buf, const gd_sr_opt_t *opt,
                           int64_t *cand_off, gd_sr_cand_t *cand, int64_t cand_cap, uint32_t *cigar, int64_t cigar_cap,

@@ -69,6 +69,8 @@ def run_prog(binary, extra, env, fa, fq, out, cores, n_reads):
         r["reads_per_s_pipeline"] = n_reads / float(pipe.group(1)) if pipe else None
     if p.returncode != 0:
         r["stderr_tail"] = p.stderr[-600:]
+    if "GD_MAP_PROFILE" in env:  # the calls of the mapping step: prologue (buffers) and slices, per mini-batch
+        r["profile"] = [l for l in p.stderr.splitlines() if l.startswith("[gd_sr_map_sam_batch]")][:40]
     return r
 
 
@@ -93,6 +95,8 @@ def main():
         got, n_got = sam_digest(bat_sam) if r["returncode"] == 0 else ("", 0)
         r["sam_file_identical"] = got == want and n_got == n_want
         out["batched_host"].append(r)
+    if os.environ.get("FILE_BENCH_PROFILE"):
+        out["batched_host_profile"] = run_prog(bat_bin, [], {"GDIET_GPUS": gpus, "GD_MAP_PROFILE": "1"}, fa, fq, bat_sam, cores, n_reads)
     print(json.dumps(out), flush=True)
 
 

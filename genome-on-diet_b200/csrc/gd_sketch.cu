@@ -21,6 +21,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gd_sketch_tile_kernel
 	if (B.tile_base) B.ntiles = B.tile_base[B.njobs];
 	sketch_tile_body<THREADS>(S, B, (SketchSmem<THREADS> *)gd_sk_smem);
 }
+// design v3 of the tile body (gd_sketch.cuh); the default.  GDIET_SK_V=2 selects the kernel above (A/B measurements).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) gd_sketch_tile3_kernel(const SketchParams S, SketchBatch B)
+{
+	extern __shared__ __align__(16) uint8_t gd_sk_smem[];
+	if (B.tile_base) B.ntiles = B.tile_base[B.njobs];
+	sketch_tile_body3<THREADS>(S, B, (SketchSmem3<THREADS> *)gd_sk_smem);
+}
 
 // jobs for index-build sketching: one per sequence, shift 0
 __global__ void gd_sketch_ref_jobs_kernel(int n, const int64_t *off, const int32_t *len, const uint32_t *rid, SketchJob *jobs)
@@ -237,7 +245,13 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 		kern<<<std::max(blocks, 1), threads, smem, s>>>(S, B);
 		return GD_OK;
 	};
-	if (small) rc = launch(gd_sketch_tile_kernel<32>, 32, sizeof(SketchSmem<32>));
+	static const int sk_ver = getenv("GDIET_SK_V") ? atoi(getenv("GDIET_SK_V")) : 3;
+	if (sk_ver != 2) {
+		if (small) rc = launch(gd_sketch_tile3_kernel<32>, 32, sizeof(SketchSmem3<32>));
+		else if (big_threads == 64) rc = launch(gd_sketch_tile3_kernel<64>, 64, sizeof(SketchSmem3<64>));
+		else if (big_threads == 128) rc = launch(gd_sketch_tile3_kernel<128>, 128, sizeof(SketchSmem3<128>));
+		else rc = launch(gd_sketch_tile3_kernel<256>, 256, sizeof(SketchSmem3<256>));
+	} else if (small) rc = launch(gd_sketch_tile_kernel<32>, 32, sizeof(SketchSmem<32>));
 	else if (big_threads == 64) rc = launch(gd_sketch_tile_kernel<64>, 64, sizeof(SketchSmem<64>));
 	else if (big_threads == 128) rc = launch(gd_sketch_tile_kernel<128>, 128, sizeof(SketchSmem<128>));
 	else rc = launch(gd_sketch_tile_kernel<256>, 256, sizeof(SketchSmem<256>));

@@ -420,4 +420,452 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 	}
 }
 
+
+// =============================================================================================
+// Tile body, design v3 (round 2): the same tiles, phases and output order as sketch_tile_body above -- about a third of
+// its instructions.  What changed, phase by phase (SASS counts of the 256-thread kernel in DESIGN.md 4):
+//   * tile header (ticket, tile -> job search, sparsified length, staged byte range) is computed by ONE thread and
+//     broadcast through shared memory;
+//   * encode: one shared-memory table look-up per base (code | N flag << 16), accumulated with a shift-add; the pattern
+//     walk has a stride-W form for patterns with a single '1' ("10", "100"); threads whose 8 positions lie inside the
+//     sequence skip the range tests;
+//   * N-free run lengths come from a bitmap of N flags in shared memory (two 32-bit probes for w+k-1 <= 32) instead of a
+//     block-wide max-scan;
+//   * both k-mers of all 8 positions are funnel-shifted out of three registers of the forward / reversed 2-bit stream
+//     (no rolling dependency chain); hash64 runs on explicit 32-bit halves (the high half of a 2k <= 56 bit key has
+//     <= 24 bits, so two of the three xor-shifts touch only the low word; 2k <= 32 is all 32-bit);
+//   * window minima / emission maxima run on key = hash | 1 << 56 (0 = "no full window", ~0 = no k-mer); the chunk
+//     geometry of a window (which 8-position chunk it starts in, how many whole chunks lie between) is the same for
+//     every thread, so the addresses are `thread * 8 + uniform offset` and the in-between loop has a uniform trip count.
+// =============================================================================================
+template <int THREADS> struct SketchSmem3 {
+	enum { NP = THREADS * 8, F2W = NP / 16 + GD_SK_PADW + 4, R2W = NP / 16 + 6 };
+	uint64_t SUF[NP];  // w >= 9: minimum of the keys over [s, end of s's chunk]; w <= 8: the key itself   ([p][thread])
+	uint64_t PREM[NP]; // w >= 9: maximum of M over [start of chunk, s];          w <= 8: M itself          ([p][thread])
+	uint32_t F2[F2W];  // 2-bit codes, position s at bit 2s (after GD_SK_PADW zero words)
+	uint32_t R2[R2W];  // 2-bit codes, position s at bit 2(NP-1-s); zero words behind
+	uint16_t NB[NP / 8 + 4]; // N flags: position s at bit 2(s & 7) of halfword 2 + s / 8 (two zero halfwords in front)
+	uint32_t lut[256]; // seq_nt4_table (sketch.c:11-18) as code, or 1 << 16 for N
+	int32_t warp_cnt[32];
+	long long excl;
+	// tile header, written by thread 0
+	long long h_tile, h_seq_off;
+	int32_t h_job, h_i0, h_dl, h_staged, h_raw_lo, h_nbytes, h_safe;
+	uint32_t h_shift, h_rid;
+	uint8_t ones_loc[64];
+	alignas(16) uint32_t raw[GD_SK_RAW(THREADS) / 4 + 4]; // the tile's slice of the ASCII sequence (16-byte aligned in global memory)
+};
+
+GD_DEV uint32_t sk_mask_from(int a) { return a <= 0 ? 0xffu : a >= 8 ? 0u : (0xffu << a) & 0xffu; } // bits p >= a of 8
+
+// hash64 (sketch.c:25-34) of a key of 32 < 2k <= 56 bits held as (hi < 2^24, lo); mhi = mask >> 32
+GD_DEV void sk_hash_hl(uint32_t &lo, uint32_t &hi, const uint32_t mhi)
+{
+	uint64_t t = (uint64_t)lo * 0x1fffffu + 0xffffffffffffffffull; // key * (2^21 - 1) - 1 = ~key + (key << 21)
+	hi = ((uint32_t)(t >> 32) + hi * 0x1fffffu) & mhi, lo = (uint32_t)t;
+	lo ^= funnel_r(lo, hi, 24); // key ^= key >> 24 (hi >> 24 == 0)
+	t = (uint64_t)lo * 265u;    // key + (key << 3) + (key << 8)
+	hi = ((uint32_t)(t >> 32) + hi * 265u) & mhi, lo = (uint32_t)t;
+	lo ^= funnel_r(lo, hi, 14), hi ^= hi >> 14;
+	t = (uint64_t)lo * 21u; // key + (key << 2) + (key << 4)
+	hi = ((uint32_t)(t >> 32) + hi * 21u) & mhi, lo = (uint32_t)t;
+	lo ^= funnel_r(lo, hi, 28); // hi >> 28 == 0
+	t = (uint64_t)lo * 0x80000001u; // key + (key << 31)
+	hi = ((uint32_t)(t >> 32) + hi * 0x80000001u) & mhi, lo = (uint32_t)t;
+}
+GD_DEV uint32_t sk_hash_32(uint32_t key, const uint32_t m)
+{ // the same for 2k <= 32
+	key = (key * 0x1fffffu - 1u) & m;
+	key ^= key >> 24;
+	key = (key * 265u) & m;
+	key ^= key >> 14;
+	key = (key * 21u) & m;
+	key ^= key >> 28;
+	key = (key * 0x80000001u) & m;
+	return key;
+}
+
+template <int THREADS>
+GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, SketchSmem3<THREADS> *sm)
+{
+	const int NP = THREADS * 8;
+	const int tid = thread_idx(), lane = tid & 31, wid = tid >> 5;
+	const int w = S.w, k = S.k, full_run = w + k - 1, wm1 = w - 1;
+	const int HL = sk_halo_left(w, k);
+	const bool ones1 = S.ones == 1;
+	const bool k32 = 2 * k <= 32;
+	const uint32_t mlo = (uint32_t)S.mask, mhi = (uint32_t)(S.mask >> 32);
+	uint16_t *const F2h = (uint16_t *)(sm->F2 + GD_SK_PADW), *const R2h = (uint16_t *)sm->R2;
+	for (int i = tid; i < SketchSmem3<THREADS>::F2W; i += THREADS) sm->F2[i] = 0;
+	for (int i = tid; i < SketchSmem3<THREADS>::R2W; i += THREADS) sm->R2[i] = 0;
+	if (tid < 4) sm->NB[tid < 2 ? tid : NP / 8 + tid] = 0;
+	for (int i = tid; i < 64; i += THREADS) sm->ones_loc[i] = S.ones_loc[i];
+	for (int c = tid; c < 256; c += THREADS) sm->lut[c] = (uint32_t)sk_nt4((unsigned)c) < 4u ? (uint32_t)sk_nt4((unsigned)c) : 0x10000u;
+	const bool fixed = B.fixed_stride > 0;
+	// Tiles are handed out in order by a global ticket, drawn when the block is free: every tile's predecessors are then held by
+	// blocks that are already computing them, so the look-back below never waits for a tile nobody has started.  (Drawing the
+	// NEXT tile's ticket while the current one is computed was measured on a B200 and is twice as slow: a block that is late
+	// holds a low ticket hostage, and every later tile spins on it in the look-back -- 850 probes per tile.)
+	// Fixed-stride mode: static assignment, nothing orders the tiles.
+	long long next = block_idx();
+	sync_block();
+	for (;;) {
+		if (tid == 0) {
+			const long long tile = fixed ? next : (long long)atomic_add(B.ticket, 1);
+			sm->h_tile = tile;
+			if (tile < B.ntiles) {
+				int job;
+				long long chunk;
+				if (S.one_tile_per_job) job = (int)tile, chunk = 0;
+				else {
+					int lo = 0, hi = B.njobs; // last job with tile_base[job] <= tile
+					while (hi - lo > 1) {
+						int mid = (lo + hi) >> 1;
+						if (B.tile_base[mid] <= tile) lo = mid;
+						else hi = mid;
+					}
+					job = lo, chunk = tile - B.tile_base[lo];
+				}
+				const SketchJob J = B.jobs[job];
+				const uint32_t shift = (uint32_t)J.shift;
+				const int dl = (int)sk_diet_len((uint32_t)J.len, shift, S);
+				const int i0 = (int)(chunk * S.TP), B0 = i0 - HL;
+				sm->h_job = job, sm->h_i0 = i0, sm->h_dl = dl, sm->h_shift = shift, sm->h_rid = J.rid, sm->h_seq_off = J.seq_off;
+				// bytes of the original sequence the tile touches: [real(first loaded position), real(last loaded position)]
+				const int jlo = B0 > 0 ? B0 : 0, jhi = (B0 + NP < dl ? B0 + NP : dl) - 1;
+				int staged = 0, raw_lo = 0, nbytes = 0, safe = 0;
+				if (dl >= full_run && jhi >= jlo) {
+					const uint32_t rlo = sk_real((uint32_t)jlo, shift, S), rhi = sk_real((uint32_t)jhi, shift, S);
+					const uint32_t lead = (uint32_t)((unsigned long long)(B.buf + J.seq_off + rlo) & 15);
+					safe = (int)rlo;
+					nbytes = (int)(rhi - rlo + 1 + lead);
+					if (nbytes <= GD_SK_RAW(THREADS)) staged = 1, raw_lo = (int)rlo - (int)lead;
+				}
+				sm->h_staged = staged, sm->h_raw_lo = raw_lo, sm->h_nbytes = nbytes, sm->h_safe = safe;
+				next = tile + grid_dim();
+			}
+		}
+		sync_block();
+		const long long tile = sm->h_tile;
+		if (tile >= B.ntiles) break;
+		const int job = sm->h_job, dl = sm->h_dl, i0 = sm->h_i0, B0 = i0 - HL;
+		const uint32_t shift = sm->h_shift;
+		const char *seq = B.buf + sm->h_seq_off;
+		const int s0 = tid * 8, j0 = B0 + s0;
+		uint32_t zbits = 0, emit = 0, okbits = 0;
+		uint64_t key[8];
+		int cnt = 0;
+		if (dl >= full_run) {
+			// ---- phase 0: stage the bytes with 16-byte loads (the tail bytewise) ----
+			const int staged = sm->h_staged, raw_lo = sm->h_raw_lo, safe = sm->h_safe;
+			if (staged) {
+				const int nbytes = sm->h_nbytes, nvec = nbytes >> 4;
+				const uint4 *gsrc = (const uint4 *)(seq + raw_lo);
+				uint4 *sdst = (uint4 *)sm->raw;
+				for (int i = tid; i < nvec; i += THREADS) sdst[i] = gsrc[i];
+				if (tid < (nbytes & 15)) ((uint8_t *)sm->raw)[nvec * 16 + tid] = (uint8_t)seq[raw_lo + nvec * 16 + tid];
+				sync_block();
+			}
+			// ---- phase 1: 8 positions per thread -> 2-bit codes (bits 0..15) and N flags (bit 16 + 2p); positions outside
+			// [0, dl) count as N.  real(j) = (j / ones) * W + ones_loc[j % ones] + shift (get_real_location, sketch.c:20-23) ----
+			uint32_t acc = 0;
+			{
+				const bool all_in = j0 >= 0 && j0 + 7 < dl;
+				uint32_t qd = 0, rm = 0;
+				if (j0 > 0) {
+					if (ones1) qd = (uint32_t)j0;
+					else qd = (uint32_t)j0 / (uint32_t)S.ones, rm = (uint32_t)j0 - qd * (uint32_t)S.ones;
+				}
+				uint32_t base = qd * (uint32_t)S.W + shift;
+				const uint32_t loc0 = sm->ones_loc[0];
+				if (staged) {
+					const uint8_t *rs = (const uint8_t *)sm->raw;
+					if (all_in && ones1) {
+						uint32_t idx = base + loc0 - (uint32_t)raw_lo;
+#pragma unroll
+						for (int p = 0; p < 8; ++p) acc += sm->lut[rs[idx]] << (2 * p), idx += (uint32_t)S.W;
+					} else if (all_in) {
+#pragma unroll
+						for (int p = 0; p < 8; ++p) {
+							acc += sm->lut[rs[base + sm->ones_loc[rm] - (uint32_t)raw_lo]] << (2 * p);
+							if (++rm == (uint32_t)S.ones) rm = 0, base += (uint32_t)S.W;
+						}
+					} else {
+#pragma unroll
+						for (int p = 0; p < 8; ++p) {
+							const int j = j0 + p;
+							const bool in = j >= 0 && j < dl;
+							const uint32_t rp = base + sm->ones_loc[rm];
+							const uint32_t v = sm->lut[rs[(in ? rp : (uint32_t)safe) - (uint32_t)raw_lo]];
+							acc += (in ? v : 0x10000u) << (2 * p);
+							if (j >= 0 && ++rm == (uint32_t)S.ones) rm = 0, base += (uint32_t)S.W;
+						}
+					}
+				} else { // sparse patterns (more than three original bytes per position): straight from global memory
+					const uint8_t *gs = (const uint8_t *)seq;
+#pragma unroll
+					for (int p = 0; p < 8; ++p) {
+						const int j = j0 + p;
+						const bool in = j >= 0 && j < dl;
+						const uint32_t rp = base + sm->ones_loc[rm];
+						const uint32_t v = sm->lut[gs[in ? rp : (uint32_t)safe]];
+						acc += (in ? v : 0x10000u) << (2 * p);
+						if (j >= 0 && ++rm == (uint32_t)S.ones) rm = 0, base += (uint32_t)S.W;
+					}
+				}
+			}
+			const uint32_t code = acc & 0xffffu, nsp = acc >> 16;
+			F2h[tid] = (uint16_t)code;
+			{ // the same 8 codes in reverse position order: bit reversal, then the two bits of every code swapped back
+				const uint32_t br = (uint32_t)(brev64((uint64_t)code) >> 48);
+				R2h[THREADS - 1 - tid] = (uint16_t)(((br & 0x5555u) << 1) | ((br >> 1) & 0x5555u));
+			}
+			sm->NB[2 + tid] = (uint16_t)nsp;
+			sync_block();
+			// ---- last N position before the chunk (slot -1 counts as N); only runs up to w+k-1 matter ----
+			int L0 = s0 - full_run - 1;
+			if (L0 < -1) L0 = -1;
+			{
+				int hi = tid; // the 16 positions below 8 * hi are the halfwords hi, hi + 1
+				for (int rem = full_run; rem > 0 && hi > 0; rem -= 16, hi -= 2) {
+					const uint32_t bits = (uint32_t)sm->NB[hi] | (uint32_t)sm->NB[hi + 1] << 16;
+					if (bits) {
+						const int f = hi * 8 - 16 + ((31 - clz32(bits)) >> 1);
+						if (f > L0) L0 = f;
+						break;
+					}
+				}
+			}
+			// ---- k-mers that have no N (valid) and windows that are full, as 8-bit masks ----
+			uint32_t validbits, fullbits;
+			if (nsp == 0) {
+				const int d = s0 - L0; // run length at p = 0
+				validbits = sk_mask_from(k - d), fullbits = sk_mask_from(full_run - d);
+			} else {
+				validbits = fullbits = 0;
+				int ln = L0;
+#pragma unroll
+				for (int p = 0; p < 8; ++p) {
+					if (nsp >> (2 * p) & 1) ln = s0 + p;
+					const int run = s0 + p - ln;
+					if (run >= k) validbits |= 1u << p;
+					if (run >= full_run) fullbits |= 1u << p;
+				}
+			}
+			// ---- phase 2: both k-mers of every position out of the packed streams, canonical k-mer, hash (sketch.c:1660-1683).
+			// rv(p): base s0+p-k+1 (complemented) at bit 0 = forward stream at bit 2(s0-k+1) + 2p; fw(p): base s0+p at bit 0 =
+			// reversed stream at bit 2(NP-8-s0) + 2(7-p).  Bases before slot 0 read as zero bits (never valid: slot -1 is N).
+			{
+				const int bf = 32 * GD_SK_PADW + 2 * (s0 - k + 1), br = 2 * (NP - 8 - s0);
+				const uint32_t *fp = sm->F2 + (bf >> 5), *rp = sm->R2 + (br >> 5);
+				const uint32_t fs = (uint32_t)bf & 31u, rs = (uint32_t)br & 31u;
+				const uint32_t a0 = fp[0], a1 = fp[1], a2 = fp[2], c0 = rp[0], c1 = rp[1], c2 = rp[2];
+				const uint32_t f0 = funnel_r(a0, a1, fs), f1 = funnel_r(a1, a2, fs), g0 = funnel_r(c0, c1, rs), g1 = funnel_r(c1, c2, rs);
+				if (k32) {
+#pragma unroll
+					for (int p = 0; p < 8; ++p) {
+						const uint32_t rv = ~funnel_r(f0, f1, 2 * p) & mlo, fw = funnel_r(g0, g1, 2 * (7 - p)) & mlo;
+						uint64_t x = GD_SK_MAXU64;
+						if ((validbits >> p & 1) && fw != rv) {
+							const uint32_t z = fw < rv ? 0u : 1u;
+							x = (1ull << 56) | sk_hash_32(z ? rv : fw, mlo);
+							zbits |= z << p, okbits |= 1u << p;
+						}
+						key[p] = x;
+					}
+				} else {
+					const uint32_t a3 = fp[3], c3 = rp[3];
+					const uint32_t f2 = funnel_r(a2, a3, fs), g2 = funnel_r(c2, c3, rs);
+#pragma unroll
+					for (int p = 0; p < 8; ++p) {
+						const uint32_t rl = ~funnel_r(f0, f1, 2 * p), rh = ~funnel_r(f1, f2, 2 * p) & mhi;
+						const uint32_t fl = funnel_r(g0, g1, 2 * (7 - p)), fh = funnel_r(g1, g2, 2 * (7 - p)) & mhi;
+						const uint64_t rv = (uint64_t)rh << 32 | rl, fw = (uint64_t)fh << 32 | fl;
+						uint64_t x = GD_SK_MAXU64;
+						if ((validbits >> p & 1) && fw != rv) {
+							const bool z = !(fw < rv);
+							uint32_t lo = z ? rl : fl, hi = z ? rh : fh;
+							sk_hash_hl(lo, hi, mhi);
+							x = (uint64_t)(hi | 0x01000000u) << 32 | lo;
+							zbits |= (uint32_t)z << p, okbits |= 1u << p;
+						}
+						key[p] = x;
+					}
+				}
+			}
+			// emit candidates: inside the tile's emit range and the sequence, and a k-mer
+			uint32_t cand;
+			{
+				const int elo = HL - s0, ehi = imin(HL + S.TP, dl - B0) - s0; // p in [elo, ehi)
+				cand = sk_mask_from(elo) & ~sk_mask_from(ehi) & okbits;
+			}
+			if (w >= 9) {
+				// ---- phase 3: minimum of every full window ending at e = s0+p (0 = no full window ends here).  The window starts
+				// at a = e-(w-1) in chunk tid-dt, slot q (the same dt, q for every thread): own prefix minimum, whole chunks in
+				// between, suffix minimum of the first chunk.  A full window never starts before slot 0 (full => run <= e+1) ----
+				uint64_t pre[8], M[8];
+				{
+					uint64_t suf = GD_SK_MAXU64, pr = GD_SK_MAXU64;
+#pragma unroll
+					for (int p = 7; p >= 0; --p) suf = sk_min64(suf, key[p]), sm->SUF[p * THREADS + tid] = suf;
+#pragma unroll
+					for (int p = 0; p < 8; ++p) pr = sk_min64(pr, key[p]), pre[p] = pr;
+				}
+				sync_block();
+				// whole chunks between the window's first chunk and the thread's own: tid-dt+1 .. tid-1 with dt = D for the upper
+				// positions of the chunk and D + 1 for the lower ones -- two minima per thread, not one loop per position
+				const int D = -((7 - wm1) >> 3);
+				uint64_t midA = GD_SK_MAXU64, midB = GD_SK_MAXU64;
+				if (tid >= D) {
+#pragma unroll 1
+					for (int c = 1; c < D; ++c) midA = sk_min64(midA, sm->SUF[tid - D + c]); // SUF[0][c] = minimum of chunk c
+					midB = sk_min64(midA, sm->SUF[tid - D]);
+				}
+#pragma unroll
+				for (int p = 0; p < 8; ++p) {
+					const int d = p - wm1, q = d & 7, dt = -(d >> 3); // d < 0; a = 8 (tid - dt) + q
+					uint64_t m = 0;
+					if (fullbits >> p & 1) m = sk_min64(sk_min64(pre[p], sm->SUF[q * THREADS + tid - dt]), dt == D ? midA : midB);
+					M[p] = m;
+				}
+				// ---- phase 4: a key is emitted iff it equals the largest full-window minimum among the windows that contain its
+				// position, i.e. the maximum of M over [i, i+w-1] (a window of only non-k-mers has minimum ~0, but such a window
+				// cannot contain a k-mer's position): own suffix maximum, whole chunks, prefix maximum of the last chunk ----
+				uint64_t sufm[8];
+				{
+					uint64_t pm = 0, sx = 0;
+#pragma unroll
+					for (int p = 0; p < 8; ++p) pm = sk_max64(pm, M[p]), sm->PREM[p * THREADS + tid] = pm;
+#pragma unroll
+					for (int p = 7; p >= 0; --p) sx = sk_max64(sx, M[p]), sufm[p] = sx;
+				}
+				sync_block();
+				// whole chunks between the thread's own and the last window's last chunk: tid+1 .. tid+dt-1, dt = E or E + 1
+				const int E = wm1 >> 3;
+				uint64_t mxA = 0, mxB = 0;
+				if (cand) { // indices are clamped: a candidate's own chunks are always inside the tile
+#pragma unroll 1
+					for (int c = 1; c < E; ++c) mxA = sk_max64(mxA, sm->PREM[7 * THREADS + imin(tid + c, THREADS - 1)]); // PREM[7][c] = maximum of chunk c
+					mxB = sk_max64(mxA, sm->PREM[7 * THREADS + imin(tid + E, THREADS - 1)]);
+				}
+#pragma unroll
+				for (int p = 0; p < 8; ++p) {
+					if (cand >> p & 1) {
+						const int d = p + wm1, q = d & 7, dt = d >> 3; // last position of the last window: 8 (tid + dt) + q < NP in the emit range
+						const uint64_t mx = sk_max64(sk_max64(sufm[p], sm->PREM[q * THREADS + tid + dt]), dt == E ? mxA : mxB);
+						if (mx == key[p]) emit |= 1u << p, ++cnt;
+					}
+				}
+			} else {
+				// ---- small windows (w <= 8): direct scans over the keys and M in shared memory ----
+#pragma unroll
+				for (int p = 0; p < 8; ++p) sm->SUF[p * THREADS + tid] = key[p];
+				sync_block();
+#pragma unroll
+				for (int p = 0; p < 8; ++p) {
+					const int sp = s0 + p;
+					uint64_t m = 0;
+					if (fullbits >> p & 1) {
+						m = GD_SK_MAXU64;
+#pragma unroll 1
+						for (int d = 0; d < w; ++d) m = sk_min64(m, sm->SUF[((sp - d) & 7) * THREADS + ((sp - d) >> 3)]);
+					}
+					sm->PREM[p * THREADS + tid] = m;
+				}
+				sync_block();
+#pragma unroll
+				for (int p = 0; p < 8; ++p) {
+					const int sp = s0 + p;
+					if (cand >> p & 1) {
+						uint64_t mx = 0;
+#pragma unroll 1
+						for (int d = 0; d < w; ++d) mx = sk_max64(mx, sm->PREM[((sp + d) & 7) * THREADS + ((sp + d) >> 3)]);
+						if (mx == key[p]) emit |= 1u << p, ++cnt;
+					}
+				}
+			}
+		} // dl >= full_run
+		// ---- block exclusive scan of cnt ----
+		int inc = cnt;
+		for (int d = 1; d < 32; d <<= 1) {
+			int o = (int)shfl_up(0xffffffffu, (uint32_t)inc, d, 32);
+			if (lane >= d) inc += o;
+		}
+		if (lane == 31) sm->warp_cnt[wid] = inc;
+		sync_block();
+		int wbase = 0, total = 0;
+		for (int i = 0; i < THREADS / 32; ++i) {
+			int c = sm->warp_cnt[i];
+			if (i < wid) wbase += c;
+			total += c;
+		}
+		const int local = wbase + inc - cnt;
+		// ---- decoupled look-back over tiles, 32 predecessors per probe (warp 0); fixed-stride mode: the job's own slot ----
+		if (fixed) {
+			if (tid == 0) {
+				sm->excl = (long long)job * B.fixed_stride;
+				B.out_off[job] = sm->excl, B.out_cnt[job] = total;
+				if (tile == B.ntiles - 1) B.out_off[B.njobs] = (long long)B.njobs * B.fixed_stride;
+			}
+		} else if (wid == 0) {
+			long long excl = 0;
+			if (tile == 0) {
+				if (lane == 0) st_volatile(&B.status[0], (2ull << 62) | (unsigned long long)total);
+			} else {
+				if (lane == 0) {
+					st_volatile(&B.status[tile], (1ull << 62) | (unsigned long long)total);
+					fence();
+				}
+				long long pt = tile - 1;
+				for (;;) {
+					const long long idx = pt - lane;
+					unsigned long long sv = 2ull << 62; // "before the first tile": an inclusive prefix of 0
+					if (idx >= 0) do sv = ld_volatile(&B.status[idx]);
+						while ((sv >> 62) == 0);
+					const uint32_t incl = ballot(0xffffffffu, (sv >> 62) == 2); // lanes that hold an inclusive prefix
+					const int first = incl ? ffs32(incl) - 1 : 32;                // the nearest one ends the walk
+					unsigned long long c = lane <= first ? (sv & 0x3fffffffffffffffull) : 0ull;
+					for (int d = 16; d >= 1; d >>= 1) {
+						const uint32_t lo = shfl_xor(0xffffffffu, (uint32_t)c, d, 32), hi = shfl_xor(0xffffffffu, (uint32_t)(c >> 32), d, 32);
+						c += (unsigned long long)hi << 32 | lo;
+					}
+					excl += (long long)c;
+					if (incl) break;
+					pt -= 32;
+				}
+				if (lane == 0) st_volatile(&B.status[tile], (2ull << 62) | (unsigned long long)(excl + total));
+			}
+			if (lane == 0) {
+				sm->excl = excl;
+				if (i0 == 0) B.out_off[job] = excl;
+				if (tile == B.ntiles - 1) B.out_off[B.njobs] = excl + total;
+			}
+		}
+		sync_block();
+		if (emit) {
+			const long long obase = sm->excl + local;
+			const uint64_t yhi = (uint64_t)sm->h_rid << 32;
+			int o = 0;
+#pragma unroll
+			for (int p = 0; p < 8; ++p)
+				if (emit >> p & 1) {
+					const long long dst = obase + o;
+					if (fixed ? (local + o < B.fixed_stride) : (dst < B.out_cap)) {
+						const uint32_t j = (uint32_t)(j0 + p); // >= 0: a k-mer
+						uint32_t real;
+						if (ones1) real = j * (uint32_t)S.W + sm->ones_loc[0] + shift;
+						else {
+							const uint32_t qd = j / (uint32_t)S.ones, rm = j - qd * (uint32_t)S.ones;
+							real = qd * (uint32_t)S.W + sm->ones_loc[rm] + shift;
+						}
+						B.out[2 * dst] = key[p] << 8 | (uint64_t)k; // hash64 << 8 | k: the marker bit 56 leaves at the top
+						B.out[2 * dst + 1] = yhi | (uint64_t)real << 1 | (uint64_t)(zbits >> p & 1);
+					}
+					++o;
+				}
+		}
+		sync_block(); // shared memory (and the header) is reused by the next tile
+	}
+}
+
 } // namespace gd

@@ -7,11 +7,18 @@
 
 using namespace gd;
 
+static int g_ver = 3; // tile body: 3 = sketch_tile_body3 (the product default), 2 = sketch_tile_body
+extern "C" void emu_sketch_version(int v) { g_ver = v; }
+
 template <int THREADS>
 static void run_tiles(const SketchParams &S, SketchBatch &B, int grid)
 {
-	emu::launch(grid, THREADS, sizeof(SketchSmem<THREADS>),
-	            [&]() { sketch_tile_body<THREADS>(S, B, (SketchSmem<THREADS> *)emu::smem()); });
+	if (g_ver == 2)
+		emu::launch(grid, THREADS, sizeof(SketchSmem<THREADS>),
+		            [&]() { sketch_tile_body<THREADS>(S, B, (SketchSmem<THREADS> *)emu::smem()); });
+	else
+		emu::launch(grid, THREADS, sizeof(SketchSmem3<THREADS>),
+		            [&]() { sketch_tile_body3<THREADS>(S, B, (SketchSmem3<THREADS> *)emu::smem()); });
 }
 
 // jobs: n x {seq_off, len, shift, rid}; small != 0 forces the one-tile-per-job configuration

@@ -156,3 +156,40 @@ def test_emu_sketch(emu, oracle):
         for i, (s, sh) in enumerate(zip(seqs, shifts)):
             exp, _ = oracle.mm_sketch3(s, w, k, i, Z, sh, 0)
             assert np.array_equal(exp, got[i]), (it, i)
+
+
+@pytest.mark.parametrize("ver", [3, 2])
+def test_emu_sketch_geometry(emu, oracle, ver):
+    """Window / k-mer geometries at the edges of the tile body's cases: w = 9, 16, 17, 24, 25 (how many whole 8-position
+    chunks lie inside a window), 2k = 32 / 34 (32-bit against two-word hashing), k = 28, tiny k, multi-tile jobs whose
+    tile seams fall at every phase of the pattern, N runs across seams."""
+    emu.lib.emu_sketch_version(ver)
+    try:
+        rng = np.random.default_rng(11)
+        cfgs = [(16, 9), (17, 16), (28, 17), (9, 24), (21, 25), (4, 33), (15, 50), (8, 12), (16, 3), (17, 1)]
+        pats = ["10", "1", "110", "100", "10110", "10"]
+        for it, (k, w) in enumerate(cfgs):
+            Z = pats[it % len(pats)]
+            for small in (0, 1):
+                if small:
+                    tp = 256 - (2 * w + k - 3) - (w - 1)
+                    if tp < 8:
+                        continue
+                    lens = [int(rng.integers(len(Z), max(len(Z) + 1, tp * len(Z) // Z.count("1")))) for _ in range(6)]
+                else:
+                    lens = [int(x) for x in rng.choice([300, 2100, 4500, 7000], 3)]
+                seqs = []
+                for n in lens:
+                    c = rng.integers(0, 4, n)
+                    if k >= 12 and it % 2 == 1:
+                        for _ in range(3):
+                            a = int(rng.integers(0, n))
+                            c[a:a + int(rng.integers(1, 30))] = 4
+                    seqs.append(bytes(synth.ACGTN[c]))
+                shifts = [int(rng.integers(0, len(Z))) for _ in seqs]
+                got = emu.sketch_jobs(seqs, shifts, list(range(len(seqs))), w, k, Z, small)
+                for i, (sq, sh) in enumerate(zip(seqs, shifts)):
+                    exp, _ = oracle.mm_sketch3(sq, w, k, i, Z, sh, 0)
+                    assert np.array_equal(exp, got[i]), (ver, k, w, Z, small, i)
+    finally:
+        emu.lib.emu_sketch_version(3)

@@ -31,31 +31,31 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gd_sketch_tile3_kerne
 }
 
 // jobs for index-build sketching: one per sequence, shift 0
-__global__ void gd_sketch_ref_jobs_kernel(int n, const int64_t *off, const int32_t *len, const uint32_t *rid, SketchJob *jobs)
+__global__ void gd_sketch_ref_jobs_kernel(const SketchParams S, int n, const int64_t *off, const int32_t *len, const uint32_t *rid, SketchJob *jobs)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	SketchJob j;
-	j.seq_off = off[i], j.len = len[i], j.shift = 0, j.rid = rid ? rid[i] : (uint32_t)i, j.pad = 0;
+	j.seq_off = off[i], j.len = len[i], j.shift = 0, j.rid = rid ? rid[i] : (uint32_t)i, j.dl = (int32_t)sk_diet_len((uint32_t)len[i], 0, S);
 	jobs[i] = j;
 }
 
 // jobs for read sketching: per read W full-length jobs (shift 0..W-1) and, if crop, one extra job
 // (shift 0 on the prefix (unsigned)(max_seeds*len), GDiet-ShortReads/sketch.c:2177-2183)
-__global__ void gd_sketch_read_jobs_kernel(int n, const int64_t *off, const int32_t *len, int W, int crop, float max_seeds,
+__global__ void gd_sketch_read_jobs_kernel(const SketchParams S, int n, const int64_t *off, const int32_t *len, int W, int crop, float max_seeds,
                                            SketchJob *jobs)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const int JW = W + (crop ? 1 : 0);
 	SketchJob j;
-	j.seq_off = off[i], j.rid = 0, j.pad = 0;
+	j.seq_off = off[i], j.rid = 0;
 	for (int s = 0; s < W; ++s) {
-		j.len = len[i], j.shift = s;
+		j.len = len[i], j.shift = s, j.dl = (int32_t)sk_diet_len((uint32_t)len[i], (uint32_t)s, S);
 		jobs[(size_t)i * JW + s] = j;
 	}
 	if (crop) {
-		j.len = (int32_t)(unsigned)((float)max_seeds * len[i]), j.shift = 0;
+		j.len = (int32_t)(unsigned)((float)max_seeds * len[i]), j.shift = 0, j.dl = (int32_t)sk_diet_len((uint32_t)j.len, 0, S);
 		jobs[(size_t)i * JW + W] = j;
 	}
 }
@@ -246,6 +246,8 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 		return GD_OK;
 	};
 	static const int sk_ver = getenv("GDIET_SK_V") ? atoi(getenv("GDIET_SK_V")) : 3;
+	static const int sk_defer = getenv("GDIET_SK_DEFER") ? atoi(getenv("GDIET_SK_DEFER")) : 1; // v3: deferred look-back (A/B switch)
+	B.defer = sk_defer;
 	if (sk_ver != 2) {
 		if (small) rc = launch(gd_sketch_tile3_kernel<32>, 32, sizeof(SketchSmem3<32>));
 		else if (big_threads == 64) rc = launch(gd_sketch_tile3_kernel<64>, 64, sizeof(SketchSmem3<64>));
@@ -275,7 +277,7 @@ extern "C" int gd_sketch_ref_batch_device(gd_ctx *ctx, int n, const int64_t *d_o
 	int rc = make_params(ctx, w, k, Z, W, S);
 	if (rc) return rc;
 	if ((rc = gd_reserve(ctx, ctx->sk_jobs, (size_t)n * sizeof(SketchJob)))) return rc;
-	gd_sketch_ref_jobs_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, d_off, d_len, d_rid, (SketchJob *)ctx->sk_jobs.p);
+	gd_sketch_ref_jobs_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(S, n, d_off, d_len, d_rid, (SketchJob *)ctx->sk_jobs.p);
 	ctx->stat_launches++;
 	// without per-sequence lengths on the host, assume the longest job may need the multi-tile path
 	return gd_sketch_run_jobs(ctx, S, n, (const SketchJob *)ctx->sk_jobs.p, total_len, total_len, d_buf, d_out_off,
@@ -321,7 +323,7 @@ extern "C" int gd_sketch_ref_batch(gd_ctx *ctx, int n, const int64_t *off, const
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->sk_off.p, off, (size_t)n * 8, cudaMemcpyHostToDevice, s));
 	GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->sk_len.p, len, (size_t)n * 4, cudaMemcpyHostToDevice, s));
 	if (rid) GD_CUDA_OK(ctx, cudaMemcpyAsync(ctx->sk_rid.p, rid, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-	gd_sketch_ref_jobs_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, (const int64_t *)ctx->sk_off.p, (const int32_t *)ctx->sk_len.p,
+	gd_sketch_ref_jobs_kernel<<<(n + 255) / 256, 256, 0, s>>>(S, n, (const int64_t *)ctx->sk_off.p, (const int32_t *)ctx->sk_len.p,
 	                                                      rid ? (const uint32_t *)ctx->sk_rid.p : nullptr,
 	                                                      (SketchJob *)ctx->sk_jobs.p);
 	ctx->stat_launches++;
@@ -522,7 +524,7 @@ int gd_sketch_reads_device_raw(gd_ctx *ctx, int n, const int64_t *d_off, const i
 	if ((rc = gd_reserve(ctx, ctx->sk_jobs, (size_t)njobs * sizeof(SketchJob)))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->sk_out_off, (size_t)(njobs + 1) * 8))) return rc;
 	if ((rc = gd_reserve(ctx, ctx->sk_out, (size_t)worst * 16 + 64))) return rc;
-	gd_sketch_read_jobs_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, d_off, d_len, W, crop, max_seeds, (SketchJob *)ctx->sk_jobs.p);
+	gd_sketch_read_jobs_kernel<<<(n + 255) / 256, 256, 0, s>>>(S, n, d_off, d_len, W, crop, max_seeds, (SketchJob *)ctx->sk_jobs.p);
 	ctx->stat_launches++;
 	rc = gd_sketch_run_jobs(ctx, S, njobs, (const SketchJob *)ctx->sk_jobs.p, per_job, worst, d_buf, (int64_t *)ctx->sk_out_off.p,
 	                        (uint64_t *)ctx->sk_out.p, worst, fixed ? per_job : 0, d_cnt);

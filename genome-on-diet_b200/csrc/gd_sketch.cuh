@@ -26,7 +26,7 @@ struct SketchJob {
 	int32_t len;      // bytes visible to this job (len or len_crop)
 	int32_t shift;
 	uint32_t rid;
-	int32_t pad;
+	int32_t dl;       // sparsified length, sk_diet_len(len, shift) -- filled by the job kernels (read by the v3 tile body)
 };
 
 struct SketchParams {
@@ -52,6 +52,7 @@ struct SketchBatch {
 	// and its count to out_cnt[j].  No tile depends on another one then: no ticket, no look-back.
 	int64_t fixed_stride;      // 0 = dense output in job order (decoupled look-back)
 	int32_t *out_cnt;          // [njobs], fixed-stride mode
+	int32_t defer;             // v3, dense output: a tile's look-back and copy-out run in the middle of the block's next tile
 };
 
 GD_DEV uint64_t sk_hash64(uint64_t key, uint64_t mask)
@@ -508,40 +509,93 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 	// holds a low ticket hostage, and every later tile spins on it in the look-back -- 850 probes per tile.)
 	// Fixed-stride mode: static assignment, nothing orders the tiles.
 	long long next = block_idx();
+	// Dense output: the records of a tile are parked in shared memory (SUF | PREM, free between phase 4 of a tile and phase 3 of
+	// the next) and its count is published; the look-back over the predecessors and the copy-out run in the middle of the
+	// block's NEXT tile, when the predecessors have long published theirs -- nobody waits at a barrier for warp 0 to spin.
+	int pend = 0, pend_total = 0, pend_job = 0, pend_first = 0;
+	long long pend_tile = 0;
+	auto flush = [&]() {
+		if (wid == 0) { // decoupled look-back over tiles, 32 predecessors per probe
+			long long excl = 0, pt = pend_tile - 1;
+			for (;;) {
+				const long long idx = pt - lane;
+				unsigned long long sv = 2ull << 62; // "before the first tile": an inclusive prefix of 0
+				if (idx >= 0) do sv = ld_volatile(&B.status[idx]);
+					while ((sv >> 62) == 0);
+				const uint32_t incl = ballot(0xffffffffu, (sv >> 62) == 2); // lanes that hold an inclusive prefix
+				const int first = incl ? ffs32(incl) - 1 : 32;                // the nearest one ends the walk
+				unsigned long long c = lane <= first ? (sv & 0x3fffffffffffffffull) : 0ull;
+				for (int d = 16; d >= 1; d >>= 1) {
+					const uint32_t lo = shfl_xor(0xffffffffu, (uint32_t)c, d, 32), hi = shfl_xor(0xffffffffu, (uint32_t)(c >> 32), d, 32);
+					c += (unsigned long long)hi << 32 | lo;
+				}
+				excl += (long long)c;
+				if (incl) break;
+				pt -= 32;
+			}
+			if (lane == 0) {
+				st_volatile(&B.status[pend_tile], (2ull << 62) | (unsigned long long)(excl + pend_total));
+				sm->excl = excl;
+				if (pend_first) B.out_off[pend_job] = excl;
+				if (pend_tile == B.ntiles - 1) B.out_off[B.njobs] = excl + pend_total;
+			}
+		}
+		sync_block();
+		const long long excl = sm->excl;
+		const ulonglong2 *st = (const ulonglong2 *)sm->SUF;
+		for (int r = tid; r < pend_total; r += THREADS)
+			if (excl + r < B.out_cap) {
+				const ulonglong2 v = st[r];
+				B.out[2 * (excl + r)] = v.x, B.out[2 * (excl + r) + 1] = v.y;
+			}
+		sync_block(); // SUF | PREM are free again
+		pend = 0;
+	};
 	sync_block();
 	for (;;) {
-		if (tid == 0) {
-			const long long tile = fixed ? next : (long long)atomic_add(B.ticket, 1);
-			sm->h_tile = tile;
+		if (wid == 0) { // tile header: ticket, tile -> job, byte range to stage
+			long long tile = 0;
+			if (lane == 0) tile = fixed ? next : (long long)atomic_add(B.ticket, 1);
+			tile = (long long)((uint64_t)shfl_idx(0xffffffffu, (uint32_t)tile, 0, 32) |
+			                   (uint64_t)shfl_idx(0xffffffffu, (uint32_t)((uint64_t)tile >> 32), 0, 32) << 32);
+			if (lane == 0) sm->h_tile = tile;
 			if (tile < B.ntiles) {
 				int job;
 				long long chunk;
 				if (S.one_tile_per_job) job = (int)tile, chunk = 0;
-				else {
-					int lo = 0, hi = B.njobs; // last job with tile_base[job] <= tile
+				else { // last job with tile_base[job] <= tile: 32 split points per round trip
+					long long lo = 0, hi = B.njobs, lo_base = 0;
 					while (hi - lo > 1) {
-						int mid = (lo + hi) >> 1;
-						if (B.tile_base[mid] <= tile) lo = mid;
-						else hi = mid;
+						const long long step = (hi - lo + 31) >> 5, idx = lo + (lane + 1) * step;
+						const long long v = idx < hi ? B.tile_base[idx] : 0;
+						const uint32_t le = ballot(0xffffffffu, idx < hi && v <= tile);
+						const int c = popc(le); // the predicate is monotone: the first c split points are <= tile
+						if (c > 0)
+							lo_base = (long long)((uint64_t)shfl_idx(0xffffffffu, (uint32_t)v, c - 1, 32) |
+							                      (uint64_t)shfl_idx(0xffffffffu, (uint32_t)((uint64_t)v >> 32), c - 1, 32) << 32);
+						if (lo + (c + 1) * step < hi) hi = lo + (c + 1) * step;
+						lo += c * step;
 					}
-					job = lo, chunk = tile - B.tile_base[lo];
+					job = (int)lo, chunk = tile - lo_base;
 				}
 				const SketchJob J = B.jobs[job];
-				const uint32_t shift = (uint32_t)J.shift;
-				const int dl = (int)sk_diet_len((uint32_t)J.len, shift, S);
-				const int i0 = (int)(chunk * S.TP), B0 = i0 - HL;
-				sm->h_job = job, sm->h_i0 = i0, sm->h_dl = dl, sm->h_shift = shift, sm->h_rid = J.rid, sm->h_seq_off = J.seq_off;
-				// bytes of the original sequence the tile touches: [real(first loaded position), real(last loaded position)]
-				const int jlo = B0 > 0 ? B0 : 0, jhi = (B0 + NP < dl ? B0 + NP : dl) - 1;
-				int staged = 0, raw_lo = 0, nbytes = 0, safe = 0;
-				if (dl >= full_run && jhi >= jlo) {
-					const uint32_t rlo = sk_real((uint32_t)jlo, shift, S), rhi = sk_real((uint32_t)jhi, shift, S);
-					const uint32_t lead = (uint32_t)((unsigned long long)(B.buf + J.seq_off + rlo) & 15);
-					safe = (int)rlo;
-					nbytes = (int)(rhi - rlo + 1 + lead);
-					if (nbytes <= GD_SK_RAW(THREADS)) staged = 1, raw_lo = (int)rlo - (int)lead;
+				if (lane == 0) {
+					const uint32_t shift = (uint32_t)J.shift;
+					const int dl = J.dl;
+					const int i0 = (int)(chunk * S.TP), B0 = i0 - HL;
+					sm->h_job = job, sm->h_i0 = i0, sm->h_dl = dl, sm->h_shift = shift, sm->h_rid = J.rid, sm->h_seq_off = J.seq_off;
+					// bytes of the original sequence the tile touches: [real(first loaded position), real(last loaded position)]
+					const int jlo = B0 > 0 ? B0 : 0, jhi = (B0 + NP < dl ? B0 + NP : dl) - 1;
+					int staged = 0, raw_lo = 0, nbytes = 0, safe = 0;
+					if (dl >= full_run && jhi >= jlo) {
+						const uint32_t rlo = sk_real((uint32_t)jlo, shift, S), rhi = sk_real((uint32_t)jhi, shift, S);
+						const uint32_t lead = (uint32_t)((unsigned long long)(B.buf + J.seq_off + rlo) & 15);
+						safe = (int)rlo;
+						nbytes = (int)(rhi - rlo + 1 + lead);
+						if (nbytes <= GD_SK_RAW(THREADS)) staged = 1, raw_lo = (int)rlo - (int)lead;
+					}
+					sm->h_staged = staged, sm->h_raw_lo = raw_lo, sm->h_nbytes = nbytes, sm->h_safe = safe;
 				}
-				sm->h_staged = staged, sm->h_raw_lo = raw_lo, sm->h_nbytes = nbytes, sm->h_safe = safe;
 				next = tile + grid_dim();
 			}
 		}
@@ -699,6 +753,7 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 				const int elo = HL - s0, ehi = imin(HL + S.TP, dl - B0) - s0; // p in [elo, ehi)
 				cand = sk_mask_from(elo) & ~sk_mask_from(ehi) & okbits;
 			}
+			if (pend) flush(); // the previous tile's records leave SUF | PREM before phase 3 writes there
 			if (w >= 9) {
 				// ---- phase 3: minimum of every full window ending at e = s0+p (0 = no full window ends here).  The window starts
 				// at a = e-(w-1) in chunk tid-dt, slot q (the same dt, q for every thread): own prefix minimum, whole chunks in
@@ -800,72 +855,55 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 			total += c;
 		}
 		const int local = wbase + inc - cnt;
-		// ---- decoupled look-back over tiles, 32 predecessors per probe (warp 0); fixed-stride mode: the job's own slot ----
-		if (fixed) {
+		const uint64_t yhi = (uint64_t)sm->h_rid << 32;
+		// record o of the thread: x = hash64 << 8 | k (the marker bit 56 leaves at the top), y = rid << 32 | position << 1 | strand
+		auto put = [&](uint64_t *dst, int p) {
+			const uint32_t j = (uint32_t)(j0 + p); // >= 0: a k-mer
+			uint32_t real;
+			if (ones1) real = j * (uint32_t)S.W + sm->ones_loc[0] + shift;
+			else {
+				const uint32_t qd = j / (uint32_t)S.ones, rm = j - qd * (uint32_t)S.ones;
+				real = qd * (uint32_t)S.W + sm->ones_loc[rm] + shift;
+			}
+			dst[0] = key[p] << 8 | (uint64_t)k;
+			dst[1] = yhi | (uint64_t)real << 1 | (uint64_t)(zbits >> p & 1);
+		};
+		if (fixed) { // the job's own slot of fixed_stride records; nothing orders the tiles
 			if (tid == 0) {
-				sm->excl = (long long)job * B.fixed_stride;
-				B.out_off[job] = sm->excl, B.out_cnt[job] = total;
+				B.out_off[job] = (long long)job * B.fixed_stride, B.out_cnt[job] = total;
 				if (tile == B.ntiles - 1) B.out_off[B.njobs] = (long long)B.njobs * B.fixed_stride;
 			}
-		} else if (wid == 0) {
-			long long excl = 0;
-			if (tile == 0) {
-				if (lane == 0) st_volatile(&B.status[0], (2ull << 62) | (unsigned long long)total);
-			} else {
-				if (lane == 0) {
-					st_volatile(&B.status[tile], (1ull << 62) | (unsigned long long)total);
-					fence();
-				}
-				long long pt = tile - 1;
-				for (;;) {
-					const long long idx = pt - lane;
-					unsigned long long sv = 2ull << 62; // "before the first tile": an inclusive prefix of 0
-					if (idx >= 0) do sv = ld_volatile(&B.status[idx]);
-						while ((sv >> 62) == 0);
-					const uint32_t incl = ballot(0xffffffffu, (sv >> 62) == 2); // lanes that hold an inclusive prefix
-					const int first = incl ? ffs32(incl) - 1 : 32;                // the nearest one ends the walk
-					unsigned long long c = lane <= first ? (sv & 0x3fffffffffffffffull) : 0ull;
-					for (int d = 16; d >= 1; d >>= 1) {
-						const uint32_t lo = shfl_xor(0xffffffffu, (uint32_t)c, d, 32), hi = shfl_xor(0xffffffffu, (uint32_t)(c >> 32), d, 32);
-						c += (unsigned long long)hi << 32 | lo;
-					}
-					excl += (long long)c;
-					if (incl) break;
-					pt -= 32;
-				}
-				if (lane == 0) st_volatile(&B.status[tile], (2ull << 62) | (unsigned long long)(excl + total));
-			}
-			if (lane == 0) {
-				sm->excl = excl;
-				if (i0 == 0) B.out_off[job] = excl;
-				if (tile == B.ntiles - 1) B.out_off[B.njobs] = excl + total;
-			}
-		}
-		sync_block();
-		if (emit) {
-			const long long obase = sm->excl + local;
-			const uint64_t yhi = (uint64_t)sm->h_rid << 32;
-			int o = 0;
+			if (emit) {
+				const long long obase = (long long)job * B.fixed_stride + local;
+				int o = 0;
 #pragma unroll
-			for (int p = 0; p < 8; ++p)
-				if (emit >> p & 1) {
-					const long long dst = obase + o;
-					if (fixed ? (local + o < B.fixed_stride) : (dst < B.out_cap)) {
-						const uint32_t j = (uint32_t)(j0 + p); // >= 0: a k-mer
-						uint32_t real;
-						if (ones1) real = j * (uint32_t)S.W + sm->ones_loc[0] + shift;
-						else {
-							const uint32_t qd = j / (uint32_t)S.ones, rm = j - qd * (uint32_t)S.ones;
-							real = qd * (uint32_t)S.W + sm->ones_loc[rm] + shift;
-						}
-						B.out[2 * dst] = key[p] << 8 | (uint64_t)k; // hash64 << 8 | k: the marker bit 56 leaves at the top
-						B.out[2 * dst + 1] = yhi | (uint64_t)real << 1 | (uint64_t)(zbits >> p & 1);
+				for (int p = 0; p < 8; ++p)
+					if (emit >> p & 1) {
+						if (local + o < B.fixed_stride) put(B.out + 2 * (obase + o), p);
+						++o;
 					}
-					++o;
-				}
+			}
+		} else {
+			if (pend) flush(); // (tiles of jobs too short to emit skip the phases above)
+			if (emit) {
+				int o = 0;
+#pragma unroll
+				for (int p = 0; p < 8; ++p)
+					if (emit >> p & 1) put(sm->SUF + 2 * (local + o), p), ++o;
+			}
+			if (tid == 0) { // the tile's count: an aggregate for the look-backs of later tiles (tile 0: already its inclusive prefix)
+				st_volatile(&B.status[tile], ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)total);
+				fence();
+			}
+			pend = 1, pend_tile = tile, pend_total = total, pend_job = job, pend_first = i0 == 0;
+			if (!B.defer) {
+				sync_block();
+				flush();
+			}
 		}
 		sync_block(); // shared memory (and the header) is reused by the next tile
 	}
+	if (pend) flush();
 }
 
 } // namespace gd

@@ -7,8 +7,8 @@
 
 using namespace gd;
 
-static int g_ver = 3; // tile body: 3 = sketch_tile_body3 (the product default), 2 = sketch_tile_body
-extern "C" void emu_sketch_version(int v) { g_ver = v; }
+static int g_ver = 3, g_defer = 1; // tile body: 3 = sketch_tile_body3 (the product default; +4: look-back not deferred), 2 = sketch_tile_body
+extern "C" void emu_sketch_version(int v) { g_ver = v & 3, g_defer = !(v & 4); }
 
 template <int THREADS>
 static void run_tiles(const SketchParams &S, SketchBatch &B, int grid)
@@ -32,7 +32,6 @@ extern "C" long emu_sketch_jobs(int njobs, const int64_t *seq_off, const int32_t
 	for (int g = 0; g < W; ++g)
 		if (Z[g] == '1') S.ones_loc[S.ones++] = (uint8_t)g;
 	std::vector<SketchJob> jobs(njobs);
-	for (int i = 0; i < njobs; ++i) jobs[i] = SketchJob{seq_off[i], len[i], shift[i], rid[i], 0};
 	S.TP = sk_tile_emit(small ? 256 : 2048, w, k);
 	S.one_tile_per_job = small;
 	std::vector<int64_t> tb(njobs + 1, 0);
@@ -45,6 +44,7 @@ extern "C" long emu_sketch_jobs(int njobs, const int64_t *seq_off, const int32_t
 			for (int o = 0; o < S.ones; ++o)
 				if (S.ones_loc[o] < rem) ++dl;
 		}
+		jobs[i] = SketchJob{seq_off[i], len[i], shift[i], rid[i], (int32_t)dl};
 		int64_t t = small ? 1 : (dl + S.TP - 1) / S.TP;
 		tb[i + 1] = tb[i] + (t < 1 ? 1 : t);
 	}
@@ -53,6 +53,7 @@ extern "C" long emu_sketch_jobs(int njobs, const int64_t *seq_off, const int32_t
 	SketchBatch B;
 	memset(&B, 0, sizeof(B));
 	B.njobs = njobs, B.ntiles = tb[njobs], B.jobs = jobs.data(), B.tile_base = small ? nullptr : tb.data();
+	B.defer = g_defer;
 	B.buf = buf, B.status = status.data(), B.ticket = &ticket, B.out_off = out_off, B.out = out, B.out_cap = out_cap;
 	if (small) run_tiles<32>(S, B, grid);
 	else run_tiles<256>(S, B, grid);

@@ -239,6 +239,7 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 	B.ticket = (int32_t *)((char *)ctx->sk_state.p + (size_t)ntiles_bound * 8);
 	auto launch = [&](auto kern, int threads, size_t smem) -> int {
 		int occ = 0;
+		if (smem > 48 * 1024) GD_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
 		int blocks = (int)std::min<int64_t>(ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));
 		GdKernelTimer tm(ctx, &ctx->tm_sketch);
@@ -246,8 +247,6 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 		return GD_OK;
 	};
 	static const int sk_ver = getenv("GDIET_SK_V") ? atoi(getenv("GDIET_SK_V")) : 3;
-	static const int sk_defer = getenv("GDIET_SK_DEFER") ? atoi(getenv("GDIET_SK_DEFER")) : 1; // v3: deferred look-back (A/B switch)
-	B.defer = sk_defer;
 	if (sk_ver != 2) {
 		if (small) rc = launch(gd_sketch_tile3_kernel<32>, 32, sizeof(SketchSmem3<32>));
 		else if (big_threads == 64) rc = launch(gd_sketch_tile3_kernel<64>, 64, sizeof(SketchSmem3<64>));

@@ -52,7 +52,6 @@ struct SketchBatch {
 	// and its count to out_cnt[j].  No tile depends on another one then: no ticket, no look-back.
 	int64_t fixed_stride;      // 0 = dense output in job order (decoupled look-back)
 	int32_t *out_cnt;          // [njobs], fixed-stride mode
-	int32_t defer;             // v3, dense output: a tile's look-back and copy-out run in the middle of the block's next tile
 };
 
 GD_DEV uint64_t sk_hash64(uint64_t key, uint64_t mask)
@@ -440,7 +439,8 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 //     every thread, so the addresses are `thread * 8 + uniform offset` and the in-between loop has a uniform trip count.
 // =============================================================================================
 template <int THREADS> struct SketchSmem3 {
-	enum { NP = THREADS * 8, F2W = NP / 16 + GD_SK_PADW + 4, R2W = NP / 16 + 6 };
+	enum { NP = THREADS * 8, F2W = NP / 16 + GD_SK_PADW + 4, R2W = NP / 16 + 6,
+	       PARK = THREADS >= 64 ? NP / 4 : 8 }; // records the parking area holds (one-warp tiles are used with fixed-stride output, which parks nothing)
 	uint64_t SUF[NP];  // w >= 9: minimum of the keys over [s, end of s's chunk]; w <= 8: the key itself   ([p][thread])
 	uint64_t PREM[NP]; // w >= 9: maximum of M over [start of chunk, s];          w <= 8: M itself          ([p][thread])
 	uint32_t F2[F2W];  // 2-bit codes, position s at bit 2s (after GD_SK_PADW zero words)
@@ -449,11 +449,18 @@ template <int THREADS> struct SketchSmem3 {
 	uint32_t lut[256]; // seq_nt4_table (sketch.c:11-18) as code, or 1 << 16 for N
 	int32_t warp_cnt[32];
 	long long excl;
-	// tile header, written by thread 0
-	long long h_tile, h_seq_off;
-	int32_t h_job, h_i0, h_dl, h_staged, h_raw_lo, h_nbytes, h_safe;
-	uint32_t h_shift, h_rid;
+	// tile headers, written by warp 0 while the block finishes the previous tile (two copies, used alternately)
+	struct Hdr {
+		long long tile, seq_off;
+		int32_t job, i0, dl, staged, raw_lo, nbytes, safe;
+		uint32_t shift, rid;
+	} hdr[2];
+	// the job of the block's previous tile: its tile range and record (most tiles of a contig stay in the same job)
+	long long c_lo, c_hi;
+	int32_t c_job;
+	SketchJob c_J;
 	uint8_t ones_loc[64];
+	alignas(16) unsigned long long park[2 * PARK]; // dense output: the records of the block's previous tile until their offset is known
 	alignas(16) uint32_t raw[GD_SK_RAW(THREADS) / 4 + 4]; // the tile's slice of the ASCII sequence (16-byte aligned in global memory)
 };
 
@@ -502,118 +509,137 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 	if (tid < 4) sm->NB[tid < 2 ? tid : NP / 8 + tid] = 0;
 	for (int i = tid; i < 64; i += THREADS) sm->ones_loc[i] = S.ones_loc[i];
 	for (int c = tid; c < 256; c += THREADS) sm->lut[c] = (uint32_t)sk_nt4((unsigned)c) < 4u ? (uint32_t)sk_nt4((unsigned)c) : 0x10000u;
+	if (tid == 0) sm->c_lo = 0, sm->c_hi = 0, sm->c_job = -1;
 	const bool fixed = B.fixed_stride > 0;
-	// Tiles are handed out in order by a global ticket, drawn when the block is free: every tile's predecessors are then held by
-	// blocks that are already computing them, so the look-back below never waits for a tile nobody has started.  (Drawing the
-	// NEXT tile's ticket while the current one is computed was measured on a B200 and is twice as slow: a block that is late
-	// holds a low ticket hostage, and every later tile spins on it in the look-back -- 850 probes per tile.)
-	// Fixed-stride mode: static assignment, nothing orders the tiles.
-	long long next = block_idx();
-	// Dense output: the records of a tile are parked in shared memory (SUF | PREM, free between phase 4 of a tile and phase 3 of
-	// the next) and its count is published; the look-back over the predecessors and the copy-out run in the middle of the
-	// block's NEXT tile, when the predecessors have long published theirs -- nobody waits at a barrier for warp 0 to spin.
+	// Tiles are handed out in order by a global ticket, drawn when the block is about to start the tile: every tile's
+	// predecessors are then held by blocks that are already computing them.  (Drawing the ticket one tile ahead was measured
+	// on a B200 and is twice as slow: a block that is late holds a low ticket hostage and every later tile spins on it in the
+	// look-back -- 850 probes per tile.  A static tile = block + round * grid assignment of the fixed-stride mode left a third
+	// of the resident warps idle: with grid a multiple of the jobs per read, the same blocks got all the 15-base cropped jobs.)
+	// The header of a tile -- ticket, tile -> job, byte range to stage -- is made by warp 0 right after it parked the records
+	// of the previous tile, so the barrier that ends a tile also publishes the next header.
+	auto make_header = [&](typename SketchSmem3<THREADS>::Hdr *h) { // warp 0
+		long long tile = 0;
+		if (lane == 0) tile = (long long)atomic_add(B.ticket, 1);
+		tile = (long long)((uint64_t)shfl_idx(0xffffffffu, (uint32_t)tile, 0, 32) |
+		                   (uint64_t)shfl_idx(0xffffffffu, (uint32_t)((uint64_t)tile >> 32), 0, 32) << 32);
+		if (lane == 0) h->tile = tile;
+		if (tile >= B.ntiles) return;
+		int job;
+		long long chunk;
+		SketchJob J;
+		if (S.one_tile_per_job) job = (int)tile, chunk = 0, J = B.jobs[job];
+		else if (tile >= sm->c_lo && tile < sm->c_hi) job = sm->c_job, chunk = tile - sm->c_lo, J = sm->c_J;
+		else { // last job with tile_base[job] <= tile: 32 split points per round trip
+			long long lo = 0, hi = B.njobs, lo_base = 0;
+			while (hi - lo > 1) {
+				const long long step = (hi - lo + 31) >> 5, idx = lo + (lane + 1) * step;
+				const long long v = idx < hi ? B.tile_base[idx] : 0;
+				const uint32_t le = ballot(0xffffffffu, idx < hi && v <= tile);
+				const int c = popc(le); // the predicate is monotone: the first c split points are <= tile
+				if (c > 0)
+					lo_base = (long long)((uint64_t)shfl_idx(0xffffffffu, (uint32_t)v, c - 1, 32) |
+					                      (uint64_t)shfl_idx(0xffffffffu, (uint32_t)((uint64_t)v >> 32), c - 1, 32) << 32);
+				if (lo + (c + 1) * step < hi) hi = lo + (c + 1) * step;
+				lo += c * step;
+			}
+			job = (int)lo, chunk = tile - lo_base;
+			J = B.jobs[job];
+			const long long hi_base = B.tile_base[job + 1];
+			sync_warp(0xffffffffu); // every lane has read the cache
+			if (lane == 0) sm->c_lo = lo_base, sm->c_hi = hi_base, sm->c_job = job, sm->c_J = J;
+			sync_warp(0xffffffffu);
+		}
+		if (lane == 0) {
+			const uint32_t shift = (uint32_t)J.shift;
+			const int dl = J.dl;
+			const int i0 = (int)(chunk * S.TP), B0 = i0 - HL;
+			h->job = job, h->i0 = i0, h->dl = dl, h->shift = shift, h->rid = J.rid, h->seq_off = J.seq_off;
+			// bytes of the original sequence the tile touches: [real(first loaded position), real(last loaded position)]
+			const int jlo = B0 > 0 ? B0 : 0, jhi = (B0 + NP < dl ? B0 + NP : dl) - 1;
+			int staged = 0, raw_lo = 0, nbytes = 0, safe = 0;
+			if (dl >= full_run && jhi >= jlo) {
+				const uint32_t rlo = sk_real((uint32_t)jlo, shift, S), rhi = sk_real((uint32_t)jhi, shift, S);
+				const uint32_t lead = (uint32_t)((unsigned long long)(B.buf + J.seq_off + rlo) & 15);
+				safe = (int)rlo;
+				nbytes = (int)(rhi - rlo + 1 + lead);
+				if (nbytes <= GD_SK_RAW(THREADS)) staged = 1, raw_lo = (int)rlo - (int)lead;
+			}
+			h->staged = staged, h->raw_lo = raw_lo, h->nbytes = nbytes, h->safe = safe;
+		}
+	};
+	// Dense output: the records of a tile are parked in shared memory and its count is published; the look-back over the
+	// predecessors and the copy-out run in the middle of the block's NEXT tile, when the predecessors have long published
+	// theirs: warp 0 issues the first probe when the tile starts and sums up after its hashing phase, the offset travels with
+	// the barrier of the window-minimum phase, and nobody waits for warp 0 to spin.  (Measured on a B200, contigs: look-back
+	// at the end of the own tile 172 Gbases/s -- 28 % of the stall samples at the barrier behind it --, deferred to the next
+	// tile's hashing phase 211, deferred only to the next tile's encode phase 166: too early, 10 probes per tile.)
+	// A tile with more records than the parking area (windows of w <= 6) waits for its offset and writes from registers.
 	int pend = 0, pend_total = 0, pend_job = 0, pend_first = 0;
 	long long pend_tile = 0;
-	auto flush = [&]() {
-		if (wid == 0) { // decoupled look-back over tiles, 32 predecessors per probe
-			long long excl = 0, pt = pend_tile - 1;
-			for (;;) {
-				const long long idx = pt - lane;
-				unsigned long long sv = 2ull << 62; // "before the first tile": an inclusive prefix of 0
-				if (idx >= 0) do sv = ld_volatile(&B.status[idx]);
-					while ((sv >> 62) == 0);
-				const uint32_t incl = ballot(0xffffffffu, (sv >> 62) == 2); // lanes that hold an inclusive prefix
-				const int first = incl ? ffs32(incl) - 1 : 32;                // the nearest one ends the walk
-				unsigned long long c = lane <= first ? (sv & 0x3fffffffffffffffull) : 0ull;
-				for (int d = 16; d >= 1; d >>= 1) {
-					const uint32_t lo = shfl_xor(0xffffffffu, (uint32_t)c, d, 32), hi = shfl_xor(0xffffffffu, (uint32_t)(c >> 32), d, 32);
-					c += (unsigned long long)hi << 32 | lo;
-				}
-				excl += (long long)c;
-				if (incl) break;
-				pt -= 32;
+	unsigned long long sv0 = 0; // warp 0: first look-back probe of the pending tile
+	auto lookback_issue = [&]() { // warp 0
+		const long long idx = pend_tile - 1 - lane;
+		sv0 = idx >= 0 ? ld_volatile(&B.status[idx]) : 2ull << 62; // "before the first tile": an inclusive prefix of 0
+	};
+	auto lookback_finish = [&]() { // warp 0: decoupled look-back over tiles, 32 predecessors per probe
+		long long excl = 0, pt = pend_tile - 1;
+		unsigned long long sv = sv0;
+		for (;;) {
+			const long long idx = pt - lane;
+			if (idx >= 0)
+				while ((sv >> 62) == 0) sv = ld_volatile(&B.status[idx]);
+			const uint32_t incl = ballot(0xffffffffu, (sv >> 62) == 2); // lanes that hold an inclusive prefix
+			const int first = incl ? ffs32(incl) - 1 : 32;                // the nearest one ends the walk
+			unsigned long long c = lane <= first ? (sv & 0x3fffffffffffffffull) : 0ull;
+			for (int d = 16; d >= 1; d >>= 1) {
+				const uint32_t lo = shfl_xor(0xffffffffu, (uint32_t)c, d, 32), hi = shfl_xor(0xffffffffu, (uint32_t)(c >> 32), d, 32);
+				c += (unsigned long long)hi << 32 | lo;
 			}
-			if (lane == 0) {
-				st_volatile(&B.status[pend_tile], (2ull << 62) | (unsigned long long)(excl + pend_total));
-				sm->excl = excl;
-				if (pend_first) B.out_off[pend_job] = excl;
-				if (pend_tile == B.ntiles - 1) B.out_off[B.njobs] = excl + pend_total;
-			}
+			excl += (long long)c;
+			if (incl) break;
+			pt -= 32;
+			sv = pt - lane >= 0 ? ld_volatile(&B.status[pt - lane]) : 2ull << 62;
 		}
-		sync_block();
+		if (lane == 0) {
+			st_volatile(&B.status[pend_tile], (2ull << 62) | (unsigned long long)(excl + pend_total));
+			sm->excl = excl;
+			if (pend_first) B.out_off[pend_job] = excl;
+			if (pend_tile == B.ntiles - 1) B.out_off[B.njobs] = excl + pend_total;
+		}
+	};
+	auto copy_out = [&]() { // every thread, after a barrier behind lookback_finish
 		const long long excl = sm->excl;
-		const ulonglong2 *st = (const ulonglong2 *)sm->SUF;
+		const ulonglong2 *st = (const ulonglong2 *)sm->park;
 		for (int r = tid; r < pend_total; r += THREADS)
 			if (excl + r < B.out_cap) {
 				const ulonglong2 v = st[r];
 				B.out[2 * (excl + r)] = v.x, B.out[2 * (excl + r) + 1] = v.y;
 			}
-		sync_block(); // SUF | PREM are free again
-		pend = 0;
 	};
 	sync_block();
+	int cur = 0;
+	if (wid == 0) make_header(&sm->hdr[0]);
 	for (;;) {
-		if (wid == 0) { // tile header: ticket, tile -> job, byte range to stage
-			long long tile = 0;
-			if (lane == 0) tile = fixed ? next : (long long)atomic_add(B.ticket, 1);
-			tile = (long long)((uint64_t)shfl_idx(0xffffffffu, (uint32_t)tile, 0, 32) |
-			                   (uint64_t)shfl_idx(0xffffffffu, (uint32_t)((uint64_t)tile >> 32), 0, 32) << 32);
-			if (lane == 0) sm->h_tile = tile;
-			if (tile < B.ntiles) {
-				int job;
-				long long chunk;
-				if (S.one_tile_per_job) job = (int)tile, chunk = 0;
-				else { // last job with tile_base[job] <= tile: 32 split points per round trip
-					long long lo = 0, hi = B.njobs, lo_base = 0;
-					while (hi - lo > 1) {
-						const long long step = (hi - lo + 31) >> 5, idx = lo + (lane + 1) * step;
-						const long long v = idx < hi ? B.tile_base[idx] : 0;
-						const uint32_t le = ballot(0xffffffffu, idx < hi && v <= tile);
-						const int c = popc(le); // the predicate is monotone: the first c split points are <= tile
-						if (c > 0)
-							lo_base = (long long)((uint64_t)shfl_idx(0xffffffffu, (uint32_t)v, c - 1, 32) |
-							                      (uint64_t)shfl_idx(0xffffffffu, (uint32_t)((uint64_t)v >> 32), c - 1, 32) << 32);
-						if (lo + (c + 1) * step < hi) hi = lo + (c + 1) * step;
-						lo += c * step;
-					}
-					job = (int)lo, chunk = tile - lo_base;
-				}
-				const SketchJob J = B.jobs[job];
-				if (lane == 0) {
-					const uint32_t shift = (uint32_t)J.shift;
-					const int dl = J.dl;
-					const int i0 = (int)(chunk * S.TP), B0 = i0 - HL;
-					sm->h_job = job, sm->h_i0 = i0, sm->h_dl = dl, sm->h_shift = shift, sm->h_rid = J.rid, sm->h_seq_off = J.seq_off;
-					// bytes of the original sequence the tile touches: [real(first loaded position), real(last loaded position)]
-					const int jlo = B0 > 0 ? B0 : 0, jhi = (B0 + NP < dl ? B0 + NP : dl) - 1;
-					int staged = 0, raw_lo = 0, nbytes = 0, safe = 0;
-					if (dl >= full_run && jhi >= jlo) {
-						const uint32_t rlo = sk_real((uint32_t)jlo, shift, S), rhi = sk_real((uint32_t)jhi, shift, S);
-						const uint32_t lead = (uint32_t)((unsigned long long)(B.buf + J.seq_off + rlo) & 15);
-						safe = (int)rlo;
-						nbytes = (int)(rhi - rlo + 1 + lead);
-						if (nbytes <= GD_SK_RAW(THREADS)) staged = 1, raw_lo = (int)rlo - (int)lead;
-					}
-					sm->h_staged = staged, sm->h_raw_lo = raw_lo, sm->h_nbytes = nbytes, sm->h_safe = safe;
-				}
-				next = tile + grid_dim();
-			}
-		}
-		sync_block();
-		const long long tile = sm->h_tile;
+		sync_block(); // header of this tile; the previous tile's parked records
+		const typename SketchSmem3<THREADS>::Hdr *const h = &sm->hdr[cur];
+		const long long tile = h->tile;
 		if (tile >= B.ntiles) break;
-		const int job = sm->h_job, dl = sm->h_dl, i0 = sm->h_i0, B0 = i0 - HL;
-		const uint32_t shift = sm->h_shift;
-		const char *seq = B.buf + sm->h_seq_off;
+		const int job = h->job, dl = h->dl, i0 = h->i0, B0 = i0 - HL;
+		const uint32_t shift = h->shift;
+		const char *seq = B.buf + h->seq_off;
+		const bool go = dl >= full_run; // a shorter job cannot emit (the 15-base cropped job of mm_sketch2 on a 150 bp read)
+		if (pend && wid == 0) lookback_issue();
 		const int s0 = tid * 8, j0 = B0 + s0;
 		uint32_t zbits = 0, emit = 0, okbits = 0;
 		uint64_t key[8];
 		int cnt = 0;
-		if (dl >= full_run) {
+		uint32_t nsp = 0;
+		if (go) {
 			// ---- phase 0: stage the bytes with 16-byte loads (the tail bytewise) ----
-			const int staged = sm->h_staged, raw_lo = sm->h_raw_lo, safe = sm->h_safe;
+			const int staged = h->staged, raw_lo = h->raw_lo, safe = h->safe;
 			if (staged) {
-				const int nbytes = sm->h_nbytes, nvec = nbytes >> 4;
+				const int nbytes = h->nbytes, nvec = nbytes >> 4;
 				const uint4 *gsrc = (const uint4 *)(seq + raw_lo);
 				uint4 *sdst = (uint4 *)sm->raw;
 				for (int i = tid; i < nvec; i += THREADS) sdst[i] = gsrc[i];
@@ -668,14 +694,17 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 					}
 				}
 			}
-			const uint32_t code = acc & 0xffffu, nsp = acc >> 16;
+			const uint32_t code = acc & 0xffffu;
+			nsp = acc >> 16;
 			F2h[tid] = (uint16_t)code;
 			{ // the same 8 codes in reverse position order: bit reversal, then the two bits of every code swapped back
 				const uint32_t br = (uint32_t)(brev64((uint64_t)code) >> 48);
 				R2h[THREADS - 1 - tid] = (uint16_t)(((br & 0x5555u) << 1) | ((br >> 1) & 0x5555u));
 			}
 			sm->NB[2 + tid] = (uint16_t)nsp;
-			sync_block();
+		}
+		sync_block(); // codes and N flags of the tile
+		if (go) {
 			// ---- last N position before the chunk (slot -1 counts as N); only runs up to w+k-1 matter ----
 			int L0 = s0 - full_run - 1;
 			if (L0 < -1) L0 = -1;
@@ -753,7 +782,7 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 				const int elo = HL - s0, ehi = imin(HL + S.TP, dl - B0) - s0; // p in [elo, ehi)
 				cand = sk_mask_from(elo) & ~sk_mask_from(ehi) & okbits;
 			}
-			if (pend) flush(); // the previous tile's records leave SUF | PREM before phase 3 writes there
+			if (pend && wid == 0) lookback_finish(); // its offset travels with the next barrier
 			if (w >= 9) {
 				// ---- phase 3: minimum of every full window ending at e = s0+p (0 = no full window ends here).  The window starts
 				// at a = e-(w-1) in chunk tid-dt, slot q (the same dt, q for every thread): own prefix minimum, whole chunks in
@@ -767,6 +796,7 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 					for (int p = 0; p < 8; ++p) pr = sk_min64(pr, key[p]), pre[p] = pr;
 				}
 				sync_block();
+				if (pend) copy_out(), pend = 0;
 				// whole chunks between the window's first chunk and the thread's own: tid-dt+1 .. tid-1 with dt = D for the upper
 				// positions of the chunk and D + 1 for the lower ones -- two minima per thread, not one loop per position
 				const int D = -((7 - wm1) >> 3);
@@ -816,6 +846,7 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 #pragma unroll
 				for (int p = 0; p < 8; ++p) sm->SUF[p * THREADS + tid] = key[p];
 				sync_block();
+				if (pend) copy_out(), pend = 0;
 #pragma unroll
 				for (int p = 0; p < 8; ++p) {
 					const int sp = s0 + p;
@@ -839,7 +870,11 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 					}
 				}
 			}
-		} // dl >= full_run
+		} else if (pend) { // a job too short to emit: the pending tile leaves here
+			if (wid == 0) lookback_finish();
+			sync_block();
+			copy_out(), pend = 0;
+		}
 		// ---- block exclusive scan of cnt ----
 		int inc = cnt;
 		for (int d = 1; d < 32; d <<= 1) {
@@ -855,7 +890,7 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 			total += c;
 		}
 		const int local = wbase + inc - cnt;
-		const uint64_t yhi = (uint64_t)sm->h_rid << 32;
+		const uint64_t yhi = (uint64_t)h->rid << 32;
 		// record o of the thread: x = hash64 << 8 | k (the marker bit 56 leaves at the top), y = rid << 32 | position << 1 | strand
 		auto put = [&](uint64_t *dst, int p) {
 			const uint32_t j = (uint32_t)(j0 + p); // >= 0: a k-mer
@@ -883,27 +918,43 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 						++o;
 					}
 			}
-		} else {
-			if (pend) flush(); // (tiles of jobs too short to emit skip the phases above)
-			if (emit) {
-				int o = 0;
-#pragma unroll
-				for (int p = 0; p < 8; ++p)
-					if (emit >> p & 1) put(sm->SUF + 2 * (local + o), p), ++o;
-			}
-			if (tid == 0) { // the tile's count: an aggregate for the look-backs of later tiles (tile 0: already its inclusive prefix)
+		} else { // publish the count; park the records until the look-back inside the next tile has their offset
+			if (tid == 0) { // an aggregate for the look-backs of later tiles (tile 0: already its inclusive prefix)
 				st_volatile(&B.status[tile], ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)total);
 				fence();
 			}
 			pend = 1, pend_tile = tile, pend_total = total, pend_job = job, pend_first = i0 == 0;
-			if (!B.defer) {
+			if (total <= SketchSmem3<THREADS>::PARK) {
+				if (emit) {
+					int o = 0;
+#pragma unroll
+					for (int p = 0; p < 8; ++p)
+						if (emit >> p & 1) put((uint64_t *)sm->park + 2 * (local + o), p), ++o;
+				}
+			} else { // too many records to park: wait for the offset, write from registers
+				if (wid == 0) lookback_issue(), lookback_finish();
 				sync_block();
-				flush();
+				if (emit) {
+					const long long obase = sm->excl + local;
+					int o = 0;
+#pragma unroll
+					for (int p = 0; p < 8; ++p)
+						if (emit >> p & 1) {
+							if (obase + o < B.out_cap) put(B.out + 2 * (obase + o), p);
+							++o;
+						}
+				}
+				pend = 0;
 			}
 		}
-		sync_block(); // shared memory (and the header) is reused by the next tile
+		cur ^= 1;
+		if (wid == 0) make_header(&sm->hdr[cur]);
 	}
-	if (pend) flush();
+	if (pend) { // the block's last tile
+		if (wid == 0) lookback_issue(), lookback_finish();
+		sync_block();
+		copy_out();
+	}
 }
 
 } // namespace gd

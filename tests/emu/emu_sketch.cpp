@@ -7,8 +7,8 @@
 
 using namespace gd;
 
-static int g_ver = 3, g_defer = 1; // tile body: 3 = sketch_tile_body3 (the product default; +4: look-back not deferred), 2 = sketch_tile_body
-extern "C" void emu_sketch_version(int v) { g_ver = v & 3, g_defer = !(v & 4); }
+static int g_ver = 3; // tile body: 3 = sketch_tile_body3 (the product default), 2 = sketch_tile_body
+extern "C" void emu_sketch_version(int v) { g_ver = v; }
 
 template <int THREADS>
 static void run_tiles(const SketchParams &S, SketchBatch &B, int grid)
@@ -53,7 +53,6 @@ extern "C" long emu_sketch_jobs(int njobs, const int64_t *seq_off, const int32_t
 	SketchBatch B;
 	memset(&B, 0, sizeof(B));
 	B.njobs = njobs, B.ntiles = tb[njobs], B.jobs = jobs.data(), B.tile_base = small ? nullptr : tb.data();
-	B.defer = g_defer;
 	B.buf = buf, B.status = status.data(), B.ticket = &ticket, B.out_off = out_off, B.out = out, B.out_cap = out_cap;
 	if (small) run_tiles<32>(S, B, grid);
 	else run_tiles<256>(S, B, grid);

@@ -198,8 +198,9 @@ static int make_params(gd_ctx *ctx, int w, int k, const char *Z, int W, SketchPa
 // d_out_cnt[j]; the caller sized d_out for njobs * fixed_stride records.
 static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const SketchJob *d_jobs, int64_t max_dl,
                               int64_t pos_total, const char *d_buf, int64_t *d_out_off, uint64_t *d_out, int64_t out_cap,
-                              int64_t fixed_stride = 0, int32_t *d_out_cnt = nullptr)
-{
+                              int64_t fixed_stride = 0, int32_t *d_out_cnt = nullptr, int pack_group = 0, int64_t pack_slots = 0)
+{ // pack_group / pack_slots (fixed-stride mode): the jobs come in groups of pack_group (a read: one job per shift and the cropped
+  // job) that need at most pack_slots tile slots (sparsified positions of the jobs that can emit, one N behind each)
 	cudaStream_t s = ctx->stream;
 	int rc;
 	SketchBatch B;
@@ -233,6 +234,22 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 		if ((rc = gd_exclusive_scan(ctx, njobs, tb, tb, ctx->sk_out2))) return rc;
 		B.tile_base = tb, B.ntiles = 0;
 	}
+	static const int sk_ver = getenv("GDIET_SK_V") ? atoi(getenv("GDIET_SK_V")) : 3;
+	static const int sk_pack = getenv("GDIET_SK_PACK") ? atoi(getenv("GDIET_SK_PACK")) : 1;   // several reads per tile (A/B switch)
+	static const int sk_early = getenv("GDIET_SK_EARLY") ? atoi(getenv("GDIET_SK_EARLY")) : 1; // ticket drawn ahead (A/B switch)
+	B.early_ticket = sk_early;
+	int pack_threads = 0;
+	if (small && fixed_stride > 0 && sk_ver != 2 && sk_pack && pack_group > 0 && pack_group <= 32 && pack_slots > 0) {
+		// whole groups per tile: the tile shape (one, two or four warps) that leaves the fewest slots empty
+		double best = 0.30; // one job per one-warp tile fills about this much with 150 bp reads
+		for (int T = 32; T <= 128; T *= 2) {
+			int64_t R = ((int64_t)T * 8 - (S.w - 1)) / pack_slots;
+			if (R * pack_group > 32) R = 32 / pack_group;
+			const double util = (double)(R * pack_slots) / (T * 8);
+			if (R >= 1 && util > best + 0.05) best = util, pack_threads = T, B.pack_jobs = (int32_t)(R * pack_group);
+		}
+		if (pack_threads) B.ntiles = (njobs + B.pack_jobs - 1) / B.pack_jobs;
+	}
 	if ((rc = gd_reserve(ctx, ctx->sk_state, (size_t)ntiles_bound * 8 + 64))) return rc;
 	GD_CUDA_OK(ctx, cudaMemsetAsync(ctx->sk_state.p, 0, (size_t)ntiles_bound * 8 + 64, s));
 	B.status = (unsigned long long *)ctx->sk_state.p;
@@ -241,13 +258,14 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 		int occ = 0;
 		if (smem > 48 * 1024) GD_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		GD_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-		int blocks = (int)std::min<int64_t>(ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));
+		int blocks = (int)std::min<int64_t>(B.pack_jobs > 0 ? B.ntiles : ntiles_bound, (int64_t)ctx->sms * std::max(occ, 1));
 		GdKernelTimer tm(ctx, &ctx->tm_sketch);
 		kern<<<std::max(blocks, 1), threads, smem, s>>>(S, B);
 		return GD_OK;
 	};
-	static const int sk_ver = getenv("GDIET_SK_V") ? atoi(getenv("GDIET_SK_V")) : 3;
-	if (sk_ver != 2) {
+	if (pack_threads == 64) rc = launch(gd_sketch_tile3_kernel<64>, 64, sizeof(SketchSmem3<64>));
+	else if (pack_threads == 128) rc = launch(gd_sketch_tile3_kernel<128>, 128, sizeof(SketchSmem3<128>));
+	else if (sk_ver != 2) {
 		if (small) rc = launch(gd_sketch_tile3_kernel<32>, 32, sizeof(SketchSmem3<32>));
 		else if (big_threads == 64) rc = launch(gd_sketch_tile3_kernel<64>, 64, sizeof(SketchSmem3<64>));
 		else if (big_threads == 128) rc = launch(gd_sketch_tile3_kernel<128>, 128, sizeof(SketchSmem3<128>));
@@ -525,8 +543,11 @@ int gd_sketch_reads_device_raw(gd_ctx *ctx, int n, const int64_t *d_off, const i
 	if ((rc = gd_reserve(ctx, ctx->sk_out, (size_t)worst * 16 + 64))) return rc;
 	gd_sketch_read_jobs_kernel<<<(n + 255) / 256, 256, 0, s>>>(S, n, d_off, d_len, W, crop, max_seeds, (SketchJob *)ctx->sk_jobs.p);
 	ctx->stat_launches++;
+	// slots a read needs in a packed tile: its W full-length jobs, and the cropped job if that one is long enough to emit
+	const int64_t crop_dl = crop ? (int64_t)((double)max_seeds * max_len) / S.W * S.ones + S.ones : 0;
+	const int64_t read_slots = (int64_t)W * (per_job + 1) + (crop && crop_dl >= S.w + S.k - 1 ? crop_dl + 1 : 0);
 	rc = gd_sketch_run_jobs(ctx, S, njobs, (const SketchJob *)ctx->sk_jobs.p, per_job, worst, d_buf, (int64_t *)ctx->sk_out_off.p,
-	                        (uint64_t *)ctx->sk_out.p, worst, fixed ? per_job : 0, d_cnt);
+	                        (uint64_t *)ctx->sk_out.p, worst, fixed ? per_job : 0, d_cnt, JW, read_slots);
 	if (rc) return rc;
 	const size_t nq = (size_t)n * W;
 	const size_t need = (nq + 1) * 8 * 2 + nq * 4 * 2 + (size_t)(n + 1) * 8 + 128; // c3 | c2 | ret | cnt2 | per-read offsets (host API)

@@ -52,6 +52,9 @@ struct SketchBatch {
 	// and its count to out_cnt[j].  No tile depends on another one then: no ticket, no look-back.
 	int64_t fixed_stride;      // 0 = dense output in job order (decoupled look-back)
 	int32_t *out_cnt;          // [njobs], fixed-stride mode
+	// v3 tile body only:
+	int32_t pack_jobs;         // > 0 (fixed-stride mode): a tile holds this many whole jobs (<= 32), one N slot between them
+	int32_t early_ticket;      // dense mode: the next tile's ticket is drawn before the emission phase of the current one
 };
 
 GD_DEV uint64_t sk_hash64(uint64_t key, uint64_t mask)
@@ -457,6 +460,11 @@ template <int THREADS> struct SketchSmem3 {
 	} hdr[2];
 	// the job of the block's previous tile: its tile range and record (most tiles of a contig stay in the same job)
 	long long c_lo, c_hi;
+	// packed tiles: the jobs of the tile -- first slot, slot behind the last position + its N, sparsified length, records in
+	// lower slots
+	long long pk_seq[32];
+	int32_t pk_base[33], pk_end[32], pk_dl[32], pk_R[33], pk_n;
+	uint32_t pk_shift[32], pk_rid[32];
 	int32_t c_job;
 	SketchJob c_J;
 	uint8_t ones_loc[64];
@@ -507,7 +515,12 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 	for (int i = tid; i < SketchSmem3<THREADS>::F2W; i += THREADS) sm->F2[i] = 0;
 	for (int i = tid; i < SketchSmem3<THREADS>::R2W; i += THREADS) sm->R2[i] = 0;
 	if (tid < 4) sm->NB[tid < 2 ? tid : NP / 8 + tid] = 0;
-	for (int i = tid; i < 64; i += THREADS) sm->ones_loc[i] = S.ones_loc[i];
+	if (tid == 0) { // with constant indices the kernel parameter stays in the constant bank (a run-time index makes a local copy of S)
+		const uint32_t *src = (const uint32_t *)S.ones_loc;
+		uint32_t *dst = (uint32_t *)sm->ones_loc;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) dst[i] = src[i];
+	}
 	for (int c = tid; c < 256; c += THREADS) sm->lut[c] = (uint32_t)sk_nt4((unsigned)c) < 4u ? (uint32_t)sk_nt4((unsigned)c) : 0x10000u;
 	if (tid == 0) sm->c_lo = 0, sm->c_hi = 0, sm->c_job = -1;
 	const bool fixed = B.fixed_stride > 0;
@@ -518,13 +531,34 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 	// of the resident warps idle: with grid a multiple of the jobs per read, the same blocks got all the 15-base cropped jobs.)
 	// The header of a tile -- ticket, tile -> job, byte range to stage -- is made by warp 0 right after it parked the records
 	// of the previous tile, so the barrier that ends a tile also publishes the next header.
+	int tk = -1; // lane 0 of warp 0: a ticket drawn ahead (early_ticket)
 	auto make_header = [&](typename SketchSmem3<THREADS>::Hdr *h) { // warp 0
 		long long tile = 0;
-		if (lane == 0) tile = (long long)atomic_add(B.ticket, 1);
+		if (lane == 0) tile = tk >= 0 ? (long long)tk : (long long)atomic_add(B.ticket, 1), tk = -1;
 		tile = (long long)((uint64_t)shfl_idx(0xffffffffu, (uint32_t)tile, 0, 32) |
 		                   (uint64_t)shfl_idx(0xffffffffu, (uint32_t)((uint64_t)tile >> 32), 0, 32) << 32);
 		if (lane == 0) h->tile = tile;
 		if (tile >= B.ntiles) return;
+		if (B.pack_jobs > 0) { // jobs tile * G .. : lane g takes job g; a job that cannot emit gets no slots
+			const long long jfirst = tile * B.pack_jobs;
+			const int n = (int)(B.njobs - jfirst < (long long)B.pack_jobs ? B.njobs - jfirst : (long long)B.pack_jobs);
+			SketchJob J;
+			J.seq_off = 0, J.len = 0, J.shift = 0, J.rid = 0, J.dl = 0;
+			if (lane < n) J = B.jobs[jfirst + lane];
+			const int seg = lane < n && J.dl >= full_run ? J.dl + 1 : 0;
+			int inc = seg;
+			for (int d = 1; d < 32; d <<= 1) {
+				const int o = (int)shfl_up(0xffffffffu, (uint32_t)inc, d, 32);
+				if (lane >= d) inc += o;
+			}
+			if (lane < n) {
+				sm->pk_seq[lane] = J.seq_off, sm->pk_base[lane] = inc - seg, sm->pk_end[lane] = inc, sm->pk_dl[lane] = seg ? J.dl : 0;
+				sm->pk_shift[lane] = (uint32_t)J.shift, sm->pk_rid[lane] = J.rid;
+				if (lane == n - 1) sm->pk_base[n] = inc, sm->pk_n = n;
+			}
+			if (lane == 0) h->job = (int)jfirst, h->i0 = 0, h->dl = full_run, h->shift = 0, h->rid = 0, h->seq_off = 0, h->staged = 0, h->raw_lo = 0, h->nbytes = 0, h->safe = 0;
+			return;
+		}
 		int job;
 		long long chunk;
 		SketchJob J;
@@ -559,7 +593,11 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 			const int jlo = B0 > 0 ? B0 : 0, jhi = (B0 + NP < dl ? B0 + NP : dl) - 1;
 			int staged = 0, raw_lo = 0, nbytes = 0, safe = 0;
 			if (dl >= full_run && jhi >= jlo) {
-				const uint32_t rlo = sk_real((uint32_t)jlo, shift, S), rhi = sk_real((uint32_t)jhi, shift, S);
+				auto real_of = [&](uint32_t i) { // get_real_location, sketch.c:20-23
+					const uint32_t qd = i / (uint32_t)S.ones, rm = i - qd * (uint32_t)S.ones;
+					return qd * (uint32_t)S.W + sm->ones_loc[rm] + shift;
+				};
+				const uint32_t rlo = real_of((uint32_t)jlo), rhi = real_of((uint32_t)jhi);
 				const uint32_t lead = (uint32_t)((unsigned long long)(B.buf + J.seq_off + rlo) & 15);
 				safe = (int)rlo;
 				nbytes = (int)(rhi - rlo + 1 + lead);
@@ -619,13 +657,15 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 	};
 	sync_block();
 	int cur = 0;
-	if (wid == 0) make_header(&sm->hdr[0]);
 	for (;;) {
+		if (B.pack_jobs > 0 && THREADS > 32) sync_block(); // the job table of the previous tile is still being read by the other warps
+		if (wid == 0) make_header(&sm->hdr[cur]); // right behind warp 0's share of the previous tile's records
 		sync_block(); // header of this tile; the previous tile's parked records
 		const typename SketchSmem3<THREADS>::Hdr *const h = &sm->hdr[cur];
 		const long long tile = h->tile;
 		if (tile >= B.ntiles) break;
-		const int job = h->job, dl = h->dl, i0 = h->i0, B0 = i0 - HL;
+		const bool packed = B.pack_jobs > 0; // several whole jobs per tile: slot 0 is the first position of the first job (no halo)
+		const int job = h->job, dl = h->dl, i0 = h->i0, B0 = packed ? 0 : i0 - HL;
 		const uint32_t shift = h->shift;
 		const char *seq = B.buf + h->seq_off;
 		const bool go = dl >= full_run; // a shorter job cannot emit (the 15-base cropped job of mm_sketch2 on a 150 bp read)
@@ -658,7 +698,30 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 				}
 				uint32_t base = qd * (uint32_t)S.W + shift;
 				const uint32_t loc0 = sm->ones_loc[0];
-				if (staged) {
+				if (packed) { // the slots of job g are [pk_base[g], pk_end[g]): dl positions and one N; bytes straight from global memory
+					const int n = sm->pk_n;
+					int g = 0;
+#pragma unroll
+					for (int p = 0; p < 8; ++p) {
+						const int sl = s0 + p;
+#pragma unroll 1
+						while (g < n && sl >= sm->pk_end[g]) ++g;
+						uint32_t v = 0x10000u;
+						if (g < n) {
+							const uint32_t j = (uint32_t)(sl - sm->pk_base[g]);
+							if ((int)j < sm->pk_dl[g]) {
+								uint32_t real;
+								if (ones1) real = j * (uint32_t)S.W + loc0 + sm->pk_shift[g];
+								else {
+									const uint32_t q = j / (uint32_t)S.ones;
+									real = q * (uint32_t)S.W + sm->ones_loc[j - q * (uint32_t)S.ones] + sm->pk_shift[g];
+								}
+								v = sm->lut[(uint8_t)B.buf[sm->pk_seq[g] + real]];
+							}
+						}
+						acc += v << (2 * p);
+					}
+				} else if (staged) {
 					const uint8_t *rs = (const uint8_t *)sm->raw;
 					if (all_in && ones1) {
 						uint32_t idx = base + loc0 - (uint32_t)raw_lo;
@@ -779,7 +842,7 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 			// emit candidates: inside the tile's emit range and the sequence, and a k-mer
 			uint32_t cand;
 			{
-				const int elo = HL - s0, ehi = imin(HL + S.TP, dl - B0) - s0; // p in [elo, ehi)
+				const int elo = (packed ? 0 : HL) - s0, ehi = (packed ? NP - wm1 : imin(HL + S.TP, dl - B0)) - s0; // p in [elo, ehi)
 				cand = sk_mask_from(elo) & ~sk_mask_from(ehi) & okbits;
 			}
 			if (pend && wid == 0) lookback_finish(); // its offset travels with the next barrier
@@ -825,6 +888,7 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 					for (int p = 7; p >= 0; --p) sx = sk_max64(sx, M[p]), sufm[p] = sx;
 				}
 				sync_block();
+				if (B.early_ticket && tid == 0) tk = atomic_add(B.ticket, 1); // its latency hides behind the emission phase
 				// whole chunks between the thread's own and the last window's last chunk: tid+1 .. tid+dt-1, dt = E or E + 1
 				const int E = wm1 >> 3;
 				uint64_t mxA = 0, mxB = 0;
@@ -890,65 +954,79 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 			total += c;
 		}
 		const int local = wbase + inc - cnt;
-		const uint64_t yhi = (uint64_t)h->rid << 32;
-		// record o of the thread: x = hash64 << 8 | k (the marker bit 56 leaves at the top), y = rid << 32 | position << 1 | strand
-		auto put = [&](uint64_t *dst, int p) {
-			const uint32_t j = (uint32_t)(j0 + p); // >= 0: a k-mer
+		// a record: x = hash64 << 8 | k (the marker bit 56 leaves at the top), y = rid << 32 | position << 1 | strand
+		auto put_at = [&](uint64_t *dst, int p, uint32_t j, uint32_t sh, uint32_t rid) { // j: sparsified position in its job
 			uint32_t real;
-			if (ones1) real = j * (uint32_t)S.W + sm->ones_loc[0] + shift;
+			if (ones1) real = j * (uint32_t)S.W + sm->ones_loc[0] + sh;
 			else {
 				const uint32_t qd = j / (uint32_t)S.ones, rm = j - qd * (uint32_t)S.ones;
-				real = qd * (uint32_t)S.W + sm->ones_loc[rm] + shift;
+				real = qd * (uint32_t)S.W + sm->ones_loc[rm] + sh;
 			}
 			dst[0] = key[p] << 8 | (uint64_t)k;
-			dst[1] = yhi | (uint64_t)real << 1 | (uint64_t)(zbits >> p & 1);
+			dst[1] = (uint64_t)rid << 32 | (uint64_t)real << 1 | (uint64_t)(zbits >> p & 1);
 		};
-		if (fixed) { // the job's own slot of fixed_stride records; nothing orders the tiles
+		// where the records go: 0 = the job's own slot of fixed_stride records, 1 = the slots of the tile's jobs (packed tile),
+		// 2 = the parking area, 3 = the dense output (after waiting for the offset)
+		int mode;
+		long long obase = 0;
+		if (packed) {
+			// records of job g = ranks [R_g, R_g+1) of the tile's records, R_g = records in slots below pk_base[g]: the thread
+			// whose chunk holds that slot knows it
+			const int n = sm->pk_n;
+			int g = 0;
+#pragma unroll 1
+			while (g <= n && sm->pk_base[g] < s0) ++g;
+#pragma unroll 1
+			for (; g <= n && sm->pk_base[g] < s0 + 8; ++g) sm->pk_R[g] = local + popc(emit & ((1u << (sm->pk_base[g] - s0)) - 1u));
+			sync_block();
+			if (tid < n) {
+				const long long jb = (long long)job + tid;
+				B.out_off[jb] = jb * B.fixed_stride, B.out_cnt[jb] = sm->pk_R[tid + 1] - sm->pk_R[tid];
+				if (jb == B.njobs - 1) B.out_off[B.njobs] = (long long)B.njobs * B.fixed_stride;
+			}
+			mode = 1;
+		} else if (fixed) { // nothing orders the tiles
 			if (tid == 0) {
 				B.out_off[job] = (long long)job * B.fixed_stride, B.out_cnt[job] = total;
 				if (tile == B.ntiles - 1) B.out_off[B.njobs] = (long long)B.njobs * B.fixed_stride;
 			}
-			if (emit) {
-				const long long obase = (long long)job * B.fixed_stride + local;
-				int o = 0;
-#pragma unroll
-				for (int p = 0; p < 8; ++p)
-					if (emit >> p & 1) {
-						if (local + o < B.fixed_stride) put(B.out + 2 * (obase + o), p);
-						++o;
-					}
-			}
+			mode = 0, obase = (long long)job * B.fixed_stride + local;
 		} else { // publish the count; park the records until the look-back inside the next tile has their offset
 			if (tid == 0) { // an aggregate for the look-backs of later tiles (tile 0: already its inclusive prefix)
 				st_volatile(&B.status[tile], ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)total);
 				fence();
 			}
 			pend = 1, pend_tile = tile, pend_total = total, pend_job = job, pend_first = i0 == 0;
-			if (total <= SketchSmem3<THREADS>::PARK) {
-				if (emit) {
-					int o = 0;
-#pragma unroll
-					for (int p = 0; p < 8; ++p)
-						if (emit >> p & 1) put((uint64_t *)sm->park + 2 * (local + o), p), ++o;
-				}
-			} else { // too many records to park: wait for the offset, write from registers
+			if (total <= SketchSmem3<THREADS>::PARK) mode = 2;
+			else { // too many records to park: wait for the offset, write from registers
 				if (wid == 0) lookback_issue(), lookback_finish();
 				sync_block();
-				if (emit) {
-					const long long obase = sm->excl + local;
-					int o = 0;
-#pragma unroll
-					for (int p = 0; p < 8; ++p)
-						if (emit >> p & 1) {
-							if (obase + o < B.out_cap) put(B.out + 2 * (obase + o), p);
-							++o;
-						}
-				}
-				pend = 0;
+				mode = 3, obase = sm->excl + local, pend = 0;
 			}
 		}
+		if (emit) {
+			int o = 0, g = 0;
+#pragma unroll
+			for (int p = 0; p < 8; ++p)
+				if (emit >> p & 1) {
+					uint64_t *dst;
+					bool ok = true;
+					uint32_t jj = (uint32_t)(j0 + p), sh = shift, rid = h->rid; // j0 + p >= 0: a k-mer
+					if (mode == 1) {
+						const int sl = s0 + p;
+#pragma unroll 1
+						while (sl >= sm->pk_end[g]) ++g; // a record's slot lies inside a job
+						const int r = local + o - sm->pk_R[g];
+						ok = r < B.fixed_stride, dst = B.out + 2 * (((long long)job + g) * B.fixed_stride + r);
+						jj = (uint32_t)(sl - sm->pk_base[g]), sh = sm->pk_shift[g], rid = sm->pk_rid[g];
+					} else if (mode == 0) ok = local + o < B.fixed_stride, dst = B.out + 2 * (obase + o);
+					else if (mode == 2) dst = (uint64_t *)sm->park + 2 * (local + o);
+					else ok = obase + o < B.out_cap, dst = B.out + 2 * (obase + o);
+					if (ok) put_at(dst, p, jj, sh, rid);
+					++o;
+				}
+		}
 		cur ^= 1;
-		if (wid == 0) make_header(&sm->hdr[cur]);
 	}
 	if (pend) { // the block's last tile
 		if (wid == 0) lookback_issue(), lookback_finish();

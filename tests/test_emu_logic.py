@@ -193,3 +193,38 @@ def test_emu_sketch_geometry(emu, oracle, ver):
                     assert np.array_equal(exp, got[i]), (ver, k, w, Z, small, i)
     finally:
         emu.lib.emu_sketch_version(3)
+
+
+def test_emu_sketch_packed_tiles(emu, oracle):
+    """Several whole jobs per tile (the short-read configuration: fixed-stride output, one N slot between the jobs): every job's
+    list equals mm_sketch3 of that job alone -- jobs of mixed lengths, jobs too short to emit (they get no slots), Ns next to
+    the seams, one / two / four warps per tile, a last tile that is not full."""
+    rng = np.random.default_rng(23)
+    cases = [(21, 11, "10", 6, 64, 150), (21, 11, "10", 3, 32, 150), (15, 10, "10", 12, 128, 150), (19, 9, "110", 4, 64, 120),
+             (12, 5, "10", 6, 32, 60), (28, 17, "1", 2, 64, 100), (17, 12, "101", 5, 128, 250)]
+    for k, w, Z, pack, threads, maxlen in cases:
+        W, ones = len(Z), Z.count("1")
+        seg = maxlen // W * ones + ones + 1
+        assert pack * seg <= threads * 8 - (w - 1), (pack, seg)
+        seqs, shifts = [], []
+        for i in range(2 * pack + 3):
+            n = int(rng.integers(max(W, 8), maxlen + 1)) if i % 4 else maxlen
+            if i % 5 == 3:
+                n = int(rng.integers(W, 20))  # cannot emit
+            c = rng.integers(0, 4, n)
+            if i % 3 == 1 and k >= 12:
+                c[[0, n - 1]] = 4
+                a = int(rng.integers(0, n))
+                c[a:a + int(rng.integers(1, 6))] = 4
+            seqs.append(bytes(synth.ACGTN[c]))
+            shifts.append(int(rng.integers(0, W)))
+        for early in (0, 1):
+            got = emu.sketch_packed(seqs, shifts, list(range(len(seqs))), w, k, Z, pack, threads, early)
+            for i, (sq, sh) in enumerate(zip(seqs, shifts)):
+                exp, _ = oracle.mm_sketch3(sq, w, k, i, Z, sh, 0)
+                assert np.array_equal(exp, got[i]), (k, w, Z, pack, threads, early, i)
+    # one job per tile through the same entry (tickets in fixed-stride mode)
+    got = emu.sketch_packed(seqs, shifts, list(range(len(seqs))), w, k, Z, 0, 32)
+    for i, (sq, sh) in enumerate(zip(seqs, shifts)):
+        exp, _ = oracle.mm_sketch3(sq, w, k, i, Z, sh, 0)
+        assert np.array_equal(exp, got[i]), i

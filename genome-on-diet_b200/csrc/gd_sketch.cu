@@ -22,12 +22,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gd_sketch_tile_kernel
 	sketch_tile_body<THREADS>(S, B, (SketchSmem<THREADS> *)gd_sk_smem);
 }
 // design v3 of the tile body (gd_sketch.cuh); the default.  GDIET_SK_V=2 selects the kernel above (A/B measurements).
-template <int THREADS>
+template <int THREADS, bool PACKED>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gd_sketch_tile3_kernel(const SketchParams S, SketchBatch B)
 {
 	extern __shared__ __align__(16) uint8_t gd_sk_smem[];
 	if (B.tile_base) B.ntiles = B.tile_base[B.njobs];
-	sketch_tile_body3<THREADS>(S, B, (SketchSmem3<THREADS> *)gd_sk_smem);
+	sketch_tile_body3<THREADS, PACKED>(S, B, (SketchSmem3<THREADS> *)gd_sk_smem);
 }
 
 // jobs for index-build sketching: one per sequence, shift 0
@@ -236,8 +236,6 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 	}
 	static const int sk_ver = getenv("GDIET_SK_V") ? atoi(getenv("GDIET_SK_V")) : 3;
 	static const int sk_pack = getenv("GDIET_SK_PACK") ? atoi(getenv("GDIET_SK_PACK")) : 1;   // several reads per tile (A/B switch)
-	static const int sk_early = getenv("GDIET_SK_EARLY") ? atoi(getenv("GDIET_SK_EARLY")) : 1; // ticket drawn ahead (A/B switch)
-	B.early_ticket = sk_early;
 	int pack_threads = 0;
 	if (small && fixed_stride > 0 && sk_ver != 2 && sk_pack && pack_group > 0 && pack_group <= 32 && pack_slots > 0) {
 		// whole groups per tile: the tile shape (one, two or four warps) that leaves the fewest slots empty
@@ -263,13 +261,14 @@ static int gd_sketch_run_jobs(gd_ctx *ctx, SketchParams &S, int njobs, const Ske
 		kern<<<std::max(blocks, 1), threads, smem, s>>>(S, B);
 		return GD_OK;
 	};
-	if (pack_threads == 64) rc = launch(gd_sketch_tile3_kernel<64>, 64, sizeof(SketchSmem3<64>));
-	else if (pack_threads == 128) rc = launch(gd_sketch_tile3_kernel<128>, 128, sizeof(SketchSmem3<128>));
+	if (pack_threads == 32) rc = launch(gd_sketch_tile3_kernel<32, true>, 32, sizeof(SketchSmem3<32>));
+	else if (pack_threads == 64) rc = launch(gd_sketch_tile3_kernel<64, true>, 64, sizeof(SketchSmem3<64>));
+	else if (pack_threads == 128) rc = launch(gd_sketch_tile3_kernel<128, true>, 128, sizeof(SketchSmem3<128>));
 	else if (sk_ver != 2) {
-		if (small) rc = launch(gd_sketch_tile3_kernel<32>, 32, sizeof(SketchSmem3<32>));
-		else if (big_threads == 64) rc = launch(gd_sketch_tile3_kernel<64>, 64, sizeof(SketchSmem3<64>));
-		else if (big_threads == 128) rc = launch(gd_sketch_tile3_kernel<128>, 128, sizeof(SketchSmem3<128>));
-		else rc = launch(gd_sketch_tile3_kernel<256>, 256, sizeof(SketchSmem3<256>));
+		if (small) rc = launch(gd_sketch_tile3_kernel<32, false>, 32, sizeof(SketchSmem3<32>));
+		else if (big_threads == 64) rc = launch(gd_sketch_tile3_kernel<64, false>, 64, sizeof(SketchSmem3<64>));
+		else if (big_threads == 128) rc = launch(gd_sketch_tile3_kernel<128, false>, 128, sizeof(SketchSmem3<128>));
+		else rc = launch(gd_sketch_tile3_kernel<256, false>, 256, sizeof(SketchSmem3<256>));
 	} else if (small) rc = launch(gd_sketch_tile_kernel<32>, 32, sizeof(SketchSmem<32>));
 	else if (big_threads == 64) rc = launch(gd_sketch_tile_kernel<64>, 64, sizeof(SketchSmem<64>));
 	else if (big_threads == 128) rc = launch(gd_sketch_tile_kernel<128>, 128, sizeof(SketchSmem<128>));

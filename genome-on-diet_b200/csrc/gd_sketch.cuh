@@ -54,7 +54,6 @@ struct SketchBatch {
 	int32_t *out_cnt;          // [njobs], fixed-stride mode
 	// v3 tile body only:
 	int32_t pack_jobs;         // > 0 (fixed-stride mode): a tile holds this many whole jobs (<= 32), one N slot between them
-	int32_t early_ticket;      // dense mode: the next tile's ticket is drawn before the emission phase of the current one
 };
 
 GD_DEV uint64_t sk_hash64(uint64_t key, uint64_t mask)
@@ -501,7 +500,7 @@ GD_DEV uint32_t sk_hash_32(uint32_t key, const uint32_t m)
 	return key;
 }
 
-template <int THREADS>
+template <int THREADS, bool PACKED>
 GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, SketchSmem3<THREADS> *sm)
 {
 	const int NP = THREADS * 8;
@@ -527,19 +526,18 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 	// Tiles are handed out in order by a global ticket, drawn when the block is about to start the tile: every tile's
 	// predecessors are then held by blocks that are already computing them.  (Drawing the ticket one tile ahead was measured
 	// on a B200 and is twice as slow: a block that is late holds a low ticket hostage and every later tile spins on it in the
-	// look-back -- 850 probes per tile.  A static tile = block + round * grid assignment of the fixed-stride mode left a third
+	// look-back -- 850 probes per tile; drawing it just one phase ahead, with the look-back deferred: 192 against 198 Gbases/s.  A static tile = block + round * grid assignment of the fixed-stride mode left a third
 	// of the resident warps idle: with grid a multiple of the jobs per read, the same blocks got all the 15-base cropped jobs.)
 	// The header of a tile -- ticket, tile -> job, byte range to stage -- is made by warp 0 right after it parked the records
 	// of the previous tile, so the barrier that ends a tile also publishes the next header.
-	int tk = -1; // lane 0 of warp 0: a ticket drawn ahead (early_ticket)
 	auto make_header = [&](typename SketchSmem3<THREADS>::Hdr *h) { // warp 0
 		long long tile = 0;
-		if (lane == 0) tile = tk >= 0 ? (long long)tk : (long long)atomic_add(B.ticket, 1), tk = -1;
+		if (lane == 0) tile = (long long)atomic_add(B.ticket, 1);
 		tile = (long long)((uint64_t)shfl_idx(0xffffffffu, (uint32_t)tile, 0, 32) |
 		                   (uint64_t)shfl_idx(0xffffffffu, (uint32_t)((uint64_t)tile >> 32), 0, 32) << 32);
 		if (lane == 0) h->tile = tile;
 		if (tile >= B.ntiles) return;
-		if (B.pack_jobs > 0) { // jobs tile * G .. : lane g takes job g; a job that cannot emit gets no slots
+		if (PACKED) { // jobs tile * G .. : lane g takes job g; a job that cannot emit gets no slots
 			const long long jfirst = tile * B.pack_jobs;
 			const int n = (int)(B.njobs - jfirst < (long long)B.pack_jobs ? B.njobs - jfirst : (long long)B.pack_jobs);
 			SketchJob J;
@@ -649,6 +647,7 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 	auto copy_out = [&]() { // every thread, after a barrier behind lookback_finish
 		const long long excl = sm->excl;
 		const ulonglong2 *st = (const ulonglong2 *)sm->park;
+#pragma unroll 1
 		for (int r = tid; r < pend_total; r += THREADS)
 			if (excl + r < B.out_cap) {
 				const ulonglong2 v = st[r];
@@ -658,13 +657,13 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 	sync_block();
 	int cur = 0;
 	for (;;) {
-		if (B.pack_jobs > 0 && THREADS > 32) sync_block(); // the job table of the previous tile is still being read by the other warps
+		if (PACKED && THREADS > 32) sync_block(); // the job table of the previous tile is still being read by the other warps
 		if (wid == 0) make_header(&sm->hdr[cur]); // right behind warp 0's share of the previous tile's records
 		sync_block(); // header of this tile; the previous tile's parked records
 		const typename SketchSmem3<THREADS>::Hdr *const h = &sm->hdr[cur];
 		const long long tile = h->tile;
 		if (tile >= B.ntiles) break;
-		const bool packed = B.pack_jobs > 0; // several whole jobs per tile: slot 0 is the first position of the first job (no halo)
+		const bool packed = PACKED; // several whole jobs per tile: slot 0 is the first position of the first job (no halo)
 		const int job = h->job, dl = h->dl, i0 = h->i0, B0 = packed ? 0 : i0 - HL;
 		const uint32_t shift = h->shift;
 		const char *seq = B.buf + h->seq_off;
@@ -888,7 +887,6 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 					for (int p = 7; p >= 0; --p) sx = sk_max64(sx, M[p]), sufm[p] = sx;
 				}
 				sync_block();
-				if (B.early_ticket && tid == 0) tk = atomic_add(B.ticket, 1); // its latency hides behind the emission phase
 				// whole chunks between the thread's own and the last window's last chunk: tid+1 .. tid+dt-1, dt = E or E + 1
 				const int E = wm1 >> 3;
 				uint64_t mxA = 0, mxB = 0;
@@ -1012,7 +1010,7 @@ GD_DEV void sketch_tile_body3(const SketchParams &S, const SketchBatch &B, Sketc
 					uint64_t *dst;
 					bool ok = true;
 					uint32_t jj = (uint32_t)(j0 + p), sh = shift, rid = h->rid; // j0 + p >= 0: a k-mer
-					if (mode == 1) {
+					if (PACKED) {
 						const int sl = s0 + p;
 #pragma unroll 1
 						while (sl >= sm->pk_end[g]) ++g; // a record's slot lies inside a job

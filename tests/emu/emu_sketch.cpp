@@ -16,9 +16,12 @@ static void run_tiles(const SketchParams &S, SketchBatch &B, int grid)
 	if (g_ver == 2)
 		emu::launch(grid, THREADS, sizeof(SketchSmem<THREADS>),
 		            [&]() { sketch_tile_body<THREADS>(S, B, (SketchSmem<THREADS> *)emu::smem()); });
+	else if (B.pack_jobs > 0)
+		emu::launch(grid, THREADS, sizeof(SketchSmem3<THREADS>),
+		            [&]() { sketch_tile_body3<THREADS, true>(S, B, (SketchSmem3<THREADS> *)emu::smem()); });
 	else
 		emu::launch(grid, THREADS, sizeof(SketchSmem3<THREADS>),
-		            [&]() { sketch_tile_body3<THREADS>(S, B, (SketchSmem3<THREADS> *)emu::smem()); });
+		            [&]() { sketch_tile_body3<THREADS, false>(S, B, (SketchSmem3<THREADS> *)emu::smem()); });
 }
 
 // jobs: n x {seq_off, len, shift, rid}; small != 0 forces the one-tile-per-job configuration
@@ -62,7 +65,7 @@ extern "C" long emu_sketch_jobs(int njobs, const int64_t *seq_off, const int32_t
 // fixed-stride output with `pack` whole jobs per tile of `threads` threads (the short-read configuration of gd_sketch_run_jobs);
 // job j's records land at out[j * stride ..], its count in out_cnt[j].  pack = 0: one job per one-warp tile.
 extern "C" int emu_sketch_packed(int njobs, const int64_t *seq_off, const int32_t *len, const int32_t *shift, const uint32_t *rid,
-                                 const char *buf, int w, int k, const char *Z, int W, int pack, int threads, int early, int grid,
+                                 const char *buf, int w, int k, const char *Z, int W, int pack, int threads, int grid,
                                  int64_t stride, int32_t *out_cnt, uint64_t *out)
 {
 	SketchParams S;
@@ -89,7 +92,7 @@ extern "C" int emu_sketch_packed(int njobs, const int64_t *seq_off, const int32_
 	memset(&B, 0, sizeof(B));
 	B.njobs = njobs, B.ntiles = pack > 0 ? (njobs + pack - 1) / pack : njobs, B.jobs = jobs.data(), B.buf = buf;
 	B.status = status.data(), B.ticket = &ticket, B.out_off = oo.data(), B.out = out, B.out_cap = (int64_t)njobs * stride;
-	B.fixed_stride = stride, B.out_cnt = out_cnt, B.pack_jobs = pack, B.early_ticket = early;
+	B.fixed_stride = stride, B.out_cnt = out_cnt, B.pack_jobs = pack;
 	if (threads == 32) run_tiles<32>(S, B, grid);
 	else if (threads == 64) run_tiles<64>(S, B, grid);
 	else if (threads == 128) run_tiles<128>(S, B, grid);

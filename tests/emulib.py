@@ -40,12 +40,12 @@ class Emu:
         L.emu_sketch_jobs.argtypes = [C.c_int, i64p, i32p, i32p, u32p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int,
                                       C.c_int, C.c_int, i64p, u64p, C.c_int64]
 
-    def sketch_packed(self, seqs, shifts, rids, w, k, Z, pack, threads, early=1, grid=3):
+    def sketch_packed(self, seqs, shifts, rids, w, k, Z, pack, threads, grid=3):
         """fixed-stride output, `pack` whole jobs per tile (0: one job per one-warp tile); returns the list of every job"""
         L = self.lib
         L.emu_sketch_packed.restype = C.c_int
         L.emu_sketch_packed.argtypes = [C.c_int, i64p, i32p, i32p, u32p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int,
-                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, i32p, u64p]
+                                        C.c_int, C.c_int, C.c_int, C.c_int64, i32p, u64p]
         buf = b"".join(seqs)
         lens = np.array([len(s) for s in seqs], np.int32)
         off = np.zeros(len(seqs), np.int64)
@@ -54,7 +54,7 @@ class Emu:
         out = np.zeros(2 * stride * len(seqs), np.uint64)
         cnt = np.full(len(seqs), -1, np.int32)
         rc = L.emu_sketch_packed(len(seqs), off, lens, np.array(shifts, np.int32), np.array(rids, np.uint32), buf, w, k, Z.encode(),
-                                 len(Z), pack, threads, early, grid, stride, cnt, out)
+                                 len(Z), pack, threads, grid, stride, cnt, out)
         assert rc == 0, rc
         return [out[2 * stride * i:2 * (stride * i + cnt[i])].reshape(-1, 2) for i in range(len(seqs))]
 

@@ -218,11 +218,10 @@ def test_emu_sketch_packed_tiles(emu, oracle):
                 c[a:a + int(rng.integers(1, 6))] = 4
             seqs.append(bytes(synth.ACGTN[c]))
             shifts.append(int(rng.integers(0, W)))
-        for early in (0, 1):
-            got = emu.sketch_packed(seqs, shifts, list(range(len(seqs))), w, k, Z, pack, threads, early)
-            for i, (sq, sh) in enumerate(zip(seqs, shifts)):
-                exp, _ = oracle.mm_sketch3(sq, w, k, i, Z, sh, 0)
-                assert np.array_equal(exp, got[i]), (k, w, Z, pack, threads, early, i)
+        got = emu.sketch_packed(seqs, shifts, list(range(len(seqs))), w, k, Z, pack, threads)
+        for i, (sq, sh) in enumerate(zip(seqs, shifts)):
+            exp, _ = oracle.mm_sketch3(sq, w, k, i, Z, sh, 0)
+            assert np.array_equal(exp, got[i]), (k, w, Z, pack, threads, i)
     # one job per tile through the same entry (tickets in fixed-stride mode)
     got = emu.sketch_packed(seqs, shifts, list(range(len(seqs))), w, k, Z, 0, 32)
     for i, (sq, sh) in enumerate(zip(seqs, shifts)):

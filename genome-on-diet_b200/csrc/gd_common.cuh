@@ -130,6 +130,7 @@ GD_DEV int block_dim() { return emu::block_dim(); }
 GD_DEV int grid_dim() { return emu::grid_dim(); }
 GD_DEV int atomic_add(int *p, int v)
 {
+	emu::yield(); // a scheduling point: other threads / blocks may draw first
 	int o = *p;
 	*p = o + v;
 	return o;

@@ -10,17 +10,26 @@ using namespace gd;
 static int g_ver = 3; // tile body: 3 = sketch_tile_body3 (the product default), 2 = sketch_tile_body
 extern "C" void emu_sketch_version(int v) { g_ver = v; }
 
+static unsigned g_conc = 0; // != 0: all blocks resident, scheduled in a pseudo-random interleaving seeded with this value
+extern "C" void emu_sketch_concurrency(unsigned seed) { g_conc = seed; }
+
+static void launch_tiles(int grid, int threads, size_t smem, std::function<void()> body)
+{
+	if (g_conc) emu::launch_concurrent(grid, threads, smem, body, g_conc);
+	else emu::launch(grid, threads, smem, body);
+}
+
 template <int THREADS>
 static void run_tiles(const SketchParams &S, SketchBatch &B, int grid)
 {
 	if (g_ver == 2)
-		emu::launch(grid, THREADS, sizeof(SketchSmem<THREADS>),
+		launch_tiles(grid, THREADS, sizeof(SketchSmem<THREADS>),
 		            [&]() { sketch_tile_body<THREADS>(S, B, (SketchSmem<THREADS> *)emu::smem()); });
 	else if (B.pack_jobs > 0)
-		emu::launch(grid, THREADS, sizeof(SketchSmem3<THREADS>),
+		launch_tiles(grid, THREADS, sizeof(SketchSmem3<THREADS>),
 		            [&]() { sketch_tile_body3<THREADS, true>(S, B, (SketchSmem3<THREADS> *)emu::smem()); });
 	else
-		emu::launch(grid, THREADS, sizeof(SketchSmem3<THREADS>),
+		launch_tiles(grid, THREADS, sizeof(SketchSmem3<THREADS>),
 		            [&]() { sketch_tile_body3<THREADS, false>(S, B, (SketchSmem3<THREADS> *)emu::smem()); });
 }
 

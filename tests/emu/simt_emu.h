@@ -52,6 +52,7 @@ inline long &rowmax_mismatches()
 inline void yield()
 {
 	BlockState *b = cur_block();
+	if (!b) return; // device code run as a plain host loop (no fibers): nothing to switch to
 	swapcontext(&b->th[b->cur].ctx, &b->sched);
 }
 
@@ -187,6 +188,60 @@ inline void launch(int grid, int block, size_t smem_bytes, std::function<void()>
 		free(b.smem);
 		cur_block() = 0;
 	}
+}
+
+// The same, with all blocks of the grid resident at once: the scheduler visits the blocks in a pseudo-random order and lets
+// each one run one to three sweeps (every live thread once, up to its next barrier / collective / volatile load) per visit.
+// For protocols BETWEEN blocks -- ordering tickets, decoupled look-back, deferred copy-out -- under many interleavings.
+inline void launch_concurrent(int grid, int block, size_t smem_bytes, std::function<void()> body, unsigned seed)
+{
+	const size_t STK = 256 * 1024;
+	std::vector<BlockState> bs(grid);
+	for (int bid = 0; bid < grid; ++bid) {
+		BlockState &b = bs[bid];
+		b.bid = bid, b.nthreads = block, b.grid = grid, b.body = body, b.cur = 0;
+		size_t nb = (smem_bytes + 255) / 128 * 128;
+		b.smem = (char *)aligned_alloc(128, nb);
+		memset(b.smem, 0xCD, nb);
+		b.th.resize(block);
+		cur_block() = &b;
+		for (int t = 0; t < block; ++t) {
+			Fiber &f = b.th[t];
+			f.done = false, f.wepoch = f.bepoch = 0, f.xchg = 0;
+			f.stack = (char *)malloc(STK);
+			getcontext(&f.ctx);
+			f.ctx.uc_stack.ss_sp = f.stack, f.ctx.uc_stack.ss_size = STK, f.ctx.uc_link = &b.sched;
+			makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+		}
+	}
+	unsigned long long rng = 0x9e3779b97f4a7c15ull ^ seed;
+	auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (unsigned)(rng >> 33); };
+	std::vector<int> order(grid);
+	for (int i = 0; i < grid; ++i) order[i] = i;
+	for (;;) {
+		bool any = false;
+		for (int i = grid - 1; i > 0; --i) { // shuffle
+			int j = (int)(next() % (unsigned)(i + 1)), t = order[i];
+			order[i] = order[j], order[j] = t;
+		}
+		for (int oi = 0; oi < grid; ++oi) {
+			BlockState &b = bs[order[oi]];
+			cur_block() = &b;
+			for (int sweeps = 1 + (int)(next() % 3u); sweeps > 0; --sweeps)
+				for (int t = 0; t < block; ++t) {
+					if (b.th[t].done) continue;
+					any = true;
+					b.cur = t;
+					swapcontext(&b.sched, &b.th[t].ctx);
+				}
+		}
+		if (!any) break;
+	}
+	for (int bid = 0; bid < grid; ++bid) {
+		for (int t = 0; t < block; ++t) free(bs[bid].th[t].stack);
+		free(bs[bid].smem);
+	}
+	cur_block() = 0;
 }
 
 } // namespace emu

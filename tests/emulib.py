@@ -40,6 +40,11 @@ class Emu:
         L.emu_sketch_jobs.argtypes = [C.c_int, i64p, i32p, i32p, u32p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int,
                                       C.c_int, C.c_int, i64p, u64p, C.c_int64]
 
+    def sketch_concurrency(self, seed):
+        """seed != 0: the sketch tiles run with all blocks resident, interleaved pseudo-randomly (simt_emu.h: launch_concurrent)"""
+        self.lib.emu_sketch_concurrency.argtypes = [C.c_uint]
+        self.lib.emu_sketch_concurrency(seed)
+
     def sketch_packed(self, seqs, shifts, rids, w, k, Z, pack, threads, grid=3):
         """fixed-stride output, `pack` whole jobs per tile (0: one job per one-warp tile); returns the list of every job"""
         L = self.lib

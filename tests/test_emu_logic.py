@@ -227,3 +227,40 @@ def test_emu_sketch_packed_tiles(emu, oracle):
     for i, (sq, sh) in enumerate(zip(seqs, shifts)):
         exp, _ = oracle.mm_sketch3(sq, w, k, i, Z, sh, 0)
         assert np.array_equal(exp, got[i]), i
+
+
+def test_emu_sketch_concurrent_blocks(emu, oracle):
+    """The protocol BETWEEN blocks of the dense sketch kernel -- ordering tickets, a tile's count published before its
+    offset is known, records parked in shared memory, look-back and copy-out inside the block's next tile -- with all
+    blocks resident and scheduled in pseudo-random interleavings: the output must be the reference's, in order, whatever
+    the interleaving (and no interleaving may dead-lock).  Also the one-warp dense tiles, the packed tiles and the v2 body."""
+    rng = np.random.default_rng(5)
+    seqs = [bytes(synth.ACGTN[rng.integers(0, 4, n)]) for n in (30000, 9000, 40, 17000, 4200)]
+    exp = {}
+    try:
+        for it, (k, w, Z, grid) in enumerate([(21, 11, "10", 4), (15, 10, "10", 6), (19, 19, "110", 3), (12, 3, "1", 5)]):
+            shifts = [int(rng.integers(0, len(Z))) for _ in seqs]
+            want = [oracle.mm_sketch3(s, w, k, i, Z, sh, 0)[0] for i, (s, sh) in enumerate(zip(seqs, shifts))]
+            for seed in (1, 2, 3):
+                emu.sketch_concurrency(1000 * it + seed)
+                got = emu.sketch_jobs(seqs, shifts, list(range(len(seqs))), w, k, Z, 0, grid=grid)
+                for i in range(len(seqs)):
+                    assert np.array_equal(want[i], got[i]), (k, w, Z, grid, seed, i)
+        # one-warp tiles with dense output (look-back over one-tile jobs), packed tiles, and the previous body
+        short = [bytes(synth.ACGTN[rng.integers(0, 4, int(n))]) for n in rng.integers(30, 300, 24)]
+        sh = [int(rng.integers(0, 2)) for _ in short]
+        want = [oracle.mm_sketch3(s, 11, 21, i, "10", x, 0)[0] for i, (s, x) in enumerate(zip(short, sh))]
+        for seed in (7, 8):
+            emu.sketch_concurrency(seed)
+            got = emu.sketch_jobs(short, sh, list(range(len(short))), 11, 21, "10", 1, grid=5)
+            assert all(np.array_equal(a, b) for a, b in zip(want, got)), seed
+            got = emu.sketch_packed(short, sh, list(range(len(short))), 11, 21, "10", 3, 64, grid=4)
+            assert all(np.array_equal(a, b) for a, b in zip(want, got)), seed
+        emu.lib.emu_sketch_version(2)
+        emu.sketch_concurrency(11)
+        got = emu.sketch_jobs(seqs[:3], [0, 1, 0], [0, 1, 2], 11, 21, "10", 0, grid=3)
+        for i in range(3):
+            assert np.array_equal(oracle.mm_sketch3(seqs[i], 11, 21, i, "10", [0, 1, 0][i], 0)[0], got[i])
+    finally:
+        emu.lib.emu_sketch_version(3)
+        emu.sketch_concurrency(0)

@@ -426,8 +426,11 @@ GD_DEV void sketch_tile_body(const SketchParams &S, const SketchBatch &B, Sketch
 // =============================================================================================
 // Tile body, design v3 (round 2): the same tiles, phases and output order as sketch_tile_body above -- about a third of
 // its instructions.  What changed, phase by phase (SASS counts of the 256-thread kernel in DESIGN.md 4):
-//   * tile header (ticket, tile -> job search, sparsified length, staged byte range) is computed by ONE thread and
-//     broadcast through shared memory;
+//   * tile header (ticket, tile -> job by a cached job or a 32-ary search, sparsified length from the job record, staged
+//     byte range) is made by warp 0 alone, right behind its share of the previous tile, and broadcast through shared memory;
+//   * dense output: a tile publishes its count and parks its records in shared memory; the decoupled look-back and the
+//     coalesced copy-out run inside the block's next tile, so no barrier waits for a spinning warp;
+//   * short reads: PACKED tiles hold several whole jobs, one N slot between them, each with its own fixed-stride output;
 //   * encode: one shared-memory table look-up per base (code | N flag << 16), accumulated with a shift-add; the pattern
 //     walk has a stride-W form for patterns with a single '1' ("10", "100"); threads whose 8 positions lie inside the
 //     sequence skip the range tests;

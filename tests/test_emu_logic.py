@@ -2,6 +2,8 @@
 reproduce the oracle.  This checks lane ownership, the shared-memory ring, carries between steps, the
 tag-carrying packed arithmetic, the exact-max reduction and the look-back compaction without a GPU.
 (The GPU parity tests in test_gpu_*.py remain the authority for the real hardware path.)"""
+import os
+
 import numpy as np
 import pytest
 
@@ -264,3 +266,38 @@ def test_emu_sketch_concurrent_blocks(emu, oracle):
     finally:
         emu.lib.emu_sketch_version(3)
         emu.sketch_concurrency(0)
+
+
+def _asan_run(tmp_path, driver, kernel_src, timeout):
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "asan_driver")
+    csrc = os.path.join(os.path.dirname(here), "genome-on-diet_b200", "csrc")
+    cmd = ["g++", "-O1", "-fsanitize=address", "-fno-omit-frame-pointer", "-std=c++17", "-I", os.path.join(here, "emu"), "-I", csrc,
+           os.path.join(here, "emu", driver), os.path.join(here, "emu", kernel_src), "-o", exe]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    if b.returncode != 0 and "sanitize" in b.stderr:
+        pytest.skip("this g++ has no AddressSanitizer runtime")
+    assert b.returncode == 0, b.stderr[-2000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect_leaks=0")
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=timeout)
+    assert r.returncode == 0 and "ERROR: AddressSanitizer" not in r.stderr, (r.stdout[-1000:], r.stderr[-3000:])
+    return r.stdout
+
+
+def test_emu_sketch_address_sanitizer(tmp_path):
+    """The sketch kernels' device code under AddressSanitizer (exact-size heap buffers for the sequences, outputs, job and
+    status arrays and the blocks' shared memory): dense, one-warp and packed tiles over random geometries, sequential and
+    interleaved blocks.  Out-of-bounds shared-memory reads do not fault on a GPU; here they abort."""
+    out = _asan_run(tmp_path, "asan_sketch_driver.cpp", "emu_sketch.cpp", 600)
+    assert out.count("packed T") >= 12
+
+
+def test_emu_ksw_address_sanitizer(tmp_path):
+    """The DP, traceback and lead-in kernels' device code under AddressSanitizer: random pairs (1..420 bases), bands 0..460,
+    ten flag sets, every gang size from 4 lanes to a 128-thread block per pair."""
+    out = _asan_run(tmp_path, "asan_ksw_driver.cpp", "emu_ksw.cpp", 900)
+    assert out.count(" rc 0 ") == 12

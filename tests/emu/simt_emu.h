@@ -191,7 +191,8 @@ inline void launch(int grid, int block, size_t smem_bytes, std::function<void()>
 }
 
 // The same, with all blocks of the grid resident at once: the scheduler visits the blocks in a pseudo-random order and lets
-// each one run one to three sweeps (every live thread once, up to its next barrier / collective / volatile load) per visit.
+// each one run one to three sweeps (every live thread once -- in a rotated, possibly reversed order -- up to its next barrier /
+// collective / volatile load) per visit.
 // For protocols BETWEEN blocks -- ordering tickets, decoupled look-back, deferred copy-out -- under many interleavings.
 inline void launch_concurrent(int grid, int block, size_t smem_bytes, std::function<void()> body, unsigned seed)
 {
@@ -227,13 +228,18 @@ inline void launch_concurrent(int grid, int block, size_t smem_bytes, std::funct
 		for (int oi = 0; oi < grid; ++oi) {
 			BlockState &b = bs[order[oi]];
 			cur_block() = &b;
-			for (int sweeps = 1 + (int)(next() % 3u); sweeps > 0; --sweeps)
-				for (int t = 0; t < block; ++t) {
+			for (int sweeps = 1 + (int)(next() % 3u); sweeps > 0; --sweeps) {
+				// the threads of the block in a rotated, possibly reversed order: between two barriers a thread may run before OR
+				// after any other one, so a missing barrier (a read of what another thread has yet to write, or has already
+				// overwritten) gives wrong output for some seed instead of passing by the accident of index order
+				const int start = (int)(next() % (unsigned)block), dir = next() & 1u ? 1 : block - 1;
+				for (int i = 0, t = start; i < block; ++i, t = (t + dir) % block) {
 					if (b.th[t].done) continue;
 					any = true;
 					b.cur = t;
 					swapcontext(&b.sched, &b.th[t].ctx);
 				}
+			}
 		}
 		if (!any) break;
 	}

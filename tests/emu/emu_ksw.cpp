@@ -100,3 +100,6 @@ extern "C" int emu_ksw_batch(int n, const int32_t *qlen, const int64_t *qoff, co
 	if (emu::rowmax_mismatches()) return -2; // fast row maximum disagreed with the literal scan
 	return 0;
 }
+
+// != 0: every later launch of this library keeps all blocks resident and runs blocks and threads in pseudo-random orders
+extern "C" void emu_set_shuffle(unsigned seed) { emu::shuffle_seed() = seed; }

@@ -43,6 +43,12 @@ inline BlockState *&cur_block()
 	return b;
 }
 
+inline unsigned &shuffle_seed()
+{ // != 0: launch() keeps all blocks resident and schedules blocks and threads in pseudo-random orders (launch_concurrent)
+	static unsigned s = 0;
+	return s;
+}
+
 inline long &rowmax_mismatches()
 { // self-check counter of the DP kernel's exact-max fast path (see gd_ksw.cuh)
 	static long n = 0;
@@ -153,8 +159,13 @@ inline void fiber_entry()
 }
 
 // Run `body` once per thread for every block of the grid (blocks run one after another, in order).
+inline void launch_concurrent(int grid, int block, size_t smem_bytes, std::function<void()> body, unsigned seed);
 inline void launch(int grid, int block, size_t smem_bytes, std::function<void()> body)
 {
+	if (shuffle_seed()) {
+		launch_concurrent(grid, block, smem_bytes, body, shuffle_seed());
+		return;
+	}
 	const size_t STK = 256 * 1024;
 	for (int bid = 0; bid < grid; ++bid) {
 		BlockState b;

@@ -2,6 +2,7 @@
 reproduce the oracle.  This checks lane ownership, the shared-memory ring, carries between steps, the
 tag-carrying packed arithmetic, the exact-max reduction and the look-back compaction without a GPU.
 (The GPU parity tests in test_gpu_*.py remain the authority for the real hardware path.)"""
+import ctypes as C
 import os
 
 import numpy as np
@@ -266,6 +267,21 @@ def test_emu_sketch_concurrent_blocks(emu, oracle):
     finally:
         emu.lib.emu_sketch_version(3)
         emu.sketch_concurrency(0)
+
+
+def test_emu_ksw_shuffled_schedules(emu, oracle):
+    """The DP kernel with blocks AND the threads inside a block scheduled in pseudo-random orders between barriers / warp
+    collectives (simt_emu.h: launch_concurrent): a missing __syncwarp / __syncthreads around the shared-memory ring would give
+    a wrong result for some order.  Warp gangs of 4 / 8 / 32 lanes and the block-per-pair gangs."""
+    emu.lib.emu_set_shuffle.argtypes = [C.c_uint]
+    try:
+        for seed, (G, flag, mx) in enumerate([(4, 0x00, 160), (4, 0x08, 160), (8, 0x40, 200), (32, 0x00, 260), (64, 0x08, 420), (128, 0x00, 420)]):
+            emu.lib.emu_set_shuffle(101 + seed)
+            P = synth.ragged_pairs(6, seed=40 + seed, max_len=mx)
+            w = np.minimum(np.maximum(P["qlen"], P["tlen"]), 150).astype(np.int32)
+            _check(emu, oracle, P, w, "sr", flag, G)
+    finally:
+        emu.lib.emu_set_shuffle(0)
 
 
 def _asan_run(tmp_path, driver, kernel_src, timeout):

@@ -21,7 +21,7 @@ int main()
 	const int gangs[] = {4, 8, 16, 32, 64, 128};
 	int8_t mat[25];
 	for (int i = 0; i < 25; ++i) mat[i] = (i / 5 == 4 || i % 5 == 4) ? 0 : (i / 5 == i % 5 ? 2 : -8);
-	for (int it = 0; it < 12; ++it) {
+	for (int it = 0; it < 10; ++it) {
 		const int flag = flags[it % 10], G = gangs[it % 6], n = 5;
 		const int maxlen = G >= 64 ? 420 : G >= 16 ? 300 : 200;
 		std::vector<int32_t> ql(n), tl(n), w(n);

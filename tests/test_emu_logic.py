@@ -244,7 +244,7 @@ def test_emu_sketch_concurrent_blocks(emu, oracle):
         for it, (k, w, Z, grid) in enumerate([(21, 11, "10", 4), (15, 10, "10", 6), (19, 19, "110", 3), (12, 3, "1", 5)]):
             shifts = [int(rng.integers(0, len(Z))) for _ in seqs]
             want = [oracle.mm_sketch3(s, w, k, i, Z, sh, 0)[0] for i, (s, sh) in enumerate(zip(seqs, shifts))]
-            for seed in (1, 2, 3):
+            for seed in (1, 2):
                 emu.sketch_concurrency(1000 * it + seed)
                 got = emu.sketch_jobs(seqs, shifts, list(range(len(seqs))), w, k, Z, 0, grid=grid)
                 for i in range(len(seqs)):
@@ -316,4 +316,4 @@ def test_emu_ksw_address_sanitizer(tmp_path):
     """The DP, traceback and lead-in kernels' device code under AddressSanitizer: random pairs (1..420 bases), bands 0..460,
     ten flag sets, every gang size from 4 lanes to a 128-thread block per pair."""
     out = _asan_run(tmp_path, "asan_ksw_driver.cpp", "emu_ksw.cpp", 900)
-    assert out.count(" rc 0 ") == 12
+    assert out.count(" rc 0 ") == 10
